@@ -1,0 +1,119 @@
+/*
+ * oracle.h — C API of the CPU oracle (TEST INFRASTRUCTURE, NOT PRODUCT).
+ *
+ * The oracle is a dependency-free, single-threaded C++ restatement of the
+ * reference's CPU algorithm for the BA + ORB hot path of VIS4ROB-lab/ccm_slam
+ * (vendored g2o + cslam Optimizer/ORBextractor/ORBmatcher).  Only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * load it.  The product library (libccm_b200.so) never links or calls it.
+ *
+ * PARITY PINNING: the reference ships no tests or golden vectors for this path and
+ * cannot be compiled in this environment (no Eigen / OpenCV C++ / Boost / ROS), so
+ * the oracle is pinned by independent witnesses instead: scipy (sparse solve,
+ * finite differences, Rotation) for the BA/PGO part and Python cv2 4.13 for the
+ * ORB primitives (tests/test_oracle_*.py, fixtures under tests/golden/).
+ * "parity unpinned by the reference's own tests" — see DESIGN.md §3.
+ *
+ * Citations: G/ = cslam/thirdparty/g2o/g2o/, S/ = cslam/src/ under /root/reference.
+ */
+#ifndef CCM_ORACLE_H
+#define CCM_ORACLE_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- flat BA problem (same field meaning as include/ccm_b200.h) ---- */
+typedef struct {
+  int32_t K, P, E;
+  const double* poses;       /* K*7: qx qy qz qw tx ty tz  (g2o::SE3Quat, Tcw) */
+  const double* intr;        /* K*4: fx fy cx cy */
+  const uint8_t* fixed;      /* K: 1 = vertex fixed */
+  const double* points;      /* P*3 world xyz */
+  const int32_t* obs_kf;     /* E: pose index */
+  const int32_t* obs_mp;     /* E: point index */
+  const float* obs_uv;       /* E*2: undistorted pixel */
+  const float* obs_w;        /* E: invSigma2 of the keypoint octave */
+  const uint8_t* edge_flags; /* E or NULL: bit0 = level 1 (inactive), bit1 = no robust kernel */
+} orc_ba_problem;
+
+typedef struct {
+  int32_t iterations;        /* optimize(n) */
+  int32_t robust;            /* 1 = Huber on every edge without bit1 */
+  double huber_delta;        /* sqrt(5.99) GBA, sqrt(5.991) LocalBA */
+  double lambda_init;        /* <=0: tau * max diag(H), tau = 1e-5 */
+  int32_t max_trials;        /* 10 */
+  const volatile uint8_t* stop; /* force-stop flag, may be NULL */
+} orc_ba_options;
+
+#define ORC_TRACE_COLS 6 /* iter, lambda_used_last_trial, chi2_after, rho, trials, lambda_after */
+
+typedef struct {
+  double* poses;             /* K*7 out */
+  double* points;            /* P*3 out */
+  double* chi2;              /* E out: plain e'We at the last evaluated state; inactive edges untouched */
+  uint8_t* depth_pos;        /* E out: z>0 at the final estimate (all edges) */
+  double* trace;             /* trace_cap*ORC_TRACE_COLS or NULL */
+  int32_t trace_cap;
+  int32_t trace_len;
+  int32_t iters_done;        /* return value of SparseOptimizer::optimize */
+  int32_t trials_total;
+  double chi2_initial, chi2_final, lambda_final;
+  double t_build_s, t_schur_s, t_solve_s, t_resid_s, t_total_s, t_structure_s;
+} orc_ba_result;
+
+int orc_ba_solve(const orc_ba_problem* p, const orc_ba_options* o, orc_ba_result* r);
+
+/* pieces, for kernel-level parity tests */
+/* per-edge: err[2E], Jpose[12E] (2x6 row-major), Jpoint[6E] (2x3 row-major), rho1[E], chi2[E]; returns robust chi2 sum */
+double orc_ba_linearize(const orc_ba_problem* p, int robust, double huber_delta,
+                        double* err, double* Jpose, double* Jpoint, double* rho1, double* chi2);
+/* dense block outputs in pose/point index space (fixed poses get zero blocks):
+ * Hpp[K*36] row-major 6x6, bp[K*6], Hll[P*9], bl[P*3], W[E*18] (6x3 row-major, pose-rows x point-cols) */
+void orc_ba_build(const orc_ba_problem* p, int robust, double huber_delta,
+                  double* Hpp, double* bp, double* Hll, double* bl, double* W);
+/* one damped Schur solve at the current linearisation: dx_pose[K*6] (zero for fixed), dx_point[P*3];
+ * also returns dense reduced system if S_dense (6K x 6K row-major) / bschur (6K) non-NULL. returns 0 on success */
+int orc_ba_schur_solve(const orc_ba_problem* p, int robust, double huber_delta, double lambda,
+                       double* dx_pose, double* dx_point, double* S_dense, double* bschur);
+
+void orc_se3_exp(const double upd[6], double out_qt[7]);                /* G/types/se3quat.h:223-257 */
+void orc_se3_mul(const double a[7], const double b[7], double out[7]);  /* G/types/se3quat.h:105-118 */
+void orc_se3_map(const double qt[7], const double x[3], double out[3]); /* G/types/se3quat.h:217-220 */
+void orc_pose_from_Tcw_f32(const float T[16], double out_qt[7]);        /* S/Converter.cc:40-51 */
+void orc_pose_to_Tcw_f32(const double qt[7], float T[16]);              /* S/Converter.cc:53-72 */
+void orc_huber(double e, double delta, double rho[3]);                  /* G/core/robust_kernel_impl.cpp:77-91 */
+
+/* ---- Sim3 pose graph (essential graph) ---- */
+typedef struct {
+  int32_t K, E;
+  const double* sim3;        /* K*8: qx qy qz qw tx ty tz s */
+  const uint8_t* fixed;      /* K */
+  const int32_t* edge_i;     /* E: vertex 0 */
+  const int32_t* edge_j;     /* E: vertex 1 */
+  const double* meas;        /* E*8: Sji measurement */
+  int32_t fix_scale;
+} orc_pgo_problem;
+
+typedef struct {
+  double* sim3;              /* K*8 out */
+  double* trace; int32_t trace_cap; int32_t trace_len;
+  int32_t iters_done;
+  double chi2_initial, chi2_final, lambda_final;
+  double t_total_s;
+} orc_pgo_result;
+
+/* analytic_jac: 0 = numeric central differences delta=1e-9 as the reference (G/core/base_binary_edge.hpp:131-205) */
+int orc_pgo_solve(const orc_pgo_problem* p, int32_t iterations, double lambda_init, int32_t analytic_jac,
+                  const volatile uint8_t* stop, orc_pgo_result* r);
+void orc_sim3_exp(const double upd[7], double out[8]);                 /* G/types/sim3.h:70-142 */
+void orc_sim3_log(const double s[8], double out[7]);                   /* G/types/sim3.h:148-230 */
+void orc_sim3_mul(const double a[8], const double b[8], double out[8]);/* G/types/sim3.h:266-272 */
+void orc_sim3_inv(const double a[8], double out[8]);                   /* G/types/sim3.h:233-236 */
+void orc_pgo_edge_error(const double meas[8], const double si[8], const double sj[8], double err[7]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,149 @@
+"""Pins the BA part of the CPU oracle against independent witnesses (scipy / dense numpy LM / finite differences).
+
+The reference (g2o + cslam::Optimizer) ships no tests and cannot be compiled here; these are the known-answer
+checks that stand in for them."""
+import numpy as np
+import pytest
+from scipy.spatial.transform import Rotation
+
+from ccm_slam_b200 import synth
+from tests import witness as W
+
+
+def test_se3_exp_matches_scipy_and_keeps_small_angle_quirk(oracle):
+    rng = np.random.default_rng(0)
+    for _ in range(50):
+        u = np.concatenate([rng.normal(size=3) * rng.choice([1e-3, 0.1, 1.0]), rng.normal(size=3)])
+        qt = oracle.se3_exp(u)
+        R, t = W.se3_exp(u)
+        assert np.allclose(Rotation.from_quat(qt[:4]).as_matrix(), R, atol=1e-13)
+        assert np.allclose(qt[4:], t, atol=1e-13)
+        assert qt[3] >= 0 and abs(np.linalg.norm(qt[:4]) - 1) < 1e-15
+    # theta < 1e-5: R = I + W + W^2 (NOT 1/2 W^2) and V = R  (G/types/se3quat.h:237-243)
+    u = np.array([3e-6, -2e-6, 1e-6, 0.3, -0.2, 0.1])
+    qt = oracle.se3_exp(u)
+    Wm = W.skew(u[:3]); Rq = np.eye(3) + Wm + Wm @ Wm
+    assert np.allclose(qt[4:], Rq @ u[3:], atol=1e-15)
+
+
+def test_pose_conversion_roundtrip_and_branches(oracle):
+    rng = np.random.default_rng(1)
+    for i in range(200):
+        rv = rng.normal(size=3)
+        rv *= (np.pi * rng.uniform(0.0, 1.0)) / np.linalg.norm(rv)  # includes trace<=0 branches
+        R = Rotation.from_rotvec(rv).as_matrix()
+        T = np.eye(4, dtype=np.float32); T[:3, :3] = R; T[:3, 3] = rng.normal(size=3)
+        qt = oracle.pose_from_Tcw_f32(T)
+        assert qt[3] >= 0
+        R64 = T[:3, :3].astype(np.float64)
+        Rq = Rotation.from_quat(qt[:4]).as_matrix()
+        assert np.allclose(Rq, R64, atol=2e-7)  # f32 input is only orthonormal to ~1e-7
+        T2 = oracle.pose_to_Tcw_f32(qt)
+        assert np.allclose(T2, T, atol=3e-7)
+
+
+def test_huber_known_answers(oracle):
+    d = float(np.float32(np.sqrt(5.99)))   # `const float thHuber2D = sqrt(5.99)` (S/Optimizer.cpp:712)
+    assert np.allclose(oracle.huber(d * d, d), [d * d, 1, 0])          # e == delta^2 is an inlier (<=)
+    assert oracle.huber(d * d * (1 + 1e-9), d)[1] < 1.0
+    r = oracle.huber(100.0, d)
+    assert np.allclose(r, [2 * 10 * d - d * d, d / 10, -0.5 * (d / 10) / 100])
+
+
+@pytest.mark.parametrize("name", ["tiny", "small"])
+def test_jacobians_vs_chain_rule_and_finite_differences(oracle, name):
+    p = synth.make_config(name)
+    lin = oracle.ba_linearize(p)
+    rng = np.random.default_rng(2)
+    for e in rng.choice(p.E, size=min(p.E, 40), replace=False):
+        k, j = p.obs_kf[e], p.obs_mp[e]
+        R, t = W.qt_to_Rt(p.poses[k])
+        r, Xc = W.residual(R, t, p.points[j], p.obs_uv[e].astype(float), p.intr[k])
+        Jp, Jl = W.jacobians(R, Xc, p.intr[k])
+        assert np.allclose(lin["err"][e], r, rtol=1e-11, atol=1e-10)
+        assert np.allclose(lin["Jpose"][e], Jp, rtol=1e-10, atol=1e-9)
+        assert np.allclose(lin["Jpoint"][e], Jl, rtol=1e-10, atol=1e-9)
+        # finite differences through the oracle's own oplus (exp(d) * T)
+        h = 1e-6
+        for d in range(6):
+            up = np.zeros(6); up[d] = h
+            qp = oracle.se3_mul(oracle.se3_exp(up), p.poses[k]); qm = oracle.se3_mul(oracle.se3_exp(-up), p.poses[k])
+            rp, _ = W.residual(*W.qt_to_Rt(qp), p.points[j], p.obs_uv[e].astype(float), p.intr[k])
+            rm, _ = W.residual(*W.qt_to_Rt(qm), p.points[j], p.obs_uv[e].astype(float), p.intr[k])
+            assert np.allclose((rp - rm) / (2 * h), lin["Jpose"][e][:, d], rtol=2e-5, atol=2e-4)
+
+
+@pytest.mark.parametrize("name", ["tiny", "small"])
+def test_build_and_schur_vs_dense_full_system(oracle, name):
+    p = synth.make_config(name)
+    lm = W.DenseLM(p)
+    H, b = lm.build()
+    blk = oracle.ba_build(p)
+    npz = len(lm.free_pose)
+    for k, i in lm.pi.items():
+        assert np.allclose(blk["Hpp"][k], H[6 * i:6 * i + 6, 6 * i:6 * i + 6], rtol=1e-9, atol=1e-6)
+        assert np.allclose(blk["bp"][k], b[6 * i:6 * i + 6], rtol=1e-9, atol=1e-6)
+    for j, i in lm.li.items():
+        s = slice(6 * npz + 3 * i, 6 * npz + 3 * i + 3)
+        assert np.allclose(blk["Hll"][j], H[s, s], rtol=1e-9, atol=1e-6)
+        assert np.allclose(blk["bl"][j], b[s], rtol=1e-9, atol=1e-6)
+    lam = 1e-5 * np.abs(np.diag(H)).max()
+    x = np.linalg.solve(H + lam * np.eye(lm.n), b)
+    sol = oracle.ba_schur_solve(p, lam, dense=True)
+    assert sol["rc"] == 0
+    scale = np.abs(x).max()
+    for k, i in lm.pi.items():
+        assert np.allclose(sol["dx_pose"][k], x[6 * i:6 * i + 6], rtol=1e-6, atol=1e-8 * scale)
+    for j, i in lm.li.items():
+        assert np.allclose(sol["dx_point"][j], x[6 * npz + 3 * i:6 * npz + 3 * i + 3], rtol=1e-6, atol=1e-8 * scale)
+    # reduced system itself: S = Hpp + lam - Hpl (Hll + lam)^-1 Hlp
+    A = H + lam * np.eye(lm.n)
+    Sref = A[:6 * npz, :6 * npz] - A[:6 * npz, 6 * npz:] @ np.linalg.solve(A[6 * npz:, 6 * npz:], A[6 * npz:, :6 * npz])
+    idx = np.concatenate([np.arange(6 * k, 6 * k + 6) for k in lm.free_pose])
+    assert np.allclose(sol["S"][np.ix_(idx, idx)], Sref, rtol=1e-8, atol=1e-6 * np.abs(Sref).max())
+
+
+@pytest.mark.parametrize("name,iters", [("tiny", 12), ("small", 6)])
+def test_lm_trace_vs_dense_witness(oracle, name, iters):
+    p = synth.make_config(name)
+    lm = W.DenseLM(p)
+    tr_w = lm.optimize(iters)
+    res = oracle.ba_solve(p, iterations=iters)
+    tr_o = res["trace"]
+    assert len(tr_w) == len(tr_o)
+    assert np.allclose(tr_o[:, 1], tr_w[:, 1], rtol=1e-6)         # lambda per iteration
+    assert np.allclose(tr_o[:, 2], tr_w[:, 2], rtol=1e-7)         # robust chi2 per iteration
+    assert np.array_equal(tr_o[:, 4], tr_w[:, 4])                 # trials per iteration
+    for k in range(p.K):
+        R, t = lm.Rt[k]
+        assert np.allclose(Rotation.from_quat(res["poses"][k, :4]).as_matrix(), R, atol=1e-7)
+        assert np.allclose(res["poses"][k, 4:], t, atol=1e-6 * max(1, np.abs(t).max()))
+    assert np.allclose(res["points"], lm.X, atol=1e-6 * np.abs(lm.X).max())
+
+
+def test_local_ba_two_round_protocol_and_stale_chi2(oracle):
+    """LocalBundleAdjustmentClient: optimize(5), mark chi2>5.991 or depth<=0 as level 1 + drop kernels, optimize(10);
+    level-1 edges keep their round-1 chi2 (S/Optimizer.cpp:536-587, SURVEY §7 hard parts)."""
+    p = synth.make_config("cfg2", P=400)
+    d = np.sqrt(5.991)
+    r1 = oracle.ba_solve(p, iterations=5, huber_delta=d)
+    out = (r1["chi2"] > 5.991) | (r1["depth_pos"] == 0)
+    assert 0 < out.sum() < p.E
+    p2 = p.copy(); p2.poses = r1["poses"]; p2.points = r1["points"]
+    p2.edge_flags = (out.astype(np.uint8) | 2).astype(np.uint8)
+    r2 = oracle.ba_solve(p2, iterations=10, huber_delta=d, chi2_in=r1["chi2"])
+    assert np.array_equal(r2["chi2"][out], r1["chi2"][out])        # stale by design
+    assert not np.array_equal(r2["chi2"][~out], r1["chi2"][~out])
+    assert r2["chi2_final"] < r1["chi2_final"]
+    lm = W.DenseLM(p2, robust=True, delta=d)
+    tr = lm.optimize(10)
+    assert np.allclose(r2["trace"][:, 2], tr[:, 2], rtol=1e-7)
+
+
+def test_stop_flag_and_zero_iterations(oracle):
+    p = synth.make_config("small")
+    stop = np.ones(1, np.uint8)
+    r = oracle.ba_solve(p, iterations=20, stop=stop)
+    assert r["iters_done"] == 0 and np.array_equal(r["poses"], p.poses)
+    r = oracle.ba_solve(p, iterations=0)
+    assert r["iters_done"] == 0 and np.array_equal(r["points"], p.points)
