@@ -1,0 +1,279 @@
+"""ctypes binding of libccm_b200.so — the thin Python face of the C ABI in include/ccm_b200.h.
+
+This is host-side plumbing for tests and bench.py; the product is the shared library.  There is no CPU fallback:
+if the library is missing, or no CUDA device is present, the calls raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libccm_b200.so")
+TRACE_COLS = 8
+_lib = None
+
+
+class CCMError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libccm_b200 error {code}: {msg}")
+        self.code = code
+
+
+class BAProblemC(C.Structure):
+    _fields_ = [("K", C.c_int32), ("P", C.c_int32), ("E", C.c_int32),
+                ("poses", C.c_void_p), ("intr", C.c_void_p), ("fixed", C.c_void_p), ("points", C.c_void_p),
+                ("obs_kf", C.c_void_p), ("obs_mp", C.c_void_p), ("obs_uv", C.c_void_p), ("obs_w", C.c_void_p),
+                ("edge_flags", C.c_void_p)]
+
+
+class BAOptionsC(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("robust", C.c_int32), ("huber_delta", C.c_double),
+                ("lambda_init", C.c_double), ("max_trials", C.c_int32), ("pcg_max_iter", C.c_int32),
+                ("pcg_tol", C.c_double), ("stop", C.c_void_p)]
+
+
+class BAResultC(C.Structure):
+    _fields_ = [("poses", C.c_void_p), ("points", C.c_void_p), ("chi2", C.c_void_p), ("depth_pos", C.c_void_p),
+                ("trace", C.c_void_p), ("trace_cap", C.c_int32), ("trace_len", C.c_int32),
+                ("iters_done", C.c_int32), ("trials_total", C.c_int32), ("pcg_iters_total", C.c_int32),
+                ("pcg_not_converged", C.c_int32),
+                ("chi2_initial", C.c_double), ("chi2_final", C.c_double), ("lambda_final", C.c_double),
+                ("t_setup_ms", C.c_double), ("t_optimize_ms", C.c_double), ("t_download_ms", C.c_double)]
+
+
+class BAInfoC(C.Structure):
+    _fields_ = [("K", C.c_int32), ("K_free", C.c_int32), ("P_local", C.c_int32), ("E_local", C.c_int32),
+                ("rank", C.c_int32), ("nranks", C.c_int32), ("s_blocks_upper", C.c_int64),
+                ("s_blocks_full", C.c_int64), ("schur_products", C.c_int64), ("device_bytes", C.c_int64)]
+
+
+class PGOProblemC(C.Structure):
+    _fields_ = [("K", C.c_int32), ("E", C.c_int32), ("sim3", C.c_void_p), ("fixed", C.c_void_p),
+                ("edge_i", C.c_void_p), ("edge_j", C.c_void_p), ("meas", C.c_void_p), ("fix_scale", C.c_int32)]
+
+
+class PGOOptionsC(C.Structure):
+    _fields_ = [("iterations", C.c_int32), ("lambda_init", C.c_double), ("pcg_max_iter", C.c_int32),
+                ("pcg_tol", C.c_double), ("stop", C.c_void_p)]
+
+
+class PGOResultC(C.Structure):
+    _fields_ = [("sim3", C.c_void_p), ("trace", C.c_void_p), ("trace_cap", C.c_int32), ("trace_len", C.c_int32),
+                ("iters_done", C.c_int32), ("chi2_initial", C.c_double), ("chi2_final", C.c_double),
+                ("lambda_final", C.c_double), ("t_total_ms", C.c_double)]
+
+
+class ORBConfigC(C.Structure):
+    _fields_ = [("nfeatures", C.c_int32), ("scale_factor", C.c_float), ("nlevels", C.c_int32),
+                ("ini_th_fast", C.c_int32), ("min_th_fast", C.c_int32), ("blur_2413", C.c_int32)]
+
+
+class KeyPointC(C.Structure):
+    _fields_ = [("x", C.c_float), ("y", C.c_float), ("size", C.c_float), ("angle", C.c_float),
+                ("response", C.c_float), ("octave", C.c_int32)]
+
+
+class FeatureVectorC(C.Structure):
+    _fields_ = [("n_nodes", C.c_int32), ("node_id", C.c_void_p), ("node_ptr", C.c_void_p), ("feat", C.c_void_p)]
+
+
+class TriViewC(C.Structure):
+    _fields_ = [("desc", C.c_void_p), ("n", C.c_int32), ("has_mp", C.c_void_p), ("kp_xy", C.c_void_p),
+                ("octave", C.c_void_p), ("angle", C.c_void_p), ("fv", C.POINTER(FeatureVectorC)),
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float)]
+
+
+def lib():
+    """Loads the shared library; fails loudly when it has not been built (python ccm_slam_b200/build.py)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise CCMError(-100, f"{LIB_PATH} is missing: run `python ccm_slam_b200/build.py` (no CPU fallback exists)")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.ccm_last_error.restype = C.c_char_p
+        _lib.ccm_kernel_launches.restype = C.c_uint64
+    return _lib
+
+
+def _chk(rc):
+    if rc != 0:
+        raise CCMError(rc, lib().ccm_last_error().decode())
+
+
+def _p(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def device_count() -> int:
+    return lib().ccm_device_count()
+
+
+def init(device: int = 0):
+    _chk(lib().ccm_init(device))
+
+
+def kernel_launches() -> int:
+    return int(lib().ccm_kernel_launches())
+
+
+def comm_unique_id() -> np.ndarray:
+    buf = np.zeros(128, np.uint8)
+    _chk(lib().ccm_comm_unique_id(_p(buf)))
+    return buf
+
+
+def comm_init(rank: int, nranks: int, uid: np.ndarray):
+    uid = np.ascontiguousarray(uid, np.uint8)
+    _chk(lib().ccm_comm_init(rank, nranks, _p(uid)))
+
+
+def comm_destroy():
+    _chk(lib().ccm_comm_destroy())
+
+
+def _ba_arrays(p):
+    return dict(poses=np.ascontiguousarray(p.poses, np.float64), intr=np.ascontiguousarray(p.intr, np.float64),
+                fixed=np.ascontiguousarray(p.fixed, np.uint8), points=np.ascontiguousarray(p.points, np.float64),
+                obs_kf=np.ascontiguousarray(p.obs_kf, np.int32), obs_mp=np.ascontiguousarray(p.obs_mp, np.int32),
+                obs_uv=np.ascontiguousarray(p.obs_uv, np.float32), obs_w=np.ascontiguousarray(p.obs_w, np.float32),
+                edge_flags=None if p.edge_flags is None else np.ascontiguousarray(p.edge_flags, np.uint8))
+
+
+def _ba_struct(arrs):
+    return BAProblemC(arrs["poses"].shape[0], arrs["points"].shape[0], arrs["obs_kf"].shape[0],
+                      *[_p(arrs[k]) for k in ("poses", "intr", "fixed", "points", "obs_kf", "obs_mp", "obs_uv", "obs_w", "edge_flags")])
+
+
+def _ba_options(iterations, robust, huber_delta, lambda_init, max_trials, pcg_max_iter, pcg_tol, stop):
+    return BAOptionsC(iterations, int(robust), float(huber_delta), float(lambda_init), max_trials, pcg_max_iter,
+                      float(pcg_tol), _p(stop))
+
+
+def _result_dict(res, poses, points, chi2, depth, trace):
+    return dict(poses=poses, points=points, chi2=chi2, depth_pos=depth, trace=trace[:res.trace_len],
+                iters_done=res.iters_done, trials_total=res.trials_total, pcg_iters_total=res.pcg_iters_total,
+                pcg_not_converged=res.pcg_not_converged, chi2_initial=res.chi2_initial, chi2_final=res.chi2_final,
+                lambda_final=res.lambda_final, t_setup_ms=res.t_setup_ms, t_optimize_ms=res.t_optimize_ms,
+                t_download_ms=res.t_download_ms)
+
+
+HUBER_GBA = float(np.float32(np.sqrt(5.99)))     # `const float thHuber2D = sqrt(5.99)`   S/Optimizer.cpp:712
+HUBER_LOCAL = float(np.float32(np.sqrt(5.991)))  # `const float thHuberMono = sqrt(5.991)` S/Optimizer.cpp:468
+
+
+def ba_solve(p, iterations=20, robust=True, huber_delta=HUBER_GBA, lambda_init=-1.0, max_trials=10,
+             pcg_max_iter=0, pcg_tol=0.0, stop=None, chi2_in=None, want_edges=True):
+    """One-shot ccm_ba_solve: host buffers in, host buffers out (upload + structure + LM + download)."""
+    arrs = _ba_arrays(p)
+    prob = _ba_struct(arrs)
+    K, P, E = prob.K, prob.P, prob.E
+    poses = np.empty((K, 7)); points = np.empty((P, 3))
+    chi2 = (np.zeros(E) if chi2_in is None else np.array(chi2_in, np.float64)) if want_edges else None
+    depth = np.zeros(E, np.uint8) if want_edges else None
+    trace = np.zeros((max(iterations, 1), TRACE_COLS))
+    opt = _ba_options(iterations, robust, huber_delta, lambda_init, max_trials, pcg_max_iter, pcg_tol, stop)
+    res = BAResultC(_p(poses), _p(points), _p(chi2), _p(depth), _p(trace), trace.shape[0])
+    _chk(lib().ccm_ba_solve(C.byref(prob), C.byref(opt), C.byref(res)))
+    return _result_dict(res, poses, points, chi2, depth, trace)
+
+
+class BAHandle:
+    """ccm_ba_create / optimize / reset / destroy: the device-resident form used by LocalBA's two rounds and bench.py."""
+
+    def __init__(self, p):
+        self._arrs = _ba_arrays(p)
+        prob = _ba_struct(self._arrs)
+        self.K, self.P, self.E = prob.K, prob.P, prob.E
+        self._h = C.c_void_p()
+        _chk(lib().ccm_ba_create(C.byref(prob), C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().ccm_ba_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def reset(self):
+        _chk(lib().ccm_ba_reset(self._h))
+
+    def set_edge_flags(self, flags):
+        f = None if flags is None else np.ascontiguousarray(flags, np.uint8)
+        _chk(lib().ccm_ba_set_edge_flags(self._h, _p(f)))
+
+    def info(self):
+        i = BAInfoC()
+        _chk(lib().ccm_ba_get_info(self._h, C.byref(i)))
+        return {k: getattr(i, k) for k, _ in BAInfoC._fields_}
+
+    def optimize(self, iterations=20, robust=True, huber_delta=HUBER_GBA, lambda_init=-1.0, max_trials=10,
+                 pcg_max_iter=0, pcg_tol=0.0, stop=None, chi2_in=None, want_state=True, want_edges=False):
+        poses = np.empty((self.K, 7)) if want_state else None
+        points = np.empty((self.P, 3)) if want_state else None
+        chi2 = (np.zeros(self.E) if chi2_in is None else np.array(chi2_in, np.float64)) if want_edges else None
+        depth = np.zeros(self.E, np.uint8) if want_edges else None
+        trace = np.zeros((max(iterations, 1), TRACE_COLS))
+        opt = _ba_options(iterations, robust, huber_delta, lambda_init, max_trials, pcg_max_iter, pcg_tol, stop)
+        res = BAResultC(_p(poses), _p(points), _p(chi2), _p(depth), _p(trace), trace.shape[0])
+        _chk(lib().ccm_ba_optimize(self._h, C.byref(opt), C.byref(res)))
+        return _result_dict(res, poses, points, chi2, depth, trace)
+
+    def debug_build(self, robust=True, huber_delta=HUBER_GBA):
+        Hpp = np.empty((self.K, 6, 6)); bp = np.empty((self.K, 6)); Hll = np.empty((self.P, 3, 3)); bl = np.empty((self.P, 3))
+        W = np.empty((self.E, 6, 3)); chi = C.c_double()
+        _chk(lib().ccm_ba_debug_build(self._h, int(robust), C.c_double(huber_delta), _p(Hpp), _p(bp), _p(Hll), _p(bl), _p(W), C.byref(chi)))
+        return dict(Hpp=Hpp, bp=bp, Hll=Hll, bl=bl, W=W, chi2_robust_sum=chi.value)
+
+    def debug_schur(self, lam, robust=True, huber_delta=HUBER_GBA, dense=False):
+        S = np.empty((6 * self.K, 6 * self.K)) if dense else None
+        bs = np.empty(6 * self.K); dxp = np.empty((self.K, 6)); dxl = np.empty((self.P, 3))
+        it = C.c_int32(); rr = C.c_double()
+        _chk(lib().ccm_ba_debug_schur(self._h, int(robust), C.c_double(huber_delta), C.c_double(lam), _p(S), _p(bs), _p(dxp), _p(dxl), C.byref(it), C.byref(rr)))
+        return dict(S=S, bschur=bs, dx_pose=dxp, dx_point=dxl, pcg_iters=it.value, pcg_relres=rr.value)
+
+    def time_kernel(self, which, reps=5, huber_delta=HUBER_GBA, lam=1.0):
+        ms = C.c_double()
+        _chk(lib().ccm_ba_time_kernel(self._h, which, reps, C.c_double(huber_delta), C.c_double(lam), C.byref(ms)))
+        return ms.value
+
+
+def poses_from_Tcw_f32(T):
+    T = np.ascontiguousarray(T, np.float32).reshape(-1, 16)
+    out = np.empty((T.shape[0], 7))
+    lib().ccm_pose_from_Tcw_f32(_p(T), T.shape[0], _p(out))
+    return out
+
+
+def poses_to_Tcw_f32(qt):
+    qt = np.ascontiguousarray(qt, np.float64).reshape(-1, 7)
+    out = np.empty((qt.shape[0], 4, 4), np.float32)
+    lib().ccm_pose_to_Tcw_f32(_p(qt), qt.shape[0], _p(out))
+    return out
+
+
+def pgo_solve(p, iterations=20, lambda_init=1e-16, pcg_max_iter=0, pcg_tol=0.0, stop=None):
+    arrs = dict(sim3=np.ascontiguousarray(p.sim3, np.float64), fixed=np.ascontiguousarray(p.fixed, np.uint8),
+                ei=np.ascontiguousarray(p.edge_i, np.int32), ej=np.ascontiguousarray(p.edge_j, np.int32),
+                meas=np.ascontiguousarray(p.meas, np.float64))
+    K, E = arrs["sim3"].shape[0], arrs["ei"].shape[0]
+    prob = PGOProblemC(K, E, _p(arrs["sim3"]), _p(arrs["fixed"]), _p(arrs["ei"]), _p(arrs["ej"]), _p(arrs["meas"]), int(p.fix_scale))
+    out = np.empty((K, 8)); trace = np.zeros((max(iterations, 1), TRACE_COLS))
+    opt = PGOOptionsC(iterations, float(lambda_init), pcg_max_iter, float(pcg_tol), _p(stop))
+    res = PGOResultC(_p(out), _p(trace), trace.shape[0])
+    _chk(lib().ccm_pgo_solve(C.byref(prob), C.byref(opt), C.byref(res)))
+    return dict(sim3=out, trace=trace[:res.trace_len], iters_done=res.iters_done, chi2_initial=res.chi2_initial,
+                chi2_final=res.chi2_final, lambda_final=res.lambda_final, t_total_ms=res.t_total_ms)
+
+
+def hamming_matrix(A, B):
+    A = np.ascontiguousarray(A, np.uint8).reshape(-1, 32); B = np.ascontiguousarray(B, np.uint8).reshape(-1, 32)
+    D = np.empty((A.shape[0], B.shape[0]), np.uint16)
+    _chk(lib().ccm_hamming_matrix(_p(A), A.shape[0], _p(B), B.shape[0], _p(D)))
+    return D

@@ -1,0 +1,793 @@
+// ba_kernels.cuh — sm_100a kernels of the Levenberg-Marquardt bundle-adjustment hot path.
+//
+// Data layout in HBM (one landmark shard per GPU; poses replicated):
+//   pose      [K][7]  f64  AoS  (gathered per observation, K is small -> L1/L2 resident)
+//   pt        [Pl][3] f64  AoS  (observations are sorted by landmark -> consecutive threads share lines)
+//   o_kf,o_lm [El]    i32       observation -> keyframe index / local landmark index (landmark order)
+//   o_uv      [El]    float2    undistorted pixel
+//   o_w       [El]    f32       invSigma2; sign bit = "no robust kernel"; 0 = inactive edge (level 1)
+//   W         [18][Ep] f64 SoA  Hpl block per observation (6x3 row-major entry c at W[c*Ep+e]) -> coalesced stores
+//   Z         [El][18] f64 AoS  W * U^-1 with (Hll + lambda I) = U^T U; gathered 144 B rows by the Schur products
+//   Hll       [6][Pl]  f64 SoA  upper triangle (00 01 02 11 12 22);  bl [3][Pl]
+//   Hpp       [Kf][36], bp [Kf][6] ; U_val [nub][36] upper Schur blocks ; s_val [nnzb][36] full block-CSR for PCG
+//
+// Kernels (reference loop each one replaces: SURVEY.md §2.2 K1..K7):
+//   k_linearize   K1+K2  residual + Huber + Jacobians + W store + Hll/bl warp-segmented reduction + chi2
+//   k_pose_pass   K2     Hpp/bp per free pose (CTA per pose, register accumulation, no atomics)
+//   k_residual    K1     robust chi2 of a trial state
+//   k_scale       K3/K4  Z = W U^-1, g = U^-T bl        (lambda folded in here, no setLambda/restoreDiagonal passes)
+//   k_schur       K4     S_ab = sum_l Z_al Z_bl^T over precomputed product lists (register accumulation, no atomics)
+//   k_finalize_S  K4     S = [a==b](Hpp + lambda I) - products, mirrored to full block-CSR
+//   k_block_jacobi K5    6x6 inverses of the diagonal blocks + bschur
+//   k_pcg         K5     persistent cooperative PCG on the reduced camera system
+//   k_update_poses / k_backsub_points  K6+K7  back-substitution, oplus into the trial state, gain-ratio denominator
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "ba_math.cuh"
+
+namespace ccm {
+namespace ba {
+
+constexpr int TPB = 256;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// block-wide sum; result valid in thread 0.  smem must hold TPB/32 doubles.
+__device__ __forceinline__ double block_sum(double v, double* smem) {
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) smem[wid] = v;
+  __syncthreads();
+  double r = 0;
+  if (wid == 0) {
+    r = lane < (blockDim.x >> 5) ? smem[lane] : 0.0;
+    r = warp_sum(r);
+  }
+  return r;
+}
+
+__device__ __forceinline__ Pose load_pose(const double* __restrict__ pose, int k) {
+  const double* p = pose + 7 * (size_t)k;
+  Pose T;
+  T.qx = __ldg(p); T.qy = __ldg(p + 1); T.qz = __ldg(p + 2); T.qw = __ldg(p + 3);
+  T.tx = __ldg(p + 4); T.ty = __ldg(p + 5); T.tz = __ldg(p + 6);
+  return T;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K1+K2: one thread per observation (landmark order).
+//   reads  20 B/obs (kf, lm, uv, w) + gathers (pose 56 B, intr 32 B, point 24 B: cache resident)
+//   writes 144 B/obs (W, SoA, fully coalesced) + 72 B/landmark (Hll, bl) via warp-segmented reduction
+__global__ void __launch_bounds__(TPB) k_linearize(
+    const int* __restrict__ o_kf, const int* __restrict__ o_lm, const float2* __restrict__ o_uv,
+    const float* __restrict__ o_w, const double* __restrict__ pose, const double* __restrict__ intr,
+    const int* __restrict__ pose_slot, const double* __restrict__ pt, int E, size_t Ep, int Pl, int robust,
+    double delta, double* __restrict__ W, double* __restrict__ Hll, double* __restrict__ bl,
+    double* __restrict__ chi2_partials) {
+  __shared__ double red[TPB / 32];
+  double chi_acc = 0.0;
+  const int lane = threadIdx.x & 31;
+  for (long long base = (long long)blockIdx.x * TPB; base < E; base += (long long)gridDim.x * TPB) {
+    const long long e = base + threadIdx.x;
+    const bool valid = e < E;
+    int lm = -1;
+    double h[9];  // Hll upper (6) + bl (3)
+#pragma unroll
+    for (int i = 0; i < 9; i++) h[i] = 0.0;
+    if (valid) {
+      const int kf = o_kf[e];
+      lm = o_lm[e];
+      const float2 uv = o_uv[e];
+      const float wf = o_w[e];
+      const double w = fabs((double)wf);
+      const bool rob = robust && !signbit(wf);
+      const Pose T = load_pose(pose, kf);
+      const double in4[4] = {__ldg(intr + 4 * (size_t)kf), __ldg(intr + 4 * (size_t)kf + 1),
+                             __ldg(intr + 4 * (size_t)kf + 2), __ldg(intr + 4 * (size_t)kf + 3)};
+      const double* X = pt + 3 * (size_t)lm;
+      ObsLin L;
+      linearize_obs(T, in4, X[0], X[1], X[2], (double)uv.x, (double)uv.y, w, L);
+      double rho0 = L.chi2, rho1 = 1.0;
+      if (rob) huber(L.chi2, delta, rho0, rho1);
+      chi_acc += rho0;
+      const double wo = rho1 * w;               // weightedOmega = rho'(chi2) * omega
+      const double r0 = -wo * L.ex, r1 = -wo * L.ey;  // omega_r = -omega e * rho'
+      // point block
+      h[0] = wo * (L.Jl[0] * L.Jl[0] + L.Jl[3] * L.Jl[3]);
+      h[1] = wo * (L.Jl[0] * L.Jl[1] + L.Jl[3] * L.Jl[4]);
+      h[2] = wo * (L.Jl[0] * L.Jl[2] + L.Jl[3] * L.Jl[5]);
+      h[3] = wo * (L.Jl[1] * L.Jl[1] + L.Jl[4] * L.Jl[4]);
+      h[4] = wo * (L.Jl[1] * L.Jl[2] + L.Jl[4] * L.Jl[5]);
+      h[5] = wo * (L.Jl[2] * L.Jl[2] + L.Jl[5] * L.Jl[5]);
+      h[6] = L.Jl[0] * r0 + L.Jl[3] * r1;
+      h[7] = L.Jl[1] * r0 + L.Jl[4] * r1;
+      h[8] = L.Jl[2] * r0 + L.Jl[5] * r1;
+      // pose-landmark block W = Jp^T (wo I) Jl  (zero when the pose vertex is fixed)
+      const double wz = __ldg(pose_slot + kf) >= 0 ? wo : 0.0;
+#pragma unroll
+      for (int r = 0; r < 6; r++) {
+        const double a = wz * L.Jp[r], b = wz * L.Jp[6 + r];
+#pragma unroll
+        for (int c = 0; c < 3; c++) W[(size_t)(r * 3 + c) * Ep + e] = a * L.Jl[c] + b * L.Jl[3 + c];
+      }
+    }
+    // segmented (by landmark) warp reduction of the 9 point-side sums; observations of one landmark are contiguous
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int lm_o = __shfl_down_sync(0xffffffffu, lm, off);
+      const bool take = (lane + off < 32) && (lm_o == lm);
+#pragma unroll
+      for (int i = 0; i < 9; i++) {
+        const double v = __shfl_down_sync(0xffffffffu, h[i], off);
+        if (take) h[i] += v;
+      }
+    }
+    const int lm_prev = __shfl_up_sync(0xffffffffu, lm, 1);
+    if (lm >= 0 && (lane == 0 || lm_prev != lm)) {
+      // a landmark may straddle warps: red.add into the zeroed accumulators (<= a few partial sums per landmark)
+#pragma unroll
+      for (int i = 0; i < 6; i++) atomicAdd(Hll + (size_t)i * Pl + lm, h[i]);
+#pragma unroll
+      for (int i = 0; i < 3; i++) atomicAdd(bl + (size_t)i * Pl + lm, h[6 + i]);
+    }
+  }
+  const double tot = block_sum(chi_acc, red);
+  if (threadIdx.x == 0) chi2_partials[blockIdx.x] = tot;
+}
+
+// K1 on a (trial) state: robust chi2 only.  20 B/obs read.
+__global__ void __launch_bounds__(TPB) k_residual(
+    const int* __restrict__ o_kf, const int* __restrict__ o_lm, const float2* __restrict__ o_uv,
+    const float* __restrict__ o_w, const double* __restrict__ pose, const double* __restrict__ intr,
+    const double* __restrict__ pt, int E, int robust, double delta, double* __restrict__ chi2_partials) {
+  __shared__ double red[TPB / 32];
+  double chi_acc = 0.0;
+  for (long long e = (long long)blockIdx.x * TPB + threadIdx.x; e < E; e += (long long)gridDim.x * TPB) {
+    const int kf = o_kf[e];
+    const int lm = o_lm[e];
+    const float2 uv = o_uv[e];
+    const float wf = o_w[e];
+    const double w = fabs((double)wf);
+    const Pose T = load_pose(pose, kf);
+    const double in4[4] = {__ldg(intr + 4 * (size_t)kf), __ldg(intr + 4 * (size_t)kf + 1),
+                           __ldg(intr + 4 * (size_t)kf + 2), __ldg(intr + 4 * (size_t)kf + 3)};
+    const double* X = pt + 3 * (size_t)lm;
+    double ex, ey, chi2, Xc[3];
+    project_residual(T, in4, X[0], X[1], X[2], (double)uv.x, (double)uv.y, w, ex, ey, chi2, Xc);
+    double rho0 = chi2, rho1;
+    if (robust && !signbit(wf)) huber(chi2, delta, rho0, rho1);
+    chi_acc += rho0;
+  }
+  const double tot = block_sum(chi_acc, red);
+  if (threadIdx.x == 0) chi2_partials[blockIdx.x] = tot;
+}
+
+// per-edge report for the caller: plain chi2 at the last evaluated state, depth sign at the final estimate
+__global__ void __launch_bounds__(TPB) k_edge_report(
+    const int* __restrict__ o_kf, const int* __restrict__ o_lm, const float2* __restrict__ o_uv,
+    const float* __restrict__ o_w, const double* __restrict__ pose_eval, const double* __restrict__ pt_eval,
+    const double* __restrict__ pose_fin, const double* __restrict__ pt_fin, const double* __restrict__ intr, int E,
+    double* __restrict__ chi2_out, uint8_t* __restrict__ depth_out) {
+  const long long e = (long long)blockIdx.x * TPB + threadIdx.x;
+  if (e >= E) return;
+  const int kf = o_kf[e], lm = o_lm[e];
+  const float2 uv = o_uv[e];
+  const double w = fabs((double)o_w[e]);
+  const double in4[4] = {intr[4 * (size_t)kf], intr[4 * (size_t)kf + 1], intr[4 * (size_t)kf + 2], intr[4 * (size_t)kf + 3]};
+  double ex, ey, chi2, Xc[3];
+  {
+    const Pose T = load_pose(pose_eval, kf);
+    const double* X = pt_eval + 3 * (size_t)lm;
+    project_residual(T, in4, X[0], X[1], X[2], (double)uv.x, (double)uv.y, w, ex, ey, chi2, Xc);
+    chi2_out[e] = chi2;
+  }
+  {
+    const Pose T = load_pose(pose_fin, kf);
+    const double* X = pt_fin + 3 * (size_t)lm;
+    project_residual(T, in4, X[0], X[1], X[2], (double)uv.x, (double)uv.y, w, ex, ey, chi2, Xc);
+    depth_out[e] = Xc[2] > 0.0 ? 1 : 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K2 pose side: one CTA per free pose; its observations are the product list of the diagonal Schur block (a,a).
+__global__ void __launch_bounds__(128) k_pose_pass(
+    const uint2* __restrict__ prod, const unsigned* __restrict__ u_prod_ptr, const int* __restrict__ u_diag,
+    const int* __restrict__ slot_pose, const int* __restrict__ o_lm, const float2* __restrict__ o_uv,
+    const float* __restrict__ o_w, const double* __restrict__ pose, const double* __restrict__ intr,
+    const double* __restrict__ pt, int robust, double delta, double* __restrict__ Hpp, double* __restrict__ bp) {
+  __shared__ double red[27][4];
+  const int a = blockIdx.x;
+  const int kf = slot_pose[a];
+  const int u = u_diag[a];
+  const unsigned beg = u_prod_ptr[u], end = u_prod_ptr[u + 1];
+  const Pose T = load_pose(pose, kf);
+  const double in4[4] = {intr[4 * (size_t)kf], intr[4 * (size_t)kf + 1], intr[4 * (size_t)kf + 2], intr[4 * (size_t)kf + 3]};
+  double acc[27];
+#pragma unroll
+  for (int i = 0; i < 27; i++) acc[i] = 0.0;
+  for (unsigned p = beg + threadIdx.x; p < end; p += blockDim.x) {
+    const unsigned e = prod[p].x;
+    const int lm = o_lm[e];
+    const float2 uv = o_uv[e];
+    const float wf = o_w[e];
+    const double w = fabs((double)wf);
+    const double* X = pt + 3 * (size_t)lm;
+    ObsLin L;
+    linearize_obs(T, in4, X[0], X[1], X[2], (double)uv.x, (double)uv.y, w, L);
+    double rho0, rho1 = 1.0;
+    if (robust && !signbit(wf)) huber(L.chi2, delta, rho0, rho1);
+    const double wo = rho1 * w;
+    const double r0 = -wo * L.ex, r1 = -wo * L.ey;
+    int q = 0;
+#pragma unroll
+    for (int i = 0; i < 6; i++)
+#pragma unroll
+      for (int j = i; j < 6; j++) acc[q++] += wo * (L.Jp[i] * L.Jp[j] + L.Jp[6 + i] * L.Jp[6 + j]);
+#pragma unroll
+    for (int i = 0; i < 6; i++) acc[21 + i] += L.Jp[i] * r0 + L.Jp[6 + i] * r1;
+  }
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < 27; i++) {
+    const double v = warp_sum(acc[i]);
+    if (lane == 0) red[i][wid] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < 27) {
+    const double v = red[threadIdx.x][0] + red[threadIdx.x][1] + red[threadIdx.x][2] + red[threadIdx.x][3];
+    if (threadIdx.x < 21) {
+      // unpack upper-triangular index -> (i,j)
+      int i = 0, q = threadIdx.x;
+      while (q >= 6 - i) { q -= 6 - i; i++; }
+      const int j = i + q;
+      Hpp[(size_t)a * 36 + i * 6 + j] = v;
+      Hpp[(size_t)a * 36 + j * 6 + i] = v;
+    } else {
+      bp[(size_t)a * 6 + (threadIdx.x - 21)] = v;
+    }
+  }
+}
+
+// max |diag| over Hpp and Hll -> bits of a non-negative double, atomicMax as unsigned long long
+__global__ void __launch_bounds__(TPB) k_max_diag(const double* __restrict__ Hpp, int Kf, const double* __restrict__ Hll,
+                                                  int Pl, unsigned long long* __restrict__ out) {
+  double m = 0.0;
+  const long long n1 = (long long)Kf * 6, n2 = (long long)Pl * 3;
+  for (long long i = (long long)blockIdx.x * TPB + threadIdx.x; i < n1 + n2; i += (long long)gridDim.x * TPB) {
+    double v;
+    if (i < n1) {
+      v = Hpp[(i / 6) * 36 + (i % 6) * 7];
+    } else {
+      const long long j = i - n1;
+      const int d = (int)(j / Pl);  // 0,1,2 -> rows 0,3,5 of the packed upper triangle
+      const int row = d == 0 ? 0 : (d == 1 ? 3 : 5);
+      v = Hll[(size_t)row * Pl + (j % Pl)];
+    }
+    m = fmax(m, fabs(v));
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) atomicMax(out, (unsigned long long)__double_as_longlong(m));
+}
+
+// single-block deterministic sum of partials: out[0] = sum
+__global__ void __launch_bounds__(1024) k_sum_partials(const double* __restrict__ partials, int n, double* __restrict__ out) {
+  __shared__ double red[32];
+  double v = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) v += partials[i];
+  const double t = block_sum(v, red);
+  if (threadIdx.x == 0) out[0] = t;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K3/K4 first half: Z = W U^-1 (AoS, staged through shared memory for coalesced 144 B rows), g = U^-T bl.
+// reads 144 B/obs (W) + cached Hll ; writes 144 B/obs (Z)
+__global__ void __launch_bounds__(TPB) k_scale(const int* __restrict__ o_lm, const double* __restrict__ W, size_t Ep,
+                                               const double* __restrict__ Hll, const double* __restrict__ bl, int Pl,
+                                               int E, double lambda, double* __restrict__ Z, double* __restrict__ gvec) {
+  __shared__ double tile[TPB * 19];
+  const long long e0 = (long long)blockIdx.x * TPB;
+  const long long e = e0 + threadIdx.x;
+  if (e < E) {
+    const int lm = o_lm[e];
+    double d[6], u[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) d[i] = __ldg(Hll + (size_t)i * Pl + lm);
+    d[0] += lambda; d[3] += lambda; d[5] += lambda;
+    chol3_upper(d, u);
+#pragma unroll
+    for (int r = 0; r < 6; r++) {
+      const double w0 = W[(size_t)(r * 3) * Ep + e], w1 = W[(size_t)(r * 3 + 1) * Ep + e], w2 = W[(size_t)(r * 3 + 2) * Ep + e];
+      double z0, z1, z2;
+      row_times_Uinv(u, w0, w1, w2, z0, z1, z2);
+      tile[threadIdx.x * 19 + r * 3] = z0;
+      tile[threadIdx.x * 19 + r * 3 + 1] = z1;
+      tile[threadIdx.x * 19 + r * 3 + 2] = z2;
+    }
+    const bool head = (e == 0) || (o_lm[e - 1] != lm);
+    if (head) {
+      const double b3[3] = {__ldg(bl + lm), __ldg(bl + (size_t)Pl + lm), __ldg(bl + 2 * (size_t)Pl + lm)};
+      double g[3];
+      UTinv_times(u, b3, g);
+      gvec[3 * (size_t)lm] = g[0]; gvec[3 * (size_t)lm + 1] = g[1]; gvec[3 * (size_t)lm + 2] = g[2];
+    }
+  }
+  __syncthreads();
+  const long long nvalid = (E - e0 < TPB ? E - e0 : TPB) * 18;
+  double* out = Z + e0 * 18;
+  for (int i = threadIdx.x; i < nvalid; i += TPB) out[i] = tile[(i / 18) * 19 + (i % 18)];
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K4: Schur products.  One warp per upper block u = (a,b): lane = (row r = lane % 6, stream s = lane / 6), 5 streams.
+//   acc[r][c] += sum_k Z_oa[r][k] * Z_ob[c][k]  over the block's product list; diagonal blocks also build
+//   bneg_a = sum_o Z_o g_l(o).  Outputs are written NEGATED (S = Hpp + lambda I - sum).
+__global__ void __launch_bounds__(TPB) k_schur(const uint2* __restrict__ prod, const unsigned* __restrict__ u_prod_ptr,
+                                               const int* __restrict__ u_row, const int* __restrict__ u_col, int nub,
+                                               const double* __restrict__ Z, const int* __restrict__ o_lm,
+                                               const double* __restrict__ gvec, double* __restrict__ U_val,
+                                               double* __restrict__ bneg) {
+  const int warp = (int)(((long long)blockIdx.x * TPB + threadIdx.x) >> 5);
+  if (warp >= nub) return;
+  const int lane = threadIdx.x & 31;
+  const int r = lane % 6, s = lane / 6;  // lanes 30,31: s == 5 -> idle stream
+  const unsigned beg = u_prod_ptr[warp], end = u_prod_ptr[warp + 1];
+  const bool diag = u_row[warp] == u_col[warp];
+  double acc[6] = {0, 0, 0, 0, 0, 0};
+  double bacc = 0.0;
+  if (s < 5) {
+    for (unsigned p = beg + s; p < end; p += 5) {
+      const uint2 pr = prod[p];
+      const double* za = Z + (size_t)pr.x * 18 + r * 3;
+      const double a0 = za[0], a1 = za[1], a2 = za[2];
+      const double2* zb = reinterpret_cast<const double2*>(Z + (size_t)pr.y * 18);
+      double b[18];
+#pragma unroll
+      for (int i = 0; i < 9; i++) {
+        const double2 t = zb[i];
+        b[2 * i] = t.x; b[2 * i + 1] = t.y;
+      }
+#pragma unroll
+      for (int c = 0; c < 6; c++) acc[c] += a0 * b[c * 3] + a1 * b[c * 3 + 1] + a2 * b[c * 3 + 2];
+      if (diag) {
+        const double* g = gvec + 3 * (size_t)o_lm[pr.x];
+        bacc += a0 * g[0] + a1 * g[1] + a2 * g[2];
+      }
+    }
+  }
+  // combine the 5 streams: lane r gathers lanes r+6, r+12, r+18, r+24
+#pragma unroll
+  for (int c = 0; c < 6; c++) {
+    double v = acc[c];
+    v += __shfl_sync(0xffffffffu, acc[c], (r + 6) & 31) + __shfl_sync(0xffffffffu, acc[c], (r + 12) & 31) +
+         __shfl_sync(0xffffffffu, acc[c], (r + 18) & 31) + __shfl_sync(0xffffffffu, acc[c], (r + 24) & 31);
+    acc[c] = v;
+  }
+  {
+    double v = bacc;
+    v += __shfl_sync(0xffffffffu, bacc, (r + 6) & 31) + __shfl_sync(0xffffffffu, bacc, (r + 12) & 31) +
+         __shfl_sync(0xffffffffu, bacc, (r + 18) & 31) + __shfl_sync(0xffffffffu, bacc, (r + 24) & 31);
+    bacc = v;
+  }
+  if (lane < 6) {
+#pragma unroll
+    for (int c = 0; c < 6; c++) U_val[(size_t)warp * 36 + r * 6 + c] = -acc[c];
+    if (diag) bneg[(size_t)u_row[warp] * 6 + r] = -bacc;
+  }
+}
+
+// S (full block-CSR) from the upper blocks: diagonal gets Hpp + lambda I, lower blocks are transposed copies.
+__global__ void __launch_bounds__(TPB) k_finalize_S(const int* __restrict__ s_row, const int* __restrict__ s_col,
+                                                    const int* __restrict__ csr_u, long long nnzb,
+                                                    const double* __restrict__ U_val, const double* __restrict__ Hpp,
+                                                    double lambda, double* __restrict__ s_val) {
+  const long long i = (long long)blockIdx.x * TPB + threadIdx.x;
+  if (i >= nnzb * 36) return;
+  const long long pos = i / 36;
+  const int ent = (int)(i % 36);
+  const int a = s_row[pos], b = s_col[pos];
+  const int u = csr_u[pos];
+  double v;
+  if (a <= b) {
+    v = U_val[(size_t)u * 36 + ent];
+    if (a == b) {
+      v += Hpp[(size_t)a * 36 + ent];
+      if (ent % 7 == 0) v += lambda;
+    }
+  } else {
+    v = U_val[(size_t)u * 36 + (ent % 6) * 6 + ent / 6];
+  }
+  s_val[i] = v;
+}
+
+// block-Jacobi preconditioner: Minv_a = inverse(S_aa) by Cholesky; bschur = bp + bneg
+__global__ void __launch_bounds__(128) k_block_jacobi(const int* __restrict__ s_diag, const double* __restrict__ s_val,
+                                                      const double* __restrict__ bp, const double* __restrict__ bneg,
+                                                      int Kf, double* __restrict__ Minv, double* __restrict__ bschur,
+                                                      int* __restrict__ fail) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= Kf) return;
+  double A[36], Li[36];
+  const double* src = s_val + (size_t)s_diag[a] * 36;
+#pragma unroll
+  for (int i = 0; i < 36; i++) A[i] = src[i];
+  // Cholesky A = L L^T (lower), in place
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < 6; j++) {
+    double d = A[j * 6 + j];
+#pragma unroll
+    for (int k = 0; k < j; k++) d -= A[j * 6 + k] * A[j * 6 + k];
+    if (!(d > 0.0)) { ok = false; d = 1.0; }
+    const double l = sqrt(d);
+    A[j * 6 + j] = l;
+    const double il = 1.0 / l;
+#pragma unroll
+    for (int i = j + 1; i < 6; i++) {
+      double v = A[i * 6 + j];
+#pragma unroll
+      for (int k = 0; k < j; k++) v -= A[i * 6 + k] * A[j * 6 + k];
+      A[i * 6 + j] = v * il;
+    }
+  }
+  // Li = L^-1 (lower)
+#pragma unroll
+  for (int i = 0; i < 36; i++) Li[i] = 0.0;
+#pragma unroll
+  for (int c = 0; c < 6; c++) {
+    Li[c * 6 + c] = 1.0 / A[c * 6 + c];
+#pragma unroll
+    for (int i = c + 1; i < 6; i++) {
+      double v = 0.0;
+#pragma unroll
+      for (int k = c; k < i; k++) v -= A[i * 6 + k] * Li[k * 6 + c];
+      Li[i * 6 + c] = v / A[i * 6 + i];
+    }
+  }
+  // Minv = Li^T Li
+#pragma unroll
+  for (int i = 0; i < 6; i++)
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+      double v = 0.0;
+#pragma unroll
+      for (int k = 0; k < 6; k++) v += Li[k * 6 + i] * Li[k * 6 + j];
+      Minv[(size_t)a * 36 + i * 6 + j] = v;
+    }
+#pragma unroll
+  for (int i = 0; i < 6; i++) bschur[(size_t)a * 6 + i] = bp[(size_t)a * 6 + i] + bneg[(size_t)a * 6 + i];
+  if (!ok) atomicExch(fail, 1);
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K5: persistent cooperative PCG on S x = b (block-Jacobi preconditioned).  One warp per block row, grid-wide
+// barriers through a global counter; dot products are reduced in a fixed order so every CTA sees identical scalars.
+struct PcgArgs {
+  int n;  // block rows
+  const int* rowptr; const int* col; const double* val; const double* Minv; const double* b;
+  double *x, *r, *z, *p, *q;
+  double* partials;  // 3 * gridDim.x
+  unsigned* bar;
+  double tol; int max_iter;
+  double* status;    // [iters, relres, flag(0 ok, 1 max_iter, 2 breakdown)]
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& target) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    target += gridDim.x;
+    __threadfence();
+    atomicAdd(bar, 1u);
+    while (*(volatile unsigned*)bar < target) {}
+    __threadfence();
+  }
+  __syncthreads();
+}
+
+// sum of partials[0..g) in a fixed order, same value in every thread of the calling warp
+__device__ __forceinline__ double sum_partials(const double* partials, int g) {
+  double v = 0.0;
+  for (int i = threadIdx.x & 31; i < g; i += 32) v += __ldcg(partials + i);
+  return warp_sum(v);
+}
+
+__global__ void __launch_bounds__(TPB) k_pcg(PcgArgs A) {
+  __shared__ double red[TPB / 32];
+  __shared__ double bcast[2];
+  const int lane = threadIdx.x & 31;
+  const int gw = (blockIdx.x * TPB + threadIdx.x) >> 5;
+  const int nw = (gridDim.x * TPB) >> 5;
+  const int G = gridDim.x;
+  unsigned target = 0;
+  double* part0 = A.partials;
+  double* part1 = A.partials + G;
+  double* part2 = A.partials + 2 * G;
+
+  // init: x = 0, r = b, z = Minv r, p = z ; rz = r.z ; bb = b.b
+  double acc_rz = 0.0, acc_bb = 0.0;
+  for (int a = gw; a < A.n; a += nw) {
+    double rv = 0.0, zv = 0.0;
+    if (lane < 6) {
+      rv = A.b[(size_t)a * 6 + lane];
+      const double* M = A.Minv + (size_t)a * 36 + lane * 6;
+      const double* ra = A.b + (size_t)a * 6;
+#pragma unroll
+      for (int k = 0; k < 6; k++) zv += M[k] * ra[k];
+      A.x[(size_t)a * 6 + lane] = 0.0;
+      A.r[(size_t)a * 6 + lane] = rv;
+      A.z[(size_t)a * 6 + lane] = zv;
+      A.p[(size_t)a * 6 + lane] = zv;
+      acc_rz += rv * zv;
+      acc_bb += rv * rv;
+    }
+  }
+  {
+    const double t0 = block_sum(acc_rz, red);
+    const double t1 = block_sum(acc_bb, red);
+    if (threadIdx.x == 0) { part0[blockIdx.x] = t0; part1[blockIdx.x] = t1; }
+  }
+  grid_barrier(A.bar, target);
+  double rz = sum_partials(part0, G);
+  const double bb = sum_partials(part1, G);
+  const double stop2 = A.tol * A.tol * bb;
+  int it = 0, flag = 1;
+  double rr = bb;
+  if (!(bb > 0.0)) { flag = 0; }
+  else
+    for (it = 0; it < A.max_iter; it++) {
+      // q = S p ; pq = p.q
+      double acc_pq = 0.0;
+      for (int a = gw; a < A.n; a += nw) {
+        double y[6] = {0, 0, 0, 0, 0, 0};
+        const int beg = A.rowptr[a], end = A.rowptr[a + 1];
+        for (int j = beg + lane; j < end; j += 32) {
+          const double2* v = reinterpret_cast<const double2*>(A.val + (size_t)j * 36);
+          const double* pj = A.p + (size_t)A.col[j] * 6;
+          double pv[6];
+#pragma unroll
+          for (int k = 0; k < 6; k++) pv[k] = __ldcg(pj + k);
+#pragma unroll
+          for (int rI = 0; rI < 6; rI++) {
+            const double2 v0 = __ldg(v + rI * 3), v1 = __ldg(v + rI * 3 + 1), v2 = __ldg(v + rI * 3 + 2);
+            y[rI] += v0.x * pv[0] + v0.y * pv[1] + v1.x * pv[2] + v1.y * pv[3] + v2.x * pv[4] + v2.y * pv[5];
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 6; k++) y[k] = warp_sum(y[k]);
+        if (lane < 6) {
+          double yl = y[0];
+#pragma unroll
+          for (int k = 1; k < 6; k++) yl = lane == k ? y[k] : yl;
+          A.q[(size_t)a * 6 + lane] = yl;
+          acc_pq += yl * A.p[(size_t)a * 6 + lane];
+        }
+      }
+      {
+        const double t0 = block_sum(acc_pq, red);
+        if (threadIdx.x == 0) part0[blockIdx.x] = t0;
+      }
+      grid_barrier(A.bar, target);
+      const double pq = sum_partials(part0, G);
+      if (!(pq > 0.0) || !isfinite(pq)) { flag = 2; break; }
+      const double alpha = rz / pq;
+      // x += alpha p ; r -= alpha q ; z = Minv r ; rz_new = r.z ; rr = r.r   (rows owned by this warp)
+      double acc_rz2 = 0.0, acc_rr = 0.0;
+      for (int a = gw; a < A.n; a += nw) {
+        double rv = 0.0;
+        if (lane < 6) {
+          rv = A.r[(size_t)a * 6 + lane] - alpha * A.q[(size_t)a * 6 + lane];
+          A.x[(size_t)a * 6 + lane] += alpha * A.p[(size_t)a * 6 + lane];
+          A.r[(size_t)a * 6 + lane] = rv;
+        }
+        double r6[6];
+#pragma unroll
+        for (int k = 0; k < 6; k++) r6[k] = __shfl_sync(0xffffffffu, rv, k);
+        if (lane < 6) {
+          const double* M = A.Minv + (size_t)a * 36 + lane * 6;
+          double zv = 0.0;
+#pragma unroll
+          for (int k = 0; k < 6; k++) zv += M[k] * r6[k];
+          A.z[(size_t)a * 6 + lane] = zv;
+          acc_rz2 += rv * zv;
+          acc_rr += rv * rv;
+        }
+      }
+      {
+        const double t0 = block_sum(acc_rz2, red);
+        const double t1 = block_sum(acc_rr, red);
+        if (threadIdx.x == 0) { part1[blockIdx.x] = t0; part2[blockIdx.x] = t1; }
+      }
+      grid_barrier(A.bar, target);
+      const double rz_new = sum_partials(part1, G);
+      rr = sum_partials(part2, G);
+      if (rr <= stop2) { flag = 0; it++; break; }
+      const double beta = rz_new / rz;
+      rz = rz_new;
+      for (int a = gw; a < A.n; a += nw)
+        if (lane < 6) A.p[(size_t)a * 6 + lane] = A.z[(size_t)a * 6 + lane] + beta * A.p[(size_t)a * 6 + lane];
+      grid_barrier(A.bar, target);
+    }
+  (void)bcast;
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    A.status[0] = (double)it;
+    A.status[1] = bb > 0.0 ? sqrt(rr / bb) : 0.0;
+    A.status[2] = (double)flag;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K6+K7 (poses): trial = exp(x) * T ; partial of sum x (lambda x + b) over pose unknowns
+__global__ void __launch_bounds__(TPB) k_update_poses(const double* __restrict__ pose, const int* __restrict__ pose_slot,
+                                                      const double* __restrict__ x, const double* __restrict__ bp, int K,
+                                                      double lambda, double* __restrict__ pose_trial,
+                                                      double* __restrict__ scale_partials) {
+  __shared__ double red[TPB / 32];
+  double acc = 0.0;
+  for (int k = blockIdx.x * TPB + threadIdx.x; k < K; k += gridDim.x * TPB) {
+    Pose T;
+    const double* p = pose + 7 * (size_t)k;
+    T.qx = p[0]; T.qy = p[1]; T.qz = p[2]; T.qw = p[3]; T.tx = p[4]; T.ty = p[5]; T.tz = p[6];
+    const int s = pose_slot[k];
+    if (s >= 0) {
+      double u[6];
+#pragma unroll
+      for (int i = 0; i < 6; i++) {
+        u[i] = x[(size_t)s * 6 + i];
+        acc += u[i] * (lambda * u[i] + bp[(size_t)s * 6 + i]);
+      }
+      T = se3_exp_times(u, T);
+    }
+    double* o = pose_trial + 7 * (size_t)k;
+    o[0] = T.qx; o[1] = T.qy; o[2] = T.qz; o[3] = T.qw; o[4] = T.tx; o[5] = T.ty; o[6] = T.tz;
+  }
+  const double t = block_sum(acc, red);
+  if (threadIdx.x == 0) scale_partials[blockIdx.x] = t;
+}
+
+// K6+K7 (landmarks): xl = U^-1 (g - sum_o Z_o^T xp), trial point = point + xl, partial of sum xl (lambda xl + bl)
+__global__ void __launch_bounds__(TPB) k_backsub_points(const int* __restrict__ lm_ptr, const int* __restrict__ o_kf,
+                                                        const int* __restrict__ pose_slot, const double* __restrict__ Z,
+                                                        const double* __restrict__ Hll, const double* __restrict__ bl,
+                                                        const double* __restrict__ x, const double* __restrict__ pt,
+                                                        int Pl, double lambda, double* __restrict__ pt_trial,
+                                                        double* __restrict__ dx_out, double* __restrict__ scale_partials) {
+  __shared__ double red[TPB / 32];
+  double acc = 0.0;
+  for (int l = blockIdx.x * TPB + threadIdx.x; l < Pl; l += gridDim.x * TPB) {
+    double d[6], u[6], b3[3], g[3], t[3] = {0, 0, 0}, xl[3];
+#pragma unroll
+    for (int i = 0; i < 6; i++) d[i] = Hll[(size_t)i * Pl + l];
+    d[0] += lambda; d[3] += lambda; d[5] += lambda;
+    chol3_upper(d, u);
+    b3[0] = bl[l]; b3[1] = bl[(size_t)Pl + l]; b3[2] = bl[2 * (size_t)Pl + l];
+    UTinv_times(u, b3, g);
+    const int beg = lm_ptr[l], end = lm_ptr[l + 1];
+    for (int o = beg; o < end; o++) {
+      const int s = __ldg(pose_slot + o_kf[o]);
+      if (s < 0) continue;
+      const double2* z2 = reinterpret_cast<const double2*>(Z + (size_t)o * 18);
+      double z[18];
+#pragma unroll
+      for (int i = 0; i < 9; i++) { const double2 v = z2[i]; z[2 * i] = v.x; z[2 * i + 1] = v.y; }
+#pragma unroll
+      for (int r = 0; r < 6; r++) {
+        const double xr = __ldg(x + (size_t)s * 6 + r);
+        t[0] += z[r * 3] * xr; t[1] += z[r * 3 + 1] * xr; t[2] += z[r * 3 + 2] * xr;
+      }
+    }
+    const double gm[3] = {g[0] - t[0], g[1] - t[1], g[2] - t[2]};
+    Uinv_times(u, gm, xl);
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+      pt_trial[3 * (size_t)l + c] = pt[3 * (size_t)l + c] + xl[c];
+      acc += xl[c] * (lambda * xl[c] + b3[c]);
+      if (dx_out) dx_out[3 * (size_t)l + c] = xl[c];
+    }
+  }
+  const double tt = block_sum(acc, red);
+  if (threadIdx.x == 0) scale_partials[blockIdx.x] = tt;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// structure building (once per create): covisibility bitmap -> block-CSR pattern -> Schur product lists
+__global__ void __launch_bounds__(TPB) k_pattern_bitmap(const int* __restrict__ g_kf, const int* __restrict__ g_lm_of,
+                                                        const int* __restrict__ g_lm_ptr, const int* __restrict__ pose_slot,
+                                                        long long E, int words, unsigned* __restrict__ bitmap) {
+  const long long e = (long long)blockIdx.x * TPB + threadIdx.x;
+  if (e >= E) return;
+  const int a = pose_slot[g_kf[e]];
+  if (a < 0) return;
+  const int lm = g_lm_of[e];
+  const int beg = g_lm_ptr[lm], end = g_lm_ptr[lm + 1];
+  for (int o = beg; o < end; o++) {
+    const int b = pose_slot[g_kf[o]];
+    if (b < 0) continue;
+    unsigned* wp = bitmap + (size_t)a * words + (b >> 5);
+    const unsigned bit = 1u << (b & 31);
+    if (!(*(volatile unsigned*)wp & bit)) atomicOr(wp, bit);
+  }
+}
+
+__global__ void __launch_bounds__(TPB) k_set_diag_bits(int Kf, int words, unsigned* __restrict__ bitmap) {
+  const int a = blockIdx.x * TPB + threadIdx.x;
+  if (a < Kf) atomicOr(bitmap + (size_t)a * words + (a >> 5), 1u << (a & 31));
+}
+
+// per row: exclusive popcount prefix per word + row total
+__global__ void __launch_bounds__(TPB) k_row_prefix(const unsigned* __restrict__ bitmap, int Kf, int words,
+                                                    int* __restrict__ word_prefix, int* __restrict__ row_count) {
+  const int a = blockIdx.x * TPB + threadIdx.x;
+  if (a >= Kf) return;
+  int run = 0;
+  for (int w = 0; w < words; w++) {
+    word_prefix[(size_t)a * words + w] = run;
+    run += __popc(bitmap[(size_t)a * words + w]);
+  }
+  row_count[a] = run;
+}
+
+__global__ void __launch_bounds__(TPB) k_fill_cols(const unsigned* __restrict__ bitmap, const int* __restrict__ word_prefix,
+                                                   const int* __restrict__ s_rowptr, int Kf, int words,
+                                                   int* __restrict__ s_col, int* __restrict__ s_row) {
+  const long long i = (long long)blockIdx.x * TPB + threadIdx.x;
+  if (i >= (long long)Kf * words) return;
+  const int a = (int)(i / words), w = (int)(i % words);
+  unsigned bits = bitmap[i];
+  int pos = s_rowptr[a] + word_prefix[i];
+  while (bits) {
+    const int b = __ffs(bits) - 1;
+    bits &= bits - 1;
+    s_col[pos] = w * 32 + b;
+    s_row[pos] = a;
+    pos++;
+  }
+}
+
+__device__ __forceinline__ int csr_pos(const unsigned* __restrict__ bitmap, const int* __restrict__ word_prefix,
+                                       const int* __restrict__ s_rowptr, int words, int a, int b) {
+  const size_t wi = (size_t)a * words + (b >> 5);
+  return s_rowptr[a] + word_prefix[wi] + __popc(bitmap[wi] & ((1u << (b & 31)) - 1u));
+}
+
+// count (fill == 0) or fill (fill == 1) the product lists of the upper blocks; one thread per local observation
+__global__ void __launch_bounds__(TPB) k_products(const int* __restrict__ o_kf, const int* __restrict__ o_lm,
+                                                  const int* __restrict__ lm_ptr, const int* __restrict__ pose_slot,
+                                                  const unsigned* __restrict__ bitmap, const int* __restrict__ word_prefix,
+                                                  const int* __restrict__ s_rowptr, const int* __restrict__ csr_u, int words,
+                                                  int E, int fill, unsigned* __restrict__ counters,
+                                                  const unsigned* __restrict__ u_prod_ptr, uint2* __restrict__ prod) {
+  const long long e = (long long)blockIdx.x * TPB + threadIdx.x;
+  if (e >= E) return;
+  const int a = pose_slot[o_kf[e]];
+  if (a < 0) return;
+  const int lm = o_lm[e];
+  const int beg = lm_ptr[lm], end = lm_ptr[lm + 1];
+  for (int o = beg; o < end; o++) {
+    const int b = pose_slot[o_kf[o]];
+    if (b < a || (b == a && o != (int)e)) continue;
+    const int u = csr_u[csr_pos(bitmap, word_prefix, s_rowptr, words, a, b)];
+    const unsigned slot = atomicAdd(counters + u, 1u);
+    if (fill) prod[u_prod_ptr[u] + slot] = make_uint2((unsigned)e, (unsigned)o);
+  }
+}
+
+__global__ void __launch_bounds__(TPB) k_apply_flags(const float* __restrict__ w_raw, const uint8_t* __restrict__ flags,
+                                                     int E, float* __restrict__ o_w) {
+  const long long e = (long long)blockIdx.x * TPB + threadIdx.x;
+  if (e >= E) return;
+  const uint8_t f = flags ? flags[e] : 0;
+  float w = (f & 1) ? 0.0f : w_raw[e];
+  if (f & 2) w = -w;  // -0.0f keeps the sign bit: inactive + no kernel
+  o_w[e] = w;
+}
+
+}  // namespace ba
+}  // namespace ccm

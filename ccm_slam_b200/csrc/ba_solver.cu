@@ -1,0 +1,808 @@
+// ba_solver.cu — host driver of the B200 bundle-adjustment path + its C ABI (include/ccm_b200.h).
+//
+// Control flow restates g2o's OptimizationAlgorithmLevenberg::solve + SparseOptimizer::optimize
+// (G/core/optimization_algorithm_levenberg.cpp:61-164, G/core/sparse_optimizer.cpp:354-419): the scalar LM schedule
+// (lambda, nu, rho, stop rules, force-stop flag polling) runs on the host, every O(E)/O(P)/O(K) step is a kernel from
+// ba_kernels.cuh on the handle's stream.  push/pop/discardTop become a (current, trial) double buffer.
+// Multi-GPU: landmarks (and their observations) are sharded across ranks; per LM iteration one all-reduce of
+// [Hpp | bp | chi2], per LM trial one all-reduce of [S upper blocks | bschur part] and one of [chi2, scale].
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <limits>
+#include <numeric>
+
+#include "ba_kernels.cuh"
+#include "common.cuh"
+
+namespace ccm {
+void allreduce_f64(double* buf, size_t count, int op, cudaStream_t s);  // runtime.cu ; op: 0 sum, 2 max
+}
+
+using namespace ccm;
+using namespace ccm::ba;
+
+namespace {
+template <typename T>
+void upload_vec(DevBuf<T>& b, const std::vector<T>& v, cudaStream_t s) {  // never a zero-sized allocation
+  b.alloc(std::max(v.size(), (size_t)1));
+  if (!v.empty()) CCM_CUDA(cudaMemcpyAsync(b.p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, s));
+}
+double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+}  // namespace
+
+struct ccm_ba_handle {
+  cudaStream_t stream = nullptr;
+  int device = 0;
+  int K = 0, P = 0, E = 0, Kf = 0;
+  int rank = 0, nranks = 1;
+  int L0 = 0, L1 = 0, Pl = 0, El = 0;
+  long long E0 = 0;
+  size_t Ep = 0;
+  bool sorted_input = true;
+  std::vector<int> perm;            // landmark-sorted position -> input edge index (only if !sorted_input)
+  std::vector<uint8_t> h_flags;     // local shard, sorted order
+  std::vector<int> h_pose_slot, h_slot_pose;
+  int words = 0, nub = 0;
+  long long nnzb = 0, nprod = 0;
+  // state
+  DevBuf<double> pose0, poseA, poseB, intr, pt0, ptA, ptB;
+  double *pose_cur = nullptr, *pose_trial = nullptr, *pt_cur = nullptr, *pt_trial = nullptr;
+  const double *pose_eval = nullptr, *pt_eval = nullptr;  // last state errors were evaluated on
+  DevBuf<int> pose_slot, slot_pose;
+  // observations (landmark order, local shard)
+  DevBuf<int> o_kf, o_lm, lm_ptr;
+  DevBuf<float2> o_uv;
+  DevBuf<float> o_w, o_w_raw;
+  DevBuf<uint8_t> d_flags;
+  // linear system
+  DevBuf<double> W, Z, HllBl, gvec;       // HllBl = [Hll 6*Pl | bl 3*Pl]
+  DevBuf<double> Hbuf;                    // [Hpp Kf*36 | bp Kf*6 | chi2_cur | maxdiag-bits]
+  DevBuf<double> Ubuf;                    // [U_val nub*36 | bneg Kf*6]
+  DevBuf<double> s_val, Minv, bschur;
+  DevBuf<int> s_rowptr, s_col, s_row, s_diag, csr_u, u_row, u_col, u_diag, word_prefix;
+  DevBuf<unsigned> bitmap, u_prod_ptr;
+  DevBuf<uint2> prod;
+  // pcg
+  DevBuf<double> x, pr, pz, pp, pq, pcg_partials, pcg_status, dxl;
+  DevBuf<unsigned> pcg_bar;
+  DevBuf<int> jac_fail;
+  int pcg_grid = 0;
+  // scalars / partials
+  DevBuf<double> partials, scal;  // scal: [0] chi2_trial [1] scale_l [2] scale_p [3..5] pcg status
+  double* h_scal = nullptr;       // pinned, 16 doubles
+  DevBuf<double> rep_chi2;
+  DevBuf<uint8_t> rep_depth;
+  int64_t device_bytes = 0;
+  double t_setup_ms = 0;
+
+  double* Hll() { return HllBl.p; }
+  double* bl() { return HllBl.p + (size_t)6 * Pl; }
+  double* Hpp() { return Hbuf.p; }
+  double* bp() { return Hbuf.p + (size_t)Kf * 36; }
+  double* chi2_cur_dev() { return Hbuf.p + (size_t)Kf * 42; }
+  double* U_val() { return Ubuf.p; }
+  double* bneg() { return Ubuf.p + (size_t)nub * 36; }
+
+  ~ccm_ba_handle() {
+    if (h_scal) cudaFreeHost(h_scal);
+    if (stream) cudaStreamDestroy(stream);
+  }
+};
+
+namespace {
+
+int grid_stride(long long n) {
+  long long g = (n + TPB - 1) / TPB;
+  const long long cap = (long long)sm_count() * 8;
+  if (g > cap) g = cap;
+  if (g < 1) g = 1;
+  return (int)g;
+}
+
+void sum_partials_to(ccm_ba_handle* h, int n, double* out) {
+  k_sum_partials<<<1, 1024, 0, h->stream>>>(h->partials.p, n, out);
+  CCM_LAUNCHED();
+}
+
+// ---- kernels wrapped as steps --------------------------------------------------------------------------------
+void step_linearize(ccm_ba_handle* h, int robust, double delta) {
+  cudaStream_t s = h->stream;
+  CCM_CUDA(cudaMemsetAsync(h->HllBl.p, 0, h->HllBl.bytes(), s));
+  const int g = grid_stride(h->El);
+  k_linearize<<<g, TPB, 0, s>>>(h->o_kf.p, h->o_lm.p, h->o_uv.p, h->o_w.p, h->pose_cur, h->intr.p, h->pose_slot.p,
+                                h->pt_cur, h->El, h->Ep, h->Pl, robust, delta, h->W.p, h->Hll(), h->bl(), h->partials.p);
+  CCM_LAUNCHED();
+  sum_partials_to(h, g, h->chi2_cur_dev());
+  if (h->Kf > 0) {
+    k_pose_pass<<<h->Kf, 128, 0, s>>>(h->prod.p, h->u_prod_ptr.p, h->u_diag.p, h->slot_pose.p, h->o_lm.p, h->o_uv.p,
+                                      h->o_w.p, h->pose_cur, h->intr.p, h->pt_cur, robust, delta, h->Hpp(), h->bp());
+    CCM_LAUNCHED();
+  }
+  if (h->nranks > 1) allreduce_f64(h->Hbuf.p, (size_t)h->Kf * 42 + 1, 0, s);
+  h->pose_eval = h->pose_cur;
+  h->pt_eval = h->pt_cur;
+}
+
+double step_max_diag(ccm_ba_handle* h) {
+  cudaStream_t s = h->stream;
+  double* slot = h->Hbuf.p + (size_t)h->Kf * 42 + 1;
+  CCM_CUDA(cudaMemsetAsync(slot, 0, sizeof(double), s));
+  k_max_diag<<<grid_stride((long long)h->Kf * 6 + (long long)h->Pl * 3), TPB, 0, s>>>(
+      h->Hpp(), h->Kf, h->Hll(), h->Pl, reinterpret_cast<unsigned long long*>(slot));
+  CCM_LAUNCHED();
+  if (h->nranks > 1) allreduce_f64(slot, 1, 2, s);
+  CCM_CUDA(cudaMemcpyAsync(h->h_scal + 8, h->chi2_cur_dev(), 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  CCM_CUDA(cudaStreamSynchronize(s));
+  return h->h_scal[9];
+}
+
+double read_chi2_cur(ccm_ba_handle* h) {
+  CCM_CUDA(cudaMemcpyAsync(h->h_scal + 8, h->chi2_cur_dev(), sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+  CCM_CUDA(cudaStreamSynchronize(h->stream));
+  return h->h_scal[8];
+}
+
+void step_scale(ccm_ba_handle* h, double lambda) {
+  if (h->El == 0) return;
+  k_scale<<<div_up(h->El, TPB), TPB, 0, h->stream>>>(h->o_lm.p, h->W.p, h->Ep, h->Hll(), h->bl(), h->Pl, h->El, lambda,
+                                                     h->Z.p, h->gvec.p);
+  CCM_LAUNCHED();
+}
+
+void step_schur(ccm_ba_handle* h) {
+  k_schur<<<div_up((long long)h->nub * 32, TPB), TPB, 0, h->stream>>>(h->prod.p, h->u_prod_ptr.p, h->u_row.p, h->u_col.p,
+                                                                      h->nub, h->Z.p, h->o_lm.p, h->gvec.p, h->U_val(),
+                                                                      h->bneg());
+  CCM_LAUNCHED();
+}
+
+void step_finalize(ccm_ba_handle* h, double lambda) {
+  cudaStream_t s = h->stream;
+  if (h->nranks > 1) allreduce_f64(h->Ubuf.p, (size_t)h->nub * 36 + (size_t)h->Kf * 6, 0, s);
+  k_finalize_S<<<div_up(h->nnzb * 36, TPB), TPB, 0, s>>>(h->s_row.p, h->s_col.p, h->csr_u.p, h->nnzb, h->U_val(), h->Hpp(),
+                                                         lambda, h->s_val.p);
+  CCM_LAUNCHED();
+  CCM_CUDA(cudaMemsetAsync(h->jac_fail.p, 0, sizeof(int), s));
+  k_block_jacobi<<<div_up(h->Kf, 128), 128, 0, s>>>(h->s_diag.p, h->s_val.p, h->bp(), h->bneg(), h->Kf, h->Minv.p,
+                                                    h->bschur.p, h->jac_fail.p);
+  CCM_LAUNCHED();
+}
+
+void step_pcg(ccm_ba_handle* h, double tol, int max_iter) {
+  cudaStream_t s = h->stream;
+  CCM_CUDA(cudaMemsetAsync(h->pcg_bar.p, 0, sizeof(unsigned), s));
+  PcgArgs a;
+  a.n = h->Kf; a.rowptr = h->s_rowptr.p; a.col = h->s_col.p; a.val = h->s_val.p; a.Minv = h->Minv.p; a.b = h->bschur.p;
+  a.x = h->x.p; a.r = h->pr.p; a.z = h->pz.p; a.p = h->pp.p; a.q = h->pq.p;
+  a.partials = h->pcg_partials.p; a.bar = h->pcg_bar.p; a.tol = tol; a.max_iter = max_iter; a.status = h->pcg_status.p;
+  void* args[] = {&a};
+  CCM_CUDA(cudaLaunchCooperativeKernel((void*)k_pcg, dim3(h->pcg_grid), dim3(TPB), args, 0, s));
+  CCM_LAUNCHED();
+}
+
+// trial state + gain-ratio denominator + chi2 of the trial state -> scal[0..5]
+void step_update_and_residual(ccm_ba_handle* h, double lambda, int robust, double delta, double* dx_points) {
+  cudaStream_t s = h->stream;
+  const int g1 = grid_stride(h->K);
+  k_update_poses<<<g1, TPB, 0, s>>>(h->pose_cur, h->pose_slot.p, h->x.p, h->bp(), h->K, lambda, h->pose_trial, h->partials.p);
+  CCM_LAUNCHED();
+  sum_partials_to(h, g1, h->scal.p + 2);
+  const int g2 = grid_stride(h->Pl);
+  k_backsub_points<<<g2, TPB, 0, s>>>(h->lm_ptr.p, h->o_kf.p, h->pose_slot.p, h->Z.p, h->Hll(), h->bl(), h->x.p, h->pt_cur,
+                                      h->Pl, lambda, h->pt_trial, dx_points, h->partials.p);
+  CCM_LAUNCHED();
+  sum_partials_to(h, g2, h->scal.p + 1);
+  const int g3 = grid_stride(h->El);
+  k_residual<<<g3, TPB, 0, s>>>(h->o_kf.p, h->o_lm.p, h->o_uv.p, h->o_w.p, h->pose_trial, h->intr.p, h->pt_trial, h->El,
+                                robust, delta, h->partials.p);
+  CCM_LAUNCHED();
+  sum_partials_to(h, g3, h->scal.p + 0);
+  if (h->nranks > 1) allreduce_f64(h->scal.p, 2, 0, s);
+  h->pose_eval = h->pose_trial;
+  h->pt_eval = h->pt_trial;
+}
+
+// ---- structure ------------------------------------------------------------------------------------------------
+void build(ccm_ba_handle* h, const ccm_ba_problem* p) {
+  const double T0 = now_ms();
+  ensure_device();
+  h->device = current_device();
+  CCM_CUDA(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CCM_CUDA(cudaMallocHost((void**)&h->h_scal, 16 * sizeof(double)));
+  cudaStream_t s = h->stream;
+  CCM_REQUIRE(p && p->K > 0 && p->P >= 0 && p->E >= 0, "ccm_ba_create: bad sizes");
+  CCM_REQUIRE(p->poses && p->intr && p->fixed && (p->P == 0 || p->points), "ccm_ba_create: null pose/point arrays");
+  CCM_REQUIRE(p->E == 0 || (p->obs_kf && p->obs_mp && p->obs_uv && p->obs_w), "ccm_ba_create: null observation arrays");
+  h->K = p->K; h->P = p->P; h->E = p->E;
+  h->rank = comm().rank; h->nranks = comm().nranks;
+  const int K = p->K, P = p->P, E = p->E;
+
+  // observations must be grouped by landmark (the reference adds edges landmark by landmark); sort if they are not
+  bool sorted = true;
+  for (int e = 0; e < E; e++) {
+    CCM_REQUIRE(p->obs_kf[e] >= 0 && p->obs_kf[e] < K && p->obs_mp[e] >= 0 && p->obs_mp[e] < P,
+                "ccm_ba_create: observation index out of range");
+    if (e && p->obs_mp[e] < p->obs_mp[e - 1]) sorted = false;
+  }
+  std::vector<int> g_lm_ptr((size_t)P + 1, 0);
+  for (int e = 0; e < E; e++) g_lm_ptr[p->obs_mp[e] + 1]++;
+  for (int l = 0; l < P; l++) g_lm_ptr[l + 1] += g_lm_ptr[l];
+  h->sorted_input = sorted;
+  std::vector<int> g_kf((size_t)E), g_lm((size_t)E);
+  if (sorted) {
+    std::copy(p->obs_kf, p->obs_kf + E, g_kf.begin());
+    std::copy(p->obs_mp, p->obs_mp + E, g_lm.begin());
+  } else {
+    h->perm.resize(E);
+    std::vector<int> cur(g_lm_ptr.begin(), g_lm_ptr.end() - 1);
+    for (int e = 0; e < E; e++) h->perm[cur[p->obs_mp[e]]++] = e;
+    for (int i = 0; i < E; i++) { g_kf[i] = p->obs_kf[h->perm[i]]; g_lm[i] = p->obs_mp[h->perm[i]]; }
+  }
+  auto src = [&](long long i) { return sorted ? i : (long long)h->perm[i]; };
+
+  // landmark shard of this rank: contiguous landmark range balanced by observation count
+  auto cut = [&](int r) {
+    if (r <= 0) return 0;
+    if (r >= h->nranks) return P;
+    const long long target = (long long)E * r / h->nranks;
+    return (int)(std::lower_bound(g_lm_ptr.begin(), g_lm_ptr.end(), (int)target) - g_lm_ptr.begin());
+  };
+  h->L0 = std::min(cut(h->rank), P); h->L1 = std::min(std::max(cut(h->rank + 1), h->L0), P);
+  h->Pl = h->L1 - h->L0;
+  h->E0 = g_lm_ptr[h->L0];
+  h->El = g_lm_ptr[h->L1] - g_lm_ptr[h->L0];
+  h->Ep = ((size_t)h->El + 31) / 32 * 32;
+  const int Pl = h->Pl, El = h->El;
+
+  // free poses
+  h->h_pose_slot.assign(K, -1);
+  for (int k = 0; k < K; k++)
+    if (!p->fixed[k]) { h->h_pose_slot[k] = (int)h->h_slot_pose.size(); h->h_slot_pose.push_back(k); }
+  h->Kf = (int)h->h_slot_pose.size();
+  const int Kf = h->Kf;
+
+  // ---- uploads
+  h->pose0.upload(p->poses, (size_t)K * 7, s);
+  h->poseA.alloc((size_t)K * 7); h->poseB.alloc((size_t)K * 7);
+  h->intr.upload(p->intr, (size_t)K * 4, s);
+  h->pose_slot.upload(h->h_pose_slot.data(), K, s);
+  upload_vec(h->slot_pose, h->h_slot_pose, s);
+  h->pt0.alloc(std::max((size_t)Pl * 3, (size_t)1));
+  if (Pl) CCM_CUDA(cudaMemcpyAsync(h->pt0.p, p->points + 3 * (size_t)h->L0, sizeof(double) * 3 * Pl, cudaMemcpyHostToDevice, s));
+  h->ptA.alloc(std::max((size_t)Pl * 3, (size_t)1)); h->ptB.alloc(std::max((size_t)Pl * 3, (size_t)1));
+  std::vector<int> l_kf(El), l_lm(El), l_ptr((size_t)Pl + 1);
+  std::vector<float2> l_uv(El);
+  std::vector<float> l_w(El);
+  h->h_flags.assign(El, 0);
+  for (int i = 0; i < El; i++) {
+    const long long gi = h->E0 + i, si = src(gi);
+    l_kf[i] = g_kf[gi];
+    l_lm[i] = g_lm[gi] - h->L0;
+    l_uv[i] = make_float2(p->obs_uv[2 * si], p->obs_uv[2 * si + 1]);
+    l_w[i] = p->obs_w[si];
+    CCM_REQUIRE(l_w[i] >= 0.0f, "ccm_ba_create: negative information weight");
+    if (p->edge_flags) h->h_flags[i] = p->edge_flags[si];
+  }
+  for (int l = 0; l <= Pl; l++) l_ptr[l] = g_lm_ptr[h->L0 + l] - (int)h->E0;
+  upload_vec(h->o_kf, l_kf, s); upload_vec(h->o_lm, l_lm, s); upload_vec(h->lm_ptr, l_ptr, s);
+  upload_vec(h->o_uv, l_uv, s); upload_vec(h->o_w_raw, l_w, s);
+  h->o_w.alloc(std::max(El, 1)); h->d_flags.alloc(std::max(El, 1));
+  if (El) {
+    h->d_flags.upload(h->h_flags.data(), El, s);
+    k_apply_flags<<<div_up(El, TPB), TPB, 0, s>>>(h->o_w_raw.p, h->d_flags.p, El, h->o_w.p);
+    CCM_LAUNCHED();
+  }
+
+  // ---- covisibility bitmap over ALL observations (every rank needs the global pattern of S)
+  h->words = (Kf + 31) / 32;
+  const int words = std::max(h->words, 1);
+  h->words = words;
+  h->bitmap.alloc_zero((size_t)std::max(Kf, 1) * words, s);
+  h->word_prefix.alloc((size_t)std::max(Kf, 1) * words);
+  DevBuf<int> row_count; row_count.alloc(std::max(Kf, 1));
+  {
+    DevBuf<int> d_gkf, d_glm, d_gptr;
+    const int *pk, *pl, *pp_;
+    if (h->nranks == 1) { pk = h->o_kf.p; pl = h->o_lm.p; pp_ = h->lm_ptr.p; }
+    else {
+      d_gkf.upload(g_kf.data(), E, s); d_glm.upload(g_lm.data(), E, s); d_gptr.upload(g_lm_ptr.data(), (size_t)P + 1, s);
+      pk = d_gkf.p; pl = d_glm.p; pp_ = d_gptr.p;
+    }
+    if (Kf > 0) {
+      if (E > 0) {
+        k_pattern_bitmap<<<div_up(E, TPB), TPB, 0, s>>>(pk, pl, pp_, h->pose_slot.p, E, words, h->bitmap.p);
+        CCM_LAUNCHED();
+      }
+      k_set_diag_bits<<<div_up(Kf, TPB), TPB, 0, s>>>(Kf, words, h->bitmap.p);
+      CCM_LAUNCHED();
+      k_row_prefix<<<div_up(Kf, TPB), TPB, 0, s>>>(h->bitmap.p, Kf, words, h->word_prefix.p, row_count.p);
+      CCM_LAUNCHED();
+    }
+    CCM_CUDA(cudaStreamSynchronize(s));  // temporaries die here
+  }
+  std::vector<int> h_rowptr((size_t)Kf + 1, 0);
+  if (Kf > 0) {
+    std::vector<int> cnt(Kf);
+    row_count.download(cnt.data(), Kf, s);
+    CCM_CUDA(cudaStreamSynchronize(s));
+    long long run = 0;
+    for (int a = 0; a < Kf; a++) { h_rowptr[a] = (int)run; run += cnt[a]; CCM_REQUIRE(run < (1ll << 31), "S pattern too large"); }
+    h_rowptr[Kf] = (int)run;
+  }
+  h->nnzb = h_rowptr[Kf];
+  const long long nnzb = h->nnzb;
+  upload_vec(h->s_rowptr, h_rowptr, s);
+  h->s_col.alloc(std::max<long long>(nnzb, 1)); h->s_row.alloc(std::max<long long>(nnzb, 1));
+  if (Kf > 0) {
+    k_fill_cols<<<div_up((long long)Kf * words, TPB), TPB, 0, s>>>(h->bitmap.p, h->word_prefix.p, h->s_rowptr.p, Kf, words,
+                                                                  h->s_col.p, h->s_row.p);
+    CCM_LAUNCHED();
+  }
+  // upper-block numbering, mirror map, diagonal positions (host, O(nnzb log))
+  std::vector<int> h_col(nnzb), h_csr_u(nnzb), h_urow, h_ucol, h_udiag(std::max(Kf, 1), 0), h_sdiag(std::max(Kf, 1), 0);
+  if (nnzb) { h->s_col.download(h_col.data(), nnzb, s); CCM_CUDA(cudaStreamSynchronize(s)); }
+  for (int a = 0; a < Kf; a++)
+    for (int q = h_rowptr[a]; q < h_rowptr[a + 1]; q++) {
+      const int b = h_col[q];
+      if (b >= a) {
+        h_csr_u[q] = (int)h_urow.size();
+        if (b == a) { h_udiag[a] = (int)h_urow.size(); h_sdiag[a] = q; }
+        h_urow.push_back(a); h_ucol.push_back(b);
+      }
+    }
+  for (int a = 0; a < Kf; a++)
+    for (int q = h_rowptr[a]; q < h_rowptr[a + 1]; q++) {
+      const int b = h_col[q];
+      if (b < a) {
+        const int* bb = h_col.data() + h_rowptr[b];
+        const int* ee = h_col.data() + h_rowptr[b + 1];
+        const int* it = std::lower_bound(bb, ee, a);
+        CCM_REQUIRE(it != ee && *it == a, "internal: asymmetric covisibility pattern");
+        h_csr_u[q] = h_csr_u[it - h_col.data()];
+      }
+    }
+  h->nub = (int)h_urow.size();
+  const int nub = h->nub;
+  upload_vec(h->csr_u, h_csr_u, s);
+  upload_vec(h->u_row, h_urow, s); upload_vec(h->u_col, h_ucol, s);
+  upload_vec(h->u_diag, h_udiag, s); upload_vec(h->s_diag, h_sdiag, s);
+
+  // ---- Schur product lists (local shard)
+  DevBuf<unsigned> counters; counters.alloc_zero(std::max(nub, 1), s);
+  std::vector<unsigned> h_pp((size_t)nub + 1, 0);
+  if (El && nub) {
+    k_products<<<div_up(El, TPB), TPB, 0, s>>>(h->o_kf.p, h->o_lm.p, h->lm_ptr.p, h->pose_slot.p, h->bitmap.p,
+                                               h->word_prefix.p, h->s_rowptr.p, h->csr_u.p, words, El, 0, counters.p,
+                                               nullptr, nullptr);
+    CCM_LAUNCHED();
+    std::vector<unsigned> c(nub);
+    counters.download(c.data(), nub, s);
+    CCM_CUDA(cudaStreamSynchronize(s));
+    unsigned long long run = 0;
+    for (int u = 0; u < nub; u++) { h_pp[u] = (unsigned)run; run += c[u]; }
+    CCM_REQUIRE(run < (1ull << 32), "too many Schur products for 32-bit offsets");
+    h_pp[nub] = (unsigned)run;
+  }
+  h->nprod = h_pp[nub];
+  upload_vec(h->u_prod_ptr, h_pp, s);
+  h->prod.alloc(std::max<long long>(h->nprod, 1));
+  if (h->nprod) {
+    CCM_CUDA(cudaMemsetAsync(counters.p, 0, sizeof(unsigned) * nub, s));
+    k_products<<<div_up(El, TPB), TPB, 0, s>>>(h->o_kf.p, h->o_lm.p, h->lm_ptr.p, h->pose_slot.p, h->bitmap.p,
+                                               h->word_prefix.p, h->s_rowptr.p, h->csr_u.p, words, El, 1, counters.p,
+                                               h->u_prod_ptr.p, h->prod.p);
+    CCM_LAUNCHED();
+  }
+
+  // ---- linear-system storage
+  h->W.alloc(std::max(h->Ep * 18, (size_t)1)); h->Z.alloc(std::max((size_t)El * 18, (size_t)2));
+  h->HllBl.alloc(std::max((size_t)Pl * 9, (size_t)1)); h->gvec.alloc(std::max((size_t)Pl * 3, (size_t)1));
+  h->Hbuf.alloc_zero((size_t)Kf * 42 + 2, s);
+  h->Ubuf.alloc_zero((size_t)nub * 36 + (size_t)Kf * 6 + 1, s);
+  h->s_val.alloc(std::max<long long>(nnzb * 36, 1)); h->Minv.alloc(std::max((size_t)Kf * 36, (size_t)1));
+  h->bschur.alloc(std::max((size_t)Kf * 6, (size_t)1));
+  const size_t nv = std::max((size_t)Kf * 6, (size_t)1);
+  h->x.alloc_zero(nv, s); h->pr.alloc(nv); h->pz.alloc(nv); h->pp.alloc(nv); h->pq.alloc(nv);
+  h->dxl.alloc(std::max((size_t)Pl * 3, (size_t)1));
+  h->pcg_status.alloc_zero(4, s); h->pcg_bar.alloc_zero(1, s); h->jac_fail.alloc_zero(1, s);
+  int per_sm = 0;
+  CCM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg, TPB, 0));
+  per_sm = std::max(1, std::min(per_sm, env_int("CCM_PCG_BLOCKS_PER_SM", 4)));
+  h->pcg_grid = std::max(1, std::min(per_sm * sm_count(), div_up((long long)std::max(Kf, 1) * 32, TPB)));
+  h->pcg_partials.alloc((size_t)3 * h->pcg_grid);
+  h->partials.alloc((size_t)sm_count() * 8 + 8);
+  h->scal.alloc_zero(16, s);
+  h->rep_chi2.alloc(std::max(El, 1)); h->rep_depth.alloc(std::max(El, 1));
+
+  h->pose_cur = h->poseA.p; h->pose_trial = h->poseB.p; h->pt_cur = h->ptA.p; h->pt_trial = h->ptB.p;
+  CCM_CUDA(cudaMemcpyAsync(h->pose_cur, h->pose0.p, h->pose0.bytes(), cudaMemcpyDeviceToDevice, s));
+  CCM_CUDA(cudaMemcpyAsync(h->pose_trial, h->pose0.p, h->pose0.bytes(), cudaMemcpyDeviceToDevice, s));
+  if (Pl) CCM_CUDA(cudaMemcpyAsync(h->pt_cur, h->pt0.p, sizeof(double) * 3 * Pl, cudaMemcpyDeviceToDevice, s));
+  if (Pl) CCM_CUDA(cudaMemcpyAsync(h->pt_trial, h->pt0.p, sizeof(double) * 3 * Pl, cudaMemcpyDeviceToDevice, s));
+  h->pose_eval = h->pose_cur; h->pt_eval = h->pt_cur;
+  CCM_CUDA(cudaStreamSynchronize(s));
+  h->device_bytes = (int64_t)(h->W.bytes() + h->Z.bytes() + h->prod.bytes() + h->s_val.bytes() + h->Ubuf.bytes() +
+                              h->bitmap.bytes() + h->word_prefix.bytes() + h->HllBl.bytes() + h->o_kf.bytes() * 2 +
+                              h->o_uv.bytes() + h->o_w.bytes() * 2 + h->ptA.bytes() * 3);
+  h->t_setup_ms = now_ms() - T0;
+}
+
+void do_reset(ccm_ba_handle* h) {
+  cudaStream_t s = h->stream;
+  CCM_CUDA(cudaMemcpyAsync(h->pose_cur, h->pose0.p, h->pose0.bytes(), cudaMemcpyDeviceToDevice, s));
+  if (h->Pl) CCM_CUDA(cudaMemcpyAsync(h->pt_cur, h->pt0.p, sizeof(double) * 3 * h->Pl, cudaMemcpyDeviceToDevice, s));
+  h->pose_eval = h->pose_cur; h->pt_eval = h->pt_cur;
+  CCM_CUDA(cudaStreamSynchronize(s));
+}
+
+void download_state(ccm_ba_handle* h, ccm_ba_result* r) {
+  cudaStream_t s = h->stream;
+  if (r->poses) CCM_CUDA(cudaMemcpyAsync(r->poses, h->pose_cur, sizeof(double) * 7 * h->K, cudaMemcpyDeviceToHost, s));
+  if (r->points && h->P) {
+    if (h->nranks == 1) {
+      CCM_CUDA(cudaMemcpyAsync(r->points, h->pt_cur, sizeof(double) * 3 * h->Pl, cudaMemcpyDeviceToHost, s));
+    } else {  // every rank returns the full point set: scatter own shard into a zeroed P*3 buffer and all-reduce
+      DevBuf<double> full; full.alloc_zero((size_t)h->P * 3, s);
+      if (h->Pl) CCM_CUDA(cudaMemcpyAsync(full.p + 3 * (size_t)h->L0, h->pt_cur, sizeof(double) * 3 * h->Pl, cudaMemcpyDeviceToDevice, s));
+      allreduce_f64(full.p, (size_t)h->P * 3, 0, s);
+      full.download(r->points, (size_t)h->P * 3, s);
+      CCM_CUDA(cudaStreamSynchronize(s));
+    }
+  }
+  if ((r->chi2 || r->depth_pos) && h->El) {
+    k_edge_report<<<div_up(h->El, TPB), TPB, 0, s>>>(h->o_kf.p, h->o_lm.p, h->o_uv.p, h->o_w_raw.p, h->pose_eval, h->pt_eval,
+                                                     h->pose_cur, h->pt_cur, h->intr.p, h->El, h->rep_chi2.p, h->rep_depth.p);
+    CCM_LAUNCHED();
+    std::vector<double> c(h->El);
+    std::vector<uint8_t> d(h->El);
+    h->rep_chi2.download(c.data(), h->El, s); h->rep_depth.download(d.data(), h->El, s);
+    CCM_CUDA(cudaStreamSynchronize(s));
+    for (int i = 0; i < h->El; i++) {
+      const long long gi = h->E0 + i;
+      const long long e = h->sorted_input ? gi : (long long)h->perm[gi];
+      if (r->chi2 && !(h->h_flags[i] & 1)) r->chi2[e] = c[i];
+      if (r->depth_pos) r->depth_pos[e] = d[i];
+    }
+  }
+  CCM_CUDA(cudaStreamSynchronize(s));
+}
+
+void optimize(ccm_ba_handle* h, const ccm_ba_options* o, ccm_ba_result* r) {
+  CCM_CUDA(cudaSetDevice(h->device));
+  const double T0 = now_ms();
+  cudaStream_t s = h->stream;
+  const int robust = o->robust ? 1 : 0;
+  const double delta = o->huber_delta;
+  const int max_trials = o->max_trials > 0 ? o->max_trials : 10;
+  const int pcg_max = o->pcg_max_iter > 0 ? o->pcg_max_iter : 2000;
+  const double pcg_tol = o->pcg_tol > 0 ? o->pcg_tol : 1e-10;
+  r->trace_len = 0; r->iters_done = 0; r->trials_total = 0; r->pcg_iters_total = 0; r->pcg_not_converged = 0;
+  r->chi2_initial = r->chi2_final = 0; r->lambda_final = 0;
+  auto terminate = [&]() { return o->stop && *o->stop; };
+  int ret_iters = 0;
+  if (h->Kf == 0 || h->E == 0) {
+    // g2o: landmarks-only graphs are still optimised, but every cslam call site has free poses; keep it simple
+    ret_iters = h->E == 0 ? -1 : 0;
+  }
+  double lambda = -1, ni = 2;
+  int nBad = 0;
+  bool ok = true;
+  for (int it = 0; h->Kf > 0 && h->E > 0 && it < o->iterations && !terminate() && ok; it++) {
+    step_linearize(h, robust, delta);
+    double currentChi;
+    if (it == 0) {
+      const double maxdiag = step_max_diag(h);
+      currentChi = h->h_scal[8];
+      lambda = o->lambda_init > 0 ? o->lambda_init : 1e-5 * maxdiag;
+      ni = 2; nBad = 0;
+      r->chi2_initial = currentChi;
+    } else {
+      currentChi = read_chi2_cur(h);
+    }
+    const double iniChi = currentChi;
+    double tempChi = currentChi, rho = 0, lambda_used = lambda;
+    int qmax = 0, last_pcg_it = 0;
+    double last_relres = 0;
+    do {
+      lambda_used = lambda;
+      step_scale(h, lambda);
+      step_schur(h);
+      step_finalize(h, lambda);
+      step_pcg(h, pcg_tol, pcg_max);
+      step_update_and_residual(h, lambda, robust, delta, nullptr);
+      CCM_CUDA(cudaMemcpyAsync(h->h_scal, h->scal.p, 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+      CCM_CUDA(cudaMemcpyAsync(h->h_scal + 3, h->pcg_status.p, 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+      CCM_CUDA(cudaMemcpyAsync(h->h_scal + 6, h->jac_fail.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+      CCM_CUDA(cudaStreamSynchronize(s));
+      tempChi = h->h_scal[0];
+      const int pcg_it = (int)h->h_scal[3];
+      const int pcg_flag = (int)h->h_scal[5];
+      int jfail;
+      memcpy(&jfail, h->h_scal + 6, sizeof(int));
+      last_pcg_it = pcg_it; last_relres = h->h_scal[4];
+      r->pcg_iters_total += pcg_it;
+      if (pcg_flag == 1) r->pcg_not_converged++;
+      const bool ok2 = !(pcg_flag == 2 || jfail);  // linear solve failed (not SPD): the trial is rejected
+      if (!ok2) tempChi = std::numeric_limits<double>::max();
+      rho = currentChi - tempChi;
+      double scale = h->h_scal[1] + h->h_scal[2];
+      scale += 1e-3;
+      rho /= scale;
+      if (rho > 0 && std::isfinite(tempChi)) {
+        double alpha = 1. - std::pow((2 * rho - 1), 3);
+        alpha = std::min(alpha, 2. / 3.);
+        const double scaleFactor = std::max(1. / 3., alpha);
+        lambda *= scaleFactor;
+        ni = 2;
+        currentChi = tempChi;
+        std::swap(h->pose_cur, h->pose_trial);  // discardTop: the trial state becomes the estimate
+        std::swap(h->pt_cur, h->pt_trial);
+      } else {
+        lambda *= ni;
+        ni *= 2;  // pop: the estimate stays
+      }
+      qmax++;
+      r->trials_total++;
+    } while (rho < 0 && qmax < max_trials && !terminate());
+    ret_iters++;
+    if (r->trace && r->trace_len < r->trace_cap) {
+      double* tr = r->trace + (size_t)r->trace_len * CCM_TRACE_COLS;
+      tr[0] = it; tr[1] = lambda_used; tr[2] = currentChi; tr[3] = rho; tr[4] = qmax; tr[5] = lambda;
+      tr[6] = last_pcg_it; tr[7] = last_relres;
+      r->trace_len++;
+    }
+    r->chi2_final = currentChi; r->lambda_final = lambda;
+    if (qmax == max_trials || rho == 0) { ok = false; continue; }
+    if ((iniChi - currentChi) * 1e3 < iniChi) nBad++; else nBad = 0;
+    if (nBad >= 3) { ok = false; continue; }
+  }
+  r->iters_done = ret_iters;
+  CCM_CUDA(cudaStreamSynchronize(s));
+  r->t_optimize_ms = now_ms() - T0;
+  const double T1 = now_ms();
+  download_state(h, r);
+  r->t_download_ms = now_ms() - T1;
+  r->t_setup_ms = h->t_setup_ms;
+}
+
+}  // namespace
+
+// ---- C ABI ------------------------------------------------------------------------------------------------------
+extern "C" int ccm_ba_create(const ccm_ba_problem* p, ccm_ba_handle** out) {
+  return guarded([&] {
+    CCM_REQUIRE(out, "ccm_ba_create: out is NULL");
+    *out = nullptr;
+    ccm_ba_handle* h = new ccm_ba_handle();
+    try {
+      build(h, p);
+    } catch (...) {
+      delete h;
+      throw;
+    }
+    *out = h;
+  });
+}
+
+extern "C" void ccm_ba_destroy(ccm_ba_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  delete h;
+}
+
+extern "C" int ccm_ba_reset(ccm_ba_handle* h) {
+  return guarded([&] { CCM_REQUIRE(h, "null handle"); CCM_CUDA(cudaSetDevice(h->device)); do_reset(h); });
+}
+
+extern "C" int ccm_ba_set_edge_flags(ccm_ba_handle* h, const uint8_t* edge_flags) {
+  return guarded([&] {
+    CCM_REQUIRE(h, "null handle");
+    CCM_CUDA(cudaSetDevice(h->device));
+    for (int i = 0; i < h->El; i++) {
+      const long long gi = h->E0 + i;
+      h->h_flags[i] = edge_flags ? edge_flags[h->sorted_input ? gi : (long long)h->perm[gi]] : 0;
+    }
+    if (h->El) {
+      h->d_flags.upload(h->h_flags.data(), h->El, h->stream);
+      k_apply_flags<<<div_up(h->El, TPB), TPB, 0, h->stream>>>(h->o_w_raw.p, h->d_flags.p, h->El, h->o_w.p);
+      CCM_LAUNCHED();
+      CCM_CUDA(cudaStreamSynchronize(h->stream));
+    }
+  });
+}
+
+extern "C" int ccm_ba_optimize(ccm_ba_handle* h, const ccm_ba_options* o, ccm_ba_result* r) {
+  return guarded([&] { CCM_REQUIRE(h && o && r, "null argument"); optimize(h, o, r); });
+}
+
+extern "C" int ccm_ba_solve(const ccm_ba_problem* p, const ccm_ba_options* o, ccm_ba_result* r) {
+  ccm_ba_handle* h = nullptr;
+  int rc = ccm_ba_create(p, &h);
+  if (rc != CCM_OK) return rc;
+  rc = ccm_ba_optimize(h, o, r);
+  ccm_ba_destroy(h);
+  return rc;
+}
+
+extern "C" int ccm_ba_get_info(const ccm_ba_handle* h, ccm_ba_info* info) {
+  return guarded([&] {
+    CCM_REQUIRE(h && info, "null argument");
+    info->K = h->K; info->K_free = h->Kf; info->P_local = h->Pl; info->E_local = h->El; info->rank = h->rank;
+    info->nranks = h->nranks; info->s_blocks_upper = h->nub; info->s_blocks_full = h->nnzb;
+    info->schur_products = h->nprod; info->device_bytes = h->device_bytes;
+  });
+}
+
+extern "C" int ccm_ba_debug_build(ccm_ba_handle* h, int robust, double huber_delta, double* Hpp, double* bp, double* Hll,
+                                  double* bl, double* W, double* chi2_robust_sum) {
+  return guarded([&] {
+    CCM_REQUIRE(h, "null handle");
+    CCM_REQUIRE(h->nranks == 1, "debug entry points are single-rank");
+    CCM_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    step_linearize(h, robust, huber_delta);
+    const int K = h->K, Kf = h->Kf, Pl = h->Pl, El = h->El;
+    std::vector<double> hH((size_t)Kf * 42 + 1), hL((size_t)Pl * 9), hW(h->Ep * 18);
+    h->Hbuf.download(hH.data(), hH.size(), s); h->HllBl.download(hL.data(), hL.size(), s); h->W.download(hW.data(), hW.size(), s);
+    CCM_CUDA(cudaStreamSynchronize(s));
+    if (Hpp) memset(Hpp, 0, sizeof(double) * 36 * K);
+    if (bp) memset(bp, 0, sizeof(double) * 6 * K);
+    for (int a = 0; a < Kf; a++) {
+      if (Hpp) memcpy(Hpp + 36 * (size_t)h->h_slot_pose[a], hH.data() + (size_t)a * 36, 36 * sizeof(double));
+      if (bp) memcpy(bp + 6 * (size_t)h->h_slot_pose[a], hH.data() + (size_t)Kf * 36 + (size_t)a * 6, 6 * sizeof(double));
+    }
+    static const int ut[9] = {0, 1, 2, 1, 3, 4, 2, 4, 5};
+    for (int l = 0; l < Pl; l++) {
+      if (Hll) for (int i = 0; i < 9; i++) Hll[9 * (size_t)l + i] = hL[(size_t)ut[i] * Pl + l];
+      if (bl) for (int i = 0; i < 3; i++) bl[3 * (size_t)l + i] = hL[(size_t)(6 + i) * Pl + l];
+    }
+    if (W)
+      for (int i = 0; i < El; i++) {
+        const long long e = h->sorted_input ? i : (long long)h->perm[i];
+        for (int c = 0; c < 18; c++) W[18 * (size_t)e + c] = hW[(size_t)c * h->Ep + i];
+      }
+    if (chi2_robust_sum) *chi2_robust_sum = hH[(size_t)Kf * 42];
+  });
+}
+
+extern "C" int ccm_ba_debug_schur(ccm_ba_handle* h, int robust, double huber_delta, double lambda, double* S_dense,
+                                  double* bschur, double* dx_pose, double* dx_point, int32_t* pcg_iters, double* pcg_relres) {
+  return guarded([&] {
+    CCM_REQUIRE(h, "null handle");
+    CCM_REQUIRE(h->nranks == 1, "debug entry points are single-rank");
+    CCM_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    step_linearize(h, robust, huber_delta);
+    step_scale(h, lambda);
+    step_schur(h);
+    step_finalize(h, lambda);
+    step_pcg(h, 1e-13, 5000);
+    step_update_and_residual(h, lambda, robust, huber_delta, h->dxl.p);
+    const int K = h->K, Kf = h->Kf, Pl = h->Pl;
+    std::vector<double> hx((size_t)Kf * 6), hdl((size_t)Pl * 3), hb((size_t)Kf * 6), st(3);
+    h->x.download(hx.data(), hx.size(), s); h->dxl.download(hdl.data(), hdl.size(), s);
+    h->bschur.download(hb.data(), hb.size(), s); h->pcg_status.download(st.data(), 3, s);
+    CCM_CUDA(cudaStreamSynchronize(s));
+    if (pcg_iters) *pcg_iters = (int)st[0];
+    if (pcg_relres) *pcg_relres = st[1];
+    if (dx_pose) {
+      memset(dx_pose, 0, sizeof(double) * 6 * K);
+      for (int a = 0; a < Kf; a++) memcpy(dx_pose + 6 * (size_t)h->h_slot_pose[a], hx.data() + (size_t)a * 6, 6 * sizeof(double));
+    }
+    if (dx_point) memcpy(dx_point, hdl.data(), sizeof(double) * 3 * Pl);
+    if (bschur) {
+      memset(bschur, 0, sizeof(double) * 6 * K);
+      for (int a = 0; a < Kf; a++) memcpy(bschur + 6 * (size_t)h->h_slot_pose[a], hb.data() + (size_t)a * 6, 6 * sizeof(double));
+    }
+    if (S_dense) {
+      const size_t n = 6 * (size_t)K;
+      memset(S_dense, 0, sizeof(double) * n * n);
+      std::vector<int> rp((size_t)Kf + 1), cl(h->nnzb);
+      std::vector<double> v((size_t)h->nnzb * 36);
+      h->s_rowptr.download(rp.data(), rp.size(), s); h->s_col.download(cl.data(), cl.size(), s); h->s_val.download(v.data(), v.size(), s);
+      CCM_CUDA(cudaStreamSynchronize(s));
+      for (int a = 0; a < Kf; a++)
+        for (int q = rp[a]; q < rp[a + 1]; q++) {
+          const size_t gi = 6 * (size_t)h->h_slot_pose[a], gj = 6 * (size_t)h->h_slot_pose[cl[q]];
+          for (int rr = 0; rr < 6; rr++)
+            for (int cc = 0; cc < 6; cc++) S_dense[(gi + rr) * n + gj + cc] = v[(size_t)q * 36 + rr * 6 + cc];
+        }
+    }
+  });
+}
+
+extern "C" int ccm_ba_time_kernel(ccm_ba_handle* h, int which, int reps, double huber_delta, double lambda, double* ms_per_launch) {
+  return guarded([&] {
+    CCM_REQUIRE(h && ms_per_launch && reps > 0, "bad argument");
+    CCM_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    // make sure every input of the timed kernel exists
+    step_linearize(h, 1, huber_delta);
+    step_scale(h, lambda);
+    step_schur(h);
+    step_finalize(h, lambda);
+    step_pcg(h, 1e-10, 2000);
+    cudaEvent_t e0, e1;
+    CCM_CUDA(cudaEventCreate(&e0)); CCM_CUDA(cudaEventCreate(&e1));
+    float total = 0.f;
+    for (int i = 0; i < reps; i++) {
+      if (which == 0) CCM_CUDA(cudaMemsetAsync(h->HllBl.p, 0, h->HllBl.bytes(), s));
+      CCM_CUDA(cudaEventRecord(e0, s));
+      switch (which) {
+        case 0:
+          k_linearize<<<grid_stride(h->El), TPB, 0, s>>>(h->o_kf.p, h->o_lm.p, h->o_uv.p, h->o_w.p, h->pose_cur, h->intr.p,
+                                                         h->pose_slot.p, h->pt_cur, h->El, h->Ep, h->Pl, 1, huber_delta, h->W.p,
+                                                         h->Hll(), h->bl(), h->partials.p);
+          break;
+        case 1:
+          k_pose_pass<<<h->Kf, 128, 0, s>>>(h->prod.p, h->u_prod_ptr.p, h->u_diag.p, h->slot_pose.p, h->o_lm.p, h->o_uv.p,
+                                            h->o_w.p, h->pose_cur, h->intr.p, h->pt_cur, 1, huber_delta, h->Hpp(), h->bp());
+          break;
+        case 2:
+          k_residual<<<grid_stride(h->El), TPB, 0, s>>>(h->o_kf.p, h->o_lm.p, h->o_uv.p, h->o_w.p, h->pose_cur, h->intr.p,
+                                                        h->pt_cur, h->El, 1, huber_delta, h->partials.p);
+          break;
+        case 3:
+          k_scale<<<div_up(h->El, TPB), TPB, 0, s>>>(h->o_lm.p, h->W.p, h->Ep, h->Hll(), h->bl(), h->Pl, h->El, lambda, h->Z.p, h->gvec.p);
+          break;
+        case 4:
+          k_schur<<<div_up((long long)h->nub * 32, TPB), TPB, 0, s>>>(h->prod.p, h->u_prod_ptr.p, h->u_row.p, h->u_col.p, h->nub,
+                                                                      h->Z.p, h->o_lm.p, h->gvec.p, h->U_val(), h->bneg());
+          break;
+        case 5:
+          k_backsub_points<<<grid_stride(h->Pl), TPB, 0, s>>>(h->lm_ptr.p, h->o_kf.p, h->pose_slot.p, h->Z.p, h->Hll(), h->bl(),
+                                                              h->x.p, h->pt_cur, h->Pl, lambda, h->pt_trial, nullptr, h->partials.p);
+          break;
+        case 6: {
+          step_pcg(h, 1e-10, 2000);
+          break;
+        }
+        default:
+          throw Error(CCM_ERR_INVALID, "ccm_ba_time_kernel: unknown kernel id");
+      }
+      if (which != 6) CCM_LAUNCHED();
+      CCM_CUDA(cudaEventRecord(e1, s));
+      CCM_CUDA(cudaEventSynchronize(e1));
+      float ms = 0.f;
+      CCM_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+      total += ms;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (which == 0) step_linearize(h, 1, huber_delta);  // leave Hll consistent
+    *ms_per_launch = total / reps;
+  });
+}
+
+// Converter::toSE3Quat: f32 4x4 -> (q, t) in f64 through SE3Quat(R, t)  (S/Converter.cc:40-51, G/types/se3quat.h:58-60)
+extern "C" void ccm_pose_from_Tcw_f32(const float* T, int32_t n, double* qt) {
+  for (int i = 0; i < n; i++) {
+    const float* t = T + 16 * (size_t)i;
+    const double R[9] = {t[0], t[1], t[2], t[4], t[5], t[6], t[8], t[9], t[10]};
+    double x, y, z, w;
+    R_to_quat(R, x, y, z, w);
+    quat_normalize_pos_w(x, y, z, w);
+    double* o = qt + 7 * (size_t)i;
+    o[0] = x; o[1] = y; o[2] = z; o[3] = w; o[4] = t[3]; o[5] = t[7]; o[6] = t[11];
+  }
+}
+
+// Converter::toCvMat(SE3Quat): homogeneous matrix rounded to f32  (S/Converter.cc:53-72)
+extern "C" void ccm_pose_to_Tcw_f32(const double* qt, int32_t n, float* T) {
+  for (int i = 0; i < n; i++) {
+    const double* q = qt + 7 * (size_t)i;
+    double R[9];
+    quat_to_R(q[0], q[1], q[2], q[3], R);
+    float* o = T + 16 * (size_t)i;
+    for (int r = 0; r < 3; r++) {
+      for (int c = 0; c < 3; c++) o[r * 4 + c] = (float)R[r * 3 + c];
+      o[r * 4 + 3] = (float)q[4 + r];
+    }
+    o[12] = o[13] = o[14] = 0.f; o[15] = 1.f;
+  }
+}

@@ -1,0 +1,250 @@
+/*
+ * ccm_b200.h — C ABI of libccm_b200.so: the B200-native (sm_100a) replacement for the
+ * bundle-adjustment + ORB hot path of VIS4ROB-lab/ccm_slam.
+ *
+ * The reference has no FFI for this path: the boundary is plain C++ linkage of
+ *   cslam::Optimizer  (cslam/include/cslam/Optimizer.h:84-112)  -> vendored g2o
+ *   cslam::ORBextractor (cslam/include/cslam/ORBextractor.h:103-138)
+ *   cslam::ORBmatcher   (cslam/include/cslam/ORBmatcher.h:97-145)
+ * A drop-in keeps those headers byte-identical and replaces the three .cpp files by shim TUs (shim/)
+ * that flatten the pointer graph into the structs below, call these entry points, and write back.
+ * INTEGRATION.md shows the binding.  Every entry point cites the reference code it replaces.
+ *
+ * Conventions: plain pointers + sizes, host buffers, no torch / CUDA types.  All functions return
+ * CCM_OK (0) or a negative error code; ccm_last_error() gives the message (thread-local).  The library
+ * never falls back to a CPU path: without a CUDA device every compute entry point returns
+ * CCM_ERR_NO_DEVICE.  Thread-safe per handle; each handle owns its CUDA stream.
+ */
+#ifndef CCM_B200_H
+#define CCM_B200_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CCM_OK 0
+#define CCM_ERR_INVALID (-1)
+#define CCM_ERR_NO_DEVICE (-2)
+#define CCM_ERR_CUDA (-3)
+#define CCM_ERR_NCCL (-4)
+#define CCM_ERR_OOM (-5)
+
+int ccm_version(void);
+const char* ccm_last_error(void);
+/* number of CUDA devices visible (0 when none / driver missing); never fails */
+int ccm_device_count(void);
+/* bind the calling thread's subsequent handles to `device` */
+int ccm_init(int device);
+int ccm_shutdown(void);
+/* cumulative number of kernels this library launched in this process (bench.py's gpu_launches) */
+uint64_t ccm_kernel_launches(void);
+
+/* ---- multi-GPU: one process per GPU, landmarks sharded across ranks --------------------
+ * Rank 0 calls ccm_comm_unique_id and ships the 128 bytes to the other ranks (e.g. torch.distributed
+ * broadcast); every rank then calls ccm_comm_init.  NCCL is dlopen'ed lazily (libnccl.so.2). */
+int ccm_comm_unique_id(uint8_t id[128]);
+int ccm_comm_init(int rank, int nranks, const uint8_t id[128]);
+int ccm_comm_destroy(void);
+int ccm_comm_rank(void);
+int ccm_comm_size(void);
+
+/* ---- bundle adjustment ---------------------------------------------------------------------------------
+ * Replaces g2o::SparseOptimizer::{initializeOptimization, optimize} as driven by
+ *   Optimizer::MapFusionGBA                (cslam/src/Optimizer.cpp:646-859, optimize at :797)
+ *   Optimizer::LocalBundleAdjustmentClient (cslam/src/Optimizer.cpp:349-644, optimize at :537 and :567)
+ *   Optimizer::BundleAdjustmentClient      (cslam/src/Optimizer.cpp:40-212,  optimize at :166)
+ * i.e. BlockSolver_6_3 + OptimizationAlgorithmLevenberg + EdgeSE3ProjectXYZ + RobustKernelHuber
+ * (cslam/thirdparty/g2o/g2o/core/optimization_algorithm_levenberg.cpp:61-164, core/block_solver.hpp:354-604,
+ *  types/types_six_dof_expmap.{h:80-109,cpp:103-147}).  The direct LDL^T on the reduced camera system
+ * (solvers/linear_solver_eigen.h:106-133) is replaced by block-Jacobi PCG run to `pcg_tol`.               */
+typedef struct ccm_ba_problem {
+  int32_t K, P, E;
+  const double* poses;       /* K*7 : qx qy qz qw tx ty tz of Tcw  (g2o::SE3Quat; Converter::toSE3Quat, Converter.cc:40-51) */
+  const double* intr;        /* K*4 : fx fy cx cy (KeyFrame::fx.. widened, Optimizer.cpp:777-780) */
+  const uint8_t* fixed;      /* K   : vSE3->setFixed(...)  (Optimizer.cpp:705, :435, :455) */
+  const double* points;      /* P*3 : Converter::toVector3d(pMP->GetWorldPos()) */
+  const int32_t* obs_kf;     /* E   : pose index of the observing keyframe */
+  const int32_t* obs_mp;     /* E   : point index */
+  const float* obs_uv;       /* E*2 : kpUn.pt.{x,y}  (Optimizer.cpp:758-762) */
+  const float* obs_w;        /* E   : pKF->mvInvLevelSigma2[kpUn.octave]  (Optimizer.cpp:768-769) */
+  const uint8_t* edge_flags; /* E or NULL : bit0 = e->setLevel(1) (inactive), bit1 = e->setRobustKernel(0)  (Optimizer.cpp:556-561) */
+} ccm_ba_problem;
+
+typedef struct ccm_ba_options {
+  int32_t iterations;        /* optimizer.optimize(n) */
+  int32_t robust;            /* bRobust: Huber kernel on every edge that does not carry bit1 */
+  double huber_delta;        /* (double)(float)sqrt(5.99) for GBA, sqrt(5.991) for LocalBA */
+  double lambda_init;        /* <= 0 : g2o default tau*max|H_jj|, tau = 1e-5 */
+  int32_t max_trials;        /* <= 0 : 10 (maxTrialsAfterFailure) */
+  int32_t pcg_max_iter;      /* <= 0 : 2000 */
+  double pcg_tol;            /* <= 0 : 1e-10 ; stop when |r|_2 <= pcg_tol*|b|_2 */
+  const volatile uint8_t* stop; /* optimizer.setForceStopFlag(pbStopFlag): polled between LM iterations and trials; may be NULL */
+} ccm_ba_options;
+
+#define CCM_TRACE_COLS 8 /* iter, lambda_used, chi2_after, rho, trials, lambda_after, pcg_iters(last trial), pcg_relres */
+
+typedef struct ccm_ba_result {
+  double* poses;             /* K*7 out (may be NULL) */
+  double* points;            /* P*3 out (may be NULL) */
+  double* chi2;              /* E out or NULL: e'We per ACTIVE edge at the last evaluated state; inactive entries untouched
+                                (reference keeps the round-1 value there, Optimizer.cpp:582) */
+  uint8_t* depth_pos;        /* E out or NULL: EdgeSE3ProjectXYZ::isDepthPositive on the final estimate, all edges */
+  double* trace;             /* trace_cap*CCM_TRACE_COLS or NULL */
+  int32_t trace_cap;
+  int32_t trace_len;
+  int32_t iters_done;        /* return value of SparseOptimizer::optimize (-1: nothing to optimise) */
+  int32_t trials_total;
+  int32_t pcg_iters_total;
+  int32_t pcg_not_converged; /* number of trials whose PCG hit pcg_max_iter */
+  double chi2_initial, chi2_final, lambda_final;
+  double t_setup_ms;         /* upload + structure (buildStructure equivalent) */
+  double t_optimize_ms;      /* LM loop (device time + host control) */
+  double t_download_ms;
+} ccm_ba_result;
+
+typedef struct ccm_ba_handle ccm_ba_handle;
+
+/* one-shot: upload, build structure, optimise, download (the call the shim makes). */
+int ccm_ba_solve(const ccm_ba_problem* p, const ccm_ba_options* o, ccm_ba_result* r);
+
+/* handle API (device-resident state between calls; used by LocalBA's two rounds and by bench.py) */
+int ccm_ba_create(const ccm_ba_problem* p, ccm_ba_handle** out);
+/* restore the estimate uploaded at create time (edge flags unchanged) */
+int ccm_ba_reset(ccm_ba_handle* h);
+/* replace edge flags (E bytes, same order as at create) — LocalBA round 2 */
+int ccm_ba_set_edge_flags(ccm_ba_handle* h, const uint8_t* edge_flags);
+int ccm_ba_optimize(ccm_ba_handle* h, const ccm_ba_options* o, ccm_ba_result* r);
+void ccm_ba_destroy(ccm_ba_handle* h);
+
+/* problem-shape facts of a handle (for roofline accounting) */
+typedef struct ccm_ba_info {
+  int32_t K, K_free, P_local, E_local, rank, nranks;
+  int64_t s_blocks_upper, s_blocks_full, schur_products;
+  int64_t device_bytes;
+} ccm_ba_info;
+int ccm_ba_get_info(const ccm_ba_handle* h, ccm_ba_info* info);
+
+/* kernel-level entry points for parity tests and ncu: run ONE pass on the handle's current estimate.
+ * Outputs are host buffers in the caller's index space (same layout as the oracle's orc_ba_build). */
+int ccm_ba_debug_build(ccm_ba_handle* h, int robust, double huber_delta,
+                       double* Hpp /*K*36*/, double* bp /*K*6*/, double* Hll /*P*9*/, double* bl /*P*3*/,
+                       double* W /*E*18*/, double* chi2_robust_sum);
+int ccm_ba_debug_schur(ccm_ba_handle* h, int robust, double huber_delta, double lambda,
+                       double* S_dense /*(6K)^2 or NULL*/, double* bschur /*6K or NULL*/,
+                       double* dx_pose /*K*6*/, double* dx_point /*P*3*/, int32_t* pcg_iters, double* pcg_relres);
+/* time `reps` launches of one kernel with CUDA events on the handle's stream; returns mean ms per launch.
+ * which: 0 linearize (landmark pass), 1 pose pass, 2 residual/chi2, 3 scale (W->Z), 4 schur products, 5 back-substitution */
+int ccm_ba_time_kernel(ccm_ba_handle* h, int which, int reps, double huber_delta, double lambda, double* ms_per_launch);
+
+/* Converter::toSE3Quat / toCvMat restated (cslam/src/Converter.cc:40-72) — host-side helpers for the shim */
+void ccm_pose_from_Tcw_f32(const float* T /*n*16 row-major*/, int32_t n, double* qt /*n*7*/);
+void ccm_pose_to_Tcw_f32(const double* qt /*n*7*/, int32_t n, float* T /*n*16*/);
+
+/* ---- Sim3 essential-graph optimisation -----------------------------------------------------------------
+ * Replaces optimizer.optimize(20) in Optimizer::OptimizeEssentialGraph{LoopClosure,MapFusion}
+ * (cslam/src/Optimizer.cpp:1277, :1513): VertexSim3Expmap / EdgeSim3 with identity information
+ * (types/types_seven_dof_expmap.h:48-126), BlockSolver_7_3 without Schur, Levenberg, lambda0 = 1e-16. */
+typedef struct ccm_pgo_problem {
+  int32_t K, E;
+  const double* sim3;        /* K*8 : qx qy qz qw tx ty tz s */
+  const uint8_t* fixed;      /* K */
+  const int32_t* edge_i;     /* E : vertex 0 */
+  const int32_t* edge_j;     /* E : vertex 1 */
+  const double* meas;        /* E*8 : Sji */
+  int32_t fix_scale;         /* VSim3->_fix_scale */
+} ccm_pgo_problem;
+
+typedef struct ccm_pgo_options {
+  int32_t iterations;        /* 20 */
+  double lambda_init;        /* 1e-16 (solver->setUserLambdaInit) ; <=0: tau*max diag */
+  int32_t pcg_max_iter;
+  double pcg_tol;
+  const volatile uint8_t* stop;
+} ccm_pgo_options;
+
+typedef struct ccm_pgo_result {
+  double* sim3;              /* K*8 out */
+  double* trace; int32_t trace_cap; int32_t trace_len;
+  int32_t iters_done;
+  double chi2_initial, chi2_final, lambda_final;
+  double t_total_ms;
+} ccm_pgo_result;
+
+int ccm_pgo_solve(const ccm_pgo_problem* p, const ccm_pgo_options* o, ccm_pgo_result* r);
+
+/* ---- ORB front end ------------------------------------------------------------------------------------
+ * ccm_orb_* replace ORBextractor::operator() (cslam/src/ORBextractor.cpp:1216-1278) and its helpers
+ * (ComputePyramid :1280-1304, ComputeKeyPointsOctTree :933-1024, IC_Angle :68-95, computeOrbDescriptor :100-316);
+ * OpenCV primitives follow the 4.x integer semantics pinned in SURVEY.md §8(c'). */
+typedef struct ccm_orb_config {
+  int32_t nfeatures;         /* 1000 */
+  float scale_factor;        /* 1.2 */
+  int32_t nlevels;           /* 8 */
+  int32_t ini_th_fast;       /* 20 */
+  int32_t min_th_fast;       /* 7 */
+  int32_t blur_2413;         /* 0: OpenCV 4.x GaussianBlur taps [18,34,48,56,48,34,18]; 1: 2.4.13 taps [18,34,49,55,49,34,18] */
+} ccm_orb_config;
+
+typedef struct ccm_keypoint {  /* cv::KeyPoint fields the reference reads */
+  float x, y, size, angle, response;
+  int32_t octave;
+} ccm_keypoint;
+
+typedef struct ccm_orb_handle ccm_orb_handle;
+int ccm_orb_create(const ccm_orb_config* cfg, int32_t width, int32_t height, ccm_orb_handle** out);
+/* extract: kps capacity max_kp; returns count in *n; desc = n*32 bytes */
+int ccm_orb_extract(ccm_orb_handle* h, const uint8_t* img, int32_t stride, ccm_keypoint* kps, int32_t max_kp,
+                    int32_t* n, uint8_t* desc);
+/* pyramid level readback (mvImagePyramid[level], public member of the reference class) */
+int ccm_orb_get_level(ccm_orb_handle* h, int32_t level, uint8_t* out, int32_t* w, int32_t* hgt);
+void ccm_orb_destroy(ccm_orb_handle* h);
+
+/* ---- Hamming matching ----------------------------------------------------------------------------------
+ * ccm_hamming_matrix replaces the ORBmatcher::DescriptorDistance inner loops (cslam/src/ORBmatcher.cpp:1653-1669)
+ * of SearchByBoW (:178-306, :565-698) and SearchForTriangulation (:700-852): D[i*nB+j] = popcount(A_i xor B_j).
+ * The order-dependent greedy selection stays on the host (ccm_match_* below) and reads D. */
+int ccm_hamming_matrix(const uint8_t* A, int32_t nA, const uint8_t* B, int32_t nB, uint16_t* D);
+
+typedef struct ccm_feature_vector { /* DBoW2::FeatureVector flattened: nodes ascending, features per node */
+  int32_t n_nodes;
+  const uint32_t* node_id;   /* n_nodes */
+  const int32_t* node_ptr;   /* n_nodes+1 into feat */
+  const uint32_t* feat;      /* feature indices */
+} ccm_feature_vector;
+
+/* SearchByBoW(kfptr, Frame&, vpMapPointMatches)  (cslam/src/ORBmatcher.cpp:178-306)
+ * kf_has_mp[i]: KF feature i has a good MapPoint; out match_f_of_kf[i] = frame feature matched to KF feature i or -1 -> the
+ * shim turns it into vpMapPointMatches[frame idx] = KF's MapPoint.  Returns nmatches via *nmatches. */
+int ccm_match_bow_kf_frame(const uint8_t* desc_kf, int32_t n_kf, const uint8_t* kf_has_mp, const float* angle_kf,
+                           const ccm_feature_vector* fv_kf,
+                           const uint8_t* desc_f, int32_t n_f, const float* angle_f, const ccm_feature_vector* fv_f,
+                           float nnratio, int32_t check_orientation, int32_t* match_kf_of_f /*n_f, -1 = none*/,
+                           int32_t* nmatches);
+/* SearchByBoW(kfptr, kfptr, vpMatches12)  (cslam/src/ORBmatcher.cpp:565-698) */
+int ccm_match_bow_kf_kf(const uint8_t* desc1, int32_t n1, const uint8_t* has_mp1, const float* angle1,
+                        const ccm_feature_vector* fv1,
+                        const uint8_t* desc2, int32_t n2, const uint8_t* has_mp2, const float* angle2,
+                        const ccm_feature_vector* fv2,
+                        float nnratio, int32_t check_orientation, int32_t* match12 /*n1, -1 = none*/, int32_t* nmatches);
+
+typedef struct ccm_tri_view {  /* the per-keyframe read set of SearchForTriangulation */
+  const uint8_t* desc; int32_t n;
+  const uint8_t* has_mp;     /* n : pKF->GetMapPoint(idx) != NULL */
+  const float* kp_xy;        /* n*2 : mvKeysUn[idx].pt */
+  const int32_t* octave;     /* n */
+  const float* angle;        /* n */
+  const ccm_feature_vector* fv;
+  float fx, fy, cx, cy;
+} ccm_tri_view;
+/* SearchForTriangulation(pKF1, pKF2, F12, vMatchedPairs)  (cslam/src/ORBmatcher.cpp:700-852)
+ * epipole = C1 projected into view 2 (ex, ey) is computed by the shim from the poses (:704-712); F12 row-major 3x3 f32;
+ * level_sigma2 : pKF2->mvLevelSigma2 (nlevels); scale_factors : pKF2->mvScaleFactors. */
+int ccm_match_triangulation(const ccm_tri_view* v1, const ccm_tri_view* v2, const float F12[9], float ex, float ey,
+                            const float* level_sigma2, const float* scale_factors, int32_t nlevels,
+                            int32_t check_orientation, int32_t* pairs /*2*min(n1,n2)*/, int32_t* npairs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
