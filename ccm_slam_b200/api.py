@@ -41,7 +41,8 @@ class BAResultC(C.Structure):
                 ("iters_done", C.c_int32), ("trials_total", C.c_int32), ("pcg_iters_total", C.c_int32),
                 ("pcg_not_converged", C.c_int32),
                 ("chi2_initial", C.c_double), ("chi2_final", C.c_double), ("lambda_final", C.c_double),
-                ("t_setup_ms", C.c_double), ("t_optimize_ms", C.c_double), ("t_download_ms", C.c_double)]
+                ("t_setup_ms", C.c_double), ("t_optimize_ms", C.c_double), ("t_download_ms", C.c_double),
+                ("t_optimize_event_ms", C.c_double)]
 
 
 class BAInfoC(C.Structure):
@@ -115,6 +116,18 @@ def init(device: int = 0):
     _chk(lib().ccm_init(device))
 
 
+def l2_flush():
+    _chk(lib().ccm_l2_flush())
+
+
+def host_register(arr: np.ndarray):
+    _chk(lib().ccm_host_register(_p(arr), C.c_uint64(arr.nbytes)))
+
+
+def host_unregister(arr: np.ndarray):
+    _chk(lib().ccm_host_unregister(_p(arr)))
+
+
 def kernel_launches() -> int:
     return int(lib().ccm_kernel_launches())
 
@@ -157,7 +170,7 @@ def _result_dict(res, poses, points, chi2, depth, trace):
                 iters_done=res.iters_done, trials_total=res.trials_total, pcg_iters_total=res.pcg_iters_total,
                 pcg_not_converged=res.pcg_not_converged, chi2_initial=res.chi2_initial, chi2_final=res.chi2_final,
                 lambda_final=res.lambda_final, t_setup_ms=res.t_setup_ms, t_optimize_ms=res.t_optimize_ms,
-                t_download_ms=res.t_download_ms)
+                t_download_ms=res.t_download_ms, t_optimize_event_ms=res.t_optimize_event_ms)
 
 
 HUBER_GBA = float(np.float32(np.sqrt(5.99)))     # `const float thHuber2D = sqrt(5.99)`   S/Optimizer.cpp:712
@@ -224,6 +237,16 @@ class BAHandle:
         res = BAResultC(_p(poses), _p(points), _p(chi2), _p(depth), _p(trace), trace.shape[0])
         _chk(lib().ccm_ba_optimize(self._h, C.byref(opt), C.byref(res)))
         return _result_dict(res, poses, points, chi2, depth, trace)
+
+    KERNEL_NAMES = ["linearize", "pose_pass", "scale", "schur", "allreduce", "finalize", "pcg", "backsub", "residual"]
+
+    def set_profile(self, on=True):
+        _chk(lib().ccm_ba_set_profile(self._h, int(on)))
+
+    def kernel_stats(self):
+        ms = np.zeros(len(self.KERNEL_NAMES)); cnt = np.zeros(len(self.KERNEL_NAMES), np.int64)
+        _chk(lib().ccm_ba_get_kernel_stats(self._h, _p(ms), _p(cnt)))
+        return {n: dict(total_ms=float(ms[i]), launches=int(cnt[i])) for i, n in enumerate(self.KERNEL_NAMES)}
 
     def debug_build(self, robust=True, huber_delta=HUBER_GBA):
         Hpp = np.empty((self.K, 6, 6)); bp = np.empty((self.K, 6)); Hll = np.empty((self.P, 3, 3)); bl = np.empty((self.P, 3))

@@ -81,6 +81,14 @@ struct ccm_ba_handle {
   DevBuf<uint8_t> rep_depth;
   int64_t device_bytes = 0;
   double t_setup_ms = 0;
+  // per-kernel CUDA-event accounting (ccm_ba_get_kernel_stats): events are recorded on the launching stream
+  bool profile = false;
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  struct Span { int which; size_t e0, e1; };
+  std::vector<Span> spans;
+  double k_ms[CCM_BA_NKERNELS] = {0};
+  long long k_count[CCM_BA_NKERNELS] = {0};
 
   double* Hll() { return HllBl.p; }
   double* bl() { return HllBl.p + (size_t)6 * Pl; }
@@ -91,6 +99,7 @@ struct ccm_ba_handle {
   double* bneg() { return Ubuf.p + (size_t)nub * 36; }
 
   ~ccm_ba_handle() {
+    for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
     if (h_scal) cudaFreeHost(h_scal);
     if (stream) cudaStreamDestroy(stream);
   }
@@ -106,6 +115,29 @@ int grid_stride(long long n) {
   return (int)g;
 }
 
+size_t ev_record(ccm_ba_handle* h) {
+  if (h->ev_used == h->ev_pool.size()) {
+    cudaEvent_t e;
+    CCM_CUDA(cudaEventCreate(&e));
+    h->ev_pool.push_back(e);
+  }
+  CCM_CUDA(cudaEventRecord(h->ev_pool[h->ev_used], h->stream));
+  return h->ev_used++;
+}
+struct KernelSpan {  // brackets one kernel (or kernel group) with events when profiling is on
+  ccm_ba_handle* h; int which; size_t e0 = 0;
+  KernelSpan(ccm_ba_handle* h_, int w) : h(h_), which(w) { if (h->profile) e0 = ev_record(h); }
+  ~KernelSpan() { if (h->profile) { try { size_t e1 = ev_record(h); h->spans.push_back({which, e0, e1}); } catch (...) {} } }
+};
+void collect_spans(ccm_ba_handle* h) {  // call after a stream synchronize
+  for (const auto& sp : h->spans) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, h->ev_pool[sp.e0], h->ev_pool[sp.e1]) == cudaSuccess) { h->k_ms[sp.which] += ms; h->k_count[sp.which]++; }
+  }
+  h->spans.clear();
+  h->ev_used = 0;
+}
+
 void sum_partials_to(ccm_ba_handle* h, int n, double* out) {
   k_sum_partials<<<1, 1024, 0, h->stream>>>(h->partials.p, n, out);
   CCM_LAUNCHED();
@@ -116,11 +148,15 @@ void step_linearize(ccm_ba_handle* h, int robust, double delta) {
   cudaStream_t s = h->stream;
   CCM_CUDA(cudaMemsetAsync(h->HllBl.p, 0, h->HllBl.bytes(), s));
   const int g = grid_stride(h->El);
-  k_linearize<<<g, TPB, 0, s>>>(h->o_kf.p, h->o_lm.p, h->o_uv.p, h->o_w.p, h->pose_cur, h->intr.p, h->pose_slot.p,
-                                h->pt_cur, h->El, h->Ep, h->Pl, robust, delta, h->W.p, h->Hll(), h->bl(), h->partials.p);
-  CCM_LAUNCHED();
+  {
+    KernelSpan sp(h, CCM_BA_K_LINEARIZE);
+    k_linearize<<<g, TPB, 0, s>>>(h->o_kf.p, h->o_lm.p, h->o_uv.p, h->o_w.p, h->pose_cur, h->intr.p, h->pose_slot.p,
+                                  h->pt_cur, h->El, h->Ep, h->Pl, robust, delta, h->W.p, h->Hll(), h->bl(), h->partials.p);
+    CCM_LAUNCHED();
+  }
   sum_partials_to(h, g, h->chi2_cur_dev());
   if (h->Kf > 0) {
+    KernelSpan sp(h, CCM_BA_K_POSE_PASS);
     k_pose_pass<<<h->Kf, 128, 0, s>>>(h->prod.p, h->u_prod_ptr.p, h->u_diag.p, h->slot_pose.p, h->o_lm.p, h->o_uv.p,
                                       h->o_w.p, h->pose_cur, h->intr.p, h->pt_cur, robust, delta, h->Hpp(), h->bp());
     CCM_LAUNCHED();
@@ -151,12 +187,14 @@ double read_chi2_cur(ccm_ba_handle* h) {
 
 void step_scale(ccm_ba_handle* h, double lambda) {
   if (h->El == 0) return;
+  KernelSpan sp(h, CCM_BA_K_SCALE);
   k_scale<<<div_up(h->El, TPB), TPB, 0, h->stream>>>(h->o_lm.p, h->W.p, h->Ep, h->Hll(), h->bl(), h->Pl, h->El, lambda,
                                                      h->Z.p, h->gvec.p);
   CCM_LAUNCHED();
 }
 
 void step_schur(ccm_ba_handle* h) {
+  KernelSpan sp(h, CCM_BA_K_SCHUR);
   k_schur<<<div_up((long long)h->nub * 32, TPB), TPB, 0, h->stream>>>(h->prod.p, h->u_prod_ptr.p, h->u_row.p, h->u_col.p,
                                                                       h->nub, h->Z.p, h->o_lm.p, h->gvec.p, h->U_val(),
                                                                       h->bneg());
@@ -165,7 +203,11 @@ void step_schur(ccm_ba_handle* h) {
 
 void step_finalize(ccm_ba_handle* h, double lambda) {
   cudaStream_t s = h->stream;
-  if (h->nranks > 1) allreduce_f64(h->Ubuf.p, (size_t)h->nub * 36 + (size_t)h->Kf * 6, 0, s);
+  if (h->nranks > 1) {
+    KernelSpan sp(h, CCM_BA_K_ALLREDUCE);
+    allreduce_f64(h->Ubuf.p, (size_t)h->nub * 36 + (size_t)h->Kf * 6, 0, s);
+  }
+  KernelSpan sp(h, CCM_BA_K_FINALIZE);
   k_finalize_S<<<div_up(h->nnzb * 36, TPB), TPB, 0, s>>>(h->s_row.p, h->s_col.p, h->csr_u.p, h->nnzb, h->U_val(), h->Hpp(),
                                                          lambda, h->s_val.p);
   CCM_LAUNCHED();
@@ -177,6 +219,7 @@ void step_finalize(ccm_ba_handle* h, double lambda) {
 
 void step_pcg(ccm_ba_handle* h, double tol, int max_iter) {
   cudaStream_t s = h->stream;
+  KernelSpan sp(h, CCM_BA_K_PCG);
   CCM_CUDA(cudaMemsetAsync(h->pcg_bar.p, 0, sizeof(unsigned), s));
   PcgArgs a;
   a.n = h->Kf; a.rowptr = h->s_rowptr.p; a.col = h->s_col.p; a.val = h->s_val.p; a.Minv = h->Minv.p; a.b = h->bschur.p;
@@ -191,6 +234,7 @@ void step_pcg(ccm_ba_handle* h, double tol, int max_iter) {
 void step_update_and_residual(ccm_ba_handle* h, double lambda, int robust, double delta, double* dx_points) {
   cudaStream_t s = h->stream;
   const int g1 = grid_stride(h->K);
+  size_t ev0 = h->profile ? ev_record(h) : 0;
   k_update_poses<<<g1, TPB, 0, s>>>(h->pose_cur, h->pose_slot.p, h->x.p, h->bp(), h->K, lambda, h->pose_trial, h->partials.p);
   CCM_LAUNCHED();
   sum_partials_to(h, g1, h->scal.p + 2);
@@ -199,11 +243,13 @@ void step_update_and_residual(ccm_ba_handle* h, double lambda, int robust, doubl
                                       h->Pl, lambda, h->pt_trial, dx_points, h->partials.p);
   CCM_LAUNCHED();
   sum_partials_to(h, g2, h->scal.p + 1);
+  if (h->profile) { size_t ev1 = ev_record(h); h->spans.push_back({CCM_BA_K_BACKSUB, ev0, ev1}); ev0 = ev1; }
   const int g3 = grid_stride(h->El);
   k_residual<<<g3, TPB, 0, s>>>(h->o_kf.p, h->o_lm.p, h->o_uv.p, h->o_w.p, h->pose_trial, h->intr.p, h->pt_trial, h->El,
                                 robust, delta, h->partials.p);
   CCM_LAUNCHED();
   sum_partials_to(h, g3, h->scal.p + 0);
+  if (h->profile) { size_t ev1 = ev_record(h); h->spans.push_back({CCM_BA_K_RESIDUAL, ev0, ev1}); }
   if (h->nranks > 1) allreduce_f64(h->scal.p, 2, 0, s);
   h->pose_eval = h->pose_trial;
   h->pt_eval = h->pt_trial;
@@ -478,6 +524,9 @@ void optimize(ccm_ba_handle* h, const ccm_ba_options* o, ccm_ba_result* r) {
   CCM_CUDA(cudaSetDevice(h->device));
   const double T0 = now_ms();
   cudaStream_t s = h->stream;
+  cudaEvent_t evA, evB;  // device-side bracket of the whole LM loop
+  CCM_CUDA(cudaEventCreate(&evA)); CCM_CUDA(cudaEventCreate(&evB));
+  CCM_CUDA(cudaEventRecord(evA, s));
   const int robust = o->robust ? 1 : 0;
   const double delta = o->huber_delta;
   const int max_trials = o->max_trials > 0 ? o->max_trials : 10;
@@ -521,6 +570,7 @@ void optimize(ccm_ba_handle* h, const ccm_ba_options* o, ccm_ba_result* r) {
       CCM_CUDA(cudaMemcpyAsync(h->h_scal + 3, h->pcg_status.p, 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
       CCM_CUDA(cudaMemcpyAsync(h->h_scal + 6, h->jac_fail.p, sizeof(int), cudaMemcpyDeviceToHost, s));
       CCM_CUDA(cudaStreamSynchronize(s));
+      if (h->profile) collect_spans(h);
       tempChi = h->h_scal[0];
       const int pcg_it = (int)h->h_scal[3];
       const int pcg_flag = (int)h->h_scal[5];
@@ -564,8 +614,16 @@ void optimize(ccm_ba_handle* h, const ccm_ba_options* o, ccm_ba_result* r) {
     if (nBad >= 3) { ok = false; continue; }
   }
   r->iters_done = ret_iters;
+  CCM_CUDA(cudaEventRecord(evB, s));
   CCM_CUDA(cudaStreamSynchronize(s));
+  if (h->profile) collect_spans(h);
   r->t_optimize_ms = now_ms() - T0;
+  {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, evA, evB);
+    r->t_optimize_event_ms = ms;
+    cudaEventDestroy(evA); cudaEventDestroy(evB);
+  }
   const double T1 = now_ms();
   download_state(h, r);
   r->t_download_ms = now_ms() - T1;
@@ -628,6 +686,22 @@ extern "C" int ccm_ba_solve(const ccm_ba_problem* p, const ccm_ba_options* o, cc
   rc = ccm_ba_optimize(h, o, r);
   ccm_ba_destroy(h);
   return rc;
+}
+
+extern "C" int ccm_ba_set_profile(ccm_ba_handle* h, int on) {
+  return guarded([&] {
+    CCM_REQUIRE(h, "null handle");
+    h->profile = on != 0;
+    for (int i = 0; i < CCM_BA_NKERNELS; i++) { h->k_ms[i] = 0; h->k_count[i] = 0; }
+    h->spans.clear(); h->ev_used = 0;
+  });
+}
+
+extern "C" int ccm_ba_get_kernel_stats(const ccm_ba_handle* h, double* total_ms, int64_t* launches) {
+  return guarded([&] {
+    CCM_REQUIRE(h && total_ms && launches, "null argument");
+    for (int i = 0; i < CCM_BA_NKERNELS; i++) { total_ms[i] = h->k_ms[i]; launches[i] = h->k_count[i]; }
+  });
 }
 
 extern "C" int ccm_ba_get_info(const ccm_ba_handle* h, ccm_ba_info* info) {

@@ -163,3 +163,25 @@ extern "C" int ccm_comm_init(int rank, int nranks, const uint8_t id[128]) {
 extern "C" int ccm_comm_destroy(void) { return ccm_shutdown(); }
 extern "C" int ccm_comm_rank(void) { return g_comm.rank; }
 extern "C" int ccm_comm_size(void) { return g_comm.nranks; }
+
+extern "C" int ccm_l2_flush(void) {
+  return guarded([&] {
+    ensure_device();
+    static void* buf = nullptr;
+    const size_t n = 256ull << 20;
+    if (!buf) CCM_CUDA(cudaMalloc(&buf, n));
+    CCM_CUDA(cudaMemset(buf, 0x5a, n));
+    CCM_CUDA(cudaDeviceSynchronize());
+  });
+}
+
+extern "C" int ccm_host_register(void* ptr, uint64_t bytes) {
+  return guarded([&] {
+    ensure_device();
+    CCM_CUDA(cudaHostRegister(ptr, bytes, cudaHostRegisterDefault));
+  });
+}
+
+extern "C" int ccm_host_unregister(void* ptr) {
+  return guarded([&] { CCM_CUDA(cudaHostUnregister(ptr)); });
+}

@@ -40,6 +40,12 @@ int ccm_shutdown(void);
 /* cumulative number of kernels this library launched in this process (bench.py's gpu_launches) */
 uint64_t ccm_kernel_launches(void);
 
+/* write a buffer larger than L2 (256 MiB) and synchronise: benchmarks call it between timed iterations */
+int ccm_l2_flush(void);
+/* page-lock / unlock caller memory so that the uploads inside ccm_*_create/solve run from pinned memory */
+int ccm_host_register(void* ptr, uint64_t bytes);
+int ccm_host_unregister(void* ptr);
+
 /* ---- multi-GPU: one process per GPU, landmarks sharded across ranks --------------------
  * Rank 0 calls ccm_comm_unique_id and ships the 128 bytes to the other ranks (e.g. torch.distributed
  * broadcast); every rank then calls ccm_comm_init.  NCCL is dlopen'ed lazily (libnccl.so.2). */
@@ -101,6 +107,7 @@ typedef struct ccm_ba_result {
   double t_setup_ms;         /* upload + structure (buildStructure equivalent) */
   double t_optimize_ms;      /* LM loop (device time + host control) */
   double t_download_ms;
+  double t_optimize_event_ms; /* the LM loop bracketed by CUDA events on the handle's stream */
 } ccm_ba_result;
 
 typedef struct ccm_ba_handle ccm_ba_handle;
@@ -124,6 +131,21 @@ typedef struct ccm_ba_info {
   int64_t device_bytes;
 } ccm_ba_info;
 int ccm_ba_get_info(const ccm_ba_handle* h, ccm_ba_info* info);
+
+/* per-kernel CUDA-event accounting over everything ccm_ba_optimize launches while profiling is on (events are
+ * recorded on the handle's stream around each kernel / kernel group; two records per span). */
+#define CCM_BA_K_LINEARIZE 0   /* k_linearize: residual + Jacobian + W store + Hll/bl            (per LM iteration) */
+#define CCM_BA_K_POSE_PASS 1   /* k_pose_pass: Hpp/bp                                            (per LM iteration) */
+#define CCM_BA_K_SCALE 2       /* k_scale: Z = W U^-1                                            (per LM trial) */
+#define CCM_BA_K_SCHUR 3       /* k_schur: Schur products                                        (per LM trial) */
+#define CCM_BA_K_ALLREDUCE 4   /* NCCL all-reduce of [S upper | bschur part]                     (per LM trial, N>1) */
+#define CCM_BA_K_FINALIZE 5    /* k_finalize_S + k_block_jacobi                                  (per LM trial) */
+#define CCM_BA_K_PCG 6         /* k_pcg (persistent)                                             (per LM trial) */
+#define CCM_BA_K_BACKSUB 7     /* k_update_poses + k_backsub_points (+ their partial sums)       (per LM trial) */
+#define CCM_BA_K_RESIDUAL 8    /* k_residual on the trial state (+ partial sum)                  (per LM trial) */
+#define CCM_BA_NKERNELS 9
+int ccm_ba_set_profile(ccm_ba_handle* h, int on);   /* also zeroes the counters */
+int ccm_ba_get_kernel_stats(const ccm_ba_handle* h, double* total_ms /*CCM_BA_NKERNELS*/, int64_t* launches /*CCM_BA_NKERNELS*/);
 
 /* kernel-level entry points for parity tests and ncu: run ONE pass on the handle's current estimate.
  * Outputs are host buffers in the caller's index space (same layout as the oracle's orc_ba_build). */
