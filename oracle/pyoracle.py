@@ -186,3 +186,152 @@ def pgo_solve(p, iterations=20, lambda_init=1e-16, analytic_jac=False, stop=None
     assert rc == 0
     return dict(sim3=out, trace=trace[:res.trace_len], iters_done=res.iters_done, chi2_initial=res.chi2_initial,
                 chi2_final=res.chi2_final, lambda_final=res.lambda_final, t_total=res.t_total_s)
+
+
+# ---- ORB extractor / matching ------------------------------------------------------------------------------------
+class _OrbCfg(C.Structure):
+    _fields_ = [("nfeatures", C.c_int32), ("scale_factor", C.c_float), ("nlevels", C.c_int32),
+                ("ini_th_fast", C.c_int32), ("min_th_fast", C.c_int32), ("blur_2413", C.c_int32)]
+
+
+class _KP(C.Structure):
+    _fields_ = [("x", C.c_float), ("y", C.c_float), ("size", C.c_float), ("angle", C.c_float),
+                ("response", C.c_float), ("octave", C.c_int32)]
+
+
+KP_DTYPE = np.dtype([("x", "f4"), ("y", "f4"), ("size", "f4"), ("angle", "f4"), ("response", "f4"), ("octave", "i4")])
+
+
+def orb_cfg(nfeatures=1000, scale_factor=1.2, nlevels=8, ini_th=20, min_th=7, blur_2413=0):
+    return _OrbCfg(nfeatures, scale_factor, nlevels, ini_th, min_th, blur_2413)
+
+
+def orb_extract(img, cfg=None, max_kp=8192):
+    cfg = cfg or orb_cfg()
+    img = np.ascontiguousarray(img, np.uint8)
+    h, w = img.shape
+    kps = np.zeros(max_kp, KP_DTYPE); desc = np.zeros((max_kp, 32), np.uint8); n = C.c_int()
+    lib().orc_orb_extract(_p(img), w, h, w, C.byref(cfg), _p(kps), max_kp, C.byref(n), _p(desc))
+    return kps[:n.value].copy(), desc[:n.value].copy()
+
+
+def orb_tables(cfg, w, h):
+    npl = np.zeros(cfg.nlevels, np.int32); umax = np.zeros(16, np.int32); wh = np.zeros((cfg.nlevels, 2), np.int32)
+    lib().orc_orb_tables(C.byref(cfg), w, h, _p(npl), _p(umax), _p(wh))
+    return npl, umax, wh
+
+
+def resize_linear_u8(src, dw, dh):
+    src = np.ascontiguousarray(src, np.uint8); dst = np.empty((dh, dw), np.uint8)
+    lib().orc_resize_linear_u8(_p(src), src.shape[1], src.shape[0], _p(dst), dw, dh)
+    return dst
+
+
+def gaussian_blur7(src, taps2413=False):
+    src = np.ascontiguousarray(src, np.uint8); dst = np.empty_like(src)
+    lib().orc_gaussian_blur7(_p(src), src.shape[1], src.shape[0], _p(dst), int(taps2413))
+    return dst
+
+
+def fast(img, threshold, max_out=100000):
+    img = np.ascontiguousarray(img, np.uint8)
+    xy = np.zeros((max_out, 2), np.int32); sc = np.zeros(max_out, np.int32)
+    n = lib().orc_fast(_p(img), img.shape[1], img.shape[0], threshold, _p(xy), _p(sc), max_out)
+    return xy[:n], sc[:n]
+
+
+def fast_atan2(y, x):
+    f = lib().orc_fast_atan2
+    f.restype = C.c_float
+    return f(C.c_float(y), C.c_float(x))
+
+
+def orb_level_candidates(img, cfg, level, max_out=200000):
+    img = np.ascontiguousarray(img, np.uint8)
+    out = np.zeros((max_out, 3), np.float32)
+    n = lib().orc_orb_level_candidates(_p(img), img.shape[1], img.shape[0], C.byref(cfg), level, _p(out), max_out)
+    return out[:n]
+
+
+def orb_descriptor(img, x, y, angle):
+    img = np.ascontiguousarray(img, np.uint8); d = np.zeros(32, np.uint8)
+    lib().orc_orb_descriptor(_p(img), img.shape[1], img.shape[0], C.c_float(x), C.c_float(y), C.c_float(angle), _p(d))
+    return d
+
+
+def ic_angle(img, x, y):
+    img = np.ascontiguousarray(img, np.uint8)
+    f = lib().orc_ic_angle
+    f.restype = C.c_float
+    m01 = C.c_int(); m10 = C.c_int()
+    a = f(_p(img), img.shape[1], img.shape[0], C.c_float(x), C.c_float(y), C.byref(m01), C.byref(m10))
+    return a, m01.value, m10.value
+
+
+class _FV(C.Structure):
+    _fields_ = [("n_nodes", C.c_int32), ("node_id", C.c_void_p), ("node_ptr", C.c_void_p), ("feat", C.c_void_p)]
+
+
+class FeatureVector:
+    """Flattened DBoW2::FeatureVector: nodes ascending, features per node in insertion order."""
+
+    def __init__(self, node_of_feature):
+        node_of_feature = np.asarray(node_of_feature)
+        order = np.argsort(node_of_feature, kind="stable")
+        nodes, counts = np.unique(node_of_feature, return_counts=True)
+        self.node_id = nodes.astype(np.uint32)
+        self.node_ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+        self.feat = order.astype(np.uint32)
+
+    def c(self, cls=_FV):
+        return cls(len(self.node_id), _p(self.node_id), _p(self.node_ptr), _p(self.feat))
+
+
+def descriptor_distance(a, b):
+    a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+    return lib().orc_descriptor_distance(_p(a), _p(b))
+
+
+def match_bow_kf_frame(desc_kf, has_mp, ang_kf, fv_kf, desc_f, ang_f, fv_f, nnratio=0.7, check_ori=True):
+    desc_kf = np.ascontiguousarray(desc_kf, np.uint8); desc_f = np.ascontiguousarray(desc_f, np.uint8)
+    has_mp = np.ascontiguousarray(has_mp, np.uint8); ang_kf = np.ascontiguousarray(ang_kf, np.float32); ang_f = np.ascontiguousarray(ang_f, np.float32)
+    out = np.empty(desc_f.shape[0], np.int32)
+    fk, ff = fv_kf.c(), fv_f.c()
+    n = lib().orc_match_bow_kf_frame(_p(desc_kf), desc_kf.shape[0], _p(has_mp), _p(ang_kf), C.byref(fk), _p(desc_f), desc_f.shape[0],
+                                     _p(ang_f), C.byref(ff), C.c_float(nnratio), int(check_ori), _p(out))
+    return out, n
+
+
+def match_bow_kf_kf(d1, has1, a1, fv1, d2, has2, a2, fv2, nnratio=0.8, check_ori=True):
+    d1 = np.ascontiguousarray(d1, np.uint8); d2 = np.ascontiguousarray(d2, np.uint8)
+    has1 = np.ascontiguousarray(has1, np.uint8); has2 = np.ascontiguousarray(has2, np.uint8)
+    a1 = np.ascontiguousarray(a1, np.float32); a2 = np.ascontiguousarray(a2, np.float32)
+    out = np.empty(d1.shape[0], np.int32)
+    f1, f2 = fv1.c(), fv2.c()
+    n = lib().orc_match_bow_kf_kf(_p(d1), d1.shape[0], _p(has1), _p(a1), C.byref(f1), _p(d2), d2.shape[0], _p(has2), _p(a2), C.byref(f2),
+                                  C.c_float(nnratio), int(check_ori), _p(out))
+    return out, n
+
+
+class _TriView(C.Structure):
+    _fields_ = [("desc", C.c_void_p), ("n", C.c_int32), ("has_mp", C.c_void_p), ("kp_xy", C.c_void_p), ("octave", C.c_void_p),
+                ("angle", C.c_void_p), ("fv", C.POINTER(_FV)), ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float)]
+
+
+def match_triangulation(v1, v2, F12, ex, ey, level_sigma2, scale_factors, check_ori=False):
+    """v = dict(desc, has_mp, kp_xy, octave, angle, fv, intr)"""
+    keep = []
+
+    def view(v):
+        arrs = dict(desc=np.ascontiguousarray(v["desc"], np.uint8), has=np.ascontiguousarray(v["has_mp"], np.uint8),
+                    xy=np.ascontiguousarray(v["kp_xy"], np.float32), oc=np.ascontiguousarray(v["octave"], np.int32),
+                    an=np.ascontiguousarray(v["angle"], np.float32))
+        fv = v["fv"].c(); keep.extend([arrs, fv])
+        fx, fy, cx, cy = v["intr"]
+        return _TriView(_p(arrs["desc"]), arrs["desc"].shape[0], _p(arrs["has"]), _p(arrs["xy"]), _p(arrs["oc"]), _p(arrs["an"]),
+                        C.pointer(fv), fx, fy, cx, cy)
+    a, b = view(v1), view(v2)
+    F = np.ascontiguousarray(F12, np.float32); ls = np.ascontiguousarray(level_sigma2, np.float32); sf = np.ascontiguousarray(scale_factors, np.float32)
+    pairs = np.empty((min(a.n, b.n) + 1, 2), np.int32)
+    n = lib().orc_match_triangulation(C.byref(a), C.byref(b), _p(F), C.c_float(ex), C.c_float(ey), _p(ls), _p(sf), int(check_ori), _p(pairs))
+    return pairs[:n].copy()
