@@ -15,6 +15,7 @@ CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libccm_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--use_fast_math=false",
+         "-Xcompiler", "-ffp-contract=off",
          "-Xcompiler", "-fPIC,-O3,-Wall", "-shared", "-lcudart", "-ldl"]
 
 

@@ -26,32 +26,14 @@
 #include <stdint.h>
 
 #include "ba_math.cuh"
+#include "pcg.cuh"
 
 namespace ccm {
 namespace ba {
 
-constexpr int TPB = 256;
-
-__device__ __forceinline__ double warp_sum(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-
-// block-wide sum; result valid in thread 0.  smem must hold TPB/32 doubles.
-__device__ __forceinline__ double block_sum(double v, double* smem) {
-  v = warp_sum(v);
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  __syncthreads();
-  if (lane == 0) smem[wid] = v;
-  __syncthreads();
-  double r = 0;
-  if (wid == 0) {
-    r = lane < (blockDim.x >> 5) ? smem[lane] : 0.0;
-    r = warp_sum(r);
-  }
-  return r;
-}
+using ccm::TPB;
+using ccm::warp_sum;
+using ccm::block_sum;
 
 __device__ __forceinline__ Pose load_pose(const double* __restrict__ pose, int k) {
   const double* p = pose + 7 * (size_t)k;
@@ -465,162 +447,6 @@ __global__ void __launch_bounds__(128) k_block_jacobi(const int* __restrict__ s_
 #pragma unroll
   for (int i = 0; i < 6; i++) bschur[(size_t)a * 6 + i] = bp[(size_t)a * 6 + i] + bneg[(size_t)a * 6 + i];
   if (!ok) atomicExch(fail, 1);
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// K5: persistent cooperative PCG on S x = b (block-Jacobi preconditioned).  One warp per block row, grid-wide
-// barriers through a global counter; dot products are reduced in a fixed order so every CTA sees identical scalars.
-struct PcgArgs {
-  int n;  // block rows
-  const int* rowptr; const int* col; const double* val; const double* Minv; const double* b;
-  double *x, *r, *z, *p, *q;
-  double* partials;  // 3 * gridDim.x
-  unsigned* bar;
-  double tol; int max_iter;
-  double* status;    // [iters, relres, flag(0 ok, 1 max_iter, 2 breakdown)]
-};
-
-__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& target) {
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    target += gridDim.x;
-    __threadfence();
-    atomicAdd(bar, 1u);
-    while (*(volatile unsigned*)bar < target) {}
-    __threadfence();
-  }
-  __syncthreads();
-}
-
-// sum of partials[0..g) in a fixed order, same value in every thread of the calling warp
-__device__ __forceinline__ double sum_partials(const double* partials, int g) {
-  double v = 0.0;
-  for (int i = threadIdx.x & 31; i < g; i += 32) v += __ldcg(partials + i);
-  return warp_sum(v);
-}
-
-__global__ void __launch_bounds__(TPB) k_pcg(PcgArgs A) {
-  __shared__ double red[TPB / 32];
-  __shared__ double bcast[2];
-  const int lane = threadIdx.x & 31;
-  const int gw = (blockIdx.x * TPB + threadIdx.x) >> 5;
-  const int nw = (gridDim.x * TPB) >> 5;
-  const int G = gridDim.x;
-  unsigned target = 0;
-  double* part0 = A.partials;
-  double* part1 = A.partials + G;
-  double* part2 = A.partials + 2 * G;
-
-  // init: x = 0, r = b, z = Minv r, p = z ; rz = r.z ; bb = b.b
-  double acc_rz = 0.0, acc_bb = 0.0;
-  for (int a = gw; a < A.n; a += nw) {
-    double rv = 0.0, zv = 0.0;
-    if (lane < 6) {
-      rv = A.b[(size_t)a * 6 + lane];
-      const double* M = A.Minv + (size_t)a * 36 + lane * 6;
-      const double* ra = A.b + (size_t)a * 6;
-#pragma unroll
-      for (int k = 0; k < 6; k++) zv += M[k] * ra[k];
-      A.x[(size_t)a * 6 + lane] = 0.0;
-      A.r[(size_t)a * 6 + lane] = rv;
-      A.z[(size_t)a * 6 + lane] = zv;
-      A.p[(size_t)a * 6 + lane] = zv;
-      acc_rz += rv * zv;
-      acc_bb += rv * rv;
-    }
-  }
-  {
-    const double t0 = block_sum(acc_rz, red);
-    const double t1 = block_sum(acc_bb, red);
-    if (threadIdx.x == 0) { part0[blockIdx.x] = t0; part1[blockIdx.x] = t1; }
-  }
-  grid_barrier(A.bar, target);
-  double rz = sum_partials(part0, G);
-  const double bb = sum_partials(part1, G);
-  const double stop2 = A.tol * A.tol * bb;
-  int it = 0, flag = 1;
-  double rr = bb;
-  if (!(bb > 0.0)) { flag = 0; }
-  else
-    for (it = 0; it < A.max_iter; it++) {
-      // q = S p ; pq = p.q
-      double acc_pq = 0.0;
-      for (int a = gw; a < A.n; a += nw) {
-        double y[6] = {0, 0, 0, 0, 0, 0};
-        const int beg = A.rowptr[a], end = A.rowptr[a + 1];
-        for (int j = beg + lane; j < end; j += 32) {
-          const double2* v = reinterpret_cast<const double2*>(A.val + (size_t)j * 36);
-          const double* pj = A.p + (size_t)A.col[j] * 6;
-          double pv[6];
-#pragma unroll
-          for (int k = 0; k < 6; k++) pv[k] = __ldcg(pj + k);
-#pragma unroll
-          for (int rI = 0; rI < 6; rI++) {
-            const double2 v0 = __ldg(v + rI * 3), v1 = __ldg(v + rI * 3 + 1), v2 = __ldg(v + rI * 3 + 2);
-            y[rI] += v0.x * pv[0] + v0.y * pv[1] + v1.x * pv[2] + v1.y * pv[3] + v2.x * pv[4] + v2.y * pv[5];
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < 6; k++) y[k] = warp_sum(y[k]);
-        if (lane < 6) {
-          double yl = y[0];
-#pragma unroll
-          for (int k = 1; k < 6; k++) yl = lane == k ? y[k] : yl;
-          A.q[(size_t)a * 6 + lane] = yl;
-          acc_pq += yl * A.p[(size_t)a * 6 + lane];
-        }
-      }
-      {
-        const double t0 = block_sum(acc_pq, red);
-        if (threadIdx.x == 0) part0[blockIdx.x] = t0;
-      }
-      grid_barrier(A.bar, target);
-      const double pq = sum_partials(part0, G);
-      if (!(pq > 0.0) || !isfinite(pq)) { flag = 2; break; }
-      const double alpha = rz / pq;
-      // x += alpha p ; r -= alpha q ; z = Minv r ; rz_new = r.z ; rr = r.r   (rows owned by this warp)
-      double acc_rz2 = 0.0, acc_rr = 0.0;
-      for (int a = gw; a < A.n; a += nw) {
-        double rv = 0.0;
-        if (lane < 6) {
-          rv = A.r[(size_t)a * 6 + lane] - alpha * A.q[(size_t)a * 6 + lane];
-          A.x[(size_t)a * 6 + lane] += alpha * A.p[(size_t)a * 6 + lane];
-          A.r[(size_t)a * 6 + lane] = rv;
-        }
-        double r6[6];
-#pragma unroll
-        for (int k = 0; k < 6; k++) r6[k] = __shfl_sync(0xffffffffu, rv, k);
-        if (lane < 6) {
-          const double* M = A.Minv + (size_t)a * 36 + lane * 6;
-          double zv = 0.0;
-#pragma unroll
-          for (int k = 0; k < 6; k++) zv += M[k] * r6[k];
-          A.z[(size_t)a * 6 + lane] = zv;
-          acc_rz2 += rv * zv;
-          acc_rr += rv * rv;
-        }
-      }
-      {
-        const double t0 = block_sum(acc_rz2, red);
-        const double t1 = block_sum(acc_rr, red);
-        if (threadIdx.x == 0) { part1[blockIdx.x] = t0; part2[blockIdx.x] = t1; }
-      }
-      grid_barrier(A.bar, target);
-      const double rz_new = sum_partials(part1, G);
-      rr = sum_partials(part2, G);
-      if (rr <= stop2) { flag = 0; it++; break; }
-      const double beta = rz_new / rz;
-      rz = rz_new;
-      for (int a = gw; a < A.n; a += nw)
-        if (lane < 6) A.p[(size_t)a * 6 + lane] = A.z[(size_t)a * 6 + lane] + beta * A.p[(size_t)a * 6 + lane];
-      grid_barrier(A.bar, target);
-    }
-  (void)bcast;
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    A.status[0] = (double)it;
-    A.status[1] = bb > 0.0 ? sqrt(rr / bb) : 0.0;
-    A.status[2] = (double)flag;
-  }
 }
 
 // ------------------------------------------------------------------------------------------------------------

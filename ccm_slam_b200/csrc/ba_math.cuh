@@ -66,8 +66,8 @@ CCM_HD void R_to_quat(const double R[9], double& x, double& y, double& z, double
 
 CCM_HD void quat_normalize_pos_w(double& x, double& y, double& z, double& w) {
   if (w < 0) { x = -x; y = -y; z = -z; w = -w; }
-  const double inv = 1.0 / sqrt(x * x + y * y + z * z + w * w);
-  x *= inv; y *= inv; z *= inv; w *= inv;
+  const double n = sqrt(x * x + y * y + z * z + w * w);  // Eigen's normalize(): coefficient-wise division by the norm
+  x /= n; y /= n; z /= n; w /= n;
 }
 
 // out = exp(upd) * T with upd = (omega, upsilon).  Includes g2o's theta < 1e-5 branch (R = I + W + W^2, V = R).

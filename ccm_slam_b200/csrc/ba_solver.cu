@@ -226,7 +226,7 @@ void step_pcg(ccm_ba_handle* h, double tol, int max_iter) {
   a.x = h->x.p; a.r = h->pr.p; a.z = h->pz.p; a.p = h->pp.p; a.q = h->pq.p;
   a.partials = h->pcg_partials.p; a.bar = h->pcg_bar.p; a.tol = tol; a.max_iter = max_iter; a.status = h->pcg_status.p;
   void* args[] = {&a};
-  CCM_CUDA(cudaLaunchCooperativeKernel((void*)k_pcg, dim3(h->pcg_grid), dim3(TPB), args, 0, s));
+  CCM_CUDA(cudaLaunchCooperativeKernel((void*)k_pcg<6>, dim3(h->pcg_grid), dim3(TPB), args, 0, s));
   CCM_LAUNCHED();
 }
 
@@ -459,7 +459,7 @@ void build(ccm_ba_handle* h, const ccm_ba_problem* p) {
   h->dxl.alloc(std::max((size_t)Pl * 3, (size_t)1));
   h->pcg_status.alloc_zero(4, s); h->pcg_bar.alloc_zero(1, s); h->jac_fail.alloc_zero(1, s);
   int per_sm = 0;
-  CCM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg, TPB, 0));
+  CCM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg<6>, TPB, 0));
   per_sm = std::max(1, std::min(per_sm, env_int("CCM_PCG_BLOCKS_PER_SM", 4)));
   h->pcg_grid = std::max(1, std::min(per_sm * sm_count(), div_up((long long)std::max(Kf, 1) * 32, TPB)));
   h->pcg_partials.alloc((size_t)3 * h->pcg_grid);

@@ -1,0 +1,505 @@
+// pgo.cu — Sim3 essential-graph optimisation on the GPU behind ccm_pgo_solve (include/ccm_b200.h).
+//
+// Replaces optimizer.optimize(20) of Optimizer::OptimizeEssentialGraph{LoopClosure,MapFusion} (S/Optimizer.cpp:1277, :1513):
+//   vertex  VertexSim3Expmap, oplus = Sim3(update) * estimate, update[6] := 0 when _fix_scale  (G/types/types_seven_dof_expmap.h:60-69)
+//   edge    EdgeSim3, e = log(C * S_i * S_j^-1), information = I7                               (:105-114, S/Optimizer.cpp:1125)
+//   solver  BlockSolver_7_3 without Schur, Levenberg with user lambda 1e-16                     (S/Optimizer.cpp:1066-1072)
+// The reference differentiates numerically (central differences, delta = 1e-9, G/core/base_binary_edge.hpp:131-205);
+// k_pgo_linearize does the same per edge (one thread per edge, 28 error evaluations) so that the Jacobians carry the same
+// discretisation, then scatters J^T J / J^T e into the 7x7 block-CSR Hessian with red.add.f64.  The linear solve is the
+// shared persistent PCG (pcg.cuh, BS = 7) instead of the reference's sparse LDL^T.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <limits>
+
+#include "ba_math.cuh"
+#include "common.cuh"
+#include "pcg.cuh"
+
+using namespace ccm;
+
+namespace {
+
+struct S3 { double qx, qy, qz, qw, tx, ty, tz, s; };
+
+CCM_HD S3 s3_load(const double* p) { return S3{p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7]}; }
+CCM_HD void s3_store(const S3& a, double* p) { p[0] = a.qx; p[1] = a.qy; p[2] = a.qz; p[3] = a.qw; p[4] = a.tx; p[5] = a.ty; p[6] = a.tz; p[7] = a.s; }
+
+CCM_HD S3 s3_mul(const S3& a, const S3& b) {  // G/types/sim3.h:266-272 (no quaternion normalisation)
+  S3 r;
+  r.qw = a.qw * b.qw - a.qx * b.qx - a.qy * b.qy - a.qz * b.qz;
+  r.qx = a.qw * b.qx + a.qx * b.qw + a.qy * b.qz - a.qz * b.qy;
+  r.qy = a.qw * b.qy + a.qy * b.qw + a.qz * b.qx - a.qx * b.qz;
+  r.qz = a.qw * b.qz + a.qz * b.qw + a.qx * b.qy - a.qy * b.qx;
+  double rx, ry, rz;
+  quat_rotate(a.qx, a.qy, a.qz, a.qw, b.tx, b.ty, b.tz, rx, ry, rz);
+  r.tx = a.s * rx + a.tx; r.ty = a.s * ry + a.ty; r.tz = a.s * rz + a.tz;
+  r.s = a.s * b.s;
+  return r;
+}
+
+CCM_HD S3 s3_inv(const S3& a) {  // G/types/sim3.h:233-236
+  S3 r;
+  r.qx = -a.qx; r.qy = -a.qy; r.qz = -a.qz; r.qw = a.qw;
+  const double k = -1. / a.s;
+  quat_rotate(r.qx, r.qy, r.qz, r.qw, k * a.tx, k * a.ty, k * a.tz, r.tx, r.ty, r.tz);
+  r.s = 1. / a.s;
+  return r;
+}
+
+// coefficients A, B, C of W = A*Omega + B*Omega^2 + C*I shared by exp and log (G/types/sim3.h:88-135, 166-208)
+CCM_HD void s3_abc(double sigma, double s, double theta, bool small_theta, double& A, double& B, double& C) {
+  const double eps = 0.00001;
+  if (fabs(sigma) < eps) {
+    C = 1;
+    if (small_theta) { A = 1. / 2.; B = 1. / 6.; }
+    else {
+      const double theta2 = theta * theta;
+      A = (1 - cos(theta)) / theta2;
+      B = (theta - sin(theta)) / (theta2 * theta);
+    }
+  } else {
+    C = (s - 1) / sigma;
+    if (small_theta) {
+      const double sigma2 = sigma * sigma;
+      A = ((sigma - 1) * s + 1) / sigma2;
+      B = ((0.5 * sigma2 - sigma + 1) * s) / (sigma2 * sigma);
+    } else {
+      const double a = s * sin(theta), b = s * cos(theta);
+      const double theta2 = theta * theta, sigma2 = sigma * sigma;
+      const double c = theta2 + sigma2;
+      A = (a * sigma + (1 - b) * theta) / (theta * c);
+      B = (C - ((b - 1) * sigma + a * theta) / (c)) * 1. / (theta2);
+    }
+  }
+}
+
+CCM_HD S3 s3_exp(const double u[7]) {  // Sim3(Vector7d), G/types/sim3.h:70-142
+  const double ox = u[0], oy = u[1], oz = u[2], sigma = u[6];
+  const double theta2 = ox * ox + oy * oy + oz * oz, theta = sqrt(theta2);
+  const double eps = 0.00001;
+  S3 r;
+  r.s = exp(sigma);
+  double A, B, C;
+  s3_abc(sigma, r.s, theta, theta < eps, A, B, C);
+  double ra, rb;  // R = I + ra*Omega + rb*Omega^2
+  if (theta < eps) { ra = 1.0; rb = 1.0; }
+  else { ra = sin(theta) / theta; rb = (1 - cos(theta)) / (theta * theta); }
+  const double Om[9] = {0, -oz, oy, oz, 0, -ox, -oy, ox, 0};
+  const double O2[9] = {ox * ox - theta2, ox * oy, ox * oz, ox * oy, oy * oy - theta2, oy * oz, ox * oz, oy * oz, oz * oz - theta2};
+  double R[9], W[9];
+#pragma unroll
+  for (int i = 0; i < 9; i++) {
+    const double id = (i == 0 || i == 4 || i == 8) ? 1.0 : 0.0;
+    R[i] = id + ra * Om[i] + rb * O2[i];
+    W[i] = A * Om[i] + B * O2[i] + C * id;
+  }
+  R_to_quat(R, r.qx, r.qy, r.qz, r.qw);
+  r.tx = W[0] * u[3] + W[1] * u[4] + W[2] * u[5];
+  r.ty = W[3] * u[3] + W[4] * u[4] + W[5] * u[5];
+  r.tz = W[6] * u[3] + W[7] * u[4] + W[8] * u[5];
+  return r;
+}
+
+CCM_HD void s3_log(const S3& S, double res[7]) {  // Sim3::log, G/types/sim3.h:148-230
+  const double sigma = log(S.s);
+  double R[9];
+  quat_to_R(S.qx, S.qy, S.qz, S.qw, R);
+  const double d = 0.5 * (R[0] + R[4] + R[8] - 1);
+  const double eps = 0.00001;
+  const bool small_theta = d > 1 - eps;
+  const double dR[3] = {R[7] - R[5], R[2] - R[6], R[3] - R[1]};
+  double om[3], theta = 0.0;
+  if (small_theta) {
+    om[0] = 0.5 * dR[0]; om[1] = 0.5 * dR[1]; om[2] = 0.5 * dR[2];
+  } else {
+    theta = acos(d);
+    const double f = theta / (2 * sqrt(1 - d * d));
+    om[0] = f * dR[0]; om[1] = f * dR[1]; om[2] = f * dR[2];
+  }
+  double A, B, C;
+  s3_abc(sigma, S.s, theta, small_theta, A, B, C);
+  const double ox = om[0], oy = om[1], oz = om[2];
+  const double n2 = ox * ox + oy * oy + oz * oz;
+  const double Om[9] = {0, -oz, oy, oz, 0, -ox, -oy, ox, 0};
+  const double O2[9] = {ox * ox - n2, ox * oy, ox * oz, ox * oy, oy * oy - n2, oy * oz, ox * oz, oy * oz, oz * oz - n2};
+  double W[9];
+#pragma unroll
+  for (int i = 0; i < 9; i++) W[i] = A * Om[i] + B * O2[i] + C * ((i == 0 || i == 4 || i == 8) ? 1.0 : 0.0);
+  // upsilon = W.lu().solve(t): Gaussian elimination with partial pivoting
+  double y[3] = {S.tx, S.ty, S.tz};
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    int piv = k;
+    double best = fabs(W[k * 3 + k]);
+    for (int i = k + 1; i < 3; i++)
+      if (fabs(W[i * 3 + k]) > best) { best = fabs(W[i * 3 + k]); piv = i; }
+    if (piv != k) {
+      for (int j = 0; j < 3; j++) { const double t = W[k * 3 + j]; W[k * 3 + j] = W[piv * 3 + j]; W[piv * 3 + j] = t; }
+      const double t = y[k]; y[k] = y[piv]; y[piv] = t;
+    }
+    for (int i = k + 1; i < 3; i++) {
+      const double f = W[i * 3 + k] / W[k * 3 + k];
+      for (int j = k + 1; j < 3; j++) W[i * 3 + j] -= f * W[k * 3 + j];
+      y[i] -= f * y[k];
+    }
+  }
+  double ups[3];
+  ups[2] = y[2] / W[8];
+  ups[1] = (y[1] - W[5] * ups[2]) / W[4];
+  ups[0] = (y[0] - W[1] * ups[1] - W[2] * ups[2]) / W[0];
+  res[0] = om[0]; res[1] = om[1]; res[2] = om[2];
+  res[3] = ups[0]; res[4] = ups[1]; res[5] = ups[2];
+  res[6] = sigma;
+}
+
+CCM_HD void edge_error(const S3& C, const S3& vi, const S3& vj, double e[7]) {
+  s3_log(s3_mul(s3_mul(C, vi), s3_inv(vj)), e);
+}
+
+CCM_HD S3 s3_oplus(const S3& v, double u[7], int fix_scale) {
+  if (fix_scale) u[6] = 0;
+  return s3_mul(s3_exp(u), v);
+}
+
+struct PgoEdge { int i, j, ai, aj, idx_ii, idx_jj, idx_ij; int ij_transposed; };  // ai/aj: free index or -1
+
+__global__ void __launch_bounds__(128) k_pgo_error(const double* __restrict__ v, const PgoEdge* __restrict__ edges,
+                                                   const double* __restrict__ meas, int E, double* __restrict__ partials) {
+  __shared__ double red[4];
+  double acc = 0.0;
+  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < E; e += gridDim.x * blockDim.x) {
+    double err[7];
+    edge_error(s3_load(meas + 8 * (size_t)e), s3_load(v + 8 * (size_t)edges[e].i), s3_load(v + 8 * (size_t)edges[e].j), err);
+#pragma unroll
+    for (int k = 0; k < 7; k++) acc += err[k] * err[k];
+  }
+  const double t = block_sum(acc, red);
+  if (threadIdx.x == 0) partials[blockIdx.x] = t;
+}
+
+// one thread per edge: error, numeric Jacobians (central differences through oplus), scatter into H and b
+__global__ void __launch_bounds__(64) k_pgo_linearize(const double* __restrict__ v, const PgoEdge* __restrict__ edges,
+                                                      const double* __restrict__ meas, int E, int fix_scale,
+                                                      double* __restrict__ H, double* __restrict__ b) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= E) return;
+  const PgoEdge ed = edges[e];
+  const S3 C = s3_load(meas + 8 * (size_t)e), vi = s3_load(v + 8 * (size_t)ed.i), vj = s3_load(v + 8 * (size_t)ed.j);
+  double err[7];
+  edge_error(C, vi, vj, err);
+  const double delta = 1e-9, scalar = 1.0 / (2 * delta);
+  double Ji[49], Jj[49];
+  for (int side = 0; side < 2; side++) {
+    double* J = side ? Jj : Ji;
+    const bool free_v = (side ? ed.aj : ed.ai) >= 0;
+    for (int d = 0; d < 7; d++) {
+      double ep[7], em[7], add[7] = {0, 0, 0, 0, 0, 0, 0};
+      if (free_v) {
+        add[d] = delta;
+        if (side) edge_error(C, vi, s3_oplus(vj, add, fix_scale), ep); else edge_error(C, s3_oplus(vi, add, fix_scale), vj, ep);
+        add[d] = -delta;
+        if (side) edge_error(C, vi, s3_oplus(vj, add, fix_scale), em); else edge_error(C, s3_oplus(vi, add, fix_scale), vj, em);
+      }
+      for (int r = 0; r < 7; r++) J[r * 7 + d] = free_v ? scalar * (ep[r] - em[r]) : 0.0;
+    }
+  }
+  if (ed.ai >= 0) {
+    for (int r = 0; r < 7; r++) {
+      double g = 0;
+      for (int k = 0; k < 7; k++) g -= Ji[k * 7 + r] * err[k];
+      atomicAdd(b + (size_t)ed.ai * 7 + r, g);
+      for (int c = 0; c < 7; c++) {
+        double hh = 0;
+        for (int k = 0; k < 7; k++) hh += Ji[k * 7 + r] * Ji[k * 7 + c];
+        atomicAdd(H + (size_t)ed.idx_ii * 49 + r * 7 + c, hh);
+      }
+    }
+  }
+  if (ed.aj >= 0) {
+    for (int r = 0; r < 7; r++) {
+      double g = 0;
+      for (int k = 0; k < 7; k++) g -= Jj[k * 7 + r] * err[k];
+      atomicAdd(b + (size_t)ed.aj * 7 + r, g);
+      for (int c = 0; c < 7; c++) {
+        double hh = 0;
+        for (int k = 0; k < 7; k++) hh += Jj[k * 7 + r] * Jj[k * 7 + c];
+        atomicAdd(H + (size_t)ed.idx_jj * 49 + r * 7 + c, hh);
+      }
+    }
+  }
+  if (ed.ai >= 0 && ed.aj >= 0 && ed.ai != ed.aj) {
+    // block (ai, aj) += Ji^T Jj and its mirror (aj, ai) += Jj^T Ji: the PCG works on the full symmetric block-CSR
+    for (int r = 0; r < 7; r++)
+      for (int c = 0; c < 7; c++) {
+        double hh = 0;
+        for (int k = 0; k < 7; k++) hh += Ji[k * 7 + r] * Jj[k * 7 + c];
+        atomicAdd(H + (size_t)ed.idx_ij * 49 + r * 7 + c, hh);
+        atomicAdd(H + (size_t)ed.ij_transposed * 49 + c * 7 + r, hh);
+      }
+  }
+}
+
+// per free vertex: Hd = H + lambda I on the diagonal block (written to Hs), Minv = inverse of that block (Gauss-Jordan)
+__global__ void __launch_bounds__(64) k_pgo_damp(const double* __restrict__ H, double* __restrict__ Hs, long long nnz49,
+                                                 const int* __restrict__ diag, int n, double lambda, double* __restrict__ Minv,
+                                                 double* __restrict__ maxdiag_bits, int* __restrict__ fail) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (long long k = i; k < nnz49; k += (long long)gridDim.x * blockDim.x) Hs[k] = H[k];
+  (void)maxdiag_bits;
+  if (i >= n) return;
+  double A[49], I[49];
+  const double* src = H + (size_t)diag[i] * 49;
+  for (int k = 0; k < 49; k++) { A[k] = src[k]; I[k] = 0.0; }
+  for (int k = 0; k < 7; k++) { A[k * 8] += lambda; I[k * 8] = 1.0; }
+  bool ok = true;
+  for (int c = 0; c < 7; c++) {
+    int piv = c;
+    double best = fabs(A[c * 7 + c]);
+    for (int r = c + 1; r < 7; r++)
+      if (fabs(A[r * 7 + c]) > best) { best = fabs(A[r * 7 + c]); piv = r; }
+    if (!(best > 0.0)) { ok = false; break; }
+    if (piv != c)
+      for (int k = 0; k < 7; k++) {
+        double t = A[c * 7 + k]; A[c * 7 + k] = A[piv * 7 + k]; A[piv * 7 + k] = t;
+        t = I[c * 7 + k]; I[c * 7 + k] = I[piv * 7 + k]; I[piv * 7 + k] = t;
+      }
+    const double ip = 1.0 / A[c * 7 + c];
+    for (int k = 0; k < 7; k++) { A[c * 7 + k] *= ip; I[c * 7 + k] *= ip; }
+    for (int r = 0; r < 7; r++) {
+      if (r == c) continue;
+      const double f = A[r * 7 + c];
+      for (int k = 0; k < 7; k++) { A[r * 7 + k] -= f * A[c * 7 + k]; I[r * 7 + k] -= f * I[c * 7 + k]; }
+    }
+  }
+  for (int k = 0; k < 49; k++) Minv[(size_t)i * 49 + k] = ok ? I[k] : (k % 8 == 0 ? 1.0 : 0.0);
+  if (!ok) atomicExch(fail, 1);
+}
+
+__global__ void k_pgo_add_lambda(double* __restrict__ Hs, const int* __restrict__ diag, int n, double lambda) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * 7) return;
+  Hs[(size_t)diag[i / 7] * 49 + (i % 7) * 8] += lambda;
+}
+
+__global__ void __launch_bounds__(128) k_pgo_update(const double* __restrict__ v, const int* __restrict__ vidx,
+                                                    const double* __restrict__ x, const double* __restrict__ b, int K,
+                                                    int fix_scale, double lambda, double* __restrict__ vt,
+                                                    double* __restrict__ partials) {
+  __shared__ double red[4];
+  double acc = 0.0;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < K; k += gridDim.x * blockDim.x) {
+    S3 s = s3_load(v + 8 * (size_t)k);
+    const int a = vidx[k];
+    if (a >= 0) {
+      double u[7];
+      for (int d = 0; d < 7; d++) u[d] = x[(size_t)a * 7 + d];
+      if (fix_scale) u[6] = 0;  // oplusImpl zeroes the solver's x[6] in place before computeScale reads it
+      for (int d = 0; d < 7; d++) acc += u[d] * (lambda * u[d] + b[(size_t)a * 7 + d]);
+      s = s3_oplus(s, u, fix_scale);
+    }
+    s3_store(s, vt + 8 * (size_t)k);
+  }
+  const double t = block_sum(acc, red);
+  if (threadIdx.x == 0) partials[blockIdx.x] = t;
+}
+
+__global__ void __launch_bounds__(1024) k_sum(const double* __restrict__ p, int n, double* __restrict__ out) {
+  __shared__ double red[32];
+  double v = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) v += p[i];
+  const double t = block_sum(v, red);
+  if (threadIdx.x == 0) out[0] = t;
+}
+
+__global__ void k_pgo_maxdiag(const double* __restrict__ H, const int* __restrict__ diag, int n, unsigned long long* out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n * 7) return;
+  const double v = fabs(H[(size_t)diag[i / 7] * 49 + (i % 7) * 8]);
+  atomicMax(out, (unsigned long long)__double_as_longlong(v));
+}
+
+void pgo_solve(const ccm_pgo_problem* p, const ccm_pgo_options* o, ccm_pgo_result* r) {
+  const auto T0 = std::chrono::steady_clock::now();
+  ensure_device();
+  CCM_REQUIRE(p && o && r && p->K > 0 && p->E >= 0 && p->sim3 && p->fixed && r->sim3, "ccm_pgo_solve: bad argument");
+  cudaStream_t s;
+  CCM_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamDestroy(s); } } sg{s};
+  const int K = p->K, E = p->E;
+  // active set (edges with at least one free vertex) and index mapping
+  std::vector<char> has(K, 0);
+  std::vector<int> act;
+  for (int e = 0; e < E; e++) {
+    const int i = p->edge_i[e], j = p->edge_j[e];
+    CCM_REQUIRE(i >= 0 && i < K && j >= 0 && j < K, "ccm_pgo_solve: edge index out of range");
+    if (p->fixed[i] && p->fixed[j]) continue;
+    act.push_back(e);
+    has[i] = has[j] = 1;
+  }
+  std::vector<int> vidx(K, -1), idxv;
+  for (int k = 0; k < K; k++)
+    if (has[k] && !p->fixed[k]) { vidx[k] = (int)idxv.size(); idxv.push_back(k); }
+  const int n = (int)idxv.size(), Ea = (int)act.size();
+  r->trace_len = 0; r->iters_done = 0; r->chi2_initial = r->chi2_final = 0; r->lambda_final = 0;
+  memcpy(r->sim3, p->sim3, sizeof(double) * 8 * K);
+  if (n == 0 || Ea == 0) { r->iters_done = -1; return; }
+  // full symmetric block-CSR pattern
+  std::vector<std::vector<int>> rows(n);
+  for (int a = 0; a < n; a++) rows[a].push_back(a);
+  for (int e : act) {
+    const int a = vidx[p->edge_i[e]], b = vidx[p->edge_j[e]];
+    if (a >= 0 && b >= 0 && a != b) { rows[a].push_back(b); rows[b].push_back(a); }
+  }
+  std::vector<int> rowptr(n + 1, 0), col, diag(n);
+  for (int a = 0; a < n; a++) {
+    std::sort(rows[a].begin(), rows[a].end());
+    rows[a].erase(std::unique(rows[a].begin(), rows[a].end()), rows[a].end());
+    col.insert(col.end(), rows[a].begin(), rows[a].end());
+    rowptr[a + 1] = (int)col.size();
+  }
+  auto find = [&](int a, int b) {
+    const int* bb = col.data() + rowptr[a];
+    const int* ee = col.data() + rowptr[a + 1];
+    return (int)(std::lower_bound(bb, ee, b) - col.data());
+  };
+  for (int a = 0; a < n; a++) diag[a] = find(a, a);
+  std::vector<PgoEdge> edges(Ea);
+  std::vector<double> meas((size_t)Ea * 8);
+  for (int k = 0; k < Ea; k++) {
+    const int e = act[k];
+    PgoEdge& ed = edges[k];
+    ed.i = p->edge_i[e]; ed.j = p->edge_j[e]; ed.ai = vidx[ed.i]; ed.aj = vidx[ed.j];
+    ed.idx_ii = ed.ai >= 0 ? diag[ed.ai] : 0; ed.idx_jj = ed.aj >= 0 ? diag[ed.aj] : 0;
+    ed.idx_ij = (ed.ai >= 0 && ed.aj >= 0 && ed.ai != ed.aj) ? find(ed.ai, ed.aj) : 0;
+    ed.ij_transposed = (ed.ai >= 0 && ed.aj >= 0 && ed.ai != ed.aj) ? find(ed.aj, ed.ai) : 0;
+    memcpy(&meas[(size_t)k * 8], p->meas + 8 * (size_t)e, 8 * sizeof(double));
+  }
+  const long long nnzb = (long long)col.size();
+  DevBuf<double> d_v, d_vt, d_meas, H, Hs, b, Minv, x, pr, pz, pp, pq, partials, scal, pcg_partials, pcg_status;
+  DevBuf<int> d_vidx, d_rowptr, d_col, d_diag, fail;
+  DevBuf<PgoEdge> d_edges;
+  DevBuf<unsigned> bar;
+  d_v.upload(p->sim3, (size_t)K * 8, s); d_vt.alloc((size_t)K * 8);
+  d_meas.upload(meas.data(), meas.size(), s); d_edges.upload(edges.data(), Ea, s);
+  d_vidx.upload(vidx.data(), K, s); d_rowptr.upload(rowptr.data(), n + 1, s); d_col.upload(col.data(), nnzb, s);
+  d_diag.upload(diag.data(), n, s);
+  H.alloc(nnzb * 49); Hs.alloc(nnzb * 49); b.alloc((size_t)n * 7); Minv.alloc((size_t)n * 49);
+  x.alloc_zero((size_t)n * 7, s); pr.alloc((size_t)n * 7); pz.alloc((size_t)n * 7); pp.alloc((size_t)n * 7); pq.alloc((size_t)n * 7);
+  const int gsm = sm_count();
+  partials.alloc((size_t)gsm * 8 + 8); scal.alloc_zero(8, s); pcg_status.alloc_zero(4, s); bar.alloc_zero(1, s); fail.alloc_zero(1, s);
+  int per_sm = 0;
+  CCM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg<7>, TPB, 0));
+  const int pcg_grid = std::max(1, std::min(std::max(1, std::min(per_sm, 4)) * gsm, div_up((long long)n * 32, TPB)));
+  pcg_partials.alloc((size_t)3 * pcg_grid);
+  double* h_scal = nullptr;
+  CCM_CUDA(cudaMallocHost((void**)&h_scal, 8 * sizeof(double)));
+  struct HostGuard { double* p; ~HostGuard() { cudaFreeHost(p); } } hg{h_scal};
+  double *cur = d_v.p, *trial = d_vt.p;
+  const int pcg_max = o->pcg_max_iter > 0 ? o->pcg_max_iter : 5000;
+  const double pcg_tol = o->pcg_tol > 0 ? o->pcg_tol : 1e-10;
+  auto terminate = [&] { return o->stop && *o->stop; };
+  auto chi2_of = [&](const double* state, double* dev_out) {
+    const int g = std::max(1, std::min(div_up(Ea, 128), gsm * 8));
+    k_pgo_error<<<g, 128, 0, s>>>(state, d_edges.p, d_meas.p, Ea, partials.p);
+    CCM_LAUNCHED();
+    k_sum<<<1, 1024, 0, s>>>(partials.p, g, dev_out);
+    CCM_LAUNCHED();
+  };
+  double lambda = -1, ni = 2;
+  int nBad = 0, ret = 0;
+  bool ok = true;
+  for (int it = 0; it < o->iterations && !terminate() && ok; it++) {
+    chi2_of(cur, scal.p);
+    CCM_CUDA(cudaMemsetAsync(H.p, 0, H.bytes(), s));
+    CCM_CUDA(cudaMemsetAsync(b.p, 0, b.bytes(), s));
+    k_pgo_linearize<<<div_up(Ea, 64), 64, 0, s>>>(cur, d_edges.p, d_meas.p, Ea, p->fix_scale, H.p, b.p);
+    CCM_LAUNCHED();
+    if (it == 0 && !(o->lambda_init > 0)) {
+      CCM_CUDA(cudaMemsetAsync(scal.p + 4, 0, sizeof(double), s));
+      k_pgo_maxdiag<<<div_up(n * 7, 128), 128, 0, s>>>(H.p, d_diag.p, n, reinterpret_cast<unsigned long long*>(scal.p + 4));
+      CCM_LAUNCHED();
+    }
+    CCM_CUDA(cudaMemcpyAsync(h_scal, scal.p, 5 * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CCM_CUDA(cudaStreamSynchronize(s));
+    double currentChi = h_scal[0];
+    const double iniChi = currentChi;
+    if (it == 0) {
+      r->chi2_initial = currentChi;
+      lambda = o->lambda_init > 0 ? o->lambda_init : 1e-5 * h_scal[4];
+      ni = 2; nBad = 0;
+    }
+    double rho = 0, tempChi = currentChi, lambda_used = lambda, relres = 0;
+    int qmax = 0, pcg_it = 0;
+    do {
+      lambda_used = lambda;
+      CCM_CUDA(cudaMemsetAsync(fail.p, 0, sizeof(int), s));
+      k_pgo_damp<<<std::max(div_up(n, 64), std::min(div_up(nnzb * 49, 64), gsm * 16)), 64, 0, s>>>(
+          H.p, Hs.p, nnzb * 49, d_diag.p, n, lambda, Minv.p, nullptr, fail.p);
+      CCM_LAUNCHED();
+      k_pgo_add_lambda<<<div_up(n * 7, 128), 128, 0, s>>>(Hs.p, d_diag.p, n, lambda);
+      CCM_LAUNCHED();
+      CCM_CUDA(cudaMemsetAsync(bar.p, 0, sizeof(unsigned), s));
+      PcgArgs a;
+      a.n = n; a.rowptr = d_rowptr.p; a.col = d_col.p; a.val = Hs.p; a.Minv = Minv.p; a.b = b.p;
+      a.x = x.p; a.r = pr.p; a.z = pz.p; a.p = pp.p; a.q = pq.p; a.partials = pcg_partials.p; a.bar = bar.p;
+      a.tol = pcg_tol; a.max_iter = pcg_max; a.status = pcg_status.p;
+      void* args[] = {&a};
+      CCM_CUDA(cudaLaunchCooperativeKernel((void*)k_pcg<7>, dim3(pcg_grid), dim3(TPB), args, 0, s));
+      CCM_LAUNCHED();
+      const int g = std::max(1, std::min(div_up(K, 128), gsm * 8));
+      k_pgo_update<<<g, 128, 0, s>>>(cur, d_vidx.p, x.p, b.p, K, p->fix_scale, lambda, trial, partials.p);
+      CCM_LAUNCHED();
+      k_sum<<<1, 1024, 0, s>>>(partials.p, g, scal.p + 1);
+      CCM_LAUNCHED();
+      chi2_of(trial, scal.p + 2);
+      CCM_CUDA(cudaMemcpyAsync(h_scal, scal.p, 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+      CCM_CUDA(cudaMemcpyAsync(h_scal + 3, pcg_status.p, 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+      CCM_CUDA(cudaMemcpyAsync(h_scal + 6, fail.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+      CCM_CUDA(cudaStreamSynchronize(s));
+      int jfail;
+      memcpy(&jfail, h_scal + 6, sizeof(int));
+      tempChi = h_scal[2];
+      pcg_it = (int)h_scal[3]; relres = h_scal[4];
+      const bool ok2 = !((int)h_scal[5] == 2 || jfail);
+      if (!ok2) tempChi = std::numeric_limits<double>::max();
+      rho = currentChi - tempChi;
+      double scale = h_scal[1];
+      scale += 1e-3;
+      rho /= scale;
+      if (rho > 0 && std::isfinite(tempChi)) {
+        double alpha = 1. - std::pow((2 * rho - 1), 3);
+        alpha = std::min(alpha, 2. / 3.);
+        lambda *= std::max(1. / 3., alpha);
+        ni = 2;
+        currentChi = tempChi;
+        std::swap(cur, trial);
+      } else {
+        lambda *= ni;
+        ni *= 2;
+      }
+      qmax++;
+    } while (rho < 0 && qmax < 10 && !terminate());
+    ret++;
+    if (r->trace && r->trace_len < r->trace_cap) {
+      double* tr = r->trace + (size_t)r->trace_len * CCM_TRACE_COLS;
+      tr[0] = it; tr[1] = lambda_used; tr[2] = currentChi; tr[3] = rho; tr[4] = qmax; tr[5] = lambda; tr[6] = pcg_it; tr[7] = relres;
+      r->trace_len++;
+    }
+    r->chi2_final = currentChi; r->lambda_final = lambda;
+    if (qmax == 10 || rho == 0) { ok = false; continue; }
+    if ((iniChi - currentChi) * 1e3 < iniChi) nBad++; else nBad = 0;
+    if (nBad >= 3) { ok = false; continue; }
+  }
+  r->iters_done = ret;
+  CCM_CUDA(cudaMemcpyAsync(r->sim3, cur, sizeof(double) * 8 * K, cudaMemcpyDeviceToHost, s));
+  CCM_CUDA(cudaStreamSynchronize(s));
+  r->t_total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - T0).count();
+}
+
+}  // namespace
+
+extern "C" int ccm_pgo_solve(const ccm_pgo_problem* p, const ccm_pgo_options* o, ccm_pgo_result* r) {
+  return guarded([&] { pgo_solve(p, o, r); });
+}
