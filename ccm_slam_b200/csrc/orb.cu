@@ -65,9 +65,9 @@ __global__ void k_resize(const uint8_t* __restrict__ src, int sw, int sh, uint8_
 }
 
 // ---- FAST per cell -----------------------------------------------------------------------------------------------
-__device__ __forceinline__ int corner_score(const uint8_t* t, int stride, int x, int y) {
+__device__ __forceinline__ int corner_score(const uint8_t* t, int stride, int x, int y, int lo_th) {
   const int v = t[y * stride + x];
-  int d[25];
+  int d[16];
   d[0] = v - t[(y + 3) * stride + x];       d[1] = v - t[(y + 3) * stride + x + 1];
   d[2] = v - t[(y + 2) * stride + x + 2];   d[3] = v - t[(y + 1) * stride + x + 3];
   d[4] = v - t[y * stride + x + 3];         d[5] = v - t[(y - 1) * stride + x + 3];
@@ -76,23 +76,39 @@ __device__ __forceinline__ int corner_score(const uint8_t* t, int stride, int x,
   d[10] = v - t[(y - 2) * stride + x - 2];  d[11] = v - t[(y - 1) * stride + x - 3];
   d[12] = v - t[y * stride + x - 3];        d[13] = v - t[(y + 1) * stride + x - 3];
   d[14] = v - t[(y + 2) * stride + x - 2];  d[15] = v - t[(y + 3) * stride + x - 1];
+  // cornerScore<16> = the largest threshold t for which 9 contiguous ring pixels are all darker than v - t or all
+  // brighter than v + t.  "Is a corner at t" is monotone in t, so the score is found by bisection on t with a 16-bit
+  // ring mask per polarity and a run-length test (a min/max formulation over the 16 arcs compiled to wrong VIMNMX3
+  // chains with nvcc 12.9 for sm_100a, so the test is written with compares and bit operations only).
+  auto corner_at = [&](int t) -> bool {
+    unsigned dark = 0, bright = 0;
 #pragma unroll
-  for (int k = 16; k < 25; k++) d[k] = d[k - 16];
-  int best = -1000;
-#pragma unroll
-  for (int k = 0; k < 16; k++) {
-    int mn = d[k], mx = d[k];
-#pragma unroll
-    for (int i = 1; i < 9; i++) { mn = min(mn, d[k + i]); mx = max(mx, d[k + i]); }
-    best = max(best, max(mn, -mx));
+    for (int i = 0; i < 16; i++) {
+      dark |= (d[i] > t ? 1u : 0u) << i;
+      bright |= (d[i] < -t ? 1u : 0u) << i;
+    }
+    unsigned m = dark | (dark << 16);
+    unsigned r = m & (m >> 1); r &= r >> 2; r &= r >> 4; r &= m >> 8;   // bit i: 9 consecutive ones starting at i
+    unsigned hit = r & 0xffffu;
+    m = bright | (bright << 16);
+    r = m & (m >> 1); r &= r >> 2; r &= r >> 4; r &= m >> 8;
+    hit |= r & 0xffffu;
+    return hit != 0u;
+  };
+  if (!corner_at(lo_th)) return -1;  // not even a corner at the lowest threshold anyone asks for
+  int lo = lo_th, hi = 255;          // corner_at(lo) holds, corner_at(hi) does not (|d| <= 255)
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (corner_at(mid)) lo = mid; else hi = mid;
   }
-  return best - 1;  // cornerScore<16>: largest threshold for which the pixel is still a 9/16 corner
+  return lo;
 }
 
 // dynamic smem: tile (u8, tw*th) | score (short, tw*th) | flag (u8, tw*th)
 __global__ void __launch_bounds__(256) k_fast_cells(const uint8_t* __restrict__ pyr, const Cell* __restrict__ cells,
                                                     int ini_th, int min_th, int tile_cap, int max_per_cell,
-                                                    int* __restrict__ cell_count, ushort4* __restrict__ cell_out) {
+                                                    int* __restrict__ cell_count, ushort4* __restrict__ cell_out,
+                                                    int dbg_cell, int* __restrict__ dbg) {
   extern __shared__ unsigned char smem[];
   const Cell c = cells[blockIdx.x];
   const int tw = c.x1 - c.x0, th = c.y1 - c.y0;
@@ -117,7 +133,7 @@ __global__ void __launch_bounds__(256) k_fast_cells(const uint8_t* __restrict__ 
   const int iw = tw - 6, ih = th - 6, ni = iw * ih;
   for (int i = threadIdx.x; i < ni; i += blockDim.x) {
     const int y = 3 + i / iw, x = 3 + i % iw;
-    const int s = corner_score(tile, tw, x, y);
+    const int s = corner_score(tile, tw, x, y, min_th);
     score[y * tw + x] = (short)(s >= min_th ? s : 0);  // the reference's score buffer: 0 for non-corners
   }
   __syncthreads();
@@ -159,6 +175,11 @@ __global__ void __launch_bounds__(256) k_fast_cells(const uint8_t* __restrict__ 
       base += __popc(m);
     }
     if (threadIdx.x == 0) cell_count[blockIdx.x] = min(base, max_per_cell);
+  }
+  if (dbg && (int)blockIdx.x == dbg_cell) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { dbg[i] = tile[i]; dbg[n + i] = score[i]; dbg[2 * n + i] = flag[i]; }
+    if (threadIdx.x == 0) { dbg[3 * n] = n_ini; dbg[3 * n + 1] = tw; dbg[3 * n + 2] = th; }
   }
 }
 
@@ -474,6 +495,8 @@ struct ccm_orb_handle {
   DevBuf<ushort4> cell_out;
   DevBuf<Cand> cand;
   DevBuf<KpIn> kp_in;
+  DevBuf<int> dbg;
+  int dbg_cell = -1;
   uint8_t* h_img = nullptr;   // pinned staging
   Cand* h_cand = nullptr;     // pinned
   int* h_total = nullptr;     // pinned
@@ -638,7 +661,7 @@ void orb_extract(ccm_orb_handle* h, const uint8_t* img, int stride, ccm_keypoint
   }
   const size_t smem = ((size_t)h->tile_cap + 15) / 16 * 16 + 3 * (size_t)h->tile_cap + 16;
   k_fast_cells<<<h->ncells, 256, smem, s>>>(h->pyr.p, h->cells.p, h->cfg.ini_th_fast, h->cfg.min_th_fast, h->tile_cap,
-                                            h->max_per_cell, h->cell_count.p, h->cell_out.p);
+                                            h->max_per_cell, h->cell_count.p, h->cell_out.p, h->dbg_cell, h->dbg.p);
   CCM_LAUNCHED();
   k_scan_cells<<<1, 1024, 0, s>>>(h->cell_count.p, h->ncells, h->cell_off.p);
   CCM_LAUNCHED();
@@ -734,6 +757,19 @@ extern "C" int ccm_orb_extract(ccm_orb_handle* h, const uint8_t* img, int32_t st
   });
 }
 
+// debug: the candidate list of the last ccm_orb_extract call (x, y relative to minBorder, score, level), reference order
+extern "C" int ccm_orb_debug_candidates(ccm_orb_handle* h, float* xys, int32_t* level, int32_t max_out, int32_t* n) {
+  return guarded([&] {
+    CCM_REQUIRE(h && n, "null argument");
+    const int total = std::min(h->h_total[0], h->max_cand);
+    *n = total;
+    for (int i = 0; i < std::min(total, max_out); i++) {
+      xys[3 * i] = h->h_cand[i].x; xys[3 * i + 1] = h->h_cand[i].y; xys[3 * i + 2] = (float)h->h_cand[i].score;
+      level[i] = h->h_cand[i].level;
+    }
+  });
+}
+
 extern "C" int ccm_orb_get_level(ccm_orb_handle* h, int32_t level, uint8_t* out, int32_t* w, int32_t* hgt) {
   return guarded([&] {
     CCM_REQUIRE(h && level >= 0 && level < h->cfg.nlevels, "ccm_orb_get_level: bad level");
@@ -744,6 +780,28 @@ extern "C" int ccm_orb_get_level(ccm_orb_handle* h, int32_t level, uint8_t* out,
       CCM_CUDA(cudaMemcpyAsync(out, h->pyr.p + h->loff[level], (size_t)h->lw[level] * h->lh[level], cudaMemcpyDeviceToHost, h->stream));
       CCM_CUDA(cudaStreamSynchronize(h->stream));
     }
+  });
+}
+
+extern "C" int ccm_orb_debug_dump(ccm_orb_handle* h, int32_t cell, int32_t* out, int32_t n_ints) {
+  return guarded([&] {
+    if (!h->dbg.p) { h->dbg.alloc_zero(16384, h->stream); CCM_CUDA(cudaStreamSynchronize(h->stream)); }
+    if (out) CCM_CUDA(cudaMemcpy(out, h->dbg.p, sizeof(int) * (size_t)std::min(n_ints, 16384), cudaMemcpyDeviceToHost));
+    h->dbg_cell = cell;
+  });
+}
+
+// debug: geometry + raw per-cell output of one FAST cell after the last extract call
+extern "C" int ccm_orb_debug_cell(ccm_orb_handle* h, int32_t cell, int32_t* geom8, uint16_t* entries4, int32_t* count) {
+  return guarded([&] {
+    CCM_REQUIRE(h && cell >= 0 && cell < h->ncells, "bad cell");
+    CCM_CUDA(cudaSetDevice(h->device));
+    Cell c;
+    CCM_CUDA(cudaMemcpy(&c, h->cells.p + cell, sizeof(Cell), cudaMemcpyDeviceToHost));
+    geom8[0] = c.level; geom8[1] = c.img_off; geom8[2] = c.img_w; geom8[3] = c.x0; geom8[4] = c.y0; geom8[5] = c.x1; geom8[6] = c.y1; geom8[7] = c.out_off;
+    CCM_CUDA(cudaMemcpy(count, h->cell_count.p + cell, sizeof(int), cudaMemcpyDeviceToHost));
+    CCM_CUDA(cudaMemcpy(entries4, h->cell_out.p + c.out_off, sizeof(ushort4) * (size_t)std::min(*count, h->max_per_cell), cudaMemcpyDeviceToHost));
+    geom8[1] = h->tile_cap; geom8[2] = h->max_per_cell;
   });
 }
 

@@ -220,6 +220,8 @@ int ccm_orb_extract(ccm_orb_handle* h, const uint8_t* img, int32_t stride, ccm_k
                     int32_t* n, uint8_t* desc);
 /* pyramid level readback (mvImagePyramid[level], public member of the reference class) */
 int ccm_orb_get_level(ccm_orb_handle* h, int32_t level, uint8_t* out, int32_t* w, int32_t* hgt);
+/* test hook: FAST candidates of the last extract call before the quadtree (3 floats each: x, y relative to the 16 px border, score) */
+int ccm_orb_debug_candidates(ccm_orb_handle* h, float* xys, int32_t* level, int32_t max_out, int32_t* n);
 void ccm_orb_destroy(ccm_orb_handle* h);
 
 /* ---- Hamming matching ----------------------------------------------------------------------------------
