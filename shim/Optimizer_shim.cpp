@@ -1,0 +1,287 @@
+// Optimizer_shim.cpp — reference-side translation unit: keeps cslam/include/cslam/Optimizer.h byte-identical and replaces
+// cslam/src/Optimizer.cpp for the entry points on the BA hot path.  Everything g2o did between "graph built" and "results
+// read back" is one call into libccm_b200.so; graph selection and write-back keep the reference's rules.
+//
+// NOT compiled in this repository's environment (needs the reference's OpenCV / Eigen / Boost / ROS headers).  It is the
+// binding a maintainer adds to cslam/CMakeLists.txt in place of src/Optimizer.cpp.
+// PoseOptimizationClient and OptimizeSim3 stay on the reference implementation (single vertex, out of scope: DESIGN.md §8);
+// compile them from the original file into a second TU or keep g2o linked for those two.
+#include <cslam/Optimizer.h>
+
+#include <unordered_map>
+
+#include "ccm_b200.h"
+
+namespace cslam {
+
+namespace {
+
+struct FlatBA {
+  std::vector<double> poses, intr, points;
+  std::vector<uint8_t> fixed;
+  std::vector<int32_t> obs_kf, obs_mp;
+  std::vector<float> obs_uv, obs_w;
+  std::vector<KeyFrame*> kf_of_row;   // raw pointers only for index lookup during flattening
+  std::unordered_map<KeyFrame*, int> row_of_kf;
+
+  int add_kf(const boost::shared_ptr<KeyFrame>& pKF, bool fix) {
+    const int row = (int)kf_of_row.size();
+    row_of_kf[pKF.get()] = row;
+    kf_of_row.push_back(pKF.get());
+    cv::Mat T = pKF->GetPose();                       // 4x4 CV_32F, Converter::toSE3Quat(pKF->GetPose())
+    double qt[7];
+    ccm_pose_from_Tcw_f32(T.ptr<float>(0), 1, qt);     // same R->q branches + normalisation as g2o::SE3Quat(R, t)
+    poses.insert(poses.end(), qt, qt + 7);
+    intr.push_back(pKF->fx); intr.push_back(pKF->fy); intr.push_back(pKF->cx); intr.push_back(pKF->cy);
+    fixed.push_back(fix ? 1 : 0);
+    return row;
+  }
+  int add_mp(const boost::shared_ptr<MapPoint>& pMP) {
+    cv::Mat X = pMP->GetWorldPos();
+    for (int i = 0; i < 3; i++) points.push_back(X.at<float>(i));
+    return (int)points.size() / 3 - 1;
+  }
+  void add_obs(int kf_row, int mp_row, const boost::shared_ptr<KeyFrame>& pKF, size_t idx) {
+    const cv::KeyPoint& kpUn = pKF->mvKeysUn[idx];
+    obs_kf.push_back(kf_row); obs_mp.push_back(mp_row);
+    obs_uv.push_back(kpUn.pt.x); obs_uv.push_back(kpUn.pt.y);
+    obs_w.push_back(pKF->mvInvLevelSigma2[kpUn.octave]);
+  }
+  ccm_ba_problem problem(const uint8_t* flags = nullptr) const {
+    ccm_ba_problem p;
+    p.K = (int32_t)fixed.size(); p.P = (int32_t)points.size() / 3; p.E = (int32_t)obs_kf.size();
+    p.poses = poses.data(); p.intr = intr.data(); p.fixed = fixed.data(); p.points = points.data();
+    p.obs_kf = obs_kf.data(); p.obs_mp = obs_mp.data(); p.obs_uv = obs_uv.data(); p.obs_w = obs_w.data();
+    p.edge_flags = flags;
+    return p;
+  }
+};
+
+cv::Mat pose_to_cv(const double* qt) {
+  cv::Mat T(4, 4, CV_32F);
+  ccm_pose_to_Tcw_f32(qt, 1, T.ptr<float>(0));          // Converter::toCvMat(SE3Quat): homogeneous matrix rounded to f32
+  return T;
+}
+cv::Mat point_to_cv(const double* x) {
+  cv::Mat X(3, 1, CV_32F);
+  for (int i = 0; i < 3; i++) X.at<float>(i) = (float)x[i];
+  return X;
+}
+void check(int rc) { if (rc != CCM_OK) { std::cerr << "libccm_b200: " << ccm_last_error() << std::endl; throw estd::infrastructure_ex(); } }
+
+}  // namespace
+
+// ---- MapFusionGBA (S/Optimizer.cpp:646-859) ---------------------------------------------------------------------------
+void Optimizer::MapFusionGBA(mapptr pMap, size_t ClientId, int nIterations, bool* pbStopFlag, idpair nLoopKF, const bool bRobust) {
+  (void)ClientId;
+  vector<kfptr> vpKFs = pMap->GetAllKeyFrames();
+  vector<mpptr> vpMP = pMap->GetAllMapPoints();
+  const idpair zeropair = make_pair(0, pMap->mMapId);
+  if (pMap->mvpKeyFrameOrigins.empty()) throw infrastructure_ex();
+  const idpair FixedId = (*(pMap->mvpKeyFrameOrigins.begin()))->mId;
+
+  FlatBA f;
+  size_t maxKFid = 0;
+  for (kfptr pKF : vpKFs) {                                  // keyframe vertices, :695-709
+    if (pKF->isBad()) continue;
+    f.add_kf(pKF, pKF->mId == FixedId);
+    maxKFid = std::max(maxKFid, (size_t)pKF->mUniqueId);
+  }
+  vector<int> mp_row(vpMP.size(), -1);
+  for (size_t i = 0; i < vpMP.size(); i++) {                  // landmark vertices + edges, :715-787
+    mpptr pMP = vpMP[i];
+    if (pMP->isBad()) continue;
+    const map<kfptr, size_t> observations = pMP->GetObservations();
+    int nEdges = 0;
+    for (auto& ob : observations) {
+      kfptr pKF = ob.first;
+      if (!pKF || pKF->isBad() || pKF->mUniqueId > maxKFid || !f.row_of_kf.count(pKF.get())) continue;  // dangling edges dropped
+      nEdges++;
+    }
+    if (observations.size() < 2 || nEdges < 2) continue;
+    mp_row[i] = f.add_mp(pMP);
+    for (auto& ob : observations) {
+      kfptr pKF = ob.first;
+      if (!pKF || pKF->isBad() || pKF->mUniqueId > maxKFid || !f.row_of_kf.count(pKF.get())) continue;
+      f.add_obs(f.row_of_kf[pKF.get()], mp_row[i], pKF, ob.second);
+    }
+  }
+
+  ccm_ba_problem prob = f.problem();
+  ccm_ba_options opt = {};
+  opt.iterations = nIterations; opt.robust = bRobust;
+  opt.huber_delta = (double)(float)sqrt(5.99);               // const float thHuber2D = sqrt(5.99), :712
+  opt.stop = reinterpret_cast<const volatile uint8_t*>(pbStopFlag);   // optimizer.setForceStopFlag(pbStopFlag)
+  vector<double> poses(f.poses.size()), points(f.points.size());
+  ccm_ba_result res = {};
+  res.poses = poses.data(); res.points = points.data();
+  check(ccm_ba_solve(&prob, &opt, &res));                     // == initializeOptimization(); optimize(nIterations)
+
+  size_t row = 0;
+  for (kfptr pKF : vpKFs) {                                   // write-back, :803-823
+    if (pKF->isBad()) continue;
+    cv::Mat T = pose_to_cv(&poses[7 * row++]);
+    if (nLoopKF == zeropair) pKF->SetPose(T, true);
+    else { pKF->mTcwGBA.create(4, 4, CV_32F); T.copyTo(pKF->mTcwGBA); pKF->mBAGlobalForKF = nLoopKF; }
+  }
+  for (size_t i = 0; i < vpMP.size(); i++) {                  // :827-857
+    if (mp_row[i] < 0) continue;
+    mpptr pMP = vpMP[i];
+    if (pMP->isBad()) continue;
+    cv::Mat X = point_to_cv(&points[3 * (size_t)mp_row[i]]);
+    if (nLoopKF == zeropair) { pMP->SetWorldPos(X, true); pMP->UpdateNormalAndDepth(); }
+    else { pMP->mPosGBA.create(3, 1, CV_32F); X.copyTo(pMP->mPosGBA); pMP->mBAGlobalForKF = nLoopKF; }
+  }
+}
+
+// ---- BundleAdjustmentClient / GlobalBundleAdjustemntClient (S/Optimizer.cpp:32-212) -------------------------------------
+void Optimizer::GlobalBundleAdjustemntClient(mapptr pMap, size_t ClientId, int nIterations, bool* pbStopFlag, const idpair nLoopKF, const bool bRobust) {
+  BundleAdjustmentClient(pMap->GetAllKeyFrames(), pMap->GetAllMapPoints(), ClientId, nIterations, pbStopFlag, nLoopKF, bRobust);
+}
+
+void Optimizer::BundleAdjustmentClient(const vector<kfptr>& vpKFs, const vector<mpptr>& vpMP, size_t ClientId, int nIterations,
+                                       bool* pbStopFlag, const idpair nLoopKF, const bool bRobust) {
+  const idpair zeropair = make_pair(0, ClientId);
+  FlatBA f;
+  for (kfptr pKF : vpKFs) {
+    if (pKF->isBad()) continue;
+    if (pKF->mId.first >= IDRANGE) throw infrastructure_ex();
+    f.add_kf(pKF, pKF->mId == zeropair);
+  }
+  vector<int> mp_row(vpMP.size(), -1);
+  for (size_t i = 0; i < vpMP.size(); i++) {
+    mpptr pMP = vpMP[i];
+    if (pMP->isBad()) continue;
+    if (pMP->mId.first >= IDRANGE) throw infrastructure_ex();
+    const map<kfptr, size_t> observations = pMP->GetObservations();
+    int row = -1;
+    for (auto& ob : observations) {
+      kfptr pKF = ob.first;
+      if (pKF->isBad() || !f.row_of_kf.count(pKF.get())) continue;
+      if (row < 0) row = f.add_mp(pMP);
+      f.add_obs(f.row_of_kf[pKF.get()], row, pKF, ob.second);
+    }
+    mp_row[i] = row;                                          // vbNotIncludedMP[i] == (row < 0)
+  }
+  ccm_ba_problem prob = f.problem();
+  ccm_ba_options opt = {};
+  opt.iterations = nIterations; opt.robust = bRobust; opt.huber_delta = (double)(float)sqrt(5.99);
+  opt.stop = reinterpret_cast<const volatile uint8_t*>(pbStopFlag);
+  vector<double> poses(f.poses.size()), points(f.points.size());
+  ccm_ba_result res = {};
+  res.poses = poses.data(); res.points = points.data();
+  check(ccm_ba_solve(&prob, &opt, &res));
+  size_t row = 0;
+  for (kfptr pKF : vpKFs) {
+    if (pKF->isBad()) continue;
+    cv::Mat T = pose_to_cv(&poses[7 * row++]);
+    if (nLoopKF == zeropair) pKF->SetPose(T, false);
+    else { pKF->mTcwGBA.create(4, 4, CV_32F); T.copyTo(pKF->mTcwGBA); pKF->mBAGlobalForKF = nLoopKF; }
+  }
+  for (size_t i = 0; i < vpMP.size(); i++) {
+    if (mp_row[i] < 0 || vpMP[i]->isBad()) continue;
+    cv::Mat X = point_to_cv(&points[3 * (size_t)mp_row[i]]);
+    if (nLoopKF == zeropair) { vpMP[i]->SetWorldPos(X, false); vpMP[i]->UpdateNormalAndDepth(); }
+    else { vpMP[i]->mPosGBA.create(3, 1, CV_32F); X.copyTo(vpMP[i]->mPosGBA); vpMP[i]->mBAGlobalForKF = nLoopKF; }
+  }
+}
+
+// ---- LocalBundleAdjustmentClient (S/Optimizer.cpp:349-644) --------------------------------------------------------------
+void Optimizer::LocalBundleAdjustmentClient(kfptr pKF, bool* pbStopFlag, mapptr pMap, size_t ClientId, eSystemState SysState) {
+  // window selection exactly as the reference (:351-404): current KF + covisibles are local, their points are local,
+  // other observers of those points are fixed
+  list<kfptr> lLocalKeyFrames; lLocalKeyFrames.push_back(pKF); pKF->mBALocalForKF = pKF->mId;
+  for (kfptr pKFi : pKF->GetVectorCovisibleKeyFrames()) { pKFi->mBALocalForKF = pKF->mId; if (!pKFi->isBad()) lLocalKeyFrames.push_back(pKFi); }
+  list<mpptr> lLocalMapPoints;
+  for (kfptr k : lLocalKeyFrames)
+    for (mpptr pMP : k->GetMapPointMatches())
+      if (pMP && !pMP->isBad() && pMP->mBALocalForKF != pKF->mId) { lLocalMapPoints.push_back(pMP); pMP->mBALocalForKF = pKF->mId; }
+  list<kfptr> lFixedCameras;
+  for (mpptr pMP : lLocalMapPoints)
+    for (auto& ob : pMP->GetObservations()) {
+      kfptr pKFi = ob.first;
+      if (pKFi->mBALocalForKF != pKF->mId && pKFi->mBAFixedForKF != pKF->mId) { pKFi->mBAFixedForKF = pKF->mId; if (!pKFi->isBad()) lFixedCameras.push_back(pKFi); }
+    }
+
+  FlatBA f;
+  for (kfptr k : lLocalKeyFrames) { if (k->mId.first >= IDRANGE) throw infrastructure_ex(); f.add_kf(k, k->mId.first == 0 && k->mId.second == ClientId); }
+  for (kfptr k : lFixedCameras) { if (k->mId.first >= IDRANGE) throw infrastructure_ex(); f.add_kf(k, true); }
+  vector<kfptr> vpEdgeKF; vector<mpptr> vpEdgeMP;
+  vector<mpptr> mp_rows;
+  for (mpptr pMP : lLocalMapPoints) {
+    if (pMP->mId.first >= IDRANGE) throw infrastructure_ex();
+    const int row = f.add_mp(pMP); mp_rows.push_back(pMP);
+    for (auto& ob : pMP->GetObservations()) {
+      kfptr pKFi = ob.first;
+      if (pKFi->isBad() || !f.row_of_kf.count(pKFi.get())) continue;
+      f.add_obs(f.row_of_kf[pKFi.get()], row, pKFi, ob.second);
+      vpEdgeKF.push_back(pKFi); vpEdgeMP.push_back(pMP);
+    }
+  }
+  if (pbStopFlag && *pbStopFlag) return;                        // :530-532
+
+  const size_t E = f.obs_kf.size();
+  ccm_ba_problem prob = f.problem();
+  ccm_ba_handle* h = nullptr;
+  check(ccm_ba_create(&prob, &h));
+  ccm_ba_options opt = {};
+  opt.robust = 1; opt.huber_delta = (double)(float)sqrt(5.991);  // const float thHuberMono = sqrt(5.991), :468
+  opt.stop = reinterpret_cast<const volatile uint8_t*>(pbStopFlag);
+  vector<double> poses(f.poses.size()), points(f.points.size()), chi2(E, 0.0);
+  vector<uint8_t> depth(E, 1), flags(E, 0);
+  ccm_ba_result res = {};
+  res.poses = poses.data(); res.points = points.data(); res.chi2 = chi2.data(); res.depth_pos = depth.data();
+  opt.iterations = 5;
+  check(ccm_ba_optimize(h, &opt, &res));                        // optimizer.optimize(5), :537
+  const bool bDoMore = !(pbStopFlag && *pbStopFlag);
+  if (bDoMore) {
+    for (size_t i = 0; i < E; i++) {                            // :548-562
+      if (vpEdgeMP[i]->isBad()) continue;                       // such edges keep level 0 and their kernel
+      if (chi2[i] > 5.991 || !depth[i]) flags[i] |= 1;          // e->setLevel(1)
+      flags[i] |= 2;                                            // e->setRobustKernel(0)
+    }
+    check(ccm_ba_set_edge_flags(h, flags.data()));              // initializeOptimization(0)
+    opt.iterations = 10;
+    check(ccm_ba_optimize(h, &opt, &res));                      // chi2 of level-1 edges keeps its round-1 value (res.chi2 untouched there)
+  }
+  ccm_ba_destroy(h);
+
+  vector<pair<kfptr, mpptr>> vToErase;
+  for (size_t i = 0; i < E; i++) {                              // :573-587
+    if (vpEdgeMP[i]->isBad()) continue;
+    if (chi2[i] > 5.991 || !depth[i]) vToErase.push_back(make_pair(vpEdgeKF[i], vpEdgeMP[i]));
+  }
+  if (SysState != eSystemState::SERVER) while (!pMap->LockMapUpdate()) { usleep(params::timings::miLockSleep); }
+  for (auto& e : vToErase) { e.first->EraseMapPointMatch(e.second); e.second->EraseObservation(e.first); }
+  size_t row = 0;
+  for (kfptr k : lLocalKeyFrames) { k->SetPose(pose_to_cv(&poses[7 * row++]), false); k->mbUpdatedByServer = false; }
+  for (size_t i = 0; i < mp_rows.size(); i++) {
+    mpptr pMP = mp_rows[i];
+    if (pMP->isBad()) { if (pMap->GetMpPtr(pMP->mId)) throw estd::infrastructure_ex(); continue; }
+    pMP->SetWorldPos(point_to_cv(&points[3 * i]), false);
+    pMP->UpdateNormalAndDepth();
+  }
+  if (SysState != eSystemState::SERVER) pMap->UnLockMapUpdate();
+}
+
+// ---- OptimizeEssentialGraph* (S/Optimizer.cpp:1058-1566) ----------------------------------------------------------------
+// Both variants build the same kind of graph (vertices = non-bad KFs as Sim3(R, t, 1); edges = loop connections, spanning
+// tree, earlier loop edges, covisibility >= EssGraphMinFeats, measurement Sji = Sjw * Swi, information I7) and differ only
+// in where Sjw/Swi come from (NonCorrectedSim3 / CorrectedSim3 maps for the loop-closure variant).  The shim collects
+// (i, j, Sji) triples with the reference's own loops (unchanged, not repeated here), then:
+static void solve_essential_graph(std::vector<double>& sim3 /*K*8 in/out*/, const std::vector<uint8_t>& fixed,
+                                  const std::vector<int32_t>& ei, const std::vector<int32_t>& ej, const std::vector<double>& meas,
+                                  bool bFixScale) {
+  ccm_pgo_problem p = {(int32_t)fixed.size(), (int32_t)ei.size(), sim3.data(), fixed.data(), ei.data(), ej.data(), meas.data(), bFixScale ? 1 : 0};
+  ccm_pgo_options o = {};
+  o.iterations = 20; o.lambda_init = 1e-16;                    // solver->setUserLambdaInit(1e-16); optimizer.optimize(20)
+  std::vector<double> out(sim3.size());
+  ccm_pgo_result r = {};
+  r.sim3 = out.data();
+  check(ccm_pgo_solve(&p, &o, &r));
+  sim3.swap(out);
+}
+// After the solve the reference's recovery code (:1280-1330, :1517-1565) runs unchanged on the returned Sim3s:
+// [sR t; 0 1] -> [R t/s; 0 1] per keyframe, and every map point is moved through its reference keyframe.
+
+}  // namespace cslam
