@@ -255,6 +255,19 @@ void step_update_and_residual(ccm_ba_handle* h, double lambda, int robust, doubl
   h->pt_eval = h->pt_trial;
 }
 
+// landmark range [L0, L1) of `rank`: contiguous, cut where the observation prefix crosses rank * E / nranks
+void shard_range(const int* lm_ptr, int P, int rank, int nranks, int* L0, int* L1) {
+  const long long E = lm_ptr[P];
+  auto cut = [&](int r) {
+    if (r <= 0) return 0;
+    if (r >= nranks) return P;
+    const long long target = E * r / nranks;
+    return (int)(std::lower_bound(lm_ptr, lm_ptr + P + 1, (int)target) - lm_ptr);
+  };
+  *L0 = std::min(cut(rank), P);
+  *L1 = std::min(std::max(cut(rank + 1), *L0), P);
+}
+
 // ---- structure ------------------------------------------------------------------------------------------------
 void build(ccm_ba_handle* h, const ccm_ba_problem* p) {
   const double T0 = now_ms();
@@ -294,13 +307,7 @@ void build(ccm_ba_handle* h, const ccm_ba_problem* p) {
   auto src = [&](long long i) { return sorted ? i : (long long)h->perm[i]; };
 
   // landmark shard of this rank: contiguous landmark range balanced by observation count
-  auto cut = [&](int r) {
-    if (r <= 0) return 0;
-    if (r >= h->nranks) return P;
-    const long long target = (long long)E * r / h->nranks;
-    return (int)(std::lower_bound(g_lm_ptr.begin(), g_lm_ptr.end(), (int)target) - g_lm_ptr.begin());
-  };
-  h->L0 = std::min(cut(h->rank), P); h->L1 = std::min(std::max(cut(h->rank + 1), h->L0), P);
+  shard_range(g_lm_ptr.data(), P, h->rank, h->nranks, &h->L0, &h->L1);
   h->Pl = h->L1 - h->L0;
   h->E0 = g_lm_ptr[h->L0];
   h->El = g_lm_ptr[h->L1] - g_lm_ptr[h->L0];
@@ -701,6 +708,19 @@ extern "C" int ccm_ba_get_kernel_stats(const ccm_ba_handle* h, double* total_ms,
   return guarded([&] {
     CCM_REQUIRE(h && total_ms && launches, "null argument");
     for (int i = 0; i < CCM_BA_NKERNELS; i++) { total_ms[i] = h->k_ms[i]; launches[i] = h->k_count[i]; }
+  });
+}
+
+extern "C" int ccm_ba_shard_range(const int32_t* obs_mp, int32_t E, int32_t P, int32_t rank, int32_t nranks, int32_t* L0,
+                                   int32_t* L1, int64_t* E0, int64_t* E1) {
+  return guarded([&] {  // host only: usable without a device
+    CCM_REQUIRE(P >= 0 && E >= 0 && nranks >= 1 && rank >= 0 && rank < nranks && L0 && L1, "ccm_ba_shard_range: bad argument");
+    std::vector<int> ptr((size_t)P + 1, 0);
+    for (int e = 0; e < E; e++) { CCM_REQUIRE(obs_mp[e] >= 0 && obs_mp[e] < P, "obs_mp out of range"); ptr[obs_mp[e] + 1]++; }
+    for (int l = 0; l < P; l++) ptr[l + 1] += ptr[l];
+    shard_range(ptr.data(), P, rank, nranks, L0, L1);
+    if (E0) *E0 = ptr[*L0];
+    if (E1) *E1 = ptr[*L1];
   });
 }
 

@@ -124,6 +124,11 @@ int ccm_ba_set_edge_flags(ccm_ba_handle* h, const uint8_t* edge_flags);
 int ccm_ba_optimize(ccm_ba_handle* h, const ccm_ba_options* o, ccm_ba_result* r);
 void ccm_ba_destroy(ccm_ba_handle* h);
 
+/* host-only: the landmark range [L0, L1) and observation range [E0, E1) rank `rank` of `nranks` owns (the same cut
+ * ccm_ba_create applies to its communicator rank); observations need not be sorted */
+int ccm_ba_shard_range(const int32_t* obs_mp, int32_t E, int32_t P, int32_t rank, int32_t nranks, int32_t* L0, int32_t* L1,
+                       int64_t* E0, int64_t* E1);
+
 /* problem-shape facts of a handle (for roofline accounting) */
 typedef struct ccm_ba_info {
   int32_t K, K_free, P_local, E_local, rank, nranks;
