@@ -101,7 +101,7 @@ def test_search_by_bow_against_python_restatement(oracle):
     d2[perm] = d1[:200]                                  # true matches ...
     flip = rng.integers(0, 32, size=(200, 3))
     for r, cols in zip(perm, flip):                      # ... with a few flipped bits
-        d2[r, cols] ^= 1 << rng.integers(0, 8)
+        d2[r, cols] ^= np.uint8(1 << int(rng.integers(0, 8)))
     node1 = rng.integers(0, 12, size=n1); node2 = rng.integers(0, 12, size=n2); node2[perm] = node1[:200]
     has = (rng.random(n1) < 0.8).astype(np.uint8)
     a1 = rng.uniform(0, 360, n1).astype(np.float32); a2 = rng.uniform(0, 360, n2).astype(np.float32); a2[perm] = a1[:200] + 2.0
