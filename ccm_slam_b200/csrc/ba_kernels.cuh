@@ -605,6 +605,31 @@ __global__ void __launch_bounds__(TPB) k_products(const int* __restrict__ o_kf, 
   }
 }
 
+// validation of the caller's observation arrays: flags[0] |= out-of-range / negative weight, flags[1] |= not grouped by landmark
+__global__ void __launch_bounds__(TPB) k_check_obs(const int* __restrict__ kf, const int* __restrict__ mp,
+                                                  const float* __restrict__ w, int E, int K, int P, int* __restrict__ flags) {
+  int bad = 0, unsorted = 0;
+  for (long long e = (long long)blockIdx.x * TPB + threadIdx.x; e < E; e += (long long)gridDim.x * TPB) {
+    const int k = kf[e], m = mp[e];
+    if (k < 0 || k >= K || m < 0 || m >= P || !(w[e] >= 0.0f)) bad = 1;
+    if (e > 0 && mp[e - 1] > m) unsorted = 1;
+  }
+  if (bad) atomicOr(flags, 1);
+  if (unsorted) atomicOr(flags + 1, 1);
+}
+
+// lm_ptr[l] = first observation of landmark l in the landmark-sorted observation list (lower bound), lm_ptr[P] = E
+__global__ void __launch_bounds__(TPB) k_lm_ptr(const int* __restrict__ mp, int E, int P, int* __restrict__ lm_ptr) {
+  const int l = blockIdx.x * TPB + threadIdx.x;
+  if (l > P) return;
+  int lo = 0, hi = E;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (mp[mid] < l) lo = mid + 1; else hi = mid;
+  }
+  lm_ptr[l] = lo;
+}
+
 __global__ void __launch_bounds__(TPB) k_apply_flags(const float* __restrict__ w_raw, const uint8_t* __restrict__ flags,
                                                      int E, float* __restrict__ o_w) {
   const long long e = (long long)blockIdx.x * TPB + threadIdx.x;

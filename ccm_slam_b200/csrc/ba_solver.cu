@@ -70,10 +70,13 @@ struct ccm_ba_handle {
   DevBuf<unsigned> bitmap, u_prod_ptr;
   DevBuf<uint2> prod;
   // pcg
-  DevBuf<double> x, pr, pz, pp, pq, pcg_partials, pcg_status, dxl;
+  DevBuf<double> x, pr, pz, pp, pq, pcg_partials, pcg_status, dxl, pcg_Ac, pcg_rc, pcg_yc;
+  int pcg_agg = 0, pcg_nc = 0, pcg_refresh = 4, pcg_age = 0;
+  bool pcg_coarse_valid = false;  // Ac holds a usable inverse from an earlier trial
   DevBuf<unsigned> pcg_bar;
+  DevBuf<long long> pcg_prof;  // allocated only with CCM_PCG_PROF=1
   DevBuf<int> jac_fail;
-  int pcg_grid = 0;
+  int pcg_grid = 0, pcg_block = 256, pcg_last_mode = 1;
   // scalars / partials
   DevBuf<double> partials, scal;  // scal: [0] chi2_trial [1] scale_l [2] scale_p [3..5] pcg status
   double* h_scal = nullptr;       // pinned, 16 doubles
@@ -225,8 +228,12 @@ void step_pcg(ccm_ba_handle* h, double tol, int max_iter) {
   a.n = h->Kf; a.rowptr = h->s_rowptr.p; a.col = h->s_col.p; a.val = h->s_val.p; a.Minv = h->Minv.p; a.b = h->bschur.p;
   a.x = h->x.p; a.r = h->pr.p; a.z = h->pz.p; a.p = h->pp.p; a.q = h->pq.p;
   a.partials = h->pcg_partials.p; a.bar = h->pcg_bar.p; a.tol = tol; a.max_iter = max_iter; a.status = h->pcg_status.p;
+  a.agg = h->pcg_agg; a.nc = h->pcg_nc; a.Ac = h->pcg_Ac.p; a.rc = h->pcg_rc.p; a.yc = h->pcg_yc.p;
+  a.prof = h->pcg_prof.p;
+  a.coarse_mode = (h->pcg_coarse_valid && h->pcg_age < h->pcg_refresh) ? 2 : 1;
+  h->pcg_last_mode = a.coarse_mode;
   void* args[] = {&a};
-  CCM_CUDA(cudaLaunchCooperativeKernel((void*)k_pcg<6>, dim3(h->pcg_grid), dim3(TPB), args, 0, s));
+  CCM_CUDA(cudaLaunchCooperativeKernel((void*)k_pcg<6>, dim3(h->pcg_grid), dim3(h->pcg_block), args, 0, s));
   CCM_LAUNCHED();
 }
 
@@ -283,69 +290,94 @@ void build(ccm_ba_handle* h, const ccm_ba_problem* p) {
   h->rank = comm().rank; h->nranks = comm().nranks;
   const int K = p->K, P = p->P, E = p->E;
 
-  // observations must be grouped by landmark (the reference adds edges landmark by landmark); sort if they are not
-  bool sorted = true;
-  for (int e = 0; e < E; e++) {
-    CCM_REQUIRE(p->obs_kf[e] >= 0 && p->obs_kf[e] < K && p->obs_mp[e] >= 0 && p->obs_mp[e] < P,
-                "ccm_ba_create: observation index out of range");
-    if (e && p->obs_mp[e] < p->obs_mp[e - 1]) sorted = false;
-  }
-  std::vector<int> g_lm_ptr((size_t)P + 1, 0);
-  for (int e = 0; e < E; e++) g_lm_ptr[p->obs_mp[e] + 1]++;
-  for (int l = 0; l < P; l++) g_lm_ptr[l + 1] += g_lm_ptr[l];
-  h->sorted_input = sorted;
-  std::vector<int> g_kf((size_t)E), g_lm((size_t)E);
-  if (sorted) {
-    std::copy(p->obs_kf, p->obs_kf + E, g_kf.begin());
-    std::copy(p->obs_mp, p->obs_mp + E, g_lm.begin());
-  } else {
-    h->perm.resize(E);
-    std::vector<int> cur(g_lm_ptr.begin(), g_lm_ptr.end() - 1);
-    for (int e = 0; e < E; e++) h->perm[cur[p->obs_mp[e]]++] = e;
-    for (int i = 0; i < E; i++) { g_kf[i] = p->obs_kf[h->perm[i]]; g_lm[i] = p->obs_mp[h->perm[i]]; }
-  }
-  auto src = [&](long long i) { return sorted ? i : (long long)h->perm[i]; };
-
-  // landmark shard of this rank: contiguous landmark range balanced by observation count
-  shard_range(g_lm_ptr.data(), P, h->rank, h->nranks, &h->L0, &h->L1);
-  h->Pl = h->L1 - h->L0;
-  h->E0 = g_lm_ptr[h->L0];
-  h->El = g_lm_ptr[h->L1] - g_lm_ptr[h->L0];
-  h->Ep = ((size_t)h->El + 31) / 32 * 32;
-  const int Pl = h->Pl, El = h->El;
-
   // free poses
   h->h_pose_slot.assign(K, -1);
   for (int k = 0; k < K; k++)
     if (!p->fixed[k]) { h->h_pose_slot[k] = (int)h->h_slot_pose.size(); h->h_slot_pose.push_back(k); }
   h->Kf = (int)h->h_slot_pose.size();
   const int Kf = h->Kf;
-
-  // ---- uploads
   h->pose0.upload(p->poses, (size_t)K * 7, s);
   h->poseA.alloc((size_t)K * 7); h->poseB.alloc((size_t)K * 7);
   h->intr.upload(p->intr, (size_t)K * 4, s);
   h->pose_slot.upload(h->h_pose_slot.data(), K, s);
   upload_vec(h->slot_pose, h->h_slot_pose, s);
+
+  // Observations must be grouped by landmark (the reference adds edges landmark by landmark).
+  // Fast path (single rank, already grouped): the caller's arrays go to the device as they are, validation and the
+  // landmark offsets are kernels - no host pass over the observations.  Otherwise: host counting sort + shard cut.
+  std::vector<int> g_lm_ptr, g_kf, g_lm;
+  bool fast = (h->nranks == 1 && E > 0);
+  if (fast) {
+    h->o_kf.upload(p->obs_kf, E, s); h->o_lm.upload(p->obs_mp, E, s);
+    h->o_uv.upload(reinterpret_cast<const float2*>(p->obs_uv), E, s); h->o_w_raw.upload(p->obs_w, E, s);
+    DevBuf<int> chk; chk.alloc_zero(2, s);
+    k_check_obs<<<grid_stride(E), TPB, 0, s>>>(h->o_kf.p, h->o_lm.p, h->o_w_raw.p, E, K, P, chk.p);
+    CCM_LAUNCHED();
+    int hc[2];
+    chk.download(hc, 2, s);
+    CCM_CUDA(cudaStreamSynchronize(s));
+    CCM_REQUIRE(hc[0] == 0, "ccm_ba_create: observation index out of range or negative information weight");
+    if (hc[1] != 0) fast = false;  // not grouped by landmark: take the sorting path
+  }
+  if (fast) {
+    h->sorted_input = true;
+    h->L0 = 0; h->L1 = P; h->Pl = P; h->E0 = 0; h->El = E;
+    h->Ep = ((size_t)E + 31) / 32 * 32;
+    h->lm_ptr.alloc((size_t)P + 1);
+    k_lm_ptr<<<div_up((long long)P + 1, TPB), TPB, 0, s>>>(h->o_lm.p, E, P, h->lm_ptr.p);
+    CCM_LAUNCHED();
+    if (p->edge_flags) h->h_flags.assign(p->edge_flags, p->edge_flags + E); else h->h_flags.assign(E, 0);
+  } else {
+    bool sorted = true;
+    for (int e = 0; e < E; e++) {
+      CCM_REQUIRE(p->obs_kf[e] >= 0 && p->obs_kf[e] < K && p->obs_mp[e] >= 0 && p->obs_mp[e] < P,
+                  "ccm_ba_create: observation index out of range");
+      if (e && p->obs_mp[e] < p->obs_mp[e - 1]) sorted = false;
+    }
+    g_lm_ptr.assign((size_t)P + 1, 0);
+    for (int e = 0; e < E; e++) g_lm_ptr[p->obs_mp[e] + 1]++;
+    for (int l = 0; l < P; l++) g_lm_ptr[l + 1] += g_lm_ptr[l];
+    h->sorted_input = sorted;
+    g_kf.resize((size_t)E); g_lm.resize((size_t)E);
+    if (sorted) {
+      std::copy(p->obs_kf, p->obs_kf + E, g_kf.begin());
+      std::copy(p->obs_mp, p->obs_mp + E, g_lm.begin());
+    } else {
+      h->perm.resize(E);
+      std::vector<int> cur(g_lm_ptr.begin(), g_lm_ptr.end() - 1);
+      for (int e = 0; e < E; e++) h->perm[cur[p->obs_mp[e]]++] = e;
+      for (int i = 0; i < E; i++) { g_kf[i] = p->obs_kf[h->perm[i]]; g_lm[i] = p->obs_mp[h->perm[i]]; }
+    }
+    auto src = [&](long long i) { return sorted ? i : (long long)h->perm[i]; };
+    // landmark shard of this rank: contiguous landmark range balanced by observation count
+    shard_range(g_lm_ptr.data(), P, h->rank, h->nranks, &h->L0, &h->L1);
+    h->Pl = h->L1 - h->L0;
+    h->E0 = g_lm_ptr[h->L0];
+    h->El = g_lm_ptr[h->L1] - g_lm_ptr[h->L0];
+    h->Ep = ((size_t)h->El + 31) / 32 * 32;
+    const int El_ = h->El, Pl_ = h->Pl;
+    std::vector<int> l_kf(El_), l_lm(El_), l_ptr((size_t)Pl_ + 1);
+    std::vector<float2> l_uv(El_);
+    std::vector<float> l_w(El_);
+    h->h_flags.assign(El_, 0);
+    for (int i = 0; i < El_; i++) {
+      const long long gi = h->E0 + i, si = src(gi);
+      l_kf[i] = g_kf[gi];
+      l_lm[i] = g_lm[gi] - h->L0;
+      l_uv[i] = make_float2(p->obs_uv[2 * si], p->obs_uv[2 * si + 1]);
+      l_w[i] = p->obs_w[si];
+      CCM_REQUIRE(l_w[i] >= 0.0f, "ccm_ba_create: negative information weight");
+      if (p->edge_flags) h->h_flags[i] = p->edge_flags[si];
+    }
+    for (int l = 0; l <= Pl_; l++) l_ptr[l] = g_lm_ptr[h->L0 + l] - (int)h->E0;
+    upload_vec(h->o_kf, l_kf, s); upload_vec(h->o_lm, l_lm, s); upload_vec(h->lm_ptr, l_ptr, s);
+    upload_vec(h->o_uv, l_uv, s); upload_vec(h->o_w_raw, l_w, s);
+    CCM_CUDA(cudaStreamSynchronize(s));  // the staging vectors die at the end of this scope
+  }
+  const int Pl = h->Pl, El = h->El;
   h->pt0.alloc(std::max((size_t)Pl * 3, (size_t)1));
   if (Pl) CCM_CUDA(cudaMemcpyAsync(h->pt0.p, p->points + 3 * (size_t)h->L0, sizeof(double) * 3 * Pl, cudaMemcpyHostToDevice, s));
   h->ptA.alloc(std::max((size_t)Pl * 3, (size_t)1)); h->ptB.alloc(std::max((size_t)Pl * 3, (size_t)1));
-  std::vector<int> l_kf(El), l_lm(El), l_ptr((size_t)Pl + 1);
-  std::vector<float2> l_uv(El);
-  std::vector<float> l_w(El);
-  h->h_flags.assign(El, 0);
-  for (int i = 0; i < El; i++) {
-    const long long gi = h->E0 + i, si = src(gi);
-    l_kf[i] = g_kf[gi];
-    l_lm[i] = g_lm[gi] - h->L0;
-    l_uv[i] = make_float2(p->obs_uv[2 * si], p->obs_uv[2 * si + 1]);
-    l_w[i] = p->obs_w[si];
-    CCM_REQUIRE(l_w[i] >= 0.0f, "ccm_ba_create: negative information weight");
-    if (p->edge_flags) h->h_flags[i] = p->edge_flags[si];
-  }
-  for (int l = 0; l <= Pl; l++) l_ptr[l] = g_lm_ptr[h->L0 + l] - (int)h->E0;
-  upload_vec(h->o_kf, l_kf, s); upload_vec(h->o_lm, l_lm, s); upload_vec(h->lm_ptr, l_ptr, s);
-  upload_vec(h->o_uv, l_uv, s); upload_vec(h->o_w_raw, l_w, s);
   h->o_w.alloc(std::max(El, 1)); h->d_flags.alloc(std::max(El, 1));
   if (El) {
     h->d_flags.upload(h->h_flags.data(), El, s);
@@ -466,10 +498,22 @@ void build(ccm_ba_handle* h, const ccm_ba_problem* p) {
   h->dxl.alloc(std::max((size_t)Pl * 3, (size_t)1));
   h->pcg_status.alloc_zero(4, s); h->pcg_bar.alloc_zero(1, s); h->jac_fail.alloc_zero(1, s);
   int per_sm = 0;
-  CCM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg<6>, TPB, 0));
-  per_sm = std::max(1, std::min(per_sm, env_int("CCM_PCG_BLOCKS_PER_SM", 4)));
-  h->pcg_grid = std::max(1, std::min(per_sm * sm_count(), div_up((long long)std::max(Kf, 1) * 32, TPB)));
+  CCM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg<6>, PCG_TPB, 0));
+  CCM_REQUIRE(per_sm >= 1, "k_pcg does not fit on an SM");
+  // one warp per block row: fat 1024-thread CTAs (one per SM, cheap grid barrier) when the rows fill the chip, otherwise
+  // 256-thread CTAs so that a small system still spreads over many SMs
+  h->pcg_block = ((long long)Kf * 32 >= (long long)sm_count() * PCG_TPB) ? PCG_TPB : 256;
+  h->pcg_grid = std::max(1, std::min(sm_count() * (PCG_TPB / h->pcg_block), div_up((long long)std::max(Kf, 1) * 32, h->pcg_block)));
   h->pcg_partials.alloc((size_t)3 * h->pcg_grid);
+  if (env_int("CCM_PCG_PROF", 0)) h->pcg_prof.alloc_zero(8, s);
+  // coarse space: <= 64 aggregates for small systems (the in-kernel inversion costs one grid barrier per coarse unknown),
+  // <= 128 for long trajectories where the smooth modes dominate the iteration count
+  pcg_coarse_shape(Kf, env_int("CCM_PCG_NC", Kf >= 4096 ? 256 : 64), &h->pcg_agg, &h->pcg_nc);
+  h->pcg_refresh = std::max(1, env_int("CCM_PCG_REFRESH", Kf >= 4096 ? 4 : 1));
+  {
+    const size_t nC = (size_t)6 * h->pcg_nc;
+    h->pcg_Ac.alloc(std::max(2 * nC * nC, (size_t)1)); h->pcg_rc.alloc(std::max(2 * nC, (size_t)1)); h->pcg_yc.alloc(std::max(nC, (size_t)1));
+  }
   h->partials.alloc((size_t)sm_count() * 8 + 8);
   h->scal.alloc_zero(16, s);
   h->rep_chi2.alloc(std::max(El, 1)); h->rep_depth.alloc(std::max(El, 1));
@@ -539,6 +583,7 @@ void optimize(ccm_ba_handle* h, const ccm_ba_options* o, ccm_ba_result* r) {
   const int max_trials = o->max_trials > 0 ? o->max_trials : 10;
   const int pcg_max = o->pcg_max_iter > 0 ? o->pcg_max_iter : 2000;
   const double pcg_tol = o->pcg_tol > 0 ? o->pcg_tol : 1e-10;
+  h->pcg_coarse_valid = false;  // every optimize() starts with a fresh coarse inverse
   r->trace_len = 0; r->iters_done = 0; r->trials_total = 0; r->pcg_iters_total = 0; r->pcg_not_converged = 0;
   r->chi2_initial = r->chi2_final = 0; r->lambda_final = 0;
   auto terminate = [&]() { return o->stop && *o->stop; };
@@ -574,15 +619,16 @@ void optimize(ccm_ba_handle* h, const ccm_ba_options* o, ccm_ba_result* r) {
       step_pcg(h, pcg_tol, pcg_max);
       step_update_and_residual(h, lambda, robust, delta, nullptr);
       CCM_CUDA(cudaMemcpyAsync(h->h_scal, h->scal.p, 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
-      CCM_CUDA(cudaMemcpyAsync(h->h_scal + 3, h->pcg_status.p, 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
-      CCM_CUDA(cudaMemcpyAsync(h->h_scal + 6, h->jac_fail.p, sizeof(int), cudaMemcpyDeviceToHost, s));
+      CCM_CUDA(cudaMemcpyAsync(h->h_scal + 3, h->pcg_status.p, 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
+      CCM_CUDA(cudaMemcpyAsync(h->h_scal + 7, h->jac_fail.p, sizeof(int), cudaMemcpyDeviceToHost, s));
       CCM_CUDA(cudaStreamSynchronize(s));
       if (h->profile) collect_spans(h);
       tempChi = h->h_scal[0];
       const int pcg_it = (int)h->h_scal[3];
       const int pcg_flag = (int)h->h_scal[5];
       int jfail;
-      memcpy(&jfail, h->h_scal + 6, sizeof(int));
+      memcpy(&jfail, h->h_scal + 7, sizeof(int));
+      if (h->pcg_last_mode == 1) { h->pcg_coarse_valid = h->h_scal[6] > 0; h->pcg_age = 1; } else h->pcg_age++;
       last_pcg_it = pcg_it; last_relres = h->h_scal[4];
       r->pcg_iters_total += pcg_it;
       if (pcg_flag == 1) r->pcg_not_converged++;
@@ -721,6 +767,14 @@ extern "C" int ccm_ba_shard_range(const int32_t* obs_mp, int32_t E, int32_t P, i
     shard_range(ptr.data(), P, rank, nranks, L0, L1);
     if (E0) *E0 = ptr[*L0];
     if (E1) *E1 = ptr[*L1];
+  });
+}
+
+extern "C" int ccm_ba_debug_pcg_cycles(ccm_ba_handle* h, int64_t* cycles8) {
+  return guarded([&] {
+    CCM_REQUIRE(h && cycles8, "null argument");
+    for (int i = 0; i < 8; i++) cycles8[i] = 0;
+    if (h->pcg_prof.p) { CCM_CUDA(cudaMemcpy(cycles8, h->pcg_prof.p, 8 * sizeof(long long), cudaMemcpyDeviceToHost)); }
   });
 }
 

@@ -2,15 +2,23 @@
 //
 // Replaces the direct sparse LDL^T of g2o's LinearSolverEigen (G/solvers/linear_solver_eigen.h:106-133) on the reduced
 // camera system (BS = 6, bundle adjustment) and on the Sim3 pose-graph Hessian (BS = 7, essential graph).  One warp per
-// block row; the whole iteration runs inside one kernel launched with cudaLaunchCooperativeKernel, grid-wide barriers go
+// block row; the whole solve runs inside one kernel launched with cudaLaunchCooperativeKernel, grid-wide barriers go
 // through a global counter, dot products are reduced in a fixed order so that every CTA sees identical scalars.
-// Preconditioner: block-Jacobi (inverse diagonal blocks, computed by the caller).
+//
+// Preconditioner: two-level additive Schwarz,  M^-1 = blockdiag(S)^-1 + P (P^T S P)^-1 P^T.
+//   * fine level: block-Jacobi (inverse diagonal blocks, computed by the caller);
+//   * coarse level: aggregates of `agg` consecutive block rows (keyframes are ordered along each agent's trajectory, so
+//     index neighbours are co-visible), piecewise-constant prolongation per degree of freedom -> a dense (BS*nc)^2
+//     Galerkin matrix, nc <= 128, assembled and inverted (ping-pong Gauss-Jordan, one grid barrier per pivot) inside the
+//     same kernel before the iteration starts.  It removes the smooth error modes along the trajectory that make
+//     block-Jacobi PCG iteration counts grow with the number of keyframes.
 #pragma once
 #include <cuda_runtime.h>
 
 namespace ccm {
 
 constexpr int TPB = 256;
+constexpr int PCG_TPB = 1024;  // one fat CTA per SM keeps the grid barrier at <= 148 participants
 
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
@@ -40,7 +48,14 @@ struct PcgArgs {
   double* partials;  // 3 * gridDim.x
   unsigned* bar;     // zeroed before launch
   double tol; int max_iter;
-  double* status;    // [iters, relres, flag(0 converged, 1 max_iter, 2 breakdown: p'Sp <= 0)]
+  double* status;    // [iters, relres, flag(0 converged, 1 max_iter, 2 breakdown: p'Sp <= 0), coarse_used]
+  // coarse level (agg <= 0 disables it)
+  int agg, nc;       // rows per aggregate, number of aggregates
+  int coarse_mode;   // 1: assemble + invert now, 2: reuse the inverse a previous launch left in Ac (still a valid SPD preconditioner)
+  double* Ac;        // 2 * (BS*nc)^2 ping-pong buffers
+  double* rc;        // 2 * BS*nc restricted residual (double buffered)
+  double* yc;        // BS*nc coarse correction
+  long long* prof;   // optional: 8 cycle counters filled by CTA 0 (setup, spmv, update+restrict, coarse, precond, p-update) or NULL
 };
 
 __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& target) {
@@ -63,36 +78,140 @@ __device__ __forceinline__ double sum_partials_dev(const double* partials, int g
 }
 
 template <int BS>
-__global__ void __launch_bounds__(TPB) k_pcg(PcgArgs A) {
+__global__ void __launch_bounds__(PCG_TPB, 1) k_pcg(PcgArgs A) {
   constexpr int BB = BS * BS;
-  __shared__ double red[TPB / 32];
+  __shared__ double red[PCG_TPB / 32];
+  const int bdim = blockDim.x;  // 256 (small systems: spread over more SMs) or PCG_TPB
   const int lane = threadIdx.x & 31;
-  const int gw = (blockIdx.x * TPB + threadIdx.x) >> 5;
-  const int nw = (gridDim.x * TPB) >> 5;
+  const int gw = (blockIdx.x * bdim + threadIdx.x) >> 5;
+  const int nw = (gridDim.x * bdim) >> 5;
   const int G = gridDim.x;
+  const long long gtid = (long long)blockIdx.x * bdim + threadIdx.x, gthreads = (long long)gridDim.x * bdim;
   unsigned target = 0;
   double* part0 = A.partials;
   double* part1 = A.partials + G;
   double* part2 = A.partials + 2 * G;
+  const int nC = A.agg > 0 ? BS * A.nc : 0;
+  bool coarse = nC > 0;
+  const double* Ainv = nullptr;
 
-  // x = 0, r = b, z = Minv r, p = z
-  double acc_rz = 0.0, acc_bb = 0.0;
-  for (int a = gw; a < A.n; a += nw) {
-    if (lane < BS) {
-      const double rv = A.b[(size_t)a * BS + lane];
-      const double* M = A.Minv + (size_t)a * BB + lane * BS;
-      const double* ra = A.b + (size_t)a * BS;
-      double zv = 0.0;
-#pragma unroll
-      for (int k = 0; k < BS; k++) zv += M[k] * ra[k];
-      A.x[(size_t)a * BS + lane] = 0.0;
-      A.r[(size_t)a * BS + lane] = rv;
-      A.z[(size_t)a * BS + lane] = zv;
-      A.p[(size_t)a * BS + lane] = zv;
-      acc_rz += rv * zv;
-      acc_bb += rv * rv;
+  // ---- coarse level set-up: Ac = P^T S P, then Ac^-1 by ping-pong Gauss-Jordan -------------------------------------
+  if (coarse && A.coarse_mode == 2) {
+    Ainv = (nC & 1) ? A.Ac + (size_t)nC * nC : A.Ac;
+    for (long long i = gtid; i < 2ll * nC; i += gthreads) A.rc[i] = 0.0;
+    grid_barrier(A.bar, target);
+  } else if (coarse) {
+    double* A0 = A.Ac;
+    double* A1 = A.Ac + (size_t)nC * nC;
+    for (long long i = gtid; i < (long long)nC * nC; i += gthreads) A0[i] = 0.0;
+    for (long long i = gtid; i < 2ll * nC; i += gthreads) A.rc[i] = 0.0;
+    grid_barrier(A.bar, target);
+    // assembly: the warp walks one block row, accumulates the blocks of one aggregate column in registers, flushes with
+    // red.add when the aggregate changes (columns are sorted, so a row flushes once per touched aggregate)
+    for (int a = gw; a < A.n; a += nw) {
+      const int ra = a / A.agg;
+      double acc0 = 0.0, acc1 = 0.0;
+      int cur = -1;
+      const int beg = A.rowptr[a], end = A.rowptr[a + 1];
+      for (int j = beg; j <= end; j++) {
+        const int cb = j < end ? A.col[j] / A.agg : -2;
+        if (cb != cur) {
+          if (cur >= 0) {
+            if (lane < BB) atomicAdd(A0 + (size_t)(ra * BS + lane / BS) * nC + cur * BS + lane % BS, acc0);
+            if (lane + 32 < BB) atomicAdd(A0 + (size_t)(ra * BS + (lane + 32) / BS) * nC + cur * BS + (lane + 32) % BS, acc1);
+          }
+          cur = cb; acc0 = 0.0; acc1 = 0.0;
+        }
+        if (j < end) {
+          const double* v = A.val + (size_t)j * BB;
+          if (lane < BB) acc0 += __ldg(v + lane);
+          if (lane + 32 < BB) acc1 += __ldg(v + lane + 32);
+        }
+      }
     }
+    grid_barrier(A.bar, target);
+    // Gauss-Jordan without pivoting (the matrix is SPD): step k reads buffer k&1, writes buffer (k+1)&1
+    bool bad = false;
+    for (int k = 0; k < nC; k++) {
+      const double* src = (k & 1) ? A1 : A0;
+      double* dst = (k & 1) ? A0 : A1;
+      const double piv = __ldcg(src + (size_t)k * nC + k);
+      if (!(piv > 0.0) || !isfinite(piv)) { bad = true; break; }  // uniform: every thread reads the same pivot
+      const double ip = 1.0 / piv;
+      for (long long e = gtid; e < (long long)nC * nC; e += gthreads) {
+        const int i = (int)(e / nC), j = (int)(e - (long long)i * nC);
+        double v;
+        if (i == k) v = (j == k) ? ip : __ldcg(src + (size_t)k * nC + j) * ip;
+        else {
+          const double f = __ldcg(src + (size_t)i * nC + k) * ip;
+          v = (j == k) ? -f : __ldcg(src + e) - f * __ldcg(src + (size_t)k * nC + j);
+        }
+        dst[e] = v;
+      }
+      grid_barrier(A.bar, target);
+    }
+    if (bad) coarse = false;
+    Ainv = (nC & 1) ? A1 : A0;
   }
+
+  // z = Minv r for the rows of this warp; with the coarse level: += (P yc)[row]
+  auto precond_rows = [&](double& acc_rz, double& acc_rr, bool init) {
+    for (int a = gw; a < A.n; a += nw) {
+      double rv = 0.0;
+      if (lane < BS) rv = A.r[(size_t)a * BS + lane];
+      double r6[BS];
+#pragma unroll
+      for (int k = 0; k < BS; k++) r6[k] = __shfl_sync(0xffffffffu, rv, k);
+      if (lane < BS) {
+        const double* M = A.Minv + (size_t)a * BB + lane * BS;
+        double zv = 0.0;
+#pragma unroll
+        for (int k = 0; k < BS; k++) zv += M[k] * r6[k];
+        if (coarse) zv += __ldcg(A.yc + (size_t)(a / A.agg) * BS + lane);
+        A.z[(size_t)a * BS + lane] = zv;
+        if (init) A.p[(size_t)a * BS + lane] = zv;
+        acc_rz += rv * zv;
+        acc_rr += rv * rv;
+      }
+    }
+  };
+  // rc[buf] += P^T r over the rows of this warp (red.add), then (after a barrier) yc = Ainv rc[buf]
+  auto restrict_rows = [&](int buf) {
+    for (int a = gw; a < A.n; a += nw)
+      if (lane < BS) atomicAdd(A.rc + (size_t)buf * nC + (size_t)(a / A.agg) * BS + lane, A.r[(size_t)a * BS + lane]);
+  };
+  auto coarse_solve = [&](int buf) {
+    const double* rcv = A.rc + (size_t)buf * nC;
+    for (int i = gw; i < nC; i += nw) {
+      double s = 0.0;
+      for (int j = lane; j < nC; j += 32) s += __ldcg(Ainv + (size_t)i * nC + j) * __ldcg(rcv + j);
+      s = warp_sum(s);
+      if (lane == 0) A.yc[i] = s;
+    }
+    // clear the other buffer for the next iteration (nobody reads or writes it in this phase)
+    if (blockIdx.x == 0) for (int i = threadIdx.x; i < nC; i += bdim) A.rc[(size_t)(buf ^ 1) * nC + i] = 0.0;
+  };
+
+  const bool prof_on = A.prof != nullptr && blockIdx.x == 0 && threadIdx.x == 0;
+  long long tprev = clock64();
+  auto lap = [&](int slot) { if (prof_on) { const long long t = clock64(); A.prof[slot] += t - tprev; tprev = t; } };
+  lap(0);
+  // ---- x = 0, r = b ----------------------------------------------------------------------------------------------------
+  for (int a = gw; a < A.n; a += nw)
+    if (lane < BS) {
+      A.x[(size_t)a * BS + lane] = 0.0;
+      A.r[(size_t)a * BS + lane] = A.b[(size_t)a * BS + lane];
+    }
+  int buf = 0;
+  if (coarse) {
+    restrict_rows(buf);
+    grid_barrier(A.bar, target);
+    coarse_solve(buf);
+    grid_barrier(A.bar, target);
+    buf ^= 1;
+  }
+  double acc_rz = 0.0, acc_bb = 0.0;
+  precond_rows(acc_rz, acc_bb, true);
   {
     const double t0 = block_sum(acc_rz, red);
     const double t1 = block_sum(acc_bb, red);
@@ -127,7 +246,7 @@ __global__ void __launch_bounds__(TPB) k_pcg(PcgArgs A) {
             for (int rI = 0; rI < BS; rI++)
 #pragma unroll
               for (int c = 0; c < BS / 2; c++) {
-                const double2 t = __ldg(v2 + rI * (BS / 2) + c);
+                const double2 t = __ldg(v2 + rI * (BS / 2) + c);  // (bypassing L1 here measured 18 % slower: neighbouring loads share lines)
                 y[rI] += t.x * pv[2 * c] + t.y * pv[2 * c + 1];
               }
           } else {
@@ -152,37 +271,34 @@ __global__ void __launch_bounds__(TPB) k_pcg(PcgArgs A) {
         if (threadIdx.x == 0) part0[blockIdx.x] = t0;
       }
       grid_barrier(A.bar, target);
+      lap(1);
       const double pq = sum_partials_dev(part0, G);
       if (!(pq > 0.0) || !isfinite(pq)) { flag = 2; break; }
       const double alpha = rz / pq;
-      // x += alpha p ; r -= alpha q ; z = Minv r   (rows owned by this warp)
-      double acc_rz2 = 0.0, acc_rr = 0.0;
-      for (int a = gw; a < A.n; a += nw) {
-        double rv = 0.0;
+      // x += alpha p ; r -= alpha q   (rows owned by this warp)
+      for (int a = gw; a < A.n; a += nw)
         if (lane < BS) {
-          rv = A.r[(size_t)a * BS + lane] - alpha * A.q[(size_t)a * BS + lane];
           A.x[(size_t)a * BS + lane] += alpha * A.p[(size_t)a * BS + lane];
-          A.r[(size_t)a * BS + lane] = rv;
+          A.r[(size_t)a * BS + lane] -= alpha * A.q[(size_t)a * BS + lane];
         }
-        double r6[BS];
-#pragma unroll
-        for (int k = 0; k < BS; k++) r6[k] = __shfl_sync(0xffffffffu, rv, k);
-        if (lane < BS) {
-          const double* M = A.Minv + (size_t)a * BB + lane * BS;
-          double zv = 0.0;
-#pragma unroll
-          for (int k = 0; k < BS; k++) zv += M[k] * r6[k];
-          A.z[(size_t)a * BS + lane] = zv;
-          acc_rz2 += rv * zv;
-          acc_rr += rv * rv;
-        }
+      if (coarse) {
+        restrict_rows(buf);
+        grid_barrier(A.bar, target);
+        lap(2);
+        coarse_solve(buf);
+        grid_barrier(A.bar, target);
+        lap(3);
+        buf ^= 1;
       }
+      double acc_rz2 = 0.0, acc_rr = 0.0;
+      precond_rows(acc_rz2, acc_rr, false);
       {
         const double t0 = block_sum(acc_rz2, red);
         const double t1 = block_sum(acc_rr, red);
         if (threadIdx.x == 0) { part1[blockIdx.x] = t0; part2[blockIdx.x] = t1; }
       }
       grid_barrier(A.bar, target);
+      lap(4);
       const double rz_new = sum_partials_dev(part1, G);
       rr = sum_partials_dev(part2, G);
       if (rr <= stop2) { flag = 0; it++; break; }
@@ -191,13 +307,23 @@ __global__ void __launch_bounds__(TPB) k_pcg(PcgArgs A) {
       for (int a = gw; a < A.n; a += nw)
         if (lane < BS) A.p[(size_t)a * BS + lane] = A.z[(size_t)a * BS + lane] + beta * A.p[(size_t)a * BS + lane];
       grid_barrier(A.bar, target);
+      lap(5);
     }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {
     A.status[0] = (double)it;
     A.status[1] = bb > 0.0 ? sqrt(rr / bb) : 0.0;
     A.status[2] = (double)flag;
+    A.status[3] = coarse ? (double)nC : 0.0;
   }
+}
+
+// aggregate size for n block rows so that at most nc_max aggregates exist
+inline void pcg_coarse_shape(int n, int nc_max, int* agg, int* nc) {
+  if (nc_max <= 0 || n <= 0) { *agg = 0; *nc = 0; return; }
+  *agg = (n + nc_max - 1) / nc_max;
+  if (*agg < 1) *agg = 1;
+  *nc = (n + *agg - 1) / *agg;
 }
 
 }  // namespace ccm

@@ -390,9 +390,21 @@ void pgo_solve(const ccm_pgo_problem* p, const ccm_pgo_options* o, ccm_pgo_resul
   const int gsm = sm_count();
   partials.alloc((size_t)gsm * 8 + 8); scal.alloc_zero(8, s); pcg_status.alloc_zero(4, s); bar.alloc_zero(1, s); fail.alloc_zero(1, s);
   int per_sm = 0;
-  CCM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg<7>, TPB, 0));
-  const int pcg_grid = std::max(1, std::min(std::max(1, std::min(per_sm, 4)) * gsm, div_up((long long)n * 32, TPB)));
+  CCM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg<7>, PCG_TPB, 0));
+  CCM_REQUIRE(per_sm >= 1, "k_pcg does not fit on an SM");
+  const int pcg_block = ((long long)n * 32 >= (long long)gsm * PCG_TPB) ? PCG_TPB : 256;
+  const int pcg_grid = std::max(1, std::min(gsm * (PCG_TPB / pcg_block), div_up((long long)n * 32, pcg_block)));
   pcg_partials.alloc((size_t)3 * pcg_grid);
+  int c_agg = 0, c_nc = 0;
+  {
+    const char* e = getenv("CCM_PCG_NC");
+    pcg_coarse_shape(n, e ? atoi(e) : 64, &c_agg, &c_nc);
+  }
+  DevBuf<double> cAc, crc, cyc;
+  {
+    const size_t nC = (size_t)7 * c_nc;
+    cAc.alloc(std::max(2 * nC * nC, (size_t)1)); crc.alloc(std::max(2 * nC, (size_t)1)); cyc.alloc(std::max(nC, (size_t)1));
+  }
   double* h_scal = nullptr;
   CCM_CUDA(cudaMallocHost((void**)&h_scal, 8 * sizeof(double)));
   struct HostGuard { double* p; ~HostGuard() { cudaFreeHost(p); } } hg{h_scal};
@@ -445,8 +457,9 @@ void pgo_solve(const ccm_pgo_problem* p, const ccm_pgo_options* o, ccm_pgo_resul
       a.n = n; a.rowptr = d_rowptr.p; a.col = d_col.p; a.val = Hs.p; a.Minv = Minv.p; a.b = b.p;
       a.x = x.p; a.r = pr.p; a.z = pz.p; a.p = pp.p; a.q = pq.p; a.partials = pcg_partials.p; a.bar = bar.p;
       a.tol = pcg_tol; a.max_iter = pcg_max; a.status = pcg_status.p;
+      a.agg = c_agg; a.nc = c_nc; a.Ac = cAc.p; a.rc = crc.p; a.yc = cyc.p; a.coarse_mode = 1; a.prof = nullptr;
       void* args[] = {&a};
-      CCM_CUDA(cudaLaunchCooperativeKernel((void*)k_pcg<7>, dim3(pcg_grid), dim3(TPB), args, 0, s));
+      CCM_CUDA(cudaLaunchCooperativeKernel((void*)k_pcg<7>, dim3(pcg_grid), dim3(pcg_block), args, 0, s));
       CCM_LAUNCHED();
       const int g = std::max(1, std::min(div_up(K, 128), gsm * 8));
       k_pgo_update<<<g, 128, 0, s>>>(cur, d_vidx.p, x.p, b.p, K, p->fix_scale, lambda, trial, partials.p);

@@ -129,6 +129,9 @@ void ccm_ba_destroy(ccm_ba_handle* h);
 int ccm_ba_shard_range(const int32_t* obs_mp, int32_t E, int32_t P, int32_t rank, int32_t nranks, int32_t* L0, int32_t* L1,
                        int64_t* E0, int64_t* E1);
 
+/* developer hook: SM-clock cycles CTA 0 of the PCG kernel spent per phase (needs CCM_PCG_PROF=1 at create time) */
+int ccm_ba_debug_pcg_cycles(ccm_ba_handle* h, int64_t* cycles8);
+
 /* problem-shape facts of a handle (for roofline accounting) */
 typedef struct ccm_ba_info {
   int32_t K, K_free, P_local, E_local, rank, nranks;

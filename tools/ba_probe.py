@@ -23,3 +23,9 @@ lam = float(r["trace"][0, 1]) if len(r["trace"]) else 1.0
 for i, n in enumerate(names):
     print(f"  kernel {n:12s}: {h.time_kernel(i, reps=3, lam=lam):9.4f} ms")
 print("launches", api.kernel_launches())
+import ctypes as C
+cyc = np.zeros(8, np.int64)
+api.lib().ccm_ba_debug_pcg_cycles(h._h, cyc.ctypes.data_as(C.c_void_p))
+if cyc.sum() > 0:
+    names = ["setup", "spmv", "update+restrict", "coarse", "precond", "p-update", "-", "-"]
+    print("pcg phase cycles (CTA 0):", {n: int(c) for n, c in zip(names, cyc)}, "share:", {n: round(float(c) / cyc.sum(), 3) for n, c in zip(names, cyc) if c})
