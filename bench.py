@@ -97,7 +97,7 @@ def algorithmic_bytes(info, P_local, E_local):
     E, P = E_local, P_local
     return {
         "linearize": E * (20 + 144) + P * (24 + 72) + K * 56,          # B_lin without the Hpp write (that is pose_pass)
-        "pose_pass": E * (8 + 16) + P * 24 + K * 56 + Kf * 336,        # product-list entry + (lm, uv, w) + point + Hpp/bp write
+        "pose_pass": E * 16 + P * 24 + K * 56 + Kf * 336,              # packed (u, v, w, lm) stream + point + Hpp/bp write
         "scale": E * (144 + 144 + 4) + P * (48 + 24 + 24),             # W read, Z write, Hll/bl read, g write
         "schur": E * 144 + npr * 8 + nub * 288 + Kf * 48,              # Z once, product lists, S upper blocks + bschur write
         "finalize": nub * 288 + nnzb * 288 + Kf * (336 + 288 + 48),

@@ -47,7 +47,8 @@ __device__ __forceinline__ Pose load_pose(const double* __restrict__ pose, int k
 // K1+K2: one thread per observation (landmark order).
 //   reads  20 B/obs (kf, lm, uv, w) + gathers (pose 56 B, intr 32 B, point 24 B: cache resident)
 //   writes 144 B/obs (W, SoA, fully coalesced) + 72 B/landmark (Hll, bl) via warp-segmented reduction
-__global__ void __launch_bounds__(TPB) k_linearize(
+template <int MINB>
+__global__ void __launch_bounds__(TPB, MINB) k_linearize(
     const int* __restrict__ o_kf, const int* __restrict__ o_lm, const float2* __restrict__ o_uv,
     const float* __restrict__ o_w, const double* __restrict__ pose, const double* __restrict__ intr,
     const int* __restrict__ pose_slot, const double* __restrict__ pt, int E, size_t Ep, int Pl, int robust,
@@ -179,31 +180,43 @@ __global__ void __launch_bounds__(TPB) k_edge_report(
 }
 
 // ------------------------------------------------------------------------------------------------------------
+// per free pose: its observations packed as (u, v, signed weight, landmark) in diagonal-product-list order, so that the pose
+// pass streams 16 coalesced bytes per observation instead of chasing four index arrays
+__global__ void __launch_bounds__(128) k_pack_pose_obs(const uint2* __restrict__ prod, const unsigned* __restrict__ u_prod_ptr,
+                                                       const int* __restrict__ u_diag, const unsigned* __restrict__ kobs_ptr,
+                                                       const int* __restrict__ o_lm, const float2* __restrict__ o_uv,
+                                                       const float* __restrict__ o_w, float4* __restrict__ kobs) {
+  const int a = blockIdx.x;
+  const unsigned beg = u_prod_ptr[u_diag[a]], n = u_prod_ptr[u_diag[a] + 1] - beg, dst = kobs_ptr[a];
+  for (unsigned i = threadIdx.x; i < n; i += blockDim.x) {
+    const unsigned e = prod[beg + i].x;
+    const float2 uv = o_uv[e];
+    kobs[dst + i] = make_float4(uv.x, uv.y, o_w[e], __int_as_float(o_lm[e]));
+  }
+}
+
 // K2 pose side: one CTA per free pose; its observations are the product list of the diagonal Schur block (a,a).
 __global__ void __launch_bounds__(128) k_pose_pass(
-    const uint2* __restrict__ prod, const unsigned* __restrict__ u_prod_ptr, const int* __restrict__ u_diag,
-    const int* __restrict__ slot_pose, const int* __restrict__ o_lm, const float2* __restrict__ o_uv,
-    const float* __restrict__ o_w, const double* __restrict__ pose, const double* __restrict__ intr,
+    const float4* __restrict__ kobs, const unsigned* __restrict__ kobs_ptr,
+    const int* __restrict__ slot_pose, const double* __restrict__ pose, const double* __restrict__ intr,
     const double* __restrict__ pt, int robust, double delta, double* __restrict__ Hpp, double* __restrict__ bp) {
   __shared__ double red[27][4];
   const int a = blockIdx.x;
   const int kf = slot_pose[a];
-  const int u = u_diag[a];
-  const unsigned beg = u_prod_ptr[u], end = u_prod_ptr[u + 1];
+  const unsigned beg = kobs_ptr[a], end = kobs_ptr[a + 1];
   const Pose T = load_pose(pose, kf);
   const double in4[4] = {intr[4 * (size_t)kf], intr[4 * (size_t)kf + 1], intr[4 * (size_t)kf + 2], intr[4 * (size_t)kf + 3]};
   double acc[27];
 #pragma unroll
   for (int i = 0; i < 27; i++) acc[i] = 0.0;
   for (unsigned p = beg + threadIdx.x; p < end; p += blockDim.x) {
-    const unsigned e = prod[p].x;
-    const int lm = o_lm[e];
-    const float2 uv = o_uv[e];
-    const float wf = o_w[e];
+    const float4 ob = kobs[p];
+    const int lm = __float_as_int(ob.w);
+    const float wf = ob.z;
     const double w = fabs((double)wf);
     const double* X = pt + 3 * (size_t)lm;
     ObsLin L;
-    linearize_obs(T, in4, X[0], X[1], X[2], (double)uv.x, (double)uv.y, w, L);
+    linearize_obs(T, in4, X[0], X[1], X[2], (double)ob.x, (double)ob.y, w, L);
     double rho0, rho1 = 1.0;
     if (robust && !signbit(wf)) huber(L.chi2, delta, rho0, rho1);
     const double wo = rho1 * w;

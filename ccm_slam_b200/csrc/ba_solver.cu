@@ -69,6 +69,8 @@ struct ccm_ba_handle {
   DevBuf<int> s_rowptr, s_col, s_row, s_diag, csr_u, u_row, u_col, u_diag, word_prefix;
   DevBuf<unsigned> bitmap, u_prod_ptr;
   DevBuf<uint2> prod;
+  DevBuf<float4> kobs;            // per free pose: (u, v, signed w, landmark) of its observations, packed
+  DevBuf<unsigned> kobs_ptr;
   // pcg
   DevBuf<double> x, pr, pz, pp, pq, pcg_partials, pcg_status, dxl, pcg_Ac, pcg_rc, pcg_yc;
   int pcg_agg = 0, pcg_nc = 0, pcg_refresh = 4, pcg_age = 0;
@@ -141,6 +143,26 @@ void collect_spans(ccm_ba_handle* h) {  // call after a stream synchronize
   h->ev_used = 0;
 }
 
+void launch_linearize(ccm_ba_handle* h, int g, int robust, double delta) {
+  // 64 registers / 4 CTAs per SM by default (48 B of L1-resident spill; measured 0.77 ms vs 0.81 ms at 80 registers and
+  // 0.94 ms at 128 registers on cfg5); CCM_LIN_MINB=2|3 selects the other builds
+  static const int minb = env_int("CCM_LIN_MINB", 4);
+  cudaStream_t s = h->stream;
+#define CCM_LIN_ARGS h->o_kf.p, h->o_lm.p, h->o_uv.p, h->o_w.p, h->pose_cur, h->intr.p, h->pose_slot.p, h->pt_cur, h->El, h->Ep, \
+                     h->Pl, robust, delta, h->W.p, h->Hll(), h->bl(), h->partials.p
+  if (minb == 2) k_linearize<2><<<g, TPB, 0, s>>>(CCM_LIN_ARGS);
+  else if (minb == 3) k_linearize<3><<<g, TPB, 0, s>>>(CCM_LIN_ARGS);
+  else k_linearize<4><<<g, TPB, 0, s>>>(CCM_LIN_ARGS);
+#undef CCM_LIN_ARGS
+}
+
+void pack_pose_obs(ccm_ba_handle* h) {
+  if (h->Kf == 0 || h->El == 0) return;
+  k_pack_pose_obs<<<h->Kf, 128, 0, h->stream>>>(h->prod.p, h->u_prod_ptr.p, h->u_diag.p, h->kobs_ptr.p, h->o_lm.p, h->o_uv.p,
+                                              h->o_w.p, h->kobs.p);
+  CCM_LAUNCHED();
+}
+
 void sum_partials_to(ccm_ba_handle* h, int n, double* out) {
   k_sum_partials<<<1, 1024, 0, h->stream>>>(h->partials.p, n, out);
   CCM_LAUNCHED();
@@ -153,15 +175,14 @@ void step_linearize(ccm_ba_handle* h, int robust, double delta) {
   const int g = grid_stride(h->El);
   {
     KernelSpan sp(h, CCM_BA_K_LINEARIZE);
-    k_linearize<<<g, TPB, 0, s>>>(h->o_kf.p, h->o_lm.p, h->o_uv.p, h->o_w.p, h->pose_cur, h->intr.p, h->pose_slot.p,
-                                  h->pt_cur, h->El, h->Ep, h->Pl, robust, delta, h->W.p, h->Hll(), h->bl(), h->partials.p);
+    launch_linearize(h, g, robust, delta);
     CCM_LAUNCHED();
   }
   sum_partials_to(h, g, h->chi2_cur_dev());
   if (h->Kf > 0) {
     KernelSpan sp(h, CCM_BA_K_POSE_PASS);
-    k_pose_pass<<<h->Kf, 128, 0, s>>>(h->prod.p, h->u_prod_ptr.p, h->u_diag.p, h->slot_pose.p, h->o_lm.p, h->o_uv.p,
-                                      h->o_w.p, h->pose_cur, h->intr.p, h->pt_cur, robust, delta, h->Hpp(), h->bp());
+    k_pose_pass<<<h->Kf, 128, 0, s>>>(h->kobs.p, h->kobs_ptr.p, h->slot_pose.p, h->pose_cur, h->intr.p, h->pt_cur, robust, delta,
+                                      h->Hpp(), h->bp());
     CCM_LAUNCHED();
   }
   if (h->nranks > 1) allreduce_f64(h->Hbuf.p, (size_t)h->Kf * 42 + 1, 0, s);
@@ -486,6 +507,15 @@ void build(ccm_ba_handle* h, const ccm_ba_problem* p) {
     CCM_LAUNCHED();
   }
 
+  // packed per-pose observation stream for the pose pass
+  {
+    std::vector<unsigned> kp((size_t)Kf + 1, 0);
+    for (int a = 0; a < Kf; a++) kp[a + 1] = kp[a] + (h_pp[h_udiag[a] + 1] - h_pp[h_udiag[a]]);
+    upload_vec(h->kobs_ptr, kp, s);
+    h->kobs.alloc(std::max((size_t)kp[Kf], (size_t)1));
+    pack_pose_obs(h);
+  }
+
   // ---- linear-system storage
   h->W.alloc(std::max(h->Ep * 18, (size_t)1)); h->Z.alloc(std::max((size_t)El * 18, (size_t)2));
   h->HllBl.alloc(std::max((size_t)Pl * 9, (size_t)1)); h->gvec.alloc(std::max((size_t)Pl * 3, (size_t)1));
@@ -723,6 +753,7 @@ extern "C" int ccm_ba_set_edge_flags(ccm_ba_handle* h, const uint8_t* edge_flags
       h->d_flags.upload(h->h_flags.data(), h->El, h->stream);
       k_apply_flags<<<div_up(h->El, TPB), TPB, 0, h->stream>>>(h->o_w_raw.p, h->d_flags.p, h->El, h->o_w.p);
       CCM_LAUNCHED();
+      pack_pose_obs(h);
       CCM_CUDA(cudaStreamSynchronize(h->stream));
     }
   });
@@ -884,13 +915,11 @@ extern "C" int ccm_ba_time_kernel(ccm_ba_handle* h, int which, int reps, double 
       CCM_CUDA(cudaEventRecord(e0, s));
       switch (which) {
         case 0:
-          k_linearize<<<grid_stride(h->El), TPB, 0, s>>>(h->o_kf.p, h->o_lm.p, h->o_uv.p, h->o_w.p, h->pose_cur, h->intr.p,
-                                                         h->pose_slot.p, h->pt_cur, h->El, h->Ep, h->Pl, 1, huber_delta, h->W.p,
-                                                         h->Hll(), h->bl(), h->partials.p);
+          launch_linearize(h, grid_stride(h->El), 1, huber_delta);
           break;
         case 1:
-          k_pose_pass<<<h->Kf, 128, 0, s>>>(h->prod.p, h->u_prod_ptr.p, h->u_diag.p, h->slot_pose.p, h->o_lm.p, h->o_uv.p,
-                                            h->o_w.p, h->pose_cur, h->intr.p, h->pt_cur, 1, huber_delta, h->Hpp(), h->bp());
+          k_pose_pass<<<h->Kf, 128, 0, s>>>(h->kobs.p, h->kobs_ptr.p, h->slot_pose.p, h->pose_cur, h->intr.p, h->pt_cur, 1, huber_delta,
+                                            h->Hpp(), h->bp());
           break;
         case 2:
           k_residual<<<grid_stride(h->El), TPB, 0, s>>>(h->o_kf.p, h->o_lm.p, h->o_uv.p, h->o_w.p, h->pose_cur, h->intr.p,
