@@ -724,6 +724,7 @@ extern "C" int ccm_ba_create(const ccm_ba_problem* p, ccm_ba_handle** out) {
     try {
       build(h, p);
     } catch (...) {
+      cudaDeviceSynchronize();  // in-flight kernels must not outlive the buffers that go back to the pool
       delete h;
       throw;
     }
@@ -734,6 +735,7 @@ extern "C" int ccm_ba_create(const ccm_ba_problem* p, ccm_ba_handle** out) {
 extern "C" void ccm_ba_destroy(ccm_ba_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);  // nothing may still use the buffers that go back to the pool
   delete h;
 }
 

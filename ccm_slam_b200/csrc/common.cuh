@@ -45,6 +45,11 @@ extern std::atomic<uint64_t> g_launches;
     CCM_CUDA(cudaGetLastError());     \
   } while (0)
 
+// device allocations go through the stream-ordered allocator with an unbounded release threshold: repeated
+// create/solve/destroy cycles (LocalBA runs once per keyframe) reuse cached memory instead of paying cudaMalloc/cudaFree
+void* dev_alloc(size_t bytes);
+void dev_free(void* p);
+
 template <typename T>
 struct DevBuf {
   T* p = nullptr;
@@ -54,13 +59,13 @@ struct DevBuf {
   DevBuf& operator=(const DevBuf&) = delete;
   ~DevBuf() { release(); }
   void release() {
-    if (p) cudaFree(p);
+    if (p) dev_free(p);
     p = nullptr; n = 0;
   }
   void alloc(size_t count) {
     release();
     n = count;
-    if (count) CCM_CUDA(cudaMalloc((void**)&p, count * sizeof(T)));
+    if (count) p = static_cast<T*>(dev_alloc(count * sizeof(T)));
   }
   void alloc_zero(size_t count, cudaStream_t s) {
     alloc(count);

@@ -808,5 +808,6 @@ extern "C" int ccm_orb_debug_cell(ccm_orb_handle* h, int32_t cell, int32_t* geom
 extern "C" void ccm_orb_destroy(ccm_orb_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream);
   delete h;
 }

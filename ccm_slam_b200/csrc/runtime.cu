@@ -38,6 +38,42 @@ int sm_count() {
   return v;
 }
 
+// ---- pooled device memory --------------------------------------------------------------------------------------
+static std::mutex g_alloc_mu;
+static cudaStream_t g_alloc_stream[64] = {nullptr};
+static bool g_pool_ready[64] = {false};
+
+static cudaStream_t alloc_stream(int dev) {
+  std::lock_guard<std::mutex> lk(g_alloc_mu);
+  if (!g_pool_ready[dev]) {
+    CCM_CUDA(cudaStreamCreateWithFlags(&g_alloc_stream[dev], cudaStreamNonBlocking));
+    cudaMemPool_t pool;
+    CCM_CUDA(cudaDeviceGetDefaultMemPool(&pool, dev));
+    unsigned long long thr = ~0ull;  // never hand cached memory back to the driver
+    CCM_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    g_pool_ready[dev] = true;
+  }
+  return g_alloc_stream[dev];
+}
+
+void* dev_alloc(size_t bytes) {
+  int dev = 0;
+  CCM_CUDA(cudaGetDevice(&dev));
+  cudaStream_t s = alloc_stream(dev & 63);
+  void* p = nullptr;
+  CCM_CUDA(cudaMallocAsync(&p, bytes, s));
+  CCM_CUDA(cudaStreamSynchronize(s));  // the block is usable from any stream afterwards
+  return p;
+}
+
+void dev_free(void* p) {
+  // callers synchronise the stream that used the block before releasing it (handle destructors do)
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return;
+  if (!g_pool_ready[dev & 63]) { cudaFree(p); return; }
+  cudaFreeAsync(p, g_alloc_stream[dev & 63]);
+}
+
 // ---- NCCL through dlopen: the single-GPU path has no link-time dependency on it ----
 typedef struct { char internal[128]; } ncclUniqueId_t;
 typedef int (*fn_ncclGetUniqueId)(ncclUniqueId_t*);
