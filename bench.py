@@ -265,8 +265,12 @@ def main():
         barrier()
         t0 = time.perf_counter()
         r = api.ba_solve(p, iterations=LM_ITERS, huber_delta=delta, want_edges=False)
-        e2e_t += max_over_ranks(time.perf_counter() - t0)
+        dt = max_over_ranks(time.perf_counter() - t0)
+        e2e_t += dt
         e2e_it += r["iters_done"]; setup_ms += r["t_setup_ms"]
+        if rank == 0:
+            print("[bench] e2e step: wall %.1f ms (setup %.1f, optimize %.1f, download %.1f, pcg its %d)" % (
+                dt * 1e3, r["t_setup_ms"], r["t_optimize_ms"], r["t_download_ms"], r["pcg_iters_total"]), file=sys.stderr)
     for a in pinned:
         api.host_unregister(a)
     e2e_val = e2e_it / e2e_t

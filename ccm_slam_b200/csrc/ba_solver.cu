@@ -538,7 +538,7 @@ void build(ccm_ba_handle* h, const ccm_ba_problem* p) {
   if (env_int("CCM_PCG_PROF", 0)) h->pcg_prof.alloc_zero(8, s);
   // coarse space: <= 64 aggregates for small systems (the in-kernel inversion costs one grid barrier per coarse unknown),
   // <= 128 for long trajectories where the smooth modes dominate the iteration count
-  pcg_coarse_shape(Kf, env_int("CCM_PCG_NC", Kf >= 4096 ? 256 : 64), &h->pcg_agg, &h->pcg_nc);
+  pcg_coarse_shape(Kf, env_int("CCM_PCG_NC", Kf >= 4096 ? 384 : 64), &h->pcg_agg, &h->pcg_nc);
   h->pcg_refresh = std::max(1, env_int("CCM_PCG_REFRESH", Kf >= 4096 ? 4 : 1));
   {
     const size_t nC = (size_t)6 * h->pcg_nc;

@@ -18,6 +18,8 @@
 namespace ccm {
 
 constexpr int TPB = 256;
+constexpr int GJB = 8;          // pivots eliminated per sweep of the coarse-matrix inversion
+constexpr int GJ_CW = 256;       // column chunk a CTA stages per sweep
 constexpr int PCG_TPB = 1024;  // one fat CTA per SM keeps the grid barrier at <= 148 participants
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -81,6 +83,9 @@ template <int BS>
 __global__ void __launch_bounds__(PCG_TPB, 1) k_pcg(PcgArgs A) {
   constexpr int BB = BS * BS;
   __shared__ double red[PCG_TPB / 32];
+  __shared__ double gj_rows[GJB * GJ_CW];
+  __shared__ double gj_pi[GJB * GJB];
+  __shared__ int gj_bad;
   const int bdim = blockDim.x;  // 256 (small systems: spread over more SMs) or PCG_TPB
   const int lane = threadIdx.x & 31;
   const int gw = (blockIdx.x * bdim + threadIdx.x) >> 5;
@@ -97,7 +102,7 @@ __global__ void __launch_bounds__(PCG_TPB, 1) k_pcg(PcgArgs A) {
 
   // ---- coarse level set-up: Ac = P^T S P, then Ac^-1 by ping-pong Gauss-Jordan -------------------------------------
   if (coarse && A.coarse_mode == 2) {
-    Ainv = (nC & 1) ? A.Ac + (size_t)nC * nC : A.Ac;
+    Ainv = (((nC + GJB - 1) / GJB) & 1) ? A.Ac + (size_t)nC * nC : A.Ac;
     for (long long i = gtid; i < 2ll * nC; i += gthreads) A.rc[i] = 0.0;
     grid_barrier(A.bar, target);
   } else if (coarse) {
@@ -130,28 +135,106 @@ __global__ void __launch_bounds__(PCG_TPB, 1) k_pcg(PcgArgs A) {
       }
     }
     grid_barrier(A.bar, target);
-    // Gauss-Jordan without pivoting (the matrix is SPD): step k reads buffer k&1, writes buffer (k+1)&1
+    // Block Gauss-Jordan without pivoting (the matrix is SPD, so every pivot block is too): sweep t eliminates GJB pivots at
+    // once (rank-GJB update), reads buffer t&1 and writes buffer (t+1)&1 -> one grid barrier and one pass over the matrix
+    // per GJB pivots instead of per pivot.  With A = [[P, R], [C, D]] the sweep writes [[P^-1, P^-1 R], [-C P^-1, D - C P^-1 R]].
+    // Work split of one sweep: the matrix is cut into column chunks of GJ_CW; a CTA stages the GJB pivot rows of its chunk
+    // in shared memory once and its warps stream rows i through it (read src[i][chunk], write dst[i][chunk]); the L2
+    // traffic per sweep is one read + one write of the matrix.
     bool bad = false;
-    for (int k = 0; k < nC; k++) {
-      const double* src = (k & 1) ? A1 : A0;
-      double* dst = (k & 1) ? A0 : A1;
-      const double piv = __ldcg(src + (size_t)k * nC + k);
-      if (!(piv > 0.0) || !isfinite(piv)) { bad = true; break; }  // uniform: every thread reads the same pivot
-      const double ip = 1.0 / piv;
-      for (long long e = gtid; e < (long long)nC * nC; e += gthreads) {
-        const int i = (int)(e / nC), j = (int)(e - (long long)i * nC);
-        double v;
-        if (i == k) v = (j == k) ? ip : __ldcg(src + (size_t)k * nC + j) * ip;
-        else {
-          const double f = __ldcg(src + (size_t)i * nC + k) * ip;
-          v = (j == k) ? -f : __ldcg(src + e) - f * __ldcg(src + (size_t)k * nC + j);
+    int sweep = 0;
+    const int wid = threadIdx.x >> 5, wpc = bdim >> 5;
+    const int nch = (nC + GJ_CW - 1) / GJ_CW;
+    const int rgs = G / nch > 0 ? G / nch : 1;  // CTAs sharing one column chunk
+    for (int k0 = 0; k0 < nC; k0 += GJB, sweep++) {
+      const int kb = nC - k0 < GJB ? nC - k0 : GJB;
+      const double* src = (sweep & 1) ? A1 : A0;
+      double* dst = (sweep & 1) ? A0 : A1;
+      if (wid == 0) {  // warp 0: inverse of the pivot block in shared memory (identical in every CTA); identity past kb
+        for (int t = lane; t < GJB * GJB; t += 32) {
+          const int a = t / GJB, b2 = t % GJB;
+          gj_pi[t] = (a < kb && b2 < kb) ? __ldcg(src + (size_t)(k0 + a) * nC + k0 + b2) : (a == b2 ? 1.0 : 0.0);
         }
-        dst[e] = v;
+        if (lane == 0) gj_bad = 0;
+        __syncwarp();
+        for (int q = 0; q < GJB; q++) {
+          const double piv = gj_pi[q * GJB + q];
+          const double ip = 1.0 / piv;
+          double nv[(GJB * GJB + 31) / 32];
+#pragma unroll
+          for (int u = 0; u < (GJB * GJB + 31) / 32; u++) {
+            const int t = lane + 32 * u, r2 = t / GJB, c2 = t % GJB;
+            if (t < GJB * GJB) {
+              const double old = gj_pi[t], prq = gj_pi[r2 * GJB + q], pqc = gj_pi[q * GJB + c2];
+              nv[u] = r2 == q ? (c2 == q ? ip : pqc * ip) : (c2 == q ? -prq * ip : old - prq * (pqc * ip));
+            }
+          }
+          __syncwarp();
+#pragma unroll
+          for (int u = 0; u < (GJB * GJB + 31) / 32; u++)
+            if (lane + 32 * u < GJB * GJB) gj_pi[lane + 32 * u] = nv[u];
+          if (lane == 0 && (!(piv > 0.0) || !isfinite(piv))) gj_bad = 1;
+          __syncwarp();
+        }
       }
+      for (int item = blockIdx.x; item < nch * rgs; item += G) {
+        const int c0 = (item % nch) * GJ_CW, rg = item / nch;
+        for (int t = threadIdx.x; t < GJB * GJ_CW; t += bdim) {
+          const int l = t / GJ_CW, j = c0 + t % GJ_CW;
+          gj_rows[t] = (l < kb && j < nC) ? __ldcg(src + (size_t)(k0 + l) * nC + j) : 0.0;
+        }
+        const int rstep = rgs * wpc;
+        int i = rg * wpc + wid;
+        double fn[GJB];  // pivot-column entries of the next row, fetched one row ahead
+#pragma unroll
+        for (int m = 0; m < GJB; m++) fn[m] = (i < nC && m < kb) ? __ldcg(src + (size_t)i * nC + k0 + m) : 0.0;
+        __syncthreads();
+        for (; i < nC && !gj_bad; i += rstep) {
+          const bool ib = i >= k0 && i < k0 + kb;
+          double g[GJB];  // row coefficients: pivot row -> -P^-1[i-k0][:], other rows -> src[i][pivots] * P^-1
+#pragma unroll
+          for (int l = 0; l < GJB; l++) g[l] = 0.0;
+          if (ib) {
+#pragma unroll
+            for (int l = 0; l < GJB; l++) g[l] = -gj_pi[(i - k0) * GJB + l];
+          } else {
+#pragma unroll
+            for (int m = 0; m < GJB; m++) {
+#pragma unroll
+              for (int l = 0; l < GJB; l++) g[l] += fn[m] * gj_pi[m * GJB + l];
+            }
+          }
+          {
+            const int in = i + rstep;
+#pragma unroll
+            for (int m = 0; m < GJB; m++) fn[m] = (in < nC && m < kb) ? __ldcg(src + (size_t)in * nC + k0 + m) : 0.0;
+          }
+#pragma unroll
+          for (int t = 0; t < GJ_CW / 32; t++) {
+            const int jl = lane + 32 * t, j = c0 + jl;
+            if (j >= nC) break;
+            double v;
+            if (j >= k0 && j < k0 + kb) {
+              const int jj = j - k0;
+              v = 0.0;
+#pragma unroll
+              for (int l = 0; l < GJB; l++) v = (l == jj) ? -g[l] : v;
+            } else {
+              v = ib ? 0.0 : __ldcg(src + (size_t)i * nC + j);
+#pragma unroll
+              for (int l = 0; l < GJB; l++) v -= g[l] * gj_rows[l * GJ_CW + jl];
+            }
+            dst[(size_t)i * nC + j] = v;
+          }
+        }
+        __syncthreads();  // readers of gj_rows are done before the next item restages it
+      }
+      __syncthreads();
+      if (gj_bad) { bad = true; break; }  // uniform over the grid: every CTA inverted the same pivot block
       grid_barrier(A.bar, target);
     }
     if (bad) coarse = false;
-    Ainv = (nC & 1) ? A1 : A0;
+    Ainv = (((nC + GJB - 1) / GJB) & 1) ? A1 : A0;
   }
 
   // z = Minv r for the rows of this warp; with the coarse level: += (P yc)[row]
