@@ -46,7 +46,7 @@ __device__ __forceinline__ double block_sum(double v, double* smem) {
 struct PcgArgs {
   int n;  // block rows
   const int* rowptr; const int* col; const double* val; const double* Minv; const double* b;
-  double *x, *r, *z, *p, *q;
+  double *x, *r, *z, *p, *q;  // p: 2 * n*BS (double buffered search direction)
   double* partials;  // 3 * gridDim.x
   unsigned* bar;     // zeroed before launch
   double tol; int max_iter;
@@ -57,7 +57,7 @@ struct PcgArgs {
   double* Ac;        // 2 * (BS*nc)^2 ping-pong buffers
   double* rc;        // 2 * BS*nc restricted residual (double buffered)
   double* yc;        // BS*nc coarse correction
-  long long* prof;   // optional: 8 cycle counters filled by CTA 0 (setup, spmv, update+restrict, coarse, precond, p-update) or NULL
+  long long* prof;   // optional: 8 cycle counters filled by CTA 0 (setup, spmv, update+restrict, coarse, precond, unused) or NULL
 };
 
 __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& target) {
@@ -79,8 +79,9 @@ __device__ __forceinline__ double sum_partials_dev(const double* partials, int g
   return warp_sum(v);
 }
 
-template <int BS>
-__global__ void __launch_bounds__(PCG_TPB, 1) k_pcg(PcgArgs A) {
+// MAXT/MINB: launch bounds of the variant (1024x1 leaves 64 registers per thread, 512x1 and 256x2 leave 128)
+template <int BS, int MAXT = PCG_TPB, int MINB = 1>
+__global__ void __launch_bounds__(MAXT, MINB) k_pcg(PcgArgs A) {
   constexpr int BB = BS * BS;
   __shared__ double red[PCG_TPB / 32];
   __shared__ double gj_rows[GJB * GJ_CW];
@@ -238,7 +239,7 @@ __global__ void __launch_bounds__(PCG_TPB, 1) k_pcg(PcgArgs A) {
   }
 
   // z = Minv r for the rows of this warp; with the coarse level: += (P yc)[row]
-  auto precond_rows = [&](double& acc_rz, double& acc_rr, bool init) {
+  auto precond_rows = [&](double& acc_rz, double& acc_rr) {
     for (int a = gw; a < A.n; a += nw) {
       double rv = 0.0;
       if (lane < BS) rv = A.r[(size_t)a * BS + lane];
@@ -252,7 +253,6 @@ __global__ void __launch_bounds__(PCG_TPB, 1) k_pcg(PcgArgs A) {
         for (int k = 0; k < BS; k++) zv += M[k] * r6[k];
         if (coarse) zv += __ldcg(A.yc + (size_t)(a / A.agg) * BS + lane);
         A.z[(size_t)a * BS + lane] = zv;
-        if (init) A.p[(size_t)a * BS + lane] = zv;
         acc_rz += rv * zv;
         acc_rr += rv * rv;
       }
@@ -284,6 +284,7 @@ __global__ void __launch_bounds__(PCG_TPB, 1) k_pcg(PcgArgs A) {
     if (lane < BS) {
       A.x[(size_t)a * BS + lane] = 0.0;
       A.r[(size_t)a * BS + lane] = A.b[(size_t)a * BS + lane];
+      A.p[(size_t)a * BS + lane] = 0.0;  // p_old of the first iteration (beta = 0)
     }
   int buf = 0;
   if (coarse) {
@@ -294,7 +295,7 @@ __global__ void __launch_bounds__(PCG_TPB, 1) k_pcg(PcgArgs A) {
     buf ^= 1;
   }
   double acc_rz = 0.0, acc_bb = 0.0;
-  precond_rows(acc_rz, acc_bb, true);
+  precond_rows(acc_rz, acc_bb);
   {
     const double t0 = block_sum(acc_rz, red);
     const double t1 = block_sum(acc_bb, red);
@@ -309,7 +310,15 @@ __global__ void __launch_bounds__(PCG_TPB, 1) k_pcg(PcgArgs A) {
   if (!(bb > 0.0)) {
     flag = 0;
   } else {
-    for (it = 0; it < A.max_iter; it++) {
+    // The direction update p = z + beta p_old is folded into the product: every reader forms the entries of p it needs from
+    // z and p_old with the same fma the row owner uses (bit-identical), the owner stores its rows into the other p buffer.
+    // This removes the p-update phase and its grid barrier (4 barriers per iteration).
+    const size_t nv = (size_t)A.n * BS;
+    double beta = 0.0;
+    int pc = 0;
+    for (it = 0; it < A.max_iter; it++, pc ^= 1) {
+      const double* pold = A.p + (size_t)pc * nv;
+      double* pnew = A.p + (size_t)(pc ^ 1) * nv;
       // q = S p ; pq = p.q
       double acc_pq = 0.0;
       for (int a = gw; a < A.n; a += nw) {
@@ -319,10 +328,10 @@ __global__ void __launch_bounds__(PCG_TPB, 1) k_pcg(PcgArgs A) {
         const int beg = A.rowptr[a], end = A.rowptr[a + 1];
         for (int j = beg + lane; j < end; j += 32) {
           const double* v = A.val + (size_t)j * BB;
-          const double* pj = A.p + (size_t)A.col[j] * BS;
+          const size_t cj = (size_t)A.col[j] * BS;
           double pv[BS];
 #pragma unroll
-          for (int k = 0; k < BS; k++) pv[k] = __ldcg(pj + k);
+          for (int k = 0; k < BS; k++) pv[k] = fma(beta, __ldcg(pold + cj + k), __ldcg(A.z + cj + k));
           if constexpr (BS % 2 == 0) {
             const double2* v2 = reinterpret_cast<const double2*>(v);
 #pragma unroll
@@ -345,8 +354,10 @@ __global__ void __launch_bounds__(PCG_TPB, 1) k_pcg(PcgArgs A) {
           double yl = y[0];
 #pragma unroll
           for (int k = 1; k < BS; k++) yl = lane == k ? y[k] : yl;
+          const double pn = fma(beta, __ldcg(pold + (size_t)a * BS + lane), __ldcg(A.z + (size_t)a * BS + lane));
+          pnew[(size_t)a * BS + lane] = pn;
           A.q[(size_t)a * BS + lane] = yl;
-          acc_pq += yl * A.p[(size_t)a * BS + lane];
+          acc_pq += yl * pn;
         }
       }
       {
@@ -361,7 +372,7 @@ __global__ void __launch_bounds__(PCG_TPB, 1) k_pcg(PcgArgs A) {
       // x += alpha p ; r -= alpha q   (rows owned by this warp)
       for (int a = gw; a < A.n; a += nw)
         if (lane < BS) {
-          A.x[(size_t)a * BS + lane] += alpha * A.p[(size_t)a * BS + lane];
+          A.x[(size_t)a * BS + lane] += alpha * pnew[(size_t)a * BS + lane];
           A.r[(size_t)a * BS + lane] -= alpha * A.q[(size_t)a * BS + lane];
         }
       if (coarse) {
@@ -374,7 +385,7 @@ __global__ void __launch_bounds__(PCG_TPB, 1) k_pcg(PcgArgs A) {
         buf ^= 1;
       }
       double acc_rz2 = 0.0, acc_rr = 0.0;
-      precond_rows(acc_rz2, acc_rr, false);
+      precond_rows(acc_rz2, acc_rr);
       {
         const double t0 = block_sum(acc_rz2, red);
         const double t1 = block_sum(acc_rr, red);
@@ -385,12 +396,8 @@ __global__ void __launch_bounds__(PCG_TPB, 1) k_pcg(PcgArgs A) {
       const double rz_new = sum_partials_dev(part1, G);
       rr = sum_partials_dev(part2, G);
       if (rr <= stop2) { flag = 0; it++; break; }
-      const double beta = rz_new / rz;
+      beta = rz_new / rz;
       rz = rz_new;
-      for (int a = gw; a < A.n; a += nw)
-        if (lane < BS) A.p[(size_t)a * BS + lane] = A.z[(size_t)a * BS + lane] + beta * A.p[(size_t)a * BS + lane];
-      grid_barrier(A.bar, target);
-      lap(5);
     }
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) {

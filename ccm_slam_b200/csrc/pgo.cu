@@ -386,14 +386,16 @@ void pgo_solve(const ccm_pgo_problem* p, const ccm_pgo_options* o, ccm_pgo_resul
   d_vidx.upload(vidx.data(), K, s); d_rowptr.upload(rowptr.data(), n + 1, s); d_col.upload(col.data(), nnzb, s);
   d_diag.upload(diag.data(), n, s);
   H.alloc(nnzb * 49); Hs.alloc(nnzb * 49); b.alloc((size_t)n * 7); Minv.alloc((size_t)n * 49);
-  x.alloc_zero((size_t)n * 7, s); pr.alloc((size_t)n * 7); pz.alloc((size_t)n * 7); pp.alloc((size_t)n * 7); pq.alloc((size_t)n * 7);
+  x.alloc_zero((size_t)n * 7, s); pr.alloc((size_t)n * 7); pz.alloc((size_t)n * 7); pp.alloc((size_t)2 * n * 7); pq.alloc((size_t)n * 7);
   const int gsm = sm_count();
   partials.alloc((size_t)gsm * 8 + 8); scal.alloc_zero(8, s); pcg_status.alloc_zero(4, s); bar.alloc_zero(1, s); fail.alloc_zero(1, s);
+  const int pcg_block = ((long long)n * 32 >= (long long)gsm * PCG_TPB) ? 512 : 256;
+  void* pcg_fn = pcg_block == 512 ? (void*)k_pcg<7, 512, 1> : (void*)k_pcg<7, 256, 2>;
   int per_sm = 0;
-  CCM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pcg<7>, PCG_TPB, 0));
+  CCM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)pcg_fn, pcg_block, 0));
   CCM_REQUIRE(per_sm >= 1, "k_pcg does not fit on an SM");
-  const int pcg_block = ((long long)n * 32 >= (long long)gsm * PCG_TPB) ? PCG_TPB : 256;
-  const int pcg_grid = std::max(1, std::min(gsm * (PCG_TPB / pcg_block), div_up((long long)n * 32, pcg_block)));
+  per_sm = std::min(per_sm, pcg_block == 256 ? 2 : 1);
+  const int pcg_grid = std::max(1, std::min(gsm * per_sm, div_up((long long)n * 32, pcg_block)));
   pcg_partials.alloc((size_t)3 * pcg_grid);
   int c_agg = 0, c_nc = 0;
   {
@@ -459,7 +461,7 @@ void pgo_solve(const ccm_pgo_problem* p, const ccm_pgo_options* o, ccm_pgo_resul
       a.tol = pcg_tol; a.max_iter = pcg_max; a.status = pcg_status.p;
       a.agg = c_agg; a.nc = c_nc; a.Ac = cAc.p; a.rc = crc.p; a.yc = cyc.p; a.coarse_mode = 1; a.prof = nullptr;
       void* args[] = {&a};
-      CCM_CUDA(cudaLaunchCooperativeKernel((void*)k_pcg<7>, dim3(pcg_grid), dim3(pcg_block), args, 0, s));
+      CCM_CUDA(cudaLaunchCooperativeKernel(pcg_fn, dim3(pcg_grid), dim3(pcg_block), args, 0, s));
       CCM_LAUNCHED();
       const int g = std::max(1, std::min(div_up(K, 128), gsm * 8));
       k_pgo_update<<<g, 128, 0, s>>>(cur, d_vidx.p, x.p, b.p, K, p->fix_scale, lambda, trial, partials.p);

@@ -84,7 +84,7 @@ typedef struct ccm_ba_options {
   double lambda_init;        /* <= 0 : g2o default tau*max|H_jj|, tau = 1e-5 */
   int32_t max_trials;        /* <= 0 : 10 (maxTrialsAfterFailure) */
   int32_t pcg_max_iter;      /* <= 0 : 2000 */
-  double pcg_tol;            /* <= 0 : 1e-10 ; stop when |r|_2 <= pcg_tol*|b|_2 */
+  double pcg_tol;            /* <= 0 : 1e-8 ; stop when |r|_2 <= pcg_tol*|b|_2 */
   const volatile uint8_t* stop; /* optimizer.setForceStopFlag(pbStopFlag): polled between LM iterations and trials; may be NULL */
 } ccm_ba_options;
 

@@ -27,5 +27,5 @@ import ctypes as C
 cyc = np.zeros(8, np.int64)
 api.lib().ccm_ba_debug_pcg_cycles(h._h, cyc.ctypes.data_as(C.c_void_p))
 if cyc.sum() > 0:
-    names = ["setup", "spmv", "update+restrict", "coarse", "precond", "p-update", "-", "-"]
+    names = ["setup", "spmv", "update+restrict", "coarse", "precond", "unused", "-", "-"]
     print("pcg phase cycles (CTA 0):", {n: int(c) for n, c in zip(names, cyc)}, "share:", {n: round(float(c) / cyc.sum(), 3) for n, c in zip(names, cyc) if c})
