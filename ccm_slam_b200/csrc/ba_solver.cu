@@ -636,6 +636,10 @@ void optimize(ccm_ba_handle* h, const ccm_ba_options* o, ccm_ba_result* r) {
     double currentChi;
     if (it == 0) {
       const double maxdiag = step_max_diag(h);
+      if (!(maxdiag > 0.0)) {  // every edge is inactive (weight 0): nothing to optimise, the estimate is left alone
+        ret_iters = -1;
+        break;
+      }
       currentChi = h->h_scal[8];
       lambda = o->lambda_init > 0 ? o->lambda_init : 1e-5 * maxdiag;
       ni = 2; nBad = 0;

@@ -107,16 +107,15 @@ __device__ __forceinline__ int corner_score(const uint8_t* t, int stride, int x,
 // dynamic smem: tile (u8, tw*th) | score (short, tw*th) | flag (u8, tw*th)
 __global__ void __launch_bounds__(256) k_fast_cells(const uint8_t* __restrict__ pyr, const Cell* __restrict__ cells,
                                                     int ini_th, int min_th, int tile_cap, int max_per_cell,
-                                                    int* __restrict__ cell_count, ushort4* __restrict__ cell_out,
-                                                    int dbg_cell, int* __restrict__ dbg) {
+                                                    int* __restrict__ cell_count, ushort4* __restrict__ cell_out) {
   extern __shared__ unsigned char smem[];
   const Cell c = cells[blockIdx.x];
   const int tw = c.x1 - c.x0, th = c.y1 - c.y0;
   uint8_t* tile = smem;
   short* score = reinterpret_cast<short*>(smem + ((tile_cap + 15) & ~15));
   uint8_t* flag = smem + ((tile_cap + 15) & ~15) + 2 * tile_cap;
-  __shared__ int n_ini, n_out;
-  if (threadIdx.x == 0) { n_ini = 0; n_out = 0; }
+  __shared__ int n_ini;
+  if (threadIdx.x == 0) n_ini = 0;
   const int n = tw * th;
   if (tw < 7 || th < 7) {
     if (threadIdx.x == 0) cell_count[blockIdx.x] = 0;
@@ -175,11 +174,6 @@ __global__ void __launch_bounds__(256) k_fast_cells(const uint8_t* __restrict__ 
       base += __popc(m);
     }
     if (threadIdx.x == 0) cell_count[blockIdx.x] = min(base, max_per_cell);
-  }
-  if (dbg && (int)blockIdx.x == dbg_cell) {
-    __syncthreads();
-    for (int i = threadIdx.x; i < n; i += blockDim.x) { dbg[i] = tile[i]; dbg[n + i] = score[i]; dbg[2 * n + i] = flag[i]; }
-    if (threadIdx.x == 0) { dbg[3 * n] = n_ini; dbg[3 * n + 1] = tw; dbg[3 * n + 2] = th; }
   }
 }
 
@@ -495,8 +489,6 @@ struct ccm_orb_handle {
   DevBuf<ushort4> cell_out;
   DevBuf<Cand> cand;
   DevBuf<KpIn> kp_in;
-  DevBuf<int> dbg;
-  int dbg_cell = -1;
   uint8_t* h_img = nullptr;   // pinned staging
   Cand* h_cand = nullptr;     // pinned
   int* h_total = nullptr;     // pinned
@@ -661,7 +653,7 @@ void orb_extract(ccm_orb_handle* h, const uint8_t* img, int stride, ccm_keypoint
   }
   const size_t smem = ((size_t)h->tile_cap + 15) / 16 * 16 + 3 * (size_t)h->tile_cap + 16;
   k_fast_cells<<<h->ncells, 256, smem, s>>>(h->pyr.p, h->cells.p, h->cfg.ini_th_fast, h->cfg.min_th_fast, h->tile_cap,
-                                            h->max_per_cell, h->cell_count.p, h->cell_out.p, h->dbg_cell, h->dbg.p);
+                                            h->max_per_cell, h->cell_count.p, h->cell_out.p);
   CCM_LAUNCHED();
   k_scan_cells<<<1, 1024, 0, s>>>(h->cell_count.p, h->ncells, h->cell_off.p);
   CCM_LAUNCHED();
@@ -780,28 +772,6 @@ extern "C" int ccm_orb_get_level(ccm_orb_handle* h, int32_t level, uint8_t* out,
       CCM_CUDA(cudaMemcpyAsync(out, h->pyr.p + h->loff[level], (size_t)h->lw[level] * h->lh[level], cudaMemcpyDeviceToHost, h->stream));
       CCM_CUDA(cudaStreamSynchronize(h->stream));
     }
-  });
-}
-
-extern "C" int ccm_orb_debug_dump(ccm_orb_handle* h, int32_t cell, int32_t* out, int32_t n_ints) {
-  return guarded([&] {
-    if (!h->dbg.p) { h->dbg.alloc_zero(16384, h->stream); CCM_CUDA(cudaStreamSynchronize(h->stream)); }
-    if (out) CCM_CUDA(cudaMemcpy(out, h->dbg.p, sizeof(int) * (size_t)std::min(n_ints, 16384), cudaMemcpyDeviceToHost));
-    h->dbg_cell = cell;
-  });
-}
-
-// debug: geometry + raw per-cell output of one FAST cell after the last extract call
-extern "C" int ccm_orb_debug_cell(ccm_orb_handle* h, int32_t cell, int32_t* geom8, uint16_t* entries4, int32_t* count) {
-  return guarded([&] {
-    CCM_REQUIRE(h && cell >= 0 && cell < h->ncells, "bad cell");
-    CCM_CUDA(cudaSetDevice(h->device));
-    Cell c;
-    CCM_CUDA(cudaMemcpy(&c, h->cells.p + cell, sizeof(Cell), cudaMemcpyDeviceToHost));
-    geom8[0] = c.level; geom8[1] = c.img_off; geom8[2] = c.img_w; geom8[3] = c.x0; geom8[4] = c.y0; geom8[5] = c.x1; geom8[6] = c.y1; geom8[7] = c.out_off;
-    CCM_CUDA(cudaMemcpy(count, h->cell_count.p + cell, sizeof(int), cudaMemcpyDeviceToHost));
-    CCM_CUDA(cudaMemcpy(entries4, h->cell_out.p + c.out_off, sizeof(ushort4) * (size_t)std::min(*count, h->max_per_cell), cudaMemcpyDeviceToHost));
-    geom8[1] = h->tile_cap; geom8[2] = h->max_per_cell;
   });
 }
 

@@ -125,6 +125,41 @@ def test_stop_flag_zero_iterations_reset(oracle):
     h.close()
 
 
+def test_degenerate_graphs_behave_like_the_oracle(oracle):
+    """Empty and ragged inputs: no observations, every edge switched off, an unobserved landmark, a landmark seen once,
+    a free keyframe without observations (g2o leaves vertices without active edges alone)."""
+    p = synth.make_config("small")
+    # (1) no observations at all: "0 vertices to optimize" -> -1, estimate untouched
+    q = p.copy()
+    q.obs_kf, q.obs_mp, q.obs_uv, q.obs_w = q.obs_kf[:0], q.obs_mp[:0], q.obs_uv[:0], q.obs_w[:0]
+    ref = oracle.ba_solve(q, iterations=5, huber_delta=api.HUBER_GBA)
+    res = api.ba_solve(q, iterations=5, huber_delta=api.HUBER_GBA)
+    assert ref["iters_done"] == -1 and res["iters_done"] == -1
+    assert np.array_equal(res["poses"], p.poses) and np.array_equal(res["points"], p.points)
+    # (2) every edge at level 1 (flag bit 0): same
+    q = p.copy()
+    q.edge_flags = np.ones(p.E, np.uint8)
+    ref = oracle.ba_solve(q, iterations=5, huber_delta=api.HUBER_GBA)
+    res = api.ba_solve(q, iterations=5, huber_delta=api.HUBER_GBA)
+    assert ref["iters_done"] == -1 and res["iters_done"] == -1
+    assert np.array_equal(res["poses"], p.poses) and np.array_equal(res["points"], p.points)
+    # (3) ragged: an unobserved landmark, a landmark left with one observation, a free keyframe nobody observes from
+    q = p.copy()
+    q.points = np.vstack([q.points, [[0.5, -0.25, 3.0]]])
+    q.poses = np.vstack([q.poses, q.poses[-1:]])
+    q.intr = np.vstack([q.intr, q.intr[-1:]])
+    q.fixed = np.concatenate([q.fixed, np.zeros(1, np.uint8)])
+    first = np.flatnonzero(q.obs_mp == q.obs_mp[0])
+    keep = np.ones(q.E, bool)
+    keep[first[1:]] = False  # landmark obs_mp[0] keeps a single observation
+    q.obs_kf, q.obs_mp, q.obs_uv, q.obs_w = q.obs_kf[keep], q.obs_mp[keep], q.obs_uv[keep], q.obs_w[keep]
+    ref = oracle.ba_solve(q, iterations=6, huber_delta=api.HUBER_GBA)
+    res = api.ba_solve(q, iterations=6, huber_delta=api.HUBER_GBA)
+    assert res["iters_done"] == ref["iters_done"] and res["trials_total"] == ref["trials_total"]
+    _state_close(res, ref, 1e-4)
+    assert np.array_equal(res["points"][-1], q.points[-1]) and np.array_equal(res["poses"][-1], q.poses[-1])
+
+
 def test_cfg4_full_size_against_oracle_and_properties(oracle):
     """4-agent merged-map Global BA shape (the >=50x target shape) at full size."""
     p = synth.make_config("cfg4")
