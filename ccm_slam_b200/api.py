@@ -300,3 +300,62 @@ def hamming_matrix(A, B):
     D = np.empty((A.shape[0], B.shape[0]), np.uint16)
     _chk(lib().ccm_hamming_matrix(_p(A), A.shape[0], _p(B), B.shape[0], _p(D)))
     return D
+
+
+# ---- single-vertex optimisations ---------------------------------------------------------------------------------------
+class PoseOptProblemC(C.Structure):
+    _fields_ = [("n", C.c_int32), ("Tcw", C.c_void_p), ("Xw", C.c_void_p), ("uv", C.c_void_p), ("inv_sigma2", C.c_void_p),
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float)]
+
+
+class PoseOptResultC(C.Structure):
+    _fields_ = [("Tcw", C.c_double * 7), ("n_inliers", C.c_int32), ("outlier", C.c_void_p)]
+
+
+class Sim3OptProblemC(C.Structure):
+    _fields_ = [("n", C.c_int32), ("S12", C.c_void_p), ("P1c", C.c_void_p), ("P2c", C.c_void_p), ("uv1", C.c_void_p),
+                ("uv2", C.c_void_p), ("inv_sigma2_1", C.c_void_p), ("inv_sigma2_2", C.c_void_p), ("K1", C.c_float * 4),
+                ("K2", C.c_float * 4), ("th2", C.c_float), ("fix_scale", C.c_int32)]
+
+
+class Sim3OptResultC(C.Structure):
+    _fields_ = [("S12", C.c_double * 8), ("n_inliers", C.c_int32), ("inlier", C.c_void_p)]
+
+
+def pose_optimize(problems):
+    """Optimizer::PoseOptimizationClient for a batch of frames.  problems: list of dict(Tcw0, Xw, uv, inv_sigma2, intr)
+    (ccm_slam_b200.synth.make_pose_opt layout).  Returns a list of (Tcw (7,), outlier (n,) u8, n_inliers)."""
+    B = len(problems)
+    probs = (PoseOptProblemC * max(B, 1))(); res = (PoseOptResultC * max(B, 1))()
+    keep = []
+    for b, d in enumerate(problems):
+        a = dict(T=np.ascontiguousarray(d["Tcw0"], np.float64), X=np.ascontiguousarray(d["Xw"], np.float32).reshape(-1, 3),
+                 uv=np.ascontiguousarray(d["uv"], np.float32).reshape(-1, 2), w=np.ascontiguousarray(d["inv_sigma2"], np.float32))
+        n = a["X"].shape[0]
+        a["out"] = np.zeros(max(n, 1), np.uint8)
+        keep.append(a)
+        probs[b] = PoseOptProblemC(n, _p(a["T"]), _p(a["X"]), _p(a["uv"]), _p(a["w"]), *[float(v) for v in d["intr"]])
+        res[b].outlier = _p(a["out"])
+    _chk(lib().ccm_pose_optimize(probs, B, res))
+    return [(np.array(res[b].Tcw[:]), keep[b]["out"][:keep[b]["X"].shape[0]], int(res[b].n_inliers)) for b in range(B)]
+
+
+def sim3_optimize(problems):
+    """Optimizer::OptimizeSim3 for a batch of keyframe pairs.  problems: list of dict(S12_0, P1c, P2c, uv1, uv2, w1, w2, K1, K2,
+    th2, fix_scale) (synth.make_sim3_opt layout).  Returns a list of (S12 (8,), inlier (n,) u8, n_inliers)."""
+    B = len(problems)
+    probs = (Sim3OptProblemC * max(B, 1))(); res = (Sim3OptResultC * max(B, 1))()
+    keep = []
+    f32 = lambda x, c: np.ascontiguousarray(x, np.float32).reshape(-1, c) if c else np.ascontiguousarray(x, np.float32)
+    for b, d in enumerate(problems):
+        a = dict(S=np.ascontiguousarray(d["S12_0"], np.float64), P1=f32(d["P1c"], 3), P2=f32(d["P2c"], 3), u1=f32(d["uv1"], 2),
+                 u2=f32(d["uv2"], 2), w1=f32(d["w1"], 0), w2=f32(d["w2"], 0))
+        n = a["P1"].shape[0]
+        a["inl"] = np.zeros(max(n, 1), np.uint8)
+        keep.append(a)
+        probs[b] = Sim3OptProblemC(n, _p(a["S"]), _p(a["P1"]), _p(a["P2"]), _p(a["u1"]), _p(a["u2"]), _p(a["w1"]), _p(a["w2"]),
+                                   (C.c_float * 4)(*[float(v) for v in d["K1"]]), (C.c_float * 4)(*[float(v) for v in d["K2"]]),
+                                   float(d["th2"]), int(bool(d["fix_scale"])))
+        res[b].inlier = _p(a["inl"])
+    _chk(lib().ccm_sim3_optimize(probs, B, res))
+    return [(np.array(res[b].S12[:]), keep[b]["inl"][:keep[b]["P1"].shape[0]], int(res[b].n_inliers)) for b in range(B)]

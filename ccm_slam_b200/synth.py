@@ -269,3 +269,49 @@ def make_pgo(K=200, n_loop=6, n_covis=3, seed=5, drift=(0.002, 0.01, 0.002), fix
     fixed = np.zeros(K, np.uint8); fixed[0] = 1
     return PGOProblem(sim3=est, fixed=fixed, edge_i=np.array(ei, np.int32), edge_j=np.array(ej, np.int32),
                       meas=np.ascontiguousarray(np.array(meas)), fix_scale=fix_scale, gt=gt)
+
+
+# ---- single-vertex problems: PoseOptimizationClient (one frame against its map points), OptimizeSim3 (two keyframes) ----
+def make_pose_opt(n=300, seed=11, outlier_frac=0.15, noise_px=0.8, pose_noise=(0.03, 0.08)):
+    """One frame: n map points in front of a camera, pixel noise scaled by the octave, a share of gross outliers, and a
+    perturbed initial pose.  Returns dict(Tcw0, Xw, uv, inv_sigma2, intr, Tcw_gt)."""
+    rng = np.random.default_rng(seed)
+    fx, fy, cx, cy = [np.float32(v) for v in EUROC_INTR]
+    q_gt = _rotvec_to_quat(rng.standard_normal(3) * 0.3); t_gt = rng.standard_normal(3) * 0.5
+    Xc = np.stack([rng.uniform(-2.0, 2.0, n), rng.uniform(-1.2, 1.2, n), rng.uniform(2.0, 8.0, n)], 1)
+    qc = np.array([-q_gt[0], -q_gt[1], -q_gt[2], q_gt[3]])
+    Xw = np.stack([_quat_rot(qc, x - t_gt) for x in Xc]).astype(np.float32)
+    octave = rng.integers(0, 8, n)
+    sigma = (1.2 ** octave)
+    Xcf = np.stack([_quat_rot(q_gt, x.astype(np.float64)) + t_gt for x in Xw])
+    uv = np.stack([fx * Xcf[:, 0] / Xcf[:, 2] + cx, fy * Xcf[:, 1] / Xcf[:, 2] + cy], 1) + rng.standard_normal((n, 2)) * noise_px * sigma[:, None]
+    bad = rng.random(n) < outlier_frac
+    uv[bad] += rng.uniform(-60, 60, (int(bad.sum()), 2))
+    q0 = _quat_mul(_rotvec_to_quat(rng.standard_normal(3) * pose_noise[0]), q_gt)
+    t0 = t_gt + rng.standard_normal(3) * pose_noise[1]
+    return dict(Tcw0=np.concatenate([q0 / np.linalg.norm(q0), t0]), Xw=Xw, uv=uv.astype(np.float32),
+                inv_sigma2=(1.0 / (sigma * sigma)).astype(np.float32), intr=(fx, fy, cx, cy), Tcw_gt=np.concatenate([q_gt, t_gt]))
+
+
+def make_sim3_opt(n=120, seed=12, outlier_frac=0.2, noise_px=0.7, scale=1.15, fix_scale=False):
+    """Two keyframes seeing the same n points, each with its own copy of the point in its own camera frame (map 2 is scaled
+    against map 1).  Returns dict(S12_0, P1c, P2c, uv1, uv2, w1, w2, K1, K2, th2, fix_scale, S12_gt)."""
+    rng = np.random.default_rng(seed)
+    K = tuple(np.float32(v) for v in EUROC_INTR)
+    s = 1.0 if fix_scale else scale
+    q12 = _rotvec_to_quat(rng.standard_normal(3) * 0.2); t12 = rng.standard_normal(3) * 0.4
+    P2c = np.stack([rng.uniform(-1.5, 1.5, n), rng.uniform(-1.0, 1.0, n), rng.uniform(2.5, 7.0, n)], 1)
+    P1c = np.stack([s * _quat_rot(q12, x) + t12 for x in P2c])
+    octave1, octave2 = rng.integers(0, 8, n), rng.integers(0, 8, n)
+    s1, s2 = 1.2 ** octave1, 1.2 ** octave2
+    proj = lambda P: np.stack([K[0] * P[:, 0] / P[:, 2] + K[2], K[1] * P[:, 1] / P[:, 2] + K[3]], 1)
+    uv1 = proj(P1c) + rng.standard_normal((n, 2)) * noise_px * s1[:, None]
+    uv2 = proj(P2c) + rng.standard_normal((n, 2)) * noise_px * s2[:, None]
+    bad = rng.random(n) < outlier_frac
+    uv1[bad] += rng.uniform(-40, 40, (int(bad.sum()), 2))
+    P1c_n = P1c + rng.standard_normal((n, 3)) * 0.01; P2c_n = P2c + rng.standard_normal((n, 3)) * 0.01
+    q0 = _quat_mul(_rotvec_to_quat(rng.standard_normal(3) * 0.02), q12)
+    S0 = np.concatenate([q0 / np.linalg.norm(q0), t12 + rng.standard_normal(3) * 0.05, [s * (1.0 if fix_scale else 1.03)]])
+    return dict(S12_0=S0, P1c=P1c_n.astype(np.float32), P2c=P2c_n.astype(np.float32), uv1=uv1.astype(np.float32), uv2=uv2.astype(np.float32),
+                w1=(1.0 / (s1 * s1)).astype(np.float32), w2=(1.0 / (s2 * s2)).astype(np.float32), K1=K, K2=K, th2=np.float32(10.0),
+                fix_scale=fix_scale, S12_gt=np.concatenate([q12, t12, [s]]))

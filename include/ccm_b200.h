@@ -203,6 +203,54 @@ typedef struct ccm_pgo_result {
 
 int ccm_pgo_solve(const ccm_pgo_problem* p, const ccm_pgo_options* o, ccm_pgo_result* r);
 
+/* ---- single-vertex optimisations ------------------------------------------------------------------------
+ * ccm_pose_optimize replaces the g2o part of Optimizer::PoseOptimizationClient (cslam/src/Optimizer.cpp:215-347): one SE3
+ * vertex, n unary EdgeSE3ProjectXYZOnlyPose, Huber sqrt(5.991), 4 x {estimate := Tcw, optimize(10), chi2 > 5.991 -> outlier},
+ * robust kernel dropped after the third round.  The shim fills the arrays from Frame (mvpMapPoints[i] != NULL only), then
+ * writes `outlier` back into Frame.mvbOutlier, `Tcw` into Frame.SetPose and returns n_inliers
+ * (= nInitialCorrespondences - nBad; 0 and Tcw unchanged when n < 3).
+ * `batch` independent problems (frames of several agents) run in one launch, one CTA each. */
+typedef struct ccm_pose_opt_problem {
+  int32_t n;                 /* correspondences */
+  const double* Tcw;         /* 7: qx qy qz qw tx ty tz = ccm_pose_from_Tcw_f32(Frame.mTcw) */
+  const float* Xw;           /* n*3: MapPoint::GetWorldPos */
+  const float* uv;           /* n*2: Frame.mvKeysUn[i].pt */
+  const float* inv_sigma2;   /* n: Frame.mvInvLevelSigma2[octave] */
+  float fx, fy, cx, cy;
+} ccm_pose_opt_problem;
+typedef struct ccm_pose_opt_result {
+  double Tcw[7];
+  int32_t n_inliers;
+  uint8_t* outlier;          /* n, caller-allocated */
+} ccm_pose_opt_result;
+int ccm_pose_optimize(const ccm_pose_opt_problem* probs, int32_t batch, ccm_pose_opt_result* res);
+
+/* ccm_sim3_optimize replaces the g2o part of Optimizer::OptimizeSim3 (cslam/src/Optimizer.cpp:861-1056): one Sim3 vertex
+ * (g2oS12), per matched pair an EdgeSim3ProjectXYZ (x1 = K1 * S12 * X2c) and an EdgeInverseSim3ProjectXYZ
+ * (x2 = K2 * S12^-1 * X1c) against fixed points, numeric Jacobians, Huber sqrt(th2), optimize(5), pairs with chi2 > th2 removed,
+ * optimize(5 or 10).  The shim keeps the reference's pair filter (:917-931) and camera-frame points (:925,:932, f32), clears
+ * vpMatches1 where `inlier` is 0, and returns n_inliers (0 with S12 unchanged when fewer than 10 pairs survive the first pass).
+ * `batch`: the loop / merge candidates of one place-recognition query. */
+typedef struct ccm_sim3_opt_problem {
+  int32_t n;                 /* pairs */
+  const double* S12;         /* 8: qx qy qz qw tx ty tz s */
+  const float* P1c;          /* n*3: R1w*P1w + t1w */
+  const float* P2c;          /* n*3: R2w*P2w + t2w */
+  const float* uv1;          /* n*2: pKF1->mvKeysUn[i].pt */
+  const float* uv2;          /* n*2: pKF2->mvKeysUn[i2].pt */
+  const float* inv_sigma2_1; /* n */
+  const float* inv_sigma2_2; /* n */
+  float K1[4], K2[4];        /* fx fy cx cy */
+  float th2;
+  int32_t fix_scale;
+} ccm_sim3_opt_problem;
+typedef struct ccm_sim3_opt_result {
+  double S12[8];
+  int32_t n_inliers;
+  uint8_t* inlier;           /* n, caller-allocated */
+} ccm_sim3_opt_result;
+int ccm_sim3_optimize(const ccm_sim3_opt_problem* probs, int32_t batch, ccm_sim3_opt_result* res);
+
 /* ---- ORB front end ------------------------------------------------------------------------------------
  * ccm_orb_* replace ORBextractor::operator() (cslam/src/ORBextractor.cpp:1216-1278) and its helpers
  * (ComputePyramid :1280-1304, ComputeKeyPointsOctTree :933-1024, IC_Angle :68-95, computeOrbDescriptor :100-316);

@@ -113,6 +113,34 @@ void orc_sim3_mul(const double a[8], const double b[8], double out[8]);/* G/type
 void orc_sim3_inv(const double a[8], double out[8]);                   /* G/types/sim3.h:233-236 */
 void orc_pgo_edge_error(const double meas[8], const double si[8], const double sj[8], double err[7]);
 
+/* ---- single-vertex optimisations (single_oracle.cpp) ---- */
+typedef struct {
+  int32_t n;                 /* correspondences = frame features with a map point */
+  const double* Tcw;         /* 7: qx qy qz qw tx ty tz, Converter::toSE3Quat(Frame.mTcw) */
+  const float* Xw;           /* n*3: MapPoint::GetWorldPos (f32) */
+  const float* uv;           /* n*2: mvKeysUn[i].pt */
+  const float* inv_sigma2;   /* n: mvInvLevelSigma2[octave] */
+  float fx, fy, cx, cy;
+} orc_pose_opt_problem;
+/* Optimizer::PoseOptimizationClient (S/Optimizer.cpp:215-347); returns nInitialCorrespondences - nBad (0 when n < 3) */
+int orc_pose_optimize(const orc_pose_opt_problem* p, double* Tcw_out /*7*/, uint8_t* outlier /*n: Frame.mvbOutlier*/);
+
+typedef struct {
+  int32_t n;                 /* matched pairs that passed the reference's validity checks */
+  const double* S12;         /* 8: qx qy qz qw tx ty tz s */
+  const float* P1c;          /* n*3: R1w*P1w + t1w (camera-1 frame, f32 as the reference computes it) */
+  const float* P2c;          /* n*3: R2w*P2w + t2w */
+  const float* uv1;          /* n*2: pKF1->mvKeysUn[i].pt */
+  const float* uv2;          /* n*2: pKF2->mvKeysUn[i2].pt */
+  const float* inv_sigma2_1; /* n */
+  const float* inv_sigma2_2; /* n */
+  float K1[4], K2[4];        /* fx fy cx cy of the two keyframes */
+  float th2;
+  int32_t fix_scale;
+} orc_sim3_opt_problem;
+/* Optimizer::OptimizeSim3 (S/Optimizer.cpp:861-1056); returns nIn (0 and S12 untouched when fewer than 10 pairs survive) */
+int orc_sim3_optimize(const orc_sim3_opt_problem* p, double* S12_out /*8*/, uint8_t* inlier /*n: vpMatches1[i] kept*/);
+
 #ifdef __cplusplus
 }
 #endif

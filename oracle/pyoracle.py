@@ -335,3 +335,39 @@ def match_triangulation(v1, v2, F12, ex, ey, level_sigma2, scale_factors, check_
     pairs = np.empty((min(a.n, b.n) + 1, 2), np.int32)
     n = lib().orc_match_triangulation(C.byref(a), C.byref(b), _p(F), C.c_float(ex), C.c_float(ey), _p(ls), _p(sf), int(check_ori), _p(pairs))
     return pairs[:n].copy()
+
+
+# ---- single-vertex optimisations (PoseOptimizationClient, OptimizeSim3) ---------------------------------------------
+class _PoseOpt(C.Structure):
+    _fields_ = [("n", C.c_int32), ("Tcw", C.c_void_p), ("Xw", C.c_void_p), ("uv", C.c_void_p), ("inv_sigma2", C.c_void_p),
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float)]
+
+
+class _Sim3Opt(C.Structure):
+    _fields_ = [("n", C.c_int32), ("S12", C.c_void_p), ("P1c", C.c_void_p), ("P2c", C.c_void_p), ("uv1", C.c_void_p),
+                ("uv2", C.c_void_p), ("inv_sigma2_1", C.c_void_p), ("inv_sigma2_2", C.c_void_p), ("K1", C.c_float * 4),
+                ("K2", C.c_float * 4), ("th2", C.c_float), ("fix_scale", C.c_int32)]
+
+
+def pose_optimize(Tcw, Xw, uv, inv_sigma2, intr):
+    """Optimizer::PoseOptimizationClient on flat arrays -> (Tcw (7,), outlier (n,) u8, n_inliers)."""
+    a = dict(Tcw=np.ascontiguousarray(Tcw, np.float64), Xw=np.ascontiguousarray(Xw, np.float32).reshape(-1, 3),
+             uv=np.ascontiguousarray(uv, np.float32).reshape(-1, 2), w=np.ascontiguousarray(inv_sigma2, np.float32))
+    n = a["Xw"].shape[0]
+    prob = _PoseOpt(n, _p(a["Tcw"]), _p(a["Xw"]), _p(a["uv"]), _p(a["w"]), *[float(v) for v in intr])
+    out = np.empty(7); outlier = np.zeros(max(n, 1), np.uint8)
+    nin = lib().orc_pose_optimize(C.byref(prob), _p(out), _p(outlier))
+    return out, outlier[:n], nin
+
+
+def sim3_optimize(S12, P1c, P2c, uv1, uv2, w1, w2, K1, K2, th2, fix_scale):
+    """Optimizer::OptimizeSim3 on flat arrays -> (S12 (8,), inlier (n,) u8, n_inliers)."""
+    f32 = lambda x, c: np.ascontiguousarray(x, np.float32).reshape(-1, c) if c else np.ascontiguousarray(x, np.float32)
+    a = dict(S=np.ascontiguousarray(S12, np.float64), P1=f32(P1c, 3), P2=f32(P2c, 3), u1=f32(uv1, 2), u2=f32(uv2, 2),
+             w1=f32(w1, 0), w2=f32(w2, 0))
+    n = a["P1"].shape[0]
+    prob = _Sim3Opt(n, _p(a["S"]), _p(a["P1"]), _p(a["P2"]), _p(a["u1"]), _p(a["u2"]), _p(a["w1"]), _p(a["w2"]),
+                    (C.c_float * 4)(*[float(v) for v in K1]), (C.c_float * 4)(*[float(v) for v in K2]), float(th2), int(bool(fix_scale)))
+    out = np.empty(8); inl = np.zeros(max(n, 1), np.uint8)
+    nin = lib().orc_sim3_optimize(C.byref(prob), _p(out), _p(inl))
+    return out, inl[:n], nin
