@@ -172,7 +172,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg5", choices=sorted(synth.CONFIGS))
-    ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
 
@@ -258,22 +258,25 @@ def main():
             api.host_register(a); pinned.append(a)
         except api.CCMError:
             pass
-    api.ba_solve(p, iterations=1, huber_delta=delta, want_edges=False)  # warm
+    api.ba_solve(p, iterations=LM_ITERS, huber_delta=delta, want_edges=False)  # warm: every code path of the timed call
     barrier()
-    e2e_t, e2e_it, setup_ms = 0.0, 0, 0.0
+    # wall-clock around the public call: a fresh box stalls the HOST now and then (lazily paged image, first-touch of driver
+    # pages) for hundreds of ms, which has nothing to do with the path -> every step is listed, the MEDIAN step is reported
+    e2e_steps_ms, e2e_it, setup_ms = [], 0, 0.0
     for _ in range(args.e2e_steps):
         barrier()
         t0 = time.perf_counter()
         r = api.ba_solve(p, iterations=LM_ITERS, huber_delta=delta, want_edges=False)
         dt = max_over_ranks(time.perf_counter() - t0)
-        e2e_t += dt
+        e2e_steps_ms.append(dt * 1e3)
         e2e_it += r["iters_done"]; setup_ms += r["t_setup_ms"]
         if rank == 0:
             print("[bench] e2e step: wall %.1f ms (setup %.1f, optimize %.1f, download %.1f, pcg its %d)" % (
                 dt * 1e3, r["t_setup_ms"], r["t_optimize_ms"], r["t_download_ms"], r["pcg_iters_total"]), file=sys.stderr)
     for a in pinned:
         api.host_unregister(a)
-    e2e_val = e2e_it / e2e_t
+    e2e_ms = statistics.median(e2e_steps_ms)
+    e2e_val = (e2e_it / args.e2e_steps) / (e2e_ms * 1e-3)
     launches_all = sum_over_ranks(float(launches))
 
     if rank != 0:
@@ -316,7 +319,8 @@ def main():
             "trials_per_s": tr_tot / (t_dev_ms * 1e-3), "wall_s_timed_region": wall,
             "clocks": clocks,
             "e2e": {"value": e2e_val, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": 1e3 * e2e_t / args.e2e_steps, "setup_ms_per_step": setup_ms / args.e2e_steps, "steps": args.e2e_steps,
+                    "ms_per_step": e2e_ms, "stat": "median of the per-step wall times", "step_ms": e2e_steps_ms,
+                    "setup_ms_per_step": setup_ms / args.e2e_steps, "steps": args.e2e_steps,
                     "call": "ccm_ba_solve (host buffers, pinned)"},
             "gpu_launches": int(launches_all),
             "roofline": roof, "kernels": kernels, "cpu_baseline": cpu}
