@@ -4,8 +4,7 @@
 //
 // NOT compiled in this repository's environment (needs the reference's OpenCV / Eigen / Boost / ROS headers).  It is the
 // binding a maintainer adds to cslam/CMakeLists.txt in place of src/Optimizer.cpp.
-// PoseOptimizationClient and OptimizeSim3 stay on the reference implementation (single vertex, out of scope: DESIGN.md §8);
-// compile them from the original file into a second TU or keep g2o linked for those two.
+// g2o is only needed for the g2o::Sim3 value type that appears in Optimizer.h.
 #include <cslam/Optimizer.h>
 
 #include <unordered_map>
@@ -283,5 +282,79 @@ static void solve_essential_graph(std::vector<double>& sim3 /*K*8 in/out*/, cons
 }
 // After the solve the reference's recovery code (:1280-1330, :1517-1565) runs unchanged on the returned Sim3s:
 // [sR t; 0 1] -> [R t/s; 0 1] per keyframe, and every map point is moved through its reference keyframe.
+
+// ---- PoseOptimizationClient (S/Optimizer.cpp:215-347) ---------------------------------------------------------------------
+int Optimizer::PoseOptimizationClient(Frame& Frame) {
+  std::vector<float> Xw, uv, w;
+  std::vector<size_t> index;                                   // vnIndexEdgeMono
+  {
+    unique_lock<mutex> lock(MapPoint::mGlobalMutex);
+    for (int i = 0; i < Frame.N; i++) {
+      mpptr pMP = Frame.mvpMapPoints[i];
+      if (!pMP) continue;
+      Frame.mvbOutlier[i] = false;
+      const cv::KeyPoint& kpUn = Frame.mvKeysUn[i];
+      cv::Mat X = pMP->GetWorldPos();
+      for (int k = 0; k < 3; k++) Xw.push_back(X.at<float>(k));
+      uv.push_back(kpUn.pt.x); uv.push_back(kpUn.pt.y);
+      w.push_back(Frame.mvInvLevelSigma2[kpUn.octave]);
+      index.push_back(i);
+    }
+  }
+  const int n = (int)index.size();
+  if (n < 3) return 0;
+  double Tcw[7];
+  ccm_pose_from_Tcw_f32(Frame.mTcw.ptr<float>(0), 1, Tcw);   // Converter::toSE3Quat(Frame.mTcw)
+  ccm_pose_opt_problem prob = {n, Tcw, Xw.data(), uv.data(), w.data(), Frame.fx, Frame.fy, Frame.cx, Frame.cy};
+  std::vector<uint8_t> outlier(n);
+  ccm_pose_opt_result res = {};
+  res.outlier = outlier.data();
+  check(ccm_pose_optimize(&prob, 1, &res));                    // 4 x { setEstimate, optimize(10), classify } in one launch
+  for (int e = 0; e < n; e++) Frame.mvbOutlier[index[e]] = outlier[e] != 0;
+  Frame.SetPose(pose_to_cv(res.Tcw));
+  return res.n_inliers;                                        // nInitialCorrespondences - nBad
+}
+
+// ---- OptimizeSim3 (S/Optimizer.cpp:861-1056) --------------------------------------------------------------------------------
+int Optimizer::OptimizeSim3(kfptr pKF1, kfptr pKF2, std::vector<mpptr>& vpMatches1, g2o::Sim3& g2oS12, const float th2, bool bFixScale) {
+  const cv::Mat R1w = pKF1->GetRotation(), t1w = pKF1->GetTranslation(), R2w = pKF2->GetRotation(), t2w = pKF2->GetTranslation();
+  const vector<mpptr> vpMapPoints1 = pKF1->GetMapPointMatches();
+  std::vector<float> P1c, P2c, uv1, uv2, w1, w2;
+  std::vector<size_t> index;                                   // vnIndexEdge
+  for (size_t i = 0; i < vpMatches1.size(); i++) {
+    if (!vpMatches1[i]) continue;
+    mpptr pMP1 = vpMapPoints1[i], pMP2 = vpMatches1[i];
+    if (!pMP1 || !pMP2) continue;
+    const int i2 = pMP2->GetIndexInKeyFrame(pKF2);
+    if (pMP1->isBad() || pMP2->isBad() || i2 < 0) continue;    // the reference's pair filter (:917-931)
+    cv::Mat X1 = R1w * pMP1->GetWorldPos() + t1w, X2 = R2w * pMP2->GetWorldPos() + t2w;   // f32, as the reference
+    for (int k = 0; k < 3; k++) { P1c.push_back(X1.at<float>(k)); P2c.push_back(X2.at<float>(k)); }
+    const cv::KeyPoint &kp1 = pKF1->mvKeysUn[i], &kp2 = pKF2->mvKeysUn[i2];
+    uv1.push_back(kp1.pt.x); uv1.push_back(kp1.pt.y); uv2.push_back(kp2.pt.x); uv2.push_back(kp2.pt.y);
+    w1.push_back(pKF1->mvInvLevelSigma2[kp1.octave]); w2.push_back(pKF2->mvInvLevelSigma2[kp2.octave]);
+    index.push_back(i);
+  }
+  const Eigen::Quaterniond q = g2oS12.rotation();
+  const Eigen::Vector3d t = g2oS12.translation();
+  double S12[8] = {q.x(), q.y(), q.z(), q.w(), t[0], t[1], t[2], g2oS12.scale()};
+  ccm_sim3_opt_problem prob = {};
+  prob.n = (int32_t)index.size(); prob.S12 = S12;
+  prob.P1c = P1c.data(); prob.P2c = P2c.data(); prob.uv1 = uv1.data(); prob.uv2 = uv2.data();
+  prob.inv_sigma2_1 = w1.data(); prob.inv_sigma2_2 = w2.data();
+  const cv::Mat &K1 = pKF1->mK, &K2 = pKF2->mK;
+  prob.K1[0] = K1.at<float>(0, 0); prob.K1[1] = K1.at<float>(1, 1); prob.K1[2] = K1.at<float>(0, 2); prob.K1[3] = K1.at<float>(1, 2);
+  prob.K2[0] = K2.at<float>(0, 0); prob.K2[1] = K2.at<float>(1, 1); prob.K2[2] = K2.at<float>(0, 2); prob.K2[3] = K2.at<float>(1, 2);
+  prob.th2 = th2; prob.fix_scale = bFixScale ? 1 : 0;
+  std::vector<uint8_t> inlier(index.size() + 1);
+  ccm_sim3_opt_result res = {};
+  res.inlier = inlier.data();
+  check(ccm_sim3_optimize(&prob, 1, &res));
+  for (size_t e = 0; e < index.size(); e++)
+    if (!inlier[e]) vpMatches1[index[e]] = static_cast<mpptr>(NULL);
+  if (res.n_inliers > 0)                                        // the reference returns before writing g2oS12 when < 10 pairs survive
+    g2oS12 = g2o::Sim3(Eigen::Quaterniond(res.S12[3], res.S12[0], res.S12[1], res.S12[2]),
+                       Eigen::Vector3d(res.S12[4], res.S12[5], res.S12[6]), res.S12[7]);
+  return res.n_inliers;
+}
 
 }  // namespace cslam
