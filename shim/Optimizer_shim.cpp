@@ -351,7 +351,7 @@ int Optimizer::OptimizeSim3(kfptr pKF1, kfptr pKF2, std::vector<mpptr>& vpMatche
   check(ccm_sim3_optimize(&prob, 1, &res));
   for (size_t e = 0; e < index.size(); e++)
     if (!inlier[e]) vpMatches1[index[e]] = static_cast<mpptr>(NULL);
-  if (res.n_inliers > 0)                                        // the reference returns before writing g2oS12 when < 10 pairs survive
+  if (memcmp(res.S12, S12, sizeof S12) != 0)                    // untouched when < 10 pairs survive the first pass (the reference returns before writing g2oS12)
     g2oS12 = g2o::Sim3(Eigen::Quaterniond(res.S12[3], res.S12[0], res.S12[1], res.S12[2]),
                        Eigen::Vector3d(res.S12[4], res.S12[5], res.S12[6]), res.S12[7]);
   return res.n_inliers;
