@@ -596,6 +596,44 @@ __device__ __forceinline__ int csr_pos(const unsigned* __restrict__ bitmap, cons
   return s_rowptr[a] + word_prefix[wi] + __popc(bitmap[wi] & ((1u << (b & 31)) - 1u));
 }
 
+// CSR position of the diagonal block of every row and the number of upper blocks (diagonal included) of the row
+__global__ void __launch_bounds__(TPB) k_diag_pos(const unsigned* __restrict__ bitmap, const int* __restrict__ word_prefix,
+                                                 const int* __restrict__ s_rowptr, int Kf, int words, int* __restrict__ s_diag,
+                                                 int* __restrict__ upper_count) {
+  const int a = blockIdx.x * TPB + threadIdx.x;
+  if (a >= Kf) return;
+  const int q = csr_pos(bitmap, word_prefix, s_rowptr, words, a, a);
+  s_diag[a] = q;
+  upper_count[a] = s_rowptr[a + 1] - q;
+}
+
+// Upper-block numbering (row-major over the entries with column >= row: the columns of a row are sorted, so its upper part is
+// [s_diag[a], s_rowptr[a+1]) and numbers consecutively from u_rowstart[a]), the (row, column) of every upper block, and for every
+// position of the full pattern the upper block that holds it (the transposed one for the lower triangle).
+__global__ void __launch_bounds__(TPB) k_upper_index(const int* __restrict__ s_row, const int* __restrict__ s_col, long long nnzb,
+                                                    const unsigned* __restrict__ bitmap, const int* __restrict__ word_prefix,
+                                                    const int* __restrict__ s_rowptr, int words, const int* __restrict__ s_diag,
+                                                    const int* __restrict__ u_rowstart, int* __restrict__ csr_u,
+                                                    int* __restrict__ u_row, int* __restrict__ u_col, int* __restrict__ err) {
+  const long long q = (long long)blockIdx.x * TPB + threadIdx.x;
+  if (q >= nnzb) return;
+  const int a = s_row[q], b = s_col[q];
+  if (b >= a) {
+    const int u = u_rowstart[a] + (int)(q - s_diag[a]);
+    csr_u[q] = u; u_row[u] = a; u_col[u] = b;
+  } else {
+    if (!((bitmap[(size_t)b * words + (a >> 5)] >> (a & 31)) & 1u)) { atomicOr(err, 1); return; }  // pattern must be symmetric
+    const int qb = csr_pos(bitmap, word_prefix, s_rowptr, words, b, a);
+    csr_u[q] = u_rowstart[b] + (qb - s_diag[b]);
+  }
+}
+
+// out[i] = in[i] - off  (local landmark ids / local observation offsets of a shard)
+__global__ void __launch_bounds__(TPB) k_shift(const int* __restrict__ in, long long n, int off, int* __restrict__ out) {
+  const long long i = (long long)blockIdx.x * TPB + threadIdx.x;
+  if (i < n) out[i] = in[i] - off;
+}
+
 // count (fill == 0) or fill (fill == 1) the product lists of the upper blocks; one thread per local observation
 __global__ void __launch_bounds__(TPB) k_products(const int* __restrict__ o_kf, const int* __restrict__ o_lm,
                                                   const int* __restrict__ lm_ptr, const int* __restrict__ pose_slot,
@@ -624,7 +662,7 @@ __global__ void __launch_bounds__(TPB) k_check_obs(const int* __restrict__ kf, c
   int bad = 0, unsorted = 0;
   for (long long e = (long long)blockIdx.x * TPB + threadIdx.x; e < E; e += (long long)gridDim.x * TPB) {
     const int k = kf[e], m = mp[e];
-    if (k < 0 || k >= K || m < 0 || m >= P || !(w[e] >= 0.0f)) bad = 1;
+    if (k < 0 || k >= K || m < 0 || m >= P || (w != nullptr && !(w[e] >= 0.0f))) bad = 1;
     if (e > 0 && mp[e - 1] > m) unsorted = 1;
   }
   if (bad) atomicOr(flags, 1);

@@ -311,6 +311,16 @@ void build(ccm_ba_handle* h, const ccm_ba_problem* p) {
   h->K = p->K; h->P = p->P; h->E = p->E;
   h->rank = comm().rank; h->nranks = comm().nranks;
   const int K = p->K, P = p->P, E = p->E;
+  // CCM_SETUP_PROF=1: wall time of the set-up phases on stderr (each lap synchronises the stream: diagnostics only)
+  const bool sprof = env_int("CCM_SETUP_PROF", 0) != 0;
+  double t_lap = now_ms();
+  auto lap = [&](const char* what) {
+    if (!sprof) return;
+    cudaStreamSynchronize(s);
+    const double t = now_ms();
+    fprintf(stderr, "[ccm_ba_create r%d] %-28s %8.2f ms\n", h->rank, what, t - t_lap);
+    t_lap = t;
+  };
 
   // free poses
   h->h_pose_slot.assign(K, -1);
@@ -328,20 +338,24 @@ void build(ccm_ba_handle* h, const ccm_ba_problem* p) {
   // Fast path (single rank, already grouped): the caller's arrays go to the device as they are, validation and the
   // landmark offsets are kernels - no host pass over the observations.  Otherwise: host counting sort + shard cut.
   std::vector<int> g_lm_ptr, g_kf, g_lm;
-  bool fast = (h->nranks == 1 && E > 0);
+  DevBuf<int> g_dkf, g_dlm, g_dptr;  // multi-rank fast path: the global (kf, landmark) lists and landmark offsets on the device
+  const bool multi = h->nranks > 1;
+  bool fast = E > 0;
   if (fast) {
-    h->o_kf.upload(p->obs_kf, E, s); h->o_lm.upload(p->obs_mp, E, s);
-    h->o_uv.upload(reinterpret_cast<const float2*>(p->obs_uv), E, s); h->o_w_raw.upload(p->obs_w, E, s);
+    DevBuf<int>& dk = multi ? g_dkf : h->o_kf;
+    DevBuf<int>& dl = multi ? g_dlm : h->o_lm;
+    dk.upload(p->obs_kf, E, s); dl.upload(p->obs_mp, E, s);
+    if (!multi) { h->o_uv.upload(reinterpret_cast<const float2*>(p->obs_uv), E, s); h->o_w_raw.upload(p->obs_w, E, s); }
     DevBuf<int> chk; chk.alloc_zero(2, s);
-    k_check_obs<<<grid_stride(E), TPB, 0, s>>>(h->o_kf.p, h->o_lm.p, h->o_w_raw.p, E, K, P, chk.p);
+    k_check_obs<<<grid_stride(E), TPB, 0, s>>>(dk.p, dl.p, multi ? nullptr : h->o_w_raw.p, E, K, P, chk.p);
     CCM_LAUNCHED();
     int hc[2];
     chk.download(hc, 2, s);
     CCM_CUDA(cudaStreamSynchronize(s));
     CCM_REQUIRE(hc[0] == 0, "ccm_ba_create: observation index out of range or negative information weight");
-    if (hc[1] != 0) fast = false;  // not grouped by landmark: take the sorting path
+    if (hc[1] != 0) { fast = false; g_dkf.release(); g_dlm.release(); }  // not grouped by landmark: take the sorting path
   }
-  if (fast) {
+  if (fast && !multi) {
     h->sorted_input = true;
     h->L0 = 0; h->L1 = P; h->Pl = P; h->E0 = 0; h->El = E;
     h->Ep = ((size_t)E + 31) / 32 * 32;
@@ -349,6 +363,41 @@ void build(ccm_ba_handle* h, const ccm_ba_problem* p) {
     k_lm_ptr<<<div_up((long long)P + 1, TPB), TPB, 0, s>>>(h->o_lm.p, E, P, h->lm_ptr.p);
     CCM_LAUNCHED();
     if (p->edge_flags) h->h_flags.assign(p->edge_flags, p->edge_flags + E); else h->h_flags.assign(E, 0);
+  } else if (fast) {
+    // grouped input on several ranks: cut the shard from the landmark offsets (4 B per landmark come back to the host), slice
+    // the lists on the device, upload only this rank's measurements
+    h->sorted_input = true;
+    g_dptr.alloc((size_t)P + 1);
+    k_lm_ptr<<<div_up((long long)P + 1, TPB), TPB, 0, s>>>(g_dlm.p, E, P, g_dptr.p);
+    CCM_LAUNCHED();
+    std::vector<int> hp((size_t)P + 1);
+    g_dptr.download(hp.data(), hp.size(), s);
+    CCM_CUDA(cudaStreamSynchronize(s));
+    shard_range(hp.data(), P, h->rank, h->nranks, &h->L0, &h->L1);
+    h->Pl = h->L1 - h->L0;
+    h->E0 = hp[h->L0];
+    h->El = hp[h->L1] - hp[h->L0];
+    h->Ep = ((size_t)h->El + 31) / 32 * 32;
+    const int El_ = h->El, Pl_ = h->Pl;
+    h->o_kf.alloc(std::max(El_, 1)); h->o_lm.alloc(std::max(El_, 1)); h->lm_ptr.alloc((size_t)Pl_ + 1);
+    h->o_uv.alloc(std::max(El_, 1)); h->o_w_raw.alloc(std::max(El_, 1));
+    if (El_) {
+      CCM_CUDA(cudaMemcpyAsync(h->o_kf.p, g_dkf.p + h->E0, sizeof(int) * (size_t)El_, cudaMemcpyDeviceToDevice, s));
+      k_shift<<<div_up(El_, TPB), TPB, 0, s>>>(g_dlm.p + h->E0, El_, h->L0, h->o_lm.p);
+      CCM_LAUNCHED();
+      CCM_CUDA(cudaMemcpyAsync(h->o_uv.p, reinterpret_cast<const float2*>(p->obs_uv) + h->E0, sizeof(float2) * (size_t)El_, cudaMemcpyHostToDevice, s));
+      CCM_CUDA(cudaMemcpyAsync(h->o_w_raw.p, p->obs_w + h->E0, sizeof(float) * (size_t)El_, cudaMemcpyHostToDevice, s));
+      DevBuf<int> chk; chk.alloc_zero(2, s);
+      k_check_obs<<<grid_stride(El_), TPB, 0, s>>>(h->o_kf.p, h->o_lm.p, h->o_w_raw.p, El_, K, std::max(Pl_, 1), chk.p);
+      CCM_LAUNCHED();
+      int hc[2];
+      chk.download(hc, 2, s);
+      CCM_CUDA(cudaStreamSynchronize(s));
+      CCM_REQUIRE(hc[0] == 0, "ccm_ba_create: negative information weight");
+    }
+    k_shift<<<div_up((long long)Pl_ + 1, TPB), TPB, 0, s>>>(g_dptr.p + h->L0, (long long)Pl_ + 1, (int)h->E0, h->lm_ptr.p);
+    CCM_LAUNCHED();
+    if (p->edge_flags) h->h_flags.assign(p->edge_flags + h->E0, p->edge_flags + h->E0 + El_); else h->h_flags.assign(El_, 0);
   } else {
     bool sorted = true;
     for (int e = 0; e < E; e++) {
@@ -396,6 +445,7 @@ void build(ccm_ba_handle* h, const ccm_ba_problem* p) {
     upload_vec(h->o_uv, l_uv, s); upload_vec(h->o_w_raw, l_w, s);
     CCM_CUDA(cudaStreamSynchronize(s));  // the staging vectors die at the end of this scope
   }
+  lap("observations + shard");
   const int Pl = h->Pl, El = h->El;
   h->pt0.alloc(std::max((size_t)Pl * 3, (size_t)1));
   if (Pl) CCM_CUDA(cudaMemcpyAsync(h->pt0.p, p->points + 3 * (size_t)h->L0, sizeof(double) * 3 * Pl, cudaMemcpyHostToDevice, s));
@@ -418,6 +468,7 @@ void build(ccm_ba_handle* h, const ccm_ba_problem* p) {
     DevBuf<int> d_gkf, d_glm, d_gptr;
     const int *pk, *pl, *pp_;
     if (h->nranks == 1) { pk = h->o_kf.p; pl = h->o_lm.p; pp_ = h->lm_ptr.p; }
+    else if (g_dptr.p) { pk = g_dkf.p; pl = g_dlm.p; pp_ = g_dptr.p; }
     else {
       d_gkf.upload(g_kf.data(), E, s); d_glm.upload(g_lm.data(), E, s); d_gptr.upload(g_lm_ptr.data(), (size_t)P + 1, s);
       pk = d_gkf.p; pl = d_glm.p; pp_ = d_gptr.p;
@@ -434,6 +485,7 @@ void build(ccm_ba_handle* h, const ccm_ba_problem* p) {
     }
     CCM_CUDA(cudaStreamSynchronize(s));  // temporaries die here
   }
+  lap("points, flags, bitmap, prefix");
   std::vector<int> h_rowptr((size_t)Kf + 1, 0);
   if (Kf > 0) {
     std::vector<int> cnt(Kf);
@@ -452,35 +504,36 @@ void build(ccm_ba_handle* h, const ccm_ba_problem* p) {
                                                                   h->s_col.p, h->s_row.p);
     CCM_LAUNCHED();
   }
-  // upper-block numbering, mirror map, diagonal positions (host, O(nnzb log))
-  std::vector<int> h_col(nnzb), h_csr_u(nnzb), h_urow, h_ucol, h_udiag(std::max(Kf, 1), 0), h_sdiag(std::max(Kf, 1), 0);
-  if (nnzb) { h->s_col.download(h_col.data(), nnzb, s); CCM_CUDA(cudaStreamSynchronize(s)); }
-  for (int a = 0; a < Kf; a++)
-    for (int q = h_rowptr[a]; q < h_rowptr[a + 1]; q++) {
-      const int b = h_col[q];
-      if (b >= a) {
-        h_csr_u[q] = (int)h_urow.size();
-        if (b == a) { h_udiag[a] = (int)h_urow.size(); h_sdiag[a] = q; }
-        h_urow.push_back(a); h_ucol.push_back(b);
-      }
-    }
-  for (int a = 0; a < Kf; a++)
-    for (int q = h_rowptr[a]; q < h_rowptr[a + 1]; q++) {
-      const int b = h_col[q];
-      if (b < a) {
-        const int* bb = h_col.data() + h_rowptr[b];
-        const int* ee = h_col.data() + h_rowptr[b + 1];
-        const int* it = std::lower_bound(bb, ee, a);
-        CCM_REQUIRE(it != ee && *it == a, "internal: asymmetric covisibility pattern");
-        h_csr_u[q] = h_csr_u[it - h_col.data()];
-      }
-    }
-  h->nub = (int)h_urow.size();
+  // upper-block numbering, mirror map, diagonal positions: O(1) per pattern entry through the bitmap prefix, on the device
+  std::vector<int> h_udiag(std::max(Kf, 1), 0);
+  h->s_diag.alloc(std::max(Kf, 1)); h->u_diag.alloc(std::max(Kf, 1)); h->csr_u.alloc(std::max<long long>(nnzb, 1));
+  h->nub = 0;
+  if (Kf > 0) {
+    DevBuf<int> upper_count, u_rowstart, perr;
+    upper_count.alloc(Kf); perr.alloc_zero(1, s);
+    k_diag_pos<<<div_up(Kf, TPB), TPB, 0, s>>>(h->bitmap.p, h->word_prefix.p, h->s_rowptr.p, Kf, words, h->s_diag.p, upper_count.p);
+    CCM_LAUNCHED();
+    std::vector<int> cnt(Kf), h_ustart((size_t)Kf + 1, 0);
+    upper_count.download(cnt.data(), Kf, s);
+    CCM_CUDA(cudaStreamSynchronize(s));
+    for (int a2 = 0; a2 < Kf; a2++) { h_ustart[a2 + 1] = h_ustart[a2] + cnt[a2]; h_udiag[a2] = h_ustart[a2]; }
+    h->nub = h_ustart[Kf];
+    upload_vec(u_rowstart, h_ustart, s);
+    h->u_diag.upload(h_udiag.data(), Kf, s);
+    h->u_row.alloc(std::max(h->nub, 1)); h->u_col.alloc(std::max(h->nub, 1));
+    k_upper_index<<<div_up(nnzb, TPB), TPB, 0, s>>>(h->s_row.p, h->s_col.p, nnzb, h->bitmap.p, h->word_prefix.p, h->s_rowptr.p, words,
+                                                    h->s_diag.p, u_rowstart.p, h->csr_u.p, h->u_row.p, h->u_col.p, perr.p);
+    CCM_LAUNCHED();
+    int e1 = 0;
+    perr.download(&e1, 1, s);
+    CCM_CUDA(cudaStreamSynchronize(s));  // also keeps the host vectors alive until their uploads are done
+    CCM_REQUIRE(e1 == 0, "internal: asymmetric covisibility pattern");
+  } else {
+    h->u_row.alloc(1); h->u_col.alloc(1);
+  }
   const int nub = h->nub;
-  upload_vec(h->csr_u, h_csr_u, s);
-  upload_vec(h->u_row, h_urow, s); upload_vec(h->u_col, h_ucol, s);
-  upload_vec(h->u_diag, h_udiag, s); upload_vec(h->s_diag, h_sdiag, s);
 
+  lap("pattern, upper index");
   // ---- Schur product lists (local shard)
   DevBuf<unsigned> counters; counters.alloc_zero(std::max(nub, 1), s);
   std::vector<unsigned> h_pp((size_t)nub + 1, 0);
@@ -508,6 +561,7 @@ void build(ccm_ba_handle* h, const ccm_ba_problem* p) {
     CCM_LAUNCHED();
   }
 
+  lap("product lists");
   // packed per-pose observation stream for the pose pass
   {
     std::vector<unsigned> kp((size_t)Kf + 1, 0);
@@ -517,6 +571,7 @@ void build(ccm_ba_handle* h, const ccm_ba_problem* p) {
     pack_pose_obs(h);
   }
 
+  lap("pose observation stream");
   // ---- linear-system storage
   h->W.alloc(std::max(h->Ep * 18, (size_t)1)); h->Z.alloc(std::max((size_t)El * 18, (size_t)2));
   h->HllBl.alloc(std::max((size_t)Pl * 9, (size_t)1)); h->gvec.alloc(std::max((size_t)Pl * 3, (size_t)1));
@@ -562,6 +617,7 @@ void build(ccm_ba_handle* h, const ccm_ba_problem* p) {
   h->device_bytes = (int64_t)(h->W.bytes() + h->Z.bytes() + h->prod.bytes() + h->s_val.bytes() + h->Ubuf.bytes() +
                               h->bitmap.bytes() + h->word_prefix.bytes() + h->HllBl.bytes() + h->o_kf.bytes() * 2 +
                               h->o_uv.bytes() + h->o_w.bytes() * 2 + h->ptA.bytes() * 3);
+  lap("storage + initial state");
   h->t_setup_ms = now_ms() - T0;
 }
 
@@ -776,11 +832,16 @@ extern "C" int ccm_ba_optimize(ccm_ba_handle* h, const ccm_ba_options* o, ccm_ba
 }
 
 extern "C" int ccm_ba_solve(const ccm_ba_problem* p, const ccm_ba_options* o, ccm_ba_result* r) {
+  const bool sprof = env_int("CCM_SETUP_PROF", 0) != 0;
+  const double t0 = now_ms();
   ccm_ba_handle* h = nullptr;
   int rc = ccm_ba_create(p, &h);
   if (rc != CCM_OK) return rc;
+  const double t1 = now_ms();
   rc = ccm_ba_optimize(h, o, r);
+  const double t2 = now_ms();
   ccm_ba_destroy(h);
+  if (sprof) fprintf(stderr, "[ccm_ba_solve] create %.2f ms, optimize %.2f ms, destroy %.2f ms\n", t1 - t0, t2 - t1, now_ms() - t2);
   return rc;
 }
 

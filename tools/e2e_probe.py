@@ -11,7 +11,7 @@ arrs = [p.poses, p.intr, p.fixed, p.points, p.obs_kf, p.obs_mp, p.obs_uv, p.obs_
 for a in arrs:
     api.host_register(a)
 api.ba_solve(p, iterations=1, huber_delta=api.HUBER_GBA, want_edges=False)
-for k in range(3):
+for k in range(6):
     t0 = time.perf_counter()
     r = api.ba_solve(p, iterations=8, huber_delta=api.HUBER_GBA, want_edges=False)
     w = (time.perf_counter() - t0) * 1e3
