@@ -96,6 +96,9 @@ struct Comm {
 Comm& comm();
 void allreduce_f64(double* buf, size_t count, int op, cudaStream_t s);  // op: 0 sum, 2 max
 
+// match.cu: nA x nB Hamming distances of 32-byte descriptors (host in, pinned thread-local host out, one k_hamming launch)
+const uint16_t* hamming_matrix_host(const uint8_t* A, int nA, const uint8_t* B, int nB);
+
 // catch-all used by every extern "C" entry point
 template <typename F>
 int guarded(F&& f) {

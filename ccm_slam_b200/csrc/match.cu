@@ -139,6 +139,11 @@ void check_fv(const ccm_feature_vector* f, int n, const char* what) {
 
 }  // namespace
 
+// shared with proj_match.cu: the (thread-local, pinned) distance matrix of one call; valid until the next call on this thread
+namespace ccm {
+const uint16_t* hamming_matrix_host(const uint8_t* A, int nA, const uint8_t* B, int nB) { return distance_matrix(A, nA, B, nB); }
+}  // namespace ccm
+
 extern "C" int ccm_hamming_matrix(const uint8_t* A, int32_t nA, const uint8_t* B, int32_t nB, uint16_t* D) {
   return guarded([&] {
     CCM_REQUIRE(nA >= 0 && nB >= 0 && (nA == 0 || A) && (nB == 0 || B) && D, "ccm_hamming_matrix: bad argument");

@@ -2,6 +2,9 @@
 
   ORBextractor(nfeatures, scaleFactor, nlevels, iniThFAST, minThFAST)  ~ cslam::ORBextractor  (I/ORBextractor.h:103-138)
   ORBmatcher(nnratio, checkOri).SearchByBoW / SearchForTriangulation   ~ cslam::ORBmatcher    (I/ORBmatcher.h:97-145)
+      .SearchByProjection_* / Fuse / SearchBySim3                       ~ the projection-guided overloads (S/ORBmatcher.cpp:71-148,
+                                                                          308-446, 854-1348, 1350-1605), from GetFeaturesInArea on
+  ORBVocabulary(rows).transform(descriptors, levelsup)                 ~ DBoW2 TemplatedVocabulary::transform (D/TemplatedVocabulary.h:1127-1192)
 
 Same names, argument meaning and outputs as the reference classes, on flat numpy arrays instead of cv::Mat / KeyFrame.
 """
@@ -114,3 +117,170 @@ class ORBmatcher:
         _chk(lib().ccm_match_triangulation(C.byref(a), C.byref(b), _p(F), C.c_float(ex), C.c_float(ey), _p(ls), _p(sf), len(ls),
                                            int(self.checkOri), _p(pairs), C.byref(n)))
         return pairs[:n.value].copy()
+
+    # ---- projection-guided overloads.  g = grid dict, q = query dict (ccm_slam_b200.synth_match) ----
+    def SearchByProjection_Track(self, g, q, query_has_obs, feat_blocked, D=None):
+        """SearchByProjection(Frame&, const vector<mpptr>&, th)  (S/ORBmatcher.cpp:71-148); nnratio from the constructor.
+        D: optional precomputed distance matrix (m x n u16) -> host selection only (ccm_select_*)."""
+        keep = []; G = grid_struct(g, keep); Q = queries_struct(q, keep)
+        ho = np.ascontiguousarray(query_has_obs, np.uint8); fb = np.ascontiguousarray(feat_blocked, np.uint8)
+        out = np.empty(G.n, np.int32); n = C.c_int32()
+        if D is None:
+            _chk(lib().ccm_search_by_projection_track(C.byref(G), C.byref(Q), _p(ho), _p(fb), C.c_float(self.nnratio), _p(out), C.byref(n)))
+        else:
+            D = _dist(D, Q.m, G.n)
+            _chk(lib().ccm_select_by_projection_track(C.byref(G), C.byref(Q), _p(D), _p(ho), _p(fb), C.c_float(self.nnratio), _p(out), C.byref(n)))
+        return out, n.value
+
+    def SearchByProjection_Frame(self, g, q, query_has_obs, feat_blocked, reloc=False, ORBdist=100, D=None):
+        """reloc=False: SearchByProjection(Frame&, const Frame& LastFrame, th) (:1350-1476);
+        reloc=True: SearchByProjection(Frame&, kfptr, sAlreadyFound, th, ORBdist) (:1478-1605).  checkOri from the constructor."""
+        keep = []; G = grid_struct(g, keep); Q = queries_struct(q, keep)
+        ho = np.ascontiguousarray(query_has_obs, np.uint8); fb = np.ascontiguousarray(feat_blocked, np.uint8)
+        out = np.empty(G.n, np.int32); n = C.c_int32()
+        if D is None:
+            _chk(lib().ccm_search_by_projection_frame(C.byref(G), C.byref(Q), _p(ho), _p(fb), int(reloc), int(ORBdist), int(self.checkOri),
+                                                      _p(out), C.byref(n)))
+        else:
+            D = _dist(D, Q.m, G.n)
+            _chk(lib().ccm_select_by_projection_frame(C.byref(G), C.byref(Q), _p(D), _p(ho), _p(fb), int(reloc), int(ORBdist),
+                                                      int(self.checkOri), _p(out), C.byref(n)))
+        return out, n.value
+
+    def SearchByProjection_Sim3(self, g, q, feat_matched, existing_idx, D=None):
+        """SearchByProjection(kfptr, Scw, vpPoints, vpMatched, th)  (:308-446) -> (best_idx per query, match_of_feat, nmatches)"""
+        keep = []; G = grid_struct(g, keep); Q = queries_struct(q, keep)
+        fm = np.ascontiguousarray(feat_matched, np.uint8); ex = np.ascontiguousarray(existing_idx, np.int32)
+        best = np.empty(Q.m, np.int32); out = np.empty(G.n, np.int32); n = C.c_int32()
+        if D is None:
+            _chk(lib().ccm_search_by_projection_sim3(C.byref(G), C.byref(Q), _p(fm), _p(ex), _p(best), _p(out), C.byref(n)))
+        else:
+            D = _dist(D, Q.m, G.n)
+            _chk(lib().ccm_select_by_projection_sim3(C.byref(G), C.byref(Q), _p(D), _p(fm), _p(ex), _p(best), _p(out), C.byref(n)))
+        return best, out, n.value
+
+    def Fuse(self, g, q, inv_level_sigma2=None, D=None):
+        """search half of Fuse(kfptr, vpMapPoints, th) (:854-993, pass mvInvLevelSigma2) / Fuse(kfptr, Scw, ...) (:995-1122, None)"""
+        keep = []; G = grid_struct(g, keep); Q = queries_struct(q, keep)
+        w = None if inv_level_sigma2 is None else np.ascontiguousarray(inv_level_sigma2, np.float32)
+        nl = 0 if w is None else len(w)
+        best = np.empty(Q.m, np.int32); n = C.c_int32()
+        if D is None:
+            _chk(lib().ccm_fuse_search(C.byref(G), C.byref(Q), _p(w), nl, _p(best), C.byref(n)))
+        else:
+            D = _dist(D, Q.m, G.n)
+            _chk(lib().ccm_fuse_select(C.byref(G), C.byref(Q), _p(D), _p(w), nl, _p(best), C.byref(n)))
+        return best, n.value
+
+    def SearchBySim3(self, g1, g2, q12, q21, D12=None, D21=None):
+        """SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th)  (:1124-1348) -> (match12, nFound)"""
+        keep = []; G1 = grid_struct(g1, keep); G2 = grid_struct(g2, keep); Q12 = queries_struct(q12, keep); Q21 = queries_struct(q21, keep)
+        out = np.empty(Q12.m, np.int32); n = C.c_int32()
+        if D12 is None:
+            _chk(lib().ccm_search_by_sim3(C.byref(G1), C.byref(G2), C.byref(Q12), C.byref(Q21), _p(out), C.byref(n)))
+        else:
+            D12 = _dist(D12, Q12.m, G2.n); D21 = _dist(D21, Q21.m, G1.n)
+            _chk(lib().ccm_select_by_sim3(C.byref(G1), C.byref(G2), C.byref(Q12), C.byref(Q21), _p(D12), _p(D21), _p(out), C.byref(n)))
+        return out, n.value
+
+
+class FeatureGridC(C.Structure):
+    _fields_ = [("n", C.c_int32), ("desc", C.c_void_p), ("kp_xy", C.c_void_p), ("octave", C.c_void_p), ("angle", C.c_void_p),
+                ("min_x", C.c_float), ("min_y", C.c_float), ("max_x", C.c_float), ("max_y", C.c_float),
+                ("grid_w_inv", C.c_float), ("grid_h_inv", C.c_float), ("grid_cols", C.c_int32), ("grid_rows", C.c_int32)]
+
+
+class ProjQueriesC(C.Structure):
+    _fields_ = [("m", C.c_int32), ("valid", C.c_void_p), ("uv", C.c_void_p), ("radius", C.c_void_p), ("level", C.c_void_p),
+                ("desc", C.c_void_p), ("angle", C.c_void_p)]
+
+
+def _dist(D, m, n):
+    D = np.ascontiguousarray(D, np.uint16)
+    assert D.shape == (m, n)
+    return D
+
+
+def grid_struct(g, keep):
+    """ccm_feature_grid from dict(desc, kp_xy, octave, angle, bounds=(mnMinX, mnMinY, mnMaxX, mnMaxY), cols, rows)"""
+    a = dict(desc=np.ascontiguousarray(g["desc"], np.uint8), xy=np.ascontiguousarray(g["kp_xy"], np.float32),
+             oc=np.ascontiguousarray(g["octave"], np.int32), an=np.ascontiguousarray(g["angle"], np.float32))
+    keep.append(a)
+    x0, y0, x1, y1 = [np.float32(v) for v in g["bounds"]]
+    wi = np.float32(g["cols"]) / np.float32(x1 - x0)   # mfGridElementWidthInv  (S/Frame.cpp:86)
+    hi = np.float32(g["rows"]) / np.float32(y1 - y0)   # mfGridElementHeightInv (S/Frame.cpp:87)
+    return FeatureGridC(a["desc"].shape[0], _p(a["desc"]), _p(a["xy"]), _p(a["oc"]), _p(a["an"]), x0, y0, x1, y1, wi, hi,
+                        int(g["cols"]), int(g["rows"]))
+
+
+def queries_struct(q, keep):
+    """ccm_proj_queries from dict(valid, uv, radius, level, desc[, angle])"""
+    m = len(q["valid"])
+    a = dict(valid=np.ascontiguousarray(q["valid"], np.uint8), uv=np.ascontiguousarray(q["uv"], np.float32),
+             r=np.ascontiguousarray(q["radius"], np.float32), lv=np.ascontiguousarray(q["level"], np.int32),
+             desc=np.ascontiguousarray(q["desc"], np.uint8), an=np.ascontiguousarray(q.get("angle", np.zeros(m)), np.float32))
+    keep.append(a)
+    return ProjQueriesC(m, _p(a["valid"]), _p(a["uv"]), _p(a["r"]), _p(a["lv"]), _p(a["desc"]), _p(a["an"]))
+
+
+def GetFeaturesInArea(g, x, y, r, minLevel=-1, maxLevel=-1):
+    """Frame::GetFeaturesInArea (S/Frame.cpp:200-253); with the default levels also KeyFrame's (S/KeyFrame.cpp:1162-1201).  Host only."""
+    keep = []; G = grid_struct(g, keep)
+    out = np.empty(G.n + 1, np.int32); n = C.c_int32()
+    _chk(lib().ccm_features_in_area(C.byref(G), C.c_float(x), C.c_float(y), C.c_float(r), int(minLevel), int(maxLevel), _p(out), G.n, C.byref(n)))
+    return out[:n.value].copy()
+
+
+def bow_assemble(scoring, weighting, word, weight, node):
+    """The container half of DBoW2's transform (host only): per-feature (word, weight, node) -> BowVector, FeatureVector."""
+    word = np.ascontiguousarray(word, np.uint32); weight = np.ascontiguousarray(weight, np.float64); node = np.ascontiguousarray(node, np.uint32)
+    n = len(word)
+    bid = np.empty(n, np.uint32); bval = np.empty(n, np.float64); bn = C.c_int32()
+    fid = np.empty(n, np.uint32); fptr = np.empty(n + 1, np.int32); ff = np.empty(n, np.uint32); fn = C.c_int32()
+    _chk(lib().ccm_bow_assemble(int(scoring), int(weighting), n, _p(word), _p(weight), _p(node), _p(bid), _p(bval), C.byref(bn),
+                                _p(fid), _p(fptr), _p(ff), C.byref(fn)))
+    return dict(bow_id=bid[:bn.value].copy(), bow_val=bval[:bn.value].copy(), fv_node_id=fid[:fn.value].copy(),
+                fv_node_ptr=fptr[:fn.value + 1].copy(), fv_feat=ff[:fptr[fn.value] if fn.value else 0].copy())
+
+
+class ORBVocabulary:
+    """DBoW2::TemplatedVocabulary<FORB> resident on the device.  `v` holds the rows of the text file (row 0 = root):
+    dict(k, L, scoring, weighting, parent, is_leaf, desc, weight) — see load_text() for ORBvoc.txt itself."""
+
+    def __init__(self, v):
+        parent = np.ascontiguousarray(v["parent"], np.int32); leaf = np.ascontiguousarray(v["is_leaf"], np.uint8)
+        desc = np.ascontiguousarray(v["desc"], np.uint8); weight = np.ascontiguousarray(v["weight"], np.float64)
+        assert desc.shape == (len(parent), 32)
+        self.h = C.c_void_p()
+        _chk(lib().ccm_voc_create(int(v["k"]), int(v["L"]), int(v["scoring"]), int(v["weighting"]), len(parent), _p(parent), _p(leaf),
+                                  _p(desc), _p(weight), C.byref(self.h)))
+
+    @staticmethod
+    def load_text(path):
+        """Rows of an ORBvoc.txt-style file (loadFromTextFile, D/TemplatedVocabulary.h:1338-1422) as the dict the constructor takes."""
+        with open(path) as f:
+            k, L, n1, n2 = [int(t) for t in f.readline().split()[:4]]
+            rows = np.loadtxt(f, dtype=np.float64, ndmin=2)
+        n = rows.shape[0] + 1
+        parent = np.zeros(n, np.int32); leaf = np.zeros(n, np.uint8); desc = np.zeros((n, 32), np.uint8); weight = np.zeros(n, np.float64)
+        parent[1:] = rows[:, 0].astype(np.int32); leaf[1:] = rows[:, 1] > 0
+        desc[1:] = rows[:, 2:34].astype(np.uint8); weight[1:] = rows[:, 34]
+        return dict(k=k, L=L, scoring=n1, weighting=n2, parent=parent, is_leaf=leaf, desc=desc, weight=weight)
+
+    def words(self):
+        return lib().ccm_voc_words(self.h)
+
+    def transform(self, desc, levelsup=4):
+        """-> dict(word, node, weight per feature; bow_id/bow_val = BowVector; fv_node_id/fv_node_ptr/fv_feat = FeatureVector)"""
+        desc = np.ascontiguousarray(desc, np.uint8); n = desc.shape[0]
+        word = np.empty(n, np.uint32); node = np.empty(n, np.uint32); w = np.empty(n, np.float64)
+        bid = np.empty(n, np.uint32); bval = np.empty(n, np.float64); bn = C.c_int32()
+        fid = np.empty(n, np.uint32); fptr = np.empty(n + 1, np.int32); ff = np.empty(n, np.uint32); fn = C.c_int32()
+        _chk(lib().ccm_voc_transform(self.h, _p(desc), n, int(levelsup), _p(word), _p(node), _p(w), _p(bid), _p(bval), C.byref(bn),
+                                     _p(fid), _p(fptr), _p(ff), C.byref(fn)))
+        return dict(word=word, node=node, weight=w, bow_id=bid[:bn.value].copy(), bow_val=bval[:bn.value].copy(),
+                    fv_node_id=fid[:fn.value].copy(), fv_node_ptr=fptr[:fn.value + 1].copy(), fv_feat=ff[:fptr[fn.value] if fn.value else 0].copy())
+
+    def close(self):
+        if self.h:
+            lib().ccm_voc_destroy(self.h); self.h = C.c_void_p()

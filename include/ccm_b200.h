@@ -324,6 +324,113 @@ int ccm_match_triangulation(const ccm_tri_view* v1, const ccm_tri_view* v2, cons
                             const float* level_sigma2, const float* scale_factors, int32_t nlevels,
                             int32_t check_orientation, int32_t* pairs /*2*min(n1,n2)*/, int32_t* npairs);
 
+/* ---- projection-guided matching -------------------------------------------------
+ * The seven matchers that look a projected map point up in the image grid share one shape:
+ *   [caller's prelude]  isBad / projection / IsInImage / distance + viewing-angle gates / PredictScale — f32 cv::Mat
+ *                       arithmetic, O(#points), stays verbatim in the shim (shim/ORBmatcher_shim.cpp);
+ *   [this library]      GetFeaturesInArea (cslam/src/Frame.cpp:200-253, KeyFrame.cpp:1162-1201) over the lookup grid of
+ *                       AssignFeaturesToGrid (Frame.cpp:103-119, KeyFrame.cpp:206-226), the level filter, the descriptor
+ *                       distances of every (query, feature) pair on the GPU (k_hamming), and the order-dependent
+ *                       selection in the reference's visiting order (cell column, cell row, feature index);
+ *   [caller's epilogue] map surgery on the returned indices (AddObservation / Replace / RemapMapPointMatch ...).
+ * A query is one map point after the prelude.  ccm_search_* = device distances + selection; ccm_select_* = the selection
+ * alone over a caller-supplied distance matrix D[m x n] (u16, row = query; e.g. from ccm_hamming_matrix when several
+ * matchers share one matrix) — host code, runs without a device.                                                        */
+typedef struct ccm_feature_grid {   /* the image side: a Frame or a KeyFrame */
+  int32_t n;
+  const uint8_t* desc;       /* n*32 : mDescriptors */
+  const float* kp_xy;        /* n*2  : mvKeysUn[i].pt */
+  const int32_t* octave;     /* n    : mvKeysUn[i].octave */
+  const float* angle;        /* n    : mvKeysUn[i].angle (only read when check_orientation) */
+  float min_x, min_y, max_x, max_y;   /* mnMinX, mnMinY, mnMaxX, mnMaxY */
+  float grid_w_inv, grid_h_inv;       /* mfGridElementWidthInv, mfGridElementHeightInv (Frame.cpp:86-87) */
+  int32_t grid_cols, grid_rows;       /* FRAME_GRID_COLS x FRAME_GRID_ROWS = 75 x 48 (Frame.h:51-52) / mnGridCols x mnGridRows */
+} ccm_feature_grid;
+
+typedef struct ccm_proj_queries {
+  int32_t m;
+  const uint8_t* valid;      /* m    : the prelude let this point through */
+  const float* uv;           /* m*2  : projected pixel */
+  const float* radius;       /* m    : r handed to GetFeaturesInArea */
+  const int32_t* level;      /* m    : nPredictedLevel / mnTrackScaleLevel / nLastOctave */
+  const uint8_t* desc;       /* m*32 : pMP->GetDescriptor() */
+  const float* angle;        /* m    : keypoint angle on the query side (only read when check_orientation) */
+} ccm_proj_queries;
+
+/* GetFeaturesInArea alone (host; min_level/max_level as Frame's overload, -1/-1 = KeyFrame's): count in *n, at most cap indices */
+int ccm_features_in_area(const ccm_feature_grid* g, float x, float y, float r, int32_t min_level, int32_t max_level,
+                         int32_t* out, int32_t cap, int32_t* n);
+
+/* SearchByProjection(Frame&, const vector<mpptr>&, th)  (cslam/src/ORBmatcher.cpp:71-148): levels [L-1, L], best and
+ * second best, TH_HIGH, ratio test when both sit on one level.  query_has_obs[i] = pMP->Observations()>0 and feat_blocked[j] =
+ * (F.mvpMapPoints[j] && Observations()>0) drive the skip of :107-109.  match_of_feat[j] = query last written to
+ * F.mvpMapPoints[j], -1 = untouched. */
+int ccm_search_by_projection_track(const ccm_feature_grid* g, const ccm_proj_queries* q, const uint8_t* query_has_obs,
+                                   const uint8_t* feat_blocked, float nnratio, int32_t* match_of_feat /*n*/, int32_t* nmatches);
+int ccm_select_by_projection_track(const ccm_feature_grid* g, const ccm_proj_queries* q, const uint16_t* D, const uint8_t* query_has_obs,
+                                   const uint8_t* feat_blocked, float nnratio, int32_t* match_of_feat, int32_t* nmatches);
+
+/* reloc = 0: SearchByProjection(Frame&, const Frame& LastFrame, th)  (ORBmatcher.cpp:1350-1476), threshold TH_HIGH, a feature
+ *            is skipped when it holds a map point with observations;
+ * reloc = 1: SearchByProjection(Frame&, kfptr, sAlreadyFound, th, ORBdist)  (ORBmatcher.cpp:1478-1605), threshold orb_dist,
+ *            a feature is skipped when it holds any map point (feat_blocked) and every assignment shields.
+ * Levels [L-1, L+1].  match_of_feat[j]: >= 0 query, -1 untouched, -2 assigned then cleared by the rotation histogram. */
+int ccm_search_by_projection_frame(const ccm_feature_grid* g, const ccm_proj_queries* q, const uint8_t* query_has_obs,
+                                   const uint8_t* feat_blocked, int32_t reloc, int32_t orb_dist, int32_t check_orientation,
+                                   int32_t* match_of_feat /*n*/, int32_t* nmatches);
+int ccm_select_by_projection_frame(const ccm_feature_grid* g, const ccm_proj_queries* q, const uint16_t* D, const uint8_t* query_has_obs,
+                                   const uint8_t* feat_blocked, int32_t reloc, int32_t orb_dist, int32_t check_orientation,
+                                   int32_t* match_of_feat, int32_t* nmatches);
+
+/* SearchByProjection(kfptr, Scw, vpPoints, vpMatched, th)  (ORBmatcher.cpp:308-446): levels [L-1, L], TH_LOW.
+ * feat_matched[j] = vpMatched[j] != nullptr on entry; existing_idx[i] = pMP->GetIndexInKeyFrame(pKF).  best_idx[i] = the
+ * keypoint found for query i (-1 none): the shim calls RemapMapPointMatch for queries with existing_idx != -1 (:418-432) and
+ * sets vpMatched[best_idx] otherwise (= match_of_feat, counted in *nmatches). */
+int ccm_search_by_projection_sim3(const ccm_feature_grid* g, const ccm_proj_queries* q, const uint8_t* feat_matched,
+                                  const int32_t* existing_idx, int32_t* best_idx /*m*/, int32_t* match_of_feat /*n*/, int32_t* nmatches);
+int ccm_select_by_projection_sim3(const ccm_feature_grid* g, const ccm_proj_queries* q, const uint16_t* D, const uint8_t* feat_matched,
+                                  const int32_t* existing_idx, int32_t* best_idx, int32_t* match_of_feat, int32_t* nmatches);
+
+/* the search half of Fuse(kfptr, const vector<mpptr>&, th) (ORBmatcher.cpp:854-993; pass inv_level_sigma2 = pKF->mvInvLevelSigma2
+ * for its chi-square gate :941-947) and of Fuse(kfptr, Scw, vpPoints, th, vpReplacePoint) (:995-1122; inv_level_sigma2 = NULL):
+ * best_idx[i] = keypoint to fuse query i with (-1 none).  The epilogue (:955-990 / :1103-1118) runs in query order in the shim. */
+int ccm_fuse_search(const ccm_feature_grid* g, const ccm_proj_queries* q, const float* inv_level_sigma2, int32_t nlevels,
+                    int32_t* best_idx /*m*/, int32_t* nfound);
+int ccm_fuse_select(const ccm_feature_grid* g, const ccm_proj_queries* q, const uint16_t* D, const float* inv_level_sigma2, int32_t nlevels,
+                    int32_t* best_idx, int32_t* nfound);
+
+/* SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th)  (ORBmatcher.cpp:1124-1348): q12 = one query per KF1 feature
+ * projected into KF2 (searched in g2), q21 the converse; TH_HIGH each way, kept when both directions agree (:1327-1343).
+ * match12[i1] = idx2 or -1. */
+int ccm_search_by_sim3(const ccm_feature_grid* g1, const ccm_feature_grid* g2, const ccm_proj_queries* q12, const ccm_proj_queries* q21,
+                       int32_t* match12 /*q12->m*/, int32_t* nfound);
+int ccm_select_by_sim3(const ccm_feature_grid* g1, const ccm_feature_grid* g2, const ccm_proj_queries* q12, const ccm_proj_queries* q21,
+                       const uint16_t* D12 /*q12->m x g2->n*/, const uint16_t* D21 /*q21->m x g1->n*/, int32_t* match12, int32_t* nfound);
+
+/* ---- DBoW2 transform ------------------------------------------------------------
+ * Replaces ORBVocabulary::transform(features, BowVector&, FeatureVector&, levelsup) as called by Frame::ComputeBoW
+ * (cslam/src/Frame.cpp:268-275) and KeyFrame::ComputeBoW (KeyFrame.cpp:277-286): the tree descent of every descriptor
+ * (thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1219-1260, FORB::distance FORB.cpp:77-100) runs on the GPU over a
+ * device-resident vocabulary; the two std::map containers (TemplatedVocabulary.h:1127-1192, BowVector.cpp:34-88,
+ * FeatureVector.cpp:28-43) are assembled on the host in feature order so the f64 sums round as the reference's.
+ * The vocabulary arrives as the rows of its text file (loadFromTextFile, TemplatedVocabulary.h:1338-1422): row 0 = root,
+ * row i = node id i: parent id, leaf flag, 32 descriptor bytes, weight; word ids are dealt in order of the leaf flags. */
+typedef struct ccm_voc_handle ccm_voc_handle;
+int ccm_voc_create(int32_t k, int32_t L, int32_t scoring /*DBoW2::ScoringType*/, int32_t weighting /*DBoW2::WeightingType*/,
+                   int32_t n_nodes, const int32_t* parent, const uint8_t* is_leaf, const uint8_t* desc /*n_nodes*32*/,
+                   const double* weight, ccm_voc_handle** out);
+int ccm_voc_words(const ccm_voc_handle* h);
+/* outputs sized n (fv_node_ptr n+1); any of word/node/weight_of_feat may be NULL */
+int ccm_voc_transform(ccm_voc_handle* h, const uint8_t* desc, int32_t n, int32_t levelsup,
+                      uint32_t* word_of_feat, uint32_t* node_of_feat, double* weight_of_feat,
+                      uint32_t* bow_id, double* bow_val, int32_t* bow_n,
+                      uint32_t* fv_node_id, int32_t* fv_node_ptr, uint32_t* fv_feat, int32_t* fv_n_nodes);
+/* the container half alone (host): per-feature (word, weight, node) -> BowVector + FeatureVector */
+int ccm_bow_assemble(int32_t scoring, int32_t weighting, int32_t n, const uint32_t* word_of_feat, const double* weight_of_feat,
+                     const uint32_t* node_of_feat, uint32_t* bow_id, double* bow_val, int32_t* bow_n,
+                     uint32_t* fv_node_id, int32_t* fv_node_ptr, uint32_t* fv_feat, int32_t* fv_n_nodes);
+void ccm_voc_destroy(ccm_voc_handle* h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -337,6 +337,109 @@ def match_triangulation(v1, v2, F12, ex, ey, level_sigma2, scale_factors, check_
     return pairs[:n].copy()
 
 
+# ---- projection-guided matchers (proj_oracle.cpp) and the DBoW2 transform (bow_oracle.cpp) -----------------------------
+class _Grid(C.Structure):
+    _fields_ = [("n", C.c_int32), ("desc", C.c_void_p), ("kp_xy", C.c_void_p), ("octave", C.c_void_p), ("angle", C.c_void_p),
+                ("min_x", C.c_float), ("min_y", C.c_float), ("max_x", C.c_float), ("max_y", C.c_float),
+                ("grid_w_inv", C.c_float), ("grid_h_inv", C.c_float), ("grid_cols", C.c_int32), ("grid_rows", C.c_int32)]
+
+
+class _Queries(C.Structure):
+    _fields_ = [("m", C.c_int32), ("valid", C.c_void_p), ("uv", C.c_void_p), ("radius", C.c_void_p), ("level", C.c_void_p),
+                ("desc", C.c_void_p), ("angle", C.c_void_p)]
+
+
+def grid_struct(g, keep, cls=_Grid):
+    """g = dict(desc, kp_xy, octave, angle, bounds=(min_x, min_y, max_x, max_y), cols, rows)"""
+    a = dict(desc=np.ascontiguousarray(g["desc"], np.uint8), xy=np.ascontiguousarray(g["kp_xy"], np.float32),
+             oc=np.ascontiguousarray(g["octave"], np.int32), an=np.ascontiguousarray(g["angle"], np.float32))
+    keep.append(a)
+    x0, y0, x1, y1 = [np.float32(v) for v in g["bounds"]]
+    wi = np.float32(g["cols"]) / np.float32(x1 - x0); hi = np.float32(g["rows"]) / np.float32(y1 - y0)   # S/Frame.cpp:86-87
+    return cls(a["desc"].shape[0], _p(a["desc"]), _p(a["xy"]), _p(a["oc"]), _p(a["an"]), x0, y0, x1, y1, wi, hi, int(g["cols"]), int(g["rows"]))
+
+
+def queries_struct(q, keep, cls=_Queries):
+    """q = dict(valid, uv, radius, level, desc, angle)"""
+    a = dict(valid=np.ascontiguousarray(q["valid"], np.uint8), uv=np.ascontiguousarray(q["uv"], np.float32),
+             r=np.ascontiguousarray(q["radius"], np.float32), lv=np.ascontiguousarray(q["level"], np.int32),
+             desc=np.ascontiguousarray(q["desc"], np.uint8), an=np.ascontiguousarray(q.get("angle", np.zeros(len(q["valid"]))), np.float32))
+    keep.append(a)
+    return cls(a["valid"].shape[0], _p(a["valid"]), _p(a["uv"]), _p(a["r"]), _p(a["lv"]), _p(a["desc"]), _p(a["an"]))
+
+
+def features_in_area(g, x, y, r, min_level=-1, max_level=-1):
+    keep = []; G = grid_struct(g, keep)
+    out = np.empty(G.n + 1, np.int32)
+    n = lib().orc_features_in_area(C.byref(G), C.c_float(x), C.c_float(y), C.c_float(r), int(min_level), int(max_level), _p(out), G.n)
+    return out[:n].copy()
+
+
+def search_by_projection_track(g, q, query_has_obs, feat_blocked, nnratio=0.8):
+    keep = []; G = grid_struct(g, keep); Q = queries_struct(q, keep)
+    ho = np.ascontiguousarray(query_has_obs, np.uint8); fb = np.ascontiguousarray(feat_blocked, np.uint8)
+    out = np.empty(G.n, np.int32)
+    n = lib().orc_search_by_projection_track(C.byref(G), C.byref(Q), _p(ho), _p(fb), C.c_float(nnratio), _p(out))
+    return out, n
+
+
+def search_by_projection_frame(g, q, query_has_obs, feat_blocked, reloc=False, orb_dist=100, check_ori=True):
+    keep = []; G = grid_struct(g, keep); Q = queries_struct(q, keep)
+    ho = np.ascontiguousarray(query_has_obs, np.uint8); fb = np.ascontiguousarray(feat_blocked, np.uint8)
+    out = np.empty(G.n, np.int32)
+    n = lib().orc_search_by_projection_frame(C.byref(G), C.byref(Q), _p(ho), _p(fb), int(reloc), int(orb_dist), int(check_ori), _p(out))
+    return out, n
+
+
+def search_by_projection_sim3(g, q, feat_matched, existing_idx):
+    keep = []; G = grid_struct(g, keep); Q = queries_struct(q, keep)
+    fm = np.ascontiguousarray(feat_matched, np.uint8); ex = np.ascontiguousarray(existing_idx, np.int32)
+    best = np.empty(Q.m, np.int32); out = np.empty(G.n, np.int32)
+    n = lib().orc_search_by_projection_sim3(C.byref(G), C.byref(Q), _p(fm), _p(ex), _p(best), _p(out))
+    return best, out, n
+
+
+def fuse_search(g, q, inv_level_sigma2=None):
+    keep = []; G = grid_struct(g, keep); Q = queries_struct(q, keep)
+    w = None if inv_level_sigma2 is None else np.ascontiguousarray(inv_level_sigma2, np.float32)
+    best = np.empty(Q.m, np.int32)
+    n = lib().orc_fuse_search(C.byref(G), C.byref(Q), _p(w), _p(best))
+    return best, n
+
+
+def search_by_sim3(g1, g2, q12, q21):
+    keep = []; G1 = grid_struct(g1, keep); G2 = grid_struct(g2, keep); Q12 = queries_struct(q12, keep); Q21 = queries_struct(q21, keep)
+    out = np.empty(Q12.m, np.int32)
+    n = lib().orc_search_by_sim3(C.byref(G1), C.byref(G2), C.byref(Q12), C.byref(Q21), _p(out))
+    return out, n
+
+
+class Vocabulary:
+    """v = dict(k, L, scoring, weighting, parent, is_leaf, desc, weight) with row 0 = root (ccm_slam_b200.synth.make_vocabulary)."""
+
+    def __init__(self, v):
+        self.parent = np.ascontiguousarray(v["parent"], np.int32); self.is_leaf = np.ascontiguousarray(v["is_leaf"], np.uint8)
+        self.desc = np.ascontiguousarray(v["desc"], np.uint8); self.weight = np.ascontiguousarray(v["weight"], np.float64)
+        f = lib().orc_voc_create; f.restype = C.c_void_p
+        self.h = f(int(v["k"]), int(v["L"]), int(v["scoring"]), int(v["weighting"]), len(self.parent), _p(self.parent), _p(self.is_leaf),
+                   _p(self.desc), _p(self.weight))
+        assert self.h, "malformed vocabulary"
+
+    def transform(self, feat, levelsup=4):
+        feat = np.ascontiguousarray(feat, np.uint8); n = feat.shape[0]
+        word = np.empty(n, np.uint32); node = np.empty(n, np.uint32); w = np.empty(n, np.float64)
+        bid = np.empty(n, np.uint32); bval = np.empty(n, np.float64); bn = C.c_int32()
+        fid = np.empty(n, np.uint32); fptr = np.empty(n + 1, np.int32); ff = np.empty(n, np.uint32); fn = C.c_int32()
+        lib().orc_voc_transform(C.c_void_p(self.h), _p(feat), n, int(levelsup), _p(word), _p(node), _p(w), _p(bid), _p(bval), C.byref(bn),
+                                _p(fid), _p(fptr), _p(ff), C.byref(fn))
+        return dict(word=word, node=node, weight=w, bow_id=bid[:bn.value].copy(), bow_val=bval[:bn.value].copy(),
+                    fv_node_id=fid[:fn.value].copy(), fv_node_ptr=fptr[:fn.value + 1].copy(), fv_feat=ff[:fptr[fn.value] if fn.value else 0].copy())
+
+    def close(self):
+        if self.h:
+            lib().orc_voc_destroy(C.c_void_p(self.h)); self.h = None
+
+
 # ---- single-vertex optimisations (PoseOptimizationClient, OptimizeSim3) ---------------------------------------------
 class _PoseOpt(C.Structure):
     _fields_ = [("n", C.c_int32), ("Tcw", C.c_void_p), ("Xw", C.c_void_p), ("uv", C.c_void_p), ("inv_sigma2", C.c_void_p),
