@@ -379,6 +379,83 @@ __global__ void __launch_bounds__(TPB) k_schur(const uint2* __restrict__ prod, c
   }
 }
 
+// K4, tensor-core form (CCM_SCHUR=mma).  The gather form above spends its time in L1TEX wavefronts: every lane of a
+// stream pulls 21 doubles per product.  Here one product Z_oa (6x3) . Z_ob^T (3x6) is ONE mma.sync.m8n8k4.f64 whose
+// operand fragments are exactly one coalesced 144-byte row each:
+//   A (8x4 row-major): lane t holds A[t/4][t%4] = Z_oa[t/4][t%4]        rows 6,7 and column 3 are zero padding
+//   B (4x8 col-major): lane t holds B[t%4][t/4] = Z_ob[t/4][t%4]        -> the same offset (t/4)*3 + t%4 into the row
+//   C (8x8)          : lane t holds C[t/4][2*(t%4)], C[t/4][2*(t%4)+1]  accumulated in place over the product list
+// i.e. 18 lanes x 8 B per operand (2 cache lines), no shuffles, no cross-lane reduction.  Diagonal blocks put g_l into
+// B's column 6, so C[r][6] = sum_o Z_o[r][:] . g_l(o) = bneg comes out of the same instruction.  Two accumulator sets
+// (products alternate) keep two MMA chains in flight; they are added in a fixed order: deterministic per list order.
+__device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+template <int UNROLL, int CTA>
+__global__ void __launch_bounds__(CTA) k_schur_mma(const uint2* __restrict__ prod, const unsigned* __restrict__ u_prod_ptr,
+                                                   const int* __restrict__ u_row, const int* __restrict__ u_col, int nub,
+                                                   const double* __restrict__ Z, const int* __restrict__ o_lm,
+                                                   const double* __restrict__ gvec, double* __restrict__ U_val,
+                                                   double* __restrict__ bneg) {
+  static_assert(UNROLL % 2 == 0, "products alternate between two accumulator sets");
+  const int warp = (int)(((long long)blockIdx.x * CTA + threadIdx.x) >> 5);
+  if (warp >= nub) return;  // warp-uniform
+  const int lane = threadIdx.x & 31;
+  const int m = lane >> 2, k = lane & 3;
+  const bool ld = m < 6 && k < 3;
+  const int off = ld ? m * 3 + k : 0;  // padding lanes read element 0 of the same row (no extra line) and discard it
+  const unsigned beg = u_prod_ptr[warp], end = u_prod_ptr[warp + 1];
+  const int row = u_row[warp];
+  const bool diag = row == u_col[warp];
+  double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+  unsigned p = beg;
+  if (!diag) {
+    for (; p + UNROLL <= end; p += UNROLL) {
+      uint2 pr[UNROLL];
+#pragma unroll
+      for (int j = 0; j < UNROLL; j++) pr[j] = prod[p + j];  // one address for the whole warp
+      double a[UNROLL], b[UNROLL];
+#pragma unroll
+      for (int j = 0; j < UNROLL; j++) {
+        a[j] = Z[(size_t)pr[j].x * 18 + off];
+        b[j] = Z[(size_t)pr[j].y * 18 + off];
+      }
+#pragma unroll
+      for (int j = 0; j < UNROLL; j += 2) {
+        dmma_884(c00, c01, ld ? a[j] : 0.0, ld ? b[j] : 0.0);
+        dmma_884(c10, c11, ld ? a[j + 1] : 0.0, ld ? b[j + 1] : 0.0);
+      }
+    }
+    for (; p < end; p++) {
+      const uint2 pr = prod[p];
+      const double a = Z[(size_t)pr.x * 18 + off], b = Z[(size_t)pr.y * 18 + off];
+      if ((p - beg) & 1u) dmma_884(c10, c11, ld ? a : 0.0, ld ? b : 0.0);  // warp-uniform branch
+      else dmma_884(c00, c01, ld ? a : 0.0, ld ? b : 0.0);
+    }
+  } else {
+    // diagonal block (Kf of them): lanes 24..26 carry g_l in column 6 of B, so C[r][6] accumulates bneg
+    const bool gl = m == 6 && k < 3;
+    for (; p < end; p++) {
+      const uint2 pr = prod[p];
+      const double a = Z[(size_t)pr.x * 18 + off];
+      double b = Z[(size_t)pr.y * 18 + off];
+      if (!ld) b = 0.0;
+      if (gl) b = gvec[3 * (size_t)o_lm[pr.x] + k];
+      if ((p - beg) & 1u) dmma_884(c10, c11, ld ? a : 0.0, b);
+      else dmma_884(c00, c01, ld ? a : 0.0, b);
+    }
+  }
+  c00 += c10; c01 += c11;
+  if (ld) {
+    U_val[(size_t)warp * 36 + m * 6 + 2 * k] = -c00;
+    U_val[(size_t)warp * 36 + m * 6 + 2 * k + 1] = -c01;
+  }
+  if (diag && m < 6 && k == 3) bneg[(size_t)row * 6 + m] = -c00;  // C[m][6]
+}
+
 // S (full block-CSR) from the upper blocks: diagonal gets Hpp + lambda I, lower blocks are transposed copies.
 __global__ void __launch_bounds__(TPB) k_finalize_S(const int* __restrict__ s_row, const int* __restrict__ s_col,
                                                     const int* __restrict__ csr_u, long long nnzb,

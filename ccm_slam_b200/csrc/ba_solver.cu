@@ -218,11 +218,45 @@ void step_scale(ccm_ba_handle* h, double lambda) {
   CCM_LAUNCHED();
 }
 
+// CCM_SCHUR selects the Schur-product kernel: "mma" (default: one f64 mma.sync per product, k_schur_mma) or "gather"
+// (5 streams x 6 lanes of f64 FMA, k_schur).  Modes 2..5 are launch-shape variants of the mma form kept for tuning runs.
+std::atomic<int> g_schur_override{-1};  // ccm_ba_debug_set_schur_mode
+int schur_mode() {
+  static const int env_mode = [] {
+    const char* v = getenv("CCM_SCHUR");
+    if (!v) return 1;
+    if (!strcmp(v, "gather") || !strcmp(v, "0")) return 0;
+    if (!strcmp(v, "mma")) return 1;
+    const int m = atoi(v);
+    return (m >= 0 && m <= 5) ? m : 1;
+  }();
+  const int o = g_schur_override.load(std::memory_order_relaxed);
+  return o >= 0 ? o : env_mode;
+}
+
+template <int UNROLL, int CTA>
+void launch_schur_mma(ccm_ba_handle* h, cudaStream_t s) {
+  k_schur_mma<UNROLL, CTA><<<div_up((long long)h->nub * 32, CTA), CTA, 0, s>>>(h->prod.p, h->u_prod_ptr.p, h->u_row.p, h->u_col.p, h->nub,
+                                                                              h->Z.p, h->o_lm.p, h->gvec.p, h->U_val(), h->bneg());
+}
+
+void launch_schur(ccm_ba_handle* h, cudaStream_t s) {
+  switch (schur_mode()) {
+    case 0:
+      k_schur<<<div_up((long long)h->nub * 32, TPB), TPB, 0, s>>>(h->prod.p, h->u_prod_ptr.p, h->u_row.p, h->u_col.p, h->nub, h->Z.p,
+                                                                  h->o_lm.p, h->gvec.p, h->U_val(), h->bneg());
+      break;
+    case 2: launch_schur_mma<16, 256>(h, s); break;
+    case 3: launch_schur_mma<4, 256>(h, s); break;
+    case 4: launch_schur_mma<8, 128>(h, s); break;
+    case 5: launch_schur_mma<8, 512>(h, s); break;
+    default: launch_schur_mma<8, 256>(h, s); break;
+  }
+}
+
 void step_schur(ccm_ba_handle* h) {
   KernelSpan sp(h, CCM_BA_K_SCHUR);
-  k_schur<<<div_up((long long)h->nub * 32, TPB), TPB, 0, h->stream>>>(h->prod.p, h->u_prod_ptr.p, h->u_row.p, h->u_col.p,
-                                                                      h->nub, h->Z.p, h->o_lm.p, h->gvec.p, h->U_val(),
-                                                                      h->bneg());
+  launch_schur(h, h->stream);
   CCM_LAUNCHED();
 }
 
@@ -969,6 +1003,13 @@ extern "C" int ccm_ba_debug_schur(ccm_ba_handle* h, int robust, double huber_del
   });
 }
 
+extern "C" int ccm_ba_debug_set_schur_mode(int mode) {
+  return guarded([&] {
+    CCM_REQUIRE(mode >= -1 && mode <= 5, "ccm_ba_debug_set_schur_mode: -1 (CCM_SCHUR / default), 0 gather, 1 mma, 2..5 mma launch shapes");
+    g_schur_override.store(mode);
+  });
+}
+
 extern "C" int ccm_ba_time_kernel(ccm_ba_handle* h, int which, int reps, double huber_delta, double lambda, double* ms_per_launch) {
   return guarded([&] {
     CCM_REQUIRE(h && ms_per_launch && reps > 0, "bad argument");
@@ -1002,8 +1043,7 @@ extern "C" int ccm_ba_time_kernel(ccm_ba_handle* h, int which, int reps, double 
           k_scale<<<div_up(h->El, TPB), TPB, 0, s>>>(h->o_lm.p, h->W.p, h->Ep, h->Hll(), h->bl(), h->Pl, h->El, lambda, h->Z.p, h->gvec.p);
           break;
         case 4:
-          k_schur<<<div_up((long long)h->nub * 32, TPB), TPB, 0, s>>>(h->prod.p, h->u_prod_ptr.p, h->u_row.p, h->u_col.p, h->nub,
-                                                                      h->Z.p, h->o_lm.p, h->gvec.p, h->U_val(), h->bneg());
+          launch_schur(h, s);
           break;
         case 5:
           k_backsub_points<<<grid_stride(h->Pl), TPB, 0, s>>>(h->lm_ptr.p, h->o_kf.p, h->pose_slot.p, h->Z.p, h->Hll(), h->bl(),
