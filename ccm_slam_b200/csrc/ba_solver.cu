@@ -74,7 +74,7 @@ struct ccm_ba_handle {
   DevBuf<unsigned> kobs_ptr;
   // pcg
   DevBuf<double> x, pr, pz, pp, pq, pcg_partials, pcg_status, dxl, pcg_Ac, pcg_rc, pcg_yc;
-  int pcg_agg = 0, pcg_nc = 0, pcg_refresh = 4, pcg_age = 0;
+  int pcg_agg = 0, pcg_nc = 0, pcg_refresh = 4, pcg_age = 0, pcg_prolong = 0;
   bool pcg_coarse_valid = false;  // Ac holds a usable inverse from an earlier trial
   DevBuf<unsigned> pcg_bar;
   DevBuf<long long> pcg_prof;  // allocated only with CCM_PCG_PROF=1
@@ -246,11 +246,13 @@ void launch_schur(ccm_ba_handle* h, cudaStream_t s) {
       k_schur<<<div_up((long long)h->nub * 32, TPB), TPB, 0, s>>>(h->prod.p, h->u_prod_ptr.p, h->u_row.p, h->u_col.p, h->nub, h->Z.p,
                                                                   h->o_lm.p, h->gvec.p, h->U_val(), h->bneg());
       break;
+    // measured on cfg5 (tools/schur_variants.py, ms per launch): u8/cta128 8.72, u16/cta256 9.08, u4/cta256 9.13, u8/cta256 9.33,
+    // u8/cta512 10.07; gather form 12.78
     case 2: launch_schur_mma<16, 256>(h, s); break;
     case 3: launch_schur_mma<4, 256>(h, s); break;
-    case 4: launch_schur_mma<8, 128>(h, s); break;
+    case 4: launch_schur_mma<8, 256>(h, s); break;
     case 5: launch_schur_mma<8, 512>(h, s); break;
-    default: launch_schur_mma<8, 256>(h, s); break;
+    default: launch_schur_mma<8, 128>(h, s); break;
   }
 }
 
@@ -286,6 +288,7 @@ void step_pcg(ccm_ba_handle* h, double tol, int max_iter) {
   a.partials = h->pcg_partials.p; a.bar = h->pcg_bar.p; a.tol = tol; a.max_iter = max_iter; a.status = h->pcg_status.p;
   a.agg = h->pcg_agg; a.nc = h->pcg_nc; a.Ac = h->pcg_Ac.p; a.rc = h->pcg_rc.p; a.yc = h->pcg_yc.p;
   a.prof = h->pcg_prof.p;
+  a.prolong = h->pcg_prolong;
   a.coarse_mode = (h->pcg_coarse_valid && h->pcg_age < h->pcg_refresh) ? 2 : 1;
   h->pcg_last_mode = a.coarse_mode;
   void* args[] = {&a};
@@ -631,7 +634,9 @@ void build(ccm_ba_handle* h, const ccm_ba_problem* p) {
   if (env_int("CCM_PCG_PROF", 0)) h->pcg_prof.alloc_zero(8, s);
   // coarse space: <= 128 aggregates for small systems, <= 384 for long trajectories where the smooth modes dominate the
   // iteration count; the inverse is refreshed every 2nd / 4th solve (measured sweeps: tools/ba_probe.py with CCM_PCG_NC/REFRESH)
-  pcg_coarse_shape(Kf, env_int("CCM_PCG_NC", Kf >= 4096 ? 384 : 128), &h->pcg_agg, &h->pcg_nc);
+  // CCM_PCG_PROLONG=1: piecewise-linear prolongation (pcg.cuh); half the coarse nodes then already beat the constant P
+  h->pcg_prolong = env_int("CCM_PCG_PROLONG", 0) ? 1 : 0;
+  pcg_coarse_shape(Kf, env_int("CCM_PCG_NC", Kf >= 4096 ? (h->pcg_prolong ? 192 : 384) : 128), &h->pcg_agg, &h->pcg_nc);
   h->pcg_refresh = std::max(1, env_int("CCM_PCG_REFRESH", Kf >= 4096 ? 4 : 2));
   {
     const size_t nC = (size_t)6 * h->pcg_nc;

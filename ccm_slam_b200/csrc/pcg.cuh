@@ -7,11 +7,14 @@
 //
 // Preconditioner: two-level additive Schwarz,  M^-1 = blockdiag(S)^-1 + P (P^T S P)^-1 P^T.
 //   * fine level: block-Jacobi (inverse diagonal blocks, computed by the caller);
-//   * coarse level: aggregates of `agg` consecutive block rows (keyframes are ordered along each agent's trajectory, so
+//   * coarse level (prolong = 0, the default): aggregates of `agg` consecutive block rows (keyframes are ordered along each agent's trajectory, so
 //     index neighbours are co-visible), piecewise-constant prolongation per degree of freedom -> a dense (BS*nc)^2
 //     Galerkin matrix, nc <= 128, assembled and inverted (ping-pong Gauss-Jordan, one grid barrier per pivot) inside the
 //     same kernel before the iteration starts.  It removes the smooth error modes along the trajectory that make
 //     block-Jacobi PCG iteration counts grow with the number of keyframes.
+//   * prolong = 1 (CCM_PCG_PROLONG=1): the same coarse nodes, but P interpolates linearly between aggregate centres.  On the
+//     cfg5 chain this cuts the iteration count 2.2-2.9x at equal coarse size and a linear P over 192 nodes beats a constant P
+//     over 768 (tools/pcg_precond_study.py, profiles/pcg_precond_study_r1.txt).  Not yet run on the device: off by default.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -54,6 +57,7 @@ struct PcgArgs {
   // coarse level (agg <= 0 disables it)
   int agg, nc;       // rows per aggregate, number of aggregates
   int coarse_mode;   // 1: assemble + invert now, 2: reuse the inverse a previous launch left in Ac (still a valid SPD preconditioner)
+  int prolong = 0;   // 0: piecewise-constant prolongation (one coarse node per aggregate), 1: piecewise linear between aggregate centres
   double* Ac;        // 2 * (BS*nc)^2 ping-pong buffers
   double* rc;        // 2 * BS*nc restricted residual (double buffered)
   double* yc;        // BS*nc coarse correction
@@ -70,6 +74,25 @@ __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& target) {
     __threadfence();
   }
   __syncthreads();
+}
+
+// Coarse parents of fine block row a.  Piecewise constant: the aggregate a / agg with weight 1.  Piecewise linear: the two
+// aggregate centres ((g + 1/2) agg - 1/2) that bracket a, hat-function weights; rows outside the first / last centre take the
+// end node with weight 1.  The columns of P stay a partition of unity, so P^T S P is SPD whenever S is.
+struct CoarseParents { int lo, hi; double w0, w1; };
+__device__ __forceinline__ CoarseParents coarse_parents(int a, int agg, int nc, int prolong) {
+  CoarseParents c;
+  if (!prolong || nc < 2) {
+    c.lo = c.hi = a / agg; c.w0 = 1.0; c.w1 = 0.0;
+    return c;
+  }
+  double pos = ((double)a + 0.5) / (double)agg - 0.5;
+  pos = fmin(fmax(pos, 0.0), (double)(nc - 1));
+  int lo = (int)pos;  // pos >= 0: truncation is floor
+  if (lo > nc - 2) lo = nc - 2;
+  const double f = fmin(fmax(pos - (double)lo, 0.0), 1.0);
+  c.lo = lo; c.hi = lo + 1; c.w0 = 1.0 - f; c.w1 = f;
+  return c;
 }
 
 // sum of partials[0..g) in a fixed order, same value in every thread of the calling warp
@@ -114,6 +137,48 @@ __global__ void __launch_bounds__(MAXT, MINB) k_pcg(PcgArgs A) {
     grid_barrier(A.bar, target);
     // assembly: the warp walks one block row, accumulates the blocks of one aggregate column in registers, flushes with
     // red.add when the aggregate changes (columns are sorted, so a row flushes once per touched aggregate)
+    if (A.prolong) {
+      // piecewise-linear P: block S_ab feeds the coarse columns lo(b) and lo(b)+1.  Columns are sorted, so lo(b) never decreases
+      // along the row: keep the running sums for nodes `cur` (L) and `cur + 1` (H), shift H -> L when lo(b) advances by one, and
+      // flush a finished column sum T_J = sum_b w_J(b) S_ab into the coarse rows of both parents of a, weighted.
+      for (int a = gw; a < A.n; a += nw) {
+        const CoarseParents pa = coarse_parents(a, A.agg, A.nc, 1);
+        double l0 = 0.0, l1 = 0.0, h0 = 0.0, h1 = 0.0;
+        int cur = -1;
+        auto flush = [&](int J, double t0, double t1) {
+          if (J < 0 || J >= A.nc) return;
+          if (lane < BB) {
+            const size_t c = (size_t)J * BS + lane % BS;
+            atomicAdd(A0 + (size_t)(pa.lo * BS + lane / BS) * nC + c, pa.w0 * t0);
+            if (pa.w1 != 0.0) atomicAdd(A0 + (size_t)(pa.hi * BS + lane / BS) * nC + c, pa.w1 * t0);
+          }
+          if (lane + 32 < BB) {
+            const size_t c = (size_t)J * BS + (lane + 32) % BS;
+            atomicAdd(A0 + (size_t)(pa.lo * BS + (lane + 32) / BS) * nC + c, pa.w0 * t1);
+            if (pa.w1 != 0.0) atomicAdd(A0 + (size_t)(pa.hi * BS + (lane + 32) / BS) * nC + c, pa.w1 * t1);
+          }
+        };
+        const int beg = A.rowptr[a], end = A.rowptr[a + 1];
+        for (int j = beg; j < end; j++) {
+          const CoarseParents pb = coarse_parents(A.col[j], A.agg, A.nc, 1);
+          if (pb.lo != cur) {
+            if (cur >= 0) {
+              flush(cur, l0, l1);
+              if (pb.lo == cur + 1) { l0 = h0; l1 = h1; }
+              else { flush(cur + 1, h0, h1); l0 = 0.0; l1 = 0.0; }
+            }
+            h0 = 0.0; h1 = 0.0;
+            cur = pb.lo;
+          }
+          const double* v = A.val + (size_t)j * BB;
+          const double s0 = lane < BB ? __ldg(v + lane) : 0.0;
+          const double s1 = lane + 32 < BB ? __ldg(v + lane + 32) : 0.0;
+          l0 += pb.w0 * s0; l1 += pb.w0 * s1;
+          h0 += pb.w1 * s0; h1 += pb.w1 * s1;
+        }
+        if (cur >= 0) { flush(cur, l0, l1); flush(cur + 1, h0, h1); }
+      }
+    } else
     for (int a = gw; a < A.n; a += nw) {
       const int ra = a / A.agg;
       double acc0 = 0.0, acc1 = 0.0;
@@ -251,7 +316,14 @@ __global__ void __launch_bounds__(MAXT, MINB) k_pcg(PcgArgs A) {
         double zv = 0.0;
 #pragma unroll
         for (int k = 0; k < BS; k++) zv += M[k] * r6[k];
-        if (coarse) zv += __ldcg(A.yc + (size_t)(a / A.agg) * BS + lane);
+        if (coarse) {
+          if (A.prolong) {
+            const CoarseParents pa = coarse_parents(a, A.agg, A.nc, 1);
+            zv += pa.w0 * __ldcg(A.yc + (size_t)pa.lo * BS + lane) + pa.w1 * __ldcg(A.yc + (size_t)pa.hi * BS + lane);
+          } else {
+            zv += __ldcg(A.yc + (size_t)(a / A.agg) * BS + lane);
+          }
+        }
         A.z[(size_t)a * BS + lane] = zv;
         acc_rz += rv * zv;
         acc_rr += rv * rv;
@@ -260,6 +332,16 @@ __global__ void __launch_bounds__(MAXT, MINB) k_pcg(PcgArgs A) {
   };
   // rc[buf] += P^T r over the rows of this warp (red.add), then (after a barrier) yc = Ainv rc[buf]
   auto restrict_rows = [&](int buf) {
+    if (A.prolong) {
+      for (int a = gw; a < A.n; a += nw)
+        if (lane < BS) {
+          const CoarseParents pa = coarse_parents(a, A.agg, A.nc, 1);
+          const double rv = A.r[(size_t)a * BS + lane];
+          atomicAdd(A.rc + (size_t)buf * nC + (size_t)pa.lo * BS + lane, pa.w0 * rv);
+          if (pa.w1 != 0.0) atomicAdd(A.rc + (size_t)buf * nC + (size_t)pa.hi * BS + lane, pa.w1 * rv);
+        }
+      return;
+    }
     for (int a = gw; a < A.n; a += nw)
       if (lane < BS) atomicAdd(A.rc + (size_t)buf * nC + (size_t)(a / A.agg) * BS + lane, A.r[(size_t)a * BS + lane]);
   };

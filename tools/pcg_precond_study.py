@@ -78,15 +78,31 @@ def make_seg(S, Kf, m, overlap=0):
     return apply, nbytes
 
 
-def make_coarse(S, Kf, nc_target):
+def prolongation(Kf, nc_target, kind):
+    """6 coarse unknowns per aggregate of consecutive keyframes.  kind: "pc" piecewise constant (the kernel's), "pl" piecewise
+    linear between aggregate centres (hat functions), applied per degree of freedom."""
     agg = -(-Kf // nc_target)            # keyframes per aggregate
     nagg = -(-Kf // agg)
-    # prolongation: piecewise constant per degree of freedom -> 6 coarse unknowns per aggregate
-    rows = np.arange(6 * Kf); cols = (rows // 6 // agg) * 6 + rows % 6
-    Pm = sp.csr_matrix((np.ones(6 * Kf), (rows, cols)), shape=(6 * Kf, 6 * nagg))
+    k = np.arange(Kf)
+    if kind == "pc":
+        r = np.repeat(k, 1); c = k // agg; w = np.ones(Kf)
+    else:
+        centre = (np.arange(nagg) + 0.5) * agg - 0.5
+        pos = np.clip((k - centre[0]) / agg, 0, nagg - 1)
+        lo = np.minimum(np.floor(pos).astype(np.int64), nagg - 2) if nagg > 1 else np.zeros(Kf, np.int64)
+        f = np.clip(pos - lo, 0.0, 1.0)
+        r = np.concatenate([k, k]); c = np.concatenate([lo, np.minimum(lo + 1, nagg - 1)]); w = np.concatenate([1 - f, f])
+    Pk = sp.csr_matrix((w, (r, c)), shape=(Kf, nagg))
+    return sp.kron(Pk, sp.identity(6), format="csr"), 6 * nagg
+
+
+def make_coarse(S, Kf, nc_target, kind="pc", smooth=0.0, Dinv=None):
+    Pm, nc = prolongation(Kf, nc_target, kind)
+    if smooth > 0.0:                      # smoothed aggregation: one damped block-Jacobi sweep on the prolongator
+        Pm = (Pm - smooth * (Dinv @ (S @ Pm))).tocsr()
     Ac = (Pm.T @ S @ Pm).toarray()
     Acinv = np.linalg.inv(Ac)
-    return (lambda r: Pm @ (Acinv @ (Pm.T @ r))), 6 * nagg
+    return (lambda r: Pm @ (Acinv @ (Pm.T @ r))), nc, Pm.nnz
 
 
 def pcg(S, b, M, tol=1e-8, maxit=5000):
@@ -114,24 +130,22 @@ def main():
     S0, rhs, Kf, maxdiag = reduced_system(p, 0.0)
     lam0 = 1e-5 * maxdiag
     print(f"S: {S0.shape[0]} unknowns, {S0.nnz / 36:.0f} blocks; lambda0 = {lam0:.3e}", flush=True)
-    NC = 384
-    for lam in [lam0, lam0 / 9, lam0 / 81, lam0 / 729]:
+    lams = [lam0 / 9, lam0 / 81, lam0 / 729, lam0 / 6561]
+    for lam in lams:
         S, rhs, Kf, _ = reduced_system(p, lam)
         res = {}
         bj, _ = make_seg(S, Kf, 1)
-        coarse, nc = make_coarse(S, Kf, NC)
+        blocks = diag_blocks(S, Kf, 1)
+        Dinv = sp.block_diag([B for _, _, B in blocks], format="csr")
         res["bj"] = pcg(S, rhs, bj)
-        res["bj+c"] = pcg(S, rhs, lambda r: bj(r) + coarse(r))
-        for m in (8, 16, 32, 64):
-            seg, nb = make_seg(S, Kf, m)
-            res[f"seg({m})"] = pcg(S, rhs, seg)
-            res[f"seg({m})+c"] = pcg(S, rhs, lambda r: seg(r) + coarse(r))
-            res[f"seg({m}) MB"] = round(nb / 1e6, 1)
-        for m, o in ((16, 4), (32, 8)):
-            ov, nb = make_seg(S, Kf, m, o)
-            res[f"ovl({m},{o})+c"] = pcg(S, rhs, lambda r: ov(r) + coarse(r))
-            res[f"ovl({m},{o}) MB"] = round(nb / 1e6, 1)
-        print(f"lambda = {lam:.3e} (coarse {nc} unknowns): " + "  ".join(f"{k}={v}" for k, v in res.items()), flush=True)
+        for NC in (192, 384, 768):
+            for kind in ("pc", "pl"):
+                coarse, nc, _ = make_coarse(S, Kf, NC, kind)
+                res[f"bj+{kind}{NC}"] = pcg(S, rhs, lambda r: bj(r) + coarse(r))
+            coarse, nc, nnz = make_coarse(S, Kf, NC, "pc", smooth=0.66, Dinv=Dinv)
+            res[f"bj+sa{NC}"] = pcg(S, rhs, lambda r: bj(r) + coarse(r))
+            res[f"sa{NC} P nnz/row"] = round(nnz / (6 * Kf), 1)
+        print(f"lambda = {lam:.3e}: " + "  ".join(f"{k}={v}" for k, v in res.items()), flush=True)
 
 
 if __name__ == "__main__":
