@@ -8,6 +8,7 @@ reference algorithm) at the moment it agreed with the independent witnesses avai
   * Lie algebra  : scipy.spatial.transform.Rotation
   * ORB stages   : cv2 4.13 (resize INTER_LINEAR, GaussianBlur 7x7 sigma 2 REFLECT_101, FastFeatureDetector 9_16 + NMS, fastAtan2)
   * Hamming      : numpy unpackbits
+  * projection-guided matchers, DBoW2 transform : tests/witness_match.py (pure Python, brute-force window membership, dict containers)
 
 Each block below asserts the agreement BEFORE writing, so a fixture can only be (re)generated from an oracle the witnesses
 accept.  Run from the repo root:  python tests/golden/make_golden.py
@@ -194,12 +195,87 @@ def golden_match():
          F12=F12, ex=-5000.0, ey=float(cy), level_sigma2=ls2, scale_factors=sf, intr=np.float32([fx, fy, cx, cy]), **out)
 
 
+GRID_KEYS = ("desc", "kp_xy", "octave", "angle")
+QUERY_KEYS = ("valid", "uv", "radius", "level", "desc", "angle")
+
+
+def pack_grid(prefix, g):
+    out = {prefix + k: np.asarray(g[k]) for k in GRID_KEYS}
+    out[prefix + "bounds"] = np.asarray(g["bounds"], np.float64); out[prefix + "cols_rows"] = np.array([g["cols"], g["rows"]], np.int32)
+    return out
+
+
+def pack_queries(prefix, q):
+    return {prefix + k: np.asarray(q[k]) for k in QUERY_KEYS if k in q}
+
+
+def golden_proj():
+    """projection-guided matchers: written only where the pure-Python witness (tests/witness_match.py) agrees"""
+    import witness_match as wm
+    from ccm_slam_b200 import synth_match as sm
+    g = sm.make_grid(n=400, seed=21); q = sm.make_queries(g, m=500, seed=22, th=4.0)
+    rng = np.random.default_rng(23)
+    has_obs = (rng.random(500) < 0.85).astype(np.uint8); blocked = (rng.random(400) < 0.2).astype(np.uint8)
+    existing = np.where(rng.random(500) < 0.15, rng.integers(0, 400, 500), -1).astype(np.int32)
+    out = {}
+    m, n = orc.search_by_projection_track(g, q, has_obs, blocked, 0.8); w, wn = wm.search_track(g, q, has_obs, blocked, 0.8)
+    assert n == wn and np.array_equal(m, w) and n > 100, "track vs witness"
+    out["track_match"] = m
+    for tag, reloc, od in (("last", False, 100), ("reloc", True, 64)):
+        m, n = orc.search_by_projection_frame(g, q, has_obs, blocked, reloc, od, True); w, wn = wm.search_frame(g, q, has_obs, blocked, reloc, od, True)
+        assert n == wn and np.array_equal(m, w) and n > 80, tag + " vs witness"
+        out[tag + "_match"] = m
+    b, m, n = orc.search_by_projection_sim3(g, q, blocked, existing); wb, w, wn = wm.search_sim3proj(g, q, blocked, existing)
+    assert n == wn and np.array_equal(b, wb) and np.array_equal(m, w), "sim3 projection vs witness"
+    out["sim3_best"] = b; out["sim3_match"] = m
+    for tag, wts in (("fuse_chi2", sm.INV_LEVEL_SIGMA2), ("fuse_plain", None)):
+        b, n = orc.fuse_search(g, q, wts); wb, wn = wm.fuse_search(g, q, wts)
+        assert n == wn and np.array_equal(b, wb), tag + " vs witness"
+        out[tag] = b
+    # SearchBySim3: two keyframes sharing half of their features
+    g1 = sm.make_grid(n=300, seed=24); g2 = sm.make_grid(n=320, seed=25)
+    share = rng.permutation(300)[:150]
+    g2["desc"][:150] = sm.flip_bits(g1["desc"][share], rng.integers(0, 30, 150), rng)
+    g2["kp_xy"][:150] = g1["kp_xy"][share] + rng.normal(0, 1.5, (150, 2)).astype(np.float32); g2["octave"][:150] = g1["octave"][share]
+
+    def queries(src_g, dst_g, ps, pd):
+        mm = src_g["desc"].shape[0]
+        uv = rng.uniform(0, 700, (mm, 2)).astype(np.float32); level = src_g["octave"].copy()
+        uv[ps] = dst_g["kp_xy"][pd] + rng.normal(0, 1.0, (len(ps), 2)).astype(np.float32)
+        return dict(valid=(rng.random(mm) < 0.8).astype(np.uint8), uv=uv, radius=(np.float32(7.5) * sm.SCALE_FACTORS[level]).astype(np.float32),
+                    level=level, desc=src_g["desc"], angle=np.zeros(mm, np.float32))
+    q12 = queries(g1, g2, share, np.arange(150)); q21 = queries(g2, g1, np.arange(150), share)
+    m, n = orc.search_by_sim3(g1, g2, q12, q21); w, wn = wm.search_by_sim3(g1, g2, q12, q21)
+    assert n == wn and np.array_equal(m, w) and n > 40, "SearchBySim3 vs witness"
+    save("proj_matchers.npz", has_obs=has_obs, blocked=blocked, existing=existing, inv_level_sigma2=sm.INV_LEVEL_SIGMA2, mutual_match12=m,
+         **pack_grid("g_", g), **pack_queries("q_", q), **pack_grid("g1_", g1), **pack_grid("g2_", g2), **pack_queries("q12_", q12),
+         **pack_queries("q21_", q21), **out)
+
+
+def golden_voc():
+    """DBoW2 transform on a small synthetic vocabulary; witness = tests/witness_match.voc_transform"""
+    import witness_match as wm
+    from ccm_slam_b200 import synth_match as sm
+    voc = sm.make_vocabulary(k=6, L=3, seed=31)
+    feat = sm.make_voc_features(voc, n=300, seed=32)
+    V = orc.Vocabulary(voc)
+    out = {}
+    for levelsup in (1, 2):
+        r = V.transform(feat, levelsup); w = wm.voc_transform(voc, feat, levelsup)
+        assert [(int(a), int(b), float(c)) for a, b, c in zip(r["word"], r["node"], r["weight"])] == w["per"], "descent vs witness"
+        assert list(r["bow_id"]) == w["bow_id"] and list(r["bow_val"]) == w["bow_val"], "BowVector vs witness"
+        assert list(r["fv_node_id"]) == list(w["fv"].keys())
+        for k2, v in r.items():
+            out["l%d_%s" % (levelsup, k2)] = v
+    V.close()
+    save("voc_k6_L3.npz", feat=feat, voc_k=voc["k"], voc_L=voc["L"], voc_scoring=voc["scoring"], voc_weighting=voc["weighting"],
+         voc_parent=voc["parent"], voc_is_leaf=voc["is_leaf"], voc_desc=voc["desc"], voc_weight=voc["weight"], **out)
+
+
+ALL = dict(known=golden_known_answers, ba_tiny=lambda: golden_ba("ba_tiny.npz", "tiny", 6), ba_small=lambda: golden_ba("ba_small.npz", "small", 8),
+           local_ba=golden_local_ba, pgo=golden_pgo, orb=golden_orb, match=golden_match, proj=golden_proj, voc=golden_voc)
+
 if __name__ == "__main__":
     orc.lib()
-    golden_known_answers()
-    golden_ba("ba_tiny.npz", "tiny", 6)
-    golden_ba("ba_small.npz", "small", 8)
-    golden_local_ba()
-    golden_pgo()
-    golden_orb()
-    golden_match()
+    for name in (sys.argv[1:] or list(ALL)):   # python tests/golden/make_golden.py [known ba_tiny ba_small local_ba pgo orb match proj voc]
+        ALL[name]()

@@ -50,6 +50,35 @@ def match_inputs(g, FV):
     return fv1, fv2, view(1, fv1), view(2, fv2)
 
 
+def unpack_grid(g, prefix):
+    b = g[prefix + "bounds"]; cr = g[prefix + "cols_rows"]
+    return dict(desc=g[prefix + "desc"], kp_xy=g[prefix + "kp_xy"], octave=g[prefix + "octave"], angle=g[prefix + "angle"],
+                bounds=tuple(float(v) for v in b), cols=int(cr[0]), rows=int(cr[1]))
+
+
+def unpack_queries(g, prefix):
+    return {k: g[prefix + k] for k in ("valid", "uv", "radius", "level", "desc", "angle")}
+
+
+def unpack_voc(g):
+    return dict(k=int(g["voc_k"]), L=int(g["voc_L"]), scoring=int(g["voc_scoring"]), weighting=int(g["voc_weighting"]), parent=g["voc_parent"],
+                is_leaf=g["voc_is_leaf"], desc=g["voc_desc"], weight=g["voc_weight"])
+
+
+def check_proj_fixture(g, M):
+    """M: object with the seven matcher calls (the oracle binding or the product's ORBmatcher adaptor) -> asserts the fixture outputs"""
+    G, Q = unpack_grid(g, "g_"), unpack_queries(g, "q_")
+    m, n = M.track(G, Q, g["has_obs"], g["blocked"], 0.8)
+    assert np.array_equal(m, g["track_match"]) and n >= int((g["track_match"] >= 0).sum())   # n also counts overwritten assignments
+    m, _ = M.frame(G, Q, g["has_obs"], g["blocked"], False, 100, True); assert np.array_equal(m, g["last_match"])
+    m, _ = M.frame(G, Q, g["has_obs"], g["blocked"], True, 64, True); assert np.array_equal(m, g["reloc_match"])
+    b, m, _ = M.sim3proj(G, Q, g["blocked"], g["existing"]); assert np.array_equal(b, g["sim3_best"]) and np.array_equal(m, g["sim3_match"])
+    b, _ = M.fuse(G, Q, g["inv_level_sigma2"]); assert np.array_equal(b, g["fuse_chi2"])
+    b, _ = M.fuse(G, Q, None); assert np.array_equal(b, g["fuse_plain"])
+    m, n = M.mutual(unpack_grid(g, "g1_"), unpack_grid(g, "g2_"), unpack_queries(g, "q12_"), unpack_queries(g, "q21_"))
+    assert np.array_equal(m, g["mutual_match12"]) and n == int((g["mutual_match12"] >= 0).sum())
+
+
 # ----------------------------------------------------------------------------------------------- CPU: oracle vs fixtures
 def test_oracle_reproduces_known_answers(oracle):
     g = load("known_answers.npz")
@@ -118,6 +147,46 @@ def gpu():
     assert api.device_count() > 0, "no CUDA device: the product path has no CPU fallback"
     api.init(0)
     return api
+
+
+def test_oracle_reproduces_proj_fixture(oracle):
+    class M:
+        track = staticmethod(oracle.search_by_projection_track)
+        frame = staticmethod(oracle.search_by_projection_frame)
+        sim3proj = staticmethod(oracle.search_by_projection_sim3)
+        fuse = staticmethod(oracle.fuse_search)
+        mutual = staticmethod(oracle.search_by_sim3)
+    check_proj_fixture(load("proj_matchers.npz"), M)
+
+
+def test_oracle_reproduces_voc_fixture(oracle):
+    g = load("voc_k6_L3.npz")
+    V = oracle.Vocabulary(unpack_voc(g))
+    for levelsup in (1, 2):
+        r = V.transform(g["feat"], levelsup)
+        for k, v in r.items():
+            assert np.array_equal(v, g["l%d_%s" % (levelsup, k)]), k
+    V.close()
+
+
+def test_library_host_halves_match_proj_and_voc_fixtures():
+    """the product's selection / container code (no device involved) on the fixtures, distances from numpy"""
+    from ccm_slam_b200.frontend import ORBmatcher, bow_assemble
+    dist = lambda q, gr: np.unpackbits(q["desc"][:, None, :] ^ gr["desc"][None, :, :], axis=2).sum(axis=2).astype(np.uint16)
+
+    class M:
+        track = staticmethod(lambda G, Q, ho, bl, nn: ORBmatcher(nn).SearchByProjection_Track(G, Q, ho, bl, D=dist(Q, G)))
+        frame = staticmethod(lambda G, Q, ho, bl, reloc, od, ori: ORBmatcher(0.9, ori).SearchByProjection_Frame(G, Q, ho, bl, reloc, od, D=dist(Q, G)))
+        sim3proj = staticmethod(lambda G, Q, fm, ex: ORBmatcher().SearchByProjection_Sim3(G, Q, fm, ex, D=dist(Q, G)))
+        fuse = staticmethod(lambda G, Q, w: ORBmatcher().Fuse(G, Q, w, D=dist(Q, G)))
+        mutual = staticmethod(lambda G1, G2, Q12, Q21: ORBmatcher().SearchBySim3(G1, G2, Q12, Q21, D12=dist(Q12, G2), D21=dist(Q21, G1)))
+    check_proj_fixture(load("proj_matchers.npz"), M)
+    g = load("voc_k6_L3.npz")
+    for levelsup in (1, 2):
+        pre = "l%d_" % levelsup
+        got = bow_assemble(int(g["voc_scoring"]), int(g["voc_weighting"]), g[pre + "word"], g[pre + "weight"], g[pre + "node"])
+        for k in ("bow_id", "bow_val", "fv_node_id", "fv_node_ptr", "fv_feat"):
+            assert np.array_equal(got[k], g[pre + k]), k
 
 
 def test_library_pose_conversions_match_fixture():

@@ -132,3 +132,23 @@ def test_voc_feeds_search_by_bow(oracle):
     ref, rn = oracle.match_bow_kf_frame(d1, has, k1["angle"], fv_of(oracle.FeatureVector, r1), d2, k2["angle"], fv_of(oracle.FeatureVector, r2), 0.7, True)
     assert n == rn and np.array_equal(got, ref) and n > 100
     V.close(); R.close()
+
+
+def test_gpu_matches_proj_and_voc_fixtures():
+    """the committed golden fixtures (tests/golden/proj_matchers.npz, voc_k6_L3.npz) through the C ABI, device distances / descent"""
+    from tests.test_golden import check_proj_fixture, load, unpack_voc
+
+    class M:
+        track = staticmethod(lambda G, Q, ho, bl, nn: ORBmatcher(nn).SearchByProjection_Track(G, Q, ho, bl))
+        frame = staticmethod(lambda G, Q, ho, bl, reloc, od, ori: ORBmatcher(0.9, ori).SearchByProjection_Frame(G, Q, ho, bl, reloc, od))
+        sim3proj = staticmethod(lambda G, Q, fm, ex: ORBmatcher().SearchByProjection_Sim3(G, Q, fm, ex))
+        fuse = staticmethod(lambda G, Q, w: ORBmatcher().Fuse(G, Q, w))
+        mutual = staticmethod(lambda G1, G2, Q12, Q21: ORBmatcher().SearchBySim3(G1, G2, Q12, Q21))
+    check_proj_fixture(load("proj_matchers.npz"), M)
+    g = load("voc_k6_L3.npz")
+    V = ORBVocabulary(unpack_voc(g))
+    for levelsup in (1, 2):
+        r = V.transform(g["feat"], levelsup)
+        for k, v in r.items():
+            assert np.array_equal(v, g["l%d_%s" % (levelsup, k)]), k
+    V.close()
