@@ -3,6 +3,7 @@
 //   ORBmatcher::SearchByProjection x4   S/ORBmatcher.cpp:71-148, 308-446, 1350-1476, 1478-1605
 //   ORBmatcher::Fuse x2                 S/ORBmatcher.cpp:854-993, 995-1122
 //   ORBmatcher::SearchBySim3            S/ORBmatcher.cpp:1124-1348
+//   ORBmatcher::SearchForInitialization S/ORBmatcher.cpp:448-563
 //   Frame/KeyFrame::GetFeaturesInArea   S/Frame.cpp:200-253, S/KeyFrame.cpp:1162-1201 (grid: Frame.cpp:103-119, 255-265)
 //
 // Device work: all (query, keypoint) descriptor distances in one k_hamming launch (match.cu) — the DescriptorDistance
@@ -265,6 +266,38 @@ void select_by_sim3(const ccm_feature_grid* g1, const ccm_feature_grid* g2, cons
   *nfound = found;
 }
 
+// SearchForInitialization (S/ORBmatcher.cpp:448-563): F1's octave-0 keypoints looked up around their previous match in F2
+void select_init(const ccm_feature_grid* g2, const ccm_proj_queries* q, const uint16_t* D, float nnratio, int check_orientation,
+                 int32_t* match12, int32_t* nmatches) {
+  check_grid(g2, "ccm_search_for_initialization"); check_queries(q, "ccm_search_for_initialization");
+  CCM_REQUIRE(match12 && nmatches && (D || !q->m || !g2->n), "ccm_search_for_initialization: null argument");
+  CCM_REQUIRE(!check_orientation || ((q->m == 0 || q->angle) && (g2->n == 0 || g2->angle)), "ccm_search_for_initialization: angles missing");
+  const CellIndex cells(*g2);
+  std::vector<int> holder(g2->n, -1), held_at(g2->n, INT_MAX);   // vnMatches21, vMatchedDistance
+  std::fill(match12, match12 + q->m, -1);
+  RotHist hist;
+  int found = 0;
+  for (int i = 0; i < q->m; i++) {
+    if (q->level[i] > 0) continue;
+    const uint16_t* row = D + (size_t)i * g2->n;
+    int d1 = INT_MAX, d2 = INT_MAX, j1 = -1;
+    cells.visit(q->uv[2 * i], q->uv[2 * i + 1], q->radius[i], q->level[i], q->level[i], [&](int j) {
+      const int d = row[j];
+      if (held_at[j] <= d) return;             // an earlier keypoint of F1 sits closer to this one
+      if (d < d1) { d2 = d1; d1 = d; j1 = j; }
+      else if (d < d2) d2 = d;
+    });
+    if (d1 > TH_LOW || !((float)d1 < (float)d2 * nnratio)) continue;
+    if (holder[j1] >= 0) { match12[holder[j1]] = -1; found--; }
+    match12[i] = j1; holder[j1] = i; held_at[j1] = d1;
+    found++;
+    if (check_orientation) hist.add(q->angle[i], g2->angle[j1], i);
+  }
+  if (check_orientation)
+    hist.prune([&](int i) { if (match12[i] >= 0) { match12[i] = -1; found--; } });   // an entry may have lost its match already
+  *nmatches = found;
+}
+
 const uint16_t* device_distances(const ccm_proj_queries* q, const ccm_feature_grid* g, const char* who) {
   check_grid(g, who); check_queries(q, who);
   return hamming_matrix_host(q->desc, q->m, g->desc, g->n);
@@ -332,6 +365,17 @@ int ccm_fuse_select(const ccm_feature_grid* g, const ccm_proj_queries* q, const 
 int ccm_fuse_search(const ccm_feature_grid* g, const ccm_proj_queries* q, const float* inv_level_sigma2, int32_t nlevels,
                     int32_t* best_idx, int32_t* nfound) {
   return guarded([&] { select_fuse(g, q, device_distances(q, g, "ccm_fuse_search"), inv_level_sigma2, nlevels, best_idx, nfound); });
+}
+
+int ccm_select_for_initialization(const ccm_feature_grid* g2, const ccm_proj_queries* q, const uint16_t* D, float nnratio,
+                                  int32_t check_orientation, int32_t* match12, int32_t* nmatches) {
+  return guarded([&] { select_init(g2, q, D, nnratio, check_orientation, match12, nmatches); });
+}
+int ccm_search_for_initialization(const ccm_feature_grid* g2, const ccm_proj_queries* q, float nnratio, int32_t check_orientation,
+                                  int32_t* match12, int32_t* nmatches) {
+  return guarded([&] {
+    select_init(g2, q, device_distances(q, g2, "ccm_search_for_initialization"), nnratio, check_orientation, match12, nmatches);
+  });
 }
 
 int ccm_select_by_sim3(const ccm_feature_grid* g1, const ccm_feature_grid* g2, const ccm_proj_queries* q12, const ccm_proj_queries* q21,

@@ -183,6 +183,18 @@ class ORBmatcher:
             _chk(lib().ccm_select_by_sim3(C.byref(G1), C.byref(G2), C.byref(Q12), C.byref(Q21), _p(D12), _p(D21), _p(out), C.byref(n)))
         return out, n.value
 
+    def SearchForInitialization(self, g2, q, D=None):
+        """SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize)  (:448-563) -> (vnMatches12, nmatches);
+        q: one query per keypoint of F1 (level = octave, uv = vbPrevMatched, radius = windowSize)."""
+        keep = []; G = grid_struct(g2, keep); Q = queries_struct(q, keep)
+        out = np.empty(Q.m, np.int32); n = C.c_int32()
+        if D is None:
+            _chk(lib().ccm_search_for_initialization(C.byref(G), C.byref(Q), C.c_float(self.nnratio), int(self.checkOri), _p(out), C.byref(n)))
+        else:
+            D = _dist(D, Q.m, G.n)
+            _chk(lib().ccm_select_for_initialization(C.byref(G), C.byref(Q), _p(D), C.c_float(self.nnratio), int(self.checkOri), _p(out), C.byref(n)))
+        return out, n.value
+
 
 class FeatureGridC(C.Structure):
     _fields_ = [("n", C.c_int32), ("desc", C.c_void_p), ("kp_xy", C.c_void_p), ("octave", C.c_void_p), ("angle", C.c_void_p),

@@ -108,3 +108,21 @@ def make_voc_features(voc, n=1000, seed=0):
     rnd = rng.random(n) < 0.1
     d[rnd] = rng.integers(0, 256, size=(int(rnd.sum()), 32), dtype=np.uint8)
     return d
+
+
+def make_init_pair(n=1000, seed=0, window=100.0, shift=(6.0, -4.0)):
+    """Two frames for SearchForInitialization: F2 holds shifted, slightly perturbed copies of most of F1's keypoints.  Returns
+    (grid of F2, queries = one per keypoint of F1 with level = its octave, uv = its own position (vbPrevMatched at the first call),
+    radius = windowSize)."""
+    rng = np.random.default_rng(seed)
+    g1 = make_grid(n=n, seed=seed + 100)
+    g1["octave"][: n // 2] = 0                      # the matcher only looks at octave 0
+    g2 = make_grid(n=n, seed=seed + 200)
+    keep = rng.permutation(n)[: (3 * n) // 4]
+    g2["kp_xy"][keep] = g1["kp_xy"][keep] + np.float32(shift) + rng.normal(0, 0.75, (len(keep), 2)).astype(np.float32)
+    g2["octave"][keep] = g1["octave"][keep]
+    g2["angle"][keep] = (g1["angle"][keep] + rng.normal(0, 3.0, len(keep))).astype(np.float32) % np.float32(360)
+    g2["desc"][keep] = flip_bits(g1["desc"][keep], rng.integers(0, 45, len(keep)), rng)
+    q = dict(valid=np.ones(n, np.uint8), uv=g1["kp_xy"].copy(), radius=np.full(n, window, np.float32), level=g1["octave"].copy(),
+             desc=g1["desc"], angle=g1["angle"])
+    return g2, q

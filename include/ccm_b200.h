@@ -411,6 +411,15 @@ int ccm_search_by_sim3(const ccm_feature_grid* g1, const ccm_feature_grid* g2, c
 int ccm_select_by_sim3(const ccm_feature_grid* g1, const ccm_feature_grid* g2, const ccm_proj_queries* q12, const ccm_proj_queries* q21,
                        const uint16_t* D12 /*q12->m x g2->n*/, const uint16_t* D21 /*q21->m x g1->n*/, int32_t* match12, int32_t* nfound);
 
+/* SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize)  (ORBmatcher.cpp:448-563): one query per keypoint of F1
+ * (level = its octave: only octave 0 is searched, uv = vbPrevMatched[i1], radius = windowSize), looked up in F2's grid; a keypoint of
+ * F2 stays with the closest F1 keypoint (vMatchedDistance), ratio test, rotation histogram.  match12[i1] = i2 or -1; the shim
+ * refreshes vbPrevMatched from it (:557-560). */
+int ccm_search_for_initialization(const ccm_feature_grid* g2, const ccm_proj_queries* q, float nnratio, int32_t check_orientation,
+                                  int32_t* match12 /*q->m*/, int32_t* nmatches);
+int ccm_select_for_initialization(const ccm_feature_grid* g2, const ccm_proj_queries* q, const uint16_t* D, float nnratio,
+                                  int32_t check_orientation, int32_t* match12, int32_t* nmatches);
+
 /* ---- DBoW2 transform ------------------------------------------------------------
  * Replaces ORBVocabulary::transform(features, BowVector&, FeatureVector&, levelsup) as called by Frame::ComputeBoW
  * (cslam/src/Frame.cpp:268-275) and KeyFrame::ComputeBoW (KeyFrame.cpp:277-286): the tree descent of every descriptor

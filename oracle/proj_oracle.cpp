@@ -10,6 +10,7 @@
 //   ORBmatcher::SearchBySim3                                             S/ORBmatcher.cpp:1124-1348
 //   ORBmatcher::SearchByProjection(Frame&, const Frame& LastFrame, th)   S/ORBmatcher.cpp:1350-1476 ("last")
 //   ORBmatcher::SearchByProjection(Frame&, kfptr, sAlreadyFound, th, d)  S/ORBmatcher.cpp:1478-1605 ("reloc")
+//   ORBmatcher::SearchForInitialization                                  S/ORBmatcher.cpp:448-563
 // Everything BEFORE GetFeaturesInArea in those functions (isBad, the cv::Mat projection, IsInImage, the distance /
 // viewing-angle gates, PredictScale) is the caller's prelude: it is f32 cv::Mat arithmetic whose rounding belongs to
 // OpenCV, it is O(#points), and the drop-in shim keeps it verbatim in the reference's own types.  A query arrives as
@@ -311,6 +312,50 @@ int orc_search_by_sim3(const orc_grid* g1, const orc_grid* g2, const orc_queries
     }
   }
   return nFound;
+}
+
+// S/ORBmatcher.cpp:448-563 (monocular initialisation).  Queries = the keypoints of F1 (q.level = their octave, q.uv =
+// vbPrevMatched, q.radius = windowSize), searched in F2's grid at octave 0 only; a keypoint of F2 goes to the closest F1 keypoint
+// seen so far (vMatchedDistance), an earlier holder loses it.  match12[i1] = i2 or -1.
+int orc_search_for_initialization(const orc_grid* g2, const orc_queries* q, float nnratio, int32_t check_orientation, int32_t* match12) {
+  Grid G(*g2);
+  int nmatches = 0;
+  std::vector<int> vnMatches12(q->m, -1), vnMatches21(g2->n, -1), vMatchedDistance(g2->n, INT_MAX);
+  std::vector<int> rotHist[HISTO_LENGTH];
+  for (int i1 = 0; i1 < q->m; i1++) {
+    const int level1 = q->level[i1];
+    if (level1 > 0) continue;
+    const std::vector<int> vIndices2 = G.in_area(q->uv[2 * i1], q->uv[2 * i1 + 1], q->radius[i1], level1, level1);
+    if (vIndices2.empty()) continue;
+    int bestDist = INT_MAX, bestDist2 = INT_MAX, bestIdx2 = -1;
+    for (int i2 : vIndices2) {
+      const int dist = descriptor_distance(q->desc + 32 * (size_t)i1, g2->desc + 32 * (size_t)i2);
+      if (vMatchedDistance[i2] <= dist) continue;
+      if (dist < bestDist) { bestDist2 = bestDist; bestDist = dist; bestIdx2 = i2; }
+      else if (dist < bestDist2) bestDist2 = dist;
+    }
+    if (bestDist <= TH_LOW) {
+      if (bestDist < (float)bestDist2 * nnratio) {
+        if (vnMatches21[bestIdx2] >= 0) { vnMatches12[vnMatches21[bestIdx2]] = -1; nmatches--; }
+        vnMatches12[i1] = bestIdx2;
+        vnMatches21[bestIdx2] = i1;
+        vMatchedDistance[bestIdx2] = bestDist;
+        nmatches++;
+        if (check_orientation) rotHist[rot_bin(q->angle[i1], g2->angle[bestIdx2])].push_back(i1);
+      }
+    }
+  }
+  if (check_orientation) {
+    int ind1 = -1, ind2 = -1, ind3 = -1;
+    three_maxima(rotHist, HISTO_LENGTH, ind1, ind2, ind3);
+    for (int i = 0; i < HISTO_LENGTH; i++) {
+      if (i == ind1 || i == ind2 || i == ind3) continue;
+      for (int idx1 : rotHist[i])
+        if (vnMatches12[idx1] >= 0) { vnMatches12[idx1] = -1; nmatches--; }
+    }
+  }
+  for (int i1 = 0; i1 < q->m; i1++) match12[i1] = vnMatches12[i1];
+  return nmatches;
 }
 
 }  // extern "C"

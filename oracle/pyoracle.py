@@ -414,6 +414,13 @@ def search_by_sim3(g1, g2, q12, q21):
     return out, n
 
 
+def search_for_initialization(g2, q, nnratio=0.9, check_ori=True):
+    keep = []; G = grid_struct(g2, keep); Q = queries_struct(q, keep)
+    out = np.empty(Q.m, np.int32)
+    n = lib().orc_search_for_initialization(C.byref(G), C.byref(Q), C.c_float(nnratio), int(check_ori), _p(out))
+    return out, n
+
+
 class Vocabulary:
     """v = dict(k, L, scoring, weighting, parent, is_leaf, desc, weight) with row 0 = root (ccm_slam_b200.synth.make_vocabulary)."""
 

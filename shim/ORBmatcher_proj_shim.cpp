@@ -1,6 +1,7 @@
 // ORBmatcher_proj_shim.cpp — the projection-guided overloads of cslam::ORBmatcher on top of libccm_b200.so
 // (SURVEY.md §8(f) rank 3).  Replaces, in cslam/src/ORBmatcher.cpp:
 //   SearchByProjection(Frame&, const vector<mpptr>&, th)                        :71-148
+//   SearchForInitialization(F1, F2, vbPrevMatched, vnMatches12, windowSize)     :448-563
 //   SearchByProjection(kfptr, cv::Mat Scw, vpPoints, vpMatched, th)             :308-446
 //   Fuse(kfptr, const vector<mpptr>&, th)                                       :854-993
 //   Fuse(kfptr, cv::Mat Scw, vpPoints, th, vpReplacePoint)                      :995-1122
@@ -103,6 +104,25 @@ inline Sim3Split split_sim3(const cv::Mat& Scw) {                  // S/ORBmatch
 }
 
 }  // namespace
+
+// ---- monocular initialisation -------------------------------------------------------------------------------------------
+int ORBmatcher::SearchForInitialization(Frame& F1, Frame& F2, std::vector<cv::Point2f>& vbPrevMatched, std::vector<int>& vnMatches12,
+                                        int windowSize) {                                                 // :448-563
+  const size_t n1 = F1.mvKeysUn.size();
+  Queries q(n1);
+  for (size_t i1 = 0; i1 < n1; i1++)   // the library skips octaves > 0 itself (:466-468)
+    q.set(i1, vbPrevMatched[i1].x, vbPrevMatched[i1].y, (float)windowSize, F1.mvKeysUn[i1].octave, F1.mDescriptors.row((int)i1),
+          F1.mvKeysUn[i1].angle);
+  auto G2 = grid_of(F2);
+  ccm_proj_queries cq = q.c();
+  std::vector<int32_t> m12(n1);
+  int32_t n = 0;
+  must(ccm_search_for_initialization(&G2.g, &cq, mfNNratio, mbCheckOrientation, m12.data(), &n));
+  vnMatches12.assign(m12.begin(), m12.end());
+  for (size_t i1 = 0; i1 < n1; i1++)
+    if (vnMatches12[i1] >= 0) vbPrevMatched[i1] = F2.mvKeysUn[vnMatches12[i1]].pt;                      // :557-560
+  return n;
+}
 
 // ---- tracking the local map ---------------------------------------------------------------------------------------------
 int ORBmatcher::SearchByProjection(Frame& F, const std::vector<mpptr>& vpMapPoints, const float th) {   // :71-148

@@ -69,6 +69,14 @@ def test_search_by_sim3_mutual(oracle):
     assert n == rn and np.array_equal(got, ref) and n > 150
 
 
+def test_search_for_initialization(oracle):
+    g2, q = sm.make_init_pair(n=1500, seed=5)
+    for nnratio, ori in [(0.9, True), (0.7, False)]:
+        got, n = ORBmatcher(nnratio, ori).SearchForInitialization(g2, q)
+        ref, rn = oracle.search_for_initialization(g2, q, nnratio, ori)
+        assert n == rn and np.array_equal(got, ref) and n > 150
+
+
 def test_projection_matchers_on_extracted_frames(oracle):
     """End to end on real extractor output: frame b is frame a shifted by (5, 3) px; every keypoint of a is 'projected' to its
     shifted position and searched for in b's grid."""

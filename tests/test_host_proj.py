@@ -1,6 +1,6 @@
 """CPU suite, host logic of the product for SURVEY.md §8(f) ranks 2-3: the selection half of every projection-guided matcher
 (ccm_select_*, fed a numpy distance matrix), GetFeaturesInArea and the BowVector / FeatureVector assembly, against the oracle.
-No device work is involved (the device half — k_hamming, k_voc_descend — is covered by tests/test_gpu_next.py)."""
+No device work is involved (the device half — k_hamming, k_voc_descend — is covered by tests/test_gpu_widen.py)."""
 import numpy as np
 import pytest
 
@@ -85,6 +85,14 @@ def test_select_by_sim3(oracle):
     q12 = queries(g1, g2, share, np.arange(500)); q21 = queries(g2, g1, np.arange(500), share)
     got, n = ORBmatcher().SearchBySim3(g1, g2, q12, q21, D12=dist(q12, g2), D21=dist(q21, g1))
     ref, rn = oracle.search_by_sim3(g1, g2, q12, q21)
+    assert n == rn and np.array_equal(got, ref) and n > 150
+
+
+@pytest.mark.parametrize("nnratio,ori", [(0.9, True), (0.7, False)])
+def test_select_for_initialization(oracle, nnratio, ori):
+    g2, q = sm.make_init_pair(n=1500, seed=5)
+    got, n = ORBmatcher(nnratio, ori).SearchForInitialization(g2, q, D=dist(q, g2))
+    ref, rn = oracle.search_for_initialization(g2, q, nnratio, ori)
     assert n == rn and np.array_equal(got, ref) and n > 150
 
 

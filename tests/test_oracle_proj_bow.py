@@ -98,6 +98,18 @@ def test_search_by_sim3_mutual(oracle):
     assert n == rn and np.array_equal(got, ref) and n > 60
 
 
+@pytest.mark.parametrize("nnratio,ori", [(0.9, True), (0.7, False)])
+def test_search_for_initialization(oracle, nnratio, ori):
+    g2, q = sm.make_init_pair(n=500, seed=3)
+    got, n = oracle.search_for_initialization(g2, q, nnratio, ori)
+    ref, rn = wm.search_init(g2, q, nnratio, ori)
+    assert n == rn and np.array_equal(got, ref) and n > 60
+    assert (got[q["level"] > 0] == -1).all()                    # only octave-0 keypoints of F1 are searched
+    hit = got[got >= 0]
+    assert len(np.unique(hit)) == len(hit)                      # a keypoint of F2 stays with one keypoint of F1
+    assert (g2["octave"][hit] == 0).all()
+
+
 @pytest.mark.parametrize("scoring,weighting,levelsup", [(0, 0, 1), (0, 0, 4), (1, 1, 2), (5, 0, 1), (2, 2, 0), (0, 3, 1)])
 def test_voc_transform(oracle, scoring, weighting, levelsup):
     voc = sm.make_vocabulary(k=6, L=3, seed=11, scoring=scoring, weighting=weighting)

@@ -185,6 +185,35 @@ def search_by_sim3(g1, g2, q12, q21):
     return out, int((out >= 0).sum())
 
 
+def search_init(g2, q, nnratio, check_ori):
+    G = GridW(g2); D = hamming(np.asarray(q["desc"]), np.asarray(g2["desc"]))
+    m12 = np.full(len(q["valid"]), -1, np.int64); holder = {}; held = {}; n = 0
+    hist = [[] for _ in range(HISTO_LENGTH)]
+    for i in range(len(m12)):
+        if q["level"][i] > 0:
+            continue
+        cand = [(int(D[i, j]), j) for j in G.in_area(q["uv"][i, 0], q["uv"][i, 1], q["radius"][i], 0, 0) if held.get(j, 1 << 30) > int(D[i, j])]
+        if not cand:
+            continue
+        order = sorted(range(len(cand)), key=lambda k: (cand[k][0], k))     # stable: first minimum first
+        d1, j1 = cand[order[0]]
+        d2 = cand[order[1]][0] if len(cand) > 1 else (1 << 31) - 1
+        if d1 <= TH_LOW and f32(d1) < f32(f32(d2) * f32(nnratio)):
+            if j1 in holder:
+                m12[holder[j1]] = -1; n -= 1
+            m12[i] = j1; holder[j1] = i; held[j1] = d1; n += 1
+            if check_ori:
+                hist[_rot_bin(q["angle"][i], g2["angle"][j1])].append(i)
+    if check_ori:
+        keep = _three_maxima([len(h) for h in hist])
+        for b in range(HISTO_LENGTH):
+            if b not in keep:
+                for i in hist[b]:
+                    if m12[i] >= 0:
+                        m12[i] = -1; n -= 1
+    return m12, n
+
+
 # ---- DBoW2 transform ----------------------------------------------------------------------------------------------
 def voc_transform(voc, feat, levelsup):
     """D/TemplatedVocabulary.h:1127-1192, 1219-1260 with python containers (dict of children lists, dict accumulators)."""
