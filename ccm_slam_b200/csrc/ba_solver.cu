@@ -246,7 +246,7 @@ int schur_mode() {
     if (!strcmp(v, "gather") || !strcmp(v, "0")) return 0;
     if (!strcmp(v, "mma")) return 1;
     const int m = atoi(v);
-    return (m >= 0 && m <= 5) ? m : 1;
+    return (m >= 0 && m <= 7) ? m : 1;
   }();
   const int o = g_schur_override.load(std::memory_order_relaxed);
   return o >= 0 ? o : env_mode;
@@ -270,6 +270,8 @@ void launch_schur(ccm_ba_handle* h, cudaStream_t s) {
     case 3: launch_schur_mma<4, 256>(h, s); break;
     case 4: launch_schur_mma<8, 256>(h, s); break;
     case 5: launch_schur_mma<8, 512>(h, s); break;
+    case 6: launch_schur_mma<8, 64>(h, s); break;     // not yet measured: fewer warps share a CTA's lifetime (lists differ in length)
+    case 7: launch_schur_mma<16, 128>(h, s); break;   // not yet measured
     default: launch_schur_mma<8, 128>(h, s); break;
   }
 }
@@ -1119,7 +1121,7 @@ extern "C" int ccm_ba_debug_schur(ccm_ba_handle* h, int robust, double huber_del
 
 extern "C" int ccm_ba_debug_set_schur_mode(int mode) {
   return guarded([&] {
-    CCM_REQUIRE(mode >= -1 && mode <= 5, "ccm_ba_debug_set_schur_mode: -1 (CCM_SCHUR / default), 0 gather, 1 mma, 2..5 mma launch shapes");
+    CCM_REQUIRE(mode >= -1 && mode <= 7, "ccm_ba_debug_set_schur_mode: -1 (CCM_SCHUR / default), 0 gather, 1 mma, 2..7 mma launch shapes");
     g_schur_override.store(mode);
   });
 }

@@ -1,0 +1,96 @@
+"""Property tests of the oracle (hypothesis; CPU suite): the size-independent laws SURVEY.md §8(c) lists — group laws of the Lie
+maps, Hamming metric axioms, monotonicity of the window lookup, order invariances of the BoW containers and of the matchers."""
+import numpy as np
+import pytest
+from hypothesis import given, settings, strategies as st
+
+from ccm_slam_b200 import synth_match as sm
+
+FAST = settings(max_examples=25, deadline=None)
+vec = lambda n, lo, hi: st.lists(st.floats(lo, hi, allow_nan=False, width=64), min_size=n, max_size=n).map(np.array)
+
+
+@FAST
+@given(vec(6, -1.5, 1.5))
+def test_se3_exp_inverse_and_unit_quaternion(oracle, u):
+    if np.linalg.norm(u[:3]) < 1e-4:
+        u = u + np.array([0.01, 0, 0, 0, 0, 0])
+    a, b = oracle.se3_exp(u), oracle.se3_exp(-u)
+    assert abs(np.linalg.norm(a[:4]) - 1.0) < 1e-12
+    prod = oracle.se3_mul(a, b)
+    assert np.abs(prod[:3]).max() < 1e-10 and abs(abs(prod[3]) - 1.0) < 1e-10 and np.abs(prod[4:]).max() < 1e-9
+
+
+@FAST
+@given(vec(7, -0.8, 0.8), vec(7, -0.8, 0.8), vec(7, -0.8, 0.8))
+def test_sim3_group_laws(oracle, u, v, w):
+    a, b, c = oracle.sim3_exp(u), oracle.sim3_exp(v), oracle.sim3_exp(w)
+    assert np.abs(oracle.sim3_log(a) - u).max() < 1e-8
+    assert np.abs(oracle.sim3_inv(oracle.sim3_inv(a)) - a).max() < 1e-12
+    l = oracle.sim3_mul(oracle.sim3_mul(a, b), c); r = oracle.sim3_mul(a, oracle.sim3_mul(b, c))
+    assert np.abs(l - r).max() < 1e-9
+    e = oracle.sim3_mul(a, oracle.sim3_inv(a))
+    assert np.abs(e[:3]).max() < 1e-10 and np.abs(e[4:7]).max() < 1e-9 and abs(e[7] - 1.0) < 1e-10
+
+
+desc = st.binary(min_size=32, max_size=32).map(lambda b: np.frombuffer(b, np.uint8))
+
+
+@FAST
+@given(desc, desc, desc)
+def test_hamming_is_a_metric(oracle, a, b, c):
+    d = oracle.descriptor_distance
+    assert d(a, a) == 0 and d(a, b) == d(b, a) and 0 <= d(a, b) <= 256
+    assert d(a, c) <= d(a, b) + d(b, c)
+    assert d(a, np.bitwise_not(a)) == 256
+    assert d(a, b) == int(np.unpackbits(a ^ b).sum())
+
+
+@FAST
+@given(st.integers(0, 10_000), st.floats(0.5, 60.0), st.floats(1.0, 3.0))
+def test_window_lookup_grows_with_the_radius_and_keeps_its_order(oracle, seed, r, factor):
+    g = sm.make_grid(n=300, seed=seed % 7)
+    rng = np.random.default_rng(seed)
+    x, y = g["kp_xy"][int(rng.integers(0, 300))] + rng.normal(0, 5, 2).astype(np.float32)
+    small = list(oracle.features_in_area(g, x, y, r)); big = list(oracle.features_in_area(g, x, y, r * factor))
+    assert set(small) <= set(big)
+    it = iter(big)
+    assert all(j in it for j in small)            # `small` is a subsequence of `big`: the visiting order does not depend on r
+
+
+@FAST
+@given(st.integers(0, 10_000))
+def test_bow_containers_do_not_depend_on_the_feature_order(oracle, seed):
+    voc = sm.make_vocabulary(k=5, L=3, seed=3)
+    feat = sm.make_voc_features(voc, n=120, seed=4)
+    perm = np.random.default_rng(seed).permutation(120)
+    V = oracle.Vocabulary(voc)
+    a, b = V.transform(feat, 1), V.transform(feat[perm], 1)
+    V.close()
+    assert np.array_equal(a["word"][perm], b["word"]) and np.array_equal(a["node"][perm], b["node"])
+    assert np.array_equal(a["bow_id"], b["bow_id"]) and np.allclose(a["bow_val"], b["bow_val"], rtol=1e-12, atol=0)
+    assert np.array_equal(a["fv_node_id"], b["fv_node_id"])
+    for k in range(len(a["fv_node_id"])):             # same feature sets per node (as original indices)
+        sa = set(a["fv_feat"][a["fv_node_ptr"][k]:a["fv_node_ptr"][k + 1]].tolist())
+        sb = set(perm[b["fv_feat"][b["fv_node_ptr"][k]:b["fv_node_ptr"][k + 1]]].tolist())
+        assert sa == sb
+
+
+@FAST
+@given(st.integers(0, 10_000))
+def test_invalid_queries_are_inert(oracle, seed):
+    g = sm.make_grid(n=250, seed=1); q = sm.make_queries(g, m=200, seed=2)
+    rng = np.random.default_rng(seed)
+    ones = np.ones(200, np.uint8); none = np.zeros(250, np.uint8)
+    ref, n = oracle.fuse_search(g, q, sm.INV_LEVEL_SIGMA2)
+    # switching queries off removes exactly their results: the search of one query never depends on another
+    off = rng.random(200) < 0.3
+    q2 = dict(q, valid=np.where(off, 0, q["valid"]).astype(np.uint8))
+    got, n2 = oracle.fuse_search(g, q2, sm.INV_LEVEL_SIGMA2)
+    assert np.array_equal(got[~off], ref[~off]) and (got[off] == -1).all()
+    # in the greedy matchers an invalid query takes nothing: appending invalid queries changes no assignment
+    m, cnt = oracle.search_by_projection_track(g, q, ones, none, 0.8)
+    q3 = {k: np.concatenate([v, v[:50]]) for k, v in q.items()}
+    q3["valid"][200:] = 0
+    m3, cnt3 = oracle.search_by_projection_track(g, q3, np.ones(250, np.uint8), none, 0.8)
+    assert cnt == cnt3 and np.array_equal(m, m3)
