@@ -394,7 +394,7 @@ __device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, doubl
                : "d"(a), "d"(b));
 }
 
-template <int UNROLL, int CTA>
+template <int UNROLL, int CTA, bool PIPE = false>
 __global__ void __launch_bounds__(CTA) k_schur_mma(const uint2* __restrict__ prod, const unsigned* __restrict__ u_prod_ptr,
                                                    const int* __restrict__ u_row, const int* __restrict__ u_col, int nub,
                                                    const double* __restrict__ Z, const int* __restrict__ o_lm,
@@ -412,7 +412,41 @@ __global__ void __launch_bounds__(CTA) k_schur_mma(const uint2* __restrict__ pro
   const bool diag = row == u_col[warp];
   double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
   unsigned p = beg;
-  if (!diag) {
+  if (!diag && PIPE) {
+    // software-pipelined form (not yet measured): the product entries of batch k+1 are requested before the rows of batch k,
+    // so the entry -> row dependence costs one memory latency per batch instead of two
+    uint2 nx[UNROLL];
+    if (p + UNROLL <= end) {
+#pragma unroll
+      for (int j = 0; j < UNROLL; j++) nx[j] = prod[p + j];
+    }
+    for (; p + UNROLL <= end; p += UNROLL) {
+      uint2 pr[UNROLL];
+#pragma unroll
+      for (int j = 0; j < UNROLL; j++) pr[j] = nx[j];
+      if (p + 2 * UNROLL <= end) {
+#pragma unroll
+        for (int j = 0; j < UNROLL; j++) nx[j] = prod[p + UNROLL + j];
+      }
+      double a[UNROLL], b[UNROLL];
+#pragma unroll
+      for (int j = 0; j < UNROLL; j++) {
+        a[j] = Z[(size_t)pr[j].x * 18 + off];
+        b[j] = Z[(size_t)pr[j].y * 18 + off];
+      }
+#pragma unroll
+      for (int j = 0; j < UNROLL; j += 2) {
+        dmma_884(c00, c01, ld ? a[j] : 0.0, ld ? b[j] : 0.0);
+        dmma_884(c10, c11, ld ? a[j + 1] : 0.0, ld ? b[j + 1] : 0.0);
+      }
+    }
+    for (; p < end; p++) {
+      const uint2 pr = prod[p];
+      const double a = Z[(size_t)pr.x * 18 + off], b = Z[(size_t)pr.y * 18 + off];
+      if ((p - beg) & 1u) dmma_884(c10, c11, ld ? a : 0.0, ld ? b : 0.0);
+      else dmma_884(c00, c01, ld ? a : 0.0, ld ? b : 0.0);
+    }
+  } else if (!diag) {
     for (; p + UNROLL <= end; p += UNROLL) {
       uint2 pr[UNROLL];
 #pragma unroll

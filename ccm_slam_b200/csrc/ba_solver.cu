@@ -246,15 +246,15 @@ int schur_mode() {
     if (!strcmp(v, "gather") || !strcmp(v, "0")) return 0;
     if (!strcmp(v, "mma")) return 1;
     const int m = atoi(v);
-    return (m >= 0 && m <= 7) ? m : 1;
+    return (m >= 0 && m <= 8) ? m : 1;
   }();
   const int o = g_schur_override.load(std::memory_order_relaxed);
   return o >= 0 ? o : env_mode;
 }
 
-template <int UNROLL, int CTA>
+template <int UNROLL, int CTA, bool PIPE = false>
 void launch_schur_mma(ccm_ba_handle* h, cudaStream_t s) {
-  k_schur_mma<UNROLL, CTA><<<div_up((long long)h->nub * 32, CTA), CTA, 0, s>>>(h->prod.p, h->u_prod_ptr.p, h->u_row.p, h->u_col.p, h->nub,
+  k_schur_mma<UNROLL, CTA, PIPE><<<div_up((long long)h->nub * 32, CTA), CTA, 0, s>>>(h->prod.p, h->u_prod_ptr.p, h->u_row.p, h->u_col.p, h->nub,
                                                                               h->Z.p, h->o_lm.p, h->gvec.p, h->U_val(), h->bneg());
 }
 
@@ -272,6 +272,7 @@ void launch_schur(ccm_ba_handle* h, cudaStream_t s) {
     case 5: launch_schur_mma<8, 512>(h, s); break;
     case 6: launch_schur_mma<8, 64>(h, s); break;     // not yet measured: fewer warps share a CTA's lifetime (lists differ in length)
     case 7: launch_schur_mma<16, 128>(h, s); break;   // not yet measured
+    case 8: launch_schur_mma<8, 128, true>(h, s); break;   // not yet measured: product entries prefetched one batch ahead
     default: launch_schur_mma<8, 128>(h, s); break;
   }
 }
@@ -1121,7 +1122,7 @@ extern "C" int ccm_ba_debug_schur(ccm_ba_handle* h, int robust, double huber_del
 
 extern "C" int ccm_ba_debug_set_schur_mode(int mode) {
   return guarded([&] {
-    CCM_REQUIRE(mode >= -1 && mode <= 7, "ccm_ba_debug_set_schur_mode: -1 (CCM_SCHUR / default), 0 gather, 1 mma, 2..7 mma launch shapes");
+    CCM_REQUIRE(mode >= -1 && mode <= 8, "ccm_ba_debug_set_schur_mode: -1 (CCM_SCHUR / default), 0 gather, 1 mma, 2..8 mma variants");
     g_schur_override.store(mode);
   });
 }

@@ -164,7 +164,7 @@ int ccm_ba_debug_schur(ccm_ba_handle* h, int robust, double huber_delta, double 
                        double* S_dense /*(6K)^2 or NULL*/, double* bschur /*6K or NULL*/,
                        double* dx_pose /*K*6*/, double* dx_point /*P*3*/, int32_t* pcg_iters, double* pcg_relres);
 /* developer hook: pick the Schur-product kernel for every handle of this process: 0 = gather form (k_schur), 1 = tensor-core
- * form (k_schur_mma, one f64 mma.sync per product; the default), 2..7 = launch-shape variants of it (unroll 16 / 4, CTA 64 / 256 / 512; the default is unroll 8, CTA 128),
+ * form (k_schur_mma, one f64 mma.sync per product; the default), 2..8 = variants of it (unroll 16 / 4, CTA 64 / 256 / 512, entry prefetch; the default is unroll 8, CTA 128),
  * -1 = back to the CCM_SCHUR environment variable / built-in default */
 int ccm_ba_debug_set_schur_mode(int mode);
 /* time `reps` launches of one kernel with CUDA events on the handle's stream; returns mean ms per launch.

@@ -17,9 +17,9 @@ info = h.info()
 if capture:
     print("capture run:", h.time_kernel(4, reps=2, lam=1e-3), "ms")
     sys.exit(0)
-labels = {0: "gather", 1: "mma u8 cta128 (default)", 2: "mma u16 cta256", 3: "mma u4 cta256", 4: "mma u8 cta256", 5: "mma u8 cta512", 6: "mma u8 cta64", 7: "mma u16 cta128"}
+labels = {0: "gather", 1: "mma u8 cta128 (default)", 2: "mma u16 cta256", 3: "mma u4 cta256", 4: "mma u8 cta256", 5: "mma u8 cta512", 6: "mma u8 cta64", 7: "mma u16 cta128", 8: "mma u8 cta128 prefetch"}
 out = {"config": name, "schur_products": int(info["schur_products"]), "upper_blocks": int(info["s_blocks_upper"]), "ms_per_launch": {}}
-for mode in (1, 0, 2, 3, 4, 5, 6, 7, 1):
+for mode in (1, 0, 2, 3, 4, 5, 6, 7, 8, 1):
     api._chk(api.lib().ccm_ba_debug_set_schur_mode(mode))
     ms = h.time_kernel(4, reps=5, lam=1e-3)
     out["ms_per_launch"].setdefault(labels[mode], []).append(round(ms, 4))
