@@ -81,7 +81,7 @@ struct ccm_ba_handle {
   DevBuf<long long> pcg_prof;  // allocated only with CCM_PCG_PROF=1
   DevBuf<int> jac_fail;
   int pcg_grid = 0, pcg_block = 256, pcg_last_mode = 1;
-  // row-distributed PCG over peer memory (pcg_dist.cuh): only with CCM_PCG_DIST=1 and nranks > 1
+  // row-distributed PCG over peer memory (pcg_dist.cuh): only with CCM_PCG_DIST=1
   struct DistPcg {
     bool on = false;
     PcgDistLayout lay{};
@@ -342,10 +342,12 @@ void step_pcg(ccm_ba_handle* h, double tol, int max_iter) {
   CCM_LAUNCHED();
 }
 
-// CCM_PCG_DIST=1 and nranks > 1: exchange windows, peer mappings and the row cut of the distributed PCG (pcg_dist.cuh).
+// CCM_PCG_DIST=1: exchange windows, peer mappings and the row cut of the distributed PCG (pcg_dist.cuh).
 // The 64-byte IPC handles travel through the existing all-reduce, one double per byte (exact: each slot has one writer).
 void setup_pcg_dist(ccm_ba_handle* h) {
-  if (h->nranks <= 1 || !env_int("CCM_PCG_DIST", 0) || h->Kf < h->nranks) return;
+  // nranks == 1 is allowed on purpose: the kernel then talks to its own window only, which exercises everything but the NVLink
+  // hop on a single GPU (cheap first validation)
+  if (!env_int("CCM_PCG_DIST", 0) || h->Kf < h->nranks || h->Kf < 1) return;
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   ccm_ba_handle::DistPcg& d = h->dist;
   cudaStream_t s = h->stream;

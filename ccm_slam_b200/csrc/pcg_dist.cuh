@@ -1,7 +1,8 @@
 // pcg_dist.cuh — the PCG of pcg.cuh with its block rows distributed over the ranks of one NVLink/NVSwitch node.
 //
 // STATUS: written after the round-1 GPU budget was spent; it has never run on a device.  It is reachable only with
-// CCM_PCG_DIST=1 and nranks > 1; the default multi-rank path is the replicated k_pcg.
+// CCM_PCG_DIST=1 (with one rank it talks to its own window: a single-GPU dry run of everything but the NVLink hop); the default
+// multi-rank path is the replicated k_pcg.
 //
 // Why: with landmarks sharded everything but the reduced-camera solve scales with the number of GPUs; the
 // replicated solve is 62 % of the single-GPU step and caps the 1 -> 8 speed-up at 1.6x.  Distributing the solve through NCCL
