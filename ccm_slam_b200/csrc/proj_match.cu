@@ -10,7 +10,8 @@
 // calls of every window at once; a query's row is m*n*2 bytes back over PCIe, small next to the per-window pointer chasing
 // it replaces.  Host work: the lookup grid as a CSR over cells (counting sort in feature order == push_back order), the
 // window walk in the reference's visiting order and the order-dependent choice.  ccm_select_* run the host half on a
-// caller-supplied matrix and need no device.
+// caller-supplied matrix and need no device.  CCM_MATCH_WINDOW=1 (not yet run on a device) keeps the order-independent choices
+// (Fuse x2, SearchBySim3) on the device: k_window_best, m indices back instead of an m x n matrix.
 #include <climits>
 #include <cmath>
 
@@ -298,6 +299,117 @@ void select_init(const ccm_feature_grid* g2, const ccm_proj_queries* q, const ui
   *nmatches = found;
 }
 
+// ---- device-side window search for the order-independent matchers (CCM_MATCH_WINDOW=1; not yet run on a device) -------------
+// Fuse x2 and both directions of SearchBySim3 choose, per query, the first minimum over the window at levels [L-1, L]: no query
+// depends on another, so the whole choice can stay on the device and only m indices come back instead of an m x n matrix.
+// One warp per query walks the cell runs (columns c0..c1, rows r0..r1 — computed on the host with the reference's float
+// expressions), 32 keypoints at a time in visiting order; a lane that passes the window / level / chi-square tests forms
+// key = distance << 20 | position-in-visit, the warp keeps the minimum key = the reference's strict-'<' first minimum.
+struct WinQuery { float u, v, r; int level, c0, c1, r0, r1; };
+
+__global__ void __launch_bounds__(256) k_window_best(const WinQuery* __restrict__ Q, const uint4* __restrict__ qdesc, int m,
+                                                     const int* __restrict__ cell_ptr, const int* __restrict__ cell_feat, int grid_rows,
+                                                     const float2* __restrict__ kp_xy, const int* __restrict__ octave,
+                                                     const uint4* __restrict__ kdesc, const float* __restrict__ inv_sigma2, int nlevels,
+                                                     int* __restrict__ best_idx, int* __restrict__ best_dist) {
+  const int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (w >= m) return;  // warp-uniform
+  const int lane = threadIdx.x & 31;
+  const WinQuery q = Q[w];
+  unsigned best = 0xffffffffu;
+  int best_j = -1;
+  if (q.c0 <= q.c1 && q.r0 <= q.r1) {
+    const uint4 d0 = qdesc[(size_t)w * 2], d1 = qdesc[(size_t)w * 2 + 1];
+    unsigned ord = 0;
+    for (int c = q.c0; c <= q.c1; c++) {
+      const int beg = cell_ptr[c * grid_rows + q.r0], end = cell_ptr[c * grid_rows + q.r1 + 1];
+      for (int p = beg; p < end; p += 32, ord += 32) {
+        const int i = p + lane;
+        if (i < end) {
+          const int j = cell_feat[i];
+          const int o = octave[j];
+          const float2 k = kp_xy[j];
+          bool ok = o >= q.level - 1 && o <= q.level && fabsf(__fsub_rn(k.x, q.u)) < q.r && fabsf(__fsub_rn(k.y, q.v)) < q.r;
+          if (ok && inv_sigma2) {  // Fuse(kf, points): e2 * invSigma2[level] > 5.99 rejects (f32 product, compared as double)
+            const float ex = __fsub_rn(q.u, k.x), ey = __fsub_rn(q.v, k.y);
+            const float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
+            ok = o >= 0 && o < nlevels && !((double)__fmul_rn(e2, inv_sigma2[o]) > 5.99);
+          }
+          if (ok) {
+            const uint4 b0 = kdesc[(size_t)j * 2], b1 = kdesc[(size_t)j * 2 + 1];
+            const unsigned d = __popc(d0.x ^ b0.x) + __popc(d0.y ^ b0.y) + __popc(d0.z ^ b0.z) + __popc(d0.w ^ b0.w) +
+                               __popc(d1.x ^ b1.x) + __popc(d1.y ^ b1.y) + __popc(d1.z ^ b1.z) + __popc(d1.w ^ b1.w);
+            const unsigned key = (d << 20) | (ord + (unsigned)lane);
+            if (key < best) { best = key; best_j = j; }
+          }
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) {
+    const unsigned ob = __shfl_xor_sync(0xffffffffu, best, off);
+    const int oj = __shfl_xor_sync(0xffffffffu, best_j, off);
+    if (ob < best) { best = ob; best_j = oj; }
+  }
+  if (lane == 0) {
+    best_idx[w] = best_j;
+    best_dist[w] = best_j >= 0 ? (int)(best >> 20) : 0x7fffffff;
+  }
+}
+
+bool window_on_device() {
+  static const bool on = [] { const char* v = getenv("CCM_MATCH_WINDOW"); return v && atoi(v) != 0; }();
+  return on;
+}
+
+// best keypoint of every valid query's window on the device: out_idx[i] = index or -1, out_dist[i] = its distance
+void device_window_best(const ccm_feature_grid* g, const ccm_proj_queries* q, const float* w, int nlevels, std::vector<int>& out_idx,
+                        std::vector<int>& out_dist, const char* who) {
+  check_grid(g, who); check_queries(q, who);
+  out_idx.assign(q->m, -1); out_dist.assign(q->m, INT_MAX);
+  if (q->m == 0 || g->n == 0) return;
+  CCM_REQUIRE((long long)g->n + 32ll * g->grid_cols * 2 < (1 << 20), std::string(who) + ": too many keypoints for the 20-bit visiting position");
+  ensure_device();
+  const CellIndex cells(*g);
+  std::vector<WinQuery> hq(q->m);
+  for (int i = 0; i < q->m; i++) {
+    WinQuery& Q = hq[i];
+    Q.u = q->uv[2 * i]; Q.v = q->uv[2 * i + 1]; Q.r = q->radius[i]; Q.level = q->level[i];
+    Q.c0 = 1; Q.c1 = 0; Q.r0 = 1; Q.r1 = 0;  // empty
+    if (!q->valid[i]) continue;
+    // GetFeaturesInArea's cell range, with its early returns
+    const int c0 = std::max(0, (int)floorf((Q.u - g->min_x - Q.r) * g->grid_w_inv));
+    if (c0 >= g->grid_cols) continue;
+    const int c1 = std::min(g->grid_cols - 1, (int)ceilf((Q.u - g->min_x + Q.r) * g->grid_w_inv));
+    if (c1 < 0) continue;
+    const int r0 = std::max(0, (int)floorf((Q.v - g->min_y - Q.r) * g->grid_h_inv));
+    if (r0 >= g->grid_rows) continue;
+    const int r1 = std::min(g->grid_rows - 1, (int)ceilf((Q.v - g->min_y + Q.r) * g->grid_h_inv));
+    if (r1 < 0) continue;
+    Q.c0 = c0; Q.c1 = c1; Q.r0 = r0; Q.r1 = r1;
+  }
+  cudaStream_t s = nullptr;
+  CCM_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+  struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamDestroy(s); } } guard{s};
+  DevBuf<WinQuery> dQ; DevBuf<uint4> dqd, dkd; DevBuf<int> dptr, dfeat, doct, dbi, dbd; DevBuf<float2> dxy; DevBuf<float> dw;
+  dQ.upload(hq.data(), hq.size(), s);
+  dqd.upload(reinterpret_cast<const uint4*>(q->desc), (size_t)q->m * 2, s);
+  dkd.upload(reinterpret_cast<const uint4*>(g->desc), (size_t)g->n * 2, s);
+  dptr.upload(cells.ptr.data(), cells.ptr.size(), s);
+  if (!cells.feat.empty()) dfeat.upload(cells.feat.data(), cells.feat.size(), s); else dfeat.alloc(1);
+  doct.upload(g->octave, g->n, s);
+  dxy.upload(reinterpret_cast<const float2*>(g->kp_xy), g->n, s);
+  if (w) dw.upload(w, nlevels, s);
+  dbi.alloc(q->m); dbd.alloc(q->m);
+  k_window_best<<<div_up((long long)q->m * 32, 256), 256, 0, s>>>(dQ.p, dqd.p, q->m, dptr.p, dfeat.p, g->grid_rows, dxy.p, doct.p, dkd.p,
+                                                                 w ? dw.p : nullptr, nlevels, dbi.p, dbd.p);
+  CCM_LAUNCHED();
+  dbi.download(out_idx.data(), q->m, s);
+  dbd.download(out_dist.data(), q->m, s);
+  CCM_CUDA(cudaStreamSynchronize(s));
+}
+
 const uint16_t* device_distances(const ccm_proj_queries* q, const ccm_feature_grid* g, const char* who) {
   check_grid(g, who); check_queries(q, who);
   return hamming_matrix_host(q->desc, q->m, g->desc, g->n);
@@ -364,7 +476,22 @@ int ccm_fuse_select(const ccm_feature_grid* g, const ccm_proj_queries* q, const 
 }
 int ccm_fuse_search(const ccm_feature_grid* g, const ccm_proj_queries* q, const float* inv_level_sigma2, int32_t nlevels,
                     int32_t* best_idx, int32_t* nfound) {
-  return guarded([&] { select_fuse(g, q, device_distances(q, g, "ccm_fuse_search"), inv_level_sigma2, nlevels, best_idx, nfound); });
+  return guarded([&] {
+    if (window_on_device()) {
+      CCM_REQUIRE(best_idx && nfound && (!inv_level_sigma2 || nlevels > 0), "ccm_fuse_search: null argument");
+      std::vector<int> bi, bd;
+      device_window_best(g, q, inv_level_sigma2, nlevels, bi, bd, "ccm_fuse_search");
+      int found = 0;
+      for (int i = 0; i < q->m; i++) {
+        const bool hit = bi[i] >= 0 && bd[i] <= TH_LOW;
+        best_idx[i] = hit ? bi[i] : -1;
+        found += hit;
+      }
+      *nfound = found;
+      return;
+    }
+    select_fuse(g, q, device_distances(q, g, "ccm_fuse_search"), inv_level_sigma2, nlevels, best_idx, nfound);
+  });
 }
 
 int ccm_select_for_initialization(const ccm_feature_grid* g2, const ccm_proj_queries* q, const uint16_t* D, float nnratio,
@@ -385,6 +512,23 @@ int ccm_select_by_sim3(const ccm_feature_grid* g1, const ccm_feature_grid* g2, c
 int ccm_search_by_sim3(const ccm_feature_grid* g1, const ccm_feature_grid* g2, const ccm_proj_queries* q12, const ccm_proj_queries* q21,
                        int32_t* match12, int32_t* nfound) {
   return guarded([&] {
+    if (window_on_device()) {
+      check_grid(g1, "ccm_search_by_sim3"); check_grid(g2, "ccm_search_by_sim3");
+      check_queries(q12, "ccm_search_by_sim3"); check_queries(q21, "ccm_search_by_sim3");
+      CCM_REQUIRE(match12 && nfound && q12->m == g1->n && q21->m == g2->n, "ccm_search_by_sim3: one query per keypoint of the source keyframe");
+      std::vector<int> i12, d12, i21, d21;
+      device_window_best(g2, q12, nullptr, 0, i12, d12, "ccm_search_by_sim3");
+      device_window_best(g1, q21, nullptr, 0, i21, d21, "ccm_search_by_sim3");
+      int found = 0;
+      for (int i1 = 0; i1 < q12->m; i1++) {
+        const int j = (i12[i1] >= 0 && d12[i1] <= TH_HIGH) ? i12[i1] : -1;
+        const bool agree = j >= 0 && i21[j] == i1 && d21[j] <= TH_HIGH;
+        match12[i1] = agree ? j : -1;
+        found += agree;
+      }
+      *nfound = found;
+      return;
+    }
     // the scratch matrix is per thread and reused by the next launch: keep a copy of the first direction
     const uint16_t* d = device_distances(q12, g2, "ccm_search_by_sim3");
     const std::vector<uint16_t> D12(d, d + (size_t)q12->m * g2->n);
