@@ -447,6 +447,72 @@ class Vocabulary:
             lib().orc_voc_destroy(C.c_void_p(self.h)); self.h = None
 
 
+# ---- the reference's own DBoW2, compiled in place by `make -C oracle ref` (only where /root/reference exists) ---------------
+_REF_DBOW2 = None
+
+
+def build_ref() -> str | None:
+    """oracle/_ref/libdbow2_ref.so from the reference's DBoW2 sources (nothing copied); None where the reference tree is absent
+    and no prebuilt library travelled with the repository."""
+    so = os.path.join(_HERE, "_ref", "libdbow2_ref.so")
+    if os.path.isdir("/root/reference/cslam/thirdparty/DBoW2"):
+        subprocess.check_call(["make", "-C", _HERE, "-s", "ref"])
+    return so if os.path.exists(so) else None
+
+
+def ref_dbow2():
+    global _REF_DBOW2
+    if _REF_DBOW2 is None:
+        so = build_ref()
+        if so is None:
+            return None
+        _REF_DBOW2 = C.CDLL(so)
+        _REF_DBOW2.ref_voc_load.restype = C.c_void_p
+    return _REF_DBOW2
+
+
+def write_vocabulary_text(v, path):
+    """the rows of make_vocabulary() in the format TemplatedVocabulary::saveToTextFile writes and loadFromTextFile reads
+    (D/TemplatedVocabulary.h:1428-1448, :1338-1422); no trailing newline (the loader turns an empty last line into a node)"""
+    lines = ["%d %d  %d %d" % (v["k"], v["L"], v["scoring"], v["weighting"])]
+    for i in range(1, len(v["parent"])):
+        lines.append("%d %d %s %r" % (v["parent"][i], 1 if v["is_leaf"][i] else 0, " ".join(str(int(b)) for b in v["desc"][i]), float(v["weight"][i])))
+    with open(path, "w") as f:
+        f.write("\n".join(lines))
+
+
+class RefVocabulary:
+    """DBoW2::TemplatedVocabulary<FORB> of the reference itself, loaded from a text file"""
+
+    def __init__(self, path):
+        self.lib = ref_dbow2()
+        assert self.lib is not None, "oracle/_ref/libdbow2_ref.so is not available"
+        self.h = self.lib.ref_voc_load(path.encode())
+        assert self.h, "loadFromTextFile failed"
+
+    def words(self):
+        return self.lib.ref_voc_words(C.c_void_p(self.h))
+
+    def transform(self, feat, levelsup=4):
+        feat = np.ascontiguousarray(feat, np.uint8); n = feat.shape[0]
+        word = np.empty(n, np.uint32); node = np.empty(n, np.uint32); w = np.empty(n, np.float64)
+        bid = np.empty(n, np.uint32); bval = np.empty(n, np.float64); bn = C.c_int32()
+        fid = np.empty(n, np.uint32); fptr = np.empty(n + 1, np.int32); ff = np.empty(n, np.uint32); fn = C.c_int32()
+        self.lib.ref_voc_transform(C.c_void_p(self.h), _p(feat), n, int(levelsup), _p(word), _p(node), _p(w), _p(bid), _p(bval), C.byref(bn),
+                                   _p(fid), _p(fptr), _p(ff), C.byref(fn))
+        return dict(word=word, node=node, weight=w, bow_id=bid[:bn.value].copy(), bow_val=bval[:bn.value].copy(),
+                    fv_node_id=fid[:fn.value].copy(), fv_node_ptr=fptr[:fn.value + 1].copy(), fv_feat=ff[:fptr[fn.value] if fn.value else 0].copy())
+
+    def close(self):
+        if self.h:
+            self.lib.ref_voc_free(C.c_void_p(self.h)); self.h = None
+
+
+def ref_forb_distance(a, b):
+    a = np.ascontiguousarray(a, np.uint8); b = np.ascontiguousarray(b, np.uint8)
+    return ref_dbow2().ref_forb_distance(_p(a), _p(b))
+
+
 # ---- single-vertex optimisations (PoseOptimizationClient, OptimizeSim3) ---------------------------------------------
 class _PoseOpt(C.Structure):
     _fields_ = [("n", C.c_int32), ("Tcw", C.c_void_p), ("Xw", C.c_void_p), ("uv", C.c_void_p), ("inv_sigma2", C.c_void_p),
