@@ -6,7 +6,7 @@ from hypothesis import given, settings, strategies as st
 
 from ccm_slam_b200 import synth_match as sm
 
-FAST = settings(max_examples=25, deadline=None)
+FAST = settings(max_examples=40, deadline=None, derandomize=True, database=None)   # deterministic: the CPU suite must not flake
 vec = lambda n, lo, hi: st.lists(st.floats(lo, hi, allow_nan=False, width=64), min_size=n, max_size=n).map(np.array)
 
 
@@ -25,7 +25,12 @@ def test_se3_exp_inverse_and_unit_quaternion(oracle, u):
 @given(vec(7, -0.8, 0.8), vec(7, -0.8, 0.8), vec(7, -0.8, 0.8))
 def test_sim3_group_laws(oracle, u, v, w):
     a, b, c = oracle.sim3_exp(u), oracle.sim3_exp(v), oracle.sim3_exp(w)
-    assert np.abs(oracle.sim3_log(a) - u).max() < 1e-8
+    # g2o's Sim3 log switches to its small-angle series where cos(theta) > 1 - 1e-5, i.e. theta < ~4.5e-3, while the exponential only
+    # does so for theta < 1e-5 (G/types/sim3.h:70-142 vs :148-230, restated in oracle/lie.hpp): in between the round trip is only good
+    # to O(theta^2).  That asymmetry is the reference's; outside of it the round trip is tight.
+    theta = np.linalg.norm(u[:3])
+    tol = 1e-8 if (theta > 5e-3 or theta < 1e-6) else 1e-4 * (1.0 + np.abs(u).max())
+    assert np.abs(oracle.sim3_log(a) - u).max() < tol
     assert np.abs(oracle.sim3_inv(oracle.sim3_inv(a)) - a).max() < 1e-12
     l = oracle.sim3_mul(oracle.sim3_mul(a, b), c); r = oracle.sim3_mul(a, oracle.sim3_mul(b, c))
     assert np.abs(l - r).max() < 1e-9
