@@ -12,9 +12,10 @@
  * the oracle is pinned by independent witnesses instead: scipy (sparse solve,
  * finite differences, Rotation) for the BA/PGO part and Python cv2 4.13 for the
  * ORB primitives (tests/test_oracle_*.py, fixtures under tests/golden/).
- * "parity unpinned by the reference's own tests" — see DESIGN.md §3.  One piece of the neighbourhood does build from the
- * reference's own sources: its vendored DBoW2 (oracle/Makefile `ref` -> oracle/_ref/libdbow2_ref.so, against the stand-in OpenCV
- * header oracle/ref_stub/); bow_oracle.cpp is held to that code bit for bit (tests/test_oracle_vs_reference_dbow2.py).
+ * "parity unpinned by the reference's own tests" — see DESIGN.md §3.  Two pieces do build from the reference's own sources, in
+ * place, against the stand-in headers of oracle/ref_stub/ (oracle/Makefile `ref` -> oracle/_ref/): cslam/src/ORBextractor.cpp (on the
+ * oracle's OpenCV-primitive restatements) and the vendored DBoW2.  orb_oracle.cpp and bow_oracle.cpp are held to that code bit for
+ * bit (tests/test_oracle_vs_reference_orb.py, tests/test_oracle_vs_reference_dbow2.py).
  *
  * Citations: G/ = cslam/thirdparty/g2o/g2o/, S/ = cslam/src/ under /root/reference.
  */

@@ -471,6 +471,32 @@ def ref_dbow2():
     return _REF_DBOW2
 
 
+def ref_orb_cli():
+    """oracle/_ref/orb_ref_cli: the reference's own ORBextractor.cpp on the oracle's OpenCV-primitive restatements; None if absent"""
+    if build_ref() is None:
+        return None
+    exe = os.path.join(_HERE, "_ref", "orb_ref_cli")
+    return exe if os.path.exists(exe) else None
+
+
+def ref_orb_extract(img, cfg=None, allocator="bump"):
+    """ORBextractor::operator() of the reference itself (cslam/src/ORBextractor.cpp) -> (keypoints, descriptors) like orb_extract.
+    allocator: "bump" = monotone addresses (pointer ties of DistributeOctTree follow creation order), "malloc" = glibc."""
+    import tempfile
+    cfg = cfg or orb_cfg()
+    img = np.ascontiguousarray(img, np.uint8)
+    with tempfile.TemporaryDirectory() as d:
+        fin, fout = os.path.join(d, "in.raw"), os.path.join(d, "out.bin")
+        img.tofile(fin)
+        subprocess.check_call([ref_orb_cli(), fin, str(img.shape[1]), str(img.shape[0]), str(cfg.nfeatures), repr(float(cfg.scale_factor)),
+                               str(cfg.nlevels), str(cfg.ini_th_fast), str(cfg.min_th_fast), str(cfg.blur_2413), allocator, fout])
+        raw = open(fout, "rb").read()
+    n = int(np.frombuffer(raw[:4], np.int32)[0])
+    kps = np.frombuffer(raw[4:4 + n * KP_DTYPE.itemsize], KP_DTYPE).copy()
+    desc = np.frombuffer(raw[4 + n * KP_DTYPE.itemsize:], np.uint8).reshape(n, 32).copy()
+    return kps, desc
+
+
 def write_vocabulary_text(v, path):
     """the rows of make_vocabulary() in the format TemplatedVocabulary::saveToTextFile writes and loadFromTextFile reads
     (D/TemplatedVocabulary.h:1428-1448, :1338-1422); no trailing newline (the loader turns an empty last line into a node)"""

@@ -1,52 +1,139 @@
-// Minimal stand-in for <opencv2/core/core.hpp> (TEST INFRASTRUCTURE, NOT PRODUCT; our own code, not OpenCV's).
+// Minimal stand-in for OpenCV's core types (TEST INFRASTRUCTURE, NOT PRODUCT; our own code, not OpenCV's).
 //
-// OpenCV's C++ headers are absent from this image, so the reference cannot be compiled as a whole — but its vendored DBoW2
-// (cslam/thirdparty/DBoW2) only touches OpenCV through cv::Mat as a 1 x 32 byte container and through cv::FileStorage in its
-// YAML save/load members.  This header provides exactly that surface so that oracle/Makefile can compile the reference's OWN
-// DBoW2 sources, where they lie under /root/reference, into oracle/_ref/libdbow2_ref.so: the text-file loader, the tree descent,
-// FORB::distance and the BowVector / FeatureVector containers that check oracle/bow_oracle.cpp are then the reference's code.
-// cv::Mat here is a dense row-major byte buffer (create / zeros / clone / release / ptr<T> / rows / cols); the FileStorage family
-// is inert (the YAML path is never exercised: the reference itself loads its vocabulary with loadFromTextFile).
+// OpenCV's C++ headers are absent from this image, so the reference cannot be compiled as a whole.  Two of its translation units,
+// however, touch OpenCV only through a handful of value types and five image primitives:
+//   * the vendored DBoW2 (cslam/thirdparty/DBoW2): cv::Mat as a 1 x 32 byte container, cv::FileStorage in YAML members never called;
+//   * cslam/src/ORBextractor.cpp: cv::Mat views (ROI / rowRange / colRange sharing one buffer), KeyPoint / Point / Size / Rect,
+//     and FAST / resize / GaussianBlur / copyMakeBorder / fastAtan2 (declared in opencv2/opencv.hpp next to this file and
+//     implemented in oracle/ref_orb_wrap.cpp on top of the oracle's OpenCV-primitive restatements, which tests/test_oracle_orb.py pins
+//     to cv2 4.13).
+// This header provides exactly that surface so that oracle/Makefile can compile those reference sources where they lie under
+// /root/reference into oracle/_ref/*.so.  Semantics that the reference relies on and that are easy to get wrong are kept:
+//   * a Mat is a (shared buffer, data pointer, rows, cols, step) view; operator()(Rect), rowRange, colRange alias the parent;
+//   * assigning Mat::zeros(r, c, t) to a Mat that already has that shape fills it IN PLACE (OpenCV's MatExpr assignment re-uses the
+//     destination), which is how computeDescriptors writes through the row view of the output matrix (ORBextractor.cpp:1208);
+//   * create() on a Mat that already has the requested shape keeps its storage (resize / copyMakeBorder into an existing view);
+//   * cvRound rounds half to even (lrint under the default rounding mode).
+// FileStorage is inert but reports "opened" and yields zeros: cslam/config.h reads its parameters through it during static
+// initialisation and would exit(-1) otherwise; none of those parameters is used by the code compiled here.
 #ifndef CCM_ORACLE_REF_STUB_OPENCV_CORE_HPP
 #define CCM_ORACLE_REF_STUB_OPENCV_CORE_HPP
-// the real header pulls these in, and DBoW2 leans on that (pow / log, stringstream, ...)
+// the real header pulls these in, and the reference leans on that (pow / log, stringstream, ...)
 #include <algorithm>
+#include <cassert>
 #include <cmath>
 #include <cstddef>
 #include <cstdlib>
 #include <cstring>
 #include <iostream>
+#include <memory>
 #include <sstream>
 #include <string>
 #include <vector>
 
 #define CV_8U 0
+#define CV_8UC1 0
 #define CV_32F 5
+#define CV_PI 3.1415926535897932384626433832795
+
+typedef unsigned char uchar;
+
+inline int cvRound(double v) { return (int)lrint(v); }
+inline int cvRound(float v) { return (int)lrintf(v); }
+inline int cvRound(int v) { return v; }
+inline int cvFloor(double v) { return (int)std::floor(v); }
+inline int cvCeil(double v) { return (int)std::ceil(v); }
 
 namespace cv {
+
+template <class T> struct Point_ {
+  T x, y;
+  Point_() : x(0), y(0) {}
+  Point_(T x_, T y_) : x(x_), y(y_) {}
+  template <class U> Point_(const Point_<U>& o) : x((T)o.x), y((T)o.y) {}
+  Point_& operator*=(float s) { x = (T)(x * s); y = (T)(y * s); return *this; }
+};
+typedef Point_<int> Point2i;
+typedef Point_<int> Point;
+typedef Point_<float> Point2f;
+
+template <class T> struct Size_ {
+  T width, height;
+  Size_() : width(0), height(0) {}
+  Size_(T w, T h) : width(w), height(h) {}
+};
+typedef Size_<int> Size;
+
+template <class T> struct Rect_ {
+  T x, y, width, height;
+  Rect_() : x(0), y(0), width(0), height(0) {}
+  Rect_(T x_, T y_, T w, T h) : x(x_), y(y_), width(w), height(h) {}
+};
+typedef Rect_<int> Rect;
+
+struct KeyPoint {
+  Point2f pt;
+  float size, angle, response;
+  int octave, class_id;
+  KeyPoint() : size(0), angle(-1), response(0), octave(0), class_id(-1) {}
+  KeyPoint(float x, float y, float s, float a = -1, float r = 0, int o = 0, int c = -1) : pt(x, y), size(s), angle(a), response(r), octave(o), class_id(c) {}
+};
+
+struct MatZeros { int rows, cols, type; };
 
 class Mat {
  public:
   int rows, cols;
-  Mat() : rows(0), cols(0), type_(CV_8U) {}
-  Mat(int r, int c, int type) : rows(0), cols(0), type_(CV_8U) { create(r, c, type); }
+  size_t step;
+  uchar* data;
+  Mat() : rows(0), cols(0), step(0), data(nullptr), type_(CV_8U) {}
+  Mat(int r, int c, int type) : rows(0), cols(0), step(0), data(nullptr), type_(CV_8U) { create(r, c, type); }
+  Mat(Size s, int type) : rows(0), cols(0), step(0), data(nullptr), type_(CV_8U) { create(s.height, s.width, type); }
+  Mat(const MatZeros& z) : rows(0), cols(0), step(0), data(nullptr), type_(CV_8U) { *this = z; }
+  static int esz(int type) { return type == CV_32F ? 4 : 1; }
   void create(int r, int c, int type) {
-    rows = r; cols = c; type_ = type;
-    data_.assign((size_t)r * c * (type == CV_32F ? 4 : 1), 0);
+    if (data && r == rows && c == cols && type == type_) return;   // same shape: the storage (possibly a view) is kept
+    rows = r; cols = c; type_ = type; step = (size_t)c * esz(type);
+    buf_ = std::make_shared<std::vector<uchar> >((size_t)r * step + 64, (uchar)0);
+    data = buf_->data();
   }
-  static Mat zeros(int r, int c, int type) { return Mat(r, c, type); }
-  Mat clone() const { return *this; }
-  void release() { rows = cols = 0; data_.clear(); }
-  bool empty() const { return data_.empty(); }
-  template <class T> T* ptr(int row = 0) { return reinterpret_cast<T*>(data_.data() + (size_t)row * cols * (type_ == CV_32F ? 4 : 1)); }
-  template <class T> const T* ptr(int row = 0) const {
-    return reinterpret_cast<const T*>(data_.data() + (size_t)row * cols * (type_ == CV_32F ? 4 : 1));
+  static MatZeros zeros(int r, int c, int type) { MatZeros z; z.rows = r; z.cols = c; z.type = type; return z; }
+  Mat& operator=(const MatZeros& z) {
+    create(z.rows, z.cols, z.type);
+    for (int r = 0; r < rows; r++) memset(data + (size_t)r * step, 0, (size_t)cols * esz(type_));
+    return *this;
   }
+  Mat clone() const {
+    Mat m;
+    if (!data) return m;
+    m.create(rows, cols, type_);
+    for (int r = 0; r < rows; r++) memcpy(m.data + (size_t)r * m.step, data + (size_t)r * step, (size_t)cols * esz(type_));
+    return m;
+  }
+  void release() { rows = cols = 0; step = 0; data = nullptr; buf_.reset(); }
+  bool empty() const { return data == nullptr || rows == 0 || cols == 0; }
+  int type() const { return type_; }
+  size_t step1() const { return step / esz(type_); }
+  Size size() const { return Size(cols, rows); }
+  bool isContinuous() const { return step == (size_t)cols * esz(type_); }
+  Mat operator()(const Rect& r) const { Mat m(*this); m.data = data + (size_t)r.y * step + (size_t)r.x * esz(type_); m.rows = r.height; m.cols = r.width; return m; }
+  Mat rowRange(int a, int b) const { return (*this)(Rect(0, a, cols, b - a)); }
+  Mat colRange(int a, int b) const { return (*this)(Rect(a, 0, b - a, rows)); }
+  uchar* ptr(int row = 0) { return data + (size_t)row * step; }
+  const uchar* ptr(int row = 0) const { return data + (size_t)row * step; }
+  template <class T> T* ptr(int row = 0) { return reinterpret_cast<T*>(data + (size_t)row * step); }
+  template <class T> const T* ptr(int row = 0) const { return reinterpret_cast<const T*>(data + (size_t)row * step); }
+  template <class T> T& at(int r, int c) { return reinterpret_cast<T*>(data + (size_t)r * step)[c]; }
+  template <class T> const T& at(int r, int c) const { return reinterpret_cast<const T*>(data + (size_t)r * step)[c]; }
+  // InputArray / OutputArray surface
+  Mat getMat() const { return *this; }
 
  private:
   int type_;
-  std::vector<unsigned char> data_;
+  std::shared_ptr<std::vector<uchar> > buf_;
 };
+typedef const Mat& InputArray;
+typedef Mat& OutputArray;
 
 class FileNode {
  public:
@@ -64,7 +151,7 @@ class FileStorage {
   enum { READ = 0, WRITE = 1 };
   FileStorage() {}
   FileStorage(const std::string&, int) {}
-  bool isOpened() const { return false; }
+  bool isOpened() const { return true; }
   FileNode operator[](const std::string&) const { return FileNode(); }
   FileNode operator[](const char*) const { return FileNode(); }
 };

@@ -1,0 +1,3 @@
+// stand-in (TEST INFRASTRUCTURE): the one ROS message type cslam/estd.h names
+#pragma once
+namespace std_msgs { struct ColorRGBA { float r, g, b, a; ColorRGBA() : r(0), g(0), b(0), a(0) {} }; }
