@@ -497,6 +497,116 @@ def ref_orb_extract(img, cfg=None, allocator="bump"):
     return kps, desc
 
 
+# ---- the reference's own ORBmatcher.cpp on stand-in Frame / KeyFrame / MapPoint (oracle/_ref/libmatch_ref.so) -----------------------
+_REF_MATCH = None
+
+
+def ref_match():
+    global _REF_MATCH
+    if _REF_MATCH is None:
+        if build_ref() is None:
+            return None
+        so = os.path.join(_HERE, "_ref", "libmatch_ref.so")
+        if not os.path.exists(so):
+            return None
+        _REF_MATCH = C.CDLL(so)
+    return _REF_MATCH
+
+
+class _RefImage(C.Structure):
+    _fields_ = [("n", C.c_int32), ("desc", C.c_void_p), ("kp_xy", C.c_void_p), ("octave", C.c_void_p), ("angle", C.c_void_p),
+                ("min_x", C.c_float), ("min_y", C.c_float), ("max_x", C.c_float), ("max_y", C.c_float), ("grid_w_inv", C.c_float),
+                ("grid_h_inv", C.c_float), ("grid_cols", C.c_int32), ("grid_rows", C.c_int32),
+                ("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("R", C.c_void_p), ("t", C.c_void_p),
+                ("nlevels", C.c_int32), ("scale_factors", C.c_void_p), ("level_sigma2", C.c_void_p), ("inv_level_sigma2", C.c_void_p),
+                ("log_scale_factor", C.c_float), ("fv", C.POINTER(_FV))]
+
+
+class _RefPoints(C.Structure):
+    _fields_ = [("m", C.c_int32), ("pos", C.c_void_p), ("normal", C.c_void_p), ("min_dist", C.c_void_p), ("max_dist", C.c_void_p),
+                ("desc", C.c_void_p), ("bad", C.c_void_p), ("do_not_replace", C.c_void_p), ("n_obs", C.c_void_p), ("index_in_kf", C.c_void_p),
+                ("track_in_view", C.c_void_p), ("track_xy", C.c_void_p), ("track_level", C.c_void_p), ("track_view_cos", C.c_void_p)]
+
+
+def ref_image_struct(g, keep, intr=(0, 0, 0, 0), R=None, t=None, fv=None, nlevels=8, scale_factor=1.2):
+    """g: grid dict (desc, kp_xy, octave, angle, bounds, cols, rows); cols = 0 -> no lookup grid.  Level tables as ORBextractor builds them."""
+    a = dict(desc=np.ascontiguousarray(g["desc"], np.uint8), xy=np.ascontiguousarray(g["kp_xy"], np.float32),
+             oc=np.ascontiguousarray(g["octave"], np.int32), an=np.ascontiguousarray(g["angle"], np.float32))
+    sf = np.empty(nlevels, np.float32); sf[0] = 1.0
+    for i in range(1, nlevels):
+        sf[i] = np.float32(sf[i - 1] * np.float32(scale_factor))
+    a["sf"] = sf; a["ls2"] = (sf * sf).astype(np.float32); a["ils2"] = (np.float32(1.0) / a["ls2"]).astype(np.float32)
+    a["R"] = None if R is None else np.ascontiguousarray(R, np.float32); a["t"] = None if t is None else np.ascontiguousarray(t, np.float32)
+    cfv = None
+    if fv is not None:
+        cfv = fv.c(); a["fv"] = (fv, cfv)
+    keep.append(a)
+    x0, y0, x1, y1 = [np.float32(v) for v in g.get("bounds", (0, 0, 1, 1))]
+    cols, rows = int(g.get("cols", 0)), int(g.get("rows", 0))
+    wi = np.float32(cols) / np.float32(x1 - x0) if cols else np.float32(0); hi = np.float32(rows) / np.float32(y1 - y0) if rows else np.float32(0)
+    fx, fy, cx, cy = [np.float32(v) for v in intr]
+    return _RefImage(a["desc"].shape[0], _p(a["desc"]), _p(a["xy"]), _p(a["oc"]), _p(a["an"]), x0, y0, x1, y1, wi, hi, cols, rows, fx, fy, cx, cy,
+                     _p(a["R"]), _p(a["t"]), nlevels, _p(a["sf"]), _p(a["ls2"]), _p(a["ils2"]), np.float32(np.log(np.float32(scale_factor))),
+                     C.pointer(cfv) if cfv is not None else None)
+
+
+def ref_points_struct(p, keep):
+    """p: dict with any of pos, normal, min_dist, max_dist, desc, bad, do_not_replace, n_obs, index_in_kf, track_in_view, track_xy, track_level, track_view_cos"""
+    m = len(p["desc"])
+    spec = dict(pos=np.float32, normal=np.float32, min_dist=np.float32, max_dist=np.float32, desc=np.uint8, bad=np.uint8, do_not_replace=np.uint8,
+                n_obs=np.int32, index_in_kf=np.int32, track_in_view=np.uint8, track_xy=np.float32, track_level=np.int32, track_view_cos=np.float32)
+    a = {k: (np.ascontiguousarray(p[k], dt) if k in p and p[k] is not None else None) for k, dt in spec.items()}
+    keep.append(a)
+    return _RefPoints(m, *[_p(a[k]) for k in ("pos", "normal", "min_dist", "max_dist", "desc", "bad", "do_not_replace", "n_obs", "index_in_kf",
+                                               "track_in_view", "track_xy", "track_level", "track_view_cos")])
+
+
+def _plain(desc, angle, octave=None, xy=None):
+    n = len(desc)
+    return dict(desc=desc, kp_xy=np.zeros((n, 2), np.float32) if xy is None else xy, octave=np.zeros(n, np.int32) if octave is None else octave,
+                angle=angle)
+
+
+def ref_match_bow_kf_frame(desc_kf, has_mp, ang_kf, fv_kf, desc_f, ang_f, fv_f, nnratio=0.7, check_ori=True):
+    keep = []; K = ref_image_struct(_plain(desc_kf, ang_kf), keep, fv=fv_kf); F = ref_image_struct(_plain(desc_f, ang_f), keep, fv=fv_f)
+    has = np.ascontiguousarray(has_mp, np.uint8); out = np.empty(len(desc_f), np.int32)
+    n = ref_match().ref_match_bow_kf_frame(C.byref(K), _p(has), C.byref(F), C.c_float(nnratio), int(check_ori), _p(out))
+    return out, n
+
+
+def ref_match_bow_kf_kf(d1, has1, a1, fv1, d2, has2, a2, fv2, nnratio=0.8, check_ori=True):
+    keep = []; K1 = ref_image_struct(_plain(d1, a1), keep, fv=fv1); K2 = ref_image_struct(_plain(d2, a2), keep, fv=fv2)
+    h1 = np.ascontiguousarray(has1, np.uint8); h2 = np.ascontiguousarray(has2, np.uint8); out = np.empty(len(d1), np.int32)
+    n = ref_match().ref_match_bow_kf_kf(C.byref(K1), _p(h1), C.byref(K2), _p(h2), C.c_float(nnratio), int(check_ori), _p(out))
+    return out, n
+
+
+def ref_match_triangulation(v1, v2, F12, Cw, check_ori=False):
+    """v = dict(desc, has_mp, kp_xy, octave, angle, fv, intr); Cw = camera centre of keyframe 1 in world = in camera 2 (its pose is identity)"""
+    keep = []
+    Cw = np.asarray(Cw, np.float32)
+    K1 = ref_image_struct(_plain(v1["desc"], v1["angle"], v1["octave"], v1["kp_xy"]), keep, intr=v1["intr"], t=-Cw, fv=v1["fv"])
+    K2 = ref_image_struct(_plain(v2["desc"], v2["angle"], v2["octave"], v2["kp_xy"]), keep, intr=v2["intr"], fv=v2["fv"])
+    h1 = np.ascontiguousarray(v1["has_mp"], np.uint8); h2 = np.ascontiguousarray(v2["has_mp"], np.uint8)
+    F = np.ascontiguousarray(F12, np.float32); pairs = np.empty((min(K1.n, K2.n) + 1, 2), np.int32)
+    n = ref_match().ref_match_triangulation(C.byref(K1), _p(h1), C.byref(K2), _p(h2), _p(F), int(check_ori), _p(pairs))
+    return pairs[:n].copy()
+
+
+def ref_search_for_initialization(g1, g2, prev_matched, window, nnratio=0.9, check_ori=True):
+    keep = []; F1 = ref_image_struct(g1, keep); F2 = ref_image_struct(g2, keep)
+    prev = np.ascontiguousarray(prev_matched, np.float32).copy(); out = np.empty(F1.n, np.int32)
+    n = ref_match().ref_search_for_initialization(C.byref(F1), C.byref(F2), _p(prev), int(window), C.c_float(nnratio), int(check_ori), _p(out))
+    return out, n, prev
+
+
+def ref_search_by_projection_track(g, points, feat_blocked, th, nnratio=0.8):
+    keep = []; F = ref_image_struct(g, keep); P = ref_points_struct(points, keep)
+    fb = np.ascontiguousarray(feat_blocked, np.uint8); out = np.empty(F.n, np.int32)
+    n = ref_match().ref_search_by_projection_track(C.byref(F), C.byref(P), _p(fb), C.c_float(th), C.c_float(nnratio), _p(out))
+    return out, n
+
+
 def write_vocabulary_text(v, path):
     """the rows of make_vocabulary() in the format TemplatedVocabulary::saveToTextFile writes and loadFromTextFile reads
     (D/TemplatedVocabulary.h:1428-1448, :1338-1422); no trailing newline (the loader turns an empty last line into a node)"""

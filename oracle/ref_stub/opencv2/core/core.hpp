@@ -127,6 +127,23 @@ class Mat {
   template <class T> const T& at(int r, int c) const { return reinterpret_cast<const T*>(data + (size_t)r * step)[c]; }
   // InputArray / OutputArray surface
   Mat getMat() const { return *this; }
+  // small dense float algebra (cslam/src/ORBmatcher.cpp composes poses with it).  Evaluated eagerly, products accumulated in
+  // double and rounded to float once.  OpenCV's own gemm may round differently in the last place; the tests that run the reference's
+  // matchers (tests/test_oracle_vs_reference_matchers.py) use poses and points whose arithmetic is exact in float for that reason.
+  Mat row(int r) const { return (*this)(Rect(0, r, cols, 1)); }
+  Mat col(int c) const { return (*this)(Rect(c, 0, 1, rows)); }
+  template <class T> T& at(int i) { return rows == 1 ? at<T>(0, i) : at<T>(i, 0); }
+  template <class T> const T& at(int i) const { return rows == 1 ? at<T>(0, i) : at<T>(i, 0); }
+  Mat t() const {
+    Mat m(cols, rows, type_);
+    for (int r = 0; r < rows; r++) for (int c = 0; c < cols; c++) m.at<float>(c, r) = at<float>(r, c);
+    return m;
+  }
+  double dot(const Mat& o) const {
+    double s = 0;
+    for (int r = 0; r < rows; r++) for (int c = 0; c < cols; c++) s += (double)at<float>(r, c) * (double)o.at<float>(r, c);
+    return s;
+  }
 
  private:
   int type_;
@@ -134,6 +151,36 @@ class Mat {
 };
 typedef const Mat& InputArray;
 typedef Mat& OutputArray;
+
+inline Mat operator*(const Mat& a, const Mat& b) {
+  assert(a.cols == b.rows && a.type() == CV_32F && b.type() == CV_32F);
+  Mat m(a.rows, b.cols, CV_32F);
+  for (int r = 0; r < a.rows; r++)
+    for (int c = 0; c < b.cols; c++) {
+      double s = 0;
+      for (int k = 0; k < a.cols; k++) s += (double)a.at<float>(r, k) * (double)b.at<float>(k, c);
+      m.at<float>(r, c) = (float)s;
+    }
+  return m;
+}
+template <class F> inline Mat mat_map2(const Mat& a, const Mat& b, F f) {
+  assert(a.rows == b.rows && a.cols == b.cols);
+  Mat m(a.rows, a.cols, CV_32F);
+  for (int r = 0; r < a.rows; r++) for (int c = 0; c < a.cols; c++) m.at<float>(r, c) = f(a.at<float>(r, c), b.at<float>(r, c));
+  return m;
+}
+template <class F> inline Mat mat_map1(const Mat& a, F f) {
+  Mat m(a.rows, a.cols, CV_32F);
+  for (int r = 0; r < a.rows; r++) for (int c = 0; c < a.cols; c++) m.at<float>(r, c) = f(a.at<float>(r, c));
+  return m;
+}
+inline Mat operator+(const Mat& a, const Mat& b) { return mat_map2(a, b, [](float x, float y) { return x + y; }); }
+inline Mat operator-(const Mat& a, const Mat& b) { return mat_map2(a, b, [](float x, float y) { return x - y; }); }
+inline Mat operator-(const Mat& a) { return mat_map1(a, [](float x) { return -x; }); }
+inline Mat operator*(const Mat& a, double s) { return mat_map1(a, [s](float x) { return (float)((double)x * s); }); }
+inline Mat operator*(double s, const Mat& a) { return a * s; }
+inline Mat operator/(const Mat& a, double s) { return mat_map1(a, [s](float x) { return (float)((double)x / s); }); }
+inline double norm(const Mat& a) { return std::sqrt(a.dot(a)); }
 
 class FileNode {
  public:
