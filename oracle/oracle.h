@@ -12,10 +12,11 @@
  * the oracle is pinned by independent witnesses instead: scipy (sparse solve,
  * finite differences, Rotation) for the BA/PGO part and Python cv2 4.13 for the
  * ORB primitives (tests/test_oracle_*.py, fixtures under tests/golden/).
- * "parity unpinned by the reference's own tests" — see DESIGN.md §3.  Two pieces do build from the reference's own sources, in
+ * "parity unpinned by the reference's own tests" — see DESIGN.md §3.  Three pieces do build from the reference's own sources, in
  * place, against the stand-in headers of oracle/ref_stub/ (oracle/Makefile `ref` -> oracle/_ref/): cslam/src/ORBextractor.cpp (on the
- * oracle's OpenCV-primitive restatements) and the vendored DBoW2.  orb_oracle.cpp and bow_oracle.cpp are held to that code bit for
- * bit (tests/test_oracle_vs_reference_orb.py, tests/test_oracle_vs_reference_dbow2.py).
+ * oracle's OpenCV-primitive restatements), cslam/src/ORBmatcher.cpp (on stand-in Frame / KeyFrame / MapPoint) and the vendored DBoW2.
+ * orb_oracle.cpp, match_oracle.cpp, proj_oracle.cpp and bow_oracle.cpp are held to that code exactly
+ * (tests/test_oracle_vs_reference_{orb,matchers,dbow2}.py).
  *
  * Citations: G/ = cslam/thirdparty/g2o/g2o/, S/ = cslam/src/ under /root/reference.
  */

@@ -607,6 +607,54 @@ def ref_search_by_projection_track(g, points, feat_blocked, th, nnratio=0.8):
     return out, n
 
 
+def ref_fuse(g, intr, t, kf_mp_obs, points, th, Scw=None):
+    """Fuse(pKF, vpMapPoints, th) (Scw None) or Fuse(pKF, Scw, vpPoints, th, vpReplacePoint) -> (best_idx per point, nFused)"""
+    keep = []; K = ref_image_struct(g, keep, intr=intr, t=t); P = ref_points_struct(points, keep)
+    obs = np.ascontiguousarray(kf_mp_obs, np.int32); best = np.empty(P.m, np.int32)
+    if Scw is None:
+        n = ref_match().ref_fuse(C.byref(K), _p(obs), C.byref(P), C.c_float(th), _p(best))
+    else:
+        S = np.ascontiguousarray(Scw, np.float32)
+        n = ref_match().ref_fuse_sim3(C.byref(K), _p(obs), _p(S), C.byref(P), C.c_float(th), _p(best))
+    return best, n
+
+
+def ref_search_by_projection_sim3(g, intr, Scw, points, feat_matched, th):
+    keep = []; K = ref_image_struct(g, keep, intr=intr); P = ref_points_struct(points, keep)
+    S = np.ascontiguousarray(Scw, np.float32); fm = np.ascontiguousarray(feat_matched, np.uint8)
+    mof = np.empty(K.n, np.int32); remap = np.empty((P.m + 1, 3), np.int32); nr = C.c_int32()
+    n = ref_match().ref_search_by_projection_sim3(C.byref(K), _p(S), C.byref(P), _p(fm), int(th), _p(mof), _p(remap), C.byref(nr))
+    return mof, remap[:nr.value].copy(), n
+
+
+def ref_search_by_sim3(g1, g2, intr, t1, t2, pts1, p1_of_feat, pts2, p2_of_feat, s12, R12, t12, th):
+    keep = []; K1 = ref_image_struct(g1, keep, intr=intr, t=t1); K2 = ref_image_struct(g2, keep, intr=intr, t=t2)
+    P1 = ref_points_struct(pts1, keep); P2 = ref_points_struct(pts2, keep)
+    a = np.ascontiguousarray(p1_of_feat, np.int32); b = np.ascontiguousarray(p2_of_feat, np.int32)
+    R = np.ascontiguousarray(R12, np.float32); t = np.ascontiguousarray(t12, np.float32); out = np.empty(K1.n, np.int32)
+    n = ref_match().ref_search_by_sim3(C.byref(K1), C.byref(K2), C.byref(P1), _p(a), C.byref(P2), _p(b), C.c_float(s12), _p(R), _p(t), C.c_float(th), _p(out))
+    return out, n
+
+
+def ref_search_by_projection_last(g_cur, g_last, intr, t_cur, points, last_point, last_outlier, feat_blocked, th, check_ori=True):
+    keep = []; Cur = ref_image_struct(g_cur, keep, intr=intr, t=t_cur); Last = ref_image_struct(g_last, keep, intr=intr)
+    P = ref_points_struct(points, keep)
+    lp = np.ascontiguousarray(last_point, np.int32); lo = np.ascontiguousarray(last_outlier, np.uint8); fb = np.ascontiguousarray(feat_blocked, np.uint8)
+    out = np.empty(Cur.n, np.int32)
+    n = ref_match().ref_search_by_projection_last(C.byref(Cur), C.byref(Last), C.byref(P), _p(lp), _p(lo), _p(fb), C.c_float(th), int(check_ori), _p(out))
+    return out, n
+
+
+def ref_search_by_projection_reloc(g_cur, g_kf, intr, t_cur, points, kf_point, already_found, feat_blocked, th, orb_dist, check_ori=True):
+    keep = []; Cur = ref_image_struct(g_cur, keep, intr=intr, t=t_cur); KF = ref_image_struct(g_kf, keep, intr=intr)
+    P = ref_points_struct(points, keep)
+    kp = np.ascontiguousarray(kf_point, np.int32); af = np.ascontiguousarray(already_found, np.uint8); fb = np.ascontiguousarray(feat_blocked, np.uint8)
+    out = np.empty(Cur.n, np.int32)
+    n = ref_match().ref_search_by_projection_reloc(C.byref(Cur), C.byref(KF), C.byref(P), _p(kp), _p(af), _p(fb), C.c_float(th), int(orb_dist),
+                                                   int(check_ori), _p(out))
+    return out, n
+
+
 def write_vocabulary_text(v, path):
     """the rows of make_vocabulary() in the format TemplatedVocabulary::saveToTextFile writes and loadFromTextFile reads
     (D/TemplatedVocabulary.h:1428-1448, :1338-1422); no trailing newline (the loader turns an empty last line into a node)"""

@@ -215,4 +215,122 @@ int ref_search_by_projection_track(const ref_image* fr, const ref_points* pts, c
   return n;
 }
 
+
+// ---- the overloads with a geometric prelude.  Keypoints of the keyframe that already hold a map point get a placeholder whose tag
+// encodes the keypoint (-1000 - j), so that Replace / vpReplacePoint outcomes can be read back as keypoint indices. ----------------
+static mpptr kf_holder(int j, int n_obs) { mpptr m(new MapPoint); m->tag = -1000 - j; m->nObs = n_obs; return m; }
+static int holder_feat(const mpptr& m) { return (m && m->tag <= -1000) ? -1000 - m->tag : -1; }
+
+// Fuse(pKF, vpMapPoints, th): out best_idx[i] = keypoint the reference fused point i with (-1: not fused); returns nFused.
+// kf_mp_obs[j] >= 0: keypoint j holds a map point with that many observations, -1: none
+int ref_fuse(const ref_image* kf, const int32_t* kf_mp_obs, const ref_points* pts, float th, int32_t* best_idx) {
+  kfptr K = make_kf(*kf);
+  for (int j = 0; j < kf->n; j++) if (kf_mp_obs[j] >= 0) K->mvpMapPoints[j] = kf_holder(j, kf_mp_obs[j]);
+  std::vector<mpptr> held = K->mvpMapPoints;
+  std::vector<mpptr> P = make_points(*pts, K.get());
+  ORBmatcher matcher(0.6f, true);
+  const int n = matcher.Fuse(K, P, th);
+  // where a map point sits in the keyframe: its placeholder's keypoint, or the keypoint it was added at
+  auto sits = [&](const mpptr& x) { return x->tag <= -1000 ? holder_feat(x) : (x->added.empty() ? -1 : (int)x->added.back().second); };
+  for (int i = 0; i < pts->m; i++) {
+    best_idx[i] = -1;
+    if (!P[i]->added.empty()) best_idx[i] = (int)P[i]->added.back().second;        // AddObservation(pKF, bestIdx)
+    else if (P[i]->replacedBy) best_idx[i] = sits(P[i]->replacedBy);                // pMP->Replace(pMPinKF)
+  }
+  std::vector<mpptr> all = held;                                                    // pMPinKF->Replace(pMP): pMPinKF is a placeholder or an
+  all.insert(all.end(), P.begin(), P.end());                                        // earlier point of the list that was added to the keyframe
+  for (size_t k = 0; k < all.size(); k++)
+    if (all[k] && all[k]->replacedBy && all[k]->replacedBy->tag >= 0 && all[k]->replacedBy->added.empty() && !all[k]->replacedBy->replacedBy) {
+      const int i = all[k]->replacedBy->tag;
+      if (best_idx[i] < 0) best_idx[i] = sits(all[k]);
+    }
+  return n;
+}
+
+// Fuse(pKF, Scw, vpPoints, th, vpReplacePoint)
+int ref_fuse_sim3(const ref_image* kf, const int32_t* kf_mp_obs, const float* Scw /*16*/, const ref_points* pts, float th, int32_t* best_idx) {
+  kfptr K = make_kf(*kf);
+  for (int j = 0; j < kf->n; j++) if (kf_mp_obs[j] >= 0) K->mvpMapPoints[j] = kf_holder(j, kf_mp_obs[j]);
+  std::vector<mpptr> P = make_points(*pts, K.get());
+  std::vector<mpptr> repl(pts->m);
+  ORBmatcher matcher(0.6f, true);
+  const int n = matcher.Fuse(K, mat_f32(Scw, 4, 4), P, th, repl);
+  for (int i = 0; i < pts->m; i++) {
+    best_idx[i] = -1;
+    // vpReplacePoint[i] is whatever sat at the keypoint: a placeholder, or an earlier point of the list that was added there
+    if (repl[i]) best_idx[i] = repl[i]->tag <= -1000 ? holder_feat(repl[i]) : (repl[i]->added.empty() ? -1 : (int)repl[i]->added.back().second);
+    else if (!P[i]->added.empty()) best_idx[i] = (int)P[i]->added.back().second;
+  }
+  return n;
+}
+
+// SearchByProjection(pKF, Scw, vpPoints, vpMatched, th): feat_matched[j] = vpMatched[j] != nullptr on entry.
+// out: match_of_feat[j] = point newly written to vpMatched[j] (-1 otherwise); remap[3*k..] = (point, idx_now, idx_new); returns nmatches
+int ref_search_by_projection_sim3(const ref_image* kf, const float* Scw, const ref_points* pts, const uint8_t* feat_matched, int th,
+                                  int32_t* match_of_feat, int32_t* remap, int32_t* n_remap) {
+  kfptr K = make_kf(*kf);
+  std::vector<mpptr> P = make_points(*pts, K.get());
+  for (int i = 0; i < pts->m; i++)                                 // a point the keyframe observes sits at that keypoint
+    if (pts->index_in_kf && pts->index_in_kf[i] >= 0) K->mvpMapPoints[pts->index_in_kf[i]] = P[i];
+  std::vector<mpptr> matched(kf->n);
+  for (int j = 0; j < kf->n; j++) if (feat_matched[j]) matched[j] = holder(1);
+  ORBmatcher matcher(0.75f, true);
+  const int n = matcher.SearchByProjection(K, mat_f32(Scw, 4, 4), P, matched, th);
+  for (int j = 0; j < kf->n; j++) match_of_feat[j] = (matched[j] && matched[j]->tag >= 0) ? matched[j]->tag : -1;
+  *n_remap = (int)K->remapped.size() / 3;
+  for (size_t k = 0; k < K->remapped.size(); k++) remap[k] = K->remapped[k];
+  return n;
+}
+
+// SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th): p1_of_feat / p2_of_feat = map point index held by each keypoint (-1 none)
+int ref_search_by_sim3(const ref_image* k1, const ref_image* k2, const ref_points* pts1, const int32_t* p1_of_feat, const ref_points* pts2,
+                       const int32_t* p2_of_feat, float s12, const float* R12, const float* t12, float th, int32_t* match12) {
+  kfptr K1 = make_kf(*k1), K2 = make_kf(*k2);
+  std::vector<mpptr> P1 = make_points(*pts1, nullptr), P2 = make_points(*pts2, nullptr);
+  for (int j = 0; j < k1->n; j++) if (p1_of_feat[j] >= 0) K1->mvpMapPoints[j] = P1[p1_of_feat[j]];
+  for (int j = 0; j < k2->n; j++) if (p2_of_feat[j] >= 0) { K2->mvpMapPoints[j] = P2[p2_of_feat[j]]; P2[p2_of_feat[j]]->tag = 100000 + j; }
+  std::vector<mpptr> m12(k1->n);
+  ORBmatcher matcher(0.75f, true);
+  const int n = matcher.SearchBySim3(K1, K2, m12, s12, mat_f32(R12, 3, 3), mat_f32(t12, 3, 1), th);
+  for (int j = 0; j < k1->n; j++) match12[j] = m12[j] ? m12[j]->tag - 100000 : -1;   // the keypoint of KF2 whose point was matched
+  return n;
+}
+
+// SearchByProjection(CurrentFrame, LastFrame, th): last-frame keypoint i holds point last_point[i] (-1 none); last_outlier flags
+int ref_search_by_projection_last(const ref_image* cur, const ref_image* last, const ref_points* pts, const int32_t* last_point,
+                                  const uint8_t* last_outlier, const uint8_t* feat_blocked, float th, int check_ori, int32_t* match_of_feat) {
+  frameptr L = make_frame(*last);
+  frameptr F = make_frame(*cur);                      // the statics (bounds, intrinsics, grid) must be the current frame's: build it last
+  std::vector<mpptr> P = make_points(*pts, nullptr);
+  for (int i = 0; i < last->n; i++) { if (last_point[i] >= 0) { L->mvpMapPoints[i] = P[last_point[i]]; P[last_point[i]]->tag = i; } L->mvbOutlier[i] = last_outlier[i] != 0; }
+  for (int j = 0; j < cur->n; j++) if (feat_blocked[j]) F->mvpMapPoints[j] = holder(1);
+  ORBmatcher matcher(0.9f, check_ori != 0);
+  const int n = matcher.SearchByProjection(*F, *L, th);
+  for (int j = 0; j < cur->n; j++) {
+    const mpptr& m = F->mvpMapPoints[j];
+    match_of_feat[j] = (m && m->tag >= 0) ? m->tag : -1;   // tag = the last-frame keypoint the point came from; cleared = null = -1
+  }
+  return n;
+}
+
+// SearchByProjection(CurrentFrame, pKF, sAlreadyFound, th, ORBdist): keyframe keypoint i holds point kf_point[i] (-1 none)
+int ref_search_by_projection_reloc(const ref_image* cur, const ref_image* kf, const ref_points* pts, const int32_t* kf_point,
+                                   const uint8_t* already_found, const uint8_t* feat_blocked, float th, int orb_dist, int check_ori,
+                                   int32_t* match_of_feat) {
+  kfptr K = make_kf(*kf);
+  frameptr F = make_frame(*cur);
+  std::vector<mpptr> P = make_points(*pts, nullptr);
+  std::set<mpptr> found;
+  for (int i = 0; i < kf->n; i++) if (kf_point[i] >= 0) { K->mvpMapPoints[i] = P[kf_point[i]]; P[kf_point[i]]->tag = i; }
+  for (int i = 0; i < pts->m; i++) if (already_found[i]) found.insert(P[i]);
+  for (int j = 0; j < cur->n; j++) if (feat_blocked[j]) F->mvpMapPoints[j] = holder(1);
+  ORBmatcher matcher(0.9f, check_ori != 0);
+  const int n = matcher.SearchByProjection(*F, K, found, th, orb_dist);
+  for (int j = 0; j < cur->n; j++) {
+    const mpptr& m = F->mvpMapPoints[j];
+    match_of_feat[j] = (m && m->tag >= 0) ? m->tag : -1;
+  }
+  return n;
+}
+
 }  // extern "C"

@@ -109,3 +109,174 @@ def test_search_by_projection_track(ref, seed, th, nnratio):
     got, n = ref.search_by_projection_track(g, oq, (n_obs > 0).astype(np.uint8), blocked, nnratio)
     want, wn = ref.ref_search_by_projection_track(g, points, blocked, th, nnratio)
     assert n == wn and np.array_equal(got, want) and n > 200
+
+
+# ---- the overloads with a geometric prelude ------------------------------------------------------------------------------------
+# The reference runs its own prelude (cv::Mat pose algebra, projection, image bounds, distance / angle gates, PredictScale) in front of
+# the window search; the oracle starts at the window.  To compare them the scene is built so that the prelude's arithmetic is EXACT in
+# float32 (identity rotations, dyadic translations and depths, power-of-two focal length): whatever rounding a matrix product uses, the
+# projected pixel is the intended quarter-pixel position, and the gate quantities sit far from their thresholds.
+INTR = (f32(512.0), f32(512.0), f32(376.0), f32(240.0))
+BOUNDS = (0.0, 0.0, 752.0, 480.0)
+SF = np.empty(8, f32); SF[0] = 1
+for _i in range(1, 8):
+    SF[_i] = f32(SF[_i - 1] * f32(1.2))
+CATS = ("good", "behind", "outside", "too_far", "too_near", "bad_angle", "bad")
+
+
+def _scene(seed, n=900, m=1300, th=3.0, t=(0.25, -0.5, 1.0), scale=1.0, th_is_int=False):
+    """keypoints of one image + map points whose projection through Tcw = [I | t] (or Scw = scale * [I | t]) lands on intended pixels"""
+    rng = np.random.default_rng(seed)
+    g = sm.make_grid(n=n, seed=seed, bounds=BOUNDS)
+    fx, fy, cx, cy = [float(v) for v in INTR]
+    src = rng.integers(0, n, m)
+    dup = rng.random(m) < 0.12
+    for i in range(1, m):
+        if dup[i]:
+            src[i] = src[rng.integers(0, i)]
+    uv = np.round((g["kp_xy"][src].astype(np.float64) + rng.normal(0, 1.5, (m, 2))) * 4) / 4
+    cat = rng.choice(len(CATS), size=m, p=[0.64, 0.06, 0.06, 0.06, 0.06, 0.06, 0.06])
+    uv[cat == CATS.index("outside")] += np.array([900.0, 0.0])
+    zc = rng.choice([2.0, 4.0, 8.0], m)
+    zc[cat == CATS.index("behind")] *= -1
+    cam = np.stack([(uv[:, 0] - cx) * zc / fx, (uv[:, 1] - cy) * zc / fy, zc], 1)        # exact dyadic numbers
+    world = cam - np.asarray(t, np.float64)                                             # R = I: Xc = Xw + t
+    assert np.array_equal(world.astype(f32).astype(np.float64), world) and np.array_equal(cam.astype(f32).astype(np.float64), cam)
+    dist = np.sqrt((cam * cam).sum(1))
+    level = np.clip(g["octave"][src] + rng.choice([0, 0, 0, 1, 1, -1], m), 0, 7).astype(np.int32)
+    max_d = dist * 1.2 ** (level - 0.5)                                                  # PredictScale lands mid-interval on `level`
+    min_d = dist / 3.0
+    max_d[cat == CATS.index("too_far")] = dist[cat == CATS.index("too_far")] / 2.0
+    level[cat == CATS.index("too_far")] = 0
+    min_d[cat == CATS.index("too_near")] = dist[cat == CATS.index("too_near")] * 2.0
+    normal = cam / dist[:, None]
+    normal[cat == CATS.index("bad_angle")] *= -1
+    desc = sm.flip_bits(g["desc"][src], rng.integers(0, 70, m), rng)
+    n_obs = rng.integers(1, 6, m).astype(np.int32)
+    points = dict(pos=world.astype(f32), normal=normal.astype(f32), min_dist=min_d.astype(f32), max_dist=max_d.astype(f32), desc=desc,
+                  bad=(cat == CATS.index("bad")).astype(np.uint8), n_obs=n_obs)
+    thf = f32(int(th)) if th_is_int else f32(th)
+    # a few keypoints of make_grid lie outside the image on purpose; a point projected next to one of them fails the bounds test:
+    # KeyFrame::IsInImage is half-open (KeyFrame.cpp:1203), the Frame overloads compare against [mnMin, mnMax] inclusively
+    in_kf_image = (uv[:, 0] >= 0) & (uv[:, 0] < 752) & (uv[:, 1] >= 0) & (uv[:, 1] < 480)
+    in_frame_image = (uv[:, 0] >= 0) & (uv[:, 0] <= 752) & (uv[:, 1] >= 0) & (uv[:, 1] <= 480)
+    q = dict(valid=((cat == 0) & in_kf_image).astype(np.uint8), uv=uv.astype(f32), radius=(thf * SF[level]).astype(f32), level=level, desc=desc,
+             angle=np.zeros(m, f32))
+    Scw = np.eye(4, dtype=f32) * f32(scale); Scw[:3, 3] = np.asarray(t, f32) * f32(scale); Scw[3, 3] = 1
+    return dict(g=g, points=points, q=q, cat=cat, t=np.asarray(t, f32), Scw=Scw, rng=rng, src=src, in_frame_image=in_frame_image)
+
+
+def _holders(rng, n, frac=0.3):
+    return np.where(rng.random(n) < frac, rng.integers(1, 6, n), -1).astype(np.int32)
+
+
+@pytest.mark.parametrize("seed,th", [(20, 3.0), (21, 5.0)])
+def test_fuse(ref, seed, th):
+    S = _scene(seed, th=th)
+    rng = S["rng"]; m = len(S["cat"])
+    held = _holders(rng, 900)
+    in_kf = np.where(rng.random(m) < 0.08, rng.integers(0, 900, m), -1).astype(np.int32)      # IsInKeyFrame -> skipped
+    dnr = (rng.random(m) < 0.05).astype(np.uint8)                                             # mbDoNotReplace -> skipped
+    pts = dict(S["points"], index_in_kf=in_kf, do_not_replace=dnr)
+    q = dict(S["q"], valid=(S["q"]["valid"].astype(bool) & (in_kf < 0) & (dnr == 0)).astype(np.uint8))
+    got, n = ref.fuse_search(S["g"], q, sm.INV_LEVEL_SIGMA2)
+    want, wn = ref.ref_fuse(S["g"], INTR, S["t"], held, pts, th)
+    assert n == wn and n > 150                                   # nFused
+    seen = want >= 0                                             # (a second point fused onto a replaced placeholder leaves no trace: not compared)
+    assert np.array_equal(got[seen], want[seen]) and seen.sum() >= 0.9 * n
+
+
+@pytest.mark.parametrize("seed,th,scale", [(22, 4.0, 2.0), (23, 3.0, 0.5)])
+def test_fuse_sim3(ref, seed, th, scale):
+    S = _scene(seed, th=th, scale=scale)
+    held = _holders(S["rng"], 900)
+    got, n = ref.fuse_search(S["g"], S["q"], None)
+    want, wn = ref.ref_fuse(S["g"], INTR, None, held, S["points"], th, Scw=S["Scw"])
+    assert n == wn and np.array_equal(got, want) and n > 150
+
+
+@pytest.mark.parametrize("seed,scale", [(24, 2.0), (25, 1.0)])
+def test_search_by_projection_sim3(ref, seed, scale):
+    S = _scene(seed, th=10, scale=scale, th_is_int=True)
+    rng = S["rng"]; m = len(S["cat"])
+    matched = (rng.random(900) < 0.2).astype(np.uint8)
+    existing = np.where(rng.random(m) < 0.12, rng.integers(0, 900, m), -1).astype(np.int32)
+    existing[np.unique(existing[existing >= 0], return_index=True)[1]] = existing[np.unique(existing[existing >= 0], return_index=True)[1]]
+    pts = dict(S["points"], index_in_kf=existing)
+    best, mof, n = ref.search_by_projection_sim3(S["g"], S["q"], matched, existing)
+    wmof, remap, wn = ref.ref_search_by_projection_sim3(S["g"], INTR, S["Scw"], pts, matched, 10)
+    assert n == wn and np.array_equal(mof, wmof) and n > 100
+    # RemapMapPointMatch calls: (point, where it sat, where it goes) for every observed point that found a keypoint
+    exp = [(i, int(existing[i]), int(best[i])) for i in range(m) if best[i] >= 0 and existing[i] >= 0]
+    assert [tuple(r) for r in remap.tolist()] == exp and len(exp) > 10
+
+
+def test_search_by_sim3(ref):
+    rng = np.random.default_rng(26)
+    fx, fy, cx, cy = [float(v) for v in INTR]
+    g1 = sm.make_grid(n=700, seed=27, bounds=BOUNDS); g2 = sm.make_grid(n=720, seed=28, bounds=BOUNDS)
+    share = rng.permutation(700)[:350]                           # keypoint share[k] of KF1 and keypoint k of KF2 see the same thing
+    g2["desc"][:350] = sm.flip_bits(g1["desc"][share], rng.integers(0, 30, 350), rng); g2["octave"][:350] = g1["octave"][share]
+    t1, t2, t12, s12 = np.array([0.5, 0.25, -1.0]), np.array([-0.25, 1.0, 0.5]), np.array([1.0, -0.5, 0.25]), 2.0
+
+    def side(src_g, dst_g, src_idx, dst_idx, to_dst, t_src):
+        """one map point per keypoint of the source keyframe; those in src_idx project next to dst_idx's keypoints in the other keyframe"""
+        n = src_g["desc"].shape[0]
+        uv = np.round(rng.uniform([30, 30], [720, 450], (n, 2)) * 4) / 4
+        uv[src_idx] = np.round((dst_g["kp_xy"][dst_idx].astype(np.float64) + rng.normal(0, 1.0, (len(src_idx), 2))) * 4) / 4
+        zc = rng.choice([2.0, 4.0, 8.0], n)
+        c_dst = np.stack([(uv[:, 0] - cx) * zc / fx, (uv[:, 1] - cy) * zc / fy, zc], 1)   # in the destination camera
+        world = to_dst(c_dst) - t_src                                                    # source camera frame -> world (R = I)
+        assert np.array_equal(world.astype(f32).astype(np.float64), world)
+        dist = np.sqrt((c_dst * c_dst).sum(1)); level = src_g["octave"].astype(np.int32)
+        valid = rng.random(n) < 0.85
+        pts = dict(pos=world.astype(f32), min_dist=(dist / 3).astype(f32), max_dist=(dist * 1.2 ** (level - 0.5)).astype(f32), desc=src_g["desc"],
+                   bad=(~valid).astype(np.uint8))
+        q = dict(valid=valid.astype(np.uint8), uv=uv.astype(f32), radius=(f32(7.5) * SF[level]).astype(f32), level=level, desc=src_g["desc"])
+        return pts, q
+    # c2 = (1/s12) (c1 - t12)  <=>  c1 = s12 c2 + t12   (R12 = I), S/ORBmatcher.cpp:1139-1142
+    p1, q12 = side(g1, g2, share, np.arange(350), lambda c2: s12 * c2 + t12, t1)
+    p2, q21 = side(g2, g1, np.arange(350), share, lambda c1: (c1 - t12) / s12, t2)
+    got, n = ref.search_by_sim3(g1, g2, q12, q21)
+    want, wn = ref.ref_search_by_sim3(g1, g2, INTR, t1.astype(f32), t2.astype(f32), p1, np.arange(700), p2, np.arange(720), s12, np.eye(3, dtype=f32),
+                                      t12.astype(f32), 7.5)
+    assert n == wn and np.array_equal(got, want) and n > 80
+
+
+@pytest.mark.parametrize("seed,th,ori", [(30, 7.0, True), (31, 15.0, False)])
+def test_search_by_projection_last_frame(ref, seed, th, ori):
+    S = _scene(seed, n=900, m=800, th=th)                        # one map point per keypoint of the last frame
+    rng = S["rng"]; m = 800
+    g_last = sm.make_grid(n=m, seed=seed + 5, bounds=BOUNDS)
+    g_last["octave"] = S["q"]["level"].copy()                    # nLastOctave drives the window and the level range
+    g_last["angle"] = ((S["g"]["angle"][S["src"]] + rng.normal(0, 4, m) + np.where(rng.random(m) < 0.1, 120, 0)) % 360).astype(f32)
+    has_point = rng.random(m) < 0.9; outlier = (rng.random(m) < 0.08).astype(np.uint8)
+    last_point = np.where(has_point, np.arange(m), -1).astype(np.int32)
+    blocked = (rng.random(900) < 0.2).astype(np.uint8)
+    # what the reference lets through here (:1376-1396): a point, not an outlier, 1/z >= 0, inside [mnMin, mnMax] (inclusive)
+    cat = S["cat"]
+    ok = has_point & (outlier == 0) & (cat != CATS.index("behind")) & S["in_frame_image"]
+    q = dict(S["q"], valid=ok.astype(np.uint8), angle=g_last["angle"])
+    has_obs = (S["points"]["n_obs"] > 0).astype(np.uint8)
+    got, n = ref.search_by_projection_frame(S["g"], q, has_obs, blocked, False, 100, ori)
+    want, wn = ref.ref_search_by_projection_last(S["g"], g_last, INTR, S["t"], S["points"], last_point, outlier, blocked, th, ori)
+    assert n == wn and np.array_equal(np.where(got == -2, -1, got), want) and n > 150
+
+
+@pytest.mark.parametrize("seed,th,orb_dist,ori", [(32, 10.0, 100, True), (33, 3.0, 64, False)])
+def test_search_by_projection_relocalisation(ref, seed, th, orb_dist, ori):
+    S = _scene(seed, n=900, m=800, th=th)
+    rng = S["rng"]; m = 800
+    g_kf = sm.make_grid(n=m, seed=seed + 5, bounds=BOUNDS)
+    g_kf["angle"] = ((S["g"]["angle"][S["src"]] + rng.normal(0, 4, m) + np.where(rng.random(m) < 0.1, 120, 0)) % 360).astype(f32)
+    has_point = rng.random(m) < 0.9; found = (rng.random(m) < 0.08).astype(np.uint8)
+    kf_point = np.where(has_point, np.arange(m), -1).astype(np.int32)
+    blocked = (rng.random(900) < 0.2).astype(np.uint8)
+    # (:1500-1530): a good point not already found, inside the image, inside its distance range — this overload has neither a depth nor a
+    # viewing-angle gate, so a point BEHIND the camera that projects into the image is searched like any other (1/z < 0 flips x and y back)
+    cat = S["cat"]
+    ok = has_point & (found == 0) & np.isin(cat, [CATS.index("good"), CATS.index("bad_angle"), CATS.index("behind")]) & S["in_frame_image"]
+    q = dict(S["q"], valid=ok.astype(np.uint8), angle=g_kf["angle"])
+    got, n = ref.search_by_projection_frame(S["g"], q, np.ones(m, np.uint8), blocked, True, orb_dist, ori)
+    want, wn = ref.ref_search_by_projection_reloc(S["g"], g_kf, INTR, S["t"], S["points"], kf_point, found, blocked, th, orb_dist, ori)
+    assert n == wn and np.array_equal(np.where(got == -2, -1, got), want) and n > 150
