@@ -10,8 +10,9 @@
 //   Schur + solve .. G/core/block_solver.hpp:354-486  (+ direct LDL^T, G/solvers/linear_solver_eigen.h:106-133)
 //   edge ........... G/types/types_six_dof_expmap.{h:80-109,cpp:103-147}
 //   Huber .......... G/core/robust_kernel_impl.cpp:77-91, G/core/base_edge.h:96-102
-// Parity pinning: no reference tests exist for this path and g2o cannot be built here (no Eigen);
-// pinned by scipy / finite-difference witnesses in tests/test_oracle_ba.py.
+// Parity pinning: no reference tests exist for this path and g2o as a whole cannot be built here (no Eigen);
+// pinned by scipy / finite-difference witnesses in tests/test_oracle_ba.py, and the LM control flow of orc_ba_solve by the
+// reference's own optimization_algorithm_levenberg.cpp compiled over these pieces (ref_lm_wrap.cpp, tests/test_oracle_vs_reference_lm.py).
 #include "oracle.h"
 
 #include <chrono>

@@ -79,7 +79,7 @@ def _ba_struct(p, keep):
 
 
 def ba_solve(p, iterations=20, robust=True, huber_delta=np.sqrt(5.99), lambda_init=-1.0, max_trials=10,
-             chi2_in=None, stop=None):
+             chi2_in=None, stop=None, fn=None):
     keep = []
     prob = _ba_struct(p, keep)
     poses = np.empty((p.K, 7)); points = np.empty((p.P, 3))
@@ -88,7 +88,7 @@ def ba_solve(p, iterations=20, robust=True, huber_delta=np.sqrt(5.99), lambda_in
     trace = np.zeros((max(iterations, 1), TRACE_COLS))
     opt = _BAOptions(iterations, int(robust), float(huber_delta), float(lambda_init), max_trials, _p(stop))
     res = _BAResult(_p(poses), _p(points), _p(chi2), _p(depth), _p(trace), trace.shape[0])
-    rc = lib().orc_ba_solve(C.byref(prob), C.byref(opt), C.byref(res))
+    rc = (fn or lib().orc_ba_solve)(C.byref(prob), C.byref(opt), C.byref(res))
     assert rc == 0
     return dict(poses=poses, points=points, chi2=chi2, depth_pos=depth, trace=trace[:res.trace_len],
                 iters_done=res.iters_done, trials_total=res.trials_total, chi2_initial=res.chi2_initial,
@@ -495,6 +495,28 @@ def ref_orb_extract(img, cfg=None, allocator="bump"):
     kps = np.frombuffer(raw[4:4 + n * KP_DTYPE.itemsize], KP_DTYPE).copy()
     desc = np.frombuffer(raw[4 + n * KP_DTYPE.itemsize:], np.uint8).reshape(n, 32).copy()
     return kps, desc
+
+
+# ---- the reference's own Levenberg-Marquardt driver on the oracle's linear algebra (oracle/_ref/liblm_ref.so) -------------------------
+_REF_LM = None
+
+
+def ref_lm():
+    global _REF_LM
+    if _REF_LM is None:
+        if build_ref() is None:
+            return None
+        so = os.path.join(_HERE, "_ref", "liblm_ref.so")
+        if not os.path.exists(so):
+            return None
+        _REF_LM = C.CDLL(so)
+    return _REF_LM
+
+
+def ref_ba_solve(p, **kw):
+    """ba_solve() with g2o's own OptimizationAlgorithmLevenberg::solve (compiled from the reference tree, oracle/ref_lm_wrap.cpp)
+    deciding lambda, trials and termination; trace column 3 (rho) is NaN — it is a local of the reference's function."""
+    return ba_solve(p, fn=ref_lm().ref_lm_solve, **kw)
 
 
 # ---- the reference's own ORBmatcher.cpp on stand-in Frame / KeyFrame / MapPoint (oracle/_ref/libmatch_ref.so) -----------------------
