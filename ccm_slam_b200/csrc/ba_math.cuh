@@ -115,7 +115,7 @@ CCM_HD Pose se3_exp_times(const double upd[6], const Pose& T) {
 
 // Huber: returns rho(e) and the weight rho'(e)
 CCM_HD void huber(double e, double delta, double& rho0, double& rho1) {
-  const double dsqr = delta * delta;
+  const double dsqr = (double)(float)(delta * delta);  // the vendored kernel keeps delta^2 in a float (G/core/robust_kernel_impl.h:84)
   if (e <= dsqr) {
     rho0 = e; rho1 = 1.0;
   } else {

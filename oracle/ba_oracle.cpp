@@ -12,7 +12,9 @@
 //   Huber .......... G/core/robust_kernel_impl.cpp:77-91, G/core/base_edge.h:96-102
 // Parity pinning: no reference tests exist for this path and g2o as a whole cannot be built here (no Eigen);
 // pinned by scipy / finite-difference witnesses in tests/test_oracle_ba.py, and the LM control flow of orc_ba_solve by the
-// reference's own optimization_algorithm_levenberg.cpp compiled over these pieces (ref_lm_wrap.cpp, tests/test_oracle_vs_reference_lm.py).
+// reference's own optimization_algorithm_levenberg.cpp compiled over these pieces (ref_lm_wrap.cpp, tests/test_oracle_vs_reference_lm.py),
+// edge errors / Jacobians / Huber / constructQuadraticForm by the reference's own types compiled over a stand-in Eigen
+// (ref_g2o_wrap.cpp, tests/test_oracle_vs_reference_g2o.py) — bit for bit.
 #include "oracle.h"
 
 #include <chrono>
@@ -78,8 +80,10 @@ inline void edge_error(const BA& s, Edge& e) {  // computeError, G/types/types_s
 inline double edge_chi2(const Edge& e) {  // BaseEdge::chi2, G/core/base_edge.h:58-61
   return e.err[0] * (e.w * e.err[0]) + e.err[1] * (e.w * e.err[1]);
 }
-inline void huber(double e, double delta, double rho[3]) {  // G/core/robust_kernel_impl.cpp:77-91
-  double dsqr = delta * delta;
+inline void huber(double e, double delta, double rho[3]) {  // G/core/robust_kernel_impl.cpp:64-91
+  // the vendored RobustKernelHuber keeps delta^2 in a FLOAT member (G/core/robust_kernel_impl.h:84, set in setDelta): both the
+  // inlier test and rho(e) use the rounded value.  Found by compiling the reference's kernel (oracle/ref_g2o_wrap.cpp).
+  double dsqr = (double)(float)(delta * delta);
   if (e <= dsqr) {
     rho[0] = e; rho[1] = 1.; rho[2] = 0.;
   } else {
@@ -99,9 +103,11 @@ inline void linearize(const BA& s, const Edge& e, Lin& L) {
   double tmp[6] = {fx, 0, -x / z * fx, 0, fy, -y / z * fy};
   double R[9];
   q2R(T.r, R);
+  // `-1./z * tmp * R` groups as ((-1/z) * tmp) * R  (types_six_dof_expmap.cpp:127; pinned by oracle/ref_g2o_wrap.cpp)
+  double st[6];
+  for (int i = 0; i < 6; i++) st[i] = -1. / z * tmp[i];
   for (int i = 0; i < 2; i++)
-    for (int j = 0; j < 3; j++)
-      L.Jl[i * 3 + j] = -1. / z * (tmp[i * 3] * R[j] + tmp[i * 3 + 1] * R[3 + j] + tmp[i * 3 + 2] * R[6 + j]);
+    for (int j = 0; j < 3; j++) L.Jl[i * 3 + j] = st[i * 3] * R[j] + st[i * 3 + 1] * R[3 + j] + st[i * 3 + 2] * R[6 + j];
   L.Jp[0] = x * y / z_2 * fx;
   L.Jp[1] = -(1 + (x * x / z_2)) * fx;
   L.Jp[2] = y / z * fx;
@@ -248,7 +254,10 @@ void build_system(BA& s) {
       for (int i = 0; i < 6; i++) {
         b_p[i] += L.Jp[i] * or0 + L.Jp[6 + i] * or1;
         for (int j = 0; j < 6; j++) Hp[i * 6 + j] += L.Jp[i] * wo * L.Jp[j] + L.Jp[6 + i] * wo * L.Jp[6 + j];
-        for (int j = 0; j < 3; j++) W[i * 3 + j] += L.Jp[i] * wo * L.Jl[j] + L.Jp[6 + i] * wo * L.Jl[3 + j];
+        // the transposed pose-landmark block (block_solver.hpp:244): with a kernel  (B^T wOmega) A, without one  B^T (A^T Omega)^T —
+        // the weight multiplies the other factor first (base_binary_edge.hpp:78-81 vs :98-101)
+        if (e.robust) for (int j = 0; j < 3; j++) W[i * 3 + j] += L.Jp[i] * wo * L.Jl[j] + L.Jp[6 + i] * wo * L.Jl[3 + j];
+        else for (int j = 0; j < 3; j++) W[i * 3 + j] += L.Jp[i] * (L.Jl[j] * wo) + L.Jp[6 + i] * (L.Jl[3 + j] * wo);
       }
     }
   }

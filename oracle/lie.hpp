@@ -282,9 +282,13 @@ inline void sim3_log(const Sim3& S, double res[7]) {
     }
   }
   skew(omega, Om);
-  mat3mul(Om, Om, Om2);
+  // sim3.h:221 writes  A*Omega + B*Omega*Omega + C*I : C++ groups it (B*Omega)*Omega, unlike the exponential's B*Omega2
+  // (found by compiling the reference's header, oracle/ref_g2o_wrap.cpp; a last-bit matter that the numeric Jacobians amplify)
+  double BOm[9];
+  for (int i = 0; i < 9; i++) BOm[i] = B * Om[i];
+  mat3mul(BOm, Om, Om2);
   double W[9], ups[3];
-  for (int i = 0; i < 9; i++) W[i] = A * Om[i] + B * Om2[i] + C * I[i];
+  for (int i = 0; i < 9; i++) W[i] = A * Om[i] + Om2[i] + C * I[i];
   lu3_solve(W, S.t, ups);
   for (int i = 0; i < 3; i++) { res[i] = omega[i]; res[i + 3] = ups[i]; }
   res[6] = sigma;

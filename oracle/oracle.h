@@ -12,12 +12,13 @@
  * the oracle is pinned by independent witnesses instead: scipy (sparse solve,
  * finite differences, Rotation) for the BA/PGO part and Python cv2 4.13 for the
  * ORB primitives (tests/test_oracle_*.py, fixtures under tests/golden/).
- * "parity unpinned by the reference's own tests" — see DESIGN.md §3.  Four pieces do build from the reference's own sources, in
+ * "parity unpinned by the reference's own tests" — see DESIGN.md §3.  Five pieces do build from the reference's own sources, in
  * place, against the stand-in headers of oracle/ref_stub/ (oracle/Makefile `ref` -> oracle/_ref/): cslam/src/ORBextractor.cpp (on the
  * oracle's OpenCV-primitive restatements), cslam/src/ORBmatcher.cpp (on stand-in Frame / KeyFrame / MapPoint), the vendored DBoW2, and
- * g2o's Levenberg-Marquardt driver (optimization_algorithm*.cpp over stand-in SparseOptimizer / Solver classes backed by ba_oracle.cpp).
+ * g2o's Levenberg-Marquardt driver (optimization_algorithm*.cpp over stand-in SparseOptimizer / Solver classes backed by ba_oracle.cpp), and
+ * g2o's vertex / edge types, Lie groups, base-edge templates and Huber kernel (over a stand-in for Eigen's small fixed-size arithmetic).
  * orb_oracle.cpp, match_oracle.cpp, proj_oracle.cpp and bow_oracle.cpp are held to that code exactly
- * (tests/test_oracle_vs_reference_{orb,matchers,dbow2,lm}.py).
+ * (tests/test_oracle_vs_reference_{orb,matchers,dbow2,lm,g2o}.py).
  *
  * Citations: G/ = cslam/thirdparty/g2o/g2o/, S/ = cslam/src/ under /root/reference.
  */
@@ -117,6 +118,8 @@ void orc_sim3_log(const double s[8], double out[7]);                   /* G/type
 void orc_sim3_mul(const double a[8], const double b[8], double out[8]);/* G/types/sim3.h:266-272 */
 void orc_sim3_inv(const double a[8], double out[8]);                   /* G/types/sim3.h:233-236 */
 void orc_pgo_edge_error(const double meas[8], const double si[8], const double sj[8], double err[7]);
+void orc_pgo_edge_jacobian(const double meas[8], const double si[8], const double sj[8], int fix_scale, double Ji[49], double Jj[49]);
+void orc_sim3_map(const double s[8], const double x[3], double out[3]);  /* G/types/sim3.h:144-146 */
 
 /* ---- single-vertex optimisations (single_oracle.cpp) ---- */
 typedef struct {
@@ -145,6 +148,9 @@ typedef struct {
 } orc_sim3_opt_problem;
 /* Optimizer::OptimizeSim3 (S/Optimizer.cpp:861-1056); returns nIn (0 and S12 untouched when fewer than 10 pairs survive) */
 int orc_sim3_optimize(const orc_sim3_opt_problem* p, double* S12_out /*8*/, uint8_t* inlier /*n: vpMatches1[i] kept*/);
+/* pieces: the quadratic form all edges build at a given estimate — H (DxD row-major), b (D), err (2 per edge; Sim3: edge 2i / 2i+1) */
+void orc_pose_opt_build(const orc_pose_opt_problem* p, const double* Tcw, int robust, double delta, double* H, double* b, double* err);
+void orc_sim3_opt_build(const orc_sim3_opt_problem* p, const double* S12, int robust, double delta, double* H, double* b, double* err);
 
 #ifdef __cplusplus
 }

@@ -254,3 +254,13 @@ extern "C" void orc_pgo_edge_error(const double meas[8], const double si[8], con
   e.C = sim3_load(meas);
   edge_err(e, sim3_load(si), sim3_load(sj), err);
 }
+extern "C" void orc_pgo_edge_jacobian(const double meas[8], const double si[8], const double sj[8], int fix_scale, double Ji[49], double Jj[49]) {
+  PGO s;
+  s.fix_scale = fix_scale != 0;
+  s.v = {sim3_load(si), sim3_load(sj)};
+  PEdge e;
+  e.i = 0; e.j = 1; e.C = sim3_load(meas);
+  numeric_jac(s, e, true, true, Ji, Jj, false);
+}
+extern "C" void orc_sim3_map(const double s[8], const double x[3], double out[3]) { sim3_map(sim3_load(s), x, out); }
+

@@ -97,21 +97,23 @@ def ba_solve(p, iterations=20, robust=True, huber_delta=np.sqrt(5.99), lambda_in
                             structure=res.t_structure_s, total=res.t_total_s))
 
 
-def ba_linearize(p, robust=True, huber_delta=np.sqrt(5.99)):
+def ba_linearize(p, robust=True, huber_delta=np.sqrt(5.99), fn=None):
     keep = []
     prob = _ba_struct(p, keep)
     err = np.empty((p.E, 2)); Jp = np.empty((p.E, 2, 6)); Jl = np.empty((p.E, 2, 3))
     rho1 = np.empty(p.E); chi2 = np.empty(p.E)
-    tot = lib().orc_ba_linearize(C.byref(prob), int(robust), C.c_double(huber_delta), _p(err), _p(Jp), _p(Jl), _p(rho1), _p(chi2))
+    fn = fn or lib().orc_ba_linearize
+    fn.restype = C.c_double
+    tot = fn(C.byref(prob), int(robust), C.c_double(huber_delta), _p(err), _p(Jp), _p(Jl), _p(rho1), _p(chi2))
     return dict(err=err, Jpose=Jp, Jpoint=Jl, rho1=rho1, chi2=chi2, chi2_robust_sum=tot)
 
 
-def ba_build(p, robust=True, huber_delta=np.sqrt(5.99)):
+def ba_build(p, robust=True, huber_delta=np.sqrt(5.99), fn=None):
     keep = []
     prob = _ba_struct(p, keep)
     Hpp = np.empty((p.K, 6, 6)); bp = np.empty((p.K, 6)); Hll = np.empty((p.P, 3, 3)); bl = np.empty((p.P, 3))
     W = np.empty((p.E, 6, 3))
-    lib().orc_ba_build(C.byref(prob), int(robust), C.c_double(huber_delta), _p(Hpp), _p(bp), _p(Hll), _p(bl), _p(W))
+    (fn or lib().orc_ba_build)(C.byref(prob), int(robust), C.c_double(huber_delta), _p(Hpp), _p(bp), _p(Hll), _p(bl), _p(W))
     return dict(Hpp=Hpp, bp=bp, Hll=Hll, bl=bl, W=W)
 
 
@@ -517,6 +519,83 @@ def ref_ba_solve(p, **kw):
     """ba_solve() with g2o's own OptimizationAlgorithmLevenberg::solve (compiled from the reference tree, oracle/ref_lm_wrap.cpp)
     deciding lambda, trials and termination; trace column 3 (rho) is NaN — it is a local of the reference's function."""
     return ba_solve(p, fn=ref_lm().ref_lm_solve, **kw)
+
+
+# ---- g2o's own vertex / edge types, Lie groups and Huber kernel (oracle/_ref/libg2o_types_ref.so, oracle/ref_g2o_wrap.cpp) ---------------
+_REF_G2O = None
+
+
+def ref_g2o():
+    global _REF_G2O
+    if _REF_G2O is None:
+        if build_ref() is None:
+            return None
+        so = os.path.join(_HERE, "_ref", "libg2o_types_ref.so")
+        if not os.path.exists(so):
+            return None
+        _REF_G2O = C.CDLL(so)
+    return _REF_G2O
+
+
+class Pieces:
+    """The same piece-level entry points on either side: which='oracle' (liboracle.so, orc_*) or 'ref' (the reference's compiled
+    g2o types, ref_*).  Arrays in, arrays out; layouts as in oracle.h."""
+
+    def __init__(self, which):
+        self.l = lib() if which == "oracle" else ref_g2o()
+        self.pre = "orc_" if which == "oracle" else "ref_"
+
+    def _f(self, name):
+        return getattr(self.l, self.pre + name)
+
+    def vec(self, name, nout, *ins):
+        arrs = [np.ascontiguousarray(a, np.float64) for a in ins]
+        o = np.empty(nout)
+        self._f(name)(*[_p(a) for a in arrs], _p(o))
+        return o
+
+    def huber(self, e, delta):
+        o = np.empty(3)
+        self._f("huber")(C.c_double(e), C.c_double(delta), _p(o))
+        return o
+
+    def ba_linearize(self, p, **kw):
+        return ba_linearize(p, fn=self._f("ba_linearize"), **kw)
+
+    def ba_build(self, p, **kw):
+        return ba_build(p, fn=self._f("ba_build"), **kw)
+
+    def pose_opt_build(self, Tcw, Xw, uv, inv_sigma2, intr, robust, delta):
+        a = dict(Tcw=np.ascontiguousarray(Tcw, np.float64), Xw=np.ascontiguousarray(Xw, np.float32).reshape(-1, 3),
+                 uv=np.ascontiguousarray(uv, np.float32).reshape(-1, 2), w=np.ascontiguousarray(inv_sigma2, np.float32))
+        n = a["Xw"].shape[0]
+        prob = _PoseOpt(n, _p(a["Tcw"]), _p(a["Xw"]), _p(a["uv"]), _p(a["w"]), *[float(v) for v in intr])
+        H = np.empty((6, 6)); b = np.empty(6); err = np.empty((n, 2))
+        self._f("pose_opt_build")(C.byref(prob), _p(a["Tcw"]), int(robust), C.c_double(delta), _p(H), _p(b), _p(err))
+        return H, b, err
+
+    def sim3_opt_build(self, S12, P1c, P2c, uv1, uv2, w1, w2, K1, K2, fix_scale, robust, delta):
+        f32 = lambda x, c: np.ascontiguousarray(x, np.float32).reshape(-1, c) if c else np.ascontiguousarray(x, np.float32)
+        a = dict(S=np.ascontiguousarray(S12, np.float64), P1=f32(P1c, 3), P2=f32(P2c, 3), u1=f32(uv1, 2), u2=f32(uv2, 2), w1=f32(w1, 0), w2=f32(w2, 0))
+        n = a["P1"].shape[0]
+        prob = _Sim3Opt(n, _p(a["S"]), _p(a["P1"]), _p(a["P2"]), _p(a["u1"]), _p(a["u2"]), _p(a["w1"]), _p(a["w2"]),
+                        (C.c_float * 4)(*[float(v) for v in K1]), (C.c_float * 4)(*[float(v) for v in K2]), 0.0, int(bool(fix_scale)))
+        H = np.empty((7, 7)); b = np.empty(7); err = np.empty((2 * n, 2))
+        self._f("sim3_opt_build")(C.byref(prob), _p(a["S"]), int(robust), C.c_double(delta), _p(H), _p(b), _p(err))
+        return H, b, err
+
+    def pgo_edge_jacobian(self, meas, si, sj, fix_scale):
+        m, a, b = [np.ascontiguousarray(v, np.float64) for v in (meas, si, sj)]
+        Ji = np.empty((7, 7)); Jj = np.empty((7, 7))
+        self._f("pgo_edge_jacobian")(_p(m), _p(a), _p(b), int(bool(fix_scale)), _p(Ji), _p(Jj))
+        return Ji, Jj
+
+
+def ref_vertex_oplus(kind, est, upd, flag=0):
+    """the reference's VertexSE3Expmap (kind 0) / VertexSim3Expmap (1, flag = _fix_scale) / VertexSBAPointXYZ (2) ::oplus"""
+    e = np.ascontiguousarray(est, np.float64); u = np.ascontiguousarray(upd, np.float64); o = np.empty(len(e))
+    ref_g2o().ref_vertex_oplus(int(kind), _p(e), _p(u), int(flag), _p(o))
+    return o
 
 
 # ---- the reference's own ORBmatcher.cpp on stand-in Frame / KeyFrame / MapPoint (oracle/_ref/libmatch_ref.so) -----------------------

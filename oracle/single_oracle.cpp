@@ -26,7 +26,7 @@ namespace {
 using namespace orc;
 
 inline void huber1(double e, double delta, double rho[3]) {  // G/core/robust_kernel_impl.cpp:77-91
-  const double dsqr = delta * delta;
+  const double dsqr = (double)(float)(delta * delta);  // float member, G/core/robust_kernel_impl.h:84
   if (e <= dsqr) {
     rho[0] = e; rho[1] = 1.; rho[2] = 0.;
   } else {
@@ -69,6 +69,7 @@ bool chol_solve(const double* A, const double* b, double* x) {
 // ---- the two models: state, error of edge e, Jacobian of edge e, oplus --------------------------------------------------
 struct PoseModel {
   static constexpr int D = 6;
+  static constexpr bool unary = true;   // EdgeSE3ProjectXYZOnlyPose is a BaseUnaryEdge
   typedef SE3 State;
   const orc_pose_opt_problem* p;
   int n_edges() const { return p->n; }
@@ -96,6 +97,7 @@ struct PoseModel {
 
 struct Sim3Model {
   static constexpr int D = 7;
+  static constexpr bool unary = false;  // EdgeSim3ProjectXYZ / EdgeInverseSim3ProjectXYZ are binary edges with a fixed point vertex
   typedef Sim3 State;
   const orc_sim3_opt_problem* p;
   // edge 2i = EdgeSim3ProjectXYZ of pair i (x1 = S12 * X2c into camera 1), edge 2i+1 = EdgeInverseSim3ProjectXYZ (x2 = S12^-1 * X1c)
@@ -179,7 +181,13 @@ struct Single {
       if (robust[e]) { double rho[3]; huber1(chi2_of(e), delta, rho); wo = rho[1] * w; wr = rho[1]; }
       const double r0 = -(w * err[2 * e]) * wr, r1 = -(w * err[2 * e + 1]) * wr;  // omega_r = -Omega e, times rho[1] when robust
       for (int i = 0; i < D; i++) {
-        b[i] += J[i] * r0 + J[D + i] * r1;
+        if constexpr (M::unary) {
+          // BaseUnaryEdge::constructQuadraticForm (base_unary_edge.hpp:63-70): b -= rho[1] * A^T * Omega * e, grouped left to right
+          const double a0 = robust[e] ? wr * J[i] : J[i], a1 = robust[e] ? wr * J[D + i] : J[D + i];
+          b[i] -= (a0 * w) * err[2 * e] + (a1 * w) * err[2 * e + 1];
+        } else {
+          b[i] += J[i] * r0 + J[D + i] * r1;        // BaseBinaryEdge: b += B^T * omega_r (base_binary_edge.hpp:74-76,86-104)
+        }
         for (int j = 0; j < D; j++) H[i * D + j] += J[i] * wo * J[j] + J[D + i] * wo * J[D + j];
       }
     }
@@ -297,4 +305,27 @@ extern "C" int orc_sim3_optimize(const orc_sim3_opt_problem* p, double* S12_out,
   }
   sim3_store(s.est, S12_out);
   return nIn;
+}
+
+// ---- pieces, for the reference pin of the edge types (tests/test_oracle_vs_reference_g2o.py) ------------------------------------
+// quadratic form of every correspondence at the given estimate: H (D x D row-major), b (D), err (2 per edge)
+extern "C" void orc_pose_opt_build(const orc_pose_opt_problem* p, const double* Tcw, int robust, double delta, double* H, double* b, double* err) {
+  Single<PoseModel> s;
+  s.m.p = p;
+  s.active.assign(p->n, 1); s.robust.assign(p->n, robust ? 1 : 0); s.err.assign(2 * (size_t)p->n, 0.0);
+  s.delta = delta;
+  s.est = se3_load(Tcw);
+  s.compute_active_errors();
+  s.build(H, b);
+  if (err) std::memcpy(err, s.err.data(), sizeof(double) * s.err.size());
+}
+extern "C" void orc_sim3_opt_build(const orc_sim3_opt_problem* p, const double* S12, int robust, double delta, double* H, double* b, double* err) {
+  Single<Sim3Model> s;
+  s.m.p = p;
+  s.active.assign(2 * (size_t)p->n, 1); s.robust.assign(2 * (size_t)p->n, robust ? 1 : 0); s.err.assign(4 * (size_t)p->n, 0.0);
+  s.delta = delta;
+  s.est = sim3_load(S12);
+  s.compute_active_errors();
+  s.build(H, b);
+  if (err) std::memcpy(err, s.err.data(), sizeof(double) * s.err.size());
 }

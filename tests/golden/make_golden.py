@@ -68,13 +68,14 @@ def golden_known_answers():
     logs = np.stack([orc.sim3_log(s) for s in sim3])
     assert np.abs(logs - s_ups).max() < 1e-9, "sim3 log(exp(u)) round trip"
     d = HUBER_GBA
-    es = np.array([0.0, 1.0, d * d - 1e-9, d * d, d * d + 1e-9, 10.0, 1e4])
+    d2 = float(np.float32(d * d))   # the vendored kernel keeps delta^2 in a float member (G/core/robust_kernel_impl.h:84)
+    es = np.array([0.0, 1.0, d2 - 1e-9, d2, d2 + 1e-9, d * d, np.nextafter(max(d2, d * d), 10.0), 10.0, 1e4])
     hub = np.stack([orc.huber(e, d) for e in es])
     for e, (rho, w) in zip(es, hub[:, :2]):
-        if e <= d * d:
+        if e <= d2:
             assert rho == e and w == 1.0
         else:
-            assert abs(rho - (2 * np.sqrt(e) * d - d * d)) < 1e-12 and abs(w - d / np.sqrt(e)) < 1e-15
+            assert abs(rho - (2 * np.sqrt(e) * d - d2)) < 1e-12 and abs(w - d / np.sqrt(e)) < 1e-15
     # R -> q branches of Eigen's Quaterniond(Matrix3d): trace > 0 and the three "largest diagonal" cases
     Ts = []
     for rv in ([0.1, 0.2, -0.1], [3.0, 0.1, 0.1], [0.1, 3.0, 0.1], [0.1, 0.1, 3.0]):

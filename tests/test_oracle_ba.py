@@ -44,10 +44,17 @@ def test_pose_conversion_roundtrip_and_branches(oracle):
 
 def test_huber_known_answers(oracle):
     d = float(np.float32(np.sqrt(5.99)))   # `const float thHuber2D = sqrt(5.99)` (S/Optimizer.cpp:712)
-    assert np.allclose(oracle.huber(d * d, d), [d * d, 1, 0])          # e == delta^2 is an inlier (<=)
-    assert oracle.huber(d * d * (1 + 1e-9), d)[1] < 1.0
+    d2 = float(np.float32(d * d))          # RobustKernelHuber::dsqr is a float member (G/core/robust_kernel_impl.h:84): the threshold is rounded
+    assert d2 != d * d
+    assert np.array_equal(oracle.huber(d2, d), [d2, 1, 0])             # e == (float)delta^2 is an inlier (<=)
+    e = np.nextafter(d2, 10.0)                                         # the next double above it is not: rho'' != 0 marks the branch
+    r = oracle.huber(e, d)
+    assert r[2] != 0 and r[1] == d / np.sqrt(e)
+    if d2 < d * d:                                                     # between the rounded and the exact square the "outlier" weight exceeds 1
+        assert r[1] > 1.0 and oracle.huber(d * d, d)[2] != 0
     r = oracle.huber(100.0, d)
-    assert np.allclose(r, [2 * 10 * d - d * d, d / 10, -0.5 * (d / 10) / 100])
+    assert np.allclose(r, [2 * 10 * d - d2, d / 10, -0.5 * (d / 10) / 100], rtol=1e-15, atol=0)
+    assert abs(r[0] - (2 * 10 * d - d * d)) > 1e-8                     # and rho(e) carries the rounded square too
 
 
 @pytest.mark.parametrize("name", ["tiny", "small"])

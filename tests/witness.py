@@ -47,7 +47,7 @@ def jacobians(R, Xc, intr):
 
 
 def huber(e, delta):
-    d2 = delta * delta
+    d2 = float(np.float32(delta * delta))   # the vendored RobustKernelHuber keeps delta^2 in a float (G/core/robust_kernel_impl.h:84)
     if e <= d2:
         return e, 1.0
     s = np.sqrt(e)
