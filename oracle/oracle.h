@@ -12,13 +12,14 @@
  * the oracle is pinned by independent witnesses instead: scipy (sparse solve,
  * finite differences, Rotation) for the BA/PGO part and Python cv2 4.13 for the
  * ORB primitives (tests/test_oracle_*.py, fixtures under tests/golden/).
- * "parity unpinned by the reference's own tests" — see DESIGN.md §3.  Five pieces do build from the reference's own sources, in
+ * no reference tests exist to check against — see DESIGN.md §3.  Six pieces do build from the reference's own sources, in
  * place, against the stand-in headers of oracle/ref_stub/ (oracle/Makefile `ref` -> oracle/_ref/): cslam/src/ORBextractor.cpp (on the
  * oracle's OpenCV-primitive restatements), cslam/src/ORBmatcher.cpp (on stand-in Frame / KeyFrame / MapPoint), the vendored DBoW2, and
  * g2o's Levenberg-Marquardt driver (optimization_algorithm*.cpp over stand-in SparseOptimizer / Solver classes backed by ba_oracle.cpp), and
  * g2o's vertex / edge types, Lie groups, base-edge templates and Huber kernel (over a stand-in for Eigen's small fixed-size arithmetic).
  * orb_oracle.cpp, match_oracle.cpp, proj_oracle.cpp and bow_oracle.cpp are held to that code exactly
- * (tests/test_oracle_vs_reference_{orb,matchers,dbow2,lm,g2o}.py).
+ * (tests/test_oracle_vs_reference_{orb,matchers,dbow2,lm,g2o,single,pgo}.py); composed, the last two run every optimisation of the path
+ * as reference code except the linear solve (ref_{ba,single,pgo}_full_wrap.cpp), and the oracle equals those runs bit for bit.
  *
  * Citations: G/ = cslam/thirdparty/g2o/g2o/, S/ = cslam/src/ under /root/reference.
  */

@@ -103,7 +103,17 @@ extern "C" int orc_pgo_solve(const orc_pgo_problem* p, int32_t iterations, doubl
   r->trace_len = 0; r->iters_done = 0; r->chi2_initial = r->chi2_final = 0; r->lambda_final = 0;
   auto terminate = [&] { return stop && *stop; };
   auto errors = [&] { for (int e : s.active) { PEdge& ed = s.edges[e]; edge_err(ed, s.v[ed.i], s.v[ed.j], ed.err); } };
-  auto chi2 = [&] { double c = 0; for (int e : s.active) for (int k = 0; k < 7; k++) c += s.edges[e].err[k] * s.edges[e].err[k]; return c; };
+  // activeRobustChi2: chi += e->chi2(), each edge's e'e summed on its own first (G/core/sparse_optimizer.cpp:100-114, base_edge.h:58-61)
+  auto chi2 = [&] {
+    double c = 0;
+    for (int e : s.active) {
+      const double* er = s.edges[e].err;
+      double ce = er[0] * er[0];
+      for (int k = 1; k < 7; k++) ce += er[k] * er[k];
+      c += ce;
+    }
+    return c;
+  };
   int ret = 0;
   if (s.n == 0 || s.active.empty()) {
     ret = -1;

@@ -176,7 +176,7 @@ def pgo_edge_error(meas, si, sj):
     lib().orc_pgo_edge_error(_p(m), _p(a), _p(b), _p(o)); return o
 
 
-def pgo_solve(p, iterations=20, lambda_init=1e-16, analytic_jac=False, stop=None):
+def pgo_solve(p, iterations=20, lambda_init=1e-16, analytic_jac=False, stop=None, fn=None):
     arrs = dict(sim3=np.ascontiguousarray(p.sim3, np.float64), fixed=np.ascontiguousarray(p.fixed, np.uint8),
                 ei=np.ascontiguousarray(p.edge_i, np.int32), ej=np.ascontiguousarray(p.edge_j, np.int32),
                 meas=np.ascontiguousarray(p.meas, np.float64))
@@ -184,7 +184,7 @@ def pgo_solve(p, iterations=20, lambda_init=1e-16, analytic_jac=False, stop=None
     prob = _PGOProblem(K, E, _p(arrs["sim3"]), _p(arrs["fixed"]), _p(arrs["ei"]), _p(arrs["ej"]), _p(arrs["meas"]), int(p.fix_scale))
     out = np.empty((K, 8)); trace = np.zeros((max(iterations, 1), TRACE_COLS))
     res = _PGOResult(_p(out), _p(trace), trace.shape[0])
-    rc = lib().orc_pgo_solve(C.byref(prob), iterations, C.c_double(lambda_init), int(analytic_jac), _p(stop), C.byref(res))
+    rc = (fn or lib().orc_pgo_solve)(C.byref(prob), iterations, C.c_double(lambda_init), int(analytic_jac), _p(stop), C.byref(res))
     assert rc == 0
     return dict(sim3=out, trace=trace[:res.trace_len], iters_done=res.iters_done, chi2_initial=res.chi2_initial,
                 chi2_final=res.chi2_final, lambda_final=res.lambda_final, t_total=res.t_total_s)
@@ -515,6 +515,27 @@ def ref_lm():
     return _REF_LM
 
 
+_REF_BA_FULL = None
+
+
+def ref_ba_full():
+    global _REF_BA_FULL
+    if _REF_BA_FULL is None:
+        if build_ref() is None:
+            return None
+        so = os.path.join(_HERE, "_ref", "libba_full_ref.so")
+        if not os.path.exists(so):
+            return None
+        _REF_BA_FULL = C.CDLL(so)
+    return _REF_BA_FULL
+
+
+def ref_ba_full_solve(p, **kw):
+    """ba_solve() where the reference's LM driver runs over the reference's own vertices, edges and kernels (oracle/ref_ba_full_wrap.cpp);
+    only the Schur complement + LDL^T under Solver::solve() are the oracle's."""
+    return ba_solve(p, fn=ref_ba_full().ref_ba_full_solve, **kw)
+
+
 def ref_ba_solve(p, **kw):
     """ba_solve() with g2o's own OptimizationAlgorithmLevenberg::solve (compiled from the reference tree, oracle/ref_lm_wrap.cpp)
     deciding lambda, trials and termination; trace column 3 (rho) is NaN — it is a local of the reference's function."""
@@ -810,18 +831,18 @@ class _Sim3Opt(C.Structure):
                 ("K2", C.c_float * 4), ("th2", C.c_float), ("fix_scale", C.c_int32)]
 
 
-def pose_optimize(Tcw, Xw, uv, inv_sigma2, intr):
+def pose_optimize(Tcw, Xw, uv, inv_sigma2, intr, fn=None):
     """Optimizer::PoseOptimizationClient on flat arrays -> (Tcw (7,), outlier (n,) u8, n_inliers)."""
     a = dict(Tcw=np.ascontiguousarray(Tcw, np.float64), Xw=np.ascontiguousarray(Xw, np.float32).reshape(-1, 3),
              uv=np.ascontiguousarray(uv, np.float32).reshape(-1, 2), w=np.ascontiguousarray(inv_sigma2, np.float32))
     n = a["Xw"].shape[0]
     prob = _PoseOpt(n, _p(a["Tcw"]), _p(a["Xw"]), _p(a["uv"]), _p(a["w"]), *[float(v) for v in intr])
     out = np.empty(7); outlier = np.zeros(max(n, 1), np.uint8)
-    nin = lib().orc_pose_optimize(C.byref(prob), _p(out), _p(outlier))
+    nin = (fn or lib().orc_pose_optimize)(C.byref(prob), _p(out), _p(outlier))
     return out, outlier[:n], nin
 
 
-def sim3_optimize(S12, P1c, P2c, uv1, uv2, w1, w2, K1, K2, th2, fix_scale):
+def sim3_optimize(S12, P1c, P2c, uv1, uv2, w1, w2, K1, K2, th2, fix_scale, fn=None):
     """Optimizer::OptimizeSim3 on flat arrays -> (S12 (8,), inlier (n,) u8, n_inliers)."""
     f32 = lambda x, c: np.ascontiguousarray(x, np.float32).reshape(-1, c) if c else np.ascontiguousarray(x, np.float32)
     a = dict(S=np.ascontiguousarray(S12, np.float64), P1=f32(P1c, 3), P2=f32(P2c, 3), u1=f32(uv1, 2), u2=f32(uv2, 2),
@@ -830,5 +851,49 @@ def sim3_optimize(S12, P1c, P2c, uv1, uv2, w1, w2, K1, K2, th2, fix_scale):
     prob = _Sim3Opt(n, _p(a["S"]), _p(a["P1"]), _p(a["P2"]), _p(a["u1"]), _p(a["u2"]), _p(a["w1"]), _p(a["w2"]),
                     (C.c_float * 4)(*[float(v) for v in K1]), (C.c_float * 4)(*[float(v) for v in K2]), float(th2), int(bool(fix_scale)))
     out = np.empty(8); inl = np.zeros(max(n, 1), np.uint8)
-    nin = lib().orc_sim3_optimize(C.byref(prob), _p(out), _p(inl))
+    nin = (fn or lib().orc_sim3_optimize)(C.byref(prob), _p(out), _p(inl))
     return out, inl[:n], nin
+
+
+# ---- the two single-vertex optimisations run by the reference's LM driver over the reference's vertices / edges (oracle/ref_single_full_wrap.cpp)
+_REF_SINGLE = None
+
+
+def ref_single_full():
+    global _REF_SINGLE
+    if _REF_SINGLE is None:
+        if build_ref() is None:
+            return None
+        so = os.path.join(_HERE, "_ref", "libsingle_full_ref.so")
+        if not os.path.exists(so):
+            return None
+        _REF_SINGLE = C.CDLL(so)
+    return _REF_SINGLE
+
+
+def ref_pose_optimize(*a):
+    return pose_optimize(*a, fn=ref_single_full().ref_pose_optimize)
+
+
+def ref_sim3_optimize(*a):
+    return sim3_optimize(*a, fn=ref_single_full().ref_sim3_optimize)
+
+
+# ---- the essential graph run by the reference's LM driver over the reference's VertexSim3Expmap / EdgeSim3 (oracle/ref_pgo_full_wrap.cpp)
+_REF_PGO = None
+
+
+def ref_pgo_full():
+    global _REF_PGO
+    if _REF_PGO is None:
+        if build_ref() is None:
+            return None
+        so = os.path.join(_HERE, "_ref", "libpgo_full_ref.so")
+        if not os.path.exists(so):
+            return None
+        _REF_PGO = C.CDLL(so)
+    return _REF_PGO
+
+
+def ref_pgo_solve(p, **kw):
+    return pgo_solve(p, fn=ref_pgo_full().ref_pgo_solve, **kw)

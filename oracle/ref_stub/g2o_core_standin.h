@@ -49,6 +49,11 @@ class OptimizableGraph {
     void updateCache() {}
     virtual void push() = 0;
     virtual void pop() = 0;
+    virtual void discardTop() = 0;
+    virtual const double& hessian(int i, int j) const = 0;
+    virtual void mapHessianMemory(double* d) = 0;
+    virtual void clearQuadraticForm() = 0;
+    virtual int copyB(double* b) const = 0;
     virtual bool read(std::istream& is) = 0;
     virtual bool write(std::ostream& os) const = 0;
    protected:
@@ -58,6 +63,7 @@ class OptimizableGraph {
     bool _fixed, _marginalized;
   };
   typedef std::set<Vertex*> VertexSet;
+  typedef std::vector<Vertex*> VertexContainer;
 
   class Edge {
    public:

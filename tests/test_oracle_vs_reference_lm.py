@@ -9,11 +9,22 @@ import pytest
 from ccm_slam_b200 import synth
 
 
-@pytest.fixture(scope="module")
-def ref(oracle):
-    if oracle.ref_lm() is None:
-        pytest.skip("reference tree absent and no prebuilt oracle/_ref/liblm_ref.so")
-    return oracle
+class _Side:
+    """the oracle's ba_solve next to one of the two reference-driven runs"""
+
+    def __init__(self, oracle, driver):
+        self.ba_solve = oracle.ba_solve
+        self.ref_ba_solve = oracle.ref_ba_solve if driver == "lm" else oracle.ref_ba_full_solve
+
+
+# "lm":   g2o's Levenberg-Marquardt driver over the oracle's errors / quadratic form / Schur solve (oracle/ref_lm_wrap.cpp)
+# "full": the same driver over g2o's own vertices, edges, Huber kernel and base-edge templates; only the Schur complement and the
+#         LDL^T under Solver::solve() are the oracle's (oracle/ref_ba_full_wrap.cpp)
+@pytest.fixture(scope="module", params=["lm", "full"])
+def ref(oracle, request):
+    if (oracle.ref_lm() if request.param == "lm" else oracle.ref_ba_full()) is None:
+        pytest.skip("reference tree absent and no prebuilt oracle/_ref library")
+    return _Side(oracle, request.param)
 
 
 def same_run(a, b):
