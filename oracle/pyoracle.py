@@ -621,10 +621,21 @@ def ref_vertex_oplus(kind, est, upd, flag=0):
 
 # ---- the reference's own ORBmatcher.cpp on stand-in Frame / KeyFrame / MapPoint (oracle/_ref/libmatch_ref.so) -----------------------
 _REF_MATCH = None
+_SHIM_MATCH = {}
+_MATCH_SIDE = "ref"
 
 
 def ref_match():
-    global _REF_MATCH
+    """the matcher library the ref_* wrappers below talk to: the reference's own ORBmatcher.cpp (default) or, inside
+    `with matcher_side("shim")`, this repository's shim/ORBmatcher*_shim.cpp built over the same stand-in classes"""
+    global _REF_MATCH, _SHIM_MATCH
+    if _MATCH_SIDE in ("shim", "shim_gpu"):     # "shim": device half doubled on the CPU; "shim_gpu": the real device entry points
+        if _SHIM_MATCH.get(_MATCH_SIDE) is None:
+            so = os.path.join(_HERE, "_ref", "libmatch_shim.so" if _MATCH_SIDE == "shim" else "libmatch_shim_gpu.so")
+            if build_ref() is None or not os.path.exists(so):
+                return None
+            _SHIM_MATCH[_MATCH_SIDE] = C.CDLL(so)
+        return _SHIM_MATCH[_MATCH_SIDE]
     if _REF_MATCH is None:
         if build_ref() is None:
             return None
@@ -633,6 +644,19 @@ def ref_match():
             return None
         _REF_MATCH = C.CDLL(so)
     return _REF_MATCH
+
+
+class matcher_side:
+    def __init__(self, side):
+        self.side = side
+
+    def __enter__(self):
+        global _MATCH_SIDE
+        self.prev, _MATCH_SIDE = _MATCH_SIDE, self.side
+
+    def __exit__(self, *a):
+        global _MATCH_SIDE
+        _MATCH_SIDE = self.prev
 
 
 class _RefImage(C.Structure):

@@ -81,6 +81,10 @@ struct KeyPoint {
 
 struct MatZeros { int rows, cols, type; };
 
+#ifndef CV_MAJOR_VERSION
+#define CV_MAJOR_VERSION 2   /* the reference targets OpenCV 2.4 / 3.x; only compared against 3 by shim/ORBextractor_shim.cpp */
+#endif
+
 class Mat {
  public:
   int rows, cols;
@@ -109,6 +113,10 @@ class Mat {
     m.create(rows, cols, type_);
     for (int r = 0; r < rows; r++) memcpy(m.data + (size_t)r * m.step, data + (size_t)r * step, (size_t)cols * esz(type_));
     return m;
+  }
+  void copyTo(Mat& dst) const {   // OpenCV: dst.create(size, type) then a row-wise copy
+    dst.create(rows, cols, type_);
+    for (int r = 0; r < rows; r++) memcpy(dst.data + (size_t)r * dst.step, data + (size_t)r * step, (size_t)cols * esz(type_));
   }
   void release() { rows = cols = 0; step = 0; data = nullptr; buf_.reset(); }
   bool empty() const { return data == nullptr || rows == 0 || cols == 0; }

@@ -23,6 +23,10 @@ namespace cslam {
 
 namespace {
 
+// the smart-pointer aliases are class-scoped in the reference (cslam/ORBmatcher.h:91-93); the helpers below are free functions
+typedef ORBmatcher::kfptr kfptr;
+typedef ORBmatcher::mpptr mpptr;
+
 // image side of a search: keypoints + lookup-grid geometry of a Frame or a KeyFrame
 template <class ImageLike>
 struct GridView {

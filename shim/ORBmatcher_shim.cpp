@@ -1,5 +1,8 @@
-// ORBmatcher_shim.cpp — replaces the three hot methods of cslam/src/ORBmatcher.cpp (the other methods keep the reference
-// code); cslam/include/cslam/ORBmatcher.h stays byte-identical.  Not compiled here (needs OpenCV / DBoW2 headers).
+// ORBmatcher_shim.cpp — with ORBmatcher_proj_shim.cpp, replaces cslam/src/ORBmatcher.cpp as a whole: SearchByBoW x2,
+// SearchForTriangulation and DescriptorDistance here, the projection-guided searches there, plus the few small members the rest of
+// the class needs (constructor, the three thresholds, RadiusByViewingCos).  cslam/include/cslam/ORBmatcher.h stays byte-identical.
+// Type-checked against that header and run against the reference's own ORBmatcher.cpp on stand-in Frame / KeyFrame / MapPoint
+// classes by tests/test_shim_dropin.py (oracle/Makefile: _ref/libmatch_shim.so).
 #include <cslam/ORBmatcher.h>
 
 #include "ccm_b200.h"
@@ -18,6 +21,14 @@ struct FlatFV {                                      // DBoW2::FeatureVector = s
 std::vector<float> angles(const std::vector<cv::KeyPoint>& k) { std::vector<float> a(k.size()); for (size_t i = 0; i < k.size(); i++) a[i] = k[i].angle; return a; }
 std::vector<uint8_t> good_mps(const std::vector<boost::shared_ptr<MapPoint>>& v) { std::vector<uint8_t> g(v.size()); for (size_t i = 0; i < v.size(); i++) g[i] = v[i] && !v[i]->isBad(); return g; }
 }
+
+const int ORBmatcher::TH_HIGH = 100;      // S/ORBmatcher.cpp:63-65
+const int ORBmatcher::TH_LOW = 50;
+const int ORBmatcher::HISTO_LENGTH = 30;
+
+ORBmatcher::ORBmatcher(float nnratio, bool checkOri) : mfNNratio(nnratio), mbCheckOrientation(checkOri) {}
+
+float ORBmatcher::RadiusByViewingCos(const float& viewCos) { return viewCos > 0.998 ? 2.5f : 4.0f; }   // S/ORBmatcher.cpp:150-156
 
 int ORBmatcher::DescriptorDistance(const cv::Mat& a, const cv::Mat& b) {
   uint16_t d = 0;

@@ -1,0 +1,80 @@
+"""GPU suite (runs last): the reference-side shims as a drop-in for cslam::ORBmatcher, on the device.
+
+Same construction as tests/test_shim_dropin.py — shim/ORBmatcher_shim.cpp + shim/ORBmatcher_proj_shim.cpp behind the C wrappers of
+oracle/ref_match_wrap.cpp, next to the reference's own ORBmatcher.cpp — but linked against the product library itself
+(oracle/_ref/libmatch_shim_gpu.so): the Hamming matrices come from k_hamming on the GPU.  Every scene goes through both
+implementations of the class and must give identical results.  The projection-guided methods have been run this way on the CPU (link-time
+double); SearchByBoW x2 / SearchForTriangulation reach a device for the first time here and are opt-in until they have been seen green
+once (CCM_TEST_UNVALIDATED=1)."""
+import os
+
+import numpy as np
+import pytest
+
+from tests import test_oracle_vs_reference_matchers as T
+from tests.test_shim_dropin import same
+
+pytestmark = pytest.mark.gpu
+
+
+class SideBySideGPU:
+    def __init__(self, oracle, skip=()):
+        self._o, self.calls, self.skip = oracle, 0, set(skip)
+
+    def __getattr__(self, name):
+        f = getattr(self._o, name)
+        if not name.startswith("ref_") or name in self.skip or not callable(f):
+            return f
+
+        def both(*a, **k):
+            r = f(*a, **k)
+            with self._o.matcher_side("shim_gpu"):
+                s = f(*a, **k)
+            same(r, s)
+            self.calls += 1
+            return r
+        return both
+
+
+@pytest.fixture(scope="module")
+def side(oracle):
+    from ccm_slam_b200 import api
+    if api.device_count() == 0:
+        pytest.skip("no CUDA device")
+    api.init(0)
+    if oracle.ref_match() is None:
+        pytest.skip("no oracle/_ref/libmatch_ref.so")
+    with oracle.matcher_side("shim_gpu"):
+        if oracle.ref_match() is None:
+            pytest.skip("no oracle/_ref/libmatch_shim_gpu.so")
+    return SideBySideGPU(oracle)
+
+
+def ran(side, fn, *args):
+    before = side.calls
+    fn(side, *args)
+    assert side.calls > before
+
+
+def test_projection_guided_methods(side):
+    ran(side, T.test_search_for_initialization, 5, 0.9, True)
+    ran(side, T.test_search_by_projection_track, 8, 3.0, 0.8)
+    ran(side, T.test_fuse, 20, 3.0)
+    ran(side, T.test_fuse_sim3, 22, 4.0, 2.0)
+    ran(side, T.test_search_by_projection_sim3, 24, 2.0)
+    ran(side, T.test_search_by_sim3)
+    ran(side, T.test_search_by_projection_last_frame, 30, 7.0, True)
+    ran(side, T.test_search_by_projection_relocalisation, 33, 3.0, 64, False)
+
+
+@pytest.mark.skipif(os.environ.get("CCM_TEST_UNVALIDATED") != "1", reason="first device run pending (set CCM_TEST_UNVALIDATED=1)")
+def test_bow_and_triangulation_methods(side):
+    ran(side, T.test_search_by_bow, 0, 0.7, True)
+    ran(side, T.test_search_by_bow, 1, 0.9, False)
+    ran(side, T.test_search_for_triangulation, 3, False)
+    ran(side, T.test_search_for_triangulation, 4, True)
+    rng = np.random.default_rng(0)
+    with side._o.matcher_side("shim_gpu"):
+        for _ in range(20):
+            a, b = rng.integers(0, 256, 32, dtype=np.uint8), rng.integers(0, 256, 32, dtype=np.uint8)
+            assert side._o.ref_match().ref_descriptor_distance(a.ctypes.data, b.ctypes.data) == int(np.unpackbits(a ^ b).sum())
