@@ -64,6 +64,11 @@ void ref_sim3_exp(const double upd[7], double out[8]) { Vector7d u; for (int i =
 void ref_sim3_log(const double s[8], double out[7]) { Vector7d l = sim3_in(s).log(); for (int i = 0; i < 7; i++) out[i] = l[i]; }
 void ref_sim3_mul(const double a[8], const double b[8], double out[8]) { sim3_out(sim3_in(a) * sim3_in(b), out); }
 void ref_sim3_inv(const double a[8], double out[8]) { sim3_out(sim3_in(a).inverse(), out); }
+void ref_sim3_from_Rt(const double R[9], const double t[3], const double s[1], double out[8]) {   // Sim3(Matrix3d, Vector3d, double): no normalisation
+  Matrix3d m;
+  for (int i = 0; i < 3; i++) for (int j = 0; j < 3; j++) m(i, j) = R[i * 3 + j];
+  sim3_out(Sim3(m, Vector3d(t[0], t[1], t[2]), s[0]), out);
+}
 void ref_sim3_map(const double s[8], const double x[3], double out[3]) {
   Vector3d r = sim3_in(s).map(Vector3d(x[0], x[1], x[2]));
   for (int i = 0; i < 3; i++) out[i] = r[i];

@@ -14,7 +14,7 @@
 //     destination), which is how computeDescriptors writes through the row view of the output matrix (ORBextractor.cpp:1208);
 //   * create() on a Mat that already has the requested shape keeps its storage (resize / copyMakeBorder into an existing view);
 //   * cvRound rounds half to even (lrint under the default rounding mode).
-// FileStorage is inert but reports "opened" and yields zeros: cslam/config.h reads its parameters through it during static
+// FileStorage is inert but reports "opened" and yields zeros (or what CCM_REF_STUB_CONF names): cslam/config.h reads its parameters through it during static
 // initialisation and would exit(-1) otherwise; none of those parameters is used by the code compiled here.
 #ifndef CCM_ORACLE_REF_STUB_OPENCV_CORE_HPP
 #define CCM_ORACLE_REF_STUB_OPENCV_CORE_HPP
@@ -56,6 +56,8 @@ template <class T> struct Point_ {
 typedef Point_<int> Point2i;
 typedef Point_<int> Point;
 typedef Point_<float> Point2f;
+template <class T> struct Point3_ { T x, y, z; Point3_() : x(0), y(0), z(0) {} Point3_(T a, T b, T c) : x(a), y(b), z(c) {} };
+typedef Point3_<float> Point3f;
 
 template <class T> struct Size_ {
   T width, height;
@@ -100,6 +102,11 @@ class Mat {
     rows = r; cols = c; type_ = type; step = (size_t)c * esz(type);
     buf_ = std::make_shared<std::vector<uchar> >((size_t)r * step + 64, (uchar)0);
     data = buf_->data();
+  }
+  static Mat eye(int r, int c, int type) {
+    Mat m(r, c, type);
+    for (int i = 0; i < (r < c ? r : c); i++) { if (type == CV_32F) m.at<float>(i, i) = 1.0f; else m.at<uchar>(i, i) = 1; }
+    return m;
   }
   static MatZeros zeros(int r, int c, int type) { MatZeros z; z.rows = r; z.cols = c; z.type = type; return z; }
   Mat& operator=(const MatZeros& z) {
@@ -192,13 +199,17 @@ inline double norm(const Mat& a) { return std::sqrt(a.dot(a)); }
 
 class FileNode {
  public:
+  FileNode() : v_(0.0) {}
+  explicit FileNode(double v) : v_(v) {}
   FileNode operator[](const std::string&) const { return FileNode(); }
   FileNode operator[](const char*) const { return FileNode(); }
   FileNode operator[](int) const { return FileNode(); }
   size_t size() const { return 0; }
-  operator int() const { return 0; }
-  operator double() const { return 0.0; }
+  operator int() const { return (int)v_; }
+  operator double() const { return v_; }
   operator std::string() const { return std::string(); }
+ private:
+  double v_;
 };
 
 class FileStorage {
@@ -207,8 +218,19 @@ class FileStorage {
   FileStorage() {}
   FileStorage(const std::string&, int) {}
   bool isOpened() const { return true; }
-  FileNode operator[](const std::string&) const { return FileNode(); }
-  FileNode operator[](const char*) const { return FileNode(); }
+  // a test can supply parameter values through the environment: CCM_REF_STUB_CONF="Opt.EssGraphMinFeats=100,Other.Key=2.5"
+  FileNode operator[](const std::string& key) const {
+    const char* e = getenv("CCM_REF_STUB_CONF");
+    if (!e) return FileNode();
+    const std::string all(e), pat = key + "=";
+    size_t at = 0;
+    while ((at = all.find(pat, at)) != std::string::npos) {
+      if (at == 0 || all[at - 1] == ',') return FileNode(atof(all.c_str() + at + pat.size()));
+      at += pat.size();
+    }
+    return FileNode();
+  }
+  FileNode operator[](const char* key) const { return (*this)[std::string(key)]; }
 };
 template <class T> inline FileStorage& operator<<(FileStorage& fs, const T&) { return fs; }
 

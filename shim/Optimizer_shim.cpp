@@ -2,11 +2,15 @@
 // cslam/src/Optimizer.cpp for the entry points on the BA hot path.  Everything g2o did between "graph built" and "results
 // read back" is one call into libccm_b200.so; graph selection and write-back keep the reference's rules.
 //
-// NOT compiled in this repository's environment (needs the reference's OpenCV / Eigen / Boost / ROS headers).  It is the
-// binding a maintainer adds to cslam/CMakeLists.txt in place of src/Optimizer.cpp.
+// It is the binding a maintainer adds to cslam/CMakeLists.txt in place of src/Optimizer.cpp.  In this repository
+// it is compiled against the reference's own Optimizer.h / Converter.h and stand-in Map / KeyFrame / MapPoint / Frame classes and run
+// through the class interface by tests/test_shim_optimizer.py (oracle/Makefile: _ref/liboptimizer_shim.so).
 // g2o is only needed for the g2o::Sim3 value type that appears in Optimizer.h.
 #include <cslam/Optimizer.h>
 
+#include <unistd.h>
+
+#include <list>
 #include <unordered_map>
 
 #include "ccm_b200.h"
@@ -264,24 +268,158 @@ void Optimizer::LocalBundleAdjustmentClient(kfptr pKF, bool* pbStopFlag, mapptr 
 }
 
 // ---- OptimizeEssentialGraph* (S/Optimizer.cpp:1058-1566) ----------------------------------------------------------------
-// Both variants build the same kind of graph (vertices = non-bad KFs as Sim3(R, t, 1); edges = loop connections, spanning
-// tree, earlier loop edges, covisibility >= EssGraphMinFeats, measurement Sji = Sjw * Swi, information I7) and differ only
-// in where Sjw/Swi come from (NonCorrectedSim3 / CorrectedSim3 maps for the loop-closure variant).  The shim collects
-// (i, j, Sji) triples with the reference's own loops (unchanged, not repeated here), then:
-static void solve_essential_graph(std::vector<double>& sim3 /*K*8 in/out*/, const std::vector<uint8_t>& fixed,
-                                  const std::vector<int32_t>& ei, const std::vector<int32_t>& ej, const std::vector<double>& meas,
-                                  bool bFixScale) {
+// Both variants build the same kind of graph — one Sim3 vertex per keyframe (fixed: the loop keyframe), identity-information edges
+// Sji = Sjw * Swi for the new loop connections, the spanning tree, earlier loop edges and strong covisibility — and differ in where
+// the poses come from (the loop-closure variant looks keyframes up in CorrectedSim3 / NonCorrectedSim3 first) and in which
+// "corrected by" tag of a map point names its reference.  Graph collection and recovery follow the reference's loops; the
+// optimisation between them is one ccm_pgo_solve.
+namespace {
+
+void sim3_flat(const g2o::Sim3& S, double* o) {
+  o[0] = S.rotation().x(); o[1] = S.rotation().y(); o[2] = S.rotation().z(); o[3] = S.rotation().w();
+  o[4] = S.translation()[0]; o[5] = S.translation()[1]; o[6] = S.translation()[2]; o[7] = S.scale();
+}
+
+void optimize_essential_graph(Optimizer::mapptr pMap, Optimizer::kfptr pLoopKF, Optimizer::kfptr pCurKF,
+                              const Optimizer::KeyFrameAndPose* NonCorrectedSim3, const Optimizer::KeyFrameAndPose* CorrectedSim3,
+                              const map<Optimizer::kfptr, set<Optimizer::kfptr> >& LoopConnections, bool bFixScale) {
+  typedef Optimizer::kfptr kfptr;
+  typedef Optimizer::mpptr mpptr;
+  typedef Optimizer::KeyFrameAndPose KeyFrameAndPose;
+  const vector<kfptr> vpKFs = pMap->GetAllKeyFrames();
+  const vector<mpptr> vpMPs = pMap->GetAllMapPoints();
+  const int minFeat = params::opt::miEssGraphMinFeats;
+
+  // vertices, :1086-1118 / :1360-1384.  Rows in ascending mUniqueId = the order of g2o's index mapping.
+  map<size_t, g2o::Sim3> vScw;
+  map<size_t, int> row_of_id;
+  for (size_t i = 0; i < vpKFs.size(); i++) {
+    kfptr pKF = vpKFs[i];
+    if (pKF->isBad()) continue;
+    const size_t nIDi = pKF->mUniqueId;
+    KeyFrameAndPose::const_iterator it;
+    if (CorrectedSim3 && (it = CorrectedSim3->find(pKF)) != CorrectedSim3->end()) vScw[nIDi] = it->second;
+    else vScw[nIDi] = g2o::Sim3(Converter::toMatrix3d(pKF->GetRotation()), Converter::toVector3d(pKF->GetTranslation()), 1.0);
+  }
+  std::vector<double> sim3(8 * vScw.size());
+  std::vector<uint8_t> fixed(vScw.size(), 0);
+  {
+    int row = 0;
+    for (map<size_t, g2o::Sim3>::const_iterator it = vScw.begin(); it != vScw.end(); ++it, ++row) {
+      row_of_id[it->first] = row;
+      sim3_flat(it->second, &sim3[8 * (size_t)row]);
+    }
+  }
+  if (row_of_id.count(pLoopKF->mUniqueId)) fixed[row_of_id[pLoopKF->mUniqueId]] = 1;
+
+  std::vector<int32_t> ei, ej;
+  std::vector<double> meas;
+  auto in_graph = [&](const kfptr& k) { return row_of_id.count(k->mUniqueId) != 0; };
+  auto add_edge = [&](const kfptr& pKFi, const kfptr& pKFj, const g2o::Sim3& Sji) {   // vertex 0 = i, vertex 1 = j
+    ei.push_back(row_of_id[pKFi->mUniqueId]); ej.push_back(row_of_id[pKFj->mUniqueId]);
+    meas.resize(meas.size() + 8);
+    sim3_flat(Sji, &meas[meas.size() - 8]);
+  };
+  auto uncorrected = [&](const kfptr& pKF) -> g2o::Sim3 {                  // Sjw of a neighbour: NonCorrectedSim3 first (loop closure only)
+    KeyFrameAndPose::const_iterator it;
+    if (NonCorrectedSim3 && (it = NonCorrectedSim3->find(pKF)) != NonCorrectedSim3->end()) return it->second;
+    return vScw.find(pKF->mUniqueId)->second;                              // only called for keyframes in the graph
+  };
+
+  // new loop connections, :1124-1155 / :1390-1421
+  set<pair<long unsigned int, long unsigned int> > sInsertedEdges;
+  for (map<kfptr, set<kfptr> >::const_iterator mit = LoopConnections.begin(); mit != LoopConnections.end(); ++mit) {
+    kfptr pKF = mit->first;
+    if (pKF->isBad() || !in_graph(pKF)) continue;
+    const size_t nIDi = pKF->mUniqueId;
+    const g2o::Sim3 Swi = vScw.find(nIDi)->second.inverse();
+    for (set<kfptr>::const_iterator sit = mit->second.begin(); sit != mit->second.end(); ++sit) {
+      if ((*sit)->isBad() || !in_graph(*sit)) continue;
+      const size_t nIDj = (*sit)->mUniqueId;
+      if ((nIDi != pCurKF->mUniqueId || nIDj != pLoopKF->mUniqueId) && pKF->GetWeight(*sit) < minFeat) continue;
+      add_edge(pKF, *sit, vScw.find(nIDj)->second * Swi);
+      sInsertedEdges.insert(make_pair(min(nIDi, nIDj), max(nIDi, nIDj)));
+    }
+  }
+  // spanning tree, earlier loop edges, covisibility, :1158-1268 / :1424-1504.  An edge to a keyframe that is not a vertex (bad) is not
+  // added, as g2o refuses an edge with a missing vertex.
+  for (size_t i = 0; i < vpKFs.size(); i++) {
+    kfptr pKF = vpKFs[i];
+    if (pKF->isBad()) continue;
+    const size_t nIDi = pKF->mUniqueId;
+    const g2o::Sim3 Swi = uncorrected(pKF).inverse();
+    kfptr pParentKF = pKF->GetParent();
+    if (pParentKF && in_graph(pParentKF)) add_edge(pKF, pParentKF, uncorrected(pParentKF) * Swi);
+    const set<kfptr> sLoopEdges = pKF->GetLoopEdges();
+    for (set<kfptr>::const_iterator sit = sLoopEdges.begin(); sit != sLoopEdges.end(); ++sit) {
+      kfptr pLKF = *sit;
+      if (pLKF->mUniqueId < nIDi && in_graph(pLKF)) add_edge(pKF, pLKF, uncorrected(pLKF) * Swi);
+    }
+    const vector<kfptr> vpConnectedKFs = pKF->GetCovisiblesByWeight(minFeat);
+    for (vector<kfptr>::const_iterator vit = vpConnectedKFs.begin(); vit != vpConnectedKFs.end(); ++vit) {
+      kfptr pKFn = *vit;
+      if (!pKFn || pKFn->isBad() || !in_graph(pKFn)) continue;
+      if (pKFn != pParentKF && !pKF->hasChild(pKFn) && !sLoopEdges.count(pKFn)) {
+        const size_t nIDj = pKFn->mUniqueId;
+        if (nIDj < nIDi) {
+          if (sInsertedEdges.count(make_pair(min(nIDi, nIDj), max(nIDi, nIDj)))) continue;
+          add_edge(pKF, pKFn, uncorrected(pKFn) * Swi);
+        }
+      }
+    }
+  }
+
+  // solver->setUserLambdaInit(1e-16); optimizer.initializeOptimization(); optimizer.optimize(20)
   ccm_pgo_problem p = {(int32_t)fixed.size(), (int32_t)ei.size(), sim3.data(), fixed.data(), ei.data(), ej.data(), meas.data(), bFixScale ? 1 : 0};
   ccm_pgo_options o = {};
-  o.iterations = 20; o.lambda_init = 1e-16;                    // solver->setUserLambdaInit(1e-16); optimizer.optimize(20)
+  o.iterations = 20; o.lambda_init = 1e-16;
   std::vector<double> out(sim3.size());
   ccm_pgo_result r = {};
   r.sim3 = out.data();
   check(ccm_pgo_solve(&p, &o, &r));
-  sim3.swap(out);
+
+  // recovery, :1280-1330 / :1517-1565: [sR t; 0 1] -> [R t/s; 0 1] per keyframe, every map point moved through its reference keyframe
+  map<size_t, g2o::Sim3> vCorrectedSwc;
+  for (size_t i = 0; i < vpKFs.size(); i++) {
+    kfptr pKFi = vpKFs[i];
+    if (pKFi->isBad()) continue;
+    const size_t nIDi = pKFi->mUniqueId;
+    const double* q = &out[8 * (size_t)row_of_id[nIDi]];
+    g2o::Sim3 CorrectedSiw(Eigen::Quaterniond(q[3], q[0], q[1], q[2]), Eigen::Vector3d(q[4], q[5], q[6]), q[7]);
+    vCorrectedSwc[nIDi] = CorrectedSiw.inverse();
+    Eigen::Matrix3d eigR = CorrectedSiw.rotation().toRotationMatrix();
+    Eigen::Vector3d eigt = CorrectedSiw.translation();
+    double s = CorrectedSiw.scale();
+    eigt *= (1. / s);
+    pKFi->SetPose(Converter::toCvSE3(eigR, eigt), true);
+  }
+  for (size_t i = 0; i < vpMPs.size(); i++) {
+    mpptr pMP = vpMPs[i];
+    if (pMP->isBad()) continue;
+    size_t nIDr;
+    const bool tagged = NonCorrectedSim3 ? pMP->mCorrectedByKF_LC == pCurKF->mId : pMP->mCorrectedByKF_MM == pCurKF->mId;
+    if (tagged) nIDr = NonCorrectedSim3 ? pMP->mCorrectedReference_LC : pMP->mCorrectedReference_MM;
+    else nIDr = pMP->GetReferenceKeyFrame()->mUniqueId;
+    if (!vScw.count(nIDr)) continue;                           // reference keyframe not in the graph
+    Eigen::Matrix<double, 3, 1> eigP3Dw = Converter::toVector3d(pMP->GetWorldPos());
+    Eigen::Matrix<double, 3, 1> eigCorrectedP3Dw = vCorrectedSwc.find(nIDr)->second.map(vScw.find(nIDr)->second.map(eigP3Dw));
+    pMP->SetWorldPos(Converter::toCvMat(eigCorrectedP3Dw), true);
+    pMP->UpdateNormalAndDepth();
+  }
 }
-// After the solve the reference's recovery code (:1280-1330, :1517-1565) runs unchanged on the returned Sim3s:
-// [sR t; 0 1] -> [R t/s; 0 1] per keyframe, and every map point is moved through its reference keyframe.
+
+}  // namespace
+
+void Optimizer::OptimizeEssentialGraphLoopClosure(mapptr pMap, kfptr pLoopKF, kfptr pCurKF, const KeyFrameAndPose& NonCorrectedSim3,
+                                                  const KeyFrameAndPose& CorrectedSim3, const map<kfptr, set<kfptr> >& LoopConnections,
+                                                  const bool& bFixScale) {
+  optimize_essential_graph(pMap, pLoopKF, pCurKF, &NonCorrectedSim3, &CorrectedSim3, LoopConnections, bFixScale);
+}
+
+void Optimizer::OptimizeEssentialGraphMapFusion(mapptr pMap, kfptr pLoopKF, kfptr pCurKF, const map<kfptr, set<kfptr> >& LoopConnections,
+                                                const bool& bFixScale) {
+  optimize_essential_graph(pMap, pLoopKF, pCurKF, nullptr, nullptr, LoopConnections, bFixScale);
+}
 
 // ---- PoseOptimizationClient (S/Optimizer.cpp:215-347) ---------------------------------------------------------------------
 int Optimizer::PoseOptimizationClient(Frame& Frame) {
