@@ -3,7 +3,8 @@
 // KeyFrame::ComputeBoW (cslam/src/KeyFrame.cpp:277-286), i.e. the call
 //     mpORBvocabulary->transform(vCurrentDesc, mBowVec, mFeatVec, 4);
 // (thirdparty/DBoW2/DBoW2/TemplatedVocabulary.h:1127-1192).  Headers stay byte-identical; the DBoW2 containers remain the
-// reference's own types.  Not compiled here (needs OpenCV / Boost / DBoW2 headers).
+// reference's own types.  Compiled against the reference's own ORBVocabulary.h / DBoW2 and run next to ORBVocabulary::transform by
+// tests/test_shim_vocabulary.py (oracle/Makefile: _ref/libvoc_shim.so).
 //
 // The device copy of the vocabulary is made from the same text file the reference loads
 // (ClientSystem.cpp:77, ServerSystem.cpp:165: mpVoc->loadFromTextFile(strVocFile)): call ccm_b200_load_vocabulary(mpVoc.get(),
