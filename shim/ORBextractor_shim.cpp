@@ -1,5 +1,6 @@
 // ORBextractor_shim.cpp — replaces cslam/src/ORBextractor.cpp; cslam/include/cslam/ORBextractor.h stays byte-identical
-// (constructor, operator(), mvImagePyramid, the six inline getters).  Not compiled here (needs OpenCV headers).
+// (constructor, operator(), mvImagePyramid, the six inline getters).  Type-checked against the reference's own
+// cslam/ORBextractor.h (make -C oracle shim-check); its run-time path needs a device.
 #include <cslam/ORBextractor.h>
 
 #include <map>

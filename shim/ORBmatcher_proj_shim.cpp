@@ -8,7 +8,8 @@
 //   SearchBySim3(pKF1, pKF2, vpMatches12, s12, R12, t12, th)                    :1124-1348
 //   SearchByProjection(Frame& CurrentFrame, const Frame& LastFrame, th)         :1350-1476
 //   SearchByProjection(Frame& CurrentFrame, kfptr, sAlreadyFound, th, ORBdist)  :1478-1605
-// cslam/include/cslam/ORBmatcher.h stays byte-identical.  Not compiled here (needs OpenCV / Boost headers).
+// cslam/include/cslam/ORBmatcher.h stays byte-identical.  Compiled against that header and run side by side with the
+// reference's ORBmatcher.cpp on stand-in Frame / KeyFrame / MapPoint objects by tests/test_shim_dropin.py.
 //
 // Every overload has the same three parts.  PRELUDE: the reference's per-point gates up to the GetFeaturesInArea call
 // (bad / already-found tests, camera projection, image bounds, scale-invariance distance, viewing angle, PredictScale).  It is
