@@ -1,6 +1,6 @@
 // ORBextractor_shim.cpp — replaces cslam/src/ORBextractor.cpp; cslam/include/cslam/ORBextractor.h stays byte-identical
-// (constructor, operator(), mvImagePyramid, the six inline getters).  Type-checked against the reference's own
-// cslam/ORBextractor.h (make -C oracle shim-check); its run-time path needs a device.
+// (constructor, operator(), mvImagePyramid, the six inline getters).  Compiled against the reference's own
+// cslam/ORBextractor.h and run next to the reference's ORBextractor.cpp by tests/test_shim_extractor.py.
 #include <cslam/ORBextractor.h>
 
 #include <map>
