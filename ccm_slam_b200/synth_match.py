@@ -71,6 +71,20 @@ def make_queries(grid, m=1500, seed=1, th=3.0, noise_px=2.0, invalid_frac=0.1, m
     return dict(valid=valid, uv=uv, radius=radius, level=level, desc=desc, angle=angle, src=src)
 
 
+def tie_storm(grid, queries=None, pool=6, seed=0):
+    """Replace every descriptor by one of `pool` patterns that lie 8..30 bits from a common base (copies of the inputs are returned).
+    Every window then holds many candidates at exactly the same distance, below the acceptance thresholds: what is selected is decided
+    by the visiting order alone (first minimum, second best on the same level, who keeps a contested feature)."""
+    rng = np.random.default_rng(seed)
+    base = rng.integers(0, 256, size=(1, 32), dtype=np.uint8)
+    pats = np.concatenate([flip_bits(base, [int(rng.integers(8, 31))], rng) for _ in range(pool)])
+    g = dict(grid); g["desc"] = pats[rng.integers(0, pool, grid["desc"].shape[0])]
+    if queries is None:
+        return g
+    q = dict(queries); q["desc"] = pats[rng.integers(0, pool, queries["desc"].shape[0])]
+    return g, q
+
+
 def make_vocabulary(k=10, L=3, seed=0, scoring=0, weighting=0, early_leaf_frac=0.05, tie_frac=0.05, stop_frac=0.02):
     """A DBoW2-style vocabulary tree as the rows of its text file (row 0 = root): parent, leaf flag, descriptor, weight.
     Hierarchical: children are perturbed copies of their parent, so descents are decisive at the top and close at the

@@ -65,6 +65,14 @@ def test_projection_guided_methods(side):
     ran(side, T.test_search_by_sim3)
     ran(side, T.test_search_by_projection_last_frame, 30, 7.0, True)
     ran(side, T.test_search_by_projection_relocalisation, 33, 3.0, 64, False)
+    T.TIES = True                                   # and with ties everywhere: the visiting order alone decides
+    try:
+        ran(side, T.test_fuse, 40, 4.0)
+        ran(side, T.test_search_by_projection_sim3, 42, 2.0)
+        ran(side, T.test_search_by_projection_last_frame, 43, 7.0, True)
+    finally:
+        T.TIES = False
+    ran(side, T.test_ties_track_and_initialization)
 
 
 @pytest.mark.skipif(os.environ.get("CCM_TEST_UNVALIDATED") != "1", reason="first device run pending (set CCM_TEST_UNVALIDATED=1)")

@@ -13,11 +13,13 @@ def dist(q, g):
     return np.unpackbits(np.asarray(q["desc"])[:, None, :] ^ np.asarray(g["desc"])[None, :, :], axis=2).sum(axis=2).astype(np.uint16)
 
 
-@pytest.fixture(scope="module", params=[(0, 1000, 1500, 3.0), (1, 2000, 3000, 7.0), (2, 300, 200, 15.0)])
+@pytest.fixture(scope="module", params=[(0, 1000, 1500, 3.0), (1, 2000, 3000, 7.0), (2, 300, 200, 15.0), (3, 1200, 1800, 6.0)])
 def case(request):
     seed, n, m, th = request.param
     g = sm.make_grid(n=n, seed=10 + seed, clustered=seed != 2)
     q = sm.make_queries(g, m=m, seed=20 + seed, th=th)
+    if seed == 3:                                   # every window full of candidates at identical distances: the visiting order decides
+        g, q = sm.tie_storm(g, q, pool=6, seed=40)
     rng = np.random.default_rng(30 + seed)
     return dict(g=g, q=q, D=dist(q, g), has_obs=(rng.random(m) < 0.85).astype(np.uint8), blocked=(rng.random(n) < 0.2).astype(np.uint8),
                 existing=np.where(rng.random(m) < 0.15, rng.integers(0, n, m), -1).astype(np.int32))

@@ -124,6 +124,9 @@ for _i in range(1, 8):
 CATS = ("good", "behind", "outside", "too_far", "too_near", "bad_angle", "bad")
 
 
+TIES = False   # set by the tie-storm tests below: every descriptor becomes one of six nearby patterns (sm.tie_storm)
+
+
 def _scene(seed, n=900, m=1300, th=3.0, t=(0.25, -0.5, 1.0), scale=1.0, th_is_int=False):
     """keypoints of one image + map points whose projection through Tcw = [I | t] (or Scw = scale * [I | t]) lands on intended pixels"""
     rng = np.random.default_rng(seed)
@@ -152,6 +155,9 @@ def _scene(seed, n=900, m=1300, th=3.0, t=(0.25, -0.5, 1.0), scale=1.0, th_is_in
     normal = cam / dist[:, None]
     normal[cat == CATS.index("bad_angle")] *= -1
     desc = sm.flip_bits(g["desc"][src], rng.integers(0, 70, m), rng)
+    if TIES:
+        g, qd = sm.tie_storm(g, dict(desc=desc), pool=6, seed=seed + 1000)
+        desc = qd["desc"]
     n_obs = rng.integers(1, 6, m).astype(np.int32)
     points = dict(pos=world.astype(f32), normal=normal.astype(f32), min_dist=min_d.astype(f32), max_dist=max_d.astype(f32), desc=desc,
                   bad=(cat == CATS.index("bad")).astype(np.uint8), n_obs=n_obs)
@@ -280,3 +286,49 @@ def test_search_by_projection_relocalisation(ref, seed, th, orb_dist, ori):
     got, n = ref.search_by_projection_frame(S["g"], q, np.ones(m, np.uint8), blocked, True, orb_dist, ori)
     want, wn = ref.ref_search_by_projection_reloc(S["g"], g_kf, INTR, S["t"], S["points"], kf_point, found, blocked, th, orb_dist, ori)
     assert n == wn and np.array_equal(np.where(got == -2, -1, got), want) and n > 150
+
+
+# ---- the same scenes with ties everywhere ----------------------------------------------------------------------------------------
+# Six descriptor patterns 8..30 bits apart: every search window holds several candidates at exactly the same distance, under the
+# acceptance thresholds.  The outcome then rests on the visiting order alone — first minimum, second best on the same level, which query
+# keeps a contested keypoint — and must still be the reference's, index for index.
+@pytest.fixture
+def ties():
+    global TIES
+    TIES = True
+    yield
+    TIES = False
+
+
+def test_ties_projection_overloads(ref, ties):
+    test_fuse(ref, 40, 4.0)
+    test_fuse_sim3(ref, 41, 4.0, 2.0)
+    test_search_by_projection_sim3(ref, 42, 2.0)
+    test_search_by_projection_last_frame(ref, 43, 7.0, True)
+    test_search_by_projection_relocalisation(ref, 44, 10.0, 100, False)
+
+
+def test_ties_track_and_initialization(ref):
+    # these two build their inputs with sm.make_grid / make_queries directly
+    g = sm.make_grid(n=1200, seed=45); q = sm.make_queries(g, m=1500, seed=46)
+    g, q = sm.tie_storm(g, q, pool=6, seed=47)
+    rng = np.random.default_rng(48)
+    m = 1500
+    view_cos = np.where(rng.random(m) < 0.5, f32(0.9995), f32(0.9)).astype(f32)
+    n_obs = np.where(rng.random(m) < 0.85, 3, 0).astype(np.int32); bad = (rng.random(m) < 0.05).astype(np.uint8)
+    blocked = (rng.random(1200) < 0.2).astype(np.uint8)
+    points = dict(desc=q["desc"], bad=bad, n_obs=n_obs, track_in_view=q["valid"], track_xy=q["uv"], track_level=q["level"], track_view_cos=view_cos)
+    r = (np.where(view_cos > f32(0.998), f32(2.5), f32(4.0)).astype(f32) * f32(3.0)).astype(f32)
+    oq = dict(q, valid=(q["valid"].astype(bool) & ~bad.astype(bool)).astype(np.uint8), radius=(r * SF[q["level"]]).astype(f32))
+    for nnratio in (0.8, 1.0):                      # at 1.0 a tie between best and second best on one level still passes (d > ratio * d2 is false)
+        got, n = ref.search_by_projection_track(g, oq, (n_obs > 0).astype(np.uint8), blocked, nnratio)
+        want, wn = ref.ref_search_by_projection_track(g, points, blocked, 3.0, nnratio)
+        assert n == wn and np.array_equal(got, want)
+    assert n > 100
+    g2, qi = sm.make_init_pair(n=900, seed=49)
+    g2, qi = sm.tie_storm(g2, qi, pool=6, seed=50)
+    g1 = dict(desc=qi["desc"], kp_xy=qi["uv"], octave=qi["level"], angle=qi["angle"], bounds=g2["bounds"], cols=g2["cols"], rows=g2["rows"])
+    for nnratio in (0.9, 1.01):
+        got, n = ref.search_for_initialization(g2, qi, nnratio, True)
+        want, wn, prev = ref.ref_search_for_initialization(g1, g2, qi["uv"], 100, nnratio, True)
+        assert n == wn and np.array_equal(got, want)

@@ -105,6 +105,20 @@ def test_search_by_projection_relocalisation(side, seed, th, orb_dist, ori):
     ran(side, T.test_search_by_projection_relocalisation, seed, th, orb_dist, ori)
 
 
+def test_tie_storm_scenes(side):
+    """the same through both implementations with ties everywhere (six descriptor patterns): the visiting order alone decides"""
+    T.TIES = True
+    try:
+        ran(side, T.test_fuse, 40, 4.0)
+        ran(side, T.test_fuse_sim3, 41, 4.0, 2.0)
+        ran(side, T.test_search_by_projection_sim3, 42, 2.0)
+        ran(side, T.test_search_by_projection_last_frame, 43, 7.0, True)
+        ran(side, T.test_search_by_projection_relocalisation, 44, 10.0, 100, False)
+    finally:
+        T.TIES = False
+    ran(side, T.test_ties_track_and_initialization)
+
+
 def test_shims_type_check_against_the_reference_headers(oracle):
     """shim/ORBextractor_shim.cpp and the two matcher shims define members of the reference's classes: the compiler checks every
     signature against cslam/ORBextractor.h / cslam/ORBmatcher.h as they are in the reference tree (OpenCV and the Frame / KeyFrame /
