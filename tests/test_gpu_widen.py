@@ -18,11 +18,13 @@ def _dev():
     api.init(0)
 
 
-@pytest.fixture(scope="module", params=[(0, 1000, 1500, 3.0), (1, 2000, 4000, 7.0), (2, 300, 33, 15.0)])
+@pytest.fixture(scope="module", params=[(0, 1000, 1500, 3.0), (1, 2000, 4000, 7.0), (2, 300, 33, 15.0), (3, 1200, 1800, 6.0)])
 def case(request):
     seed, n, m, th = request.param
     g = sm.make_grid(n=n, seed=40 + seed, clustered=seed != 2)
     q = sm.make_queries(g, m=m, seed=50 + seed, th=th)
+    if seed == 3:       # ties in every window (six nearby descriptor patterns): the visiting order alone decides — the case that matters
+        g, q = sm.tie_storm(g, q, pool=6, seed=70)      # most for an on-device selection (CCM_MATCH_WINDOW=1)
     rng = np.random.default_rng(60 + seed)
     return dict(g=g, q=q, has_obs=(rng.random(m) < 0.85).astype(np.uint8), blocked=(rng.random(n) < 0.2).astype(np.uint8),
                 existing=np.where(rng.random(m) < 0.15, rng.integers(0, n, m), -1).astype(np.int32))
