@@ -458,7 +458,7 @@ def build_ref() -> str | None:
     and no prebuilt library travelled with the repository."""
     so = os.path.join(_HERE, "_ref", "libdbow2_ref.so")
     if os.path.isdir("/root/reference/cslam/thirdparty/DBoW2"):
-        subprocess.check_call(["make", "-C", _HERE, "-s", "ref"])
+        subprocess.check_call(["make", "-C", _HERE, "-s", "-j", str(min(8, os.cpu_count() or 1)), "ref"])
     return so if os.path.exists(so) else None
 
 
