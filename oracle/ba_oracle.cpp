@@ -320,8 +320,13 @@ bool solve_system(BA& s, double lambda) {
       const int i1 = s.pose_idx[s.edges[s.active[ea]].kf];
       const double* B = &s.Hpl[(size_t)ea * 18];
       const double* xp = &s.x[(size_t)i1 * 6];
-      for (int cc = 0; cc < 3; cc++)
-        for (int r = 0; r < 6; r++) c[cc] -= B[r * 3 + cc] * xp[r];
+      // _HplCCS->rightMultiply(cl, -xp): per block  y.segment<3>() += B^T * (-x).segment<6>()  (sparse_block_matrix_ccs.h:108-128,
+      // matrix_operations.h:54-57) — the six-term product is formed first, then added
+      for (int cc = 0; cc < 3; cc++) {
+        double d = B[cc] * -xp[0];
+        for (int r = 1; r < 6; r++) d += B[r * 3 + cc] * -xp[r];
+        c[cc] += d;
+      }
     }
     mat3vec(&s.Dinv[(size_t)l * 9], c, xl + (size_t)l * 3);
   }
