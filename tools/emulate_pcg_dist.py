@@ -90,7 +90,10 @@ def dist(S, b, Dinv_blocks, n, BS, N, agg, nc, prolong, Acinv, tol, maxit):
     for k in range(N): xs[own(k)] = x[k][own(k)]
     return xs, it
 
-for (n, BS, band, N, nc_t, prolong) in [(60, 6, 6, 2, 8, 0), (60, 6, 6, 4, 8, 1), (97, 6, 12, 8, 12, 1), (40, 7, 5, 3, 0, 0), (33, 6, 4, 8, 5, 1)]:
+CASES = [(60, 6, 6, 2, 8, 0), (60, 6, 6, 4, 8, 1), (97, 6, 12, 8, 12, 1), (40, 7, 5, 3, 0, 0), (33, 6, 4, 8, 5, 1)]
+
+
+def run_case(n, BS, band, N, nc_t, prolong):
     S = make(n, BS, band); b = rng.normal(size=n * BS)
     Db = [np.linalg.inv(S[a*BS:(a+1)*BS, a*BS:(a+1)*BS]) for a in range(n)]
     Dinv = sp.block_diag(Db).toarray()
@@ -106,4 +109,12 @@ for (n, BS, band, N, nc_t, prolong) in [(60, 6, 6, 2, 8, 0), (60, 6, 6, 4, 8, 1)
         agg = 0; nc = 0; P = None; Acinv = None
     xs, its = serial(S, b, Dinv, P, Acinv, 1e-10, 500)
     xd, itd = dist(S, b, Db, n, BS, N, agg, nc, prolong, Acinv, 1e-10, 500)
-    print(f"n={n} BS={BS} N={N} nc={nc} prolong={prolong}: serial {its} its, distributed {itd} its, |x_d - x_s| / |x_s| = {np.abs(xd - xs).max() / np.abs(xs).max():.2e}, residual {np.linalg.norm(S @ xd - b) / np.linalg.norm(b):.2e}")
+    return dict(n=n, BS=BS, N=N, nc=nc, prolong=prolong, serial_its=its, dist_its=itd, rel_err=float(np.abs(xd - xs).max() / np.abs(xs).max()),
+                residual=float(np.linalg.norm(S @ xd - b) / np.linalg.norm(b)))
+
+
+
+if __name__ == "__main__":
+    for c in CASES:
+        r = run_case(*c)
+        print("n={n} BS={BS} N={N} nc={nc} prolong={prolong}: serial {serial_its} its, distributed {dist_its} its, |x_d - x_s| / |x_s| = {rel_err:.2e}, residual {residual:.2e}".format(**r))
