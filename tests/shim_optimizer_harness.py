@@ -13,7 +13,9 @@ from ccm_slam_b200 import synth_match as sm
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "..", "oracle", "_ref", "liboptimizer_shim.so")
+_SO_GPU = os.path.join(_HERE, "..", "oracle", "_ref", "liboptimizer_shim_gpu.so")   # the same shim over the real device entry points
 _LIB = None
+_GPU = False
 VP = C.c_void_p
 
 
@@ -33,10 +35,17 @@ def lib():
     global _LIB
     if _LIB is None:
         from oracle import pyoracle
-        if pyoracle.build_ref() is None or not os.path.exists(_SO):
+        so = _SO_GPU if _GPU else _SO
+        if pyoracle.build_ref() is None or not os.path.exists(so):
             return None
-        _LIB = C.CDLL(_SO)
+        _LIB = C.CDLL(so)
     return _LIB
+
+
+def use_device(on):
+    """switch the harness between the CPU-doubled library and the one linked against the product's device entry points"""
+    global _LIB, _GPU
+    _LIB, _GPU = None, bool(on)
 
 
 def _p(a):

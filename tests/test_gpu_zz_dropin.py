@@ -86,3 +86,33 @@ def test_bow_and_triangulation_methods(side):
         for _ in range(20):
             a, b = rng.integers(0, 256, 32, dtype=np.uint8), rng.integers(0, 256, 32, dtype=np.uint8)
             assert side._o.ref_match().ref_descriptor_distance(a.ctypes.data, b.ctypes.data) == int(np.unpackbits(a ^ b).sum())
+
+
+@pytest.mark.skipif(os.environ.get("CCM_TEST_UNVALIDATED") != "1", reason="first device run pending (set CCM_TEST_UNVALIDATED=1)")
+def test_optimizer_shim_on_the_device(oracle):
+    """shim/Optimizer_shim.cpp through cslam::Optimizer's interface with the real device entry points underneath: MapFusionGBA on a
+    stand-in map must land where the CPU-doubled run lands, within the device path's tolerance (f32 poses / points written back)."""
+    from ccm_slam_b200 import api, synth
+    from tests import shim_optimizer_harness as H
+    if api.device_count() == 0:
+        pytest.skip("no CUDA device")
+    api.init(0)
+    p = synth.make_config("small")
+    sc = H.scene_from_problem(p, oracle, seed=3, map_id=0, bad_kf=0.1, bad_mp=0.1)
+    sc["kf_bad"][0] = 0
+    H.use_device(False)
+    if H.lib() is None:
+        pytest.skip("no oracle/_ref/liboptimizer_shim.so")
+    cpu = H.run_gba(sc, 0, 8, True, (0, 0))
+    H.use_device(True)
+    try:
+        if H.lib() is None:
+            pytest.skip("no oracle/_ref/liboptimizer_shim_gpu.so")
+        l0 = api.kernel_launches()
+        gpu = H.run_gba(sc, 0, 8, True, (0, 0))
+        assert api.kernel_launches() > l0
+    finally:
+        H.use_device(False)
+    assert np.array_equal(gpu["kf_set_pose"], cpu["kf_set_pose"]) and np.array_equal(gpu["mp_update_normal"], cpu["mp_update_normal"])
+    assert np.abs(gpu["kf_Tcw"] - cpu["kf_Tcw"]).max() <= 1e-4 * max(1.0, np.abs(cpu["kf_Tcw"]).max())
+    assert np.abs(gpu["mp_pos"] - cpu["mp_pos"]).max() <= 1e-4 * np.abs(cpu["mp_pos"]).max()

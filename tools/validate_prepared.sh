@@ -20,7 +20,8 @@ if [ "$mode" = single ]; then
   # 1c. device-side window search of Fuse / SearchBySim3 (k_window_best)
   (CCM_MATCH_WINDOW=1 timeout 120 python -m pytest tests/test_gpu_widen.py -m gpu -x -q 2>&1 | tail -5) > gpurun_out/match_window.log
   # 1d. the matcher shims on the device next to the reference's ORBmatcher.cpp: SearchByBoW x2 / SearchForTriangulation / DescriptorDistance
-  #     reach a device for the first time here (the projection-guided ones run ungated in the suite below)
+  #     and shim/Optimizer_shim.cpp's MapFusionGBA
+  #     reach a device for the first time here (the projection-guided matcher methods run ungated in the suite below)
   (CCM_TEST_UNVALIDATED=1 timeout 120 python -m pytest tests/test_gpu_zz_dropin.py -m gpu -x -q 2>&1 | tail -5) > gpurun_out/dropin_gpu.log
   # 2. the whole GPU suite with the current defaults (CTA-128 Schur kernel, new golden / SearchForInitialization tests)
   (timeout 120 python -m pytest tests -m gpu -x -q 2>&1 | tail -5) > gpurun_out/gpu_suite.log
