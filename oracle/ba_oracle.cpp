@@ -14,7 +14,8 @@
 // pinned by scipy / finite-difference witnesses in tests/test_oracle_ba.py, and the LM control flow of orc_ba_solve by the
 // reference's own optimization_algorithm_levenberg.cpp compiled over these pieces (ref_lm_wrap.cpp, tests/test_oracle_vs_reference_lm.py),
 // edge errors / Jacobians / Huber / constructQuadraticForm by the reference's own types compiled over a stand-in Eigen
-// (ref_g2o_wrap.cpp, tests/test_oracle_vs_reference_g2o.py) — bit for bit.
+// (ref_g2o_wrap.cpp, tests/test_oracle_vs_reference_g2o.py), structure / Schur complement / back-substitution by the reference's own
+// BlockSolver_6_3 (ref_ba_block_wrap.cpp) — bit for bit.  Only the sparse LDL^T itself has no reference counterpart here.
 #include "oracle.h"
 
 #include <chrono>

@@ -319,16 +319,19 @@ inline void sim3_map(const Sim3& S, const double x[3], double out[3]) {  // G/ty
   for (int i = 0; i < 3; i++) out[i] = S.s * r[i] + S.t[i];
 }
 
-// Eigen Matrix3d::inverse (cofactor / determinant), row-major
+// Eigen Matrix3d::inverse, row-major in / out.  Eigen/src/LU/Inverse.h (compute_inverse<MatrixType, ResultType, 3>): the cofactors of
+// column 0 give the determinant as (cofactors_col0 . col(0)).sum() — a three-term unrolled reduction, a0 + (a1 + a2) — and every
+// entry is its cofactor times 1/det.  (Which association a given Eigen build uses for that sum is a property of the build; the
+// reference's g2o sources compiled over oracle/ref_stub/Eigen — ref_ba_block_wrap.cpp — use this one.)
 inline void inv3(const double m[9], double o[9]) {
-  double c00 = m[4] * m[8] - m[5] * m[7];
-  double c10 = m[5] * m[6] - m[3] * m[8];
-  double c20 = m[3] * m[7] - m[4] * m[6];
-  double det = m[0] * c00 + m[1] * c10 + m[2] * c20;
-  double id = 1.0 / det;
-  o[0] = c00 * id; o[1] = (m[2] * m[7] - m[1] * m[8]) * id; o[2] = (m[1] * m[5] - m[2] * m[4]) * id;
-  o[3] = c10 * id; o[4] = (m[0] * m[8] - m[2] * m[6]) * id; o[5] = (m[2] * m[3] - m[0] * m[5]) * id;
-  o[6] = c20 * id; o[7] = (m[1] * m[6] - m[0] * m[7]) * id; o[8] = (m[0] * m[4] - m[1] * m[3]) * id;
+  const double c0 = m[4] * m[8] - m[5] * m[7];      // cofactor(0,0)
+  const double c1 = m[7] * m[2] - m[8] * m[1];      // cofactor(1,0)
+  const double c2 = m[1] * m[5] - m[2] * m[4];      // cofactor(2,0)
+  const double det = c0 * m[0] + (c1 * m[3] + c2 * m[6]);
+  const double id = 1.0 / det;
+  o[0] = c0 * id; o[1] = c1 * id; o[2] = c2 * id;
+  o[3] = (m[5] * m[6] - m[3] * m[8]) * id; o[4] = (m[8] * m[0] - m[6] * m[2]) * id; o[5] = (m[2] * m[3] - m[0] * m[5]) * id;
+  o[6] = (m[3] * m[7] - m[4] * m[6]) * id; o[7] = (m[6] * m[1] - m[7] * m[0]) * id; o[8] = (m[0] * m[4] - m[1] * m[3]) * id;
 }
 
 }  // namespace orc

@@ -19,7 +19,8 @@
  * g2o's vertex / edge types, Lie groups, base-edge templates and Huber kernel (over a stand-in for Eigen's small fixed-size arithmetic).
  * orb_oracle.cpp, match_oracle.cpp, proj_oracle.cpp and bow_oracle.cpp are held to that code exactly
  * (tests/test_oracle_vs_reference_{orb,matchers,dbow2,lm,g2o,single,pgo}.py); composed, the last two run every optimisation of the path
- * as reference code except the linear solve (ref_{ba,single,pgo}_full_wrap.cpp), and the oracle equals those runs bit for bit.
+ * as reference code except the linear solve (ref_{ba,single,pgo}_full_wrap.cpp; for BA also g2o's own BlockSolver_6_3, ref_ba_block_wrap.cpp:
+ * only the sparse factorisation is then the oracle's), and the oracle equals those runs bit for bit.
  *
  * Citations: G/ = cslam/thirdparty/g2o/g2o/, S/ = cslam/src/ under /root/reference.
  */

@@ -536,6 +536,28 @@ def ref_ba_full_solve(p, **kw):
     return ba_solve(p, fn=ref_ba_full().ref_ba_full_solve, **kw)
 
 
+_REF_BA_BLOCK = None
+
+
+def ref_ba_block():
+    global _REF_BA_BLOCK
+    if _REF_BA_BLOCK is None:
+        if build_ref() is None:
+            return None
+        so = os.path.join(_HERE, "_ref", "libba_block_ref.so")
+        if not os.path.exists(so):
+            return None
+        _REF_BA_BLOCK = C.CDLL(so)
+    return _REF_BA_BLOCK
+
+
+def ref_ba_block_solve(p, **kw):
+    """ba_solve() with the reference's LM driver, vertices / edges / kernels AND its BlockSolver_6_3 (structure, Schur complement,
+    back-substitution); the oracle supplies only the sparse LDL^T under LinearSolver::solve (oracle/ref_ba_block_wrap.cpp).
+    Trace columns 1 and 3 are NaN."""
+    return ba_solve(p, fn=ref_ba_block().ref_ba_block_solve, **kw)
+
+
 def ref_ba_solve(p, **kw):
     """ba_solve() with g2o's own OptimizationAlgorithmLevenberg::solve (compiled from the reference tree, oracle/ref_lm_wrap.cpp)
     deciding lambda, trials and termination; trace column 3 (rho) is NaN — it is a local of the reference's function."""

@@ -1,22 +1,19 @@
-// ref_ba_full_wrap.cpp — a whole bundle-adjustment optimize() with the reference's code on both sides of the linear solve
+// ref_ba_block_wrap.cpp — a whole bundle-adjustment optimize() in which only the sparse factorisation is not the reference's
 // (TEST INFRASTRUCTURE, NOT PRODUCT).
 //
-// Puts the two reference pins together: g2o's own Levenberg-Marquardt driver (optimization_algorithm{,_with_hessian,_levenberg}.cpp,
-// included textually below, as in ref_lm_wrap.cpp) runs over g2o's own graph elements (VertexSE3Expmap, VertexSBAPointXYZ,
-// EdgeSE3ProjectXYZ, RobustKernelHuber with their base templates: errors, Jacobians, constructQuadraticForm into mapped blocks, oplus,
-// the backup stack behind push / pop — compiled from the reference tree against oracle/ref_stub/Eigen, as in ref_g2o_wrap.cpp).
-// What is still the oracle's: the index mapping / active set (init_active), and everything under Solver::solve() — the Schur
-// complement and the LDL^T of BlockSolver / LinearSolverEigen (ba_oracle.cpp solve_system).  The glue restates, a few lines each,
-// SparseOptimizer::{optimize, computeActiveErrors, activeRobustChi2, update, push, pop} (G/core/sparse_optimizer.cpp:61-114,354-435,
-// 600-613) and BlockSolver::{buildStructure's memory mapping, buildSystem} (G/core/block_solver.hpp:175-250,501-560).
-// ref_ba_full_solve() has orc_ba_solve()'s signature; tests/test_oracle_vs_reference_lm.py compares the two runs bit for bit.
-#include "ba_oracle.cpp"  // the oracle's pieces; its unnamed namespace is visible here
+// One step further than ref_ba_full_wrap.cpp: next to g2o's own Levenberg-Marquardt driver and graph elements, g2o's own
+// BlockSolver_6_3 — buildStructure (block allocation, Hschur pattern, the transposed pose-landmark blocks), buildSystem, setLambda /
+// restoreDiagonal, and solve() with the Schur complement and the landmark back-substitution (G/core/block_solver.h(pp), solver.cpp,
+// sparse_block_matrix*.h(pp), matrix_operations.h, compiled where they lie against oracle/ref_stub/Eigen) — runs as the reference's
+// code.  The oracle supplies one thing: LinearSolver::solve on the reduced camera system (the sparse LDL^T of sparse_ldlt.hpp, standing
+// in for LinearSolverEigen, G/solvers/linear_solver_eigen.h:106-133), fed from the reference's SparseBlockMatrix.  The glue restates
+// what ref_ba_full_wrap.cpp restates of SparseOptimizer (optimize, computeActiveErrors, activeRobustChi2, update, push, pop, the
+// index mapping with its hessian indices).  ref_ba_block_solve() has orc_ba_solve()'s signature.
+#include "ba_oracle.cpp"  // BA::load / init_active for the active set and index mapping, BlockSym + SparseLDLT; unnamed namespace visible here
 
 #include <iomanip>
 #include <iostream>
 
-#define G2O_SPARSE_BLOCK_MATRIX_
-#define G2O_SOLVER_H
 #define G2O_GRAPH_OPTIMIZER_CHOL_H_
 #include <core/batch_stats.h>
 #include <core/hyper_graph.h>
@@ -26,12 +23,11 @@
 
 namespace g2o {
 
-class MatrixXd;
-template <class M> class SparseBlockMatrix;
 class OptimizationAlgorithm;
 
 class SparseOptimizer : public OptimizableGraph {
  public:
+  typedef OptimizableGraph::EdgeContainer EdgeContainer;
   SparseOptimizer(BA& s, const orc_ba_problem* p, int robust, double delta, const volatile uint8_t* stop)
       : s(s), stop_(stop), algorithm_(0), last_chi(0), chi_at_push(0), first_chi_(0), have_first_(false), trials(0) {
     for (int k = 0; k < p->K; k++) {   // S/Optimizer.cpp:700-712
@@ -61,12 +57,15 @@ class SparseOptimizer : public OptimizableGraph {
       kernels.push_back(rk);
       const double* in = p->intr + 4 * p->obs_kf[e];
       ed->fx = in[0]; ed->fy = in[1]; ed->cx = in[2]; ed->cy = in[3];
+      mp[p->obs_mp[e]]->edges().insert(ed); kf[p->obs_kf[e]]->edges().insert(ed);   // HyperGraph::addEdge (G/core/hyper_graph.cpp:80-95)
       edges.push_back(ed);
     }
-    // initializeOptimization(0): level-0 edges in id order; index mapping = free poses, then points (the oracle's init_active)
+    // initializeOptimization(0) + buildIndexMapping (G/core/sparse_optimizer.cpp:166-267): level-0 edges in id order; free poses then
+    // points, each given its position as hessian index; fixed vertices keep -1
     for (int e : s.active) active.push_back(edges[e]);
     for (int i = 0; i < s.np; i++) iv_.push_back(kf[s.idx_pose[i]]);
     for (int l = 0; l < s.nl; l++) iv_.push_back(mp[s.idx_pt[l]]);
+    for (size_t i = 0; i < iv_.size(); i++) iv_[i]->setHessianIndex((int)i);
   }
   ~SparseOptimizer() {
     for (size_t i = 0; i < edges.size(); i++) { delete edges[i]; delete kernels[i]; }
@@ -75,12 +74,14 @@ class SparseOptimizer : public OptimizableGraph {
   }
   const VertexContainer& indexMapping() const { return iv_; }
   const VertexContainer& activeVertices() const { return iv_; }
+  const EdgeContainer& activeEdges() const { return active; }
+  JacobianWorkspace& jacobianWorkspace() { return workspace; }
   void computeActiveErrors() { for (size_t k = 0; k < active.size(); k++) active[k]->computeError(); }
   double activeRobustChi2() {
     Eigen::Vector3d rho;
     double chi = 0.0;
     for (size_t k = 0; k < active.size(); k++) {
-      const EdgeSE3ProjectXYZ* e = active[k];
+      const OptimizableGraph::Edge* e = active[k];
       if (e->robustKernel()) { e->robustKernel()->robustify(e->chi2(), rho); chi += rho[0]; }
       else chi += e->chi2();
     }
@@ -93,6 +94,7 @@ class SparseOptimizer : public OptimizableGraph {
   void discardTop() { for (size_t i = 0; i < iv_.size(); i++) iv_[i]->discardTop(); }
   void update(const double* update) { for (size_t i = 0; i < iv_.size(); ++i) { iv_[i]->oplus(update); update += iv_[i]->dimension(); } }
   bool terminate() { return stop_ && *stop_; }
+  bool verbose() const { return false; }
   void setAlgorithm(OptimizationAlgorithm* a);
   int optimize(int iterations, orc_ba_result* r);
   BA& s;
@@ -100,7 +102,8 @@ class SparseOptimizer : public OptimizableGraph {
   OptimizationAlgorithm* algorithm_;
   std::vector<VertexSE3Expmap*> kf;
   std::vector<VertexSBAPointXYZ*> mp;
-  std::vector<EdgeSE3ProjectXYZ*> edges, active;
+  std::vector<EdgeSE3ProjectXYZ*> edges;
+  EdgeContainer active;
   std::vector<RobustKernelHuber*> kernels;
   VertexContainer iv_;
   double last_chi, chi_at_push, first_chi_;
@@ -109,62 +112,42 @@ class SparseOptimizer : public OptimizableGraph {
   JacobianWorkspace workspace;
 };
 
-class Solver {
+}  // namespace g2o
+
+#include <core/block_solver.h>   // the reference's own: Solver, BlockSolver<Traits>, SparseBlockMatrix*, LinearSolver
+
+namespace g2o {
+
+// LinearSolverEigen's place: the reduced camera system arrives as the reference's SparseBlockMatrix (upper triangle, column maps of
+// column-major 6x6 blocks) and is factorised by the oracle's sparse LDL^T
+class OracleLDLT : public LinearSolver<BlockSolver_6_3::PoseMatrixType> {
  public:
-  explicit Solver(BA& s) : s(s), opt_(0), lambda_(0), schur_(false) {}
-  virtual ~Solver() {}
-  bool init(SparseOptimizer* o, bool) { opt_ = o; return true; }
-  SparseOptimizer* optimizer() const { return opt_; }
-  bool buildStructure(bool = false) {
-    build_structure(s);   // the oracle's Schur pattern and landmark columns, used by solve_system below
-    hpp.assign((size_t)s.np * 36, 0.); hll.assign((size_t)s.nl * 9, 0.); hpl.assign(s.active.size() * 18, 0.);
-    b_.assign((size_t)s.np * 6 + (size_t)s.nl * 3, 0.);
-    for (int i = 0; i < s.np; i++) opt_->iv_[i]->mapHessianMemory(&hpp[(size_t)i * 36]);
-    for (int l = 0; l < s.nl; l++) opt_->iv_[s.np + l]->mapHessianMemory(&hll[(size_t)l * 9]);
-    for (size_t a = 0; a < opt_->active.size(); a++)   // edges to a fixed pose get no block (ind == -1: continue)
-      if (!static_cast<OptimizableGraph::Vertex*>(opt_->active[a]->vertex(1))->fixed()) opt_->active[a]->mapHessianMemory(&hpl[a * 18], 0, 1, true);
+  typedef BlockSolver_6_3::PoseMatrixType M;
+  OracleLDLT() : analyzed_(false), last_lambda_(0) {}
+  virtual bool init() { analyzed_ = false; return true; }
+  virtual bool solve(const SparseBlockMatrix<M>& A, double* x, double* b) {
+    const int n = (int)A.blockCols().size();
+    std::vector<std::vector<std::pair<int, const M*> > > rows(n);
+    for (int j = 0; j < n; j++)
+      for (SparseBlockMatrix<M>::IntBlockMap::const_iterator it = A.blockCols()[j].begin(); it != A.blockCols()[j].end(); ++it)
+        if (it->first <= j) rows[it->first].push_back(std::make_pair(j, (const M*)it->second));
+    S_.nb = n; S_.bs = 6; S_.rowptr.assign(n + 1, 0); S_.col.clear();
+    for (int i = 0; i < n; i++) { for (size_t q = 0; q < rows[i].size(); q++) S_.col.push_back(rows[i][q].first); S_.rowptr[i + 1] = (int)S_.col.size(); }
+    S_.val.assign(S_.col.size() * 36, 0.);
+    size_t q = 0;
+    for (int i = 0; i < n; i++)
+      for (size_t k = 0; k < rows[i].size(); k++, q++)
+        for (int r = 0; r < 6; r++) for (int c = 0; c < 6; c++) S_.val[q * 36 + r * 6 + c] = (*rows[i][k].second)(r, c);
+    if (!analyzed_) { ldlt_.analyze(S_); analyzed_ = true; }
+    if (!ldlt_.factorize(S_)) return false;
+    ldlt_.solve(b, x);
     return true;
   }
-  bool updateStructure(const std::vector<HyperGraph::Vertex*>&, const HyperGraph::EdgeSet&) { return false; }
-  bool buildSystem() {
-    for (size_t i = 0; i < opt_->iv_.size(); ++i) opt_->iv_[i]->clearQuadraticForm();
-    std::fill(hpp.begin(), hpp.end(), 0.); std::fill(hll.begin(), hll.end(), 0.); std::fill(hpl.begin(), hpl.end(), 0.);
-    for (size_t k = 0; k < opt_->active.size(); ++k) {
-      EdgeSE3ProjectXYZ* e = opt_->active[k];
-      e->BaseBinaryEdge<2, Vector2d, VertexSBAPointXYZ, VertexSE3Expmap>::linearizeOplus(opt_->workspace);
-      e->constructQuadraticForm();
-    }
-    double* b = b_.data();
-    for (size_t i = 0; i < opt_->iv_.size(); ++i) b += opt_->iv_[i]->copyB(b);
-    return true;
-  }
-  bool setLambda(double lambda, bool = false) { lambda_ = lambda; return true; }
-  void restoreDiagonal() {}
-  bool solve() {
-    // hand the system to the oracle's Schur complement + LDL^T in its own layout (row-major blocks)
-    for (int i = 0; i < s.np; i++)
-      for (int r = 0; r < 6; r++) for (int c = 0; c < 6; c++) s.Hpp[(size_t)i * 36 + r * 6 + c] = hpp[(size_t)i * 36 + c * 6 + r];
-    for (int l = 0; l < s.nl; l++)
-      for (int r = 0; r < 3; r++) for (int c = 0; c < 3; c++) s.Hll[(size_t)l * 9 + r * 3 + c] = hll[(size_t)l * 9 + c * 3 + r];
-    for (size_t a = 0; a < s.active.size(); a++)
-      for (int r = 0; r < 6; r++) for (int c = 0; c < 3; c++) s.Hpl[a * 18 + r * 3 + c] = hpl[a * 18 + c * 6 + r];
-    std::copy(b_.begin(), b_.begin() + (size_t)s.np * 6, s.bp.begin());
-    std::copy(b_.begin() + (size_t)s.np * 6, b_.end(), s.bl.begin());
-    return solve_system(s, lambda_);
-  }
-  bool computeMarginals(SparseBlockMatrix<MatrixXd>&, const std::vector<std::pair<int, int> >&) { return false; }
-  double* x() { return s.x.data(); }
-  double* b() { return b_.data(); }
-  size_t vectorSize() const { return b_.size(); }
-  bool schur() { return schur_; }
-  bool supportsSchur() { return true; }
-  void setSchur(bool v) { schur_ = v; }
-  void setWriteDebug(bool) {}
-  BA& s;
-  SparseOptimizer* opt_;
-  double lambda_;
-  bool schur_;
-  std::vector<double> hpp, hll, hpl, b_;
+ private:
+  BlockSym S_;
+  SparseLDLT ldlt_;
+  bool analyzed_;
+  double last_lambda_;
 };
 
 }  // namespace g2o
@@ -187,15 +170,17 @@ int SparseOptimizer::optimize(int iterations, orc_ba_result* r) {  // G/core/spa
   OptimizationAlgorithm::SolverResult result = OptimizationAlgorithm::OK;
   for (int i = 0; i < iterations && !terminate() && ok; i++) {
     const int trials_before = trials;
+    const double lambda_before = lm->currentLambda();
     result = algorithm_->solve(i, false);
     ok = (result == OptimizationAlgorithm::OK);
     if (i == 0) r->chi2_initial = first_chi_;
     if (r->trace && r->trace_len < r->trace_cap) {
       double* tr = r->trace + (size_t)r->trace_len * ORC_TRACE_COLS;
-      tr[0] = i; tr[1] = static_cast<Solver*>(lm->solver())->lambda_; tr[2] = last_chi;
-      tr[3] = std::numeric_limits<double>::quiet_NaN();
+      tr[0] = i; tr[1] = std::numeric_limits<double>::quiet_NaN();   // the lambda of the last trial lives inside the real BlockSolver
+      tr[2] = last_chi; tr[3] = std::numeric_limits<double>::quiet_NaN();
       tr[4] = lm->levenbergIteration(); tr[5] = lm->currentLambda();
       r->trace_len++;
+      (void)lambda_before;
     }
     r->trials_total += trials - trials_before;
     r->chi2_final = last_chi; r->lambda_final = lm->currentLambda();
@@ -207,7 +192,7 @@ int SparseOptimizer::optimize(int iterations, orc_ba_result* r) {  // G/core/spa
 
 }  // namespace g2o
 
-extern "C" int ref_ba_full_solve(const orc_ba_problem* p, const orc_ba_options* o, orc_ba_result* r) {
+extern "C" int ref_ba_block_solve(const orc_ba_problem* p, const orc_ba_options* o, orc_ba_result* r) {
   BA s;
   load(s, p, o->robust, o->huber_delta);
   init_active(s);
@@ -215,14 +200,14 @@ extern "C" int ref_ba_full_solve(const orc_ba_problem* p, const orc_ba_options* 
   r->chi2_initial = r->chi2_final = 0; r->lambda_final = 0;
   g2o::SparseOptimizer optimizer(s, p, o->robust, o->huber_delta, o->stop);
   {
-    g2o::OptimizationAlgorithmLevenberg* lm = new g2o::OptimizationAlgorithmLevenberg(new g2o::Solver(s));
+    g2o::BlockSolver_6_3* solver_ptr = new g2o::BlockSolver_6_3(new g2o::OracleLDLT());   // S/Optimizer.cpp:681-687 with the solver swapped
+    g2o::OptimizationAlgorithmLevenberg* lm = new g2o::OptimizationAlgorithmLevenberg(solver_ptr);
     if (o->lambda_init > 0) lm->setUserLambdaInit(o->lambda_init);
     if (o->max_trials > 0) lm->setMaxTrialsAfterFailure(o->max_trials);
     optimizer.setAlgorithm(lm);
     r->iters_done = optimizer.optimize(o->iterations, r);
     delete lm;
   }
-  // read the result out of the reference's vertices and edges (S/Optimizer.cpp:803-857 reads estimate(); :540-566 chi2(), isDepthPositive())
   for (int k = 0; k < p->K; k++) {
     const g2o::SE3Quat& T = optimizer.kf[k]->estimate();
     double* q = r->poses + 7 * (size_t)k;

@@ -1,6 +1,6 @@
 // Stand-in for g2o's graph classes (TEST INFRASTRUCTURE, NOT PRODUCT): what base_vertex.h, base_edge.h, base_unary_edge.h(pp),
 // base_binary_edge.h(pp) and the types/ sources of the reference use of optimizable_graph.h, jacobian_workspace.h, creators.h and
-// the two factories — and nothing else.  Force-included (-include) in front of the reference's own translation units and of
+// the two factories — and nothing else.  Vertex / Edge derive from the reference's own HyperGraph::Vertex / Edge.  Force-included (-include) in front of the reference's own translation units and of
 // oracle/ref_g2o_wrap.cpp; the guards of the replaced headers are defined here so that the quote-includes inside the reference
 // files find them "already seen".  Member names and meanings follow G/core/optimizable_graph.h:90-500.
 #ifndef CCM_REF_STUB_G2O_CORE_STANDIN
@@ -14,6 +14,7 @@
 #define G2O_REGISTER_TYPE(name, classname)
 
 #include <Eigen/Core>
+#include <core/hyper_graph.h>
 #include <cstddef>
 #include <iostream>
 #include <set>
@@ -33,17 +34,20 @@ class JacobianWorkspace {  // G/core/jacobian_workspace.h:69: one scratch block 
 
 class OptimizableGraph {
  public:
-  class Vertex {
+  // G/core/optimizable_graph.h:90-500, on top of the reference's own HyperGraph::Vertex / Edge (G/core/hyper_graph.h, compiled in place)
+  class Vertex : public HyperGraph::Vertex {
    public:
-    Vertex() : _id(-1), _dimension(-1), _fixed(false), _marginalized(false) {}
+    Vertex() : HyperGraph::Vertex(-1), _hessianIndex(-1), _dimension(-1), _colInHessian(-1), _fixed(false), _marginalized(false) {}
     virtual ~Vertex() {}
-    int id() const { return _id; }
-    void setId(int id) { _id = id; }
     int dimension() const { return _dimension; }
     bool fixed() const { return _fixed; }
     void setFixed(bool f) { _fixed = f; }
     bool marginalized() const { return _marginalized; }
     void setMarginalized(bool m) { _marginalized = m; }
+    int hessianIndex() const { return _hessianIndex; }
+    void setHessianIndex(int ti) { _hessianIndex = ti; }
+    int colInHessian() const { return _colInHessian; }
+    void setColInHessian(int c) { _colInHessian = c; }
     void oplus(const double* v) { oplusImpl(v); updateCache(); }  // G/core/optimizable_graph.h:259-263
     void setToOrigin() { setToOriginImpl(); updateCache(); }
     void updateCache() {}
@@ -59,20 +63,16 @@ class OptimizableGraph {
    protected:
     virtual void oplusImpl(const double* v) = 0;
     virtual void setToOriginImpl() = 0;
-    int _id, _dimension;
+    int _hessianIndex, _dimension, _colInHessian;
     bool _fixed, _marginalized;
   };
-  typedef std::set<Vertex*> VertexSet;
+  typedef HyperGraph::VertexSet VertexSet;
   typedef std::vector<Vertex*> VertexContainer;
 
-  class Edge {
+  class Edge : public HyperGraph::Edge {
    public:
-    Edge() : _dimension(-1), _level(0), _robustKernel(0), _id(-1) {}
+    Edge() : HyperGraph::Edge(-1), _dimension(-1), _level(0), _robustKernel(0) {}
     virtual ~Edge() {}
-    int id() const { return _id; }
-    virtual void resize(size_t n) { _vertices.resize(n); }
-    void setVertex(size_t i, Vertex* v) { _vertices[i] = v; }
-    Vertex* vertex(size_t i) const { return _vertices[i]; }
     RobustKernel* robustKernel() const { return _robustKernel; }
     void setRobustKernel(RobustKernel* k) { _robustKernel = k; }  // not owned here
     int level() const { return _level; }
@@ -91,11 +91,10 @@ class OptimizableGraph {
     virtual Vertex* createFrom() { return 0; }
     virtual Vertex* createTo() { return 0; }
    protected:
-    std::vector<Vertex*> _vertices;
     int _dimension, _level;
     RobustKernel* _robustKernel;
-    int _id;
   };
+  typedef std::vector<Edge*> EdgeContainer;
 };
 
 }  // namespace g2o

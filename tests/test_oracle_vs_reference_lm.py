@@ -14,15 +14,19 @@ class _Side:
 
     def __init__(self, oracle, driver):
         self.ba_solve = oracle.ba_solve
-        self.ref_ba_solve = oracle.ref_ba_solve if driver == "lm" else oracle.ref_ba_full_solve
+        self.ref_ba_solve = {"lm": oracle.ref_ba_solve, "full": oracle.ref_ba_full_solve, "block": oracle.ref_ba_block_solve}[driver]
+        self.driver = driver
 
 
 # "lm":   g2o's Levenberg-Marquardt driver over the oracle's errors / quadratic form / Schur solve (oracle/ref_lm_wrap.cpp)
 # "full": the same driver over g2o's own vertices, edges, Huber kernel and base-edge templates; only the Schur complement and the
 #         LDL^T under Solver::solve() are the oracle's (oracle/ref_ba_full_wrap.cpp)
-@pytest.fixture(scope="module", params=["lm", "full"])
+# "block": as "full", plus g2o's own BlockSolver_6_3 — block allocation and Hschur pattern, buildSystem, setLambda / restoreDiagonal, the Schur
+#          complement and the landmark back-substitution of solve(); only LinearSolver::solve (the sparse LDL^T) is the oracle's
+#          (oracle/ref_ba_block_wrap.cpp)
+@pytest.fixture(scope="module", params=["lm", "full", "block"])
 def ref(oracle, request):
-    if (oracle.ref_lm() if request.param == "lm" else oracle.ref_ba_full()) is None:
+    if {"lm": oracle.ref_lm, "full": oracle.ref_ba_full, "block": oracle.ref_ba_block}[request.param]() is None:
         pytest.skip("reference tree absent and no prebuilt oracle/_ref library")
     return _Side(oracle, request.param)
 
@@ -31,6 +35,8 @@ def same_run(a, b):
     assert a["iters_done"] == b["iters_done"] and a["trials_total"] == b["trials_total"]
     assert len(a["trace"]) == len(b["trace"])
     for c in (0, 1, 2, 4, 5):       # iteration, lambda of the last trial, robust chi2 kept, trials, lambda handed to the next iteration
+        if c == 1 and np.isnan(b["trace"][:, 1]).all():
+            continue                # with the reference's own BlockSolver the last trial's lambda is not visible from outside
         assert np.array_equal(a["trace"][:, c], b["trace"][:, c]), c
     assert a["chi2_initial"] == b["chi2_initial"] and a["chi2_final"] == b["chi2_final"] and a["lambda_final"] == b["lambda_final"]
     assert np.array_equal(a["poses"], b["poses"]) and np.array_equal(a["points"], b["points"])
