@@ -943,3 +943,23 @@ def ref_pgo_full():
 
 def ref_pgo_solve(p, **kw):
     return pgo_solve(p, fn=ref_pgo_full().ref_pgo_solve, **kw)
+
+
+_REF_PGO_BLOCK = None
+
+
+def ref_pgo_block():
+    global _REF_PGO_BLOCK
+    if _REF_PGO_BLOCK is None:
+        if build_ref() is None:
+            return None
+        so = os.path.join(_HERE, "_ref", "libpgo_block_ref.so")
+        if not os.path.exists(so):
+            return None
+        _REF_PGO_BLOCK = C.CDLL(so)
+    return _REF_PGO_BLOCK
+
+
+def ref_pgo_block_solve(p, **kw):
+    """as ref_pgo_solve, with g2o's own BlockSolver_7_3 between the LM driver and the oracle's sparse LDL^T (oracle/ref_pgo_block_wrap.cpp)"""
+    return pgo_solve(p, fn=ref_pgo_block().ref_pgo_block_solve, **kw)
