@@ -152,15 +152,14 @@ extern "C" int ccm_hamming_matrix(const uint8_t* A, int32_t nA, const uint8_t* B
   });
 }
 
-extern "C" int ccm_match_bow_kf_frame(const uint8_t* desc_kf, int32_t n_kf, const uint8_t* kf_has_mp, const float* angle_kf,
-                                      const ccm_feature_vector* fv_kf, const uint8_t* desc_f, int32_t n_f, const float* angle_f,
-                                      const ccm_feature_vector* fv_f, float nnratio, int32_t check_orientation,
-                                      int32_t* match_kf_of_f, int32_t* nmatches) {
-  return guarded([&] {
-    CCM_REQUIRE(match_kf_of_f && nmatches && kf_has_mp, "ccm_match_bow_kf_frame: null output");
+// ---- the selection halves: everything after the distance matrix, on the host, in the reference's visiting order -------------------
+namespace {
+void select_bow_kf_frame(const uint16_t* D, int32_t n_kf, const uint8_t* kf_has_mp, const float* angle_kf, const ccm_feature_vector* fv_kf,
+                         int32_t n_f, const float* angle_f, const ccm_feature_vector* fv_f, float nnratio, int32_t check_orientation,
+                         int32_t* match_kf_of_f, int32_t* nmatches) {
+    CCM_REQUIRE(match_kf_of_f && nmatches && kf_has_mp && (D || (size_t)n_kf * n_f == 0), "ccm_match_bow_kf_frame: null argument");
     check_fv(fv_kf, n_kf, "ccm_match_bow_kf_frame: bad keyframe FeatureVector");
     check_fv(fv_f, n_f, "ccm_match_bow_kf_frame: bad frame FeatureVector");
-    const uint16_t* D = distance_matrix(desc_kf, n_kf, desc_f, n_f);
     for (int i = 0; i < n_f; i++) match_kf_of_f[i] = -1;
     int found = 0;
     RotHist hist;
@@ -186,18 +185,14 @@ extern "C" int ccm_match_bow_kf_frame(const uint8_t* desc_kf, int32_t n_kf, cons
     });
     if (check_orientation) found -= hist.prune([&](int j) { match_kf_of_f[j] = -1; });
     *nmatches = found;
-  });
 }
 
-extern "C" int ccm_match_bow_kf_kf(const uint8_t* desc1, int32_t n1, const uint8_t* has_mp1, const float* angle1,
-                                   const ccm_feature_vector* fv1, const uint8_t* desc2, int32_t n2, const uint8_t* has_mp2,
-                                   const float* angle2, const ccm_feature_vector* fv2, float nnratio,
-                                   int32_t check_orientation, int32_t* match12, int32_t* nmatches) {
-  return guarded([&] {
-    CCM_REQUIRE(match12 && nmatches && has_mp1 && has_mp2, "ccm_match_bow_kf_kf: null argument");
+void select_bow_kf_kf(const uint16_t* D, int32_t n1, const uint8_t* has_mp1, const float* angle1, const ccm_feature_vector* fv1, int32_t n2,
+                      const uint8_t* has_mp2, const float* angle2, const ccm_feature_vector* fv2, float nnratio, int32_t check_orientation,
+                      int32_t* match12, int32_t* nmatches) {
+    CCM_REQUIRE(match12 && nmatches && has_mp1 && has_mp2 && (D || (size_t)n1 * n2 == 0), "ccm_match_bow_kf_kf: null argument");
     check_fv(fv1, n1, "ccm_match_bow_kf_kf: bad FeatureVector 1");
     check_fv(fv2, n2, "ccm_match_bow_kf_kf: bad FeatureVector 2");
-    const uint16_t* D = distance_matrix(desc1, n1, desc2, n2);
     for (int i = 0; i < n1; i++) match12[i] = -1;
     std::vector<char> taken(n2, 0);
     int found = 0;
@@ -225,18 +220,19 @@ extern "C" int ccm_match_bow_kf_kf(const uint8_t* desc1, int32_t n1, const uint8
     });
     if (check_orientation) found -= hist.prune([&](int i) { match12[i] = -1; });
     *nmatches = found;
-  });
 }
 
-extern "C" int ccm_match_triangulation(const ccm_tri_view* v1, const ccm_tri_view* v2, const float F12[9], float ex, float ey,
-                                       const float* level_sigma2, const float* scale_factors, int32_t nlevels,
-                                       int32_t check_orientation, int32_t* pairs, int32_t* npairs) {
-  return guarded([&] {
+void check_tri(const ccm_tri_view* v1, const ccm_tri_view* v2, const float F12[9], const float* level_sigma2, const float* scale_factors,
+               int32_t nlevels, const int32_t* pairs, const int32_t* npairs) {
     CCM_REQUIRE(v1 && v2 && F12 && level_sigma2 && scale_factors && pairs && npairs, "ccm_match_triangulation: null argument");
     check_fv(v1->fv, v1->n, "ccm_match_triangulation: bad FeatureVector 1");
     check_fv(v2->fv, v2->n, "ccm_match_triangulation: bad FeatureVector 2");
     for (int j = 0; j < v2->n; j++) CCM_REQUIRE(v2->octave[j] >= 0 && v2->octave[j] < nlevels, "ccm_match_triangulation: octave out of range");
-    const uint16_t* D = distance_matrix(v1->desc, v1->n, v2->desc, v2->n);
+}
+
+void select_triangulation(const uint16_t* D, const ccm_tri_view* v1, const ccm_tri_view* v2, const float F12[9], float ex, float ey,
+                          const float* level_sigma2, const float* scale_factors, int32_t check_orientation, int32_t* pairs, int32_t* npairs) {
+    CCM_REQUIRE(D || (size_t)v1->n * v2->n == 0, "ccm_select_triangulation: null distance matrix");
     std::vector<char> taken(v2->n, 0);
     std::vector<int> m12(v1->n, -1);
     int found = 0;
@@ -278,5 +274,61 @@ extern "C" int ccm_match_triangulation(const ccm_tri_view* v1, const ccm_tri_vie
     for (int i = 0; i < v1->n; i++)
       if (m12[i] >= 0) { pairs[2 * np] = i; pairs[2 * np + 1] = m12[i]; np++; }
     *npairs = np;
+}
+}  // namespace
+
+extern "C" int ccm_match_bow_kf_frame(const uint8_t* desc_kf, int32_t n_kf, const uint8_t* kf_has_mp, const float* angle_kf,
+                                      const ccm_feature_vector* fv_kf, const uint8_t* desc_f, int32_t n_f, const float* angle_f,
+                                      const ccm_feature_vector* fv_f, float nnratio, int32_t check_orientation,
+                                      int32_t* match_kf_of_f, int32_t* nmatches) {
+  return guarded([&] {
+    CCM_REQUIRE(n_kf >= 0 && n_f >= 0 && (n_kf == 0 || desc_kf) && (n_f == 0 || desc_f), "ccm_match_bow_kf_frame: bad descriptors");
+    select_bow_kf_frame(distance_matrix(desc_kf, n_kf, desc_f, n_f), n_kf, kf_has_mp, angle_kf, fv_kf, n_f, angle_f, fv_f, nnratio,
+                        check_orientation, match_kf_of_f, nmatches);
+  });
+}
+extern "C" int ccm_select_bow_kf_frame(const uint16_t* D, int32_t n_kf, const uint8_t* kf_has_mp, const float* angle_kf,
+                                       const ccm_feature_vector* fv_kf, int32_t n_f, const float* angle_f, const ccm_feature_vector* fv_f,
+                                       float nnratio, int32_t check_orientation, int32_t* match_kf_of_f, int32_t* nmatches) {
+  return guarded([&] {
+    CCM_REQUIRE(n_kf >= 0 && n_f >= 0, "ccm_select_bow_kf_frame: bad sizes");
+    select_bow_kf_frame(D, n_kf, kf_has_mp, angle_kf, fv_kf, n_f, angle_f, fv_f, nnratio, check_orientation, match_kf_of_f, nmatches);
+  });
+}
+
+extern "C" int ccm_match_bow_kf_kf(const uint8_t* desc1, int32_t n1, const uint8_t* has_mp1, const float* angle1,
+                                   const ccm_feature_vector* fv1, const uint8_t* desc2, int32_t n2, const uint8_t* has_mp2,
+                                   const float* angle2, const ccm_feature_vector* fv2, float nnratio,
+                                   int32_t check_orientation, int32_t* match12, int32_t* nmatches) {
+  return guarded([&] {
+    CCM_REQUIRE(n1 >= 0 && n2 >= 0 && (n1 == 0 || desc1) && (n2 == 0 || desc2), "ccm_match_bow_kf_kf: bad descriptors");
+    select_bow_kf_kf(distance_matrix(desc1, n1, desc2, n2), n1, has_mp1, angle1, fv1, n2, has_mp2, angle2, fv2, nnratio, check_orientation,
+                     match12, nmatches);
+  });
+}
+extern "C" int ccm_select_bow_kf_kf(const uint16_t* D, int32_t n1, const uint8_t* has_mp1, const float* angle1, const ccm_feature_vector* fv1,
+                                    int32_t n2, const uint8_t* has_mp2, const float* angle2, const ccm_feature_vector* fv2, float nnratio,
+                                    int32_t check_orientation, int32_t* match12, int32_t* nmatches) {
+  return guarded([&] {
+    CCM_REQUIRE(n1 >= 0 && n2 >= 0, "ccm_select_bow_kf_kf: bad sizes");
+    select_bow_kf_kf(D, n1, has_mp1, angle1, fv1, n2, has_mp2, angle2, fv2, nnratio, check_orientation, match12, nmatches);
+  });
+}
+
+extern "C" int ccm_match_triangulation(const ccm_tri_view* v1, const ccm_tri_view* v2, const float F12[9], float ex, float ey,
+                                       const float* level_sigma2, const float* scale_factors, int32_t nlevels,
+                                       int32_t check_orientation, int32_t* pairs, int32_t* npairs) {
+  return guarded([&] {
+    check_tri(v1, v2, F12, level_sigma2, scale_factors, nlevels, pairs, npairs);
+    select_triangulation(distance_matrix(v1->desc, v1->n, v2->desc, v2->n), v1, v2, F12, ex, ey, level_sigma2, scale_factors,
+                         check_orientation, pairs, npairs);
+  });
+}
+extern "C" int ccm_select_triangulation(const uint16_t* D, const ccm_tri_view* v1, const ccm_tri_view* v2, const float F12[9], float ex, float ey,
+                                        const float* level_sigma2, const float* scale_factors, int32_t nlevels,
+                                        int32_t check_orientation, int32_t* pairs, int32_t* npairs) {
+  return guarded([&] {
+    check_tri(v1, v2, F12, level_sigma2, scale_factors, nlevels, pairs, npairs);
+    select_triangulation(D, v1, v2, F12, ex, ey, level_sigma2, scale_factors, check_orientation, pairs, npairs);
   });
 }

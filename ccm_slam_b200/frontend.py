@@ -81,26 +81,37 @@ class ORBmatcher:
     def DescriptorDistance(a, b):
         return int(api.hamming_matrix(np.asarray(a).reshape(1, 32), np.asarray(b).reshape(1, 32))[0, 0])
 
-    def SearchByBoW_KF_Frame(self, desc_kf, kf_has_mp, angle_kf, fv_kf, desc_f, angle_f, fv_f):
+    def SearchByBoW_KF_Frame(self, desc_kf, kf_has_mp, angle_kf, fv_kf, desc_f, angle_f, fv_f, D=None):
+        """D: optional precomputed distance matrix (n_kf x n_f u16) -> host selection only (ccm_select_bow_kf_frame)"""
         desc_kf = np.ascontiguousarray(desc_kf, np.uint8); desc_f = np.ascontiguousarray(desc_f, np.uint8)
         has = np.ascontiguousarray(kf_has_mp, np.uint8); ak = np.ascontiguousarray(angle_kf, np.float32); af = np.ascontiguousarray(angle_f, np.float32)
         out = np.empty(desc_f.shape[0], np.int32); n = C.c_int32()
         fk, ff = fv_kf.c(), fv_f.c()
+        if D is not None:
+            D = np.ascontiguousarray(D, np.uint16)
+            _chk(lib().ccm_select_bow_kf_frame(_p(D), desc_kf.shape[0], _p(has), _p(ak), C.byref(fk), desc_f.shape[0], _p(af), C.byref(ff),
+                                               C.c_float(self.nnratio), int(self.checkOri), _p(out), C.byref(n)))
+            return out, n.value
         _chk(lib().ccm_match_bow_kf_frame(_p(desc_kf), desc_kf.shape[0], _p(has), _p(ak), C.byref(fk), _p(desc_f), desc_f.shape[0], _p(af),
                                           C.byref(ff), C.c_float(self.nnratio), int(self.checkOri), _p(out), C.byref(n)))
         return out, n.value
 
-    def SearchByBoW_KF_KF(self, d1, has1, a1, fv1, d2, has2, a2, fv2):
+    def SearchByBoW_KF_KF(self, d1, has1, a1, fv1, d2, has2, a2, fv2, D=None):
         d1 = np.ascontiguousarray(d1, np.uint8); d2 = np.ascontiguousarray(d2, np.uint8)
         has1 = np.ascontiguousarray(has1, np.uint8); has2 = np.ascontiguousarray(has2, np.uint8)
         a1 = np.ascontiguousarray(a1, np.float32); a2 = np.ascontiguousarray(a2, np.float32)
         out = np.empty(d1.shape[0], np.int32); n = C.c_int32()
         f1, f2 = fv1.c(), fv2.c()
+        if D is not None:
+            D = np.ascontiguousarray(D, np.uint16)
+            _chk(lib().ccm_select_bow_kf_kf(_p(D), d1.shape[0], _p(has1), _p(a1), C.byref(f1), d2.shape[0], _p(has2), _p(a2), C.byref(f2),
+                                            C.c_float(self.nnratio), int(self.checkOri), _p(out), C.byref(n)))
+            return out, n.value
         _chk(lib().ccm_match_bow_kf_kf(_p(d1), d1.shape[0], _p(has1), _p(a1), C.byref(f1), _p(d2), d2.shape[0], _p(has2), _p(a2), C.byref(f2),
                                        C.c_float(self.nnratio), int(self.checkOri), _p(out), C.byref(n)))
         return out, n.value
 
-    def SearchForTriangulation(self, v1, v2, F12, ex, ey, level_sigma2, scale_factors):
+    def SearchForTriangulation(self, v1, v2, F12, ex, ey, level_sigma2, scale_factors, D=None):
         keep = []
 
         def view(v):
@@ -114,6 +125,11 @@ class ORBmatcher:
         a, b = view(v1), view(v2)
         F = np.ascontiguousarray(F12, np.float32); ls = np.ascontiguousarray(level_sigma2, np.float32); sf = np.ascontiguousarray(scale_factors, np.float32)
         pairs = np.empty((min(a.n, b.n) + 1, 2), np.int32); n = C.c_int32()
+        if D is not None:
+            D = np.ascontiguousarray(D, np.uint16)
+            _chk(lib().ccm_select_triangulation(_p(D), C.byref(a), C.byref(b), _p(F), C.c_float(ex), C.c_float(ey), _p(ls), _p(sf), len(ls),
+                                                int(self.checkOri), _p(pairs), C.byref(n)))
+            return pairs[:n.value].copy()
         _chk(lib().ccm_match_triangulation(C.byref(a), C.byref(b), _p(F), C.c_float(ex), C.c_float(ey), _p(ls), _p(sf), len(ls),
                                            int(self.checkOri), _p(pairs), C.byref(n)))
         return pairs[:n.value].copy()

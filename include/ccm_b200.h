@@ -305,12 +305,19 @@ int ccm_match_bow_kf_frame(const uint8_t* desc_kf, int32_t n_kf, const uint8_t* 
                            const uint8_t* desc_f, int32_t n_f, const float* angle_f, const ccm_feature_vector* fv_f,
                            float nnratio, int32_t check_orientation, int32_t* match_kf_of_f /*n_f, -1 = none*/,
                            int32_t* nmatches);
+/* the host half alone: D = n_kf x n_f Hamming distances (ccm_hamming_matrix) -> the same selection (no device work) */
+int ccm_select_bow_kf_frame(const uint16_t* D, int32_t n_kf, const uint8_t* kf_has_mp, const float* angle_kf,
+                            const ccm_feature_vector* fv_kf, int32_t n_f, const float* angle_f, const ccm_feature_vector* fv_f,
+                            float nnratio, int32_t check_orientation, int32_t* match_kf_of_f, int32_t* nmatches);
 /* SearchByBoW(kfptr, kfptr, vpMatches12)  (cslam/src/ORBmatcher.cpp:565-698) */
 int ccm_match_bow_kf_kf(const uint8_t* desc1, int32_t n1, const uint8_t* has_mp1, const float* angle1,
                         const ccm_feature_vector* fv1,
                         const uint8_t* desc2, int32_t n2, const uint8_t* has_mp2, const float* angle2,
                         const ccm_feature_vector* fv2,
                         float nnratio, int32_t check_orientation, int32_t* match12 /*n1, -1 = none*/, int32_t* nmatches);
+int ccm_select_bow_kf_kf(const uint16_t* D /*n1 x n2*/, int32_t n1, const uint8_t* has_mp1, const float* angle1, const ccm_feature_vector* fv1,
+                         int32_t n2, const uint8_t* has_mp2, const float* angle2, const ccm_feature_vector* fv2,
+                         float nnratio, int32_t check_orientation, int32_t* match12, int32_t* nmatches);
 
 typedef struct ccm_tri_view {  /* the per-keyframe read set of SearchForTriangulation */
   const uint8_t* desc; int32_t n;
@@ -327,6 +334,9 @@ typedef struct ccm_tri_view {  /* the per-keyframe read set of SearchForTriangul
 int ccm_match_triangulation(const ccm_tri_view* v1, const ccm_tri_view* v2, const float F12[9], float ex, float ey,
                             const float* level_sigma2, const float* scale_factors, int32_t nlevels,
                             int32_t check_orientation, int32_t* pairs /*2*min(n1,n2)*/, int32_t* npairs);
+int ccm_select_triangulation(const uint16_t* D /*v1->n x v2->n*/, const ccm_tri_view* v1, const ccm_tri_view* v2, const float F12[9], float ex,
+                             float ey, const float* level_sigma2, const float* scale_factors, int32_t nlevels,
+                             int32_t check_orientation, int32_t* pairs, int32_t* npairs);
 
 /* ---- projection-guided matching -------------------------------------------------
  * The seven matchers that look a projected map point up in the image grid share one shape:

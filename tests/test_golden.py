@@ -140,6 +140,34 @@ def test_oracle_reproduces_match_fixture(oracle):
         assert np.array_equal(m, g["tri_ori%d" % ori])
 
 
+def test_host_selection_halves_reproduce_match_fixture(oracle):
+    """the product's host halves of SearchByBoW x2 / SearchForTriangulation (ccm_select_*: everything after the distance matrix) on the
+    CPU, fed a numpy Hamming matrix, against the fixture and the oracle — incl. a tie-storm variant where the visiting order decides"""
+    from ccm_slam_b200.frontend import FeatureVector, ORBmatcher
+    from ccm_slam_b200 import synth_match as sm
+    g = dict(load("match_shifted_pair.npz"))
+    for storm in (False, True):
+        if storm:
+            rng = np.random.default_rng(5)
+            pats = np.concatenate([sm.flip_bits(rng.integers(0, 256, (1, 32), dtype=np.uint8), [int(rng.integers(8, 31))], rng) for _ in range(6)])
+            g["d1"] = pats[rng.integers(0, 6, len(g["d1"]))]; g["d2"] = pats[rng.integers(0, 6, len(g["d2"]))]
+        fv1, fv2, v1, v2 = match_inputs(g, FeatureVector)
+        ofv1, ofv2, ov1, ov2 = match_inputs(g, oracle.FeatureVector)
+        D = np.unpackbits(g["d1"][:, None, :] ^ g["d2"][None, :, :], axis=2).sum(axis=2).astype(np.uint16)
+        for tag, nn, ori in (("a", 0.7, True), ("b", 0.9, False)):
+            m = ORBmatcher(nn, ori)
+            got, n = m.SearchByBoW_KF_Frame(g["d1"], g["has1"], g["angle1"], fv1, g["d2"], g["angle2"], fv2, D=D)
+            ref, rn = oracle.match_bow_kf_frame(g["d1"], g["has1"], g["angle1"], ofv1, g["d2"], g["angle2"], ofv2, nn, ori)
+            assert n == rn and np.array_equal(got, ref) and (storm or np.array_equal(got, g["kf_frame_" + tag]))
+            got, n = m.SearchByBoW_KF_KF(g["d1"], g["has1"], g["angle1"], fv1, g["d2"], g["has2"], g["angle2"], fv2, D=D)
+            ref, rn = oracle.match_bow_kf_kf(g["d1"], g["has1"], g["angle1"], ofv1, g["d2"], g["has2"], g["angle2"], ofv2, nn, ori)
+            assert n == rn and np.array_equal(got, ref) and (storm or np.array_equal(got, g["kf_kf_" + tag]))
+        for ori in (False, True):
+            got = ORBmatcher(0.6, ori).SearchForTriangulation(v1, v2, g["F12"], float(g["ex"]), float(g["ey"]), g["level_sigma2"], g["scale_factors"], D=D)
+            ref = oracle.match_triangulation(ov1, ov2, g["F12"], float(g["ex"]), float(g["ey"]), g["level_sigma2"], g["scale_factors"], ori)
+            assert np.array_equal(got, ref) and (storm or np.array_equal(got, g["tri_ori%d" % ori]))
+
+
 # ----------------------------------------------------------------------------------------------- GPU: C ABI vs fixtures
 @pytest.fixture()
 def gpu():

@@ -7,14 +7,15 @@ tests/test_oracle_vs_reference_matchers.py is then pushed through BOTH implement
 the results must be identical: match arrays, counts, the RemapMapPointMatch call list, the refreshed vbPrevMatched, what Fuse adds and
 replaces.  That exercises the shims' own code: pose algebra, projection, image / distance / viewing-angle gates, PredictScale, window
 radii, the write-back epilogues.  Without a GPU the device half of the six ccm_search_* entry points is a link-time double (CPU Hamming
-matrix + the library's own ccm_select_*, oracle/ccm_search_double.cpp); SearchByBoW x2 and SearchForTriangulation have no host half and
-are left to the GPU suite.  Skipped where the reference tree or the product library is absent."""
+matrix + the library's own ccm_select_*, oracle/ccm_search_double.cpp), so all eleven search methods and DescriptorDistance run here.  Skipped where the reference tree or the product library is absent."""
+import ctypes as C
+
 import numpy as np
 import pytest
 
 from tests import test_oracle_vs_reference_matchers as T
 
-DEVICE_ONLY = {"ref_match_bow_kf_frame", "ref_match_bow_kf_kf", "ref_match_triangulation"}
+DEVICE_ONLY = set()     # every method of the class has a host half behind the double since ccm_select_bow_* / ccm_select_triangulation
 
 
 def same(a, b):
@@ -37,7 +38,7 @@ class SideBySide:
 
     def __getattr__(self, name):
         f = getattr(self._o, name)
-        if not name.startswith("ref_") or name in DEVICE_ONLY or not callable(f):
+        if not name.startswith("ref_") or name in DEVICE_ONLY or name == "ref_match" or not callable(f):
             return f
 
         def both(*a, **k):
@@ -103,6 +104,25 @@ def test_search_by_projection_last_frame(side, seed, th, ori):
 @pytest.mark.parametrize("seed,th,orb_dist,ori", [(32, 10.0, 100, True), (33, 3.0, 64, False)])
 def test_search_by_projection_relocalisation(side, seed, th, orb_dist, ori):
     ran(side, T.test_search_by_projection_relocalisation, seed, th, orb_dist, ori)
+
+
+@pytest.mark.parametrize("seed,nnratio,ori", [(0, 0.7, True), (1, 0.9, False), (2, 0.6, True)])
+def test_search_by_bow(side, seed, nnratio, ori):
+    ran(side, T.test_search_by_bow, seed, nnratio, ori)
+
+
+@pytest.mark.parametrize("seed,ori", [(3, False), (4, True)])
+def test_search_for_triangulation(side, seed, ori):
+    ran(side, T.test_search_for_triangulation, seed, ori)
+
+
+def test_descriptor_distance(side):
+    rng = np.random.default_rng(0)
+    with side._o.matcher_side("shim"):
+        L = side._o.ref_match()
+        for _ in range(50):
+            a, b = rng.integers(0, 256, 32, dtype=np.uint8), rng.integers(0, 256, 32, dtype=np.uint8)
+            assert L.ref_descriptor_distance(a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p)) == int(np.unpackbits(a ^ b).sum())
 
 
 def test_tie_storm_scenes(side):
