@@ -155,125 +155,125 @@ extern "C" int ccm_hamming_matrix(const uint8_t* A, int32_t nA, const uint8_t* B
 // ---- the selection halves: everything after the distance matrix, on the host, in the reference's visiting order -------------------
 namespace {
 void select_bow_kf_frame(const uint16_t* D, int32_t n_kf, const uint8_t* kf_has_mp, const float* angle_kf, const ccm_feature_vector* fv_kf,
-                         int32_t n_f, const float* angle_f, const ccm_feature_vector* fv_f, float nnratio, int32_t check_orientation,
-                         int32_t* match_kf_of_f, int32_t* nmatches) {
-    CCM_REQUIRE(match_kf_of_f && nmatches && kf_has_mp && (D || (size_t)n_kf * n_f == 0), "ccm_match_bow_kf_frame: null argument");
-    check_fv(fv_kf, n_kf, "ccm_match_bow_kf_frame: bad keyframe FeatureVector");
-    check_fv(fv_f, n_f, "ccm_match_bow_kf_frame: bad frame FeatureVector");
-    for (int i = 0; i < n_f; i++) match_kf_of_f[i] = -1;
-    int found = 0;
-    RotHist hist;
-    for_shared_nodes(fv_kf, fv_f, [&](int a, int b) {
-      for (int ik = fv_kf->node_ptr[a]; ik < fv_kf->node_ptr[a + 1]; ik++) {
-        const int i = (int)fv_kf->feat[ik];
-        if (!kf_has_mp[i]) continue;
-        const uint16_t* row = D + (size_t)i * n_f;
-        int best = 256, second = 256, bestJ = -1;
-        for (int jf = fv_f->node_ptr[b]; jf < fv_f->node_ptr[b + 1]; jf++) {
-          const int j = (int)fv_f->feat[jf];
-          if (match_kf_of_f[j] >= 0) continue;  // already holds a MapPoint
-          const int d = row[j];
-          if (d < best) { second = best; best = d; bestJ = j; }
-          else if (d < second) second = d;
-        }
-        if (best <= TH_LOW && static_cast<float>(best) < nnratio * static_cast<float>(second)) {
-          match_kf_of_f[bestJ] = i;
-          if (check_orientation) hist.add(angle_kf[i], angle_f[bestJ], bestJ);
-          found++;
-        }
+                       int32_t n_f, const float* angle_f, const ccm_feature_vector* fv_f, float nnratio, int32_t check_orientation,
+                       int32_t* match_kf_of_f, int32_t* nmatches) {
+  CCM_REQUIRE(match_kf_of_f && nmatches && kf_has_mp && (D || (size_t)n_kf * n_f == 0), "ccm_match_bow_kf_frame: null argument");
+  check_fv(fv_kf, n_kf, "ccm_match_bow_kf_frame: bad keyframe FeatureVector");
+  check_fv(fv_f, n_f, "ccm_match_bow_kf_frame: bad frame FeatureVector");
+  for (int i = 0; i < n_f; i++) match_kf_of_f[i] = -1;
+  int found = 0;
+  RotHist hist;
+  for_shared_nodes(fv_kf, fv_f, [&](int a, int b) {
+    for (int ik = fv_kf->node_ptr[a]; ik < fv_kf->node_ptr[a + 1]; ik++) {
+      const int i = (int)fv_kf->feat[ik];
+      if (!kf_has_mp[i]) continue;
+      const uint16_t* row = D + (size_t)i * n_f;
+      int best = 256, second = 256, bestJ = -1;
+      for (int jf = fv_f->node_ptr[b]; jf < fv_f->node_ptr[b + 1]; jf++) {
+        const int j = (int)fv_f->feat[jf];
+        if (match_kf_of_f[j] >= 0) continue;  // already holds a MapPoint
+        const int d = row[j];
+        if (d < best) { second = best; best = d; bestJ = j; }
+        else if (d < second) second = d;
       }
-    });
-    if (check_orientation) found -= hist.prune([&](int j) { match_kf_of_f[j] = -1; });
-    *nmatches = found;
+      if (best <= TH_LOW && static_cast<float>(best) < nnratio * static_cast<float>(second)) {
+        match_kf_of_f[bestJ] = i;
+        if (check_orientation) hist.add(angle_kf[i], angle_f[bestJ], bestJ);
+        found++;
+      }
+    }
+  });
+  if (check_orientation) found -= hist.prune([&](int j) { match_kf_of_f[j] = -1; });
+  *nmatches = found;
 }
 
 void select_bow_kf_kf(const uint16_t* D, int32_t n1, const uint8_t* has_mp1, const float* angle1, const ccm_feature_vector* fv1, int32_t n2,
-                      const uint8_t* has_mp2, const float* angle2, const ccm_feature_vector* fv2, float nnratio, int32_t check_orientation,
-                      int32_t* match12, int32_t* nmatches) {
-    CCM_REQUIRE(match12 && nmatches && has_mp1 && has_mp2 && (D || (size_t)n1 * n2 == 0), "ccm_match_bow_kf_kf: null argument");
-    check_fv(fv1, n1, "ccm_match_bow_kf_kf: bad FeatureVector 1");
-    check_fv(fv2, n2, "ccm_match_bow_kf_kf: bad FeatureVector 2");
-    for (int i = 0; i < n1; i++) match12[i] = -1;
-    std::vector<char> taken(n2, 0);
-    int found = 0;
-    RotHist hist;
-    for_shared_nodes(fv1, fv2, [&](int a, int b) {
-      for (int k1 = fv1->node_ptr[a]; k1 < fv1->node_ptr[a + 1]; k1++) {
-        const int i = (int)fv1->feat[k1];
-        if (!has_mp1[i]) continue;
-        const uint16_t* row = D + (size_t)i * n2;
-        int best = 256, second = 256, bestJ = -1;
-        for (int k2 = fv2->node_ptr[b]; k2 < fv2->node_ptr[b + 1]; k2++) {
-          const int j = (int)fv2->feat[k2];
-          if (taken[j] || !has_mp2[j]) continue;
-          const int d = row[j];
-          if (d < best) { second = best; best = d; bestJ = j; }
-          else if (d < second) second = d;
-        }
-        if (best < TH_LOW && static_cast<float>(best) < nnratio * static_cast<float>(second)) {  // strict '<' in this overload
-          match12[i] = bestJ;
-          taken[bestJ] = 1;
-          if (check_orientation) hist.add(angle1[i], angle2[bestJ], i);
-          found++;
-        }
+                    const uint8_t* has_mp2, const float* angle2, const ccm_feature_vector* fv2, float nnratio, int32_t check_orientation,
+                    int32_t* match12, int32_t* nmatches) {
+  CCM_REQUIRE(match12 && nmatches && has_mp1 && has_mp2 && (D || (size_t)n1 * n2 == 0), "ccm_match_bow_kf_kf: null argument");
+  check_fv(fv1, n1, "ccm_match_bow_kf_kf: bad FeatureVector 1");
+  check_fv(fv2, n2, "ccm_match_bow_kf_kf: bad FeatureVector 2");
+  for (int i = 0; i < n1; i++) match12[i] = -1;
+  std::vector<char> taken(n2, 0);
+  int found = 0;
+  RotHist hist;
+  for_shared_nodes(fv1, fv2, [&](int a, int b) {
+    for (int k1 = fv1->node_ptr[a]; k1 < fv1->node_ptr[a + 1]; k1++) {
+      const int i = (int)fv1->feat[k1];
+      if (!has_mp1[i]) continue;
+      const uint16_t* row = D + (size_t)i * n2;
+      int best = 256, second = 256, bestJ = -1;
+      for (int k2 = fv2->node_ptr[b]; k2 < fv2->node_ptr[b + 1]; k2++) {
+        const int j = (int)fv2->feat[k2];
+        if (taken[j] || !has_mp2[j]) continue;
+        const int d = row[j];
+        if (d < best) { second = best; best = d; bestJ = j; }
+        else if (d < second) second = d;
       }
-    });
-    if (check_orientation) found -= hist.prune([&](int i) { match12[i] = -1; });
-    *nmatches = found;
+      if (best < TH_LOW && static_cast<float>(best) < nnratio * static_cast<float>(second)) {  // strict '<' in this overload
+        match12[i] = bestJ;
+        taken[bestJ] = 1;
+        if (check_orientation) hist.add(angle1[i], angle2[bestJ], i);
+        found++;
+      }
+    }
+  });
+  if (check_orientation) found -= hist.prune([&](int i) { match12[i] = -1; });
+  *nmatches = found;
 }
 
 void check_tri(const ccm_tri_view* v1, const ccm_tri_view* v2, const float F12[9], const float* level_sigma2, const float* scale_factors,
-               int32_t nlevels, const int32_t* pairs, const int32_t* npairs) {
-    CCM_REQUIRE(v1 && v2 && F12 && level_sigma2 && scale_factors && pairs && npairs, "ccm_match_triangulation: null argument");
-    check_fv(v1->fv, v1->n, "ccm_match_triangulation: bad FeatureVector 1");
-    check_fv(v2->fv, v2->n, "ccm_match_triangulation: bad FeatureVector 2");
-    for (int j = 0; j < v2->n; j++) CCM_REQUIRE(v2->octave[j] >= 0 && v2->octave[j] < nlevels, "ccm_match_triangulation: octave out of range");
+             int32_t nlevels, const int32_t* pairs, const int32_t* npairs) {
+  CCM_REQUIRE(v1 && v2 && F12 && level_sigma2 && scale_factors && pairs && npairs, "ccm_match_triangulation: null argument");
+  check_fv(v1->fv, v1->n, "ccm_match_triangulation: bad FeatureVector 1");
+  check_fv(v2->fv, v2->n, "ccm_match_triangulation: bad FeatureVector 2");
+  for (int j = 0; j < v2->n; j++) CCM_REQUIRE(v2->octave[j] >= 0 && v2->octave[j] < nlevels, "ccm_match_triangulation: octave out of range");
 }
 
 void select_triangulation(const uint16_t* D, const ccm_tri_view* v1, const ccm_tri_view* v2, const float F12[9], float ex, float ey,
-                          const float* level_sigma2, const float* scale_factors, int32_t check_orientation, int32_t* pairs, int32_t* npairs) {
-    CCM_REQUIRE(D || (size_t)v1->n * v2->n == 0, "ccm_select_triangulation: null distance matrix");
-    std::vector<char> taken(v2->n, 0);
-    std::vector<int> m12(v1->n, -1);
-    int found = 0;
-    RotHist hist;
-    for_shared_nodes(v1->fv, v2->fv, [&](int a, int b) {
-      for (int k1 = v1->fv->node_ptr[a]; k1 < v1->fv->node_ptr[a + 1]; k1++) {
-        const int i = (int)v1->fv->feat[k1];
-        if (v1->has_mp[i]) continue;  // only untracked keypoints are triangulated
-        const float x1 = v1->kp_xy[2 * i], y1 = v1->kp_xy[2 * i + 1];
-        // epipolar line of kp1 in image 2: l = x1' F12 (CheckDistEpipolarLine, S/ORBmatcher.cpp:159-176), f32 arithmetic
-        const float la = x1 * F12[0] + y1 * F12[3] + F12[6];
-        const float lb = x1 * F12[1] + y1 * F12[4] + F12[7];
-        const float lc = x1 * F12[2] + y1 * F12[5] + F12[8];
-        const float den = la * la + lb * lb;
-        const uint16_t* row = D + (size_t)i * v2->n;
-        int bestDist = TH_LOW, bestJ = -1;
-        for (int k2 = v2->fv->node_ptr[b]; k2 < v2->fv->node_ptr[b + 1]; k2++) {
-          const int j = (int)v2->fv->feat[k2];
-          if (taken[j] || v2->has_mp[j]) continue;  // vbMatched2 is never set in the reference; kept for fidelity
-          const int d = row[j];
-          if (d > TH_LOW || d > bestDist) continue;   // ties replace the incumbent
-          const float x2 = v2->kp_xy[2 * j], y2 = v2->kp_xy[2 * j + 1];
-          const float dex = ex - x2, dey = ey - y2;
-          if (dex * dex + dey * dey < 100 * scale_factors[v2->octave[j]]) continue;  // too close to the epipole
-          const float num = la * x2 + lb * y2 + lc;
-          if (den == 0) continue;
-          const float dsqr = num * num / den;
-          if (dsqr < 3.84 * level_sigma2[v2->octave[j]]) { bestJ = j; bestDist = d; }
-        }
-        if (bestJ >= 0) {
-          m12[i] = bestJ;
-          found++;
-          if (check_orientation) hist.add(v1->angle[i], v2->angle[bestJ], i);
-        }
+                        const float* level_sigma2, const float* scale_factors, int32_t check_orientation, int32_t* pairs, int32_t* npairs) {
+  CCM_REQUIRE(D || (size_t)v1->n * v2->n == 0, "ccm_select_triangulation: null distance matrix");
+  std::vector<char> taken(v2->n, 0);
+  std::vector<int> m12(v1->n, -1);
+  int found = 0;
+  RotHist hist;
+  for_shared_nodes(v1->fv, v2->fv, [&](int a, int b) {
+    for (int k1 = v1->fv->node_ptr[a]; k1 < v1->fv->node_ptr[a + 1]; k1++) {
+      const int i = (int)v1->fv->feat[k1];
+      if (v1->has_mp[i]) continue;  // only untracked keypoints are triangulated
+      const float x1 = v1->kp_xy[2 * i], y1 = v1->kp_xy[2 * i + 1];
+      // epipolar line of kp1 in image 2: l = x1' F12 (CheckDistEpipolarLine, S/ORBmatcher.cpp:159-176), f32 arithmetic
+      const float la = x1 * F12[0] + y1 * F12[3] + F12[6];
+      const float lb = x1 * F12[1] + y1 * F12[4] + F12[7];
+      const float lc = x1 * F12[2] + y1 * F12[5] + F12[8];
+      const float den = la * la + lb * lb;
+      const uint16_t* row = D + (size_t)i * v2->n;
+      int bestDist = TH_LOW, bestJ = -1;
+      for (int k2 = v2->fv->node_ptr[b]; k2 < v2->fv->node_ptr[b + 1]; k2++) {
+        const int j = (int)v2->fv->feat[k2];
+        if (taken[j] || v2->has_mp[j]) continue;  // vbMatched2 is never set in the reference; kept for fidelity
+        const int d = row[j];
+        if (d > TH_LOW || d > bestDist) continue;   // ties replace the incumbent
+        const float x2 = v2->kp_xy[2 * j], y2 = v2->kp_xy[2 * j + 1];
+        const float dex = ex - x2, dey = ey - y2;
+        if (dex * dex + dey * dey < 100 * scale_factors[v2->octave[j]]) continue;  // too close to the epipole
+        const float num = la * x2 + lb * y2 + lc;
+        if (den == 0) continue;
+        const float dsqr = num * num / den;
+        if (dsqr < 3.84 * level_sigma2[v2->octave[j]]) { bestJ = j; bestDist = d; }
       }
-    });
-    if (check_orientation) found -= hist.prune([&](int i) { m12[i] = -1; });
-    int np = 0;
-    for (int i = 0; i < v1->n; i++)
-      if (m12[i] >= 0) { pairs[2 * np] = i; pairs[2 * np + 1] = m12[i]; np++; }
-    *npairs = np;
+      if (bestJ >= 0) {
+        m12[i] = bestJ;
+        found++;
+        if (check_orientation) hist.add(v1->angle[i], v2->angle[bestJ], i);
+      }
+    }
+  });
+  if (check_orientation) found -= hist.prune([&](int i) { m12[i] = -1; });
+  int np = 0;
+  for (int i = 0; i < v1->n; i++)
+    if (m12[i] >= 0) { pairs[2 * np] = i; pairs[2 * np + 1] = m12[i]; np++; }
+  *npairs = np;
 }
 }  // namespace
 
