@@ -558,3 +558,21 @@ extern "C" void orc_pose_to_Tcw_f32(const double qt[7], float T[16]) {
   T[12] = T[13] = T[14] = 0.f; T[15] = 1.f;
 }
 extern "C" void orc_huber(double e, double delta, double rho[3]) { huber(e, delta, rho); }
+
+// sparse LDL^T as a service, for the LinearSolverEigen stand-in (oracle/ref_stub_g2o): the factorisation orc_ba_solve / orc_pgo_solve use
+namespace { struct LdltHandle { BlockSym S; SparseLDLT ldlt; bool analyzed = false; }; }
+extern "C" void* orc_ldlt_new(void) { return new LdltHandle; }
+extern "C" void orc_ldlt_free(void* h) { delete static_cast<LdltHandle*>(h); }
+extern "C" void orc_ldlt_reset(void* h) { static_cast<LdltHandle*>(h)->analyzed = false; }
+extern "C" int orc_ldlt_solve(void* hv, int nb, int bs, const int* rowptr, const int* col, const double* val, const double* b, double* x) {
+  LdltHandle* h = static_cast<LdltHandle*>(hv);
+  h->S.nb = nb; h->S.bs = bs;
+  h->S.rowptr.assign(rowptr, rowptr + nb + 1);
+  h->S.col.assign(col, col + rowptr[nb]);
+  h->S.val.assign(val, val + (size_t)rowptr[nb] * bs * bs);
+  if (!h->analyzed) { h->ldlt.analyze(h->S); h->analyzed = true; }
+  if (!h->ldlt.factorize(h->S)) return 1;
+  h->ldlt.solve(b, x);
+  return 0;
+}
+

@@ -20,7 +20,8 @@
  * orb_oracle.cpp, match_oracle.cpp, proj_oracle.cpp and bow_oracle.cpp are held to that code exactly
  * (tests/test_oracle_vs_reference_{orb,matchers,dbow2,lm,g2o,single,pgo}.py); composed, the last two run every optimisation of the path
  * as reference code except the linear solve (ref_{ba,single,pgo}_full_wrap.cpp; for BA also g2o's own BlockSolver_6_3, ref_ba_block_wrap.cpp:
- * only the sparse factorisation is then the oracle's), and the oracle equals those runs bit for bit.
+ * only the sparse factorisation is then the oracle's), and the oracle equals those runs bit for bit.  cslam/src/Optimizer.cpp itself builds
+ * too (with the whole g2o core; liboptimizer_ref.so) and is what shim/Optimizer_shim.cpp is compared with (tests/test_shim_optimizer.py).
  *
  * Citations: G/ = cslam/thirdparty/g2o/g2o/, S/ = cslam/src/ under /root/reference.
  */
@@ -153,6 +154,13 @@ int orc_sim3_optimize(const orc_sim3_opt_problem* p, double* S12_out /*8*/, uint
 /* pieces: the quadratic form all edges build at a given estimate — H (DxD row-major), b (D), err (2 per edge; Sim3: edge 2i / 2i+1) */
 void orc_pose_opt_build(const orc_pose_opt_problem* p, const double* Tcw, int robust, double delta, double* H, double* b, double* err);
 void orc_sim3_opt_build(const orc_sim3_opt_problem* p, const double* S12, int robust, double delta, double* H, double* b, double* err);
+
+/* the two factorisations as services, for the stand-ins of g2o's Eigen-based linear solvers (oracle/ref_stub_g2o) */
+int orc_chol_solve(int n, const double* A /*n x n row-major*/, const double* b, double* x);
+void* orc_ldlt_new(void);
+void orc_ldlt_free(void* h);
+void orc_ldlt_reset(void* h);
+int orc_ldlt_solve(void* h, int nb, int bs, const int* rowptr, const int* col, const double* val, const double* b, double* x);
 
 #ifdef __cplusplus
 }

@@ -329,3 +329,21 @@ extern "C" void orc_sim3_opt_build(const orc_sim3_opt_problem* p, const double* 
   s.build(H, b);
   if (err) std::memcpy(err, s.err.data(), sizeof(double) * s.err.size());
 }
+
+// dense SPD solve for the LinearSolverDense stand-in (oracle/ref_stub_g2o): the same Cholesky the single-vertex optimisations above use
+extern "C" int orc_chol_solve(int n, const double* A, const double* b, double* x) {
+  if (n == 6) return chol_solve<6>(A, b, x) ? 0 : 1;
+  if (n == 7) return chol_solve<7>(A, b, x) ? 0 : 1;
+  std::vector<double> L((size_t)n * n, 0.0), y(n);          // any other size: the same recurrence, runtime-sized
+  for (int i = 0; i < n; i++)
+    for (int j = 0; j <= i; j++) {
+      double s = A[(size_t)i * n + j];
+      for (int k = 0; k < j; k++) s -= L[(size_t)i * n + k] * L[(size_t)j * n + k];
+      if (i == j) { if (!(s > 0.0) || !std::isfinite(s)) return 1; L[(size_t)i * n + i] = std::sqrt(s); }
+      else L[(size_t)i * n + j] = s / L[(size_t)j * n + j];
+    }
+  for (int i = 0; i < n; i++) { double s = b[i]; for (int k = 0; k < i; k++) s -= L[(size_t)i * n + k] * y[k]; y[i] = s / L[(size_t)i * n + i]; }
+  for (int i = n - 1; i >= 0; i--) { double s = y[i]; for (int k = i + 1; k < n; k++) s -= L[(size_t)k * n + i] * x[k]; x[i] = s / L[(size_t)i * n + i]; }
+  return 0;
+}
+

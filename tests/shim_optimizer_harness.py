@@ -35,11 +35,21 @@ def lib():
     global _LIB
     if _LIB is None:
         from oracle import pyoracle
-        so = _SO_GPU if _GPU else _SO
+        so = _SO_REF if _REF else (_SO_GPU if _GPU else _SO)
         if pyoracle.build_ref() is None or not os.path.exists(so):
             return None
         _LIB = C.CDLL(so)
     return _LIB
+
+
+_SO_REF = os.path.join(_HERE, "..", "oracle", "_ref", "liboptimizer_ref.so")   # the reference's OWN Optimizer.cpp behind the same wrapper
+_REF = False
+
+
+def use_reference(on):
+    """switch the harness to the library built from the reference's own cslam/src/Optimizer.cpp + g2o core (oracle-backed linear solvers)"""
+    global _LIB, _REF
+    _LIB, _REF = None, bool(on)
 
 
 def use_device(on):

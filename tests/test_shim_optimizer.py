@@ -386,3 +386,136 @@ def test_optimize_sim3(ho, n, seed, fix, frac):
     assert np.array_equal(S, wS if wn > 0 or not np.array_equal(wS, d["S12_0"]) else np.asarray(d["S12_0"], np.float64))
     if fix and wn:
         assert S[7] == d["S12_0"][7]
+
+
+# ---- against the reference's OWN Optimizer.cpp ----------------------------------------------------------------------------------
+# oracle/_ref/liboptimizer_ref.so is cslam/src/Optimizer.cpp itself, compiled where it lies together with the whole of g2o's core and
+# types from the reference tree (over the Eigen stand-in), the same stand-in Map / KeyFrame / MapPoint / Frame and the same wrapper; the
+# only parts that are not the reference's are LinearSolverEigen / LinearSolverDense, backed by the oracle's factorisations.  Every entry
+# point is driven through both libraries on the same scene and everything the callee wrote must be identical, bit for bit.
+class BothSides:
+    def __init__(self):
+        self.n = 0
+
+    def run(self, fn, *a, **k):
+        H.use_reference(False); shim = fn(*a, **k)
+        H.use_reference(True)
+        try:
+            ref = fn(*a, **k)
+        finally:
+            H.use_reference(False)
+        self.n += 1
+        return shim, ref
+
+
+@pytest.fixture(scope="module")
+def both(ho):
+    H.use_reference(True)
+    try:
+        ok = H.lib() is not None
+    finally:
+        H.use_reference(False)
+    if not ok:
+        pytest.skip("oracle/_ref/liboptimizer_ref.so not available")
+    return BothSides()
+
+
+def same_out(a, b):
+    if isinstance(a, dict):
+        for k in a:
+            assert np.array_equal(a[k], b[k]), k
+    else:
+        assert len(a) == len(b)
+        for x, y in zip(a, b):
+            assert np.array_equal(np.asarray(x), np.asarray(y))
+
+
+@pytest.mark.parametrize("loop", [(0, 0), (7, 0)])
+@pytest.mark.parametrize("name,bad_kf,bad_mp,robust", [("tiny", 0.0, 0.0, True), ("small", 0.0, 0.0, True), ("small", 0.1, 0.1, True), ("small", 0.1, 0.1, False)])
+def test_reference_map_fusion_gba(ho, both, name, bad_kf, bad_mp, robust, loop):
+    p = synth.make_config(name)
+    sc = H.scene_from_problem(p, ho, seed=3, map_id=0, bad_kf=bad_kf, bad_mp=bad_mp)
+    sc["kf_bad"][0] = 0
+    for which in (0, 1):                                   # MapFusionGBA, GlobalBundleAdjustemntClient
+        same_out(*both.run(H.run_gba, sc, which, 8, robust, loop))
+
+
+def test_reference_local_ba(ho, both):
+    p = synth.make_config("cfg2", P=500)
+    sc = H.scene_from_problem(p, ho, seed=5, map_id=0)
+    rng = np.random.default_rng(6)
+    for center in (3, 11):
+        covis = [k for k in rng.permutation(p.K) if k != center][:10]
+        s2 = dict(sc); s2["kf_bad"] = sc["kf_bad"].copy(); s2["kf_bad"][covis[2]] = 1
+        cov_ptr = np.zeros(p.K + 1, np.int32); cov_ptr[center + 1:] = len(covis)
+        s2.update(cov_ptr=cov_ptr, cov_kf=np.array(covis, np.int32), cov_w=np.full(len(covis), 200, np.int32), mp_bad=(rng.random(p.P) < 0.05).astype(np.uint8))
+        for server in (False, True):
+            a, b = both.run(H.run_local_ba, s2, center, server)
+            same_out(a, b)
+            assert a["kf_set_pose"].sum() > 3 and (np.diff(s2["obs_ptr"]) - a["mp_n_obs"]).sum() > 0     # poses written, observations erased
+
+
+@pytest.mark.parametrize("n,seed,frac", [(300, 11, 0.15), (40, 12, 0.3), (9, 14, 0.0), (2, 13, 0.0)])
+def test_reference_pose_optimization(ho, both, n, seed, frac):
+    d = synth.make_pose_opt(n=n, seed=seed, outlier_frac=frac)
+    rng = np.random.default_rng(seed)
+    extra = 25
+    octave = rng.integers(0, 8, n).astype(np.int32)
+    T32 = ho.pose_to_Tcw_f32(d["Tcw0"])
+    sc = dict(kf_uid=np.zeros(1, np.int64), kf_id=np.zeros((1, 2), np.int64), kf_bad=np.zeros(1, np.uint8), kf_Tcw=np.eye(4, dtype=np.float32)[None],
+              kf_intr=np.float32(d["intr"])[None], kp_ptr=np.zeros(2, np.int32), kp_uv=np.zeros((0, 2), np.float32), kp_octave=np.zeros(0, np.int32),
+              inv_level_sigma2=H.sm.INV_LEVEL_SIGMA2, kf_parent=None, loop_ptr=None, loop_kf=None, cov_ptr=None, cov_kf=None, cov_w=None,
+              mp_uid=np.arange(n).astype(np.int64), mp_id=np.stack([np.arange(n), np.zeros(n, np.int64)], 1), mp_bad=np.zeros(n, np.uint8),
+              mp_pos=np.float32(d["Xw"]), mp_ref=np.zeros(n, np.int32), obs_ptr=np.zeros(n + 1, np.int32), obs_kf=np.zeros(0, np.int32),
+              obs_idx=np.zeros(0, np.int32), origin=0, map_id=0)
+    slot = np.sort(rng.permutation(n + extra)[:n])
+    kp_uv = rng.uniform(0, 700, (n + extra, 2)).astype(np.float32); kp_oct = rng.integers(0, 8, n + extra).astype(np.int32)
+    mp_of_kp = np.full(n + extra, -1, np.int32)
+    kp_uv[slot] = d["uv"]; kp_oct[slot] = octave; mp_of_kp[slot] = np.arange(n)
+    a, b = both.run(H.run_pose_optimization, sc, kp_uv, kp_oct, mp_of_kp, T32, d["intr"])
+    same_out(a, b)
+
+
+@pytest.mark.parametrize("n,seed,fix,frac", [(120, 12, False, 0.2), (120, 12, True, 0.2), (12, 5, False, 0.6), (60, 7, False, 0.0)])
+def test_reference_optimize_sim3(ho, both, n, seed, fix, frac):
+    d = synth.make_sim3_opt(n=n, seed=seed, fix_scale=fix, outlier_frac=frac)
+    rng = np.random.default_rng(seed + 1)
+    o1 = rng.integers(0, 8, n).astype(np.int32); o2 = rng.integers(0, 8, n).astype(np.int32)
+    P1, P2 = np.float32(d["P1c"]), np.float32(d["P2c"])
+    I = np.eye(4, dtype=np.float32)
+    match1 = (n + np.arange(n)).astype(np.int32); match1[rng.random(n) < 0.1] = -1
+    bad = np.zeros(2 * n, np.uint8); bad[rng.permutation(2 * n)[:n // 10]] = 1
+    unseen = rng.random(n) < 0.05
+    obs_cnt = np.r_[np.ones(n, np.int32), (~unseen).astype(np.int32)]
+    sc = dict(kf_uid=np.arange(2).astype(np.int64), kf_id=np.stack([np.arange(2), np.zeros(2, np.int64)], 1), kf_bad=np.zeros(2, np.uint8),
+              kf_Tcw=np.stack([I, I]), kf_intr=np.stack([np.float32(d["K1"]), np.float32(d["K2"])]), kp_ptr=np.array([0, n, 2 * n], np.int32),
+              kp_uv=np.r_[np.float32(d["uv1"]), np.float32(d["uv2"])], kp_octave=np.r_[o1, o2], inv_level_sigma2=H.sm.INV_LEVEL_SIGMA2, kf_parent=None,
+              loop_ptr=None, loop_kf=None, cov_ptr=None, cov_kf=None, cov_w=None, mp_uid=np.arange(2 * n).astype(np.int64),
+              mp_id=np.stack([np.arange(2 * n), np.zeros(2 * n, np.int64)], 1), mp_bad=bad, mp_pos=np.r_[P1, P2], mp_ref=np.zeros(2 * n, np.int32),
+              obs_ptr=np.concatenate([[0], np.cumsum(obs_cnt)]).astype(np.int32), obs_kf=np.r_[np.zeros(n, np.int32), np.ones((~unseen).sum(), np.int32)],
+              obs_idx=np.r_[np.arange(n), np.arange(n)[~unseen]].astype(np.int32), origin=0, map_id=0)
+    a, b = both.run(H.run_optimize_sim3, sc, 0, 1, match1, d["S12_0"], d["th2"], fix)
+    same_out(a, b)
+
+
+@pytest.mark.parametrize("fix_scale", [False, True])
+def test_reference_essential_graph(ho, both, fix_scale):
+    K = 40
+    sc, cov, loops = essential_scene(ho, K=K, seed=1)
+    loop_kf, cur_kf = 2, K - 1
+    conn = {cur_kf: [loop_kf, 4], loop_kf: [cur_kf], 4: [cur_kf], K - 2: [3]}
+    same_out(*both.run(H.run_essential_graph, sc, loop_kf, cur_kf, conn, fix_scale))
+    # loop closure variant with corrected / non-corrected maps and tagged points
+    O = ho.Pieces("oracle"); R = ho.Pieces("ref")
+    rng = np.random.default_rng(5)
+    near = [K - 1, K - 2, K - 3]
+    fix = O.vec("sim3_exp", 8, np.r_[rng.normal(0, 0.02, 3), rng.normal(0, 0.1, 3), 0.0 if fix_scale else 0.05])
+    non, cor = [], []
+    for k in near:
+        T = sc["kf_Tcw"][k].astype(np.float64)
+        non.append(R.vec("sim3_from_Rt", 8, T[:3, :3].ravel(), T[:3, 3], [1.0])); cor.append(O.vec("sim3_mul", 8, non[-1], fix))
+    mp_corr = np.where(np.random.default_rng(6).random(300) < 0.2, sc["kf_uid"][K - 2], -1).astype(np.int32)
+    a, b = both.run(H.run_essential_graph, sc, loop_kf, cur_kf, {cur_kf: [loop_kf, 4], loop_kf: [cur_kf], 4: [cur_kf]}, fix_scale, loop_closure=True,
+                    corr=(near, np.stack(cor), np.stack(non)), mp_corr_ref=mp_corr)
+    same_out(a, b)
+    assert np.abs(a["kf_Tcw"] - sc["kf_Tcw"]).max() > 1e-3
