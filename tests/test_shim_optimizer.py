@@ -519,3 +519,44 @@ def test_reference_essential_graph(ho, both, fix_scale):
                     corr=(near, np.stack(cor), np.stack(non)), mp_corr_ref=mp_corr)
     same_out(a, b)
     assert np.abs(a["kf_Tcw"] - sc["kf_Tcw"]).max() > 1e-3
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_reference_sweep(ho, both, seed):
+    """more scenes, same claim: random bad keyframes / points, iteration counts, kernels on and off, different agents' keyframes in one map"""
+    rng = np.random.default_rng(100 + seed)
+    p = synth.make_config("small")
+    client = (np.arange(p.K) >= int(p.K * rng.uniform(0.3, 0.8))).astype(np.int64)   # two agents' keyframes: mId = (k, client), mUniqueId by GetID
+    sc = H.scene_from_problem(p, ho, seed=seed, map_id=0, bad_kf=float(rng.choice([0.0, 0.05, 0.2])), bad_mp=float(rng.choice([0.0, 0.1, 0.3])),
+                              client_of_kf=client)
+    sc["kf_bad"][0] = 0; sc["kf_id"][0] = (0, 0); sc["kf_uid"][0] = 0
+    its = int(rng.choice([1, 3, 6, 12])); robust = bool(rng.random() < 0.7)
+    loop = (int(rng.integers(1, 30)), int(rng.integers(0, 2))) if rng.random() < 0.5 else (0, 0)
+    same_out(*both.run(H.run_gba, sc, 0, its, robust, loop))
+    d = synth.make_pose_opt(n=int(rng.choice([15, 80, 400])), seed=200 + seed, outlier_frac=float(rng.choice([0.0, 0.2, 0.45])),
+                            pose_noise=(0.05, 0.2) if seed % 2 else (0.03, 0.08))
+    n = len(d["uv"]); octave = rng.integers(0, 8, n).astype(np.int32)
+    scp = dict(kf_uid=np.zeros(1, np.int64), kf_id=np.zeros((1, 2), np.int64), kf_bad=np.zeros(1, np.uint8), kf_Tcw=np.eye(4, dtype=np.float32)[None],
+               kf_intr=np.float32(d["intr"])[None], kp_ptr=np.zeros(2, np.int32), kp_uv=np.zeros((0, 2), np.float32), kp_octave=np.zeros(0, np.int32),
+               inv_level_sigma2=H.sm.INV_LEVEL_SIGMA2, kf_parent=None, loop_ptr=None, loop_kf=None, cov_ptr=None, cov_kf=None, cov_w=None,
+               mp_uid=np.arange(n).astype(np.int64), mp_id=np.stack([np.arange(n), np.zeros(n, np.int64)], 1), mp_bad=np.zeros(n, np.uint8),
+               mp_pos=np.float32(d["Xw"]), mp_ref=np.zeros(n, np.int32), obs_ptr=np.zeros(n + 1, np.int32), obs_kf=np.zeros(0, np.int32),
+               obs_idx=np.zeros(0, np.int32), origin=0, map_id=0)
+    same_out(*both.run(H.run_pose_optimization, scp, np.float32(d["uv"]), octave, np.arange(n).astype(np.int32), ho.pose_to_Tcw_f32(d["Tcw0"]), d["intr"]))
+
+
+def test_reference_vertex_order_is_the_only_difference(ho, both):
+    """g2o numbers its vertices by id (mUniqueId); the shim's rows follow the map's iteration order.  When the two orders differ — here the
+    keyframes of two agents interleaved — the same system is eliminated in another order and the f64 results part in the last bits:
+    the f32 poses written back agree to an ulp instead of exactly.  (On the device the sums are reordered anyway.)"""
+    rng = np.random.default_rng(105)
+    p = synth.make_config("small")
+    client = (rng.random(p.K) < 0.4).astype(np.int64)
+    sc = H.scene_from_problem(p, ho, seed=5, map_id=0, bad_kf=0.05, bad_mp=0.3, client_of_kf=client)
+    sc["kf_bad"][0] = 0; sc["kf_id"][0] = (0, 0); sc["kf_uid"][0] = 0
+    a, b = both.run(H.run_gba, sc, 0, 12, True, (0, 0))
+    for k in a:
+        if a[k].dtype == np.float32:
+            assert np.abs(a[k] - b[k]).max() <= 2 * np.spacing(np.float32(np.abs(b[k]).max())), k
+        else:
+            assert np.array_equal(a[k], b[k]), k
