@@ -89,7 +89,7 @@ def test_bow_and_triangulation_methods(side):
 @pytest.mark.skipif(os.environ.get("CCM_TEST_UNVALIDATED") != "1", reason="first device run pending (set CCM_TEST_UNVALIDATED=1)")
 def test_optimizer_shim_on_the_device(oracle):
     """shim/Optimizer_shim.cpp through cslam::Optimizer's interface with the real device entry points underneath: MapFusionGBA on a
-    stand-in map must land where the CPU-doubled run lands, within the device path's tolerance (f32 poses / points written back)."""
+    stand-in map must land where the reference's own Optimizer.cpp lands, within the device path's tolerance (f32 poses / points)."""
     from ccm_slam_b200 import api, synth
     from tests import shim_optimizer_harness as H
     if api.device_count() == 0:
@@ -98,10 +98,13 @@ def test_optimizer_shim_on_the_device(oracle):
     p = synth.make_config("small")
     sc = H.scene_from_problem(p, oracle, seed=3, map_id=0, bad_kf=0.1, bad_mp=0.1)
     sc["kf_bad"][0] = 0
-    H.use_device(False)
-    if H.lib() is None:
-        pytest.skip("no oracle/_ref/liboptimizer_shim.so")
-    cpu = H.run_gba(sc, 0, 8, True, (0, 0))
+    H.use_device(False); H.use_reference(True)                     # the CPU side: the reference's own Optimizer.cpp (oracle/_ref/liboptimizer_ref.so)
+    try:
+        if H.lib() is None:
+            pytest.skip("no oracle/_ref/liboptimizer_ref.so")
+        cpu = H.run_gba(sc, 0, 8, True, (0, 0))
+    finally:
+        H.use_reference(False)
     H.use_device(True)
     try:
         if H.lib() is None:
