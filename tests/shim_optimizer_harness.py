@@ -86,7 +86,7 @@ def new_out(K, P):
     return o, Out(*[_p(o[n]) for n, _ in Out._fields_])
 
 
-def scene_from_problem(p, oracle, seed=0, map_id=0, bad_kf=0.0, bad_mp=0.0, client_of_kf=None):
+def scene_from_problem(p, oracle, seed=0, map_id=0, bad_kf=0.0, bad_mp=0.0, client_of_kf=None, keep_weights=False):
     """a stand-in map holding the flat BA problem p: keyframe k <- pose k (as the f32 Tcw the reference stores), one keypoint per observation"""
     rng = np.random.default_rng(seed)
     K, P = p.K, p.P
@@ -94,6 +94,10 @@ def scene_from_problem(p, oracle, seed=0, map_id=0, bad_kf=0.0, bad_mp=0.0, clie
     order = np.lexsort((p.obs_kf, p.obs_mp))                       # observations of a point, by keyframe index
     okf, omp, ouv = p.obs_kf[order], p.obs_mp[order], p.obs_uv[order]
     octave = rng.integers(0, 8, len(order)).astype(np.int32)
+    table = sm.INV_LEVEL_SIGMA2
+    if keep_weights:                                               # the problem's own weights: they become the level table, the octaves index it
+        table = np.sort(np.unique(p.obs_w))[::-1].astype(np.float32)
+        octave = np.array([int(np.flatnonzero(table == w)[0]) for w in p.obs_w[order]], np.int32)
     kp_count = np.zeros(K, np.int64); obs_idx = np.zeros(len(order), np.int32)
     for e, k in enumerate(okf):
         obs_idx[e] = kp_count[k]; kp_count[k] += 1
@@ -107,7 +111,7 @@ def scene_from_problem(p, oracle, seed=0, map_id=0, bad_kf=0.0, bad_mp=0.0, clie
     mp_id = np.stack([np.arange(P), np.zeros(P, np.int64)], 1)
     ref = np.array([okf[obs_ptr[j]] if obs_ptr[j + 1] > obs_ptr[j] else -1 for j in range(P)], np.int32)
     return dict(kf_uid=kf_uid, kf_id=kf_id, kf_bad=(rng.random(K) < bad_kf).astype(np.uint8), kf_Tcw=Tcw, kf_intr=p.intr.astype(np.float32),
-                kp_ptr=kp_ptr, kp_uv=kp_uv, kp_octave=kp_oct, inv_level_sigma2=sm.INV_LEVEL_SIGMA2, kf_parent=None, loop_ptr=None, loop_kf=None,
+                kp_ptr=kp_ptr, kp_uv=kp_uv, kp_octave=kp_oct, inv_level_sigma2=table, kf_parent=None, loop_ptr=None, loop_kf=None,
                 cov_ptr=None, cov_kf=None, cov_w=None, mp_uid=(1000000 * 4 + np.arange(P)).astype(np.int64), mp_id=mp_id,
                 mp_bad=(rng.random(P) < bad_mp).astype(np.uint8), mp_pos=p.points.astype(np.float32), mp_ref=ref, obs_ptr=obs_ptr, obs_kf=okf,
                 obs_idx=obs_idx, origin=0, map_id=map_id)

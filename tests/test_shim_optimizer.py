@@ -560,3 +560,32 @@ def test_reference_vertex_order_is_the_only_difference(ho, both):
             assert np.abs(a[k] - b[k]).max() <= 2 * np.spacing(np.float32(np.abs(b[k]).max())), k
         else:
             assert np.array_equal(a[k], b[k]), k
+
+
+@pytest.mark.parametrize("name", ["ba_tiny.npz", "ba_small.npz"])
+def test_committed_ba_fixtures_are_what_the_reference_computes(ho, both, name):
+    """tests/golden/ba_*.npz were written by the oracle (tests/golden/make_golden.py); the GPU suite compares the device path with them
+    on the GPU box, where /root/reference does not exist.  Here the same problems go through the reference's OWN Optimizer::MapFusionGBA
+    (oracle/_ref/liboptimizer_ref.so): the poses and points it writes back are the fixture's, rounded to f32 as the reference stores them."""
+    import os
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name))
+    p = synth.BAProblem(poses=g["in_poses"], intr=g["in_intr"], fixed=g["in_fixed"], points=g["in_points"], obs_kf=g["in_obs_kf"], obs_mp=g["in_obs_mp"],
+                        obs_uv=g["in_obs_uv"], obs_w=g["in_obs_w"])
+    assert abs(float(g["huber_delta"]) - api.HUBER_GBA) < 1e-15 and p.fixed.sum() == 1
+    sc = H.scene_from_problem(p, ho, seed=0, map_id=0, keep_weights=True)
+    sc["origin"] = int(np.flatnonzero(p.fixed)[0])
+    # the reference starts from the f32 poses a KeyFrame holds: only exact when the fixture's poses survive the f32 round trip
+    start = np.stack([ho.pose_from_Tcw_f32(T) for T in sc["kf_Tcw"]])
+    H.use_reference(True)
+    try:
+        out = H.run_gba(sc, 0, int(g["iterations"]), True, (0, 0))
+    finally:
+        H.use_reference(False)
+    p2 = p.copy(); p2.poses = start; p2.points = p.points.astype(np.float32).astype(np.float64)
+    want = ho.ba_solve(p2, iterations=int(g["iterations"]), robust=True, huber_delta=api.HUBER_GBA)
+    assert np.array_equal(out["kf_Tcw"], np.stack([ho.pose_to_Tcw_f32(q) for q in want["poses"]]))
+    assert np.array_equal(out["mp_pos"], want["points"].astype(np.float32))
+    # and the fixture itself (f64 start) lands within f32 resolution of that
+    Tfix = np.stack([ho.pose_to_Tcw_f32(q) for q in g["poses"]])
+    assert np.abs(out["kf_Tcw"] - Tfix).max() <= 1e-5 * max(1.0, np.abs(Tfix).max())
+    assert np.abs(out["mp_pos"] - g["points"]).max() <= 1e-5 * np.abs(g["points"]).max()
