@@ -4,7 +4,8 @@ Same construction as tests/test_shim_dropin.py — shim/ORBmatcher_shim.cpp + sh
 oracle/ref_match_wrap.cpp, next to the reference's own ORBmatcher.cpp — but linked against the product library itself
 (oracle/_ref/libmatch_shim_gpu.so): the Hamming matrices come from k_hamming on the GPU.  Every scene goes through both
 implementations of the class and must give identical results.  All eleven methods have been run this way on the CPU with the device half
-doubled (tests/test_shim_dropin.py); the optimiser shim's device run is opt-in until it has been seen green once (CCM_TEST_UNVALIDATED=1)."""
+doubled (tests/test_shim_dropin.py), and the optimiser shim against the reference's own Optimizer.cpp (tests/test_shim_optimizer.py)."""
+import ctypes as C
 import os
 
 import numpy as np
@@ -13,7 +14,9 @@ import pytest
 from tests import test_oracle_vs_reference_matchers as T
 from tests.test_shim_dropin import same
 
-pytestmark = pytest.mark.gpu
+# Opt-in as a whole (CCM_TEST_UNVALIDATED=1, tools/validate_prepared.sh) until this file has been seen green on a device once: it loads a
+# second native library into the test process, and nothing in it could be executed where it was written (no GPU).
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("CCM_TEST_UNVALIDATED") != "1", reason="first device run pending (set CCM_TEST_UNVALIDATED=1)")]
 
 
 class SideBySideGPU:
@@ -83,10 +86,9 @@ def test_bow_and_triangulation_methods(side):
     with side._o.matcher_side("shim_gpu"):
         for _ in range(20):
             a, b = rng.integers(0, 256, 32, dtype=np.uint8), rng.integers(0, 256, 32, dtype=np.uint8)
-            assert side._o.ref_match().ref_descriptor_distance(a.ctypes.data, b.ctypes.data) == int(np.unpackbits(a ^ b).sum())
+            assert side._o.ref_match().ref_descriptor_distance(a.ctypes.data_as(C.c_void_p), b.ctypes.data_as(C.c_void_p)) == int(np.unpackbits(a ^ b).sum())
 
 
-@pytest.mark.skipif(os.environ.get("CCM_TEST_UNVALIDATED") != "1", reason="first device run pending (set CCM_TEST_UNVALIDATED=1)")
 def test_optimizer_shim_on_the_device(oracle):
     """shim/Optimizer_shim.cpp through cslam::Optimizer's interface with the real device entry points underneath: MapFusionGBA on a
     stand-in map must land where the reference's own Optimizer.cpp lands, within the device path's tolerance (f32 poses / points)."""

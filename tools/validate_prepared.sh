@@ -19,7 +19,7 @@ if [ "$mode" = single ]; then
   (echo "== dist self-window"; CCM_PCG_DIST=1 timeout 90 python tools/schur_variants.py cfg5 2>&1 | tail -1) >> gpurun_out/prolong_cfg5.log
   # 1c. device-side window search of Fuse / SearchBySim3 (k_window_best)
   (CCM_MATCH_WINDOW=1 timeout 120 python -m pytest tests/test_gpu_widen.py -m gpu -x -q 2>&1 | tail -5) > gpurun_out/match_window.log
-  # 1d. shim/Optimizer_shim.cpp's MapFusionGBA over the real device entry points (the matcher shims run ungated in the suite below)
+  # 1d. the shims over the real device entry points next to the reference's ORBmatcher.cpp / Optimizer.cpp (opt-in file)
   (CCM_TEST_UNVALIDATED=1 timeout 120 python -m pytest tests/test_gpu_zz_dropin.py -m gpu -x -q 2>&1 | tail -5) > gpurun_out/dropin_gpu.log
   # 2. the whole GPU suite with the current defaults (CTA-128 Schur kernel, new golden / SearchForInitialization tests)
   (timeout 120 python -m pytest tests -m gpu -x -q 2>&1 | tail -5) > gpurun_out/gpu_suite.log
