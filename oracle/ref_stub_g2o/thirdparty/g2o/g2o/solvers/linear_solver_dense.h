@@ -18,23 +18,25 @@ class LinearSolverDense : public LinearSolver<MatrixType> {
   virtual ~LinearSolverDense() {}
   virtual bool init() { return true; }
   bool solve(const SparseBlockMatrix<MatrixType>& A, double* x, double* b) {
+    // densify: A keeps block (i, j), i <= j, in the map of block column j; mirror it below the diagonal
     const int n = A.cols();
-    std::vector<double> H((size_t)n * n, 0.);
-    for (size_t i = 0; i < A.blockCols().size(); ++i) {
-      const int c_idx = A.colBaseOfBlock((int)i);
-      const typename SparseBlockMatrix<MatrixType>::IntBlockMap& col = A.blockCols()[i];
-      for (typename SparseBlockMatrix<MatrixType>::IntBlockMap::const_iterator it = col.begin(); it != col.end(); ++it) {
-        if (it->first > (int)i) continue;                       // only the upper triangular block is processed
-        const int r_idx = A.rowBaseOfBlock(it->first);
-        const MatrixType& m = *(it->second);
-        for (int r = 0; r < m.rows(); r++)
-          for (int c = 0; c < m.cols(); c++) {
-            H[(size_t)(r_idx + r) * n + c_idx + c] = m(r, c);
-            if (r_idx != c_idx) H[(size_t)(c_idx + c) * n + r_idx + r] = m(r, c);
+    std::vector<double> dense((size_t)n * n, 0.);
+    const int ncol = (int)A.blockCols().size();
+    for (int j = 0; j < ncol; j++) {
+      const int c0 = A.colBaseOfBlock(j);
+      for (const auto& entry : A.blockCols()[j]) {
+        const int i = entry.first;
+        if (i > j) continue;
+        const int r0 = A.rowBaseOfBlock(i);
+        const MatrixType& blk = *entry.second;
+        for (int c = 0; c < blk.cols(); c++)
+          for (int r = 0; r < blk.rows(); r++) {
+            dense[(size_t)(r0 + r) * n + (c0 + c)] = blk(r, c);
+            if (i != j) dense[(size_t)(c0 + c) * n + (r0 + r)] = blk(r, c);
           }
       }
     }
-    return orc_chol_solve(n, H.data(), b, x) == 0;
+    return orc_chol_solve(n, dense.data(), b, x) == 0;
   }
 };
 
