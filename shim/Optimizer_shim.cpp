@@ -286,26 +286,26 @@ void optimize_essential_graph(Optimizer::mapptr pMap, Optimizer::kfptr pLoopKF, 
   typedef Optimizer::kfptr kfptr;
   typedef Optimizer::mpptr mpptr;
   typedef Optimizer::KeyFrameAndPose KeyFrameAndPose;
-  const vector<kfptr> vpKFs = pMap->GetAllKeyFrames();
-  const vector<mpptr> vpMPs = pMap->GetAllMapPoints();
-  const int minFeat = params::opt::miEssGraphMinFeats;
+  const vector<kfptr> kfs = pMap->GetAllKeyFrames();
+  const vector<mpptr> mps = pMap->GetAllMapPoints();
+  const int min_weight = params::opt::miEssGraphMinFeats;
 
   // vertices, :1086-1118 / :1360-1384.  Rows in ascending mUniqueId = the order of g2o's index mapping.
-  map<size_t, g2o::Sim3> vScw;
+  map<size_t, g2o::Sim3> S_cw;
   map<size_t, int> row_of_id;
-  for (size_t i = 0; i < vpKFs.size(); i++) {
-    kfptr pKF = vpKFs[i];
+  for (size_t i = 0; i < kfs.size(); i++) {
+    kfptr pKF = kfs[i];
     if (pKF->isBad()) continue;
-    const size_t nIDi = pKF->mUniqueId;
+    const size_t id_i = pKF->mUniqueId;
     KeyFrameAndPose::const_iterator it;
-    if (CorrectedSim3 && (it = CorrectedSim3->find(pKF)) != CorrectedSim3->end()) vScw[nIDi] = it->second;
-    else vScw[nIDi] = g2o::Sim3(Converter::toMatrix3d(pKF->GetRotation()), Converter::toVector3d(pKF->GetTranslation()), 1.0);
+    if (CorrectedSim3 && (it = CorrectedSim3->find(pKF)) != CorrectedSim3->end()) S_cw[id_i] = it->second;
+    else S_cw[id_i] = g2o::Sim3(Converter::toMatrix3d(pKF->GetRotation()), Converter::toVector3d(pKF->GetTranslation()), 1.0);
   }
-  std::vector<double> sim3(8 * vScw.size());
-  std::vector<uint8_t> fixed(vScw.size(), 0);
+  std::vector<double> sim3(8 * S_cw.size());
+  std::vector<uint8_t> fixed(S_cw.size(), 0);
   {
     int row = 0;
-    for (map<size_t, g2o::Sim3>::const_iterator it = vScw.begin(); it != vScw.end(); ++it, ++row) {
+    for (map<size_t, g2o::Sim3>::const_iterator it = S_cw.begin(); it != S_cw.end(); ++it, ++row) {
       row_of_id[it->first] = row;
       sim3_flat(it->second, &sim3[8 * (size_t)row]);
     }
@@ -315,55 +315,55 @@ void optimize_essential_graph(Optimizer::mapptr pMap, Optimizer::kfptr pLoopKF, 
   std::vector<int32_t> ei, ej;
   std::vector<double> meas;
   auto in_graph = [&](const kfptr& k) { return row_of_id.count(k->mUniqueId) != 0; };
-  auto add_edge = [&](const kfptr& pKFi, const kfptr& pKFj, const g2o::Sim3& Sji) {   // vertex 0 = i, vertex 1 = j
-    ei.push_back(row_of_id[pKFi->mUniqueId]); ej.push_back(row_of_id[pKFj->mUniqueId]);
+  auto add_edge = [&](const kfptr& kfi, const kfptr& pKFj, const g2o::Sim3& Sji) {   // vertex 0 = i, vertex 1 = j
+    ei.push_back(row_of_id[kfi->mUniqueId]); ej.push_back(row_of_id[pKFj->mUniqueId]);
     meas.resize(meas.size() + 8);
     sim3_flat(Sji, &meas[meas.size() - 8]);
   };
   auto uncorrected = [&](const kfptr& pKF) -> g2o::Sim3 {                  // Sjw of a neighbour: NonCorrectedSim3 first (loop closure only)
     KeyFrameAndPose::const_iterator it;
     if (NonCorrectedSim3 && (it = NonCorrectedSim3->find(pKF)) != NonCorrectedSim3->end()) return it->second;
-    return vScw.find(pKF->mUniqueId)->second;                              // only called for keyframes in the graph
+    return S_cw.find(pKF->mUniqueId)->second;                              // only called for keyframes in the graph
   };
 
   // new loop connections, :1124-1155 / :1390-1421
-  set<pair<long unsigned int, long unsigned int> > sInsertedEdges;
+  set<pair<long unsigned int, long unsigned int> > linked;
   for (map<kfptr, set<kfptr> >::const_iterator mit = LoopConnections.begin(); mit != LoopConnections.end(); ++mit) {
     kfptr pKF = mit->first;
     if (pKF->isBad() || !in_graph(pKF)) continue;
-    const size_t nIDi = pKF->mUniqueId;
-    const g2o::Sim3 Swi = vScw.find(nIDi)->second.inverse();
+    const size_t id_i = pKF->mUniqueId;
+    const g2o::Sim3 S_wi = S_cw.find(id_i)->second.inverse();
     for (set<kfptr>::const_iterator sit = mit->second.begin(); sit != mit->second.end(); ++sit) {
       if ((*sit)->isBad() || !in_graph(*sit)) continue;
-      const size_t nIDj = (*sit)->mUniqueId;
-      if ((nIDi != pCurKF->mUniqueId || nIDj != pLoopKF->mUniqueId) && pKF->GetWeight(*sit) < minFeat) continue;
-      add_edge(pKF, *sit, vScw.find(nIDj)->second * Swi);
-      sInsertedEdges.insert(make_pair(min(nIDi, nIDj), max(nIDi, nIDj)));
+      const size_t id_j = (*sit)->mUniqueId;
+      if ((id_i != pCurKF->mUniqueId || id_j != pLoopKF->mUniqueId) && pKF->GetWeight(*sit) < min_weight) continue;
+      add_edge(pKF, *sit, S_cw.find(id_j)->second * S_wi);
+      linked.insert(make_pair(min(id_i, id_j), max(id_i, id_j)));
     }
   }
   // spanning tree, earlier loop edges, covisibility, :1158-1268 / :1424-1504.  An edge to a keyframe that is not a vertex (bad) is not
   // added, as g2o refuses an edge with a missing vertex.
-  for (size_t i = 0; i < vpKFs.size(); i++) {
-    kfptr pKF = vpKFs[i];
+  for (size_t i = 0; i < kfs.size(); i++) {
+    kfptr pKF = kfs[i];
     if (pKF->isBad()) continue;
-    const size_t nIDi = pKF->mUniqueId;
-    const g2o::Sim3 Swi = uncorrected(pKF).inverse();
-    kfptr pParentKF = pKF->GetParent();
-    if (pParentKF && in_graph(pParentKF)) add_edge(pKF, pParentKF, uncorrected(pParentKF) * Swi);
-    const set<kfptr> sLoopEdges = pKF->GetLoopEdges();
-    for (set<kfptr>::const_iterator sit = sLoopEdges.begin(); sit != sLoopEdges.end(); ++sit) {
-      kfptr pLKF = *sit;
-      if (pLKF->mUniqueId < nIDi && in_graph(pLKF)) add_edge(pKF, pLKF, uncorrected(pLKF) * Swi);
+    const size_t id_i = pKF->mUniqueId;
+    const g2o::Sim3 S_wi = uncorrected(pKF).inverse();
+    kfptr parent = pKF->GetParent();
+    if (parent && in_graph(parent)) add_edge(pKF, parent, uncorrected(parent) * S_wi);
+    const set<kfptr> old_loops = pKF->GetLoopEdges();
+    for (set<kfptr>::const_iterator sit = old_loops.begin(); sit != old_loops.end(); ++sit) {
+      kfptr lk = *sit;
+      if (lk->mUniqueId < id_i && in_graph(lk)) add_edge(pKF, lk, uncorrected(lk) * S_wi);
     }
-    const vector<kfptr> vpConnectedKFs = pKF->GetCovisiblesByWeight(minFeat);
-    for (vector<kfptr>::const_iterator vit = vpConnectedKFs.begin(); vit != vpConnectedKFs.end(); ++vit) {
-      kfptr pKFn = *vit;
-      if (!pKFn || pKFn->isBad() || !in_graph(pKFn)) continue;
-      if (pKFn != pParentKF && !pKF->hasChild(pKFn) && !sLoopEdges.count(pKFn)) {
-        const size_t nIDj = pKFn->mUniqueId;
-        if (nIDj < nIDi) {
-          if (sInsertedEdges.count(make_pair(min(nIDi, nIDj), max(nIDi, nIDj)))) continue;
-          add_edge(pKF, pKFn, uncorrected(pKFn) * Swi);
+    const vector<kfptr> strong = pKF->GetCovisiblesByWeight(min_weight);
+    for (vector<kfptr>::const_iterator vit = strong.begin(); vit != strong.end(); ++vit) {
+      kfptr nb = *vit;
+      if (!nb || nb->isBad() || !in_graph(nb)) continue;
+      if (nb != parent && !pKF->hasChild(nb) && !old_loops.count(nb)) {
+        const size_t id_j = nb->mUniqueId;
+        if (id_j < id_i) {
+          if (linked.count(make_pair(min(id_i, id_j), max(id_i, id_j)))) continue;
+          add_edge(pKF, nb, uncorrected(nb) * S_wi);
         }
       }
     }
@@ -379,32 +379,32 @@ void optimize_essential_graph(Optimizer::mapptr pMap, Optimizer::kfptr pLoopKF, 
   check(ccm_pgo_solve(&p, &o, &r));
 
   // recovery, :1280-1330 / :1517-1565: [sR t; 0 1] -> [R t/s; 0 1] per keyframe, every map point moved through its reference keyframe
-  map<size_t, g2o::Sim3> vCorrectedSwc;
-  for (size_t i = 0; i < vpKFs.size(); i++) {
-    kfptr pKFi = vpKFs[i];
-    if (pKFi->isBad()) continue;
-    const size_t nIDi = pKFi->mUniqueId;
-    const double* q = &out[8 * (size_t)row_of_id[nIDi]];
-    g2o::Sim3 CorrectedSiw(Eigen::Quaterniond(q[3], q[0], q[1], q[2]), Eigen::Vector3d(q[4], q[5], q[6]), q[7]);
-    vCorrectedSwc[nIDi] = CorrectedSiw.inverse();
-    Eigen::Matrix3d eigR = CorrectedSiw.rotation().toRotationMatrix();
-    Eigen::Vector3d eigt = CorrectedSiw.translation();
-    double s = CorrectedSiw.scale();
-    eigt *= (1. / s);
-    pKFi->SetPose(Converter::toCvSE3(eigR, eigt), true);
+  map<size_t, g2o::Sim3> S_wc_new;
+  for (size_t i = 0; i < kfs.size(); i++) {
+    kfptr kfi = kfs[i];
+    if (kfi->isBad()) continue;
+    const size_t id_i = kfi->mUniqueId;
+    const double* q = &out[8 * (size_t)row_of_id[id_i]];
+    g2o::Sim3 S_iw_new(Eigen::Quaterniond(q[3], q[0], q[1], q[2]), Eigen::Vector3d(q[4], q[5], q[6]), q[7]);
+    S_wc_new[id_i] = S_iw_new.inverse();
+    Eigen::Matrix3d Rm = S_iw_new.rotation().toRotationMatrix();
+    Eigen::Vector3d tv = S_iw_new.translation();
+    double s = S_iw_new.scale();
+    tv *= (1. / s);
+    kfi->SetPose(Converter::toCvSE3(Rm, tv), true);
   }
-  for (size_t i = 0; i < vpMPs.size(); i++) {
-    mpptr pMP = vpMPs[i];
-    if (pMP->isBad()) continue;
-    size_t nIDr;
-    const bool tagged = NonCorrectedSim3 ? pMP->mCorrectedByKF_LC == pCurKF->mId : pMP->mCorrectedByKF_MM == pCurKF->mId;
-    if (tagged) nIDr = NonCorrectedSim3 ? pMP->mCorrectedReference_LC : pMP->mCorrectedReference_MM;
-    else nIDr = pMP->GetReferenceKeyFrame()->mUniqueId;
-    if (!vScw.count(nIDr)) continue;                           // reference keyframe not in the graph
-    Eigen::Matrix<double, 3, 1> eigP3Dw = Converter::toVector3d(pMP->GetWorldPos());
-    Eigen::Matrix<double, 3, 1> eigCorrectedP3Dw = vCorrectedSwc.find(nIDr)->second.map(vScw.find(nIDr)->second.map(eigP3Dw));
-    pMP->SetWorldPos(Converter::toCvMat(eigCorrectedP3Dw), true);
-    pMP->UpdateNormalAndDepth();
+  for (size_t i = 0; i < mps.size(); i++) {
+    mpptr mp = mps[i];
+    if (mp->isBad()) continue;
+    size_t id_ref;
+    const bool tagged = NonCorrectedSim3 ? mp->mCorrectedByKF_LC == pCurKF->mId : mp->mCorrectedByKF_MM == pCurKF->mId;
+    if (tagged) id_ref = NonCorrectedSim3 ? mp->mCorrectedReference_LC : mp->mCorrectedReference_MM;
+    else id_ref = mp->GetReferenceKeyFrame()->mUniqueId;
+    if (!S_cw.count(id_ref)) continue;                           // reference keyframe not in the graph
+    Eigen::Matrix<double, 3, 1> x_old = Converter::toVector3d(mp->GetWorldPos());
+    Eigen::Matrix<double, 3, 1> x_new = S_wc_new.find(id_ref)->second.map(S_cw.find(id_ref)->second.map(x_old));
+    mp->SetWorldPos(Converter::toCvMat(x_new), true);
+    mp->UpdateNormalAndDepth();
   }
 }
 
