@@ -139,12 +139,13 @@ def flat_from_scene(sc, oracle, kf_rows, fixed_of_row, mp_rows_rule):
     return p, mp_of_row
 
 
-def run_gba(sc, which, iterations, robust, loop):
+def run_gba(sc, which, iterations, robust, loop, want_rc=0):
+    """want_rc = -1: the callee is expected to throw (estd::infrastructure_ex); the wrapper reports that as -1"""
     keep = []
     S = c_scene(sc, keep)
     o, O = new_out(S.K, S.P)
     rc = lib().optw_gba(C.byref(S), int(which), int(iterations), int(robust), C.c_int64(loop[0]), C.c_int64(loop[1]), C.byref(O))
-    assert rc == 0
+    assert rc == want_rc, rc
     return o
 
 

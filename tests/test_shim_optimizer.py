@@ -589,3 +589,24 @@ def test_committed_ba_fixtures_are_what_the_reference_computes(ho, both, name):
     Tfix = np.stack([ho.pose_to_Tcw_f32(q) for q in g["poses"]])
     assert np.abs(out["kf_Tcw"] - Tfix).max() <= 1e-5 * max(1.0, np.abs(Tfix).max())
     assert np.abs(out["mp_pos"] - g["points"]).max() <= 1e-5 * np.abs(g["points"]).max()
+
+
+def test_reference_error_conventions(ho, both):
+    """the fatal cases of SURVEY.md 8(b): both implementations throw estd::infrastructure_ex and leave the map alone"""
+    p = synth.make_config("tiny")
+    sc = H.scene_from_problem(p, ho, seed=1, map_id=0)
+    no_origin = dict(sc, origin=-1)                                 # pMap->mvpKeyFrameOrigins.empty()  (S/Optimizer.cpp:663-667)
+    for ref in (False, True):
+        H.use_reference(ref)
+        try:
+            out = H.run_gba(no_origin, 0, 5, True, (0, 0), want_rc=-1)
+        finally:
+            H.use_reference(False)
+        assert not out["kf_set_pose"].any()
+    big = dict(sc); big["kf_id"] = sc["kf_id"].copy(); big["kf_id"][1, 0] = 1000000     # keyframe id >= IDRANGE  (S/Optimizer.cpp:68-72)
+    for ref in (False, True):
+        H.use_reference(ref)
+        try:
+            H.run_gba(big, 1, 5, True, (0, 0), want_rc=-1)
+        finally:
+            H.use_reference(False)
