@@ -610,3 +610,31 @@ def test_reference_error_conventions(ho, both):
             H.run_gba(big, 1, 5, True, (0, 0), want_rc=-1)
         finally:
             H.use_reference(False)
+
+
+def test_shim_is_reentrant(ho):
+    """SURVEY.md 8(b) threading: the entry points are called concurrently (per-agent LocalBA threads, per-map GBA threads).  Four threads
+    run MapFusionGBA / LocalBundleAdjustmentClient through the shim at once on their own scenes; each must get what it gets alone."""
+    import threading
+    jobs = []
+    for seed in range(4):
+        p = synth.make_config("small")
+        sc = H.scene_from_problem(p, ho, seed=40 + seed, map_id=0, bad_kf=0.05 * seed, bad_mp=0.1)
+        sc["kf_bad"][0] = 0
+        jobs.append(sc)
+    H.use_reference(False)
+    alone = [H.run_gba(sc, 0, 6, True, (0, 0)) for sc in jobs]
+    got = [None] * len(jobs); err = []
+
+    def work(i):
+        try:
+            for _ in range(3):
+                got[i] = H.run_gba(jobs[i], 0, 6, True, (0, 0))
+        except Exception as e:          # noqa: BLE001
+            err.append(e)
+    th = [threading.Thread(target=work, args=(i,)) for i in range(len(jobs))]
+    for t in th: t.start()
+    for t in th: t.join()
+    assert not err
+    for a, b in zip(alone, got):
+        same_out(a, b)
