@@ -638,3 +638,21 @@ def test_shim_is_reentrant(ho):
     assert not err
     for a, b in zip(alone, got):
         same_out(a, b)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_reference_local_ba_sweep(ho, both, seed):
+    """LocalBundleAdjustmentClient has the most selection logic (local window, local points, fixed observers, two rounds, erasures): random
+    centres, covisibility lists, bad keyframes / points and map sizes through both implementations"""
+    rng = np.random.default_rng(300 + seed)
+    p = synth.make_config("cfg2", P=int(rng.choice([150, 400, 900])))
+    sc = H.scene_from_problem(p, ho, seed=seed, map_id=0, bad_kf=float(rng.choice([0.0, 0.1])), bad_mp=float(rng.choice([0.0, 0.1, 0.3])))
+    center = int(rng.integers(0, p.K))
+    sc["kf_bad"][center] = 0
+    ncov = int(rng.integers(0, 14))
+    covis = [int(k) for k in rng.permutation(p.K) if k != center][:ncov]
+    cov_ptr = np.zeros(p.K + 1, np.int32); cov_ptr[center + 1:] = len(covis)
+    sc.update(cov_ptr=cov_ptr, cov_kf=np.array(covis, np.int32), cov_w=np.full(len(covis), 200, np.int32))
+    a, b = both.run(H.run_local_ba, sc, center, bool(seed % 2))
+    same_out(a, b)
+    assert a["kf_set_pose"][center] == 1
