@@ -656,3 +656,33 @@ def test_reference_local_ba_sweep(ho, both, seed):
     a, b = both.run(H.run_local_ba, sc, center, bool(seed % 2))
     same_out(a, b)
     assert a["kf_set_pose"][center] == 1
+
+
+@pytest.mark.parametrize("seed", range(6))
+def test_reference_essential_graph_sweep(ho, both, seed):
+    """random spanning trees, earlier loop edges, covisibility lists with weights either side of the threshold, random new loop connections,
+    free and fixed scale, both variants — shim vs the reference's OptimizeEssentialGraph*"""
+    rng = np.random.default_rng(400 + seed)
+    K = int(rng.choice([12, 30, 55]))
+    sc, cov, loops = essential_scene(ho, K=K, seed=50 + seed)
+    sc["kf_parent"] = np.array([-1] + [int(rng.integers(0, k)) for k in range(1, K)], np.int32)        # a random tree rooted at keyframe 0
+    pairs = [(int(rng.integers(2, K)), int(rng.integers(0, 2))) for _ in range(int(rng.integers(0, 4)))]
+    le = {k: set() for k in range(K)}
+    for a, b in pairs:
+        if a != b:
+            le[a].add(b); le[b].add(a)
+    sc["loop_ptr"] = np.concatenate([[0], np.cumsum([len(le[k]) for k in range(K)])]).astype(np.int32)
+    sc["loop_kf"] = np.array([j for k in range(K) for j in sorted(le[k])], np.int32)
+    loop_kf, cur_kf = int(rng.integers(0, K // 2)), K - 1
+    conn = {cur_kf: sorted({loop_kf, int(rng.integers(0, K - 1))}), loop_kf: [cur_kf]}
+    fix = bool(seed % 2)
+    same_out(*both.run(H.run_essential_graph, sc, loop_kf, cur_kf, conn, fix))
+    O = ho.Pieces("oracle"); R = ho.Pieces("ref")
+    near = sorted(set([cur_kf] + [int(k) for k in rng.integers(0, K, 3)]))
+    d = O.vec("sim3_exp", 8, np.r_[rng.normal(0, 0.03, 3), rng.normal(0, 0.1, 3), 0.0 if fix else rng.normal(0, 0.05)])
+    non, cor = [], []
+    for k in near:
+        T = sc["kf_Tcw"][k].astype(np.float64)
+        non.append(R.vec("sim3_from_Rt", 8, T[:3, :3].ravel(), T[:3, 3], [1.0])); cor.append(O.vec("sim3_mul", 8, non[-1], d))
+    tag = np.where(rng.random(300) < 0.15, sc["kf_uid"][near[0]], -1).astype(np.int32)
+    same_out(*both.run(H.run_essential_graph, sc, loop_kf, cur_kf, conn, fix, loop_closure=True, corr=(near, np.stack(cor), np.stack(non)), mp_corr_ref=tag))
