@@ -476,16 +476,15 @@ def test_reference_pose_optimization(ho, both, n, seed, frac):
     same_out(a, b)
 
 
-@pytest.mark.parametrize("n,seed,fix,frac", [(120, 12, False, 0.2), (120, 12, True, 0.2), (12, 5, False, 0.6), (60, 7, False, 0.0)])
-def test_reference_optimize_sim3(ho, both, n, seed, fix, frac):
-    d = synth.make_sim3_opt(n=n, seed=seed, fix_scale=fix, outlier_frac=frac)
+def sim3_scene(d, n, seed, drop=0.1, nbad_div=10, unseen_frac=0.05):
+    """two keyframes at the identity pose holding the pairs of a synthetic Sim3 alignment problem (so that R*P + t in f32 is P)"""
     rng = np.random.default_rng(seed + 1)
     o1 = rng.integers(0, 8, n).astype(np.int32); o2 = rng.integers(0, 8, n).astype(np.int32)
     P1, P2 = np.float32(d["P1c"]), np.float32(d["P2c"])
     I = np.eye(4, dtype=np.float32)
-    match1 = (n + np.arange(n)).astype(np.int32); match1[rng.random(n) < 0.1] = -1
-    bad = np.zeros(2 * n, np.uint8); bad[rng.permutation(2 * n)[:n // 10]] = 1
-    unseen = rng.random(n) < 0.05
+    match1 = (n + np.arange(n)).astype(np.int32); match1[rng.random(n) < drop] = -1
+    bad = np.zeros(2 * n, np.uint8); bad[rng.permutation(2 * n)[:n // nbad_div]] = 1
+    unseen = rng.random(n) < unseen_frac
     obs_cnt = np.r_[np.ones(n, np.int32), (~unseen).astype(np.int32)]
     sc = dict(kf_uid=np.arange(2).astype(np.int64), kf_id=np.stack([np.arange(2), np.zeros(2, np.int64)], 1), kf_bad=np.zeros(2, np.uint8),
               kf_Tcw=np.stack([I, I]), kf_intr=np.stack([np.float32(d["K1"]), np.float32(d["K2"])]), kp_ptr=np.array([0, n, 2 * n], np.int32),
@@ -494,6 +493,23 @@ def test_reference_optimize_sim3(ho, both, n, seed, fix, frac):
               mp_id=np.stack([np.arange(2 * n), np.zeros(2 * n, np.int64)], 1), mp_bad=bad, mp_pos=np.r_[P1, P2], mp_ref=np.zeros(2 * n, np.int32),
               obs_ptr=np.concatenate([[0], np.cumsum(obs_cnt)]).astype(np.int32), obs_kf=np.r_[np.zeros(n, np.int32), np.ones((~unseen).sum(), np.int32)],
               obs_idx=np.r_[np.arange(n), np.arange(n)[~unseen]].astype(np.int32), origin=0, map_id=0)
+    return sc, match1
+
+
+@pytest.mark.parametrize("n,seed,fix,frac", [(120, 12, False, 0.2), (120, 12, True, 0.2), (12, 5, False, 0.6), (60, 7, False, 0.0)])
+def test_reference_optimize_sim3(ho, both, n, seed, fix, frac):
+    d = synth.make_sim3_opt(n=n, seed=seed, fix_scale=fix, outlier_frac=frac)
+    sc, match1 = sim3_scene(d, n, seed)
+    a, b = both.run(H.run_optimize_sim3, sc, 0, 1, match1, d["S12_0"], d["th2"], fix)
+    same_out(a, b)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_reference_optimize_sim3_sweep(ho, both, seed):
+    rng = np.random.default_rng(500 + seed)
+    n = int(rng.choice([11, 25, 70, 200])); fix = bool(rng.random() < 0.5)
+    d = synth.make_sim3_opt(n=n, seed=60 + seed, fix_scale=fix, outlier_frac=float(rng.choice([0.0, 0.15, 0.4, 0.7])))
+    sc, match1 = sim3_scene(d, n, seed, drop=float(rng.choice([0.0, 0.2])), unseen_frac=float(rng.choice([0.0, 0.1])))
     a, b = both.run(H.run_optimize_sim3, sc, 0, 1, match1, d["S12_0"], d["th2"], fix)
     same_out(a, b)
 
