@@ -16,6 +16,7 @@
 #include <cmath>
 
 #include "common.cuh"
+#include "window_best.cuh"   // CellIndex, WinQuery, window_lane_scan and the host post-processing (shared with the host check in tests/)
 
 using namespace ccm;
 
@@ -35,52 +36,6 @@ void check_queries(const ccm_proj_queries* q, const char* who) {
   CCM_REQUIRE(q && q->m >= 0, std::string(who) + ": bad queries");
   CCM_REQUIRE(q->m == 0 || (q->valid && q->uv && q->radius && q->level && q->desc), std::string(who) + ": null query array");
 }
-
-// mGrid as cell_ptr / cell_feat; cell id = column * rows + row (mGrid[col][row])
-struct CellIndex {
-  const ccm_feature_grid& g;
-  std::vector<int> ptr, feat;
-  explicit CellIndex(const ccm_feature_grid& gg) : g(gg), ptr((size_t)gg.grid_cols * gg.grid_rows + 1, 0), feat() {
-    std::vector<int> cell_of(g.n, -1);
-    for (int i = 0; i < g.n; i++) {
-      // PosInGrid: round() of a float expression, then the bounds test
-      const int cx = (int)roundf((g.kp_xy[2 * i] - g.min_x) * g.grid_w_inv);
-      const int cy = (int)roundf((g.kp_xy[2 * i + 1] - g.min_y) * g.grid_h_inv);
-      if (cx < 0 || cx >= g.grid_cols || cy < 0 || cy >= g.grid_rows) continue;
-      cell_of[i] = cx * g.grid_rows + cy;
-      ptr[cell_of[i] + 1]++;
-    }
-    for (size_t c = 1; c < ptr.size(); c++) ptr[c] += ptr[c - 1];
-    feat.resize(ptr.back());
-    std::vector<int> fill(ptr.begin(), ptr.end() - 1);
-    for (int i = 0; i < g.n; i++)
-      if (cell_of[i] >= 0) feat[fill[cell_of[i]]++] = i;
-  }
-
-  // visits the keypoints GetFeaturesInArea(x, y, r[, lo, hi]) would return, in its order; levels: lo <= octave <= hi
-  template <typename F>
-  void visit(float x, float y, float r, int lo, int hi, F&& f) const {
-    const int c0 = std::max(0, (int)floorf((x - g.min_x - r) * g.grid_w_inv));
-    if (c0 >= g.grid_cols) return;
-    const int c1 = std::min(g.grid_cols - 1, (int)ceilf((x - g.min_x + r) * g.grid_w_inv));
-    if (c1 < 0) return;
-    const int r0 = std::max(0, (int)floorf((y - g.min_y - r) * g.grid_h_inv));
-    if (r0 >= g.grid_rows) return;
-    const int r1 = std::min(g.grid_rows - 1, (int)ceilf((y - g.min_y + r) * g.grid_h_inv));
-    if (r1 < 0) return;
-    for (int c = c0; c <= c1; c++) {
-      const int* p = feat.data() + ptr[(size_t)c * g.grid_rows + r0];
-      const int* e = feat.data() + ptr[(size_t)c * g.grid_rows + r1 + 1];   // rows r0..r1 of one column are contiguous
-      for (; p < e; ++p) {
-        const int j = *p;
-        const int o = g.octave[j];
-        if (o < lo || o > hi) continue;
-        const float dx = g.kp_xy[2 * j] - x, dy = g.kp_xy[2 * j + 1] - y;
-        if (fabsf(dx) < r && fabsf(dy) < r) f(j);
-      }
-    }
-  }
-};
 
 struct RotHist {
   std::vector<int> bins[HISTO_LENGTH];
@@ -305,8 +260,6 @@ void select_init(const ccm_feature_grid* g2, const ccm_proj_queries* q, const ui
 // One warp per query walks the cell runs (columns c0..c1, rows r0..r1 — computed on the host with the reference's float
 // expressions), 32 keypoints at a time in visiting order; a lane that passes the window / level / chi-square tests forms
 // key = distance << 20 | position-in-visit, the warp keeps the minimum key = the reference's strict-'<' first minimum.
-struct WinQuery { float u, v, r; int level, c0, c1, r0, r1; };
-
 __global__ void __launch_bounds__(256) k_window_best(const WinQuery* __restrict__ Q, const uint4* __restrict__ qdesc, int m,
                                                      const int* __restrict__ cell_ptr, const int* __restrict__ cell_feat, int grid_rows,
                                                      const float2* __restrict__ kp_xy, const int* __restrict__ octave,
@@ -318,34 +271,9 @@ __global__ void __launch_bounds__(256) k_window_best(const WinQuery* __restrict_
   const WinQuery q = Q[w];
   unsigned best = 0xffffffffu;
   int best_j = -1;
-  if (q.c0 <= q.c1 && q.r0 <= q.r1) {
-    const uint4 d0 = qdesc[(size_t)w * 2], d1 = qdesc[(size_t)w * 2 + 1];
-    unsigned ord = 0;
-    for (int c = q.c0; c <= q.c1; c++) {
-      const int beg = cell_ptr[c * grid_rows + q.r0], end = cell_ptr[c * grid_rows + q.r1 + 1];
-      for (int p = beg; p < end; p += 32, ord += 32) {
-        const int i = p + lane;
-        if (i < end) {
-          const int j = cell_feat[i];
-          const int o = octave[j];
-          const float2 k = kp_xy[j];
-          bool ok = o >= q.level - 1 && o <= q.level && fabsf(__fsub_rn(k.x, q.u)) < q.r && fabsf(__fsub_rn(k.y, q.v)) < q.r;
-          if (ok && inv_sigma2) {  // Fuse(kf, points): e2 * invSigma2[level] > 5.99 rejects (f32 product, compared as double)
-            const float ex = __fsub_rn(q.u, k.x), ey = __fsub_rn(q.v, k.y);
-            const float e2 = __fadd_rn(__fmul_rn(ex, ex), __fmul_rn(ey, ey));
-            ok = o >= 0 && o < nlevels && !((double)__fmul_rn(e2, inv_sigma2[o]) > 5.99);
-          }
-          if (ok) {
-            const uint4 b0 = kdesc[(size_t)j * 2], b1 = kdesc[(size_t)j * 2 + 1];
-            const unsigned d = __popc(d0.x ^ b0.x) + __popc(d0.y ^ b0.y) + __popc(d0.z ^ b0.z) + __popc(d0.w ^ b0.w) +
-                               __popc(d1.x ^ b1.x) + __popc(d1.y ^ b1.y) + __popc(d1.z ^ b1.z) + __popc(d1.w ^ b1.w);
-            const unsigned key = (d << 20) | (ord + (unsigned)lane);
-            if (key < best) { best = key; best_j = j; }
-          }
-        }
-      }
-    }
-  }
+  if (q.c0 <= q.c1 && q.r0 <= q.r1)
+    window_lane_scan(q, lane, qdesc[(size_t)w * 2], qdesc[(size_t)w * 2 + 1], cell_ptr, cell_feat, grid_rows, kp_xy, octave, kdesc, inv_sigma2,
+                     nlevels, best, best_j);   // window_best.cuh
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) {
     const unsigned ob = __shfl_xor_sync(0xffffffffu, best, off);
@@ -354,7 +282,7 @@ __global__ void __launch_bounds__(256) k_window_best(const WinQuery* __restrict_
   }
   if (lane == 0) {
     best_idx[w] = best_j;
-    best_dist[w] = best_j >= 0 ? (int)(best >> 20) : 0x7fffffff;
+    best_dist[w] = window_key_distance(best, best_j);
   }
 }
 
@@ -369,26 +297,11 @@ void device_window_best(const ccm_feature_grid* g, const ccm_proj_queries* q, co
   check_grid(g, who); check_queries(q, who);
   out_idx.assign(q->m, -1); out_dist.assign(q->m, INT_MAX);
   if (q->m == 0 || g->n == 0) return;
-  CCM_REQUIRE((long long)g->n + 32ll * g->grid_cols * 2 < (1 << 20), std::string(who) + ": too many keypoints for the 20-bit visiting position");
+  CCM_REQUIRE(window_key_fits(*g), std::string(who) + ": too many keypoints for the 20-bit visiting position");
   ensure_device();
   const CellIndex cells(*g);
-  std::vector<WinQuery> hq(q->m);
-  for (int i = 0; i < q->m; i++) {
-    WinQuery& Q = hq[i];
-    Q.u = q->uv[2 * i]; Q.v = q->uv[2 * i + 1]; Q.r = q->radius[i]; Q.level = q->level[i];
-    Q.c0 = 1; Q.c1 = 0; Q.r0 = 1; Q.r1 = 0;  // empty
-    if (!q->valid[i]) continue;
-    // GetFeaturesInArea's cell range, with its early returns
-    const int c0 = std::max(0, (int)floorf((Q.u - g->min_x - Q.r) * g->grid_w_inv));
-    if (c0 >= g->grid_cols) continue;
-    const int c1 = std::min(g->grid_cols - 1, (int)ceilf((Q.u - g->min_x + Q.r) * g->grid_w_inv));
-    if (c1 < 0) continue;
-    const int r0 = std::max(0, (int)floorf((Q.v - g->min_y - Q.r) * g->grid_h_inv));
-    if (r0 >= g->grid_rows) continue;
-    const int r1 = std::min(g->grid_rows - 1, (int)ceilf((Q.v - g->min_y + Q.r) * g->grid_h_inv));
-    if (r1 < 0) continue;
-    Q.c0 = c0; Q.c1 = c1; Q.r0 = r0; Q.r1 = r1;
-  }
+  std::vector<WinQuery> hq;
+  fill_window_queries(cells, *q, hq);
   cudaStream_t s = nullptr;
   CCM_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
   struct StreamGuard { cudaStream_t s; ~StreamGuard() { cudaStreamDestroy(s); } } guard{s};
@@ -481,13 +394,7 @@ int ccm_fuse_search(const ccm_feature_grid* g, const ccm_proj_queries* q, const 
       CCM_REQUIRE(best_idx && nfound && (!inv_level_sigma2 || nlevels > 0), "ccm_fuse_search: null argument");
       std::vector<int> bi, bd;
       device_window_best(g, q, inv_level_sigma2, nlevels, bi, bd, "ccm_fuse_search");
-      int found = 0;
-      for (int i = 0; i < q->m; i++) {
-        const bool hit = bi[i] >= 0 && bd[i] <= TH_LOW;
-        best_idx[i] = hit ? bi[i] : -1;
-        found += hit;
-      }
-      *nfound = found;
+      fuse_from_windows(q->m, bi.data(), bd.data(), TH_LOW, best_idx, nfound);
       return;
     }
     select_fuse(g, q, device_distances(q, g, "ccm_fuse_search"), inv_level_sigma2, nlevels, best_idx, nfound);
@@ -519,14 +426,7 @@ int ccm_search_by_sim3(const ccm_feature_grid* g1, const ccm_feature_grid* g2, c
       std::vector<int> i12, d12, i21, d21;
       device_window_best(g2, q12, nullptr, 0, i12, d12, "ccm_search_by_sim3");
       device_window_best(g1, q21, nullptr, 0, i21, d21, "ccm_search_by_sim3");
-      int found = 0;
-      for (int i1 = 0; i1 < q12->m; i1++) {
-        const int j = (i12[i1] >= 0 && d12[i1] <= TH_HIGH) ? i12[i1] : -1;
-        const bool agree = j >= 0 && i21[j] == i1 && d21[j] <= TH_HIGH;
-        match12[i1] = agree ? j : -1;
-        found += agree;
-      }
-      *nfound = found;
+      by_sim3_from_windows(q12->m, i12.data(), d12.data(), i21.data(), d21.data(), TH_HIGH, match12, nfound);
       return;
     }
     // the scratch matrix is per thread and reused by the next launch: keep a copy of the first direction
