@@ -359,3 +359,29 @@ def sim3_optimize(problems):
         res[b].inlier = _p(a["inl"])
     _chk(lib().ccm_sim3_optimize(probs, B, res))
     return [(np.array(res[b].S12[:]), keep[b]["inl"][:keep[b]["P1"].shape[0]], int(res[b].n_inliers)) for b in range(B)]
+
+
+def _map_update_args(sc):
+    """flat map view (ccm_slam_b200.synth.make_map_update layout) -> contiguous arrays + outputs for ccm_gba_map_update / its mirrors"""
+    K = len(sc["kf_parent"]); P = len(sc["mp_state"])
+    a = dict(parent=np.ascontiguousarray(sc["kf_parent"], np.int32), opt=np.ascontiguousarray(sc["kf_optimized"], np.uint8),
+             Tcw=np.ascontiguousarray(sc["kf_Tcw"], np.float32).reshape(K, 16), gba=np.array(sc["kf_TcwGBA"], np.float32).reshape(K, 16),
+             vis=np.zeros(max(K, 1), np.uint8), state=np.ascontiguousarray(sc["mp_state"], np.uint8), ref=np.ascontiguousarray(sc["mp_ref"], np.int32),
+             pos=np.ascontiguousarray(sc["mp_pos"], np.float32).reshape(P, 3), pgba=np.ascontiguousarray(sc["mp_pos_gba"], np.float32).reshape(P, 3),
+             out=np.zeros((max(P, 1), 3), np.float32), corr=np.zeros(max(P, 1), np.uint8))
+    argv = (K, _p(a["parent"]), _p(a["opt"]), _p(a["Tcw"]), _p(a["gba"]), _p(a["vis"]), P, _p(a["state"]), _p(a["ref"]), _p(a["pos"]), _p(a["pgba"]),
+            _p(a["out"]), _p(a["corr"]))
+    return a, argv, K, P
+
+
+def _map_update_result(a, K, P):
+    return dict(kf_TcwGBA=a["gba"].reshape(K, 4, 4), kf_visited=a["vis"][:K], mp_pos=a["out"][:P], mp_corrected=a["corr"][:P])
+
+
+def gba_map_update(sc):
+    """The map update after a global BA (Map::RunGBA, S/Map.cpp:1441-1570 = MapMerger::RunGBA, S/MapMerger.cpp:637-753) on a flat view
+    of the map: dict(kf_parent, kf_optimized, kf_Tcw (K,4,4) f32, kf_TcwGBA, mp_state, mp_ref, mp_pos, mp_pos_gba), see include/ccm_b200.h.
+    Returns dict(kf_TcwGBA, kf_visited, mp_pos, mp_corrected).  Keyframe pass on the host, point pass on the GPU."""
+    a, argv, K, P = _map_update_args(sc)
+    _chk(lib().ccm_gba_map_update(*argv))
+    return _map_update_result(a, K, P)

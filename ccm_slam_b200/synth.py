@@ -315,3 +315,47 @@ def make_sim3_opt(n=120, seed=12, outlier_frac=0.2, noise_px=0.7, scale=1.15, fi
     return dict(S12_0=S0, P1c=P1c_n.astype(np.float32), P2c=P2c_n.astype(np.float32), uv1=uv1.astype(np.float32), uv2=uv2.astype(np.float32),
                 w1=(1.0 / (s1 * s1)).astype(np.float32), w2=(1.0 / (s2 * s2)).astype(np.float32), K1=K, K2=K, th2=np.float32(10.0),
                 fix_scale=fix_scale, S12_gt=np.concatenate([q12, t12, [s]]))
+
+
+def make_map_update(K=200, P=5000, seed=0, new_kf_frac=0.15, outside_frac=0.03, n_origins=2, chain=0.7):
+    """A map as Map::RunGBA (S/Map.cpp:1441-1570) finds it when MapFusionGBA returns: a spanning forest over K keyframes rooted at
+    n_origins origins (chain-like: with probability `chain` a keyframe hangs under its predecessor), f32 poses, a BA result for the
+    keyframes that existed when the BA started and none for those added meanwhile (new_kf_frac, never an origin), a few keyframes
+    outside the tree (outside_frac, some of them holding a BA result), points with and without a BA result, bad points, points
+    without a reference keyframe."""
+    rng = np.random.default_rng(seed)
+
+    def se3(n, rot=0.6, trans=8.0):
+        w = rng.normal(0, rot, (n, 3)); th = np.linalg.norm(w, axis=1, keepdims=True); k = w / np.maximum(th, 1e-12)
+        Kx = np.zeros((n, 3, 3)); Kx[:, 0, 1] = -k[:, 2]; Kx[:, 0, 2] = k[:, 1]; Kx[:, 1, 0] = k[:, 2]; Kx[:, 1, 2] = -k[:, 0]; Kx[:, 2, 0] = -k[:, 1]; Kx[:, 2, 1] = k[:, 0]
+        R = np.eye(3) + np.sin(th)[:, :, None] * Kx + (1 - np.cos(th))[:, :, None] * (Kx @ Kx)
+        T = np.tile(np.eye(4), (n, 1, 1)); T[:, :3, :3] = R; T[:, :3, 3] = rng.normal(0, trans, (n, 3))
+        return T
+    parent = np.full(K, -2, np.int32)
+    n_origins = min(n_origins, K)
+    outside = np.zeros(K, bool)
+    if K > n_origins:
+        outside[n_origins:] = rng.random(K - n_origins) < outside_frac
+    last_in = []
+    for k in range(K):
+        if k < n_origins:
+            parent[k] = -1
+        elif not outside[k]:
+            parent[k] = last_in[-1] if rng.random() < chain else last_in[int(rng.integers(0, len(last_in)))]
+        if not outside[k]:
+            last_in.append(k)
+    optimized = rng.random(K) >= new_kf_frac
+    optimized[:n_origins] = True
+    Tcw = se3(K).astype(np.float32)
+    corr = se3(K, rot=0.02, trans=0.15)
+    gba = (corr @ Tcw.astype(np.float64)).astype(np.float32)
+    gba[~optimized] = np.float32(np.nan)                      # mTcwGBA is an empty Mat there; the update must never read it
+    state = rng.choice(np.array([0, 1, 2], np.uint8), P, p=[0.05, 0.8, 0.15]) if P else np.zeros(0, np.uint8)
+    ref = rng.integers(0, K, P).astype(np.int32) if K and P else np.full(P, -1, np.int32)
+    if P:
+        ref[rng.random(P) < 0.03] = -1
+    pos = rng.normal(0, 12.0, (P, 3)).astype(np.float32)
+    pos_gba = (pos + rng.normal(0, 0.05, (P, 3))).astype(np.float32)
+    pos_gba[state != 1] = np.float32(np.nan)
+    return dict(kf_parent=parent, kf_optimized=optimized.astype(np.uint8), kf_Tcw=Tcw, kf_TcwGBA=gba, mp_state=state, mp_ref=ref, mp_pos=pos,
+                mp_pos_gba=pos_gba)

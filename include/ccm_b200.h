@@ -454,6 +454,21 @@ int ccm_bow_assemble(int32_t scoring, int32_t weighting, int32_t n, const uint32
                      uint32_t* fv_node_id, int32_t* fv_node_ptr, uint32_t* fv_feat, int32_t* fv_n_nodes);
 void ccm_voc_destroy(ccm_voc_handle* h);
 
+/* ---- map update after a global BA ------------------------------------------------
+ * Replaces the loop both Map::RunGBA (cslam/src/Map.cpp:1441-1570) and MapMerger::RunGBA (cslam/src/MapMerger.cpp:637-753) run
+ * once MapFusionGBA has returned: the spanning-tree propagation of mTcwGBA to keyframes the BA did not hold, and the correction
+ * of every map point (mPosGBA, or through its reference keyframe).  Flat view of the map:
+ *   kf_parent[k]     index of the keyframe whose GetChilds() holds k; -1 = k is in mvpKeyFrameOrigins; -2 = not in the tree
+ *   kf_optimized[k]  mBAGlobalForKF == nLoopKF (kf_TcwGBA[k] holds the BA's result); origins must be optimised
+ *   kf_Tcw           GetPose() before the update (4x4 row-major f32) = what mTcwBefGBA receives
+ *   kf_TcwGBA        in/out: filled for propagated keyframes; the caller SetPose()s it on every keyframe with kf_visited[k] = 1
+ *   mp_state[i]      0 skip (isBad), 1 mBAGlobalForKF == nLoopKF (take mp_pos_gba), 2 follow reference keyframe mp_ref[i] (-1 none)
+ *   mp_pos_out       the position to SetWorldPos() where mp_corrected[i] = 1 (elsewhere a copy of mp_pos)
+ * Keyframe pass on the host (tree order), point pass on the GPU (one thread per point). */
+int ccm_gba_map_update(int32_t n_kf, const int32_t* kf_parent, const uint8_t* kf_optimized, const float* kf_Tcw, float* kf_TcwGBA,
+                       uint8_t* kf_visited, int32_t n_mp, const uint8_t* mp_state, const int32_t* mp_ref, const float* mp_pos,
+                       const float* mp_pos_gba, float* mp_pos_out, uint8_t* mp_corrected);
+
 #ifdef __cplusplus
 }
 #endif

@@ -963,3 +963,14 @@ def ref_pgo_block():
 def ref_pgo_block_solve(p, **kw):
     """as ref_pgo_solve, with g2o's own BlockSolver_7_3 between the LM driver and the oracle's sparse LDL^T (oracle/ref_pgo_block_wrap.cpp)"""
     return pgo_solve(p, fn=ref_pgo_block().ref_pgo_block_solve, **kw)
+
+
+def gba_map_update(sc, fn=None):
+    """Map::RunGBA's update loop (S/Map.cpp:1441-1570) on the flat map view of ccm_slam_b200.synth.make_map_update; same result layout
+    as ccm_slam_b200.api.gba_map_update.  fn: another entry point of the same signature (tests/host build of the product's header)."""
+    from ccm_slam_b200.api import _map_update_args, _map_update_result
+    a, argv, K, P = _map_update_args(sc)
+    rc = (fn or lib().orc_gba_map_update)(*argv)
+    if rc != 0:
+        raise ValueError("gba_map_update: a map origin has no BA result")
+    return _map_update_result(a, K, P)

@@ -21,9 +21,11 @@ if [ "$mode" = single ]; then
   (CCM_MATCH_WINDOW=1 timeout 120 python -m pytest tests/test_gpu_widen.py -m gpu -x -q 2>&1 | tail -5) > gpurun_out/match_window.log
   # 1d. the shims over the real device entry points next to the reference's ORBmatcher.cpp / Optimizer.cpp (opt-in file)
   (CCM_TEST_UNVALIDATED=1 timeout 120 python -m pytest tests/test_gpu_zz_dropin.py -m gpu -x -q 2>&1 | tail -5) > gpurun_out/dropin_gpu.log
+  # 1e. the map update after a global BA (k_map_update_points), bit for bit against the oracle
+  (CCM_TEST_UNVALIDATED=1 timeout 120 python -m pytest tests/test_gpu_zz_map_update.py -m gpu -x -q 2>&1 | tail -5) > gpurun_out/map_update_gpu.log
   # 2. the whole GPU suite with the current defaults (CTA-128 Schur kernel, new golden / SearchForInitialization tests)
   (timeout 120 python -m pytest tests -m gpu -x -q 2>&1 | tail -5) > gpurun_out/gpu_suite.log
-  cat gpurun_out/prolong_parity.log gpurun_out/match_window.log gpurun_out/dropin_gpu.log gpurun_out/dist_selfwindow_parity.log gpurun_out/prolong_cfg5.log gpurun_out/gpu_suite.log
+  cat gpurun_out/prolong_parity.log gpurun_out/match_window.log gpurun_out/dropin_gpu.log gpurun_out/map_update_gpu.log gpurun_out/dist_selfwindow_parity.log gpurun_out/prolong_cfg5.log gpurun_out/gpu_suite.log
 else
   # 3. row-distributed PCG over peer memory: parity of every rank against the oracle, replicated vs distributed, then one bench line each
   run() { timeout 150 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 "$@"; }
