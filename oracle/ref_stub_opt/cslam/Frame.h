@@ -49,6 +49,7 @@ class MapPoint {
   size_t mCorrectedReference_MM = 0;
   idpair mBAGlobalForKF;
   cv::Mat mPosGBA;
+  bool mbLoopCorrected = false;                                          // MapPoint.h:241
   static std::mutex mGlobalMutex;                                        // MapPoint.h:253
   // storage / record
   cv::Mat mWorldPos;
@@ -78,6 +79,18 @@ class KeyFrame {
     return 0;
   }
   kfptr GetParent(bool bIgnorePoseMutex = false) { (void)bIgnorePoseMutex; return mpParent; }
+  std::set<kfptr> GetChilds() { return mspChildrens; }                   // KeyFrame.h:176
+  cv::Mat GetPoseInverse() {                                             // KeyFrame.h:136; Twc as SetPose leaves it (KeyFrame.cpp:298-306)
+    cv::Mat Rcw = Tcw.rowRange(0, 3).colRange(0, 3), tcw = Tcw.rowRange(0, 3).col(3);
+    cv::Mat Rwc = Rcw.t();
+    cv::Mat Ow = -(Rwc * tcw);
+    cv::Mat Twc = cv::Mat::eye(4, 4, CV_32F);
+    for (int r = 0; r < 3; r++) {
+      for (int c = 0; c < 3; c++) Twc.at<float>(r, c) = Rwc.at<float>(r, c);
+      Twc.at<float>(r, 3) = Ow.at<float>(r);
+    }
+    return Twc;
+  }
   bool hasChild(kfptr pKF) { return mspChildrens.count(pKF) != 0; }
   std::set<kfptr> GetLoopEdges() { return mspLoopEdges; }
   void EraseMapPointMatch(const size_t& idx, bool bLock = false) { (void)bLock; mvpMapPoints[idx] = mpptr(); n_erased++; }
@@ -95,6 +108,8 @@ class KeyFrame {
   idpair mBALocalForKF;
   idpair mBAFixedForKF;
   cv::Mat mTcwGBA;
+  cv::Mat mTcwBefGBA;                                                    // KeyFrame.h:311
+  bool mbLoopCorrected = false;                                          // KeyFrame.h:313
   idpair mBAGlobalForKF;
   float fx = 0, fy = 0, cx = 0, cy = 0, invfx = 0, invfy = 0;
   std::vector<cv::KeyPoint> mvKeysUn;
