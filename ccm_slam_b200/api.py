@@ -385,3 +385,64 @@ def gba_map_update(sc):
     a, argv, K, P = _map_update_args(sc)
     _chk(lib().ccm_gba_map_update(*argv))
     return _map_update_result(a, K, P)
+
+
+class MapMirror:
+    """Persistent flat mirror of the map for the global BA (ccm_mirror_*, include/ccm_b200.h): told about
+    changes as they happen, hands out the ccm_ba_problem MapFusionGBA's flattening (S/Optimizer.cpp:658-787) would build."""
+
+    def __init__(self):
+        L = lib()
+        L.ccm_mirror_rebuilds.restype = C.c_longlong
+        for f in ("ccm_mirror_set_keyframe", "ccm_mirror_erase_keyframe", "ccm_mirror_set_point", "ccm_mirror_erase_point"):
+            getattr(L, f).argtypes = None
+        L.ccm_mirror_set_observation.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_float, C.c_float, C.c_float]
+        L.ccm_mirror_erase_observation.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64]
+        L.ccm_mirror_destroy.argtypes = [C.c_void_p]
+        L.ccm_mirror_rebuilds.argtypes = [C.c_void_p]
+        self._h = C.c_void_p()
+        _chk(L.ccm_mirror_create(C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().ccm_mirror_destroy(self._h); self._h = C.c_void_p()
+
+    def set_keyframe(self, uid, Tcw, intr=None, bad=False):
+        T = np.ascontiguousarray(Tcw, np.float32).reshape(16)
+        k = None if intr is None else np.ascontiguousarray(intr, np.float32)
+        _chk(lib().ccm_mirror_set_keyframe(self._h, C.c_uint64(uid), _p(T), _p(k), int(bad)))
+
+    def erase_keyframe(self, uid):
+        _chk(lib().ccm_mirror_erase_keyframe(self._h, C.c_uint64(uid)))
+
+    def set_point(self, uid, pos, bad=False):
+        x = np.ascontiguousarray(pos, np.float32).reshape(3)
+        _chk(lib().ccm_mirror_set_point(self._h, C.c_uint64(uid), _p(x), int(bad)))
+
+    def erase_point(self, uid):
+        _chk(lib().ccm_mirror_erase_point(self._h, C.c_uint64(uid)))
+
+    def set_observation(self, kf_uid, mp_uid, u, v, inv_sigma2):
+        _chk(lib().ccm_mirror_set_observation(self._h, kf_uid, mp_uid, float(u), float(v), float(inv_sigma2)))
+
+    def erase_observation(self, kf_uid, mp_uid):
+        _chk(lib().ccm_mirror_erase_observation(self._h, kf_uid, mp_uid))
+
+    def rebuilds(self):
+        return lib().ccm_mirror_rebuilds(self._h)
+
+    def problem(self, max_kf_uid, fixed_uids):
+        """-> (BAProblemC over the mirror's own arrays (valid until the next call on the mirror), numpy copies of every array,
+        kf_uid_of_row, mp_uid_of_row)"""
+        fx = np.ascontiguousarray(fixed_uids, np.uint64)
+        prob = BAProblemC(); ku = C.c_void_p(); mu = C.c_void_p()
+        _chk(lib().ccm_mirror_ba_problem(self._h, C.c_uint64(max_kf_uid), _p(fx), len(fx), C.byref(prob), C.byref(ku), C.byref(mu)))
+
+        def arr(ptr, n, t):
+            return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(t)), shape=(n,)).copy() if n else np.zeros(0, np.dtype(t))
+        K, P, E = prob.K, prob.P, prob.E
+        a = dict(poses=arr(prob.poses, K * 7, C.c_double).reshape(K, 7), intr=arr(prob.intr, K * 4, C.c_double).reshape(K, 4),
+                 fixed=arr(prob.fixed, K, C.c_uint8), points=arr(prob.points, P * 3, C.c_double).reshape(P, 3),
+                 obs_kf=arr(prob.obs_kf, E, C.c_int32), obs_mp=arr(prob.obs_mp, E, C.c_int32), obs_uv=arr(prob.obs_uv, E * 2, C.c_float).reshape(E, 2),
+                 obs_w=arr(prob.obs_w, E, C.c_float))
+        return prob, a, arr(ku, K, C.c_uint64), arr(mu, P, C.c_uint64)

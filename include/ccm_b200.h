@@ -469,6 +469,27 @@ int ccm_gba_map_update(int32_t n_kf, const int32_t* kf_parent, const uint8_t* kf
                        uint8_t* kf_visited, int32_t n_mp, const uint8_t* mp_state, const int32_t* mp_ref, const float* mp_pos,
                        const float* mp_pos_gba, float* mp_pos_out, uint8_t* mp_corrected);
 
+/* ---- persistent flat mirror of the map for the global BA -----------------------------
+ * Replaces the per-call flattening at the head of Optimizer::MapFusionGBA (cslam/src/Optimizer.cpp:658-787): the map tells the
+ * mirror about changes where they happen (KeyFrame::SetPose, MapPoint::SetWorldPos, AddObservation / EraseObservation, SetBadFlag;
+ * INTEGRATION.md) and ccm_mirror_ba_problem hands out a ccm_ba_problem over arrays the mirror owns, valid until the next ccm_mirror_*
+ * call on it.  Value changes patch that problem in place; structural changes cost one pass over flat arrays at the next request,
+ * applying the reference's selection rules (keyframes: not bad, uid <= max_kf_uid; edges: both ends selected; points: not bad, at
+ * least one edge).  Rows keep first-insertion order.  uid = mUniqueId.  Host code; one mirror is not thread-safe (the reference
+ * holds LockMapUpdate around a GBA). */
+typedef struct ccm_map_mirror ccm_map_mirror;
+int ccm_mirror_create(ccm_map_mirror** out);
+void ccm_mirror_destroy(ccm_map_mirror* m);
+int ccm_mirror_set_keyframe(ccm_map_mirror* m, uint64_t uid, const float* Tcw /*16*/, const float* intr4 /*fx fy cx cy; may be NULL on update*/, int32_t bad);
+int ccm_mirror_erase_keyframe(ccm_map_mirror* m, uint64_t uid);
+int ccm_mirror_set_point(ccm_map_mirror* m, uint64_t uid, const float* pos3, int32_t bad);
+int ccm_mirror_erase_point(ccm_map_mirror* m, uint64_t uid);
+int ccm_mirror_set_observation(ccm_map_mirror* m, uint64_t kf_uid, uint64_t mp_uid, float u, float v, float inv_sigma2);
+int ccm_mirror_erase_observation(ccm_map_mirror* m, uint64_t kf_uid, uint64_t mp_uid);
+int ccm_mirror_ba_problem(ccm_map_mirror* m, uint64_t max_kf_uid, const uint64_t* fixed_uid, int32_t n_fixed, ccm_ba_problem* out,
+                          const uint64_t** kf_uid_of_row, const uint64_t** mp_uid_of_row);
+long long ccm_mirror_rebuilds(const ccm_map_mirror* m);   /* how many flat passes have run (tests, tuning) */
+
 #ifdef __cplusplus
 }
 #endif
