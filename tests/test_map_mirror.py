@@ -170,3 +170,30 @@ def test_compaction_after_mass_erasure():
     same((a, ku, mu), M.flatten(10 ** 9, {back}))
     assert len(ku) > 10 and len(a["obs_kf"]) > 20
     mir.close()
+
+
+def test_row_order_only_reorders_the_sums(oracle):
+    """the mirror's rows follow insertion order, the reference's follow ids / pointer values: the same BA, summed in another order.
+    A problem fed to the mirror in shuffled order solves (CPU oracle) to the same LM trajectory and the same estimates, matched by uid."""
+    from ccm_slam_b200 import synth
+    p = synth.make_config("small")
+    T = api.poses_to_Tcw_f32(p.poses); pts = p.points.astype(np.float32)
+    base = synth.BAProblem(poses=api.poses_from_Tcw_f32(T), intr=p.intr, fixed=p.fixed, points=pts.astype(np.float64), obs_kf=p.obs_kf, obs_mp=p.obs_mp,
+                           obs_uv=p.obs_uv, obs_w=p.obs_w)
+    rng = np.random.default_rng(5)
+    mir = api.MapMirror()
+    for k in rng.permutation(p.K):
+        mir.set_keyframe(int(k), T[k], p.intr[k].astype(np.float32))
+    for i in rng.permutation(p.P):
+        mir.set_point(int(i), pts[i])
+    for e in rng.permutation(p.E):
+        mir.set_observation(int(p.obs_kf[e]), int(p.obs_mp[e]), p.obs_uv[e, 0], p.obs_uv[e, 1], p.obs_w[e])
+    _, a, ku, mu = mir.problem(10 ** 9, np.flatnonzero(p.fixed))
+    mir.close()
+    assert sorted(ku) == list(range(p.K)) and sorted(mu) == list(range(p.P)) and not np.array_equal(ku, np.arange(p.K))
+    shuffled = synth.BAProblem(poses=a["poses"], intr=a["intr"], fixed=a["fixed"], points=a["points"], obs_kf=a["obs_kf"], obs_mp=a["obs_mp"],
+                               obs_uv=a["obs_uv"], obs_w=a["obs_w"])
+    r0 = oracle.ba_solve(base, iterations=8); r1 = oracle.ba_solve(shuffled, iterations=8)
+    assert len(r0["trace"]) == len(r1["trace"]) and np.allclose(r0["trace"][:, 2], r1["trace"][:, 2], rtol=1e-9)
+    assert np.abs(r1["poses"][np.argsort(ku)] - r0["poses"]).max() < 1e-8
+    assert np.abs(r1["points"][np.argsort(mu)] - r0["points"]).max() < 1e-7
