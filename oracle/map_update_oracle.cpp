@@ -5,8 +5,10 @@
 // (MapMerger::RunGBA) both contain, on a flat view of the map (indices for pointers, the children of a keyframe = the keyframes that
 // name it as parent, in index order — the reference walks a std::set ordered by pointer value, and no result depends on that order).
 // cv::Mat arithmetic: f32 throughout; a product entry is the f32 sum, left to right, of f32 products (cv::gemm's path for inner
-// dimension <= 4).  PARITY UNPINNED for that rounding: OpenCV's sources are not in the reference tree (SURVEY.md §8(c')); the tests
-// also hold the result against an f64 evaluation at a few f32 ulps.
+// dimension <= 4).  PINNED against OpenCV itself: tests/golden/map_update_cv2.npz holds this loop evaluated with cv2.gemm (Python cv2
+// 4.13, the OpenCV generation SURVEY.md §8(c') pins) and tests/test_map_update.py requires bit-for-bit agreement, on the fixture and,
+// where cv2 can be imported, on fresh scenes.  The loop itself (which objects are touched, in which order) is restated from the two
+// member functions, which cannot be compiled apart from their classes; tests/test_shim_map_update.py runs that restatement on objects.
 #include <cstring>
 #include <list>
 #include <vector>

@@ -163,7 +163,8 @@ void orc_ldlt_reset(void* h);
 int orc_ldlt_solve(void* h, int nb, int bs, const int* rowptr, const int* col, const double* val, const double* b, double* x);
 
 /* the map update after a global BA (cslam/src/Map.cpp:1441-1570 = MapMerger.cpp:637-753); arguments as ccm_gba_map_update's
- * (include/ccm_b200.h).  Returns 0, or 1 when an origin has no BA result.  cv::gemm's f32 rounding is restated, not pinned. */
+ * (include/ccm_b200.h).  Returns 0, or 1 when an origin has no BA result.  cv::gemm's f32 rounding pinned against cv2 4.13
+ * (tests/golden/map_update_cv2.npz). */
 int orc_gba_map_update(int32_t n_kf, const int32_t* kf_parent, const uint8_t* kf_optimized, const float* kf_Tcw, float* kf_TcwGBA,
                        uint8_t* kf_visited, int32_t n_mp, const uint8_t* mp_state, const int32_t* mp_ref, const float* mp_pos,
                        const float* mp_pos_gba, float* mp_pos_out, uint8_t* mp_corrected);

@@ -3,9 +3,8 @@
 //
 // The loop lives inside Map::RunGBA (cslam/src/Map.cpp:1441-1570) and MapMerger::RunGBA (cslam/src/MapMerger.cpp:637-753), two
 // member functions that cannot be compiled apart from the ROS-facing rest of their classes; reference_loop() below restates it
-// on the stand-in classes of ref_stub_opt with cv::Mat expressions of the same shape (its Mat products accumulate in double — see
-// ref_stub/opencv2/core/core.hpp — so values are compared at f32-ulp level, the set of touched objects and the order of the setter
-// calls exactly).  mode 1 runs cslam::UpdateMapAfterGBA (the shim; ccm_gba_map_update doubled by the oracle in this library).
+// on the stand-in classes of ref_stub_opt with cv::Mat expressions of the same shape (the stand-in Mat rounds small products as
+// cv::gemm does — ref_stub/opencv2/core/core.hpp — so values, the set of touched objects and the setter calls are all compared exactly).  mode 1 runs cslam::UpdateMapAfterGBA (the shim; ccm_gba_map_update doubled by the oracle in this library).
 #include <cslam/KeyFrame.h>
 #include <cslam/Map.h>
 #include <cslam/MapPoint.h>

@@ -143,9 +143,9 @@ class Mat {
   template <class T> const T& at(int r, int c) const { return reinterpret_cast<const T*>(data + (size_t)r * step)[c]; }
   // InputArray / OutputArray surface
   Mat getMat() const { return *this; }
-  // small dense float algebra (cslam/src/ORBmatcher.cpp composes poses with it).  Evaluated eagerly, products accumulated in
-  // double and rounded to float once.  OpenCV's own gemm may round differently in the last place; the tests that run the reference's
-  // matchers (tests/test_oracle_vs_reference_matchers.py) use poses and points whose arithmetic is exact in float for that reason.
+  // small dense float algebra (cslam/src/ORBmatcher.cpp composes poses with it).  Evaluated eagerly; a product with inner dimension
+  // 2..4 rounds as cv::gemm's small-matrix path does (f32, left to right), larger ones accumulate in double.  The tests that run the
+  // reference's matchers (tests/test_oracle_vs_reference_matchers.py) use poses and points whose arithmetic is exact in float anyway.
   Mat row(int r) const { return (*this)(Rect(0, r, cols, 1)); }
   Mat col(int c) const { return (*this)(Rect(c, 0, 1, rows)); }
   template <class T> T& at(int i) { return rows == 1 ? at<T>(0, i) : at<T>(i, 0); }
@@ -173,6 +173,12 @@ inline Mat operator*(const Mat& a, const Mat& b) {
   Mat m(a.rows, b.cols, CV_32F);
   for (int r = 0; r < a.rows; r++)
     for (int c = 0; c < b.cols; c++) {
+      if (a.cols >= 2 && a.cols <= 4) {   // cv::gemm's small-matrix path: f32 products summed left to right in f32 (checked against cv2 4.13,
+        float s = a.at<float>(r, 0) * b.at<float>(0, c);                                  // tests/test_map_update.py::test_gemm_rounding_is_f32_left_to_right)
+        for (int k = 1; k < a.cols; k++) s = s + a.at<float>(r, k) * b.at<float>(k, c);
+        m.at<float>(r, c) = s;
+        continue;
+      }
       double s = 0;
       for (int k = 0; k < a.cols; k++) s += (double)a.at<float>(r, k) * (double)b.at<float>(k, c);
       m.at<float>(r, c) = (float)s;

@@ -1,8 +1,9 @@
 """CPU suite, SURVEY.md §8(f) rank 1: the map update that follows a global BA (Map::RunGBA, S/Map.cpp:1441-1570 =
 MapMerger::RunGBA, S/MapMerger.cpp:637-753) — spanning-tree propagation of mTcwGBA, correction of every map point.
 
- * the oracle (oracle/map_update_oracle.cpp) against an f64 numpy evaluation of the same rules: a few f32 ulps (the oracle's
-   f32 rounding restates cv::gemm and is not pinned — OpenCV is not in the reference tree);
+ * the oracle (oracle/map_update_oracle.cpp) against OpenCV's own arithmetic — the loop evaluated with cv2.gemm 4.13, as a committed
+   fixture (tests/golden/map_update_cv2.npz + its generator) and live where cv2 imports: bit for bit;
+ * the oracle against an f64 numpy evaluation of the same rules: a few f32 ulps;
  * the product's arithmetic (csrc/map_update_math.cuh: the host keyframe pass as shipped, the kernel body as a plain loop;
    tests/host/map_update_host.cpp, g++) against the oracle: bit for bit;
  * which keyframes / points are touched at all: exact.
@@ -138,3 +139,59 @@ def test_library_entry_point_needs_a_device():
     if api.device_count() == 0:
         with pytest.raises(api.CCMError):
             api.gba_map_update(synth.make_map_update(K=10, P=10, seed=1))
+
+
+# ---- the pin: OpenCV's own arithmetic -------------------------------------------------------------------------------------------
+def _golden_cases():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_map_update_golden", os.path.join(HERE, "golden", "make_map_update_golden.py"))
+    mod = importlib.util.module_from_spec(spec); spec.loader.exec_module(mod)
+    return mod
+
+
+def _same_as(r, w):
+    vis = w["kf_visited"].astype(bool)
+    assert np.array_equal(r["kf_visited"], w["kf_visited"]) and np.array_equal(r["mp_corrected"], w["mp_corrected"])
+    assert np.array_equal(r["kf_TcwGBA"][vis], w["kf_TcwGBA"][vis])
+    assert np.array_equal(r["mp_pos"], w["mp_pos"], equal_nan=True)
+
+
+def test_oracle_reproduces_the_opencv_fixture(oracle, host):
+    """tests/golden/map_update_cv2.npz: the loop evaluated with cv2.gemm (4.13) for every cv::Mat product — bit for bit, for the oracle
+    and for the product's arithmetic run on the host"""
+    mod = _golden_cases()
+    z = np.load(os.path.join(HERE, "golden", "map_update_cv2.npz"))
+    for n, kw in enumerate(mod.CASES):
+        sc = synth.make_map_update(**kw)
+        w = {k: z["case%d_%s" % (n, k)] for k in ("kf_TcwGBA", "kf_visited", "mp_pos", "mp_corrected")}
+        _same_as(oracle.gba_map_update(sc), w)
+        _same_as(oracle.gba_map_update(sc, fn=host), w)
+        assert w["mp_corrected"].sum() > 100 and (w["kf_visited"] == 1).sum() > 20
+
+
+@pytest.mark.parametrize("kw", [dict(K=150, P=2500, seed=31), dict(K=300, P=1000, seed=32, chain=1.0, n_origins=1, new_kf_frac=0.5),
+                                dict(K=25, P=3000, seed=33, new_kf_frac=0.6, n_origins=3)])
+def test_oracle_against_live_opencv(oracle, kw):
+    """the same witness on fresh scenes, where cv2 can be imported (it cannot be assumed on every box: the fixture above travels)"""
+    pytest.importorskip("cv2")
+    mod = _golden_cases()
+    sc = synth.make_map_update(**kw)
+    _same_as(oracle.gba_map_update(sc), mod.cv2_update(sc))
+
+
+def test_gemm_rounding_is_f32_left_to_right():
+    """the one fact the restatement rests on, checked directly: cv::gemm with inner dimension 3 or 4 sums f32 products left to right in f32"""
+    cv2 = pytest.importorskip("cv2")
+    rng = np.random.default_rng(8)
+    for shape in ((4, 4, 4), (3, 3, 1), (3, 3, 3), (4, 4, 1)):
+        for _ in range(300):
+            A = (rng.normal(0, 1, shape[:2]) * 10.0 ** rng.integers(-3, 4)).astype(np.float32)
+            B = (rng.normal(0, 1, (shape[1], shape[2])) * 10.0 ** rng.integers(-3, 4)).astype(np.float32)
+            want = np.zeros((shape[0], shape[2]), np.float32)
+            for i in range(shape[0]):
+                for j in range(shape[2]):
+                    s = np.float32(A[i, 0] * B[0, j])
+                    for k in range(1, shape[1]):
+                        s = np.float32(s + np.float32(A[i, k] * B[k, j]))
+                    want[i, j] = s
+            assert np.array_equal(cv2.gemm(A, B, 1.0, None, 0.0), want)
