@@ -242,7 +242,7 @@ std::atomic<int> g_schur_override{-1};  // ccm_ba_debug_set_schur_mode
 int schur_mode() {
   static const int env_mode = [] {
     const char* v = getenv("CCM_SCHUR");
-    if (!v) return 1;
+    if (!v) return 8;
     if (!strcmp(v, "gather") || !strcmp(v, "0")) return 0;
     if (!strcmp(v, "mma")) return 1;
     const int m = atoi(v);
@@ -273,7 +273,8 @@ void launch_schur(ccm_ba_handle* h, cudaStream_t s) {
     case 6: launch_schur_mma<8, 64>(h, s); break;     // not yet measured: fewer warps share a CTA's lifetime (lists differ in length)
     case 7: launch_schur_mma<16, 128>(h, s); break;   // not yet measured
     case 8: launch_schur_mma<8, 128, true>(h, s); break;   // not yet measured: product entries prefetched one batch ahead
-    default: launch_schur_mma<8, 128>(h, s); break;
+    case 1: launch_schur_mma<8, 128>(h, s); break;
+    default: launch_schur_mma<8, 128, true>(h, s); break;   // 8.43 ms vs 8.73 ms without the prefetch (profiles/r2/prolong_cfg5.log)
   }
 }
 
@@ -747,7 +748,7 @@ void build(ccm_ba_handle* h, const ccm_ba_problem* p) {
   // coarse space: <= 128 aggregates for small systems, <= 384 for long trajectories where the smooth modes dominate the
   // iteration count; the inverse is refreshed every 2nd / 4th solve (measured sweeps: tools/ba_probe.py with CCM_PCG_NC/REFRESH)
   // CCM_PCG_PROLONG=1: piecewise-linear prolongation (pcg.cuh); half the coarse nodes then already beat the constant P
-  h->pcg_prolong = env_int("CCM_PCG_PROLONG", 0) ? 1 : 0;
+  h->pcg_prolong = env_int("CCM_PCG_PROLONG", 1) ? 1 : 0;  // default since round 2 (cfg5: 1538 -> 617 PCG iterations per Global BA, profiles/r2/prolong_cfg5.log)
   pcg_coarse_shape(Kf, env_int("CCM_PCG_NC", Kf >= 4096 ? (h->pcg_prolong ? 192 : 384) : 128), &h->pcg_agg, &h->pcg_nc);
   h->pcg_refresh = std::max(1, env_int("CCM_PCG_REFRESH", Kf >= 4096 ? 4 : 2));
   {

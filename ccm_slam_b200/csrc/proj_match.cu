@@ -287,7 +287,7 @@ __global__ void __launch_bounds__(256) k_window_best(const WinQuery* __restrict_
 }
 
 bool window_on_device() {
-  static const bool on = [] { const char* v = getenv("CCM_MATCH_WINDOW"); return v && atoi(v) != 0; }();
+  static const bool on = [] { const char* v = getenv("CCM_MATCH_WINDOW"); return !v || atoi(v) != 0; }();  // default on (validated on B200, profiles/r2/match_window.log); CCM_MATCH_WINDOW=0: full matrix + host selection
   return on;
 }
 

@@ -14,9 +14,8 @@ import pytest
 from tests import test_oracle_vs_reference_matchers as T
 from tests.test_shim_dropin import same
 
-# Opt-in as a whole (CCM_TEST_UNVALIDATED=1, tools/validate_prepared.sh) until this file has been seen green on a device once: it loads a
-# second native library into the test process, and nothing in it could be executed where it was written (no GPU).
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("CCM_TEST_UNVALIDATED") != "1", reason="first device run pending (set CCM_TEST_UNVALIDATED=1)")]
+# Loads a second native library (the shims linked against the product) into the test process.
+pytestmark = pytest.mark.gpu   # first device run: round 2, profiles/r2/dropin_gpu.log
 
 
 class SideBySideGPU:

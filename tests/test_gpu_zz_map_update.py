@@ -8,7 +8,7 @@ import pytest
 
 from ccm_slam_b200 import api, synth
 
-pytestmark = [pytest.mark.gpu, pytest.mark.skipif(os.environ.get("CCM_TEST_UNVALIDATED") != "1", reason="first device run pending (set CCM_TEST_UNVALIDATED=1)")]
+pytestmark = pytest.mark.gpu   # first device run: round 2, profiles/r2/map_update_gpu.log
 
 
 @pytest.mark.parametrize("kw", [dict(K=200, P=5000, seed=0), dict(K=1, P=50, seed=1, n_origins=1), dict(K=300, P=0, seed=3),
