@@ -261,6 +261,12 @@ class BAHandle:
         _chk(lib().ccm_ba_debug_schur(self._h, int(robust), C.c_double(huber_delta), C.c_double(lam), _p(S), _p(bs), _p(dxp), _p(dxl), C.byref(it), C.byref(rr)))
         return dict(S=S, bschur=bs, dx_pose=dxp, dx_point=dxl, pcg_iters=it.value, pcg_relres=rr.value)
 
+    def pcg_cycles(self):
+        """SM-clock cycles CTA 0 of the PCG kernel spent per phase (handle created with CCM_PCG_PROF=1): set-up, product, coarse, precondition, ..."""
+        c = np.zeros(8, np.int64)
+        _chk(lib().ccm_ba_debug_pcg_cycles(self._h, _p(c)))
+        return [int(x) for x in c]
+
     def time_kernel(self, which, reps=5, huber_delta=HUBER_GBA, lam=1.0):
         ms = C.c_double()
         _chk(lib().ccm_ba_time_kernel(self._h, which, reps, C.c_double(huber_delta), C.c_double(lam), C.byref(ms)))
@@ -430,6 +436,11 @@ class MapMirror:
 
     def rebuilds(self):
         return lib().ccm_mirror_rebuilds(self._h)
+
+    def set_min_edges(self, n):
+        """2 = MapFusionGBA's point rule (default), 1 = BundleAdjustmentClient's"""
+        lib().ccm_mirror_set_min_edges.argtypes = [C.c_void_p, C.c_int32]
+        _chk(lib().ccm_mirror_set_min_edges(self._h, int(n)))
 
     def problem(self, max_kf_uid, fixed_uids):
         """-> (BAProblemC over the mirror's own arrays (valid until the next call on the mirror), numpy copies of every array,

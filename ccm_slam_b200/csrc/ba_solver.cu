@@ -14,6 +14,7 @@
 
 #include "ba_kernels.cuh"
 #include "common.cuh"
+#include "pcg2.cuh"
 #include "pcg_dist.cuh"
 
 namespace ccm {
@@ -95,6 +96,20 @@ struct ccm_ba_handle {
     int grid = 0, block = 256;
     long long timeout_cycles = 0;
   } dist;
+  // second-generation PCG (pcg2.cuh): TMA-streamed product, three synchronisations per iteration, rows distributed over the ranks
+  struct Pcg2 {
+    bool on = false;
+    Pcg2Layout lay{};
+    char* window = nullptr;          // own exchange window (plain cudaMalloc: exportable through cudaIpc)
+    std::vector<char*> peer;         // every rank's window as mapped here; peer[rank] == window
+    DevBuf<char*> d_win;
+    DevBuf<int> items, cta_row, cta_item;
+    DevBuf<double> yc, tpart;
+    int r0 = 0, r1 = 0, rank = 0, grid = 1;
+    long long nitems = 0;
+    unsigned long long launches = 0;
+    long long timeout_cycles = 0;
+  } p2;
   // scalars / partials
   DevBuf<double> partials, scal;  // scal: [0] chi2_trial [1] scale_l [2] scale_p [3..5] pcg status
   double* h_scal = nullptr;       // pinned, 16 doubles
@@ -123,6 +138,9 @@ struct ccm_ba_handle {
     for (size_t k = 0; k < dist.peer.size(); k++)
       if (dist.peer[k] && (int)k != dist.rank) cudaIpcCloseMemHandle(dist.peer[k]);
     if (dist.window) cudaFree(dist.window);
+    for (size_t k = 0; k < p2.peer.size(); k++)
+      if (p2.peer[k] && (int)k != p2.rank) cudaIpcCloseMemHandle(p2.peer[k]);
+    if (p2.window) cudaFree(p2.window);
     for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
     if (h_scal) cudaFreeHost(h_scal);
     if (stream) cudaStreamDestroy(stream);
@@ -313,6 +331,37 @@ void step_pcg(ccm_ba_handle* h, double tol, int max_iter) {
   a.prolong = h->pcg_prolong;
   a.coarse_mode = (h->pcg_coarse_valid && h->pcg_age < h->pcg_refresh) ? 2 : 1;
   h->pcg_last_mode = a.coarse_mode;
+  if (h->p2.on) {
+    ccm_ba_handle::Pcg2& d = h->p2;
+    if (a.coarse_mode == 1 && a.agg > 0) {  // (re)build the coarse inverse with k_pcg's set-up phase: no iteration
+      PcgArgs setup = a;
+      setup.max_iter = 0;
+      void* sargs[] = {&setup};
+      CCM_CUDA(cudaLaunchCooperativeKernel(h->pcg_fn, dim3(h->pcg_grid), dim3(h->pcg_block), sargs, 0, s));
+      CCM_LAUNCHED();
+    }
+    const int nC = a.agg > 0 ? 6 * a.nc : 0;
+    Pcg2Args b;
+    b.n = h->Kf; b.val = h->s_val.p; b.items = d.items.p; b.cta_row = d.cta_row.p; b.cta_item = d.cta_item.p;
+    b.Minv = h->Minv.p; b.b = h->bschur.p; b.x = h->x.p; b.r = h->pr.p; b.q = h->pq.p; b.p = h->pp.p;
+    b.partials = h->pcg_partials.p; b.bar = h->pcg_bar.p; b.tol = tol; b.max_iter = max_iter; b.status = h->pcg_status.p;
+    b.agg = a.agg; b.nc = a.nc; b.prolong = a.prolong;
+    b.Ainv = nC > 0 ? ((((nC + GJB - 1) / GJB) & 1) ? h->pcg_Ac.p + (size_t)nC * nC : h->pcg_Ac.p) : nullptr;
+    b.yc = d.yc.p; b.tpart = d.tpart.p;
+    b.rank = h->rank; b.nranks = h->nranks; b.r0 = d.r0; b.r1 = d.r1; b.win = d.d_win.p;
+    b.off_z = d.lay.off_z; b.off_scal = d.lay.off_scal; b.off_t = d.lay.off_t; b.off_x = d.lay.off_x;
+    b.off_flags = d.lay.off_flags; b.off_ctl = d.lay.off_ctl;
+    b.epoch0 = (++d.launches) << 24;   // every rank issues the same sequence of solves: the epochs line up and only grow
+    b.timeout_cycles = d.timeout_cycles;
+    b.prof = h->pcg_prof.p;
+    CCM_CUDA(cudaMemsetAsync(h->pcg_bar.p, 0, 2 * sizeof(unsigned), s));
+    CCM_CUDA(cudaMemsetAsync(d.tpart.p, 0, d.tpart.bytes(), s));
+    CCM_CUDA(cudaMemsetAsync(d.window + d.lay.off_ctl, 0, sizeof(unsigned), s));
+    void* bargs[] = {&b};
+    CCM_CUDA(cudaLaunchCooperativeKernel((void*)k_pcg2, dim3(d.grid), dim3(P2_TPB), bargs, P2_SMEM_BYTES, s));
+    CCM_LAUNCHED();
+    return;
+  }
   if (h->dist.on) {
     ccm_ba_handle::DistPcg& d = h->dist;
     if (a.coarse_mode == 1 && a.agg > 0) {  // (re)build the coarse inverse with the replicated kernel: set-up only, no iteration
@@ -409,8 +458,105 @@ void setup_pcg_dist(ccm_ba_handle* h) {
   d.on = true;
 }
 
+// pcg2.cuh set-up: own rows, item records, CTA cuts, exchange window (IPC-mapped on every rank when nranks > 1).
+// CCM_PCG_IMPL=1 keeps the first-generation kernel (replicated solve on several ranks).
+void setup_pcg2(ccm_ba_handle* h, const std::vector<int>& rowptr) {
+  if (env_int("CCM_PCG_IMPL", 2) != 2 || h->Kf < 1 || h->Kf < h->nranks) return;
+  if (h->pcg_agg > 0 && 6 * h->pcg_nc > P2_MAX_NC) return;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+  ccm_ba_handle::Pcg2& d = h->p2;
+  cudaStream_t s = h->stream;
+  const int N = h->nranks, Kf = h->Kf;
+  d.rank = h->rank;
+  const int nC = h->pcg_agg > 0 ? 6 * h->pcg_nc : 0;
+  // contiguous block rows per rank, cut where the block-count prefix crosses k * nnzb / N
+  auto cut = [&](int k) {
+    if (k <= 0) return 0;
+    if (k >= N) return Kf;
+    const long long want = (long long)rowptr[Kf] * k / N;
+    return (int)(std::lower_bound(rowptr.begin(), rowptr.end(), (int)want) - rowptr.begin());
+  };
+  d.r0 = std::min(cut(h->rank), Kf);
+  d.r1 = std::min(std::max(cut(h->rank + 1), d.r0), Kf);
+  const int rows = d.r1 - d.r0;
+  // items: <= 16 consecutive blocks of one row
+  std::vector<int> row_item((size_t)rows + 1, 0);
+  for (int a = 0; a < rows; a++) row_item[a + 1] = row_item[a] + (rowptr[d.r0 + a + 1] - rowptr[d.r0 + a] + P2_ITEM_BLOCKS - 1) / P2_ITEM_BLOCKS;
+  d.nitems = row_item[rows];
+  CCM_CUDA(cudaFuncSetAttribute((const void*)k_pcg2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)P2_SMEM_BYTES));  // per device
+  int per_sm = 0;
+  CCM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)k_pcg2, P2_TPB, P2_SMEM_BYTES));
+  CCM_REQUIRE(per_sm >= 1, "k_pcg2 does not fit on an SM");
+  // one CTA per SM; small systems use fewer CTAs (>= one item per warp) so that the grid barriers stay cheap
+  d.grid = (int)std::max<long long>(1, std::min<long long>(sm_count(), (d.nitems + P2_W - 1) / P2_W));
+  d.grid = std::max(1, env_int("CCM_PCG2_GRID", d.grid));
+  d.grid = std::min(d.grid, sm_count() * per_sm);
+  std::vector<int> cta_row((size_t)d.grid + 1), cta_item((size_t)d.grid + 1);
+  for (int c = 0; c <= d.grid; c++) {
+    int a = rows;
+    if (c < d.grid) {
+      const long long want = d.nitems * c / d.grid;
+      a = (int)(std::lower_bound(row_item.begin(), row_item.end(), (int)want) - row_item.begin());
+      a = std::min(a, rows);
+    }
+    cta_row[c] = d.r0 + a;
+    cta_item[c] = row_item[a];
+  }
+  cta_row[0] = d.r0; cta_item[0] = 0;
+  DevBuf<int> d_row_item;
+  upload_vec(d_row_item, row_item, s);
+  upload_vec(d.cta_row, cta_row, s);
+  upload_vec(d.cta_item, cta_item, s);
+  d.items.alloc(std::max<size_t>((size_t)d.nitems * P2_REC, 1));
+  if (rows > 0) {
+    k_pcg2_items<<<div_up(rows, 128), 128, 0, s>>>(h->s_rowptr.p, h->s_col.p, d_row_item.p, d.r0, d.r1, d.items.p);
+    CCM_LAUNCHED();
+  }
+  d.yc.alloc_zero(std::max<size_t>((size_t)2 * nC, 1), s);
+  d.tpart.alloc_zero(std::max<size_t>((size_t)2 * nC, 1), s);
+  if ((size_t)3 * d.grid > h->pcg_partials.n) h->pcg_partials.alloc((size_t)3 * d.grid);
+  if (h->pcg_bar.n < 2) h->pcg_bar.alloc_zero(2, s);
+  // exchange window
+  d.lay = pcg2_layout(Kf, N, nC);
+  CCM_CUDA(cudaMalloc((void**)&d.window, d.lay.bytes));
+  CCM_CUDA(cudaMemset(d.window, 0, d.lay.bytes));
+  d.peer.assign(N, nullptr);
+  d.peer[h->rank] = d.window;
+  DevBuf<double> tmp;
+  if (N > 1) {
+    // the 64-byte IPC handles travel through the existing all-reduce, one double per byte (exact: each slot has one writer)
+    cudaIpcMemHandle_t mine;
+    CCM_CUDA(cudaIpcGetMemHandle(&mine, d.window));
+    std::vector<double> enc((size_t)N * 64, 0.0);
+    for (int i = 0; i < 64; i++) enc[(size_t)h->rank * 64 + i] = (double)reinterpret_cast<const unsigned char*>(&mine)[i];
+    tmp.alloc(enc.size());
+    CCM_CUDA(cudaMemcpyAsync(tmp.p, enc.data(), enc.size() * sizeof(double), cudaMemcpyHostToDevice, s));
+    allreduce_f64(tmp.p, enc.size(), 0, s);
+    CCM_CUDA(cudaMemcpyAsync(enc.data(), tmp.p, enc.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CCM_CUDA(cudaStreamSynchronize(s));
+    for (int k = 0; k < N; k++) {
+      if (k == h->rank) continue;
+      cudaIpcMemHandle_t hk;
+      for (int i = 0; i < 64; i++) reinterpret_cast<unsigned char*>(&hk)[i] = (unsigned char)enc[(size_t)k * 64 + i];
+      void* ptr = nullptr;
+      CCM_CUDA(cudaIpcOpenMemHandle(&ptr, hk, cudaIpcMemLazyEnablePeerAccess));
+      d.peer[k] = static_cast<char*>(ptr);
+    }
+  }
+  d.d_win.alloc(N);
+  CCM_CUDA(cudaMemcpyAsync(d.d_win.p, d.peer.data(), sizeof(char*) * N, cudaMemcpyHostToDevice, s));
+  int khz = 0;
+  CCM_CUDA(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->device));
+  d.timeout_cycles = (long long)env_int("CCM_PCG_DIST_TIMEOUT_MS", 2000) * std::max(khz, 1000000);
+  if (N > 1) {  // every rank must have mapped every window before anybody stores into one: a last all-reduce is the fence
+    allreduce_f64(tmp.p, 1, 0, s);
+  }
+  CCM_CUDA(cudaStreamSynchronize(s));  // the staging vectors die at the end of this scope
+  d.on = true;
+}
+
 // trial state + gain-ratio denominator + chi2 of the trial state -> scal[0..5]
-void step_update_and_residual(ccm_ba_handle* h, double lambda, int robust, double delta, double* dx_points) {
+void step_update_and_residual(ccm_ba_handle* h, double lambda, int robust, double delta, double* dx_points, bool stop_local = false) {
   cudaStream_t s = h->stream;
   const int g1 = grid_stride(h->K);
   size_t ev0 = h->profile ? ev_record(h) : 0;
@@ -429,7 +575,15 @@ void step_update_and_residual(ccm_ba_handle* h, double lambda, int robust, doubl
   CCM_LAUNCHED();
   sum_partials_to(h, g3, h->scal.p + 0);
   if (h->profile) { size_t ev1 = ev_record(h); h->spans.push_back({CCM_BA_K_RESIDUAL, ev0, ev1}); }
-  if (h->nranks > 1) allreduce_f64(h->scal.p, 2, 0, s);
+  if (h->nranks > 1) {
+    // one all-reduce carries [chi2, scale_l, scale_p, stop]: scale_p is replicated (only rank 0 contributes it, so the sum is exact),
+    // stop is this rank's view of the caller's force-stop flag -> every rank takes the same decision (a flag seen by one rank a
+    // trial earlier than by its peers would otherwise desynchronise the collectives and hang the job)
+    if (h->rank != 0) CCM_CUDA(cudaMemsetAsync(h->scal.p + 2, 0, sizeof(double), s));
+    h->h_scal[12] = stop_local ? 1.0 : 0.0;
+    CCM_CUDA(cudaMemcpyAsync(h->scal.p + 3, h->h_scal + 12, sizeof(double), cudaMemcpyHostToDevice, s));
+    allreduce_f64(h->scal.p, 4, 0, s);
+  }
   h->pose_eval = h->pose_trial;
   h->pt_eval = h->pt_trial;
 }
@@ -732,7 +886,7 @@ void build(ccm_ba_handle* h, const ccm_ba_problem* p) {
   const size_t nv = std::max((size_t)Kf * 6, (size_t)1);
   h->x.alloc_zero(nv, s); h->pr.alloc(nv); h->pz.alloc(nv); h->pp.alloc(2 * nv); h->pq.alloc(nv);
   h->dxl.alloc(std::max((size_t)Pl * 3, (size_t)1));
-  h->pcg_status.alloc_zero(4, s); h->pcg_bar.alloc_zero(1, s); h->jac_fail.alloc_zero(1, s);
+  h->pcg_status.alloc_zero(4, s); h->pcg_bar.alloc_zero(2, s); h->jac_fail.alloc_zero(1, s);
   // one warp per block row: one fat CTA per SM (cheap grid barrier) when the rows fill the chip, otherwise 256-thread CTAs
   // (two per SM) so that a small system still spreads over many SMs.  512x1 and 256x2 leave the product loop 128 registers.
   h->pcg_block = ((long long)Kf * 32 >= (long long)sm_count() * PCG_TPB) ? env_int("CCM_PCG_BLOCK", 512) : 256;
@@ -755,7 +909,8 @@ void build(ccm_ba_handle* h, const ccm_ba_problem* p) {
     const size_t nC = (size_t)6 * h->pcg_nc;
     h->pcg_Ac.alloc(std::max(2 * nC * nC, (size_t)1)); h->pcg_rc.alloc(std::max(2 * nC, (size_t)1)); h->pcg_yc.alloc(std::max(nC, (size_t)1));
   }
-  setup_pcg_dist(h);
+  setup_pcg2(h, h_rowptr);
+  if (!h->p2.on) setup_pcg_dist(h);
   h->partials.alloc((size_t)sm_count() * 8 + 8);
   h->scal.alloc_zero(16, s);
   h->rep_chi2.alloc(std::max(El, 1)); h->rep_depth.alloc(std::max(El, 1));
@@ -818,8 +973,12 @@ void optimize(ccm_ba_handle* h, const ccm_ba_options* o, ccm_ba_result* r) {
   CCM_CUDA(cudaSetDevice(h->device));
   const double T0 = now_ms();
   cudaStream_t s = h->stream;
-  cudaEvent_t evA, evB;  // device-side bracket of the whole LM loop
-  CCM_CUDA(cudaEventCreate(&evA)); CCM_CUDA(cudaEventCreate(&evB));
+  struct EventPair {  // device-side bracket of the whole LM loop; destroyed on every exit path
+    cudaEvent_t a = nullptr, b = nullptr;
+    ~EventPair() { if (a) cudaEventDestroy(a); if (b) cudaEventDestroy(b); }
+  } ev;
+  CCM_CUDA(cudaEventCreate(&ev.a)); CCM_CUDA(cudaEventCreate(&ev.b));
+  cudaEvent_t evA = ev.a, evB = ev.b;
   CCM_CUDA(cudaEventRecord(evA, s));
   const int robust = o->robust ? 1 : 0;
   const double delta = o->huber_delta;
@@ -831,7 +990,19 @@ void optimize(ccm_ba_handle* h, const ccm_ba_options* o, ccm_ba_result* r) {
   h->pcg_coarse_valid = false;  // every optimize() starts with a fresh coarse inverse
   r->trace_len = 0; r->iters_done = 0; r->trials_total = 0; r->pcg_iters_total = 0; r->pcg_not_converged = 0;
   r->chi2_initial = r->chi2_final = 0; r->lambda_final = 0;
-  auto terminate = [&]() { return o->stop && *o->stop; };
+  // force-stop flag (g2o terminate()): read locally on one rank; on several ranks the decision is collective (it rides in the
+  // per-trial all-reduce, plus one all-reduce before the first iteration)
+  auto stop_local = [&]() { return o->stop && *o->stop; };
+  bool stop_all = false;
+  if (h->nranks > 1) {
+    h->h_scal[12] = stop_local() ? 1.0 : 0.0;
+    CCM_CUDA(cudaMemcpyAsync(h->scal.p + 3, h->h_scal + 12, sizeof(double), cudaMemcpyHostToDevice, s));
+    allreduce_f64(h->scal.p + 3, 1, 2, s);
+    CCM_CUDA(cudaMemcpyAsync(h->h_scal + 13, h->scal.p + 3, sizeof(double), cudaMemcpyDeviceToHost, s));
+    CCM_CUDA(cudaStreamSynchronize(s));
+    stop_all = h->h_scal[13] > 0.0;
+  }
+  auto terminate = [&]() { return h->nranks > 1 ? stop_all : stop_local(); };
   int ret_iters = 0;
   if (h->Kf == 0 || h->E == 0) {
     // g2o: landmarks-only graphs are still optimised, but every cslam call site has free poses; keep it simple
@@ -866,13 +1037,15 @@ void optimize(ccm_ba_handle* h, const ccm_ba_options* o, ccm_ba_result* r) {
       step_schur(h);
       step_finalize(h, lambda);
       step_pcg(h, pcg_tol, pcg_max);
-      step_update_and_residual(h, lambda, robust, delta, nullptr);
+      step_update_and_residual(h, lambda, robust, delta, nullptr, stop_local());
       CCM_CUDA(cudaMemcpyAsync(h->h_scal, h->scal.p, 3 * sizeof(double), cudaMemcpyDeviceToHost, s));
+      if (h->nranks > 1) CCM_CUDA(cudaMemcpyAsync(h->h_scal + 13, h->scal.p + 3, sizeof(double), cudaMemcpyDeviceToHost, s));
       CCM_CUDA(cudaMemcpyAsync(h->h_scal + 3, h->pcg_status.p, 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
       CCM_CUDA(cudaMemcpyAsync(h->h_scal + 7, h->jac_fail.p, sizeof(int), cudaMemcpyDeviceToHost, s));
       CCM_CUDA(cudaStreamSynchronize(s));
       if (h->profile) collect_spans(h);
       tempChi = h->h_scal[0];
+      if (h->nranks > 1) stop_all = h->h_scal[13] > 0.0;
       const int pcg_it = (int)h->h_scal[3];
       const int pcg_flag = (int)h->h_scal[5];
       int jfail;
@@ -925,7 +1098,6 @@ void optimize(ccm_ba_handle* h, const ccm_ba_options* o, ccm_ba_result* r) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, evA, evB);
     r->t_optimize_event_ms = ms;
-    cudaEventDestroy(evA); cudaEventDestroy(evB);
   }
   const double T1 = now_ms();
   download_state(h, r);

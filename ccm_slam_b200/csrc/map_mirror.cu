@@ -11,7 +11,10 @@
 //     ONE pass over flat arrays (no pointers, no locks, no map copies) that applies the reference's selection rules:
 //       keyframes  alive, not bad, uid <= max_kf_uid                       (S/Optimizer.cpp:693-706, :733)
 //       edges      both ends selected                                       (S/Optimizer.cpp:727-771; dangling observations are dropped)
-//       points     alive, not bad, at least one selected edge               (S/Optimizer.cpp:716-786: nEdges == 0 removes the vertex)
+//       points     alive, not bad, >= min_edges observations in all and >= min_edges selected edges; min_edges = 2 is MapFusionGBA's
+//                  rule (S/Optimizer.cpp:722-740: observations.size() < 2 || nEdges < 2 skips the point), 1 is
+//                  BundleAdjustmentClient's (:117-160: nEdges == 0 removes the vertex); ccm_mirror_set_min_edges, default 2
+//     edges are emitted grouped by point row (counting sort), the order ccm_ba_create's fast path wants;
 //     rows keep first-insertion order (erase + insert again moves to the end), so the result is deterministic — unlike the
 //     reference's, whose edge order follows pointer values (SURVEY.md §7 "hard parts"); BA parity is tolerance-based for that reason.
 // Poses are converted once per SetPose with ccm_pose_from_Tcw_f32 (Converter::toSE3Quat), points widened f32 -> f64 as
@@ -44,6 +47,7 @@ struct ccm_map_mirror {
   std::vector<float> obs_uv, obs_w;
   std::vector<uint64_t> kf_uid_of_row, mp_uid_of_row;
   long long rebuilds = 0;
+  int min_edges = 2;
 
   void compact() {   // drop dead slots once they outnumber the living; slot numbers change, maps are rebuilt
     if (dead * 2 < kfs.size() + mps.size() + obs.size() + 64) return;
@@ -73,20 +77,30 @@ struct ccm_map_mirror {
       for (int i = 0; i < n_fixed; i++) fx |= fixed_uid[i] == k.uid;
       fixed.push_back(fx); kf_uid_of_row.push_back(k.uid);
     }
-    std::vector<int> nedges(mps.size(), 0);
-    for (const Obs& o : obs)
-      if (o.alive && kfs[o.kf].alive && kfs[o.kf].row >= 0 && mps[o.mp].alive && !mps[o.mp].bad) nedges[o.mp]++;
+    int nedges_prev = 0;
+    std::vector<int> nedges(mps.size(), 0), nobs(mps.size(), 0);
+    for (const Obs& o : obs) {
+      if (!o.alive || !kfs[o.kf].alive || !mps[o.mp].alive || mps[o.mp].bad) continue;
+      nobs[o.mp]++;                                              // observations.size(): every observation the point still holds
+      if (kfs[o.kf].row >= 0) nedges[o.mp]++;                    // nEdges: those whose keyframe is in the problem
+    }
+    std::vector<int> start;                                       // first edge of every point row (counting sort by point row)
     for (size_t i = 0; i < mps.size(); i++) {
       MP& m = mps[i];
       m.row = -1;
-      if (!m.alive || m.bad || nedges[i] == 0) continue;
+      if (!m.alive || m.bad || nobs[i] < min_edges || nedges[i] < min_edges || nedges[i] == 0) continue;
       m.row = (int)mp_uid_of_row.size();
       points.insert(points.end(), m.pos, m.pos + 3); mp_uid_of_row.push_back(m.uid);
+      start.push_back(start.empty() ? 0 : start.back() + nedges_prev);
+      nedges_prev = nedges[i];
     }
-    for (const Obs& o : obs) {
-      if (!o.alive || !kfs[o.kf].alive || kfs[o.kf].row < 0 || mps[o.mp].row < 0) continue;
-      obs_kf.push_back(kfs[o.kf].row); obs_mp.push_back(mps[o.mp].row);
-      obs_uv.push_back(o.u); obs_uv.push_back(o.v); obs_w.push_back(o.w);
+    const size_t E = start.empty() ? 0 : (size_t)start.back() + nedges_prev;
+    obs_kf.resize(E); obs_mp.resize(E); obs_uv.resize(2 * E); obs_w.resize(E);
+    for (const Obs& o : obs) {                                    // insertion order is kept inside every point's group
+      if (!o.alive || !kfs[o.kf].alive || kfs[o.kf].row < 0 || !mps[o.mp].alive || mps[o.mp].row < 0) continue;
+      const size_t e = (size_t)start[mps[o.mp].row]++;
+      obs_kf[e] = kfs[o.kf].row; obs_mp[e] = mps[o.mp].row;
+      obs_uv[2 * e] = o.u; obs_uv[2 * e + 1] = o.v; obs_w[e] = o.w;
     }
     built_max_uid = max_kf_uid; built_fixed.assign(fixed_uid, fixed_uid + n_fixed);
     stale = false; rebuilds++;
@@ -207,5 +221,12 @@ int ccm_mirror_ba_problem(ccm_map_mirror* m, uint64_t max_kf_uid, const uint64_t
 }
 
 long long ccm_mirror_rebuilds(const ccm_map_mirror* m) { return m ? m->rebuilds : -1; }
+
+int ccm_mirror_set_min_edges(ccm_map_mirror* m, int32_t min_edges) {
+  return guarded([&] {
+    CCM_REQUIRE(m && (min_edges == 1 || min_edges == 2), "ccm_mirror_set_min_edges: 1 (BundleAdjustmentClient) or 2 (MapFusionGBA)");
+    if (m->min_edges != min_edges) { m->min_edges = min_edges; m->stale = true; }
+  });
+}
 
 }  // extern "C"

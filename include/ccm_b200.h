@@ -475,8 +475,10 @@ int ccm_gba_map_update(int32_t n_kf, const int32_t* kf_parent, const uint8_t* kf
  * INTEGRATION.md) and ccm_mirror_ba_problem hands out a ccm_ba_problem over arrays the mirror owns, valid until the next ccm_mirror_*
  * call on it.  Value changes patch that problem in place; structural changes cost one pass over flat arrays at the next request,
  * applying the reference's selection rules (keyframes: not bad, uid <= max_kf_uid; edges: both ends selected; points: not bad, at
- * least one edge).  Rows keep first-insertion order.  uid = mUniqueId.  Host code; one mirror is not thread-safe (the reference
- * holds LockMapUpdate around a GBA). */
+ * least min_edges observations in all and min_edges selected edges — 2, MapFusionGBA's rule (cslam/src/Optimizer.cpp:722-740), unless
+ * ccm_mirror_set_min_edges(m, 1) asks for BundleAdjustmentClient's (:117-160)).  Rows keep first-insertion order; observations come
+ * grouped by point row (insertion order inside a group), the layout ccm_ba_create takes without sorting.  uid = mUniqueId.  Host code;
+ * one mirror is not thread-safe (the reference holds LockMapUpdate around a GBA). */
 typedef struct ccm_map_mirror ccm_map_mirror;
 int ccm_mirror_create(ccm_map_mirror** out);
 void ccm_mirror_destroy(ccm_map_mirror* m);
@@ -489,6 +491,7 @@ int ccm_mirror_erase_observation(ccm_map_mirror* m, uint64_t kf_uid, uint64_t mp
 int ccm_mirror_ba_problem(ccm_map_mirror* m, uint64_t max_kf_uid, const uint64_t* fixed_uid, int32_t n_fixed, ccm_ba_problem* out,
                           const uint64_t** kf_uid_of_row, const uint64_t** mp_uid_of_row);
 long long ccm_mirror_rebuilds(const ccm_map_mirror* m);   /* how many flat passes have run (tests, tuning) */
+int ccm_mirror_set_min_edges(ccm_map_mirror* m, int32_t min_edges);   /* 2 (default, MapFusionGBA) or 1 (BundleAdjustmentClient) */
 
 #ifdef __cplusplus
 }

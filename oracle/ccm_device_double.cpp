@@ -54,7 +54,14 @@ struct ccm_ba_handle {
 
 extern "C" {
 const char* ccm_last_error(void) { return "(device double)"; }
-int ccm_ba_solve(const ccm_ba_problem* p, const ccm_ba_options* o, ccm_ba_result* r) { return run_ba(p, o, r, nullptr, nullptr); }
+/* test hook: runs between the solve and the shim's write-back (a keyframe turning bad while the GBA thread was solving) */
+void (*ccm_double_after_solve)(void*) = nullptr;
+void* ccm_double_after_solve_arg = nullptr;
+int ccm_ba_solve(const ccm_ba_problem* p, const ccm_ba_options* o, ccm_ba_result* r) {
+  const int rc = run_ba(p, o, r, nullptr, nullptr);
+  if (ccm_double_after_solve) ccm_double_after_solve(ccm_double_after_solve_arg);
+  return rc;
+}
 int ccm_ba_create(const ccm_ba_problem* p, ccm_ba_handle** out) {
   ccm_ba_handle* h = new ccm_ba_handle;
   h->poses.assign(p->poses, p->poses + 7 * (size_t)p->K); h->intr.assign(p->intr, p->intr + 4 * (size_t)p->K);

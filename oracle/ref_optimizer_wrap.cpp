@@ -126,6 +126,37 @@ int optw_gba(const optw_scene* s, int which, int iterations, int robust, int64_t
   } catch (...) { return -1; }
 }
 
+/* as optw_gba, but keyframe flip_kf turns bad after the solve and before the write-back (GBA runs in its own thread while culling goes on).
+   Needs the device double's hook (liboptimizer_shim.so); returns -2 in the builds without it. */
+}
+#include <dlfcn.h>
+namespace { struct Flip { Scene* sc; int kf; }; void do_flip(void* a) { Flip* f = static_cast<Flip*>(a); f->sc->kf_store[f->kf].mbBad = true; } }
+extern "C" {
+int optw_gba_flip(const optw_scene* s, int which, int iterations, int robust, int64_t loop_first, int64_t loop_second, int flip_kf, optw_out* o) {
+  typedef void (*hook_t)(void*);
+  Dl_info self;   /* the library is loaded RTLD_LOCAL by ctypes: look the hook up in this very object */
+  if (!dladdr(reinterpret_cast<void*>(&do_flip), &self)) return -2;
+  void* me = dlopen(self.dli_fname, RTLD_NOLOAD | RTLD_NOW);
+  if (!me) return -2;
+  hook_t* hook = reinterpret_cast<hook_t*>(dlsym(me, "ccm_double_after_solve"));
+  void** arg = reinterpret_cast<void**>(dlsym(me, "ccm_double_after_solve_arg"));
+  dlclose(me);
+  if (!hook || !arg) return -2;
+  try {
+    Scene sc(s);
+    Flip f{&sc, flip_kf};
+    *hook = do_flip; *arg = &f;
+    const idpair nLoopKF((size_t)loop_first, (size_t)loop_second);
+    try {
+      if (which == 0) Optimizer::MapFusionGBA(sc.map, (size_t)s->map_id, iterations, NULL, nLoopKF, robust != 0);
+      else Optimizer::GlobalBundleAdjustemntClient(sc.map, (size_t)s->map_id, iterations, NULL, nLoopKF, robust != 0);
+    } catch (...) { *hook = nullptr; *arg = nullptr; throw; }
+    *hook = nullptr; *arg = nullptr;
+    sc.read(s, o);
+    return 0;
+  } catch (...) { return -1; }
+}
+
 int optw_local_ba(const optw_scene* s, int kf_index, int server, optw_out* o) {
   try {
     Scene sc(s);

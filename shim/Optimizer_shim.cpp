@@ -85,9 +85,14 @@ void Optimizer::MapFusionGBA(mapptr pMap, size_t ClientId, int nIterations, bool
 
   FlatBA f;
   size_t maxKFid = 0;
-  for (kfptr pKF : vpKFs) {                                  // keyframe vertices, :695-709
+  // kf_row[i]: row of vpKFs[i] in the flat problem, -1 if skipped.  The write-back looks rows up here (the reference looks every
+  // vertex up by id, :805): GBA runs in its own thread while culling continues, so a keyframe may turn bad between flatten and
+  // write-back, and a running row counter would then hand every later keyframe its neighbour's pose.
+  vector<int> kf_row(vpKFs.size(), -1);
+  for (size_t i = 0; i < vpKFs.size(); i++) {                 // keyframe vertices, :695-709
+    kfptr pKF = vpKFs[i];
     if (pKF->isBad()) continue;
-    f.add_kf(pKF, pKF->mId == FixedId);
+    kf_row[i] = f.add_kf(pKF, pKF->mId == FixedId);
     maxKFid = std::max(maxKFid, (size_t)pKF->mUniqueId);
   }
   vector<int> mp_row(vpMP.size(), -1);
@@ -120,10 +125,10 @@ void Optimizer::MapFusionGBA(mapptr pMap, size_t ClientId, int nIterations, bool
   res.poses = poses.data(); res.points = points.data();
   check(ccm_ba_solve(&prob, &opt, &res));                     // == initializeOptimization(); optimize(nIterations)
 
-  size_t row = 0;
-  for (kfptr pKF : vpKFs) {                                   // write-back, :803-823
-    if (pKF->isBad()) continue;
-    cv::Mat T = pose_to_cv(&poses[7 * row++]);
+  for (size_t i = 0; i < vpKFs.size(); i++) {                 // write-back, :803-823
+    kfptr pKF = vpKFs[i];
+    if (kf_row[i] < 0 || pKF->isBad()) continue;
+    cv::Mat T = pose_to_cv(&poses[7 * (size_t)kf_row[i]]);
     if (nLoopKF == zeropair) pKF->SetPose(T, true);
     else { pKF->mTcwGBA.create(4, 4, CV_32F); T.copyTo(pKF->mTcwGBA); pKF->mBAGlobalForKF = nLoopKF; }
   }
@@ -146,10 +151,12 @@ void Optimizer::BundleAdjustmentClient(const vector<kfptr>& vpKFs, const vector<
                                        bool* pbStopFlag, const idpair nLoopKF, const bool bRobust) {
   const idpair zeropair = make_pair(0, ClientId);
   FlatBA f;
-  for (kfptr pKF : vpKFs) {
+  vector<int> kf_row(vpKFs.size(), -1);                       // as in MapFusionGBA: rows by table, not by a running counter
+  for (size_t i = 0; i < vpKFs.size(); i++) {
+    kfptr pKF = vpKFs[i];
     if (pKF->isBad()) continue;
     if (pKF->mId.first >= IDRANGE) throw infrastructure_ex();
-    f.add_kf(pKF, pKF->mId == zeropair);
+    kf_row[i] = f.add_kf(pKF, pKF->mId == zeropair);
   }
   vector<int> mp_row(vpMP.size(), -1);
   for (size_t i = 0; i < vpMP.size(); i++) {
@@ -174,10 +181,10 @@ void Optimizer::BundleAdjustmentClient(const vector<kfptr>& vpKFs, const vector<
   ccm_ba_result res = {};
   res.poses = poses.data(); res.points = points.data();
   check(ccm_ba_solve(&prob, &opt, &res));
-  size_t row = 0;
-  for (kfptr pKF : vpKFs) {
-    if (pKF->isBad()) continue;
-    cv::Mat T = pose_to_cv(&poses[7 * row++]);
+  for (size_t i = 0; i < vpKFs.size(); i++) {
+    kfptr pKF = vpKFs[i];
+    if (kf_row[i] < 0 || pKF->isBad()) continue;
+    cv::Mat T = pose_to_cv(&poses[7 * (size_t)kf_row[i]]);
     if (nLoopKF == zeropair) pKF->SetPose(T, false);
     else { pKF->mTcwGBA.create(4, 4, CV_32F); T.copyTo(pKF->mTcwGBA); pKF->mBAGlobalForKF = nLoopKF; }
   }
@@ -227,6 +234,10 @@ void Optimizer::LocalBundleAdjustmentClient(kfptr pKF, bool* pbStopFlag, mapptr 
   ccm_ba_problem prob = f.problem();
   ccm_ba_handle* h = nullptr;
   check(ccm_ba_create(&prob, &h));
+  struct HandleGuard {                                          // every exit path (check() throws on OOM / CUDA errors) destroys the handle
+    ccm_ba_handle* h;
+    ~HandleGuard() { if (h) ccm_ba_destroy(h); }
+  } guard{h};
   ccm_ba_options opt = {};
   opt.robust = 1; opt.huber_delta = (double)(float)sqrt(5.991);  // const float thHuberMono = sqrt(5.991), :468
   opt.stop = reinterpret_cast<const volatile uint8_t*>(pbStopFlag);
@@ -247,7 +258,7 @@ void Optimizer::LocalBundleAdjustmentClient(kfptr pKF, bool* pbStopFlag, mapptr 
     opt.iterations = 10;
     check(ccm_ba_optimize(h, &opt, &res));                      // chi2 of level-1 edges keeps its round-1 value (res.chi2 untouched there)
   }
-  ccm_ba_destroy(h);
+  ccm_ba_destroy(h); guard.h = nullptr;
 
   vector<pair<kfptr, mpptr>> vToErase;
   for (size_t i = 0; i < E; i++) {                              // :573-587

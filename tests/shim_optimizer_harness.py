@@ -149,6 +149,16 @@ def run_gba(sc, which, iterations, robust, loop, want_rc=0):
     return o
 
 
+def run_gba_flip(sc, which, iterations, robust, loop, flip_kf):
+    """As run_gba, but keyframe flip_kf turns bad between the solve and the write-back (device double's hook; shim library only)."""
+    keep = []
+    S = c_scene(sc, keep)
+    o, O = new_out(S.K, S.P)
+    rc = lib().optw_gba_flip(C.byref(S), int(which), int(iterations), int(robust), C.c_int64(loop[0]), C.c_int64(loop[1]), int(flip_kf), C.byref(O))
+    assert rc == 0, rc
+    return o
+
+
 def run_essential_graph(sc, loop_kf, cur_kf, conn, fix_scale, loop_closure=False, corr=None, mp_corr_ref=None):
     """conn: {keyframe index: [keyframe indices]} = LoopConnections; corr = (kf indices, corrected (n,8), noncorrected (n,8))"""
     keep = []

@@ -22,19 +22,27 @@ class Model:
     def __init__(self):
         self.kf, self.mp, self.obs = {}, {}, {}
 
-    def flatten(self, max_uid, fixed):
+    def flatten(self, max_uid, fixed, min_edges=2):
+        """MapFusionGBA (min_edges = 2, S/Optimizer.cpp:722-740: observations.size() < 2 || nEdges < 2 skips the point) or
+        BundleAdjustmentClient (min_edges = 1); observations grouped by point row, insertion order inside a group"""
         rows = {}; poses = []; intr = []; fx = []
         for uid, k in self.kf.items():
             if k["bad"] or uid > max_uid:
                 continue
             rows[uid] = len(poses); poses.append(k["T"]); intr.append(k["intr"]); fx.append(uid in fixed)
-        edges = [(m, k, o) for (m, k), o in self.obs.items() if k in rows and m in self.mp and not self.mp[m]["bad"]]
-        seen = {m for m, _, _ in edges}
+        nobs, nedges = {}, {}
+        for (m, k), o in self.obs.items():
+            if m in self.mp and not self.mp[m]["bad"]:
+                nobs[m] = nobs.get(m, 0) + 1
+                if k in rows:
+                    nedges[m] = nedges.get(m, 0) + 1
         prow = {}; pts = []
         for uid, p in self.mp.items():
-            if p["bad"] or uid not in seen:
+            if p["bad"] or nobs.get(uid, 0) < min_edges or nedges.get(uid, 0) < min_edges:
                 continue
             prow[uid] = len(pts); pts.append(p["x"])
+        edges = [(m, k, o) for (m, k), o in self.obs.items() if k in rows and m in prow]
+        edges.sort(key=lambda e: prow[e[0]])                       # stable: insertion order inside a point's group
         T = np.array(poses, np.float32).reshape(-1, 16)
         return dict(poses=api.poses_from_Tcw_f32(T) if len(T) else np.zeros((0, 7)), intr=np.array(intr, np.float32).astype(np.float64).reshape(-1, 4),
                     fixed=np.array(fx, np.uint8), points=np.array(pts, np.float32).astype(np.float64).reshape(-1, 3),
@@ -95,19 +103,21 @@ def burst(rng, M, mir, n, next_uid, structural=True):
 def test_random_history(seed):
     rng = np.random.default_rng(seed)
     M = Model(); mir = api.MapMirror(); nxt = [0, 0]; most = [0, 0]
+    min_edges = 1 + seed % 2
+    mir.set_min_edges(min_edges)
     for rnd in range(12):
         burst(rng, M, mir, int(rng.integers(50, 400)), nxt)
         max_uid = int(rng.integers(0, max(nxt[0], 1) + 2)) if rnd % 3 == 2 else 10 ** 9          # sometimes a cut like MapFusionGBA's maxKFid
         fixed = {0} if rnd % 2 == 0 else {int(u) for u in list(M.kf)[:2]}
         _, a, ku, mu = mir.problem(max_uid, sorted(fixed))
-        same((a, ku, mu), M.flatten(max_uid, fixed))
+        same((a, ku, mu), M.flatten(max_uid, fixed, min_edges))
         # value-only burst: no rebuild, still exact
         r0 = mir.rebuilds()
         _, a, ku, mu = mir.problem(max_uid, sorted(fixed)); assert mir.rebuilds() == r0               # the same question again: cached
         burst(rng, M, mir, 60, nxt, structural=False)
         _, a, ku, mu = mir.problem(max_uid, sorted(fixed))
         assert mir.rebuilds() == r0
-        same((a, ku, mu), M.flatten(max_uid, fixed))
+        same((a, ku, mu), M.flatten(max_uid, fixed, min_edges))
         most = [max(most[0], len(a["obs_kf"])), max(most[1], len(ku))]
     assert most[0] > 50 and most[1] > 5
     mir.close()

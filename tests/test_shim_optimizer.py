@@ -67,6 +67,30 @@ def test_map_fusion_gba(ho, name, bad_kf, bad_mp, loop_mode):
     assert np.abs(Tw - sc["kf_Tcw"][rows]).max() > 1e-4           # the optimisation did move things
 
 
+@pytest.mark.parametrize("which,loop_mode", [(0, False), (0, True), (1, False)])
+def test_gba_keyframe_turning_bad_during_the_solve(ho, which, loop_mode):
+    """LoopFinder::RunGBA and the client GBA run in their own thread while culling continues: a keyframe that turns bad between flattening
+    and write-back must not shift the rows of the keyframes after it (the reference looks every vertex up by id, S/Optimizer.cpp:805).
+    Every other keyframe and every point gets exactly what it gets without the flip; the flipped keyframe is left alone."""
+    p = synth.make_config("small")
+    sc = H.scene_from_problem(p, ho, seed=3, map_id=0)
+    loop = (7, 0) if loop_mode else (0, 0)
+    base = H.run_gba(sc, which, 6, True, loop)
+    K = len(sc["kf_uid"])
+    flip = K // 2
+    got = H.run_gba_flip(sc, which, 6, True, loop, flip)
+    others = np.arange(K) != flip
+    key = "kf_TcwGBA" if loop_mode else "kf_Tcw"
+    assert np.array_equal(got[key][others], base[key][others])
+    assert np.abs(base[key][flip + 1] - base[key][flip]).max() > 1e-3     # neighbouring rows do differ: a shift would have shown
+    if loop_mode:
+        assert not got["kf_TcwGBA"][flip].any() and not got["kf_gba_tag"][flip].any()
+    else:
+        assert np.array_equal(got["kf_Tcw"][flip], sc["kf_Tcw"][flip]) and got["kf_set_pose"][flip] == 0
+    for k in ("mp_pos", "mp_posGBA", "mp_gba_tag", "mp_set_pos"):
+        assert np.array_equal(got[k], base[k]), k
+
+
 # ---- essential graph ----------------------------------------------------------------------------------------------------------
 MIN_FEAT = 100      # params::opt::miEssGraphMinFeats, handed to the reference's config.h through the FileStorage stand-in (conftest sets it)
 
