@@ -394,15 +394,27 @@ __device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, doubl
                : "d"(a), "d"(b));
 }
 
-template <int UNROLL, int CTA, bool PIPE = false>
+// TILED: the CTA takes the upper blocks of one T x T tile of S (tile_ptr / tile_u, built by build_schur_tiles): its warps share
+// the Z rows of T block rows and T block columns, and -- the product lists being sorted by landmark -- meet them at about the same
+// time, so most of the 2 x 144 bytes per product come from L1 instead of L2.
+template <int UNROLL, int CTA, bool PIPE = false, bool TILED = false>
 __global__ void __launch_bounds__(CTA) k_schur_mma(const uint2* __restrict__ prod, const unsigned* __restrict__ u_prod_ptr,
                                                    const int* __restrict__ u_row, const int* __restrict__ u_col, int nub,
                                                    const double* __restrict__ Z, const int* __restrict__ o_lm,
                                                    const double* __restrict__ gvec, double* __restrict__ U_val,
-                                                   double* __restrict__ bneg) {
+                                                   double* __restrict__ bneg, const int* __restrict__ tile_ptr = nullptr,
+                                                   const int* __restrict__ tile_u = nullptr) {
   static_assert(UNROLL % 2 == 0, "products alternate between two accumulator sets");
-  const int warp = (int)(((long long)blockIdx.x * CTA + threadIdx.x) >> 5);
-  if (warp >= nub) return;  // warp-uniform
+  int warp;
+  if (TILED) {
+    const int t0 = tile_ptr[blockIdx.x], t1 = tile_ptr[blockIdx.x + 1];
+    const int w = threadIdx.x >> 5;
+    if (w >= t1 - t0) return;  // ragged tile (diagonal, band edge): warp-uniform
+    warp = tile_u[t0 + w];
+  } else {
+    warp = (int)(((long long)blockIdx.x * CTA + threadIdx.x) >> 5);
+    if (warp >= nub) return;  // warp-uniform
+  }
   const int lane = threadIdx.x & 31;
   const int m = lane >> 2, k = lane & 3;
   const bool ld = m < 6 && k < 3;
@@ -743,6 +755,66 @@ __global__ void __launch_bounds__(TPB) k_upper_index(const int* __restrict__ s_r
 __global__ void __launch_bounds__(TPB) k_shift(const int* __restrict__ in, long long n, int off, int* __restrict__ out) {
   const long long i = (long long)blockIdx.x * TPB + threadIdx.x;
   if (i < n) out[i] = in[i] - off;
+}
+
+// Product lists come out of k_products in the order the atomic slots were handed out.  Sorting every list by (first observation,
+// second observation) = by landmark makes the Schur sums deterministic and lets the warps of a tile walk Z together (k_schur_mma,
+// TILED).  One CTA per list, bitonic network in shared memory; lists beyond the shared buffer (a keyframe with more than 4096
+// observations in one block) keep their order, which only costs locality.
+constexpr int SORT_CAP = 4096;
+__global__ void __launch_bounds__(256) k_sort_products(const unsigned* __restrict__ u_prod_ptr, int nub, uint2* __restrict__ prod) {
+  __shared__ unsigned long long s[SORT_CAP];
+  const int u = blockIdx.x;
+  if (u >= nub) return;
+  const unsigned beg = u_prod_ptr[u], end = u_prod_ptr[u + 1];
+  const int n = (int)(end - beg);
+  if (n <= 1 || n > SORT_CAP) return;
+  int m = 2;
+  while (m < n) m <<= 1;
+  for (int i = threadIdx.x; i < m; i += 256) {
+    unsigned long long v = ~0ull;
+    if (i < n) { const uint2 p = prod[beg + i]; v = ((unsigned long long)p.x << 32) | p.y; }
+    s[i] = v;
+  }
+  __syncthreads();
+  for (int k = 2; k <= m; k <<= 1)
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < m; i += 256) {
+        const int ixj = i ^ j;
+        if (ixj > i) {
+          const unsigned long long a = s[i], b = s[ixj];
+          const bool up = (i & k) == 0;
+          if ((a > b) == up) { s[i] = b; s[ixj] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  for (int i = threadIdx.x; i < n; i += 256) prod[beg + i] = make_uint2((unsigned)(s[i] >> 32), (unsigned)(s[i] & 0xffffffffu));
+}
+
+// tile schedule of the upper blocks: key = (row group, column group | position inside the T x T tile), value = block number
+__global__ void __launch_bounds__(TPB) k_tile_keys(const int* __restrict__ u_row, const int* __restrict__ u_col, int nub, int T,
+                                                   unsigned long long ngroups, unsigned long long* __restrict__ keys,
+                                                   int* __restrict__ vals) {
+  const int u = blockIdx.x * TPB + threadIdx.x;
+  if (u >= nub) return;
+  const int a = u_row[u], b = u_col[u];
+  keys[u] = (((unsigned long long)(a / T) * ngroups + (unsigned long long)(b / T)) << 8) | (unsigned)((a % T) * T + (b % T));
+  vals[u] = u;
+}
+// head[i] = 1 where a new tile starts in the sorted key list
+__global__ void __launch_bounds__(TPB) k_tile_heads(const unsigned long long* __restrict__ keys, int nub, int* __restrict__ head) {
+  const int i = blockIdx.x * TPB + threadIdx.x;
+  if (i >= nub) return;
+  head[i] = (i == 0 || (keys[i] >> 8) != (keys[i - 1] >> 8)) ? 1 : 0;
+}
+// tile_ptr[t] = first sorted position of tile t (rank = inclusive scan of the heads), tile_ptr[ntiles] = nub
+__global__ void __launch_bounds__(TPB) k_tile_ptr(const int* __restrict__ head, const int* __restrict__ rank, int nub,
+                                                  int* __restrict__ tile_ptr) {
+  const int i = blockIdx.x * TPB + threadIdx.x;
+  if (i >= nub) return;
+  if (head[i]) tile_ptr[rank[i] - 1] = i;
+  if (i == nub - 1) tile_ptr[rank[i]] = nub;
 }
 
 // count (fill == 0) or fill (fill == 1) the product lists of the upper blocks; one thread per local observation

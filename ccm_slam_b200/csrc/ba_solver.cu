@@ -12,6 +12,9 @@
 #include <limits>
 #include <numeric>
 
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+
 #include "ba_kernels.cuh"
 #include "common.cuh"
 #include "pcg2.cuh"
@@ -72,6 +75,8 @@ struct ccm_ba_handle {
   DevBuf<int> s_rowptr, s_col, s_row, s_diag, csr_u, u_row, u_col, u_diag, word_prefix;
   DevBuf<unsigned> bitmap, u_prod_ptr;
   DevBuf<uint2> prod;
+  DevBuf<int> tile_ptr, tile_u;   // T x T tiles of upper blocks: the CTA schedule of the tiled Schur kernel
+  int ntiles = 0, tile_T = 0;
   DevBuf<float4> kobs;            // per free pose: (u, v, signed w, landmark) of its observations, packed
   DevBuf<unsigned> kobs_ptr;
   // pcg
@@ -264,10 +269,16 @@ int schur_mode() {
     if (!strcmp(v, "gather") || !strcmp(v, "0")) return 0;
     if (!strcmp(v, "mma")) return 1;
     const int m = atoi(v);
-    return (m >= 0 && m <= 8) ? m : 1;
+    return (m >= 0 && m <= 9) ? m : 1;
   }();
   const int o = g_schur_override.load(std::memory_order_relaxed);
   return o >= 0 ? o : env_mode;
+}
+
+template <int UNROLL, int CTA>
+void launch_schur_tiled(ccm_ba_handle* h, cudaStream_t s) {
+  k_schur_mma<UNROLL, CTA, true, true><<<h->ntiles, CTA, 0, s>>>(h->prod.p, h->u_prod_ptr.p, h->u_row.p, h->u_col.p, h->nub, h->Z.p, h->o_lm.p,
+                                                                  h->gvec.p, h->U_val(), h->bneg(), h->tile_ptr.p, h->tile_u.p);
 }
 
 template <int UNROLL, int CTA, bool PIPE = false>
@@ -277,7 +288,14 @@ void launch_schur_mma(ccm_ba_handle* h, cudaStream_t s) {
 }
 
 void launch_schur(ccm_ba_handle* h, cudaStream_t s) {
-  switch (schur_mode()) {
+  const int mode = schur_mode();
+  if (mode >= 9 && h->ntiles > 0) {   // tiled schedules (the tile edge was fixed when the handle was created: CCM_SCHUR_TILE)
+    if (h->tile_T == 4) launch_schur_tiled<8, 512>(h, s);
+    else if (h->tile_T == 3) launch_schur_tiled<8, 288>(h, s);
+    else launch_schur_tiled<8, 128>(h, s);
+    return;
+  }
+  switch (mode) {
     case 0:
       k_schur<<<div_up((long long)h->nub * 32, TPB), TPB, 0, s>>>(h->prod.p, h->u_prod_ptr.p, h->u_row.p, h->u_col.p, h->nub, h->Z.p,
                                                                   h->o_lm.p, h->gvec.p, h->U_val(), h->bneg());
@@ -865,6 +883,36 @@ void build(ccm_ba_handle* h, const ccm_ba_problem* p) {
     CCM_LAUNCHED();
   }
 
+  if (h->nprod && env_int("CCM_SCHUR_SORT", 1)) {   // landmark order inside every list: deterministic sums, shared Z rows meet in L1
+    k_sort_products<<<nub, 256, 0, s>>>(h->u_prod_ptr.p, nub, h->prod.p);
+    CCM_LAUNCHED();
+  }
+  h->tile_T = env_int("CCM_SCHUR_TILE", 4);
+  h->ntiles = 0;
+  if (nub > 0 && h->nprod && (h->tile_T == 2 || h->tile_T == 3 || h->tile_T == 4)) {
+    // tile schedule: sort the upper blocks by (row group, column group), cut where the tile changes
+    DevBuf<unsigned long long> k_in, k_out;
+    DevBuf<int> v_in, v_out, head, rank;
+    k_in.alloc(nub); k_out.alloc(nub); v_in.alloc(nub); v_out.alloc(nub); head.alloc(nub); rank.alloc(nub);
+    const unsigned long long ngroups = (unsigned long long)(Kf / h->tile_T + 1);
+    k_tile_keys<<<div_up(nub, TPB), TPB, 0, s>>>(h->u_row.p, h->u_col.p, nub, h->tile_T, ngroups, k_in.p, v_in.p);
+    CCM_LAUNCHED();
+    size_t tb1 = 0, tb2 = 0;
+    CCM_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb1, k_in.p, k_out.p, v_in.p, v_out.p, nub, 0, 64, s));
+    CCM_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tb2, head.p, rank.p, nub, s));
+    DevBuf<unsigned char> tmp; tmp.alloc(std::max(tb1, tb2) + 16);
+    CCM_CUDA(cub::DeviceRadixSort::SortPairs(tmp.p, tb1, k_in.p, k_out.p, v_in.p, v_out.p, nub, 0, 64, s));
+    k_tile_heads<<<div_up(nub, TPB), TPB, 0, s>>>(k_out.p, nub, head.p);
+    CCM_LAUNCHED();
+    CCM_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, tb2, head.p, rank.p, nub, s));
+    h->tile_ptr.alloc((size_t)nub + 1);
+    k_tile_ptr<<<div_up(nub, TPB), TPB, 0, s>>>(head.p, rank.p, nub, h->tile_ptr.p);
+    CCM_LAUNCHED();
+    h->tile_u.alloc(nub);
+    CCM_CUDA(cudaMemcpyAsync(h->tile_u.p, v_out.p, sizeof(int) * (size_t)nub, cudaMemcpyDeviceToDevice, s));
+    CCM_CUDA(cudaMemcpyAsync(&h->ntiles, rank.p + (nub - 1), sizeof(int), cudaMemcpyDeviceToHost, s));
+    CCM_CUDA(cudaStreamSynchronize(s));  // ntiles is the grid size; the temporaries die here
+  }
   lap("product lists");
   // packed per-pose observation stream for the pose pass
   {
@@ -1297,7 +1345,7 @@ extern "C" int ccm_ba_debug_schur(ccm_ba_handle* h, int robust, double huber_del
 
 extern "C" int ccm_ba_debug_set_schur_mode(int mode) {
   return guarded([&] {
-    CCM_REQUIRE(mode >= -1 && mode <= 8, "ccm_ba_debug_set_schur_mode: -1 (CCM_SCHUR / default), 0 gather, 1 mma, 2..8 mma variants");
+    CCM_REQUIRE(mode >= -1 && mode <= 9, "ccm_ba_debug_set_schur_mode: -1 (CCM_SCHUR / default), 0 gather, 1 mma, 2..8 mma variants, 9 tiled");
     g_schur_override.store(mode);
   });
 }

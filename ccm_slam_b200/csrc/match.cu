@@ -57,7 +57,8 @@ struct Scratch {
 };
 thread_local Scratch t_scr;
 
-const uint16_t* distance_matrix(const uint8_t* A, int nA, const uint8_t* B, int nB) {
+// Either operand may already live on the device (dA / dB != nullptr: the keyframe store of kf_store.cu); host operands are uploaded.
+const uint16_t* distance_matrix_any(const uint8_t* A, const uint4* dA, int nA, const uint8_t* B, const uint4* dB, int nB) {
   ensure_device();
   Scratch& s = t_scr;
   if (s.device != current_device()) {
@@ -67,8 +68,8 @@ const uint16_t* distance_matrix(const uint8_t* A, int nA, const uint8_t* B, int 
   if (!s.stream) CCM_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
   const size_t n = (size_t)nA * nB;
   if (n == 0) return s.hD;
-  if (s.A.n < (size_t)nA * 2) s.A.alloc((size_t)nA * 2 + 256);
-  if (s.B.n < (size_t)nB * 2) s.B.alloc((size_t)nB * 2 + 256);
+  if (!dA && s.A.n < (size_t)nA * 2) s.A.alloc((size_t)nA * 2 + 256);
+  if (!dB && s.B.n < (size_t)nB * 2) s.B.alloc((size_t)nB * 2 + 256);
   if (s.D.n < n) s.D.alloc(n + 4096);
   if (s.hD_cap < n) {
     if (s.hD) cudaFreeHost(s.hD);
@@ -76,15 +77,16 @@ const uint16_t* distance_matrix(const uint8_t* A, int nA, const uint8_t* B, int 
     CCM_CUDA(cudaMallocHost((void**)&s.hD, (n + 4096) * sizeof(uint16_t)));
     s.hD_cap = n + 4096;
   }
-  CCM_CUDA(cudaMemcpyAsync(s.A.p, A, (size_t)nA * 32, cudaMemcpyHostToDevice, s.stream));
-  CCM_CUDA(cudaMemcpyAsync(s.B.p, B, (size_t)nB * 32, cudaMemcpyHostToDevice, s.stream));
+  if (!dA) { CCM_CUDA(cudaMemcpyAsync(s.A.p, A, (size_t)nA * 32, cudaMemcpyHostToDevice, s.stream)); dA = s.A.p; }
+  if (!dB) { CCM_CUDA(cudaMemcpyAsync(s.B.p, B, (size_t)nB * 32, cudaMemcpyHostToDevice, s.stream)); dB = s.B.p; }
   dim3 g(div_up(nB, 32), div_up(nA, 32));
-  k_hamming<<<g, 256, 0, s.stream>>>(s.A.p, nA, s.B.p, nB, s.D.p);
+  k_hamming<<<g, 256, 0, s.stream>>>(dA, nA, dB, nB, s.D.p);
   CCM_LAUNCHED();
   CCM_CUDA(cudaMemcpyAsync(s.hD, s.D.p, n * sizeof(uint16_t), cudaMemcpyDeviceToHost, s.stream));
   CCM_CUDA(cudaStreamSynchronize(s.stream));
   return s.hD;
 }
+const uint16_t* distance_matrix(const uint8_t* A, int nA, const uint8_t* B, int nB) { return distance_matrix_any(A, nullptr, nA, B, nullptr, nB); }
 
 struct RotHist {
   std::vector<int> bins[HISTO_LENGTH];
@@ -139,9 +141,12 @@ void check_fv(const ccm_feature_vector* f, int n, const char* what) {
 
 }  // namespace
 
-// shared with proj_match.cu: the (thread-local, pinned) distance matrix of one call; valid until the next call on this thread
+// shared with proj_match.cu / kf_store.cu: the (thread-local, pinned) distance matrix of one call; valid until the next call on this thread
 namespace ccm {
 const uint16_t* hamming_matrix_host(const uint8_t* A, int nA, const uint8_t* B, int nB) { return distance_matrix(A, nA, B, nB); }
+const uint16_t* hamming_matrix_mixed(const uint8_t* A, const void* dA, int nA, const uint8_t* B, const void* dB, int nB) {
+  return distance_matrix_any(A, static_cast<const uint4*>(dA), nA, B, static_cast<const uint4*>(dB), nB);
+}
 }  // namespace ccm
 
 extern "C" int ccm_hamming_matrix(const uint8_t* A, int32_t nA, const uint8_t* B, int32_t nB, uint16_t* D) {

@@ -117,8 +117,10 @@ __device__ __forceinline__ void p2_st_release_sys(unsigned long long* p, unsigne
 // Grid-wide (cross = false) or node-wide (cross = true and nranks > 1) barrier.  Every CTA arrives at a counter; CTA 0 waits for
 // the arrivals, runs publish() with all its threads (partials -> exchange windows), meets the peers' CTA 0s at the flag words
 // when the barrier is node-wide, and releases the local CTAs through a generation word.  Returns false after a time-out / abort.
+// remote: the CTAs stored into peer windows since the last barrier (their arrival then needs a system-scope fence, which waits for
+// the NVLink write acknowledgements; a GPU-scope fence otherwise).
 template <typename F>
-__device__ __forceinline__ bool p2_barrier(const Pcg2Args& A, unsigned& gen, unsigned long long& epoch, bool cross, int* s_ok,
+__device__ __forceinline__ bool p2_barrier(const Pcg2Args& A, unsigned& gen, unsigned long long& epoch, bool cross, bool remote, int* s_ok,
                                            F&& publish) {
   __syncthreads();
   gen += 1;
@@ -127,7 +129,7 @@ __device__ __forceinline__ bool p2_barrier(const Pcg2Args& A, unsigned& gen, uns
   if (node) epoch += 1;
   volatile unsigned* ctl = reinterpret_cast<volatile unsigned*>(A.win[A.rank] + A.off_ctl);
   if (threadIdx.x == 0) {
-    if (multi) __threadfence_system(); else __threadfence();
+    if (multi && remote) __threadfence_system(); else __threadfence();
     atomicAdd(A.bar, 1u);
   }
   if (blockIdx.x == 0) {
@@ -381,20 +383,27 @@ __global__ void __launch_bounds__(P2_TPB, 1) k_pcg2(Pcg2Args A) {
       if (coarse) { p2_cflush(A, tp, cs.cur, cs.l, lane); p2_cflush(A, tp, cs.cur + 1, cs.h, lane); }
       if (lane == 0) sm_bcnt[wid] = npart;
       __syncthreads();
-      if (wid == 0) {  // rows cut by run boundaries: the partial sums are merged in run order
+      {  // rows cut by run boundaries: the warp that holds the first piece of a row sums the pieces in run order and finishes the row
         cs = P2CoarseAcc{-1, 0.0, 0.0};
-        int currow = -1;
-        double accv = 0.0;
-        for (int w = 0; w < P2_W; w++)
-          for (int e = 0; e < sm_bcnt[w]; e++) {
-            const int row = sm_brow[w * 2 + e];
-            if (row != currow) {
-              if (currow >= 0) row_done(currow, accv);
-              currow = row; accv = 0.0;
-            }
-            if (lane < BS) accv += sm_bval[(size_t)(w * 2 + e) * BS + lane];
+        const int mycnt = sm_bcnt[wid];
+        for (int e = 0; e < mycnt; e++) {
+          const int row = sm_brow[wid * 2 + e];
+          int prow = -1;
+          if (e > 0) prow = sm_brow[wid * 2 + e - 1];
+          else
+            for (int w = wid - 1; w >= 0; w--)
+              if (sm_bcnt[w] > 0) { prow = sm_brow[w * 2 + sm_bcnt[w] - 1]; break; }
+          if (prow == row) continue;  // an earlier warp holds the first piece
+          double accv = lane < BS ? sm_bval[(size_t)(wid * 2 + e) * BS + lane] : 0.0;
+          int w = wid, f = e + 1;
+          while (w < P2_W) {
+            if (f >= sm_bcnt[w]) { w++; f = 0; continue; }
+            if (sm_brow[w * 2 + f] != row) break;
+            if (lane < BS) accv += sm_bval[(size_t)(w * 2 + f) * BS + lane];
+            f++;
           }
-        if (currow >= 0) row_done(currow, accv);
+          row_done(row, accv);
+        }
         if (coarse) { p2_cflush(A, tp, cs.cur, cs.l, lane); p2_cflush(A, tp, cs.cur + 1, cs.h, lane); }
       }
     } else if (coarse) {
@@ -412,7 +421,7 @@ __global__ void __launch_bounds__(P2_TPB, 1) k_pcg2(Pcg2Args A) {
       if (tid == 0) part0[blockIdx.x] = t0;
     }
     // ---------------- synchronisation A: p.q and P^T q of every rank ---------------------------------------------------------
-    alive = p2_barrier(A, gen, epoch, true, &s_ok, [&] {
+    alive = p2_barrier(A, gen, epoch, true, false, &s_ok, [&] {
       if (N == 1) return;
       if (wid == 0) {
         const double v = sum_partials_dev(part0, G);
@@ -467,7 +476,7 @@ __global__ void __launch_bounds__(P2_TPB, 1) k_pcg2(Pcg2Args A) {
       }
     }
     // ---------------- synchronisation Y (this GPU only): yc complete ---------------------------------------------------------
-    alive = p2_barrier(A, gen, epoch, false, &s_ok, no_publish);
+    alive = p2_barrier(A, gen, epoch, false, false, &s_ok, no_publish);
     if (!alive) break;
     lap(it < 0 ? 0 : 2);
     // ---------------- phase 3: z = Minv r + P yc on the CTA's rows -> every rank's z buffer of the other parity; r.z, r.r -----
@@ -497,7 +506,7 @@ __global__ void __launch_bounds__(P2_TPB, 1) k_pcg2(Pcg2Args A) {
       if (tid == 0) { part1[blockIdx.x] = t0; part2[blockIdx.x] = t1; }
     }
     // ---------------- synchronisation B: r.z, r.r of every rank; the z slices are in place --------------------------------------
-    alive = p2_barrier(A, gen, epoch, true, &s_ok, [&] {
+    alive = p2_barrier(A, gen, epoch, true, true, &s_ok, [&] {
       if (N == 1) return;
       if (wid == 0) {
         const double v1 = sum_partials_dev(part1, G);
@@ -533,7 +542,7 @@ __global__ void __launch_bounds__(P2_TPB, 1) k_pcg2(Pcg2Args A) {
       const double xv = A.x[g];
       for (int k = 0; k < N; k++) reinterpret_cast<double*>(A.win[k] + A.off_x)[g] = xv;
     }
-    alive = p2_barrier(A, gen, epoch, true, &s_ok, no_publish);
+    alive = p2_barrier(A, gen, epoch, true, true, &s_ok, no_publish);
     if (alive) {
       const double* xs = reinterpret_cast<const double*>(A.win[me] + A.off_x);
       for (size_t i = (size_t)blockIdx.x * P2_TPB + tid; i < nv; i += (size_t)G * P2_TPB) A.x[i] = __ldcg(xs + i);

@@ -179,19 +179,21 @@ int ccm_voc_create(int32_t k, int32_t L, int32_t scoring, int32_t weighting, int
 
 int ccm_voc_words(const ccm_voc_handle* h) { return h ? h->n_words : 0; }
 
-int ccm_voc_transform(ccm_voc_handle* h, const uint8_t* desc, int32_t n, int32_t levelsup, uint32_t* word_of_feat, uint32_t* node_of_feat,
-                      double* weight_of_feat, uint32_t* bow_id, double* bow_val, int32_t* bow_n, uint32_t* fv_node_id,
-                      int32_t* fv_node_ptr, uint32_t* fv_feat, int32_t* fv_n_nodes) {
+// desc: host descriptors (uploaded) or, when d_resident != nullptr, descriptors already on the device (kf_store.cu: uploaded once at ingest)
+static int voc_transform_any(ccm_voc_handle* h, const uint8_t* desc, const uint4* d_resident, int32_t n, int32_t levelsup, uint32_t* word_of_feat,
+                             uint32_t* node_of_feat, double* weight_of_feat, uint32_t* bow_id, double* bow_val, int32_t* bow_n,
+                             uint32_t* fv_node_id, int32_t* fv_node_ptr, uint32_t* fv_feat, int32_t* fv_n_nodes) {
   return guarded([&] {
-    CCM_REQUIRE(h && n >= 0 && (n == 0 || desc) && bow_n && fv_n_nodes && fv_node_ptr, "ccm_voc_transform: null argument");
+    CCM_REQUIRE(h && n >= 0 && (n == 0 || desc || d_resident) && bow_n && fv_n_nodes && fv_node_ptr, "ccm_voc_transform: null argument");
     *bow_n = 0; *fv_n_nodes = 0; fv_node_ptr[0] = 0;
     if (n == 0 || h->n_words == 0) return;               // transform() of an empty vocabulary clears both containers
     ensure_device();
     CCM_CUDA(cudaSetDevice(h->device));
-    h->d_feat.upload(reinterpret_cast<const uint4*>(desc), (size_t)n * 2, h->stream);
+    const uint4* d_in = d_resident;
+    if (!d_in) { h->d_feat.upload(reinterpret_cast<const uint4*>(desc), (size_t)n * 2, h->stream); d_in = h->d_feat.p; }
     if (h->d_leaf.n < (size_t)n) { h->d_leaf.alloc(n + 256); h->d_nid.alloc(n + 256); }
     const int threads = 256;
-    k_voc_descend<<<div_up((long long)n * SUB, threads), threads, 0, h->stream>>>(h->d_feat.p, n, h->d_desc.p, h->d_child_ptr.p,
+    k_voc_descend<<<div_up((long long)n * SUB, threads), threads, 0, h->stream>>>(d_in, n, h->d_desc.p, h->d_child_ptr.p,
                                                                                   h->d_child_idx.p, h->L - levelsup, h->d_leaf.p, h->d_nid.p);
     CCM_LAUNCHED();
     h->h_leaf.resize(n); h->h_nid.resize(n);
@@ -215,6 +217,13 @@ int ccm_voc_transform(ccm_voc_handle* h, const uint8_t* desc, int32_t n, int32_t
   });
 }
 
+int ccm_voc_transform(ccm_voc_handle* h, const uint8_t* desc, int32_t n, int32_t levelsup, uint32_t* word_of_feat, uint32_t* node_of_feat,
+                      double* weight_of_feat, uint32_t* bow_id, double* bow_val, int32_t* bow_n, uint32_t* fv_node_id,
+                      int32_t* fv_node_ptr, uint32_t* fv_feat, int32_t* fv_n_nodes) {
+  return voc_transform_any(h, desc, nullptr, n, levelsup, word_of_feat, node_of_feat, weight_of_feat, bow_id, bow_val, bow_n, fv_node_id,
+                           fv_node_ptr, fv_feat, fv_n_nodes);
+}
+
 int ccm_bow_assemble(int32_t scoring, int32_t weighting, int32_t n, const uint32_t* word_of_feat, const double* weight_of_feat,
                      const uint32_t* node_of_feat, uint32_t* bow_id, double* bow_val, int32_t* bow_n, uint32_t* fv_node_id,
                      int32_t* fv_node_ptr, uint32_t* fv_feat, int32_t* fv_n_nodes) {
@@ -227,3 +236,12 @@ int ccm_bow_assemble(int32_t scoring, int32_t weighting, int32_t n, const uint32
 void ccm_voc_destroy(ccm_voc_handle* h) { delete h; }
 
 }  // extern "C"
+
+namespace ccm {
+int voc_transform_resident(ccm_voc_handle* h, const void* d_desc, int32_t n, int32_t levelsup, uint32_t* word_of_feat, uint32_t* node_of_feat,
+                           double* weight_of_feat, uint32_t* bow_id, double* bow_val, int32_t* bow_n, uint32_t* fv_node_id,
+                           int32_t* fv_node_ptr, uint32_t* fv_feat, int32_t* fv_n_nodes) {
+  return voc_transform_any(h, nullptr, static_cast<const uint4*>(d_desc), n, levelsup, word_of_feat, node_of_feat, weight_of_feat, bow_id, bow_val,
+                           bow_n, fv_node_id, fv_node_ptr, fv_feat, fv_n_nodes);
+}
+}  // namespace ccm

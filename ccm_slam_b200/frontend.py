@@ -312,3 +312,110 @@ class ORBVocabulary:
     def close(self):
         if self.h:
             lib().ccm_voc_destroy(self.h); self.h = C.c_void_p()
+
+
+WIRE_KP_DTYPE = np.dtype([("x", "<f4"), ("y", "<f4"), ("size", "u1"), ("angle", "<f4"), ("response", "u1"), ("octave", "i1")])   # packed: 15 bytes
+assert WIRE_KP_DTYPE.itemsize == 15
+
+
+def wire_keypoints(kps):
+    """ccmslam_msgs/CvKeyPoint[] as ROS serialises it, from a KP_DTYPE array (Converter::toCvKeyPointMsg, S/Converter.cc:166-178:
+    size and response are truncated to uint8, octave to int8)"""
+    w = np.zeros(len(kps), WIRE_KP_DTYPE)
+    w["x"], w["y"], w["angle"] = kps["x"], kps["y"], kps["angle"]
+    w["size"] = kps["size"].astype(np.uint8); w["response"] = kps["response"].astype(np.uint8); w["octave"] = kps["octave"].astype(np.int8)
+    return w
+
+
+def wire_keypoints_decode(wire):
+    """host only: Converter::fromCvKeyPointMsg over n packed wire records"""
+    wire = np.ascontiguousarray(wire)
+    out = np.zeros(len(wire), KP_DTYPE)
+    _chk(lib().ccm_wire_keypoints_decode(_p(wire.view(np.uint8)), len(wire), _p(out)))
+    return out
+
+
+class KeyFrameStore:
+    """Device-resident keyframe features (SURVEY.md §8(f) rank 4): descriptors uploaded once at ingest (KeyFrame::WriteMembersFromMessage,
+    S/KeyFrame.cpp:1662-1726), server-side matchers address keyframes by mUniqueId."""
+
+    def __init__(self):
+        self._h = C.c_void_p()
+        L = lib()
+        L.ccm_kfstore_features.restype = C.c_int32
+        L.ccm_kfstore_keyframes.restype = C.c_int64
+        L.ccm_kfstore_h2d_bytes.restype = C.c_int64
+        for f in (L.ccm_kfstore_features, L.ccm_kfstore_erase):
+            f.argtypes = [C.c_void_p, C.c_uint64]
+        L.ccm_kfstore_keyframes.argtypes = [C.c_void_p]; L.ccm_kfstore_h2d_bytes.argtypes = [C.c_void_p]
+        L.ccm_kfstore_destroy.argtypes = [C.c_void_p]
+        _chk(L.ccm_kfstore_create(C.byref(self._h)))
+
+    def close(self):
+        if self._h:
+            lib().ccm_kfstore_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def put_wire(self, uid, wire_kps, desc):
+        wire_kps = np.ascontiguousarray(wire_kps); desc = np.ascontiguousarray(desc, np.uint8)
+        out = np.zeros(len(wire_kps), KP_DTYPE)
+        _chk(lib().ccm_kfstore_put_wire(self._h, C.c_uint64(uid), len(wire_kps), _p(wire_kps.view(np.uint8)), _p(desc), _p(out)))
+        return out
+
+    def put(self, uid, kps, desc):
+        kps = np.ascontiguousarray(kps); desc = np.ascontiguousarray(desc, np.uint8)
+        _chk(lib().ccm_kfstore_put(self._h, C.c_uint64(uid), len(kps), _p(kps), _p(desc)))
+
+    def erase(self, uid):
+        _chk(lib().ccm_kfstore_erase(self._h, C.c_uint64(uid)))
+
+    def features(self, uid):
+        return lib().ccm_kfstore_features(self._h, C.c_uint64(uid))
+
+    def keyframes(self):
+        return lib().ccm_kfstore_keyframes(self._h)
+
+    def h2d_bytes(self):
+        return lib().ccm_kfstore_h2d_bytes(self._h)
+
+    def get(self, uid):
+        n = self.features(uid)
+        kps = np.zeros(max(n, 0), KP_DTYPE); desc = np.zeros((max(n, 0), 32), np.uint8)
+        _chk(lib().ccm_kfstore_get(self._h, C.c_uint64(uid), _p(kps), _p(desc)))
+        return kps, desc
+
+    def hamming(self, uid1, uid2):
+        D = np.zeros((self.features(uid1), self.features(uid2)), np.uint16)
+        _chk(lib().ccm_kfstore_hamming(self._h, C.c_uint64(uid1), C.c_uint64(uid2), _p(D)))
+        return D
+
+    def hamming_query(self, Q, uid):
+        Q = np.ascontiguousarray(Q, np.uint8)
+        D = np.zeros((len(Q), self.features(uid)), np.uint16)
+        _chk(lib().ccm_kfstore_hamming_query(self._h, _p(Q), len(Q), C.c_uint64(uid), _p(D)))
+        return D
+
+    def SearchByBoW_KF_KF(self, uid1, has1, fv1, uid2, has2, fv2, nnratio=0.6, checkOri=True):
+        has1 = np.ascontiguousarray(has1, np.uint8); has2 = np.ascontiguousarray(has2, np.uint8)
+        out = np.empty(self.features(uid1), np.int32); n = C.c_int32()
+        f1, f2 = fv1.c(), fv2.c()
+        _chk(lib().ccm_kfstore_match_bow_kf_kf(self._h, C.c_uint64(uid1), _p(has1), C.byref(f1), C.c_uint64(uid2), _p(has2), C.byref(f2),
+                                               C.c_float(nnratio), int(checkOri), _p(out), C.byref(n)))
+        return out, n.value
+
+    def transform(self, uid, voc, levelsup=4):
+        """as ORBVocabulary.transform, over the resident descriptors of keyframe uid"""
+        n = self.features(uid)
+        word = np.zeros(n, np.uint32); node = np.zeros(n, np.uint32); weight = np.zeros(n)
+        bow_id = np.zeros(n, np.uint32); bow_val = np.zeros(n); bn = C.c_int32()
+        fid = np.zeros(n, np.uint32); fptr = np.zeros(n + 1, np.int32); ffeat = np.zeros(n, np.uint32); fn = C.c_int32()
+        _chk(lib().ccm_kfstore_transform(self._h, C.c_uint64(uid), voc.h, int(levelsup), _p(word), _p(node), _p(weight), _p(bow_id), _p(bow_val),
+                                         C.byref(bn), _p(fid), _p(fptr), _p(ffeat), C.byref(fn)))
+        return dict(word=word, node=node, weight=weight, bow_id=bow_id[:bn.value].copy(), bow_val=bow_val[:bn.value].copy(),
+                    fv_node_id=fid[:fn.value].copy(), fv_node_ptr=fptr[:fn.value + 1].copy(), fv_feat=ffeat[:fptr[fn.value] if fn.value else 0].copy())
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

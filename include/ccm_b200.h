@@ -493,6 +493,39 @@ int ccm_mirror_ba_problem(ccm_map_mirror* m, uint64_t max_kf_uid, const uint64_t
 long long ccm_mirror_rebuilds(const ccm_map_mirror* m);   /* how many flat passes have run (tests, tuning) */
 int ccm_mirror_set_min_edges(ccm_map_mirror* m, int32_t min_edges);   /* 2 (default, MapFusionGBA) or 1 (BundleAdjustmentClient) */
 
+/* ---- device-resident keyframe features ------------------------------------------------
+ * The server receives every keyframe as a ccmslam_msgs::KF (cslam_msgs/msg/KF.msg) in Communicator::ProcessKfInServer
+ * (cslam/src/Communicator.cpp:815-1140); KeyFrame::WriteMembersFromMessage (cslam/src/KeyFrame.cpp:1662-1726) copies mvKeysUn and
+ * mDescriptors out of it, runs the vocabulary transform, and every later place-recognition / map-fusion matcher call reads the
+ * descriptors from host memory again.  The store takes them ONCE, at ingest, straight from the message's storage — keypoints in the
+ * ROS wire layout of ccmslam_msgs/CvKeyPoint (15 packed bytes: f32 x, f32 y, u8 size, f32 angle, u8 response, i8 octave; decoded
+ * as Converter::fromCvKeyPointMsg does, cslam/src/Converter.cc:180-192), descriptors as the n contiguous 32-byte records of
+ * ccmslam_msgs/Descriptor[] — keeps the descriptors in HBM, and the server-side matchers name their operands by mUniqueId.
+ * Thread-safe; a keyframe is never moved once placed. */
+typedef struct ccm_kf_store ccm_kf_store;
+int ccm_kfstore_create(ccm_kf_store** out);
+void ccm_kfstore_destroy(ccm_kf_store* s);
+int ccm_kfstore_put_wire(ccm_kf_store* s, uint64_t uid, int32_t n, const uint8_t* keypoints_wire /*n*15*/, const uint8_t* descriptors /*n*32*/,
+                         ccm_keypoint* kp_out /*n decoded keypoints for the caller's mvKeysUn, or NULL*/);
+int ccm_kfstore_put(ccm_kf_store* s, uint64_t uid, int32_t n, const ccm_keypoint* kps, const uint8_t* descriptors);
+int ccm_kfstore_erase(ccm_kf_store* s, uint64_t uid);
+int32_t ccm_kfstore_features(ccm_kf_store* s, uint64_t uid);            /* N of the keyframe, -1 if unknown */
+int64_t ccm_kfstore_keyframes(ccm_kf_store* s);
+int64_t ccm_kfstore_h2d_bytes(ccm_kf_store* s);                         /* descriptor bytes uploaded so far (ingest only) */
+int ccm_kfstore_get(ccm_kf_store* s, uint64_t uid, ccm_keypoint* kps /*or NULL*/, uint8_t* descriptors /*or NULL*/);
+int ccm_kfstore_hamming(ccm_kf_store* s, uint64_t uid1, uint64_t uid2, uint16_t* D /*n1*n2*/);
+int ccm_kfstore_hamming_query(ccm_kf_store* s, const uint8_t* Q, int32_t nQ, uint64_t uid, uint16_t* D /*nQ*n*/);
+/* ORBmatcher::SearchByBoW(kfptr, kfptr, vpMatches12) (cslam/src/ORBmatcher.cpp:565-698) on two resident keyframes */
+int ccm_kfstore_match_bow_kf_kf(ccm_kf_store* s, uint64_t uid1, const uint8_t* has_mp1, const ccm_feature_vector* fv1, uint64_t uid2,
+                                const uint8_t* has_mp2, const ccm_feature_vector* fv2, float nnratio, int32_t check_orientation,
+                                int32_t* match12 /*n1*/, int32_t* nmatches);
+/* mpORBvocabulary->transform(vCurrentDesc, mBowVec, mFeatVec, 4) of WriteMembersFromMessage over the resident descriptors; outputs as ccm_voc_transform */
+int ccm_kfstore_transform(ccm_kf_store* s, uint64_t uid, ccm_voc_handle* voc, int32_t levelsup, uint32_t* word_of_feat, uint32_t* node_of_feat,
+                          double* weight_of_feat, uint32_t* bow_id, double* bow_val, int32_t* bow_n, uint32_t* fv_node_id,
+                          int32_t* fv_node_ptr, uint32_t* fv_feat, int32_t* fv_n_nodes);
+/* host only (usable without a device): n wire keypoints -> ccm_keypoint, the arithmetic of Converter::fromCvKeyPointMsg */
+int ccm_wire_keypoints_decode(const uint8_t* keypoints_wire, int32_t n, ccm_keypoint* out);
+
 #ifdef __cplusplus
 }
 #endif

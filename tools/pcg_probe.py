@@ -12,7 +12,15 @@ from ccm_slam_b200 import api, synth  # noqa: E402
 
 name = sys.argv[1]
 variants = sys.argv[2:] or ["-"]
-api.init(0)
+rank, world, local = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1)), int(os.environ.get("LOCAL_RANK", 0))
+api.init(local)
+if world > 1:   # under torchrun: landmark shards + row-distributed PCG, every rank runs every variant, rank 0 reports
+    import torch
+    import torch.distributed as dist
+    dist.init_process_group(backend="gloo")
+    uid = torch.from_numpy(api.comm_unique_id() if rank == 0 else np.zeros(128, np.uint8))
+    dist.broadcast(uid, src=0)
+    api.comm_init(rank, world, uid.numpy())
 t = time.time(); p = synth.make_config(name); print(f"[{name}] K={p.K} P={p.P} E={p.E} generated in {time.time() - t:.1f}s", flush=True)
 os.environ["CCM_PCG_PROF"] = "1"
 ref = None
@@ -32,7 +40,8 @@ for v in variants:
         if ref is None:
             ref = r
         dp = float(np.abs(r["poses"] - ref["poses"]).max()); dx = float(np.abs(r["points"] - ref["points"]).max())
-        print("RESULT " + json.dumps({"variant": v, "iters": int(r["iters_done"]), "trials": int(r["trials_total"]), "pcg_iters": int(r["pcg_iters_total"]),
+        if rank == 0:
+          print("RESULT " + json.dumps({"variant": v, "world": world, "iters": int(r["iters_done"]), "trials": int(r["trials_total"]), "pcg_iters": int(r["pcg_iters_total"]),
                                       "pcg_not_converged": int(r["pcg_not_converged"]), "chi2_final": r["chi2_final"],
                                       "kernels_ms": {k: round(x["total_ms"], 3) for k, x in st.items() if x["launches"]},
                                       "all_kernels_ms": round(tot, 3), "event_ms": round(r["t_optimize_event_ms"], 3),
@@ -41,6 +50,7 @@ for v in variants:
                                       "pcg_cycles": cyc, "max_abs_diff_vs_first": [dp, dx]}), flush=True)
         h.close()
     except Exception as e:  # keep going: the other variants still tell something
-        print("RESULT " + json.dumps({"variant": v, "error": str(e)}), flush=True)
+        if rank == 0:
+          print("RESULT " + json.dumps({"variant": v, "world": world, "error": str(e)}), flush=True)
     for k in keys:
         os.environ.pop(k, None)
