@@ -108,7 +108,8 @@ struct ccm_ba_handle {
     char* window = nullptr;          // own exchange window (plain cudaMalloc: exportable through cudaIpc)
     std::vector<char*> peer;         // every rank's window as mapped here; peer[rank] == window
     DevBuf<char*> d_win;
-    DevBuf<int> items, cta_row, cta_item;
+    DevBuf<int> items, cta_row, cta_item, rank_row;
+    DevBuf<unsigned char> need;
     DevBuf<double> yc, tpart;
     int r0 = 0, r1 = 0, rank = 0, grid = 1;
     long long nitems = 0;
@@ -368,8 +369,10 @@ void step_pcg(ccm_ba_handle* h, double tol, int max_iter) {
     b.yc = d.yc.p; b.tpart = d.tpart.p;
     b.rank = h->rank; b.nranks = h->nranks; b.r0 = d.r0; b.r1 = d.r1; b.win = d.d_win.p;
     b.off_z = d.lay.off_z; b.off_scal = d.lay.off_scal; b.off_t = d.lay.off_t; b.off_x = d.lay.off_x;
-    b.off_flags = d.lay.off_flags; b.off_ctl = d.lay.off_ctl;
+    b.off_flags = d.lay.off_flags; b.off_ctl = d.lay.off_ctl; b.off_lls = d.lay.off_lls; b.off_llt = d.lay.off_llt;
+    b.rank_row = d.rank_row.p; b.need = d.need.p;
     b.epoch0 = (++d.launches) << 24;   // every rank issues the same sequence of solves: the epochs line up and only grow
+    b.ll_epoch0 = (unsigned)((d.launches & 0x7FFFFu) << 13) | 0x1000u;   // + 2 (it + 1) + {0, 1} <= 4003 below bit 12; never 0
     b.timeout_cycles = d.timeout_cycles;
     b.prof = h->pcg_prof.p;
     CCM_CUDA(cudaMemsetAsync(h->pcg_bar.p, 0, 2 * sizeof(unsigned), s));
@@ -479,7 +482,13 @@ void setup_pcg_dist(ccm_ba_handle* h) {
 // pcg2.cuh set-up: own rows, item records, CTA cuts, exchange window (IPC-mapped on every rank when nranks > 1).
 // CCM_PCG_IMPL=1 keeps the first-generation kernel (replicated solve on several ranks).
 void setup_pcg2(ccm_ba_handle* h, const std::vector<int>& rowptr) {
-  if (env_int("CCM_PCG_IMPL", 2) != 2 || h->Kf < 1 || h->Kf < h->nranks) return;
+  // The streamed / distributed kernel pays off when S is large: cfg5 (788 k blocks, 227 MB) 64 -> 41 ms per Global BA on one GPU and
+  // it is the only solve that scales across ranks.  Small systems (cfg3 / cfg4, LocalBA: a few 10 k blocks) are latency-bound: there
+  // the first-generation kernel is 10 % faster on one GPU (cfg4 19.8 vs 22.0 ms) and, replicated, 50 % faster than a solve that
+  // crosses NVLink twice per iteration (cfg4 at N = 2: 20.9 vs 32.4 ms; profiles/r2).  CCM_PCG_IMPL = 1 / 2 forces one of them.
+  const int impl = env_int("CCM_PCG_IMPL", 0);
+  if (impl == 1 || h->Kf < 1 || h->Kf < h->nranks) return;
+  if (impl != 2 && rowptr[h->Kf] < env_int("CCM_PCG2_MIN_BLOCKS", 200000)) return;
   if (h->pcg_agg > 0 && 6 * h->pcg_nc > P2_MAX_NC) return;
   static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
   ccm_ba_handle::Pcg2& d = h->p2;
@@ -494,8 +503,12 @@ void setup_pcg2(ccm_ba_handle* h, const std::vector<int>& rowptr) {
     const long long want = (long long)rowptr[Kf] * k / N;
     return (int)(std::lower_bound(rowptr.begin(), rowptr.end(), (int)want) - rowptr.begin());
   };
-  d.r0 = std::min(cut(h->rank), Kf);
-  d.r1 = std::min(std::max(cut(h->rank + 1), d.r0), Kf);
+  std::vector<int> rank_row((size_t)N + 1);
+  for (int k = 0; k <= N; k++) rank_row[k] = std::min(cut(k), Kf);
+  for (int k = 1; k <= N; k++) rank_row[k] = std::max(rank_row[k], rank_row[k - 1]);
+  d.r0 = rank_row[h->rank];
+  d.r1 = rank_row[h->rank + 1];
+  upload_vec(d.rank_row, rank_row, s);
   const int rows = d.r1 - d.r0;
   // items: <= 16 consecutive blocks of one row
   std::vector<int> row_item((size_t)rows + 1, 0);
@@ -526,8 +539,9 @@ void setup_pcg2(ccm_ba_handle* h, const std::vector<int>& rowptr) {
   upload_vec(d.cta_row, cta_row, s);
   upload_vec(d.cta_item, cta_item, s);
   d.items.alloc(std::max<size_t>((size_t)d.nitems * P2_REC, 1));
+  d.need.alloc_zero(std::max(Kf, 1), s);
   if (rows > 0) {
-    k_pcg2_items<<<div_up(rows, 128), 128, 0, s>>>(h->s_rowptr.p, h->s_col.p, d_row_item.p, d.r0, d.r1, d.items.p);
+    k_pcg2_items<<<div_up(rows, 128), 128, 0, s>>>(h->s_rowptr.p, h->s_col.p, d_row_item.p, d.r0, d.r1, d.items.p, d.need.p);
     CCM_LAUNCHED();
   }
   d.yc.alloc_zero(std::max<size_t>((size_t)2 * nC, 1), s);
@@ -883,13 +897,17 @@ void build(ccm_ba_handle* h, const ccm_ba_problem* p) {
     CCM_LAUNCHED();
   }
 
-  if (h->nprod && env_int("CCM_SCHUR_SORT", 1)) {   // landmark order inside every list: deterministic sums, shared Z rows meet in L1
+  // Measured on cfg5 (profiles/r2/schur_tiled_cfg5.log): sorted lists 8.42 ms vs 8.43 ms unsorted, tiles 2x2 8.16 ms, 3x3 8.72 ms,
+  // 4x4 15.3 ms (the long diagonal lists keep a 16-warp CTA alive while 12 warps idle) -- the gather is not L1-reuse bound.  Both
+  // stay available for experiments (CCM_SCHUR_SORT=1, CCM_SCHUR=9 + CCM_SCHUR_TILE) but cost set-up time, so they are off by default.
+  const bool want_tiles = schur_mode() == 9;
+  if (h->nprod && env_int("CCM_SCHUR_SORT", want_tiles ? 1 : 0)) {   // landmark order inside every list: deterministic sums
     k_sort_products<<<nub, 256, 0, s>>>(h->u_prod_ptr.p, nub, h->prod.p);
     CCM_LAUNCHED();
   }
-  h->tile_T = env_int("CCM_SCHUR_TILE", 4);
+  h->tile_T = env_int("CCM_SCHUR_TILE", 2);
   h->ntiles = 0;
-  if (nub > 0 && h->nprod && (h->tile_T == 2 || h->tile_T == 3 || h->tile_T == 4)) {
+  if (want_tiles && nub > 0 && h->nprod && (h->tile_T == 2 || h->tile_T == 3 || h->tile_T == 4)) {
     // tile schedule: sort the upper blocks by (row group, column group), cut where the tile changes
     DevBuf<unsigned long long> k_in, k_out;
     DevBuf<int> v_in, v_out, head, rank;
@@ -951,7 +969,12 @@ void build(ccm_ba_handle* h, const ccm_ba_problem* p) {
   // iteration count; the inverse is refreshed every 2nd / 4th solve (measured sweeps: tools/ba_probe.py with CCM_PCG_NC/REFRESH)
   // CCM_PCG_PROLONG=1: piecewise-linear prolongation (pcg.cuh); half the coarse nodes then already beat the constant P
   h->pcg_prolong = env_int("CCM_PCG_PROLONG", 1) ? 1 : 0;  // default since round 2 (cfg5: 1538 -> 617 PCG iterations per Global BA, profiles/r2/prolong_cfg5.log)
-  pcg_coarse_shape(Kf, env_int("CCM_PCG_NC", Kf >= 4096 ? (h->pcg_prolong ? 192 : 384) : 128), &h->pcg_agg, &h->pcg_nc);
+  // measured on cfg5 with pcg2 (profiles/r2/pcg2_sweep_cfg5.log; PCG iterations / PCG ms per Global BA): NC 192 refresh 4: 617 / 45.9,
+  // NC 192 refresh 2: 545 / 46.5, NC 256 refresh 2: 400 / 40.2, NC 256 refresh 1: 384 / 52.5, NC 384 refresh 4: 357 / 49.1 (the
+  // 2304^2 inverse costs 12 ms), NC 128 refresh 1: 1014 / 74.5; refresh 8 (one inverse per BA): 1950 iterations
+  pcg_coarse_shape(Kf, env_int("CCM_PCG_NC", Kf >= 4096 ? (h->pcg_prolong ? 256 : 384) : 128), &h->pcg_agg, &h->pcg_nc);
+  // refresh 2 / 3 / 4 with NC 256: 400 / 427 / 496 iterations, 41.0 / 39.2 / 40.3 ms on one GPU (profiles/r2/b8_cfg5.log): flat, so the
+  // large systems take the fewest inversions (the inverse is replicated work on several ranks); small systems keep 2
   h->pcg_refresh = std::max(1, env_int("CCM_PCG_REFRESH", Kf >= 4096 ? 4 : 2));
   {
     const size_t nC = (size_t)6 * h->pcg_nc;

@@ -18,12 +18,16 @@
 //    own rows, rc update (every CTA keeps rc in shared memory), the CTA's slice of the dense coarse product yc = Ainv rc.
 //    Phase 3: z = Minv r + P yc, r.z, r.r.
 //  * N ranks: rank k owns the block rows [r0, r1) (S is present on every rank after the all-reduce of the Schur blocks).
-//    Synchronisations A (after phase 1) and B (after phase 3) become node-wide: CTA 0 sums the CTA partials in a fixed order and
-//    stores them — and after phase 1 its P^T q partial — straight into every peer's exchange window (cudaIpc-mapped, plain
-//    st.global over NVLink), raises a flag in every peer's window (st.release.sys) and waits for the peers' flags; z slices are
-//    stored into every peer's window by the rows' owners in phase 3.  Every rank then forms the same scalars from the same
-//    numbers in rank order and takes the same branches: no broadcast, no host round trip, no NCCL launch inside the solve.
-//    Every spin carries a clock64 time-out that raises a node-wide abort word (status 3) instead of hanging the GPU.
+//    Synchronisations A (after phase 1) and B (after phase 3) stay local grid barriers; what crosses NVLink rides next to them:
+//    once the local CTAs have arrived, CTA 0 sums the CTA partials in a fixed order and stores them — and after phase 1 its
+//    P^T q partial — straight into every peer's exchange window (cudaIpc-mapped) as 16-byte low-latency packets
+//    {lo32, epoch, hi32, epoch}: each 8-byte half is delivered atomically, so a reader that finds the epoch of this
+//    synchronisation in both halves has the value — one NVLink traversal, no system-scope fence, no separate flag
+//    (measured with flag words + fence.sys: +11 us per synchronisation).  z is not pushed at all: an owner writes its rows into
+//    its own window, and a peer that needs a row of another rank (band rows next to the cut, loop closures) loads it over
+//    NVLink after the owner's B packet has arrived.  Every rank forms the same scalars from the same numbers in rank order and
+//    takes the same branches: no broadcast, no host round trip, no NCCL launch inside the solve.  Every spin carries a
+//    clock64 time-out that raises a node-wide abort word (status 3) instead of hanging the GPU.
 //
 // Exchange-window hazards: everything in a window is double-buffered by iteration parity; a region written in iteration i is
 // next written in iteration i + 2, and a rank gets there only through two node-wide barriers that every rank joins after it
@@ -64,6 +68,10 @@ struct Pcg2Args {
   int rank, nranks, r0, r1;
   char* const* win;            // [nranks] exchange windows as mapped in this process; win[rank] is local
   size_t off_z, off_scal, off_t, off_x, off_flags, off_ctl;
+  size_t off_lls, off_llt;     // low-latency packets: scalars [2][nranks][4], P^T q [2][nranks][6 nc], 16 bytes each
+  const int* rank_row;         // [nranks + 1] first block row of every rank
+  const unsigned char* need;   // [n] 1 where some block of this rank's rows sits in that block column (the rows of p / z this rank reads)
+  unsigned ll_epoch0;          // packets of this launch carry ll_epoch0 + 2 (it + 1) + {0: A, 1: B}; never 0
   unsigned long long epoch0;   // node barrier epochs of this launch start here (flags only ever grow)
   long long timeout_cycles;
   long long* prof;             // optional 8 cycle counters (CTA 0): [0] set-up, [1] product, [2] coarse, [3] precondition
@@ -112,6 +120,25 @@ __device__ __forceinline__ unsigned long long p2_ld_acquire_sys(const unsigned l
 }
 __device__ __forceinline__ void p2_st_release_sys(unsigned long long* p, unsigned long long v) {
   asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// low-latency packet: a double as two (32-bit half, 32-bit epoch) pairs; NVLink delivers every aligned 8-byte unit atomically
+__device__ __forceinline__ void p2_ll_store(void* slot, double v, unsigned flag) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(slot), "r"((unsigned)b), "r"(flag), "r"((unsigned)(b >> 32)), "r"(flag)
+               : "memory");
+}
+__device__ __forceinline__ bool p2_ll_try(const void* slot, unsigned flag, double& v) {
+  unsigned a, f1, b, f2;
+  asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(a), "=r"(f1), "=r"(b), "=r"(f2) : "l"(slot) : "memory");
+  if (f1 != flag || f2 != flag) return false;
+  v = __longlong_as_double((long long)(((unsigned long long)b << 32) | a));
+  return true;
+}
+__device__ __forceinline__ double p2_ld_volatile(const double* p) {
+  double v;
+  asm volatile("ld.volatile.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
 }
 
 // Grid-wide (cross = false) or node-wide (cross = true and nranks > 1) barrier.  Every CTA arrives at a counter; CTA 0 waits for
@@ -222,6 +249,31 @@ __global__ void __launch_bounds__(P2_TPB, 1) k_pcg2(Pcg2Args A) {
   auto zbuf = [&](int k, int par) { return reinterpret_cast<double*>(A.win[k] + A.off_z) + (size_t)par * nv; };
   auto scal = [&](int k, int par, int src) { return reinterpret_cast<double*>(A.win[k] + A.off_scal) + ((size_t)par * N + src) * 4; };
   auto texch = [&](int k, int par, int src) { return reinterpret_cast<double*>(A.win[k] + A.off_t) + ((size_t)par * N + src) * (size_t)nC; };
+  // low-latency packet slots in rank k's window, written by rank src: 4 scalars ([0] p.q, [1] coarse flag, [2] r.z, [3] r.r), 6 nc of P^T q
+  auto lls = [&](int k, int par, int src, int which) { return A.win[k] + A.off_lls + (((size_t)par * N + src) * 4 + which) * 16; };
+  auto llt = [&](int k, int par, int src, int j) { return A.win[k] + A.off_llt + (((size_t)par * N + src) * (size_t)nC + j) * 16; };
+  volatile unsigned* ctl_word = reinterpret_cast<volatile unsigned*>(A.win[me] + A.off_ctl);
+  bool ll_ok = true;   // cleared when a packet did not arrive in time (a peer aborted or died): the solve ends with status 3
+  auto ll_wait = [&](const void* slot, unsigned ep) -> double {
+    double v = 0.0;
+    if (p2_ll_try(slot, ep, v)) return v;
+    const long long t0 = clock64();
+    while (!p2_ll_try(slot, ep, v))
+      if (*ctl_word || clock64() - t0 > A.timeout_cycles) {
+        for (int k = 0; k < N; k++) *reinterpret_cast<volatile unsigned*>(A.win[k] + A.off_ctl) = 1u;
+        ll_ok = false;
+        return 0.0;
+      }
+    return v;
+  };
+  // owner of block row a, and z of any row: own rows from the local window, rows of another rank over NVLink from its window
+  auto owner_of = [&](int a) { int k = 0; while (k + 1 < N && a >= A.rank_row[k + 1]) k++; return k; };
+  auto load_z = [&](int par, size_t g) -> double {
+    const int a = (int)(g / BS);
+    if (N == 1 || (a >= A.r0 && a < A.r1)) return __ldcg(zbuf(me, par) + g);
+    return p2_ld_volatile(zbuf(owner_of(a), par) + g);
+  };
+  __shared__ double sm_ll[8][4];
 
   // ---- this CTA's rows and items, this warp's run of items, its ring ------------------------------------------------------
   const int c0 = A.cta_row[blockIdx.x], c1 = A.cta_row[blockIdx.x + 1];
@@ -231,7 +283,25 @@ __global__ void __launch_bounds__(P2_TPB, 1) k_pcg2(Pcg2Args A) {
   const int nwi = we - wb;
   double* ring = sm_ring + (size_t)wid * 2 * P2_ITEM_DOUBLES;
   uint64_t* mb = sm_mbar + wid * 2;
-  // direction window: the CTA's rows with an equal halo on both sides, at most P2_WIN_ROWS rows
+  // direction window: the block columns this CTA's items touch (one pass over its records), at most P2_WIN_ROWS rows around its own rows
+  __shared__ int s_cmin, s_cmax;
+  if (tid == 0) { s_cmin = A.n; s_cmax = -1; }
+  __syncthreads();
+  {
+    int cmin = A.n, cmax = -1;
+    for (int k = wb; k < we; k++) {
+      const int* rec = A.items + (size_t)k * P2_REC;
+      const int nb = __ldg(rec + 1);
+      if (lane < nb) { const int c = __ldg(rec + 4 + lane); cmin = c < cmin ? c : cmin; cmax = c > cmax ? c : cmax; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const int a = __shfl_xor_sync(0xffffffffu, cmin, o), b = __shfl_xor_sync(0xffffffffu, cmax, o);
+      cmin = a < cmin ? a : cmin; cmax = b > cmax ? b : cmax;
+    }
+    if (lane == 0 && cmax >= 0) { atomicMin(&s_cmin, cmin); atomicMax(&s_cmax, cmax); }
+  }
+  __syncthreads();
   int wlo = c0, whi = c1;
   if (c1 > c0) {
     if (c1 - c0 >= P2_WIN_ROWS) whi = c0 + P2_WIN_ROWS;
@@ -239,6 +309,10 @@ __global__ void __launch_bounds__(P2_TPB, 1) k_pcg2(Pcg2Args A) {
       const int halo = (P2_WIN_ROWS - (c1 - c0)) / 2;
       wlo = c0 - halo < 0 ? 0 : c0 - halo;
       whi = c1 + halo > A.n ? A.n : c1 + halo;
+      if (s_cmax >= 0) {   // no wider than what the items read
+        wlo = wlo < s_cmin ? (s_cmin < c0 ? s_cmin : c0) : wlo;
+        whi = whi > s_cmax + 1 ? (s_cmax + 1 > c1 ? s_cmax + 1 : c1) : whi;
+      }
     }
   }
   if (lane == 0) { p2_mbar_init(mb, 1); p2_mbar_init(mb + 1, 1); }
@@ -292,20 +366,23 @@ __global__ void __launch_bounds__(P2_TPB, 1) k_pcg2(Pcg2Args A) {
       double* pnew = A.p + (size_t)(pc ^ 1) * nv;
       const double* z = zbuf(me, par);
       // ---------------- phase 1: q = S p on the own rows, p.q, P^T q ----------------------------------------------------
+      // every rank keeps the whole direction p: the rows of other ranks are updated from their owners' z (pulled over NVLink); the
+      // first element of every thread is requested now and consumed after the product, so the round trip hides behind it
+      const size_t gstride = (size_t)G * P2_TPB, g_first = (size_t)blockIdx.x * P2_TPB + tid;
+      double z_first = 0.0;
+      const bool first_remote = N > 1 && g_first < nv && ((int)(g_first / BS) < A.r0 || (int)(g_first / BS) >= A.r1) && A.need[g_first / BS];
+      if (first_remote) z_first = load_z(par, g_first);
       for (int i = tid; i < (whi - wlo) * BS; i += P2_TPB) {
         const size_t g = (size_t)wlo * BS + i;
-        sm_pwin[i] = fma(beta, __ldcg(pold + g), __ldcg(z + g));
+        const int a = wlo + i / BS;
+        const bool mine = N == 1 || (a >= A.r0 && a < A.r1);
+        sm_pwin[i] = (mine || A.need[a]) ? fma(beta, __ldcg(pold + g), load_z(par, g)) : 0.0;   // rows of other ranks only where some block reads them
       }
-      if (N > 1)  // every rank keeps the whole direction: rows of other ranks are updated here, own rows by their row's warp
-        for (size_t i = (size_t)blockIdx.x * P2_TPB + tid; i < nv; i += (size_t)G * P2_TPB) {
-          const int a = (int)(i / BS);
-          if (a < A.r0 || a >= A.r1) pnew[i] = fma(beta, __ldcg(pold + i), __ldcg(z + i));
-        }
       __syncthreads();
       auto pvec = [&](int col, int k) -> double {  // component k of p at block column col
         if (col >= wlo && col < whi) return sm_pwin[(size_t)(col - wlo) * BS + k];
         const size_t g = (size_t)col * BS + k;
-        return fma(beta, __ldcg(pold + g), __ldcg(z + g));
+        return fma(beta, __ldcg(pold + g), load_z(par, g));
       };
       P2CoarseAcc cs{-1, 0.0, 0.0};
       auto row_done = [&](int a, double yv) {  // lanes 0..5 hold the components of (S p)_a
@@ -406,6 +483,11 @@ __global__ void __launch_bounds__(P2_TPB, 1) k_pcg2(Pcg2Args A) {
         }
         if (coarse) { p2_cflush(A, tp, cs.cur, cs.l, lane); p2_cflush(A, tp, cs.cur + 1, cs.h, lane); }
       }
+      if (N > 1)
+        for (size_t i = g_first; i < nv; i += gstride) {
+          const int a = (int)(i / BS);
+          if ((a < A.r0 || a >= A.r1) && A.need[a]) pnew[i] = fma(beta, __ldcg(pold + i), i == g_first ? z_first : load_z(par, i));
+        }
     } else if (coarse) {
       // set-up pass: P^T b of the CTA's rows (rows in increasing order per warp: the running sums still apply)
       P2CoarseAcc cs{-1, 0.0, 0.0};
@@ -421,29 +503,37 @@ __global__ void __launch_bounds__(P2_TPB, 1) k_pcg2(Pcg2Args A) {
       if (tid == 0) part0[blockIdx.x] = t0;
     }
     // ---------------- synchronisation A: p.q and P^T q of every rank ---------------------------------------------------------
-    alive = p2_barrier(A, gen, epoch, true, false, &s_ok, [&] {
+    const unsigned epA = A.ll_epoch0 + 2u * (unsigned)(it + 1), epB = epA + 1u;
+    alive = p2_barrier(A, gen, epoch, false, false, &s_ok, [&] {
       if (N == 1) return;
-      if (wid == 0) {
-        const double v = sum_partials_dev(part0, G);
-        if (lane < N) {
-          double* s = scal(lane, par, me);
-          s[0] = v;
-          if (it < 0) s[3] = coarse ? 1.0 : 0.0;
-        }
+      const double v = sum_partials_dev(part0, G);   // every warp of CTA 0 forms the same sum
+      if (tid < N && tid != me) {
+        p2_ll_store(lls(tid, par, me, 0), v, epA);
+        if (it < 0) p2_ll_store(lls(tid, par, me, 1), coarse ? 1.0 : 0.0, epA);
       }
       for (int i = tid; i < nC * N; i += P2_TPB) {
         const int k = i / nC, j = i - k * nC;
-        texch(k, par, me)[j] = __ldcg(tp + j);
+        if (k != me) p2_ll_store(llt(k, par, me, j), __ldcg(tp + j), epA);
       }
     });
     if (!alive) break;
+    if (N > 1) {  // the peers' packets: thread k < N fetches rank k's scalars for the whole CTA
+      if (wid == 0) {
+        const double own = sum_partials_dev(part0, G);
+        if (lane < N) {
+          sm_ll[lane][0] = lane == me ? own : ll_wait(lls(me, par, lane, 0), epA);
+          sm_ll[lane][1] = (it < 0 && lane != me) ? ll_wait(lls(me, par, lane, 1), epA) : 1.0;
+        }
+      }
+      if (__syncthreads_or(!ll_ok)) { alive = false; break; }
+    }
     lap(it < 0 ? 0 : 1);
     // ---------------- phase 2: alpha; x, r on the CTA's rows; rc; the CTA's slice of yc = Ainv rc -----------------------------
     double alpha = 1.0;
     if (it >= 0) {
       double pq;
       if (N == 1) pq = sum_partials_dev(part0, G);
-      else { pq = 0.0; for (int k = 0; k < N; k++) pq += __ldcg(scal(me, par, k)); }
+      else { pq = 0.0; for (int k = 0; k < N; k++) pq += sm_ll[k][0]; }
       if (!(pq > 0.0) || !isfinite(pq)) { flag = 2; break; }
       alpha = rz / pq;
       const double* pnew = A.p + (size_t)(pc ^ 1) * nv;
@@ -454,7 +544,7 @@ __global__ void __launch_bounds__(P2_TPB, 1) k_pcg2(Pcg2Args A) {
       }
     } else if (N > 1) {  // the ranks invert their coarse matrices independently: use the coarse level only if all of them can
       double all = 1.0;
-      for (int k = 0; k < N; k++) all = fmin(all, __ldcg(scal(me, par, k) + 3));
+      for (int k = 0; k < N; k++) all = fmin(all, sm_ll[k][1]);
       coarse = coarse && all > 0.0;
     }
     if (coarse) {
@@ -462,10 +552,10 @@ __global__ void __launch_bounds__(P2_TPB, 1) k_pcg2(Pcg2Args A) {
       for (int j = tid; j < nC; j += P2_TPB) {
         double t;
         if (N == 1) t = __ldcg(tp + j);
-        else { t = 0.0; for (int k = 0; k < N; k++) t += __ldcg(texch(me, par, k) + j); }
+        else { t = 0.0; for (int k = 0; k < N; k++) t += k == me ? __ldcg(tp + j) : ll_wait(llt(me, par, k, j), epA); }
         sm_rc[j] = fma(sgn, t, sm_rc[j]);
       }
-      __syncthreads();
+      if (__syncthreads_or(!ll_ok)) { alive = false; break; }
       const int i0 = (int)((long long)nC * blockIdx.x / G), i1 = (int)((long long)nC * (blockIdx.x + 1) / G);
       for (int i = i0 + wid; i < i1; i += P2_W) {
         const double* arow = A.Ainv + (size_t)i * nC;
@@ -494,7 +584,7 @@ __global__ void __launch_bounds__(P2_TPB, 1) k_pcg2(Pcg2Args A) {
         if (pa.w1 != 0.0) zv += pa.w1 * __ldcg(A.yc + (size_t)par * nC + (size_t)pa.hi * BS + c);
       }
       const double rv = rrow[c];
-      for (int k = 0; k < N; k++) zbuf(k, par ^ 1)[(size_t)a * BS + c] = zv;
+      zbuf(me, par ^ 1)[(size_t)a * BS + c] = zv;   // own window only: peers pull the rows they need
       acc_rz += rv * zv;
       acc_rr += rv * rv;
     }
@@ -506,21 +596,30 @@ __global__ void __launch_bounds__(P2_TPB, 1) k_pcg2(Pcg2Args A) {
       if (tid == 0) { part1[blockIdx.x] = t0; part2[blockIdx.x] = t1; }
     }
     // ---------------- synchronisation B: r.z, r.r of every rank; the z slices are in place --------------------------------------
-    alive = p2_barrier(A, gen, epoch, true, true, &s_ok, [&] {
+    alive = p2_barrier(A, gen, epoch, false, false, &s_ok, [&] {
       if (N == 1) return;
-      if (wid == 0) {
-        const double v1 = sum_partials_dev(part1, G);
-        const double v2 = sum_partials_dev(part2, G);
-        if (lane < N) { double* s = scal(lane, par, me); s[1] = v1; s[2] = v2; }
-      }
+      __threadfence_system();   // this rank's z rows (all CTAs have arrived) are ordered before the packets that announce them
+      const double v1 = sum_partials_dev(part1, G);
+      const double v2 = sum_partials_dev(part2, G);
+      if (tid < N && tid != me) { p2_ll_store(lls(tid, par, me, 2), v1, epB); p2_ll_store(lls(tid, par, me, 3), v2, epB); }
     });
     if (!alive) break;
+    if (N > 1) {
+      if (wid == 0) {
+        const double o1 = sum_partials_dev(part1, G), o2 = sum_partials_dev(part2, G);
+        if (lane < N) {
+          sm_ll[lane][2] = lane == me ? o1 : ll_wait(lls(me, par, lane, 2), epB);
+          sm_ll[lane][3] = lane == me ? o2 : ll_wait(lls(me, par, lane, 3), epB);
+        }
+      }
+      if (__syncthreads_or(!ll_ok)) { alive = false; break; }
+    }
     lap(it < 0 ? 0 : 3);
     double rz_new, rr_new;
     if (N == 1) { rz_new = sum_partials_dev(part1, G); rr_new = sum_partials_dev(part2, G); }
     else {
       rz_new = 0.0; rr_new = 0.0;
-      for (int k = 0; k < N; k++) { rz_new += __ldcg(scal(me, par, k) + 1); rr_new += __ldcg(scal(me, par, k) + 2); }
+      for (int k = 0; k < N; k++) { rz_new += sm_ll[k][2]; rr_new += sm_ll[k][3]; }
     }
     if (it < 0) {
       rz = rz_new; bb = rr_new; rr = bb;
@@ -563,7 +662,7 @@ __global__ void __launch_bounds__(P2_TPB, 1) k_pcg2(Pcg2Args A) {
 
 // byte layout of one exchange window
 struct Pcg2Layout {
-  size_t off_z, off_scal, off_t, off_x, off_flags, off_ctl, bytes;
+  size_t off_z, off_scal, off_t, off_x, off_flags, off_ctl, off_lls, off_llt, bytes;
 };
 inline Pcg2Layout pcg2_layout(int n, int nranks, int nC) {
   Pcg2Layout L;
@@ -576,13 +675,15 @@ inline Pcg2Layout pcg2_layout(int n, int nranks, int nC) {
   L.off_x = take(nv * sizeof(double));
   L.off_flags = take((size_t)nranks * sizeof(unsigned long long));
   L.off_ctl = take(sizeof(unsigned));
+  L.off_lls = take((size_t)2 * nranks * 4 * 16);
+  L.off_llt = take((size_t)2 * nranks * (nC > 0 ? nC : 1) * 16);
   L.bytes = o;
   return L;
 }
 
 // item records of the rows [r0, r1): one thread per row
 __global__ void k_pcg2_items(const int* __restrict__ rowptr, const int* __restrict__ col, const int* __restrict__ row_item, int r0, int r1,
-                             int* __restrict__ items) {
+                             int* __restrict__ items, unsigned char* __restrict__ need) {
   const int a = r0 + blockIdx.x * blockDim.x + threadIdx.x;
   if (a >= r1) return;
   const int beg = rowptr[a], end = rowptr[a + 1];
@@ -592,7 +693,11 @@ __global__ void k_pcg2_items(const int* __restrict__ rowptr, const int* __restri
     const int nb = end - j < P2_ITEM_BLOCKS ? end - j : P2_ITEM_BLOCKS;
     rec[0] = j; rec[1] = nb; rec[2] = a;
     rec[3] = (j == beg ? 1 : 0) | (j + P2_ITEM_BLOCKS >= end ? 2 : 0);
-    for (int k = 0; k < P2_ITEM_BLOCKS; k++) rec[4 + k] = k < nb ? col[j + k] : 0;
+    for (int k = 0; k < P2_ITEM_BLOCKS; k++) {
+      const int c = k < nb ? col[j + k] : 0;
+      rec[4 + k] = c;
+      if (k < nb) need[c] = 1;   // (many writers, one value)
+    }
   }
 }
 

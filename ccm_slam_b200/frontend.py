@@ -385,19 +385,19 @@ class KeyFrameStore:
         return kps, desc
 
     def hamming(self, uid1, uid2):
-        D = np.zeros((self.features(uid1), self.features(uid2)), np.uint16)
+        D = np.zeros((max(self.features(uid1), 0), max(self.features(uid2), 0)), np.uint16)   # unknown ids: the call reports them
         _chk(lib().ccm_kfstore_hamming(self._h, C.c_uint64(uid1), C.c_uint64(uid2), _p(D)))
         return D
 
     def hamming_query(self, Q, uid):
         Q = np.ascontiguousarray(Q, np.uint8)
-        D = np.zeros((len(Q), self.features(uid)), np.uint16)
+        D = np.zeros((len(Q), max(self.features(uid), 0)), np.uint16)
         _chk(lib().ccm_kfstore_hamming_query(self._h, _p(Q), len(Q), C.c_uint64(uid), _p(D)))
         return D
 
     def SearchByBoW_KF_KF(self, uid1, has1, fv1, uid2, has2, fv2, nnratio=0.6, checkOri=True):
         has1 = np.ascontiguousarray(has1, np.uint8); has2 = np.ascontiguousarray(has2, np.uint8)
-        out = np.empty(self.features(uid1), np.int32); n = C.c_int32()
+        out = np.empty(max(self.features(uid1), 0), np.int32); n = C.c_int32()
         f1, f2 = fv1.c(), fv2.c()
         _chk(lib().ccm_kfstore_match_bow_kf_kf(self._h, C.c_uint64(uid1), _p(has1), C.byref(f1), C.c_uint64(uid2), _p(has2), C.byref(f2),
                                                C.c_float(nnratio), int(checkOri), _p(out), C.byref(n)))
@@ -405,7 +405,7 @@ class KeyFrameStore:
 
     def transform(self, uid, voc, levelsup=4):
         """as ORBVocabulary.transform, over the resident descriptors of keyframe uid"""
-        n = self.features(uid)
+        n = max(self.features(uid), 0)
         word = np.zeros(n, np.uint32); node = np.zeros(n, np.uint32); weight = np.zeros(n)
         bow_id = np.zeros(n, np.uint32); bow_val = np.zeros(n); bn = C.c_int32()
         fid = np.zeros(n, np.uint32); fptr = np.zeros(n + 1, np.int32); ffeat = np.zeros(n, np.uint32); fn = C.c_int32()

@@ -19,8 +19,8 @@ for label, env, mode in [("untiled prefetch, unsorted lists", {"CCM_SCHUR_SORT":
     for k, v in env.items():
         os.environ[k] = v
     try:
+        api._chk(api.lib().ccm_ba_debug_set_schur_mode(mode))     # before the handle: the tile schedule is built at create time for mode 9
         t0 = time.time(); h = api.BAHandle(p); t_create = time.time() - t0
-        api._chk(api.lib().ccm_ba_debug_set_schur_mode(mode))
         ms = [round(h.time_kernel(4, reps=5, lam=1e-3), 4) for _ in range(2)]
         h.reset(); h.set_profile(True)
         r = h.optimize(iterations=20, want_state=True)
