@@ -403,7 +403,8 @@ __global__ void __launch_bounds__(CTA) k_schur_mma(const uint2* __restrict__ pro
                                                    const double* __restrict__ Z, const int* __restrict__ o_lm,
                                                    const double* __restrict__ gvec, double* __restrict__ U_val,
                                                    double* __restrict__ bneg, const int* __restrict__ tile_ptr = nullptr,
-                                                   const int* __restrict__ tile_u = nullptr) {
+                                                   const int* __restrict__ tile_u = nullptr,
+                                                   const unsigned char* __restrict__ covered = nullptr) {
   static_assert(UNROLL % 2 == 0, "products alternate between two accumulator sets");
   int warp;
   if (TILED) {
@@ -415,6 +416,7 @@ __global__ void __launch_bounds__(CTA) k_schur_mma(const uint2* __restrict__ pro
     warp = (int)(((long long)blockIdx.x * CTA + threadIdx.x) >> 5);
     if (warp >= nub) return;  // warp-uniform
   }
+  if (covered != nullptr && covered[warp]) return;  // this block belongs to the panel kernel (schur_panel.cuh)
   const int lane = threadIdx.x & 31;
   const int m = lane >> 2, k = lane & 3;
   const bool ld = m < 6 && k < 3;
@@ -823,7 +825,8 @@ __global__ void __launch_bounds__(TPB) k_products(const int* __restrict__ o_kf, 
                                                   const unsigned* __restrict__ bitmap, const int* __restrict__ word_prefix,
                                                   const int* __restrict__ s_rowptr, const int* __restrict__ csr_u, int words,
                                                   int E, int fill, unsigned* __restrict__ counters,
-                                                  const unsigned* __restrict__ u_prod_ptr, uint2* __restrict__ prod) {
+                                                  const unsigned* __restrict__ u_prod_ptr, uint2* __restrict__ prod,
+                                                  const unsigned char* __restrict__ covered = nullptr) {
   const long long e = (long long)blockIdx.x * TPB + threadIdx.x;
   if (e >= E) return;
   const int a = pose_slot[o_kf[e]];
@@ -834,6 +837,7 @@ __global__ void __launch_bounds__(TPB) k_products(const int* __restrict__ o_kf, 
     const int b = pose_slot[o_kf[o]];
     if (b < a || (b == a && o != (int)e)) continue;
     const int u = csr_u[csr_pos(bitmap, word_prefix, s_rowptr, words, a, b)];
+    if (covered != nullptr && b != a && covered[u]) continue;  // the panel kernel forms this block; diagonal lists also feed the pose pass
     const unsigned slot = atomicAdd(counters + u, 1u);
     if (fill) prod[u_prod_ptr[u] + slot] = make_uint2((unsigned)e, (unsigned)o);
   }

@@ -19,6 +19,7 @@
 #include "common.cuh"
 #include "pcg2.cuh"
 #include "pcg_dist.cuh"
+#include "schur_panel.cuh"
 
 namespace ccm {
 void allreduce_f64(double* buf, size_t count, int op, cudaStream_t s);  // runtime.cu ; op: 0 sum, 2 max
@@ -75,6 +76,11 @@ struct ccm_ba_handle {
   DevBuf<int> s_rowptr, s_col, s_row, s_diag, csr_u, u_row, u_col, u_diag, word_prefix;
   DevBuf<unsigned> bitmap, u_prod_ptr;
   DevBuf<uint2> prod;
+  // landmark-synchronous Schur panels (schur_panel.cuh)
+  bool panel_on = false;
+  int npan = 0;
+  DevBuf<int> o_slot, pose_lmin, pose_lmax, pose_cnt;
+  DevBuf<unsigned char> pan_on, covered;
   DevBuf<int> tile_ptr, tile_u;   // T x T tiles of upper blocks: the CTA schedule of the tiled Schur kernel
   int ntiles = 0, tile_T = 0;
   DevBuf<float4> kobs;            // per free pose: (u, v, signed w, landmark) of its observations, packed
@@ -285,10 +291,23 @@ void launch_schur_tiled(ccm_ba_handle* h, cudaStream_t s) {
 template <int UNROLL, int CTA, bool PIPE = false>
 void launch_schur_mma(ccm_ba_handle* h, cudaStream_t s) {
   k_schur_mma<UNROLL, CTA, PIPE><<<div_up((long long)h->nub * 32, CTA), CTA, 0, s>>>(h->prod.p, h->u_prod_ptr.p, h->u_row.p, h->u_col.p, h->nub,
-                                                                              h->Z.p, h->o_lm.p, h->gvec.p, h->U_val(), h->bneg());
+                                                                              h->Z.p, h->o_lm.p, h->gvec.p, h->U_val(), h->bneg(), nullptr,
+                                                                              nullptr, h->panel_on ? h->covered.p : nullptr);
+}
+
+void launch_schur_panel(ccm_ba_handle* h, cudaStream_t s) {
+  SchurPanelArgs a;
+  a.Z = h->Z.p; a.o_slot = h->o_slot.p; a.lm_ptr = h->lm_ptr.p; a.gvec = h->gvec.p; a.pose_lmin = h->pose_lmin.p; a.pose_lmax = h->pose_lmax.p;
+  a.pan_on = h->pan_on.p; a.Kf = h->Kf; a.bitmap = h->bitmap.p; a.word_prefix = h->word_prefix.p; a.s_rowptr = h->s_rowptr.p;
+  a.csr_u = h->csr_u.p; a.words = h->words; a.U_val = h->U_val(); a.bneg = h->bneg();
+  k_schur_panel<<<h->npan, SP_THREADS, SP_SMEM, s>>>(a);
 }
 
 void launch_schur(ccm_ba_handle* h, cudaStream_t s) {
+  if (h->panel_on) {   // the band of every enabled panel in registers, fed by TMA; the list kernel below keeps the rest
+    launch_schur_panel(h, s);
+    CCM_LAUNCHED();
+  }
   const int mode = schur_mode();
   if (mode >= 9 && h->ntiles > 0) {   // tiled schedules (the tile edge was fixed when the handle was created: CCM_SCHUR_TILE)
     if (h->tile_T == 4) launch_schur_tiled<8, 512>(h, s);
@@ -870,13 +889,32 @@ void build(ccm_ba_handle* h, const ccm_ba_problem* p) {
   const int nub = h->nub;
 
   lap("pattern, upper index");
+  // ---- landmark-synchronous Schur panels (CCM_SCHUR_PANEL=1): which upper blocks the panel kernel owns
+  h->panel_on = env_int("CCM_SCHUR_PANEL", 0) != 0 && El > 0 && nub > 0;
+  if (h->panel_on) {
+    h->npan = div_up(Kf, SP_R);
+    h->o_slot.alloc(El); h->pose_lmin.alloc(Kf); h->pose_lmax.alloc(Kf); h->pose_cnt.alloc_zero(Kf, s);
+    k_fill_int<<<div_up(Kf, TPB), TPB, 0, s>>>(h->pose_lmin.p, Kf, 0x7fffffff);
+    k_fill_int<<<div_up(Kf, TPB), TPB, 0, s>>>(h->pose_lmax.p, Kf, -1);
+    k_pose_lm_range<<<div_up(El, TPB), TPB, 0, s>>>(h->o_kf.p, h->o_lm.p, h->pose_slot.p, El, h->o_slot.p, h->pose_lmin.p, h->pose_lmax.p,
+                                                    h->pose_cnt.p);
+    CCM_LAUNCHED();
+    h->pan_on.alloc(h->npan); h->covered.alloc(nub);
+    k_panel_on<<<div_up(h->npan, TPB), TPB, 0, s>>>(h->pose_lmin.p, h->pose_lmax.p, h->lm_ptr.p, h->pose_cnt.p, Kf, h->npan,
+                                                    env_int("CCM_SCHUR_PANEL_FACTOR", 12), h->pan_on.p);
+    CCM_LAUNCHED();
+    k_covered<<<div_up(nub, TPB), TPB, 0, s>>>(h->u_row.p, h->u_col.p, nub, h->pan_on.p, h->covered.p);
+    CCM_LAUNCHED();
+    CCM_CUDA(cudaFuncSetAttribute((const void*)k_schur_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SP_SMEM));
+  }
+  const unsigned char* cov = h->panel_on ? h->covered.p : nullptr;
   // ---- Schur product lists (local shard)
   DevBuf<unsigned> counters; counters.alloc_zero(std::max(nub, 1), s);
   std::vector<unsigned> h_pp((size_t)nub + 1, 0);
   if (El && nub) {
     k_products<<<div_up(El, TPB), TPB, 0, s>>>(h->o_kf.p, h->o_lm.p, h->lm_ptr.p, h->pose_slot.p, h->bitmap.p,
                                                h->word_prefix.p, h->s_rowptr.p, h->csr_u.p, words, El, 0, counters.p,
-                                               nullptr, nullptr);
+                                               nullptr, nullptr, cov);
     CCM_LAUNCHED();
     std::vector<unsigned> c(nub);
     counters.download(c.data(), nub, s);
@@ -893,7 +931,7 @@ void build(ccm_ba_handle* h, const ccm_ba_problem* p) {
     CCM_CUDA(cudaMemsetAsync(counters.p, 0, sizeof(unsigned) * nub, s));
     k_products<<<div_up(El, TPB), TPB, 0, s>>>(h->o_kf.p, h->o_lm.p, h->lm_ptr.p, h->pose_slot.p, h->bitmap.p,
                                                h->word_prefix.p, h->s_rowptr.p, h->csr_u.p, words, El, 1, counters.p,
-                                               h->u_prod_ptr.p, h->prod.p);
+                                               h->u_prod_ptr.p, h->prod.p, cov);
     CCM_LAUNCHED();
   }
 

@@ -157,6 +157,44 @@ int optw_gba_flip(const optw_scene* s, int which, int iterations, int robust, in
   } catch (...) { return -1; }
 }
 
+/* MapFusionGBA with a persistent mirror registered for the map (shim builds only): the mirror is fed from the scene the way a server
+   would feed it (keyframes, points, observations, in map order), then the optimiser takes its problem from it. */
+}
+#if defined(CCM_SHIM_BUILD)
+#include "ccm_b200.h"
+namespace cslam { void ccm_b200_register_mirror(const Map* map, ccm_map_mirror* mirror); }
+extern "C" int optw_gba_mirror(const optw_scene* s, int iterations, int robust, int64_t loop_first, int64_t loop_second, optw_out* o) {
+  ccm_map_mirror* mir = nullptr;
+  try {
+    Scene sc(s);
+    if (ccm_mirror_create(&mir) != 0) return -3;
+    for (int k = 0; k < s->K; k++) {
+      KeyFrame& F = sc.kf_store[k];
+      const float intr[4] = {F.fx, F.fy, F.cx, F.cy};
+      if (ccm_mirror_set_keyframe(mir, (uint64_t)F.mUniqueId, F.Tcw.ptr<float>(0), intr, F.mbBad ? 1 : 0) != 0) throw 1;
+    }
+    for (int j = 0; j < s->P; j++) {
+      MapPoint& M = sc.mp_store[j];
+      if (ccm_mirror_set_point(mir, (uint64_t)M.mUniqueId, M.mWorldPos.ptr<float>(0), M.mbBad ? 1 : 0) != 0) throw 1;
+      for (auto& ob : M.mObservations) {                       /* std::map<kfptr, size_t>: the order the reference's loop visits them in */
+        const KeyFrame& F = *ob.first;
+        const cv::KeyPoint& kp = F.mvKeysUn[ob.second];
+        if (ccm_mirror_set_observation(mir, (uint64_t)F.mUniqueId, (uint64_t)M.mUniqueId, kp.pt.x, kp.pt.y, F.mvInvLevelSigma2[kp.octave]) != 0) throw 1;
+      }
+    }
+    cslam::ccm_b200_register_mirror(sc.map.get(), mir);
+    const idpair nLoopKF((size_t)loop_first, (size_t)loop_second);
+    try { Optimizer::MapFusionGBA(sc.map, (size_t)s->map_id, iterations, NULL, nLoopKF, robust != 0); }
+    catch (...) { cslam::ccm_b200_register_mirror(sc.map.get(), nullptr); ccm_mirror_destroy(mir); return -1; }
+    cslam::ccm_b200_register_mirror(sc.map.get(), nullptr);
+    ccm_mirror_destroy(mir);
+    sc.read(s, o);
+    return 0;
+  } catch (...) { if (mir) ccm_mirror_destroy(mir); return -1; }
+}
+#endif
+extern "C" {
+
 int optw_local_ba(const optw_scene* s, int kf_index, int server, optw_out* o) {
   try {
     Scene sc(s);

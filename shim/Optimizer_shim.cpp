@@ -11,6 +11,7 @@
 #include <unistd.h>
 
 #include <list>
+#include <mutex>
 #include <unordered_map>
 
 #include "ccm_b200.h"
@@ -72,7 +73,22 @@ cv::Mat point_to_cv(const double* x) {
 }
 void check(int rc) { if (rc != CCM_OK) { std::cerr << "libccm_b200: " << ccm_last_error() << std::endl; throw estd::infrastructure_ex(); } }
 
+// Optional persistent mirrors: a server that keeps a ccm_map_mirror up to date for a Map
+// registers it here; MapFusionGBA then takes the flat problem from the mirror instead of walking the pointer graph.
+std::mutex g_mirror_mu;
+std::unordered_map<const Map*, ccm_map_mirror*> g_mirrors;
+ccm_map_mirror* mirror_of(const Map* m) {
+  std::lock_guard<std::mutex> lock(g_mirror_mu);
+  auto it = g_mirrors.find(m);
+  return it == g_mirrors.end() ? nullptr : it->second;
+}
+
 }  // namespace
+
+void ccm_b200_register_mirror(const Map* map, ccm_map_mirror* mirror) {   // cslam::ccm_b200_register_mirror; mirror == nullptr: forget the map
+  std::lock_guard<std::mutex> lock(g_mirror_mu);
+  if (mirror) g_mirrors[map] = mirror; else g_mirrors.erase(map);
+}
 
 // ---- MapFusionGBA (S/Optimizer.cpp:646-859) ---------------------------------------------------------------------------
 void Optimizer::MapFusionGBA(mapptr pMap, size_t ClientId, int nIterations, bool* pbStopFlag, idpair nLoopKF, const bool bRobust) {
@@ -82,6 +98,48 @@ void Optimizer::MapFusionGBA(mapptr pMap, size_t ClientId, int nIterations, bool
   const idpair zeropair = make_pair(0, pMap->mMapId);
   if (pMap->mvpKeyFrameOrigins.empty()) throw infrastructure_ex();
   const idpair FixedId = (*(pMap->mvpKeyFrameOrigins.begin()))->mId;
+
+  if (ccm_map_mirror* mir = mirror_of(pMap.get())) {
+    // The mirror already holds the flat arrays (same selection rules, tests/test_map_mirror.py): no GetObservations() copies, no
+    // Converter::toSE3Quat per keyframe.  Only the id -> object tables of the write-back are built here: O(K + P), no observation walk.
+    std::unordered_map<uint64_t, kfptr> kf_of_uid;
+    std::unordered_map<uint64_t, mpptr> mp_of_uid;
+    size_t maxKFid = 0;
+    uint64_t fixed_uid = 0;
+    for (kfptr pKF : vpKFs) {
+      if (pKF->isBad()) continue;
+      kf_of_uid[(uint64_t)pKF->mUniqueId] = pKF;
+      maxKFid = std::max(maxKFid, (size_t)pKF->mUniqueId);
+      if (pKF->mId == FixedId) fixed_uid = (uint64_t)pKF->mUniqueId;
+    }
+    for (mpptr pMP : vpMP) if (!pMP->isBad()) mp_of_uid[(uint64_t)pMP->mUniqueId] = pMP;
+    ccm_ba_problem prob;
+    const uint64_t *kf_uid = nullptr, *mp_uid = nullptr;
+    check(ccm_mirror_ba_problem(mir, (uint64_t)maxKFid, &fixed_uid, 1, &prob, &kf_uid, &mp_uid));
+    ccm_ba_options opt = {};
+    opt.iterations = nIterations; opt.robust = bRobust;
+    opt.huber_delta = (double)(float)sqrt(5.99);
+    opt.stop = reinterpret_cast<const volatile uint8_t*>(pbStopFlag);
+    vector<double> poses((size_t)prob.K * 7), points((size_t)prob.P * 3);
+    ccm_ba_result res = {};
+    res.poses = poses.data(); res.points = points.data();
+    check(ccm_ba_solve(&prob, &opt, &res));
+    for (int r = 0; r < prob.K; r++) {                        // write-back by id, as the reference does (:803-823)
+      auto it = kf_of_uid.find(kf_uid[r]);
+      if (it == kf_of_uid.end() || it->second->isBad()) continue;
+      cv::Mat T = pose_to_cv(&poses[7 * (size_t)r]);
+      if (nLoopKF == zeropair) it->second->SetPose(T, true);
+      else { it->second->mTcwGBA.create(4, 4, CV_32F); T.copyTo(it->second->mTcwGBA); it->second->mBAGlobalForKF = nLoopKF; }
+    }
+    for (int r = 0; r < prob.P; r++) {                        // :827-857
+      auto it = mp_of_uid.find(mp_uid[r]);
+      if (it == mp_of_uid.end() || it->second->isBad()) continue;
+      cv::Mat X = point_to_cv(&points[3 * (size_t)r]);
+      if (nLoopKF == zeropair) { it->second->SetWorldPos(X, true); it->second->UpdateNormalAndDepth(); }
+      else { it->second->mPosGBA.create(3, 1, CV_32F); X.copyTo(it->second->mPosGBA); it->second->mBAGlobalForKF = nLoopKF; }
+    }
+    return;
+  }
 
   FlatBA f;
   size_t maxKFid = 0;

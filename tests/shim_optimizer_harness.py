@@ -159,6 +159,16 @@ def run_gba_flip(sc, which, iterations, robust, loop, flip_kf):
     return o
 
 
+def run_gba_mirror(sc, iterations, robust, loop):
+    """MapFusionGBA with a persistent map mirror registered for the map (shim library only): the problem comes from ccm_mirror_ba_problem"""
+    keep = []
+    S = c_scene(sc, keep)
+    o, O = new_out(S.K, S.P)
+    rc = lib().optw_gba_mirror(C.byref(S), int(iterations), int(robust), C.c_int64(loop[0]), C.c_int64(loop[1]), C.byref(O))
+    assert rc == 0, rc
+    return o
+
+
 def run_essential_graph(sc, loop_kf, cur_kf, conn, fix_scale, loop_closure=False, corr=None, mp_corr_ref=None):
     """conn: {keyframe index: [keyframe indices]} = LoopConnections; corr = (kf indices, corrected (n,8), noncorrected (n,8))"""
     keep = []

@@ -91,6 +91,23 @@ def test_gba_keyframe_turning_bad_during_the_solve(ho, which, loop_mode):
         assert np.array_equal(got[k], base[k]), k
 
 
+@pytest.mark.parametrize("loop_mode", [False, True])
+@pytest.mark.parametrize("name,bad_kf,bad_mp", [("small", 0.0, 0.0), ("small", 0.1, 0.1)])
+def test_map_fusion_gba_through_the_persistent_mirror(ho, name, bad_kf, bad_mp, loop_mode):
+    """with a ccm_map_mirror registered for the map, MapFusionGBA takes the flat problem from the mirror (no walk
+    over GetObservations()) and writes back by id.  Fed in map order the mirror hands out the very arrays the per-call flattening builds,
+    so everything the call leaves in the map is bit-identical to the plain path."""
+    p = synth.make_config(name)
+    sc = H.scene_from_problem(p, ho, seed=5, map_id=0, bad_kf=bad_kf, bad_mp=bad_mp)
+    sc["kf_bad"][0] = 0
+    loop = (7, 0) if loop_mode else (0, 0)
+    plain = H.run_gba(sc, 0, 8, True, loop)
+    mirrored = H.run_gba_mirror(sc, 8, True, loop)
+    for k in plain:
+        assert np.array_equal(plain[k], mirrored[k]), k
+    assert np.abs(plain["kf_TcwGBA" if loop_mode else "kf_Tcw"] - sc["kf_Tcw"]).max() > 1e-4
+
+
 # ---- essential graph ----------------------------------------------------------------------------------------------------------
 MIN_FEAT = 100      # params::opt::miEssGraphMinFeats, handed to the reference's config.h through the FileStorage stand-in (conftest sets it)
 
