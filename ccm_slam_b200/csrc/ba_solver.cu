@@ -111,7 +111,8 @@ struct ccm_ba_handle {
   struct Pcg2 {
     bool on = false;
     Pcg2Layout lay{};
-    char* window = nullptr;          // own exchange window (plain cudaMalloc: exportable through cudaIpc)
+    char* window = nullptr;          // own exchange window: plain cudaMalloc (exportable through cudaIpc) on several ranks, pool memory on one
+    bool window_pooled = false;
     std::vector<char*> peer;         // every rank's window as mapped here; peer[rank] == window
     DevBuf<char*> d_win;
     DevBuf<int> items, cta_row, cta_item, rank_row;
@@ -152,7 +153,7 @@ struct ccm_ba_handle {
     if (dist.window) cudaFree(dist.window);
     for (size_t k = 0; k < p2.peer.size(); k++)
       if (p2.peer[k] && (int)k != p2.rank) cudaIpcCloseMemHandle(p2.peer[k]);
-    if (p2.window) cudaFree(p2.window);
+    if (p2.window) { if (p2.window_pooled) dev_free(p2.window); else cudaFree(p2.window); }
     for (cudaEvent_t e : ev_pool) cudaEventDestroy(e);
     if (h_scal) cudaFreeHost(h_scal);
     if (stream) cudaStreamDestroy(stream);
@@ -569,8 +570,14 @@ void setup_pcg2(ccm_ba_handle* h, const std::vector<int>& rowptr) {
   if (h->pcg_bar.n < 2) h->pcg_bar.alloc_zero(2, s);
   // exchange window
   d.lay = pcg2_layout(Kf, N, nC);
-  CCM_CUDA(cudaMalloc((void**)&d.window, d.lay.bytes));
-  CCM_CUDA(cudaMemset(d.window, 0, d.lay.bytes));
+  if (N == 1) {   // no peer maps it: stream-ordered pool memory (cudaMalloc / cudaFree synchronise the device on every create / destroy)
+    d.window = static_cast<char*>(dev_alloc(d.lay.bytes));
+    d.window_pooled = true;
+    CCM_CUDA(cudaMemsetAsync(d.window, 0, d.lay.bytes, s));
+  } else {
+    CCM_CUDA(cudaMalloc((void**)&d.window, d.lay.bytes));
+    CCM_CUDA(cudaMemset(d.window, 0, d.lay.bytes));
+  }
   d.peer.assign(N, nullptr);
   d.peer[h->rank] = d.window;
   DevBuf<double> tmp;

@@ -274,6 +274,12 @@ __global__ void __launch_bounds__(P2_TPB, 1) k_pcg2(Pcg2Args A) {
     return p2_ld_volatile(zbuf(owner_of(a), par) + g);
   };
   __shared__ double sm_ll[8][4];
+  // coarse unknowns [t_lo(k), t_hi(k)) that the rows of rank k restrict to (both parents of its first and last row)
+  auto t_lo = [&](int k) { const int a0 = A.rank_row[k]; return a0 >= A.rank_row[k + 1] ? 0 : coarse_parents(a0, A.agg, A.nc, A.prolong).lo * BS; };
+  auto t_hi = [&](int k) {
+    const int a1 = A.rank_row[k + 1] - 1;
+    return a1 < A.rank_row[k] ? 0 : (coarse_parents(a1, A.agg, A.nc, A.prolong).hi + 1) * BS;
+  };
 
   // ---- this CTA's rows and items, this warp's run of items, its ring ------------------------------------------------------
   const int c0 = A.cta_row[blockIdx.x], c1 = A.cta_row[blockIdx.x + 1];
@@ -511,8 +517,10 @@ __global__ void __launch_bounds__(P2_TPB, 1) k_pcg2(Pcg2Args A) {
         p2_ll_store(lls(tid, par, me, 0), v, epA);
         if (it < 0) p2_ll_store(lls(tid, par, me, 1), coarse ? 1.0 : 0.0, epA);
       }
-      for (int i = tid; i < nC * N; i += P2_TPB) {
-        const int k = i / nC, j = i - k * nC;
+      // a rank's P^T q partial is non-zero only on the coarse nodes its own rows hang on: [trange(me).lo, trange(me).hi)
+      const int jlo = t_lo(me), jn = t_hi(me) - jlo;
+      for (int i = tid; i < jn * N; i += P2_TPB) {
+        const int k = i / jn, j = jlo + (i - k * jn);
         if (k != me) p2_ll_store(llt(k, par, me, j), __ldcg(tp + j), epA);
       }
     });
@@ -552,7 +560,12 @@ __global__ void __launch_bounds__(P2_TPB, 1) k_pcg2(Pcg2Args A) {
       for (int j = tid; j < nC; j += P2_TPB) {
         double t;
         if (N == 1) t = __ldcg(tp + j);
-        else { t = 0.0; for (int k = 0; k < N; k++) t += k == me ? __ldcg(tp + j) : ll_wait(llt(me, par, k, j), epA); }
+        else {
+          t = 0.0;
+          for (int k = 0; k < N; k++)
+            if (k == me) t += __ldcg(tp + j);
+            else if (j >= t_lo(k) && j < t_hi(k)) t += ll_wait(llt(me, par, k, j), epA);
+        }
         sm_rc[j] = fma(sgn, t, sm_rc[j]);
       }
       if (__syncthreads_or(!ll_ok)) { alive = false; break; }

@@ -172,11 +172,14 @@ def test_cfg4_full_size_against_oracle_and_properties(oracle):
     assert np.array_equal(res["poses"][0], p.poses[0])                       # the fixed origin keyframe does not move
 
 
-def test_cfg5_tenth_scale_against_oracle_and_properties(oracle):
+@pytest.mark.parametrize("impl", ["default", "streamed"])
+def test_cfg5_tenth_scale_against_oracle_and_properties(oracle, impl, monkeypatch):
     """The benchmarked shape (cfg5: banded covisibility, 20 observations / landmark) at 1/10 trajectory length, K = 1000,
     P = 100 000, 2 M observations: the same stop rule as bench.py (optimize(20), ended by the three-strike rule) against the
     oracle's exact-factorisation run (about 10 s of CPU) -- iteration and trial counts, lambda schedule, chi2 trace, state --
     plus the size-independent properties."""
+    if impl == "streamed":   # the kernel the full-size cfg5 takes (k_pcg2); at 1/10 length the size rule would pick the small-system one
+        monkeypatch.setenv("CCM_PCG_IMPL", "2")
     p = synth.make_config("cfg5", K=1000, P=100000)
     ref = oracle.ba_solve(p, iterations=20, huber_delta=api.HUBER_GBA)
     res = api.ba_solve(p, iterations=20, huber_delta=api.HUBER_GBA, want_edges=False)

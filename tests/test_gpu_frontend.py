@@ -111,9 +111,16 @@ def test_sim3_pose_graph_matches_oracle(oracle, K, fix_scale):
     p = synth.make_pgo(K=K, fix_scale=fix_scale)
     ref = oracle.pgo_solve(p, iterations=20)
     got = api.pgo_solve(p, iterations=20)
-    # after the first (accepted) step both sides sit at the optimum up to the 1e-7 noise of the numeric Jacobians, where
-    # accept/reject decisions are coin flips; the number of iterations may differ, the estimate may not
-    assert got["iters_done"] >= 1 and abs(got["chi2_initial"] - ref["chi2_initial"]) <= 1e-9 * ref["chi2_initial"]
+    # Same LM iteration count as the oracle (north_star: "after the same iteration count"), same accept / reject decision and trial count
+    # in every iteration whose gain ratio is above the noise floor.  The one decision that differs in these cases (traces:
+    # profiles/r2/pgo_trace.log) is iteration 4 of (K = 200, fixed scale): rho = +2.0e-12 on the oracle, -4.5e-13 on the device -- a chi2
+    # difference of 2e-15 relative, eight orders below the 1e-7 noise of the reference's numeric Jacobians (central differences,
+    # delta = 1e-9, G/core/base_binary_edge.hpp:147-197); the oracle accepts a step that changes nothing, the device tries ten lambdas,
+    # rejects them all, and both stop after the same five iterations with the same estimate.
+    assert got["iters_done"] == ref["iters_done"] >= 1 and abs(got["chi2_initial"] - ref["chi2_initial"]) <= 1e-9 * ref["chi2_initial"]
+    for it in range(ref["iters_done"]):
+        if abs(ref["trace"][it, 3]) > 1e-9 and abs(got["trace"][it, 3]) > 1e-9:
+            assert (got["trace"][it, 3] > 0) == (ref["trace"][it, 3] > 0) and got["trace"][it, 4] == ref["trace"][it, 4], it
     assert abs(got["trace"][0, 2] - ref["trace"][0, 2]) <= 1e-4 * ref["trace"][0, 2]
     assert abs(got["chi2_final"] - ref["chi2_final"]) <= 1e-4 * ref["chi2_final"]
     scale = np.abs(ref["sim3"]).max()

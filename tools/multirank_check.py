@@ -48,6 +48,8 @@ def case(name, p, iters, delta):
     dist.barrier()
 
 
+# CCM_PCG_IMPL=2 in the environment sends these small systems through the streamed / distributed solve too (by size they take the
+# replicated small-system kernel)
 for cfg, it in (("small", 8), ("cfg3", 10), ("cfg4", 10)):
     p = synth.make_config(cfg)
     case(cfg + " sorted", p, it, api.HUBER_GBA)
