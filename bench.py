@@ -341,7 +341,11 @@ def main():
 
     # ---- end-to-end through the one-shot C ABI call with host buffers (pinned), copies inside the timed region
     arrs = [p.poses, p.intr, p.fixed, p.points, p.obs_kf, p.obs_mp, p.obs_uv, p.obs_w]
-    h2d = int(sum(a.nbytes for a in arrs)); d2h = int(p.poses.nbytes + p.points.nbytes)
+    # bytes that cross the bus per ccm_ba_solve call on this rank: poses, intrinsics, flags and the (keyframe, landmark) index lists whole
+    # (every rank needs the global pattern of S), measurements and points of its own landmark shard only
+    El, Pl = int(info["E_local"]), int(info["P_local"])
+    h2d = int(p.poses.nbytes + p.intr.nbytes + p.fixed.nbytes + p.obs_kf.nbytes + p.obs_mp.nbytes + El * 12 + Pl * 24)
+    d2h = int(p.poses.nbytes + (p.points.nbytes if world == 1 else p.points.nbytes))
     h.close()
     pinned = []
     for a in arrs:

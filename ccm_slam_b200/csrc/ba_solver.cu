@@ -18,7 +18,6 @@
 #include "ba_kernels.cuh"
 #include "common.cuh"
 #include "pcg2.cuh"
-#include "pcg_dist.cuh"
 #include "schur_panel.cuh"
 
 namespace ccm {
@@ -93,20 +92,6 @@ struct ccm_ba_handle {
   DevBuf<long long> pcg_prof;  // allocated only with CCM_PCG_PROF=1
   DevBuf<int> jac_fail;
   int pcg_grid = 0, pcg_block = 256, pcg_last_mode = 1;
-  // row-distributed PCG over peer memory (pcg_dist.cuh): only with CCM_PCG_DIST=1
-  struct DistPcg {
-    bool on = false;
-    PcgDistLayout lay{};
-    char* window = nullptr;          // own exchange window (plain cudaMalloc: exportable through cudaIpc)
-    std::vector<char*> peer;         // every rank's window as mapped here; peer[rank] == window
-    DevBuf<char*> d_win;
-    DevBuf<unsigned long long> rel;
-    int r0 = 0, r1 = 0, rank = 0;
-    unsigned long long launches = 0;
-    void* fn = nullptr;
-    int grid = 0, block = 256;
-    long long timeout_cycles = 0;
-  } dist;
   // second-generation PCG (pcg2.cuh): TMA-streamed product, three synchronisations per iteration, rows distributed over the ranks
   struct Pcg2 {
     bool on = false;
@@ -148,9 +133,6 @@ struct ccm_ba_handle {
   double* bneg() { return Ubuf.p + (size_t)nub * 36; }
 
   ~ccm_ba_handle() {
-    for (size_t k = 0; k < dist.peer.size(); k++)
-      if (dist.peer[k] && (int)k != dist.rank) cudaIpcCloseMemHandle(dist.peer[k]);
-    if (dist.window) cudaFree(dist.window);
     for (size_t k = 0; k < p2.peer.size(); k++)
       if (p2.peer[k] && (int)k != p2.rank) cudaIpcCloseMemHandle(p2.peer[k]);
     if (p2.window) { if (p2.window_pooled) dev_free(p2.window); else cudaFree(p2.window); }
@@ -327,9 +309,9 @@ void launch_schur(ccm_ba_handle* h, cudaStream_t s) {
     case 3: launch_schur_mma<4, 256>(h, s); break;
     case 4: launch_schur_mma<8, 256>(h, s); break;
     case 5: launch_schur_mma<8, 512>(h, s); break;
-    case 6: launch_schur_mma<8, 64>(h, s); break;     // not yet measured: fewer warps share a CTA's lifetime (lists differ in length)
-    case 7: launch_schur_mma<16, 128>(h, s); break;   // not yet measured
-    case 8: launch_schur_mma<8, 128, true>(h, s); break;   // not yet measured: product entries prefetched one batch ahead
+    case 6: launch_schur_mma<8, 64>(h, s); break;     // 9.53 ms
+    case 7: launch_schur_mma<16, 128>(h, s); break;   // 8.78 ms
+    case 8: launch_schur_mma<8, 128, true>(h, s); break;   // 8.43 ms: product entries prefetched one batch ahead (the default)
     case 1: launch_schur_mma<8, 128>(h, s); break;
     default: launch_schur_mma<8, 128, true>(h, s); break;   // 8.43 ms vs 8.73 ms without the prefetch (profiles/r2/prolong_cfg5.log)
   }
@@ -388,7 +370,7 @@ void step_pcg(ccm_ba_handle* h, double tol, int max_iter) {
     b.Ainv = nC > 0 ? ((((nC + GJB - 1) / GJB) & 1) ? h->pcg_Ac.p + (size_t)nC * nC : h->pcg_Ac.p) : nullptr;
     b.yc = d.yc.p; b.tpart = d.tpart.p;
     b.rank = h->rank; b.nranks = h->nranks; b.r0 = d.r0; b.r1 = d.r1; b.win = d.d_win.p;
-    b.off_z = d.lay.off_z; b.off_scal = d.lay.off_scal; b.off_t = d.lay.off_t; b.off_x = d.lay.off_x;
+    b.off_z = d.lay.off_z; b.off_x = d.lay.off_x;
     b.off_flags = d.lay.off_flags; b.off_ctl = d.lay.off_ctl; b.off_lls = d.lay.off_lls; b.off_llt = d.lay.off_llt;
     b.rank_row = d.rank_row.p; b.need = d.need.p;
     b.epoch0 = (++d.launches) << 24;   // every rank issues the same sequence of solves: the epochs line up and only grow
@@ -403,100 +385,9 @@ void step_pcg(ccm_ba_handle* h, double tol, int max_iter) {
     CCM_LAUNCHED();
     return;
   }
-  if (h->dist.on) {
-    ccm_ba_handle::DistPcg& d = h->dist;
-    if (a.coarse_mode == 1 && a.agg > 0) {  // (re)build the coarse inverse with the replicated kernel: set-up only, no iteration
-      PcgArgs setup = a;
-      setup.max_iter = 0;
-      void* sargs[] = {&setup};
-      CCM_CUDA(cudaLaunchCooperativeKernel(h->pcg_fn, dim3(h->pcg_grid), dim3(h->pcg_block), sargs, 0, s));
-      CCM_LAUNCHED();
-      CCM_CUDA(cudaMemsetAsync(h->pcg_bar.p, 0, sizeof(unsigned), s));
-    }
-    PcgDistArgs da;
-    da.a = a; da.a.coarse_mode = 2; da.a.z = nullptr;
-    da.rank = h->rank; da.nranks = h->nranks; da.r0 = d.r0; da.r1 = d.r1;
-    da.win = d.d_win.p;
-    da.off_z = d.lay.off_z; da.off_scal = d.lay.off_scal; da.off_rc = d.lay.off_rc; da.off_x = d.lay.off_x;
-    da.off_flags = d.lay.off_flags; da.off_ctl = d.lay.off_ctl;
-    da.epoch0 = (++d.launches) << 24;   // every rank issues the same sequence of solves: the epochs line up and only grow
-    da.rel = d.rel.p;
-    da.timeout_cycles = d.timeout_cycles;
-    CCM_CUDA(cudaMemsetAsync(d.window + d.lay.off_ctl, 0, sizeof(unsigned), s));
-    void* dargs[] = {&da};
-    CCM_CUDA(cudaLaunchCooperativeKernel(d.fn, dim3(d.grid), dim3(d.block), dargs, 0, s));
-    CCM_LAUNCHED();
-    return;
-  }
   void* args[] = {&a};
   CCM_CUDA(cudaLaunchCooperativeKernel(h->pcg_fn, dim3(h->pcg_grid), dim3(h->pcg_block), args, 0, s));
   CCM_LAUNCHED();
-}
-
-// CCM_PCG_DIST=1: exchange windows, peer mappings and the row cut of the distributed PCG (pcg_dist.cuh).
-// The 64-byte IPC handles travel through the existing all-reduce, one double per byte (exact: each slot has one writer).
-void setup_pcg_dist(ccm_ba_handle* h) {
-  // nranks == 1 is allowed on purpose: the kernel then talks to its own window only, which exercises everything but the NVLink
-  // hop on a single GPU (cheap first validation)
-  if (!env_int("CCM_PCG_DIST", 0) || h->Kf < h->nranks || h->Kf < 1) return;
-  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
-  ccm_ba_handle::DistPcg& d = h->dist;
-  cudaStream_t s = h->stream;
-  const int N = h->nranks;
-  d.rank = h->rank;
-  d.lay = pcg_dist_layout(h->Kf, 6, N, h->pcg_agg > 0 ? 6 * h->pcg_nc : 0);
-  CCM_CUDA(cudaMalloc((void**)&d.window, d.lay.bytes));
-  CCM_CUDA(cudaMemset(d.window, 0, d.lay.bytes));
-  cudaIpcMemHandle_t mine;
-  CCM_CUDA(cudaIpcGetMemHandle(&mine, d.window));
-  std::vector<double> enc((size_t)N * 64, 0.0);
-  for (int i = 0; i < 64; i++) enc[(size_t)h->rank * 64 + i] = (double)reinterpret_cast<const unsigned char*>(&mine)[i];
-  DevBuf<double> tmp;
-  tmp.alloc(enc.size());
-  CCM_CUDA(cudaMemcpyAsync(tmp.p, enc.data(), enc.size() * sizeof(double), cudaMemcpyHostToDevice, s));
-  allreduce_f64(tmp.p, enc.size(), 0, s);
-  CCM_CUDA(cudaMemcpyAsync(enc.data(), tmp.p, enc.size() * sizeof(double), cudaMemcpyDeviceToHost, s));
-  CCM_CUDA(cudaStreamSynchronize(s));
-  d.peer.assign(N, nullptr);
-  for (int k = 0; k < N; k++) {
-    if (k == h->rank) { d.peer[k] = d.window; continue; }
-    cudaIpcMemHandle_t hk;
-    for (int i = 0; i < 64; i++) reinterpret_cast<unsigned char*>(&hk)[i] = (unsigned char)enc[(size_t)k * 64 + i];
-    void* ptr = nullptr;
-    CCM_CUDA(cudaIpcOpenMemHandle(&ptr, hk, cudaIpcMemLazyEnablePeerAccess));
-    d.peer[k] = static_cast<char*>(ptr);
-  }
-  d.d_win.alloc(N);
-  CCM_CUDA(cudaMemcpyAsync(d.d_win.p, d.peer.data(), sizeof(char*) * N, cudaMemcpyHostToDevice, s));
-  d.rel.alloc_zero(1, s);
-  // contiguous block rows per rank, cut where the block-count prefix crosses k * nnzb / N
-  std::vector<int> rowptr((size_t)h->Kf + 1);
-  h->s_rowptr.download(rowptr.data(), rowptr.size(), s);
-  CCM_CUDA(cudaStreamSynchronize(s));
-  auto cut = [&](int k) {
-    if (k <= 0) return 0;
-    if (k >= N) return h->Kf;
-    const long long want = (long long)rowptr[h->Kf] * k / N;
-    return (int)(std::lower_bound(rowptr.begin(), rowptr.end(), (int)want) - rowptr.begin());
-  };
-  d.r0 = std::min(cut(h->rank), h->Kf);
-  d.r1 = std::min(std::max(cut(h->rank + 1), d.r0), h->Kf);
-  const int rows = std::max(d.r1 - d.r0, 1);
-  d.block = ((long long)rows * 32 >= (long long)sm_count() * PCG_TPB) ? 512 : 256;
-  d.fn = d.block == 512 ? (void*)k_pcg_dist<6, 512, 1> : (void*)k_pcg_dist<6, 256, 2>;
-  int per_sm = 0;
-  CCM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)d.fn, d.block, 0));
-  CCM_REQUIRE(per_sm >= 1, "k_pcg_dist does not fit on an SM");
-  per_sm = std::min(per_sm, d.block == 256 ? 2 : 1);
-  d.grid = std::max(1, std::min(sm_count() * per_sm, div_up((long long)rows * 32, d.block)));
-  if ((size_t)3 * d.grid > h->pcg_partials.n) h->pcg_partials.alloc((size_t)3 * d.grid);
-  int khz = 0;
-  CCM_CUDA(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, h->device));
-  d.timeout_cycles = (long long)env_int("CCM_PCG_DIST_TIMEOUT_MS", 2000) * std::max(khz, 1000000);
-  // every rank must have mapped every window before anybody stores into one: a last all-reduce is the fence
-  allreduce_f64(tmp.p, 1, 0, s);
-  CCM_CUDA(cudaStreamSynchronize(s));
-  d.on = true;
 }
 
 // pcg2.cuh set-up: own rows, item records, CTA cuts, exchange window (IPC-mapped on every rank when nranks > 1).
@@ -1026,7 +917,6 @@ void build(ccm_ba_handle* h, const ccm_ba_problem* p) {
     h->pcg_Ac.alloc(std::max(2 * nC * nC, (size_t)1)); h->pcg_rc.alloc(std::max(2 * nC, (size_t)1)); h->pcg_yc.alloc(std::max(nC, (size_t)1));
   }
   setup_pcg2(h, h_rowptr);
-  if (!h->p2.on) setup_pcg_dist(h);
   h->partials.alloc((size_t)sm_count() * 8 + 8);
   h->scal.alloc_zero(16, s);
   h->rep_chi2.alloc(std::max(El, 1)); h->rep_depth.alloc(std::max(El, 1));
@@ -1170,7 +1060,7 @@ void optimize(ccm_ba_handle* h, const ccm_ba_options* o, ccm_ba_result* r) {
       last_pcg_it = pcg_it; last_relres = h->h_scal[4];
       r->pcg_iters_total += pcg_it;
       if (pcg_flag == 1) r->pcg_not_converged++;
-      if (pcg_flag == 3) throw Error(CCM_ERR_NCCL, "distributed PCG: a peer did not reach a barrier within CCM_PCG_DIST_TIMEOUT_MS");
+      if (pcg_flag == 3) throw Error(CCM_ERR_NCCL, "distributed PCG: a peer's packet did not arrive within CCM_PCG_DIST_TIMEOUT_MS");
       const bool ok2 = !(pcg_flag == 2 || jfail);  // linear solve failed (not SPD): the trial is rejected
       if (!ok2) tempChi = std::numeric_limits<double>::max();
       rho = currentChi - tempChi;

@@ -7,14 +7,14 @@
 //
 // Preconditioner: two-level additive Schwarz,  M^-1 = blockdiag(S)^-1 + P (P^T S P)^-1 P^T.
 //   * fine level: block-Jacobi (inverse diagonal blocks, computed by the caller);
-//   * coarse level (prolong = 0, the default): aggregates of `agg` consecutive block rows (keyframes are ordered along each agent's trajectory, so
+//   * coarse level (prolong = 0; the pose graph's BS = 7 solve and CCM_PCG_PROLONG=0): aggregates of `agg` consecutive block rows (keyframes are ordered along each agent's trajectory, so
 //     index neighbours are co-visible), piecewise-constant prolongation per degree of freedom -> a dense (BS*nc)^2
 //     Galerkin matrix, nc <= 128, assembled and inverted (ping-pong Gauss-Jordan, one grid barrier per pivot) inside the
 //     same kernel before the iteration starts.  It removes the smooth error modes along the trajectory that make
 //     block-Jacobi PCG iteration counts grow with the number of keyframes.
-//   * prolong = 1 (CCM_PCG_PROLONG=1): the same coarse nodes, but P interpolates linearly between aggregate centres.  On the
+//   * prolong = 1 (bundle adjustment's default): the same coarse nodes, but P interpolates linearly between aggregate centres.  On the
 //     cfg5 chain this cuts the iteration count 2.2-2.9x at equal coarse size and a linear P over 192 nodes beats a constant P
-//     over 768 (tools/pcg_precond_study.py, profiles/pcg_precond_study_r1.txt).  Not yet run on the device: off by default.
+//     over 768 (tools/pcg_precond_study.py, profiles/pcg_precond_study_r1.txt).  Default since round 2 (cfg5: 1538 -> 617 iterations at 192 nodes, 496 at 256 nodes).
 #pragma once
 #include <cuda_runtime.h>
 

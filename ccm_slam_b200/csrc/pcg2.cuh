@@ -67,7 +67,7 @@ struct Pcg2Args {
   double* tpart;               // 2 * 6 nc, zeroed before launch: this rank's P^T q (parity-buffered)
   int rank, nranks, r0, r1;
   char* const* win;            // [nranks] exchange windows as mapped in this process; win[rank] is local
-  size_t off_z, off_scal, off_t, off_x, off_flags, off_ctl;
+  size_t off_z, off_x, off_flags, off_ctl;
   size_t off_lls, off_llt;     // low-latency packets: scalars [2][nranks][4], P^T q [2][nranks][6 nc], 16 bytes each
   const int* rank_row;         // [nranks + 1] first block row of every rank
   const unsigned char* need;   // [n] 1 where some block of this rank's rows sits in that block column (the rows of p / z this rank reads)
@@ -247,8 +247,6 @@ __global__ void __launch_bounds__(P2_TPB, 1) k_pcg2(Pcg2Args A) {
   double* part1 = A.partials + G;
   double* part2 = A.partials + 2 * G;
   auto zbuf = [&](int k, int par) { return reinterpret_cast<double*>(A.win[k] + A.off_z) + (size_t)par * nv; };
-  auto scal = [&](int k, int par, int src) { return reinterpret_cast<double*>(A.win[k] + A.off_scal) + ((size_t)par * N + src) * 4; };
-  auto texch = [&](int k, int par, int src) { return reinterpret_cast<double*>(A.win[k] + A.off_t) + ((size_t)par * N + src) * (size_t)nC; };
   // low-latency packet slots in rank k's window, written by rank src: 4 scalars ([0] p.q, [1] coarse flag, [2] r.z, [3] r.r), 6 nc of P^T q
   auto lls = [&](int k, int par, int src, int which) { return A.win[k] + A.off_lls + (((size_t)par * N + src) * 4 + which) * 16; };
   auto llt = [&](int k, int par, int src, int j) { return A.win[k] + A.off_llt + (((size_t)par * N + src) * (size_t)nC + j) * 16; };
@@ -675,7 +673,7 @@ __global__ void __launch_bounds__(P2_TPB, 1) k_pcg2(Pcg2Args A) {
 
 // byte layout of one exchange window
 struct Pcg2Layout {
-  size_t off_z, off_scal, off_t, off_x, off_flags, off_ctl, off_lls, off_llt, bytes;
+  size_t off_z, off_x, off_flags, off_ctl, off_lls, off_llt, bytes;
 };
 inline Pcg2Layout pcg2_layout(int n, int nranks, int nC) {
   Pcg2Layout L;
@@ -683,8 +681,6 @@ inline Pcg2Layout pcg2_layout(int n, int nranks, int nC) {
   auto take = [&](size_t bytes) { const size_t at = o; o += (bytes + 255) & ~(size_t)255; return at; };
   const size_t nv = (size_t)n * 6;
   L.off_z = take(2 * nv * sizeof(double));
-  L.off_scal = take((size_t)2 * nranks * 4 * sizeof(double));
-  L.off_t = take((size_t)2 * nranks * (nC > 0 ? nC : 1) * sizeof(double));
   L.off_x = take(nv * sizeof(double));
   L.off_flags = take((size_t)nranks * sizeof(unsigned long long));
   L.off_ctl = take(sizeof(unsigned));

@@ -10,7 +10,7 @@
 // calls of every window at once; a query's row is m*n*2 bytes back over PCIe, small next to the per-window pointer chasing
 // it replaces.  Host work: the lookup grid as a CSR over cells (counting sort in feature order == push_back order), the
 // window walk in the reference's visiting order and the order-dependent choice.  ccm_select_* run the host half on a
-// caller-supplied matrix and need no device.  CCM_MATCH_WINDOW=1 (not yet run on a device) keeps the order-independent choices
+// caller-supplied matrix and need no device.  The default (CCM_MATCH_WINDOW=0 switches it off; validated on B200, profiles/r2/match_window.log) keeps the order-independent choices
 // (Fuse x2, SearchBySim3) on the device: k_window_best, m indices back instead of an m x n matrix.
 #include <climits>
 #include <cmath>
@@ -254,7 +254,7 @@ void select_init(const ccm_feature_grid* g2, const ccm_proj_queries* q, const ui
   *nmatches = found;
 }
 
-// ---- device-side window search for the order-independent matchers (CCM_MATCH_WINDOW=1; not yet run on a device) -------------
+// ---- device-side window search for the order-independent matchers (default; CCM_MATCH_WINDOW=0: full matrix + host selection) -------------
 // Fuse x2 and both directions of SearchBySim3 choose, per query, the first minimum over the window at levels [L-1, L]: no query
 // depends on another, so the whole choice can stay on the device and only m indices come back instead of an m x n matrix.
 // One warp per query walks the cell runs (columns c0..c1, rows r0..r1 — computed on the host with the reference's float

@@ -1,4 +1,4 @@
-"""GPU suite (opt-in until seen green on a device once: CCM_TEST_UNVALIDATED=1, tools/validate_prepared.sh step 1e): the map update
+"""GPU suite (first device run in round 2: profiles/r2/map_update_gpu.log): the map update
 after a global BA through the C ABI (ccm_gba_map_update: host keyframe pass + k_map_update_points) against the CPU oracle — the same
 f32 operations in the same order on both sides, so bit for bit.  The arithmetic has run on the host (tests/test_map_update.py)."""
 import os

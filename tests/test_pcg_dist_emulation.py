@@ -1,8 +1,8 @@
-"""CPU suite: the row-distributed PCG algorithm of csrc/pcg_dist.cuh (own-row products, rank-ordered partial sums, parity-buffered z,
+"""CPU suite: the row-distributed PCG algorithm of csrc/pcg2.cuh's multi-rank mode (own-row products, rank-ordered partial sums, parity-buffered z,
 exchanged restriction partials, constant and linear prolongation), emulated with 2-8 virtual ranks in numpy (tools/emulate_pcg_dist.py),
 reproduces serial two-level PCG: same iteration count up to rounding, same solution.  This checks the algorithm the kernel implements —
 every rank taking the same branches from rank-ordered sums, no read of a buffer another rank may still be writing in the emulated
-schedule — not the kernel itself, whose first device run is listed in DESIGN.md 'Prepared, not yet run on a device'."""
+schedule — not the kernel itself; that runs in tools/multirank_check.py and in the parity block of every multi-rank bench line."""
 import importlib.util
 import os
 import warnings

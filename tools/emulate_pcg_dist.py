@@ -1,4 +1,4 @@
-"""Algorithm-level emulation of k_pcg_dist (pcg_dist.cuh) with N virtual ranks in numpy: own-row SpMV, partial scalars summed in rank
+"""Algorithm-level emulation of the row-distributed PCG (k_pcg2 with nranks > 1, csrc/pcg2.cuh; first written for its predecessor k_pcg_dist) with N virtual ranks in numpy: own-row SpMV, partial scalars summed in rank
 order, z slices exchanged with iteration parity, p recomputed everywhere, partial restrictions summed, replicated coarse solve.
 Compared with a serial PCG using the same preconditioner (M^-1 = blockdiag^-1 + P Ac^-1 P^T)."""
 import numpy as np, scipy.sparse as sp

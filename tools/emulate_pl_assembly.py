@@ -1,7 +1,7 @@
 """Host emulation of the piecewise-linear Galerkin assembly of k_pcg (csrc/pcg.cuh, prolong = 1): the running-sum state machine
 (sums for coarse columns `cur` and `cur + 1`, shift when lo(b) advances, weighted flush into both row parents), lane by lane in
 numpy, against scipy's P^T S P with an independently built P; also restriction and interpolation through coarse_parents().
-The kernel path itself has not run on a device yet ("Prepared, not yet run")."""
+The kernel path itself is the default since round 2 (parity suite green on B200, profiles/r2/prolong_parity.log)."""
 import sys, numpy as np, scipy.sparse as sp
 
 def parents(a, agg, nc):
