@@ -404,7 +404,7 @@ __global__ void __launch_bounds__(CTA) k_schur_mma(const uint2* __restrict__ pro
                                                    const double* __restrict__ gvec, double* __restrict__ U_val,
                                                    double* __restrict__ bneg, const int* __restrict__ tile_ptr = nullptr,
                                                    const int* __restrict__ tile_u = nullptr,
-                                                   const unsigned char* __restrict__ covered = nullptr) {
+                                                   const unsigned char* __restrict__ covered = nullptr, int only_diag = 0) {
   static_assert(UNROLL % 2 == 0, "products alternate between two accumulator sets");
   int warp;
   if (TILED) {
@@ -424,6 +424,7 @@ __global__ void __launch_bounds__(CTA) k_schur_mma(const uint2* __restrict__ pro
   const unsigned beg = u_prod_ptr[warp], end = u_prod_ptr[warp + 1];
   const int row = u_row[warp];
   const bool diag = row == u_col[warp];
+  if (only_diag && !diag) return;  // the off-diagonal blocks belong to k_schur_rowsync
   double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
   unsigned p = beg;
   if (!diag && PIPE) {
@@ -502,6 +503,74 @@ __global__ void __launch_bounds__(CTA) k_schur_mma(const uint2* __restrict__ pro
     U_val[(size_t)warp * 36 + m * 6 + 2 * k + 1] = -c01;
   }
   if (diag && m < 6 && k == 3) bneg[(size_t)row * 6 + m] = -c00;  // C[m][6]
+}
+
+// Row-synchronous form (CCM_SCHUR=10): a CTA takes up to RS_W consecutive OFF-DIAGONAL upper blocks of ONE block row a (the schedule
+// rs_first / rs_count is cut at row boundaries) and its warps walk their product lists -- sorted by the observation of a, i.e. by
+// landmark -- chunk by chunk of 2^RS_SHIFT observation indices with a CTA barrier after every chunk.  All warps then need the same
+// rows Z_(l, a) at the same time: they are fetched from L2 once per CTA and served from L1 to the other warps, which the free-running
+// list kernel does not achieve (its warps drift apart).  The diagonal blocks (lists four times as long, and the g_l column) stay with
+// k_schur_mma, launched with only_diag = 1.
+constexpr int RS_W = 8;
+constexpr int RS_SHIFT = 13;
+template <int UNROLL>
+__global__ void __launch_bounds__(32 * RS_W) k_schur_rowsync(const uint2* __restrict__ prod, const unsigned* __restrict__ u_prod_ptr,
+                                                             const int* __restrict__ rs_first, const int* __restrict__ rs_count,
+                                                             const double* __restrict__ Z, double* __restrict__ U_val) {
+  __shared__ unsigned s_cmin, s_cmax;
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int count = rs_count[blockIdx.x];
+  const bool active = w < count;
+  const int u = active ? rs_first[blockIdx.x] + w : 0;
+  const int m = lane >> 2, k = lane & 3;
+  const bool ld = m < 6 && k < 3;
+  const int off = ld ? m * 3 + k : 0;
+  unsigned p = 0, end = 0;
+  if (active) { p = u_prod_ptr[u]; end = u_prod_ptr[u + 1]; }
+  if (threadIdx.x == 0) { s_cmin = 0xffffffffu; s_cmax = 0u; }
+  __syncthreads();
+  if (active && lane == 0 && p < end) {
+    atomicMin(&s_cmin, prod[p].x >> RS_SHIFT);
+    atomicMax(&s_cmax, prod[end - 1].x >> RS_SHIFT);
+  }
+  __syncthreads();
+  const unsigned cmin = s_cmin, cmax = s_cmax;
+  double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
+  // (the last pass, c = cmax + 1 with no limit, takes what a list too long for the set-up sort left out of order)
+  if (cmin != 0xffffffffu)
+    for (unsigned c = cmin; c <= cmax + 1u; c++) {
+      const unsigned lim = c > cmax ? 0xfffffffeu : c;
+      while (p < end) {
+        uint2 pr[UNROLL];
+        int n_in = 0;
+#pragma unroll
+        for (int j = 0; j < UNROLL; j++) {
+          pr[j] = p + j < end ? prod[p + j] : make_uint2(0xffffffffu, 0u);
+          if (pr[j].x != 0xffffffffu && (pr[j].x >> RS_SHIFT) <= lim) n_in = j + 1;   // sorted: the entries of this chunk are a prefix
+        }
+        if (n_in == 0) break;
+        double a[UNROLL], b[UNROLL];
+#pragma unroll
+        for (int j = 0; j < UNROLL; j++) {
+          const bool in = j < n_in;
+          a[j] = (in && ld) ? Z[(size_t)pr[j].x * 18 + off] : 0.0;
+          b[j] = (in && ld) ? Z[(size_t)pr[j].y * 18 + off] : 0.0;
+        }
+#pragma unroll
+        for (int j = 0; j < UNROLL; j += 2) {
+          dmma_884(c00, c01, a[j], b[j]);
+          dmma_884(c10, c11, a[j + 1], b[j + 1]);
+        }
+        p += n_in;
+      }
+      __syncthreads();
+    }
+  if (!active) return;
+  c00 += c10; c01 += c11;
+  if (ld) {
+    U_val[(size_t)u * 36 + m * 6 + 2 * k] = -c00;
+    U_val[(size_t)u * 36 + m * 6 + 2 * k + 1] = -c01;
+  }
 }
 
 // S (full block-CSR) from the upper blocks: diagonal gets Hpp + lambda I, lower blocks are transposed copies.

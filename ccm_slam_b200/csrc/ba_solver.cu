@@ -80,6 +80,8 @@ struct ccm_ba_handle {
   int npan = 0;
   DevBuf<int> o_slot, pose_lmin, pose_lmax, pose_cnt;
   DevBuf<unsigned char> pan_on, covered;
+  DevBuf<int> rs_first, rs_count;  // row-synchronous Schur schedule (CCM_SCHUR=10): CTAs of <= RS_W off-diagonal blocks of one row
+  int rs_ctas = 0;
   DevBuf<int> tile_ptr, tile_u;   // T x T tiles of upper blocks: the CTA schedule of the tiled Schur kernel
   int ntiles = 0, tile_T = 0;
   DevBuf<float4> kobs;            // per free pose: (u, v, signed w, landmark) of its observations, packed
@@ -259,7 +261,7 @@ int schur_mode() {
     if (!strcmp(v, "gather") || !strcmp(v, "0")) return 0;
     if (!strcmp(v, "mma")) return 1;
     const int m = atoi(v);
-    return (m >= 0 && m <= 9) ? m : 1;
+    return (m >= 0 && m <= 10) ? m : 1;
   }();
   const int o = g_schur_override.load(std::memory_order_relaxed);
   return o >= 0 ? o : env_mode;
@@ -292,7 +294,14 @@ void launch_schur(ccm_ba_handle* h, cudaStream_t s) {
     CCM_LAUNCHED();
   }
   const int mode = schur_mode();
-  if (mode >= 9 && h->ntiles > 0) {   // tiled schedules (the tile edge was fixed when the handle was created: CCM_SCHUR_TILE)
+  if (mode == 10 && h->rs_ctas > 0) {   // off-diagonal blocks row-synchronously, diagonal blocks by the list kernel
+    k_schur_rowsync<8><<<h->rs_ctas, 32 * RS_W, 0, s>>>(h->prod.p, h->u_prod_ptr.p, h->rs_first.p, h->rs_count.p, h->Z.p, h->U_val());
+    k_schur_mma<8, 128, true><<<div_up((long long)h->nub * 32, 128), 128, 0, s>>>(h->prod.p, h->u_prod_ptr.p, h->u_row.p, h->u_col.p, h->nub, h->Z.p,
+                                                                               h->o_lm.p, h->gvec.p, h->U_val(), h->bneg(), nullptr, nullptr,
+                                                                               h->panel_on ? h->covered.p : nullptr, 1);
+    return;
+  }
+  if (mode == 9 && h->ntiles > 0) {   // tiled schedules (the tile edge was fixed when the handle was created: CCM_SCHUR_TILE)
     if (h->tile_T == 4) launch_schur_tiled<8, 512>(h, s);
     else if (h->tile_T == 3) launch_schur_tiled<8, 288>(h, s);
     else launch_schur_tiled<8, 128>(h, s);
@@ -342,7 +351,7 @@ void step_finalize(ccm_ba_handle* h, double lambda) {
 void step_pcg(ccm_ba_handle* h, double tol, int max_iter) {
   cudaStream_t s = h->stream;
   KernelSpan sp(h, CCM_BA_K_PCG);
-  CCM_CUDA(cudaMemsetAsync(h->pcg_bar.p, 0, sizeof(unsigned), s));
+  CCM_CUDA(cudaMemsetAsync(h->pcg_bar.p, 0, 2 * sizeof(unsigned), s));
   PcgArgs a;
   a.n = h->Kf; a.rowptr = h->s_rowptr.p; a.col = h->s_col.p; a.val = h->s_val.p; a.Minv = h->Minv.p; a.b = h->bschur.p;
   a.x = h->x.p; a.r = h->pr.p; a.z = h->pz.p; a.p = h->pp.p; a.q = h->pq.p;
@@ -836,8 +845,8 @@ void build(ccm_ba_handle* h, const ccm_ba_problem* p) {
   // Measured on cfg5 (profiles/r2/schur_tiled_cfg5.log): sorted lists 8.42 ms vs 8.43 ms unsorted, tiles 2x2 8.16 ms, 3x3 8.72 ms,
   // 4x4 15.3 ms (the long diagonal lists keep a 16-warp CTA alive while 12 warps idle) -- the gather is not L1-reuse bound.  Both
   // stay available for experiments (CCM_SCHUR_SORT=1, CCM_SCHUR=9 + CCM_SCHUR_TILE) but cost set-up time, so they are off by default.
-  const bool want_tiles = schur_mode() == 9;
-  if (h->nprod && env_int("CCM_SCHUR_SORT", want_tiles ? 1 : 0)) {   // landmark order inside every list: deterministic sums
+  const bool want_tiles = schur_mode() == 9, want_rowsync = schur_mode() == 10;
+  if (h->nprod && env_int("CCM_SCHUR_SORT", (want_tiles || want_rowsync) ? 1 : 0)) {   // landmark order inside every list: deterministic sums
     k_sort_products<<<nub, 256, 0, s>>>(h->u_prod_ptr.p, nub, h->prod.p);
     CCM_LAUNCHED();
   }
@@ -866,6 +875,17 @@ void build(ccm_ba_handle* h, const ccm_ba_problem* p) {
     CCM_CUDA(cudaMemcpyAsync(h->tile_u.p, v_out.p, sizeof(int) * (size_t)nub, cudaMemcpyDeviceToDevice, s));
     CCM_CUDA(cudaMemcpyAsync(&h->ntiles, rank.p + (nub - 1), sizeof(int), cudaMemcpyDeviceToHost, s));
     CCM_CUDA(cudaStreamSynchronize(s));  // ntiles is the grid size; the temporaries die here
+  }
+  h->rs_ctas = 0;
+  if (want_rowsync && nub > 0 && h->nprod) {   // CTAs of <= RS_W consecutive off-diagonal blocks, cut at row boundaries (host: Kf rows)
+    std::vector<int> first, count;
+    for (int a2 = 0; a2 < Kf; a2++) {
+      const int u0 = h_udiag[a2] + 1, u1 = a2 + 1 < Kf ? h_udiag[a2 + 1] : nub;   // the diagonal block is the first upper block of its row
+      for (int q = u0; q < u1; q += RS_W) { first.push_back(q); count.push_back(std::min(RS_W, u1 - q)); }
+    }
+    h->rs_ctas = (int)first.size();
+    upload_vec(h->rs_first, first, s); upload_vec(h->rs_count, count, s);
+    CCM_CUDA(cudaStreamSynchronize(s));
   }
   lap("product lists");
   // packed per-pose observation stream for the pose pass
@@ -1303,7 +1323,7 @@ extern "C" int ccm_ba_debug_schur(ccm_ba_handle* h, int robust, double huber_del
 
 extern "C" int ccm_ba_debug_set_schur_mode(int mode) {
   return guarded([&] {
-    CCM_REQUIRE(mode >= -1 && mode <= 9, "ccm_ba_debug_set_schur_mode: -1 (CCM_SCHUR / default), 0 gather, 1 mma, 2..8 mma variants, 9 tiled");
+    CCM_REQUIRE(mode >= -1 && mode <= 10, "ccm_ba_debug_set_schur_mode: -1 (CCM_SCHUR / default), 0 gather, 1 mma, 2..8 mma variants, 9 tiled, 10 row-synchronous");
     g_schur_override.store(mode);
   });
 }

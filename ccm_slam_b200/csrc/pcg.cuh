@@ -64,6 +64,9 @@ struct PcgArgs {
   long long* prof;   // optional: 8 cycle counters filled by CTA 0 (setup, spmv, update+restrict, coarse, precond, unused) or NULL
 };
 
+// One counter, every CTA polls it.  (Round 2 tried the variant k_pcg2 uses -- the last arriver releases a separate generation word
+// the others poll -- here too: with 296 CTAs of 256 threads it was 8 % SLOWER on cfg4 (22.6 vs 20.9 ms of PCG per Global BA,
+// profiles/r2/b20_cfg4.log): the extra hop costs more than the contention it removes.)
 __device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned& target) {
   __syncthreads();
   if (threadIdx.x == 0) {

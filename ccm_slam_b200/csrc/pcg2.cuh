@@ -155,6 +155,26 @@ __device__ __forceinline__ bool p2_barrier(const Pcg2Args& A, unsigned& gen, uns
   const bool node = cross && multi;
   if (node) epoch += 1;
   volatile unsigned* ctl = reinterpret_cast<volatile unsigned*>(A.win[A.rank] + A.off_ctl);
+  if (!multi && !node) {
+    // one GPU: nothing to publish between arrival and release, so the LAST arriver releases the others (one hop less than routing
+    // the release through CTA 0)
+    if (threadIdx.x == 0) {
+      int ok = 1;
+      __threadfence();
+      if (atomicAdd(A.bar, 1u) + 1u == gen * gridDim.x) {
+        p2_st_release_gpu(A.bar + 1, gen);
+      } else {
+        const long long t0 = clock64();
+        unsigned g;
+        while ((g = p2_ld_acquire_gpu(A.bar + 1)) < gen)
+          if (clock64() - t0 > A.timeout_cycles) { ok = 0; break; }
+        if (g == 0xFFFFFFFFu) ok = 0;
+      }
+      *s_ok = ok;
+    }
+    __syncthreads();
+    return *s_ok != 0;
+  }
   if (threadIdx.x == 0) {
     if (multi && remote) __threadfence_system(); else __threadfence();
     atomicAdd(A.bar, 1u);

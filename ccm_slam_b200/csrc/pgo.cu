@@ -247,7 +247,7 @@ void pgo_solve(const ccm_pgo_problem* p, const ccm_pgo_options* o, ccm_pgo_resul
   H.alloc(nnzb * 49); Hs.alloc(nnzb * 49); b.alloc((size_t)n * 7); Minv.alloc((size_t)n * 49);
   x.alloc_zero((size_t)n * 7, s); pr.alloc((size_t)n * 7); pz.alloc((size_t)n * 7); pp.alloc((size_t)2 * n * 7); pq.alloc((size_t)n * 7);
   const int gsm = sm_count();
-  partials.alloc((size_t)gsm * 8 + 8); scal.alloc_zero(8, s); pcg_status.alloc_zero(4, s); bar.alloc_zero(1, s); fail.alloc_zero(1, s);
+  partials.alloc((size_t)gsm * 8 + 8); scal.alloc_zero(8, s); pcg_status.alloc_zero(4, s); bar.alloc_zero(2, s); fail.alloc_zero(1, s);
   const int pcg_block = ((long long)n * 32 >= (long long)gsm * PCG_TPB) ? 512 : 256;
   void* pcg_fn = pcg_block == 512 ? (void*)k_pcg<7, 512, 1> : (void*)k_pcg<7, 256, 2>;
   int per_sm = 0;
@@ -313,7 +313,7 @@ void pgo_solve(const ccm_pgo_problem* p, const ccm_pgo_options* o, ccm_pgo_resul
       CCM_LAUNCHED();
       k_pgo_add_lambda<<<div_up(n * 7, 128), 128, 0, s>>>(Hs.p, d_diag.p, n, lambda);
       CCM_LAUNCHED();
-      CCM_CUDA(cudaMemsetAsync(bar.p, 0, sizeof(unsigned), s));
+      CCM_CUDA(cudaMemsetAsync(bar.p, 0, 2 * sizeof(unsigned), s));
       PcgArgs a;
       a.n = n; a.rowptr = d_rowptr.p; a.col = d_col.p; a.val = Hs.p; a.Minv = Minv.p; a.b = b.p;
       a.x = x.p; a.r = pr.p; a.z = pz.p; a.p = pp.p; a.q = pq.p; a.partials = pcg_partials.p; a.bar = bar.p;

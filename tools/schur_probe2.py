@@ -13,9 +13,11 @@ name = sys.argv[1] if len(sys.argv) > 1 else "cfg5"
 api.init(0)
 t = time.time(); p = synth.make_config(name); print(f"[{name}] K={p.K} P={p.P} E={p.E} generated in {time.time() - t:.1f}s", flush=True)
 ref = None
-for label, env, mode in [("untiled prefetch, unsorted lists", {"CCM_SCHUR_SORT": "0"}, 8), ("untiled prefetch, sorted lists", {}, 8),
-                         ("tiled 2x2", {"CCM_SCHUR_TILE": "2"}, 9), ("tiled 3x3", {"CCM_SCHUR_TILE": "3"}, 9), ("tiled 4x4", {"CCM_SCHUR_TILE": "4"}, 9),
-                         ("tiled 4x4, unsorted lists", {"CCM_SCHUR_TILE": "4", "CCM_SCHUR_SORT": "0"}, 9)]:
+ALL = [("untiled prefetch, unsorted lists", {"CCM_SCHUR_SORT": "0"}, 8), ("untiled prefetch, sorted lists", {"CCM_SCHUR_SORT": "1"}, 8),
+       ("tiled 2x2", {"CCM_SCHUR_TILE": "2"}, 9), ("tiled 3x3", {"CCM_SCHUR_TILE": "3"}, 9), ("tiled 4x4", {"CCM_SCHUR_TILE": "4"}, 9),
+       ("tiled 4x4, unsorted lists", {"CCM_SCHUR_TILE": "4", "CCM_SCHUR_SORT": "0"}, 9), ("row-synchronous", {}, 10)]
+want = sys.argv[2:]   # optional: substrings of the variant labels to run
+for label, env, mode in [v for v in ALL if not want or any(w in v[0] for w in want)]:
     for k, v in env.items():
         os.environ[k] = v
     try:
