@@ -261,6 +261,12 @@ class BAHandle:
         _chk(lib().ccm_ba_debug_schur(self._h, int(robust), C.c_double(huber_delta), C.c_double(lam), _p(S), _p(bs), _p(dxp), _p(dxl), C.byref(it), C.byref(rr)))
         return dict(S=S, bschur=bs, dx_pose=dxp, dx_point=dxl, pcg_iters=it.value, pcg_relres=rr.value)
 
+    def set_estimate(self, poses=None, points=None):
+        """replace the estimate, keep structure and observations on the device (ccm_ba_set_estimate)"""
+        ps = None if poses is None else np.ascontiguousarray(poses, np.float64)
+        pt = None if points is None else np.ascontiguousarray(points, np.float64)
+        _chk(lib().ccm_ba_set_estimate(self._h, _p(ps), _p(pt)))
+
     def pcg_cycles(self):
         """SM-clock cycles CTA 0 of the PCG kernel spent per phase (handle created with CCM_PCG_PROF=1): set-up, product, coarse, precondition, ..."""
         c = np.zeros(8, np.int64)

@@ -1161,6 +1161,17 @@ extern "C" int ccm_ba_reset(ccm_ba_handle* h) {
   return guarded([&] { CCM_REQUIRE(h, "null handle"); CCM_CUDA(cudaSetDevice(h->device)); do_reset(h); });
 }
 
+extern "C" int ccm_ba_set_estimate(ccm_ba_handle* h, const double* poses, const double* points) {
+  return guarded([&] {
+    CCM_REQUIRE(h, "null handle");
+    CCM_CUDA(cudaSetDevice(h->device));
+    cudaStream_t s = h->stream;
+    if (poses) CCM_CUDA(cudaMemcpyAsync(h->pose0.p, poses, sizeof(double) * 7 * (size_t)h->K, cudaMemcpyHostToDevice, s));
+    if (points && h->Pl) CCM_CUDA(cudaMemcpyAsync(h->pt0.p, points + 3 * (size_t)h->L0, sizeof(double) * 3 * (size_t)h->Pl, cudaMemcpyHostToDevice, s));
+    do_reset(h);   // the new values become the current estimate (synchronises the stream: the caller's buffers are free again)
+  });
+}
+
 extern "C" int ccm_ba_set_edge_flags(ccm_ba_handle* h, const uint8_t* edge_flags) {
   return guarded([&] {
     CCM_REQUIRE(h, "null handle");

@@ -119,6 +119,10 @@ int ccm_ba_solve(const ccm_ba_problem* p, const ccm_ba_options* o, ccm_ba_result
 int ccm_ba_create(const ccm_ba_problem* p, ccm_ba_handle** out);
 /* restore the estimate uploaded at create time (edge flags unchanged) */
 int ccm_ba_reset(ccm_ba_handle* h);
+/* replace the estimate (K*7 poses, P*3 points; either may be NULL = keep): the structure, the observations and everything built from
+ * them stay on the device.  A server whose map changed in value only since the last global BA (the persistent mirror says so) keeps
+ * its handle and uploads K*56 + P*24 bytes instead of the whole problem (cfg5: 24.6 MB instead of 425 MB, no structure build). */
+int ccm_ba_set_estimate(ccm_ba_handle* h, const double* poses, const double* points);
 /* replace edge flags (E bytes, same order as at create) — LocalBA round 2 */
 int ccm_ba_set_edge_flags(ccm_ba_handle* h, const uint8_t* edge_flags);
 int ccm_ba_optimize(ccm_ba_handle* h, const ccm_ba_options* o, ccm_ba_result* r);

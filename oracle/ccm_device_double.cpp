@@ -54,6 +54,7 @@ struct ccm_ba_handle {
 
 extern "C" {
 const char* ccm_last_error(void) { return "(device double)"; }
+int ccm_double_ba_creates = 0;   /* test counter: how many handles ccm_ba_create has made */
 /* test hook: runs between the solve and the shim's write-back (a keyframe turning bad while the GBA thread was solving) */
 void (*ccm_double_after_solve)(void*) = nullptr;
 void* ccm_double_after_solve_arg = nullptr;
@@ -63,6 +64,7 @@ int ccm_ba_solve(const ccm_ba_problem* p, const ccm_ba_options* o, ccm_ba_result
   return rc;
 }
 int ccm_ba_create(const ccm_ba_problem* p, ccm_ba_handle** out) {
+  ccm_double_ba_creates++;
   ccm_ba_handle* h = new ccm_ba_handle;
   h->poses.assign(p->poses, p->poses + 7 * (size_t)p->K); h->intr.assign(p->intr, p->intr + 4 * (size_t)p->K);
   h->fixed.assign(p->fixed, p->fixed + p->K); h->points.assign(p->points, p->points + 3 * (size_t)p->P);
@@ -70,6 +72,11 @@ int ccm_ba_create(const ccm_ba_problem* p, ccm_ba_handle** out) {
   h->uv.assign(p->obs_uv, p->obs_uv + 2 * (size_t)p->E); h->w.assign(p->obs_w, p->obs_w + p->E);
   if (p->edge_flags) { h->flags.assign(p->edge_flags, p->edge_flags + p->E); h->has_flags = true; }
   *out = h;
+  return CCM_OK;
+}
+int ccm_ba_set_estimate(ccm_ba_handle* h, const double* poses, const double* points) {
+  if (poses) h->poses.assign(poses, poses + h->poses.size());
+  if (points) h->points.assign(points, points + h->points.size());
   return CCM_OK;
 }
 int ccm_ba_set_edge_flags(ccm_ba_handle* h, const uint8_t* f) { h->flags.assign(f, f + h->obs_kf.size()); h->has_flags = true; return CCM_OK; }

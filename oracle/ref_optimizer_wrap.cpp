@@ -192,6 +192,52 @@ extern "C" int optw_gba_mirror(const optw_scene* s, int iterations, int robust, 
     return 0;
   } catch (...) { if (mir) ccm_mirror_destroy(mir); return -1; }
 }
+/* two MapFusionGBA calls in a row on one map (direct write-back, so the second starts from the first's result); with a mirror the
+   values the first call wrote are reported to it in between (what SetPose / SetWorldPos hooks do on a server): value changes only, so
+   the second call must reuse the solver handle.  *creates = handles created in all (device double's counter), -1 if unknown. */
+extern "C" int optw_gba_twice(const optw_scene* s, int use_mirror, int iterations, optw_out* o, int32_t* creates) {
+  ccm_map_mirror* mir = nullptr;
+  Dl_info self;
+  int* counter = nullptr;
+  if (dladdr(reinterpret_cast<void*>(&do_flip), &self)) {
+    void* me = dlopen(self.dli_fname, RTLD_NOLOAD | RTLD_NOW);
+    if (me) { counter = reinterpret_cast<int*>(dlsym(me, "ccm_double_ba_creates")); dlclose(me); }
+  }
+  const int c0 = counter ? *counter : 0;
+  try {
+    Scene sc(s);
+    auto feed_values = [&]() {
+      for (int k = 0; k < s->K; k++) { KeyFrame& F = sc.kf_store[k]; if (ccm_mirror_set_keyframe(mir, (uint64_t)F.mUniqueId, F.Tcw.ptr<float>(0), nullptr, F.mbBad ? 1 : 0) != 0) throw 1; }
+      for (int j = 0; j < s->P; j++) { MapPoint& M = sc.mp_store[j]; if (ccm_mirror_set_point(mir, (uint64_t)M.mUniqueId, M.mWorldPos.ptr<float>(0), M.mbBad ? 1 : 0) != 0) throw 1; }
+    };
+    if (use_mirror) {
+      if (ccm_mirror_create(&mir) != 0) return -3;
+      for (int k = 0; k < s->K; k++) {
+        KeyFrame& F = sc.kf_store[k];
+        const float intr[4] = {F.fx, F.fy, F.cx, F.cy};
+        if (ccm_mirror_set_keyframe(mir, (uint64_t)F.mUniqueId, F.Tcw.ptr<float>(0), intr, F.mbBad ? 1 : 0) != 0) throw 1;
+      }
+      for (int j = 0; j < s->P; j++) {
+        MapPoint& M = sc.mp_store[j];
+        if (ccm_mirror_set_point(mir, (uint64_t)M.mUniqueId, M.mWorldPos.ptr<float>(0), M.mbBad ? 1 : 0) != 0) throw 1;
+        for (auto& ob : M.mObservations) {
+          const KeyFrame& F = *ob.first; const cv::KeyPoint& kp = F.mvKeysUn[ob.second];
+          if (ccm_mirror_set_observation(mir, (uint64_t)F.mUniqueId, (uint64_t)M.mUniqueId, kp.pt.x, kp.pt.y, F.mvInvLevelSigma2[kp.octave]) != 0) throw 1;
+        }
+      }
+      cslam::ccm_b200_register_mirror(sc.map.get(), mir);
+    }
+    const idpair direct((size_t)0, (size_t)s->map_id);
+    for (int round = 0; round < 2; round++) {
+      if (use_mirror && round == 1) feed_values();
+      Optimizer::MapFusionGBA(sc.map, (size_t)s->map_id, iterations, NULL, direct, true);
+    }
+    if (use_mirror) { cslam::ccm_b200_register_mirror(sc.map.get(), nullptr); ccm_mirror_destroy(mir); mir = nullptr; }
+    sc.read(s, o);
+    *creates = counter ? *counter - c0 : -1;
+    return 0;
+  } catch (...) { if (mir) ccm_mirror_destroy(mir); return -1; }
+}
 #endif
 extern "C" {
 

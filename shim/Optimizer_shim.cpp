@@ -75,19 +75,32 @@ void check(int rc) { if (rc != CCM_OK) { std::cerr << "libccm_b200: " << ccm_las
 
 // Optional persistent mirrors: a server that keeps a ccm_map_mirror up to date for a Map
 // registers it here; MapFusionGBA then takes the flat problem from the mirror instead of walking the pointer graph.
+// With the mirror comes a cached solver handle: as long as the mirror did not have to rebuild its flat arrays (values changed, the
+// structure did not), the next global BA keeps the device-resident structure and uploads the estimate only (ccm_ba_set_estimate).
+struct MirrorEntry {
+  ccm_map_mirror* mirror = nullptr;
+  ccm_ba_handle* handle = nullptr;
+  long long rebuilds = -1;                 // ccm_mirror_rebuilds() when the handle was created
+  uint64_t max_uid = 0, fixed_uid = 0;
+};
 std::mutex g_mirror_mu;
-std::unordered_map<const Map*, ccm_map_mirror*> g_mirrors;
-ccm_map_mirror* mirror_of(const Map* m) {
+std::unordered_map<const Map*, MirrorEntry> g_mirrors;
+MirrorEntry* mirror_of(const Map* m) {
   std::lock_guard<std::mutex> lock(g_mirror_mu);
   auto it = g_mirrors.find(m);
-  return it == g_mirrors.end() ? nullptr : it->second;
+  return it == g_mirrors.end() ? nullptr : &it->second;   // (entries are stable: unordered_map never moves its nodes)
 }
 
 }  // namespace
 
 void ccm_b200_register_mirror(const Map* map, ccm_map_mirror* mirror) {   // cslam::ccm_b200_register_mirror; mirror == nullptr: forget the map
   std::lock_guard<std::mutex> lock(g_mirror_mu);
-  if (mirror) g_mirrors[map] = mirror; else g_mirrors.erase(map);
+  auto it = g_mirrors.find(map);
+  if (it != g_mirrors.end()) {
+    if (it->second.handle) ccm_ba_destroy(it->second.handle);   // the cached solver state goes with the registration
+    g_mirrors.erase(it);
+  }
+  if (mirror) g_mirrors[map].mirror = mirror;
 }
 
 // ---- MapFusionGBA (S/Optimizer.cpp:646-859) ---------------------------------------------------------------------------
@@ -99,7 +112,8 @@ void Optimizer::MapFusionGBA(mapptr pMap, size_t ClientId, int nIterations, bool
   if (pMap->mvpKeyFrameOrigins.empty()) throw infrastructure_ex();
   const idpair FixedId = (*(pMap->mvpKeyFrameOrigins.begin()))->mId;
 
-  if (ccm_map_mirror* mir = mirror_of(pMap.get())) {
+  if (MirrorEntry* ent = mirror_of(pMap.get())) {
+    ccm_map_mirror* mir = ent->mirror;
     // The mirror already holds the flat arrays (same selection rules, tests/test_map_mirror.py): no GetObservations() copies, no
     // Converter::toSE3Quat per keyframe.  Only the id -> object tables of the write-back are built here: O(K + P), no observation walk.
     std::unordered_map<uint64_t, kfptr> kf_of_uid;
@@ -123,7 +137,16 @@ void Optimizer::MapFusionGBA(mapptr pMap, size_t ClientId, int nIterations, bool
     vector<double> poses((size_t)prob.K * 7), points((size_t)prob.P * 3);
     ccm_ba_result res = {};
     res.poses = poses.data(); res.points = points.data();
-    check(ccm_ba_solve(&prob, &opt, &res));
+    const long long gen = ccm_mirror_rebuilds(mir);
+    if (ent->handle && ent->rebuilds == gen && ent->max_uid == (uint64_t)maxKFid && ent->fixed_uid == fixed_uid) {
+      check(ccm_ba_set_estimate(ent->handle, prob.poses, prob.points));   // same structure: the device keeps it, only the values travel
+    } else {
+      if (ent->handle) { ccm_ba_destroy(ent->handle); ent->handle = nullptr; }
+      check(ccm_ba_create(&prob, &ent->handle));
+      ent->rebuilds = gen; ent->max_uid = (uint64_t)maxKFid; ent->fixed_uid = fixed_uid;
+    }
+    const int rc = ccm_ba_optimize(ent->handle, &opt, &res);
+    if (rc != CCM_OK) { ccm_ba_destroy(ent->handle); ent->handle = nullptr; check(rc); }
     for (int r = 0; r < prob.K; r++) {                        // write-back by id, as the reference does (:803-823)
       auto it = kf_of_uid.find(kf_uid[r]);
       if (it == kf_of_uid.end() || it->second->isBad()) continue;

@@ -169,6 +169,17 @@ def run_gba_mirror(sc, iterations, robust, loop):
     return o
 
 
+def run_gba_twice(sc, use_mirror, iterations):
+    """two MapFusionGBA calls in a row (direct write-back); returns (map state, solver handles created: -1 if the library cannot tell)"""
+    keep = []
+    S = c_scene(sc, keep)
+    o, O = new_out(S.K, S.P)
+    n = C.c_int32(-2)
+    rc = lib().optw_gba_twice(C.byref(S), int(use_mirror), int(iterations), C.byref(O), C.byref(n))
+    assert rc == 0, rc
+    return o, n.value
+
+
 def run_essential_graph(sc, loop_kf, cur_kf, conn, fix_scale, loop_closure=False, corr=None, mp_corr_ref=None):
     """conn: {keyframe index: [keyframe indices]} = LoopConnections; corr = (kf indices, corrected (n,8), noncorrected (n,8))"""
     keep = []

@@ -125,6 +125,26 @@ def test_stop_flag_zero_iterations_reset(oracle):
     h.close()
 
 
+def test_set_estimate_keeps_the_structure_on_the_device(oracle):
+    """A second global BA on a map that changed in value only (the persistent mirror + a cached handle): the new
+    estimate is uploaded with ccm_ba_set_estimate, structure and observations stay resident; the result equals a from-scratch solve."""
+    p = synth.make_config("small")
+    h = api.BAHandle(p)
+    a = h.optimize(iterations=4, huber_delta=api.HUBER_GBA)
+    h.set_estimate(a["poses"], a["points"])
+    b = h.optimize(iterations=4, huber_delta=api.HUBER_GBA)
+    q = p.copy(); q.poses = a["poses"].copy(); q.points = a["points"].copy()
+    c = api.ba_solve(q, iterations=4, huber_delta=api.HUBER_GBA)
+    ref = oracle.ba_solve(q, iterations=4, huber_delta=api.HUBER_GBA)
+    assert b["iters_done"] == c["iters_done"] == ref["iters_done"] and b["trials_total"] == c["trials_total"] == ref["trials_total"]
+    assert np.allclose(b["poses"], c["poses"], atol=1e-9) and np.allclose(b["points"], c["points"], atol=1e-9)
+    _state_close(b, ref, 1e-4)
+    h.set_estimate(p.poses, None)                                  # poses only: the points keep the last uploaded estimate
+    d = h.optimize(iterations=1, huber_delta=api.HUBER_GBA)
+    assert d["iters_done"] == 1
+    h.close()
+
+
 def test_degenerate_graphs_behave_like_the_oracle(oracle):
     """Empty and ragged inputs: no observations, every edge switched off, an unobserved landmark, a landmark seen once,
     a free keyframe without observations (g2o leaves vertices without active edges alone)."""

@@ -108,6 +108,21 @@ def test_map_fusion_gba_through_the_persistent_mirror(ho, name, bad_kf, bad_mp, 
     assert np.abs(plain["kf_TcwGBA" if loop_mode else "kf_Tcw"] - sc["kf_Tcw"]).max() > 1e-4
 
 
+def test_second_gba_on_an_unchanged_structure_reuses_the_device_state(ho):
+    """Two global BAs in a row on one map whose structure did not change in between (values only: the first BA's own results): with a
+    registered mirror the second call keeps the solver handle -- structure, observations and everything built from them stay on the
+    device, ccm_ba_set_estimate uploads the estimate -- and the map it leaves is bit-identical to the per-call path (which creates a
+    handle inside ccm_ba_solve each time)."""
+    p = synth.make_config("small")
+    sc = H.scene_from_problem(p, ho, seed=9, map_id=0)
+    plain, n_plain = H.run_gba_twice(sc, False, 4)
+    mirrored, n_mirror = H.run_gba_twice(sc, True, 4)
+    for k in plain:
+        assert np.array_equal(plain[k], mirrored[k]), k
+    assert n_mirror == 1                                           # one ccm_ba_create for two BAs (the plain path goes through ccm_ba_solve)
+    assert (plain["kf_set_pose"] == 2).all()                       # both BAs wrote every keyframe
+
+
 # ---- essential graph ----------------------------------------------------------------------------------------------------------
 MIN_FEAT = 100      # params::opt::miEssGraphMinFeats, handed to the reference's config.h through the FileStorage stand-in (conftest sets it)
 
