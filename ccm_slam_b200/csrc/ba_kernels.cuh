@@ -397,7 +397,10 @@ __device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, doubl
 // TILED: the CTA takes the upper blocks of one T x T tile of S (tile_ptr / tile_u, built by build_schur_tiles): its warps share
 // the Z rows of T block rows and T block columns, and -- the product lists being sorted by landmark -- meet them at about the same
 // time, so most of the 2 x 144 bytes per product come from L1 instead of L2.
-template <int UNROLL, int CTA, bool PIPE = false, bool TILED = false>
+// VEC: the UNROLL list entries of a batch come in with ONE coalesced load (lane j takes entry j) and reach the other lanes by shuffle,
+// instead of UNROLL broadcast loads: the kernel sits at 65 % of the L1 wavefront rate, and the entry loads are a fifth of its wavefronts.
+// PRED (with VEC): the 14 padding lanes of a fragment do not load at all (predicated off) instead of re-reading element 0 of the row.
+template <int UNROLL, int CTA, bool PIPE = false, bool TILED = false, bool VEC = false, bool PRED = false>
 __global__ void __launch_bounds__(CTA) k_schur_mma(const uint2* __restrict__ prod, const unsigned* __restrict__ u_prod_ptr,
                                                    const int* __restrict__ u_row, const int* __restrict__ u_col, int nub,
                                                    const double* __restrict__ Z, const int* __restrict__ o_lm,
@@ -427,7 +430,38 @@ __global__ void __launch_bounds__(CTA) k_schur_mma(const uint2* __restrict__ pro
   if (only_diag && !diag) return;  // the off-diagonal blocks belong to k_schur_rowsync
   double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
   unsigned p = beg;
-  if (!diag && PIPE) {
+  if (!diag && PIPE && VEC) {
+    uint2 nxv = make_uint2(0u, 0u);
+    if (p + UNROLL <= end && lane < UNROLL) nxv = prod[p + lane];
+    for (; p + UNROLL <= end; p += UNROLL) {
+      uint2 pr[UNROLL];
+#pragma unroll
+      for (int j = 0; j < UNROLL; j++) { pr[j].x = __shfl_sync(0xffffffffu, nxv.x, j); pr[j].y = __shfl_sync(0xffffffffu, nxv.y, j); }
+      if (p + 2 * UNROLL <= end && lane < UNROLL) nxv = prod[p + UNROLL + lane];
+      double a[UNROLL], b[UNROLL];
+#pragma unroll
+      for (int j = 0; j < UNROLL; j++) {
+        if (PRED) {
+          a[j] = 0.0; b[j] = 0.0;
+          if (ld) { a[j] = Z[(size_t)pr[j].x * 18 + off]; b[j] = Z[(size_t)pr[j].y * 18 + off]; }
+        } else {
+          a[j] = Z[(size_t)pr[j].x * 18 + off];
+          b[j] = Z[(size_t)pr[j].y * 18 + off];
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < UNROLL; j += 2) {
+        dmma_884(c00, c01, ld ? a[j] : 0.0, ld ? b[j] : 0.0);
+        dmma_884(c10, c11, ld ? a[j + 1] : 0.0, ld ? b[j + 1] : 0.0);
+      }
+    }
+    for (; p < end; p++) {
+      const uint2 pr = prod[p];
+      const double a = Z[(size_t)pr.x * 18 + off], b = Z[(size_t)pr.y * 18 + off];
+      if ((p - beg) & 1u) dmma_884(c10, c11, ld ? a : 0.0, ld ? b : 0.0);
+      else dmma_884(c00, c01, ld ? a : 0.0, ld ? b : 0.0);
+    }
+  } else if (!diag && PIPE) {
     // software-pipelined form (8.43 ms against 8.73 ms on cfg5: the default): the product entries of batch k+1 are requested before the rows of batch k,
     // so the entry -> row dependence costs one memory latency per batch instead of two
     uint2 nx[UNROLL];

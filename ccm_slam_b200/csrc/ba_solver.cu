@@ -261,7 +261,7 @@ int schur_mode() {
     if (!strcmp(v, "gather") || !strcmp(v, "0")) return 0;
     if (!strcmp(v, "mma")) return 1;
     const int m = atoi(v);
-    return (m >= 0 && m <= 10) ? m : 1;
+    return (m >= 0 && m <= 13) ? m : 1;
   }();
   const int o = g_schur_override.load(std::memory_order_relaxed);
   return o >= 0 ? o : env_mode;
@@ -299,6 +299,19 @@ void launch_schur(ccm_ba_handle* h, cudaStream_t s) {
     k_schur_mma<8, 128, true><<<div_up((long long)h->nub * 32, 128), 128, 0, s>>>(h->prod.p, h->u_prod_ptr.p, h->u_row.p, h->u_col.p, h->nub, h->Z.p,
                                                                                h->o_lm.p, h->gvec.p, h->U_val(), h->bneg(), nullptr, nullptr,
                                                                                h->panel_on ? h->covered.p : nullptr, 1);
+    return;
+  }
+  if (mode >= 11 && mode <= 13) {   // vectorised entry loads (unroll 8 / 16 / 8 + predicated padding lanes)
+    const unsigned char* cov = h->panel_on ? h->covered.p : nullptr;
+    if (mode == 13)
+      k_schur_mma<8, 128, true, false, true, true><<<div_up((long long)h->nub * 32, 128), 128, 0, s>>>(h->prod.p, h->u_prod_ptr.p, h->u_row.p, h->u_col.p, h->nub,
+                                                                                             h->Z.p, h->o_lm.p, h->gvec.p, h->U_val(), h->bneg(), nullptr, nullptr, cov);
+    else if (mode == 11)
+      k_schur_mma<8, 128, true, false, true><<<div_up((long long)h->nub * 32, 128), 128, 0, s>>>(h->prod.p, h->u_prod_ptr.p, h->u_row.p, h->u_col.p, h->nub,
+                                                                                       h->Z.p, h->o_lm.p, h->gvec.p, h->U_val(), h->bneg(), nullptr, nullptr, cov);
+    else
+      k_schur_mma<16, 128, true, false, true><<<div_up((long long)h->nub * 32, 128), 128, 0, s>>>(h->prod.p, h->u_prod_ptr.p, h->u_row.p, h->u_col.p, h->nub,
+                                                                                        h->Z.p, h->o_lm.p, h->gvec.p, h->U_val(), h->bneg(), nullptr, nullptr, cov);
     return;
   }
   if (mode == 9 && h->ntiles > 0) {   // tiled schedules (the tile edge was fixed when the handle was created: CCM_SCHUR_TILE)
@@ -1334,7 +1347,7 @@ extern "C" int ccm_ba_debug_schur(ccm_ba_handle* h, int robust, double huber_del
 
 extern "C" int ccm_ba_debug_set_schur_mode(int mode) {
   return guarded([&] {
-    CCM_REQUIRE(mode >= -1 && mode <= 10, "ccm_ba_debug_set_schur_mode: -1 (CCM_SCHUR / default), 0 gather, 1 mma, 2..8 mma variants, 9 tiled, 10 row-synchronous");
+    CCM_REQUIRE(mode >= -1 && mode <= 13, "ccm_ba_debug_set_schur_mode: -1 (CCM_SCHUR / default), 0 gather, 1 mma, 2..8 mma variants, 9 tiled, 10 row-synchronous, 11 / 12 vectorised entry loads");
     g_schur_override.store(mode);
   });
 }
