@@ -400,7 +400,9 @@ __device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, doubl
 // VEC: the UNROLL list entries of a batch come in with ONE coalesced load (lane j takes entry j) and reach the other lanes by shuffle,
 // instead of UNROLL broadcast loads: the kernel sits at 65 % of the L1 wavefront rate, and the entry loads are a fifth of its wavefronts.
 // PRED (with VEC): the 14 padding lanes of a fragment do not load at all (predicated off) instead of re-reading element 0 of the row.
-template <int UNROLL, int CTA, bool PIPE = false, bool TILED = false, bool VEC = false, bool PRED = false>
+// WIDE (with VEC): a 144-byte row comes in as nine 16-byte loads (lanes 0..8) and reaches its fragment lanes by two 64-bit shuffles,
+// instead of eighteen 8-byte lanes: fewer L1 wavefronts per row, more shuffles.
+template <int UNROLL, int CTA, bool PIPE = false, bool TILED = false, bool VEC = false, bool PRED = false, bool WIDE = false>
 __global__ void __launch_bounds__(CTA) k_schur_mma(const uint2* __restrict__ prod, const unsigned* __restrict__ u_prod_ptr,
                                                    const int* __restrict__ u_row, const int* __restrict__ u_col, int nub,
                                                    const double* __restrict__ Z, const int* __restrict__ o_lm,
@@ -441,7 +443,18 @@ __global__ void __launch_bounds__(CTA) k_schur_mma(const uint2* __restrict__ pro
       double a[UNROLL], b[UNROLL];
 #pragma unroll
       for (int j = 0; j < UNROLL; j++) {
-        if (PRED) {
+        if (WIDE) {
+          double2 ra = make_double2(0.0, 0.0), rb = make_double2(0.0, 0.0);
+          if (lane < 9) {
+            ra = reinterpret_cast<const double2*>(Z + (size_t)pr[j].x * 18)[lane];
+            rb = reinterpret_cast<const double2*>(Z + (size_t)pr[j].y * 18)[lane];
+          }
+          const int src = off >> 1;
+          const double ax = __shfl_sync(0xffffffffu, ra.x, src), ay = __shfl_sync(0xffffffffu, ra.y, src);
+          const double bx = __shfl_sync(0xffffffffu, rb.x, src), by = __shfl_sync(0xffffffffu, rb.y, src);
+          a[j] = (off & 1) ? ay : ax;
+          b[j] = (off & 1) ? by : bx;
+        } else if (PRED) {
           a[j] = 0.0; b[j] = 0.0;
           if (ld) { a[j] = Z[(size_t)pr[j].x * 18 + off]; b[j] = Z[(size_t)pr[j].y * 18 + off]; }
         } else {
@@ -521,10 +534,33 @@ __global__ void __launch_bounds__(CTA) k_schur_mma(const uint2* __restrict__ pro
   } else {
     // diagonal block (Kf of them): lanes 24..26 carry g_l in column 6 of B, so C[r][6] accumulates bneg
     const bool gl = m == 6 && k < 3;
+    if (VEC) {   // batches of UNROLL products: entries by one coalesced load, then all rows, landmark ids and g_l of the batch in flight together
+      for (; p + UNROLL <= end; p += UNROLL) {
+        unsigned ex = 0u;
+        if (lane < UNROLL) ex = prod[p + lane].x;
+        unsigned e[UNROLL];
+#pragma unroll
+        for (int j = 0; j < UNROLL; j++) e[j] = __shfl_sync(0xffffffffu, ex, j);
+        double a[UNROLL], g[UNROLL];
+        int lm[UNROLL];
+#pragma unroll
+        for (int j = 0; j < UNROLL; j++) {
+          a[j] = Z[(size_t)e[j] * 18 + off];
+          lm[j] = gl ? o_lm[e[j]] : 0;
+        }
+#pragma unroll
+        for (int j = 0; j < UNROLL; j++) g[j] = gl ? gvec[3 * (size_t)lm[j] + k] : 0.0;
+#pragma unroll
+        for (int j = 0; j < UNROLL; j += 2) {
+          dmma_884(c00, c01, ld ? a[j] : 0.0, gl ? g[j] : (ld ? a[j] : 0.0));
+          dmma_884(c10, c11, ld ? a[j + 1] : 0.0, gl ? g[j + 1] : (ld ? a[j + 1] : 0.0));
+        }
+      }
+    }
     for (; p < end; p++) {
       const uint2 pr = prod[p];
       const double a = Z[(size_t)pr.x * 18 + off];
-      double b = Z[(size_t)pr.y * 18 + off];
+      double b = a;   // a diagonal list holds (e, e) pairs only: one row serves both operands
       if (!ld) b = 0.0;
       if (gl) b = gvec[3 * (size_t)o_lm[pr.x] + k];
       if ((p - beg) & 1u) dmma_884(c10, c11, ld ? a : 0.0, b);

@@ -257,11 +257,11 @@ std::atomic<int> g_schur_override{-1};  // ccm_ba_debug_set_schur_mode
 int schur_mode() {
   static const int env_mode = [] {
     const char* v = getenv("CCM_SCHUR");
-    if (!v) return 8;
+    if (!v) return 11;
     if (!strcmp(v, "gather") || !strcmp(v, "0")) return 0;
     if (!strcmp(v, "mma")) return 1;
     const int m = atoi(v);
-    return (m >= 0 && m <= 13) ? m : 1;
+    return (m >= 0 && m <= 14) ? m : 1;
   }();
   const int o = g_schur_override.load(std::memory_order_relaxed);
   return o >= 0 ? o : env_mode;
@@ -301,9 +301,18 @@ void launch_schur(ccm_ba_handle* h, cudaStream_t s) {
                                                                                h->panel_on ? h->covered.p : nullptr, 1);
     return;
   }
-  if (mode >= 11 && mode <= 13) {   // vectorised entry loads (unroll 8 / 16 / 8 + predicated padding lanes)
+  // Modes 11-14: the ncu capture of the list kernel (profiles/prof_r2_k_schur_mma.ncu-rep) shows the L1 data pipe at 72 % of its wavefront
+  // rate -- the binding unit -- with 672 M load requests for 210 M products: two row loads and ONE BROADCAST ENTRY LOAD per product.
+  // 11 (default): the 8 entries of a batch in one coalesced load + shuffles: 8.43 -> 7.45 ms.  12: the same at unroll 16: 8.72 ms.
+  // 13: padding lanes predicated off instead of re-reading element 0: 9.05 ms.  14: rows as nine 16-byte loads + 64-bit shuffles to the
+  // fragment lanes: 17.3 ms (shuffles in bulk cost more than the wavefronts they save).  profiles/r2/vec_cfg5.log, vec2_cfg5.log
+  if (mode >= 11 && mode <= 14) {
     const unsigned char* cov = h->panel_on ? h->covered.p : nullptr;
-    if (mode == 13)
+    if (mode == 14)
+      k_schur_mma<8, 128, true, false, true, false, true><<<div_up((long long)h->nub * 32, 128), 128, 0, s>>>(h->prod.p, h->u_prod_ptr.p, h->u_row.p, h->u_col.p,
+                                                                                                    h->nub, h->Z.p, h->o_lm.p, h->gvec.p, h->U_val(), h->bneg(),
+                                                                                                    nullptr, nullptr, cov);
+    else if (mode == 13)
       k_schur_mma<8, 128, true, false, true, true><<<div_up((long long)h->nub * 32, 128), 128, 0, s>>>(h->prod.p, h->u_prod_ptr.p, h->u_row.p, h->u_col.p, h->nub,
                                                                                              h->Z.p, h->o_lm.p, h->gvec.p, h->U_val(), h->bneg(), nullptr, nullptr, cov);
     else if (mode == 11)
@@ -335,7 +344,7 @@ void launch_schur(ccm_ba_handle* h, cudaStream_t s) {
     case 7: launch_schur_mma<16, 128>(h, s); break;   // 8.78 ms
     case 8: launch_schur_mma<8, 128, true>(h, s); break;   // 8.43 ms: product entries prefetched one batch ahead (the default)
     case 1: launch_schur_mma<8, 128>(h, s); break;
-    default: launch_schur_mma<8, 128, true>(h, s); break;   // 8.43 ms vs 8.73 ms without the prefetch (profiles/r2/prolong_cfg5.log)
+    default: launch_schur_mma<8, 128, true>(h, s); break;   // 8.43 ms vs 8.73 ms without the prefetch (profiles/r2/prolong_cfg5.log); mode 11 (the default, above): 7.45 ms
   }
 }
 
@@ -1347,7 +1356,7 @@ extern "C" int ccm_ba_debug_schur(ccm_ba_handle* h, int robust, double huber_del
 
 extern "C" int ccm_ba_debug_set_schur_mode(int mode) {
   return guarded([&] {
-    CCM_REQUIRE(mode >= -1 && mode <= 13, "ccm_ba_debug_set_schur_mode: -1 (CCM_SCHUR / default), 0 gather, 1 mma, 2..8 mma variants, 9 tiled, 10 row-synchronous, 11 / 12 vectorised entry loads");
+    CCM_REQUIRE(mode >= -1 && mode <= 14, "ccm_ba_debug_set_schur_mode: -1 (CCM_SCHUR / default), 0 gather, 1 mma, 2..8 mma variants, 9 tiled, 10 row-synchronous, 11 / 12 vectorised entry loads");
     g_schur_override.store(mode);
   });
 }

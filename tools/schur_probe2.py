@@ -16,7 +16,8 @@ ref = None
 ALL = [("untiled prefetch, unsorted lists", {"CCM_SCHUR_SORT": "0"}, 8), ("untiled prefetch, sorted lists", {"CCM_SCHUR_SORT": "1"}, 8),
        ("tiled 2x2", {"CCM_SCHUR_TILE": "2"}, 9), ("tiled 3x3", {"CCM_SCHUR_TILE": "3"}, 9), ("tiled 4x4", {"CCM_SCHUR_TILE": "4"}, 9),
        ("tiled 4x4, unsorted lists", {"CCM_SCHUR_TILE": "4", "CCM_SCHUR_SORT": "0"}, 9), ("row-synchronous", {}, 10),
-       ("vectorised entries u8", {}, 11), ("vectorised entries u16", {}, 12), ("vectorised entries u8 + predicated padding lanes", {}, 13)]
+       ("vectorised entries u8", {}, 11), ("vectorised entries u16", {}, 12), ("vectorised entries u8 + predicated padding lanes", {}, 13),
+       ("vectorised entries u8 + wide row loads", {}, 14)]
 want = sys.argv[2:]   # optional: substrings of the variant labels to run
 for label, env, mode in [v for v in ALL if not want or any(w in v[0] for w in want)]:
     for k, v in env.items():
