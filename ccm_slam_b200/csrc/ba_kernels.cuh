@@ -283,11 +283,20 @@ __global__ void __launch_bounds__(1024) k_sum_partials(const double* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// K3/K4 first half: Z = W U^-1 (AoS, staged through shared memory for coalesced 144 B rows), g = U^-T bl.
-// reads 144 B/obs (W) + cached Hll ; writes 144 B/obs (Z)
+// Layout of a row of Z (18 doubles = Z_o, 6 x 3 row-major) in memory.  The Schur kernel reads a row as one MMA operand fragment:
+// lanes 0..15 take elements 0..11, lanes 16..23 elements 12..17, and the L1 data pipe -- the unit that bounds that kernel -- works
+// per half-warp and per 128-byte line.  stride: doubles from one row to the next; gap: doubles skipped between element 11 and
+// element 12 (so that the second half-warp's six elements can sit in a line of their own); pad1: the element position the idle
+// lanes of the second half-warp read (the idle lanes of the first read position 0).  {18, 0, 0} is the dense layout.
+struct ZLayout { int stride, gap, pad1; };
+__host__ __device__ __forceinline__ int zpos(const ZLayout& z, int c) { return c + (c >= 12 ? z.gap : 0); }
+
+// K3/K4 first half: Z = W U^-1 (AoS, staged through shared memory for coalesced rows), g = U^-T bl.
+// reads 144 B/obs (W) + cached Hll ; writes 144 B/obs (Z) (whole 32-byte sectors of a padded row: 160 B)
 __global__ void __launch_bounds__(TPB) k_scale(const int* __restrict__ o_lm, const double* __restrict__ W, size_t Ep,
                                                const double* __restrict__ Hll, const double* __restrict__ bl, int Pl,
-                                               int E, double lambda, double* __restrict__ Z, double* __restrict__ gvec) {
+                                               int E, double lambda, double* __restrict__ Z, double* __restrict__ gvec,
+                                               ZLayout zl = ZLayout{18, 0, 0}) {
   __shared__ double tile[TPB * 19];
   const long long e0 = (long long)blockIdx.x * TPB;
   const long long e = e0 + threadIdx.x;
@@ -316,9 +325,22 @@ __global__ void __launch_bounds__(TPB) k_scale(const int* __restrict__ o_lm, con
     }
   }
   __syncthreads();
-  const long long nvalid = (E - e0 < TPB ? E - e0 : TPB) * 18;
-  double* out = Z + e0 * 18;
-  for (int i = threadIdx.x; i < nvalid; i += TPB) out[i] = tile[(i / 18) * 19 + (i % 18)];
+  const int zs = zl.stride;
+  const long long nvalid = (E - e0 < TPB ? E - e0 : TPB) * zs;
+  double* out = Z + e0 * zs;
+  if (zs == 18) {
+    for (int i = threadIdx.x; i < nvalid; i += TPB) out[i] = tile[(i / 18) * 19 + (i % 18)];
+  } else {
+    // padded rows: positions [0, 12) and [12 + gap, 18 + gap) carry data; the other positions of a 32-byte sector that holds data
+    // are written as zeros (whole sectors leave the SM), sectors without data are not written at all
+    const int g = zl.gap, hi = (18 + g + 3) & ~3;
+    for (int i = threadIdx.x; i < nvalid; i += TPB) {
+      const int rw = i / zs, q = i - rw * zs;
+      if (q < 12) out[i] = tile[rw * 19 + q];
+      else if (q >= 12 + g && q < 18 + g) out[i] = tile[rw * 19 + q - g];
+      else if ((g == 0 || q >= ((12 + g) & ~3)) && q < hi) out[i] = 0.0;
+    }
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -402,14 +424,19 @@ __device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, doubl
 // PRED (with VEC): the 14 padding lanes of a fragment do not load at all (predicated off) instead of re-reading element 0 of the row.
 // WIDE (with VEC): a 144-byte row comes in as nine 16-byte loads (lanes 0..8) and reaches its fragment lanes by two 64-bit shuffles,
 // instead of eighteen 8-byte lanes: fewer L1 wavefronts per row, more shuffles.
-template <int UNROLL, int CTA, bool PIPE = false, bool TILED = false, bool VEC = false, bool PRED = false, bool WIDE = false>
+// SMB (with VEC): the entries of a batch go from the loading lanes through a per-warp shared-memory slot (double-buffered: one
+// __syncwarp per batch) and come back as broadcast 16-byte loads, two entries each: UNROLL / 2 + 1 shared-memory wavefronts per batch
+// instead of 2 UNROLL shuffles (a shuffle is a wavefront of the same L1 data pipe).
+template <int UNROLL, int CTA, bool PIPE = false, bool TILED = false, bool VEC = false, bool PRED = false, bool WIDE = false,
+          bool SMB = false>
 __global__ void __launch_bounds__(CTA) k_schur_mma(const uint2* __restrict__ prod, const unsigned* __restrict__ u_prod_ptr,
                                                    const int* __restrict__ u_row, const int* __restrict__ u_col, int nub,
                                                    const double* __restrict__ Z, const int* __restrict__ o_lm,
                                                    const double* __restrict__ gvec, double* __restrict__ U_val,
                                                    double* __restrict__ bneg, const int* __restrict__ tile_ptr = nullptr,
                                                    const int* __restrict__ tile_u = nullptr,
-                                                   const unsigned char* __restrict__ covered = nullptr, int only_diag = 0) {
+                                                   const unsigned char* __restrict__ covered = nullptr, int only_diag = 0,
+                                                   ZLayout zl = ZLayout{18, 0, 0}) {
   static_assert(UNROLL % 2 == 0, "products alternate between two accumulator sets");
   int warp;
   if (TILED) {
@@ -425,20 +452,37 @@ __global__ void __launch_bounds__(CTA) k_schur_mma(const uint2* __restrict__ pro
   const int lane = threadIdx.x & 31;
   const int m = lane >> 2, k = lane & 3;
   const bool ld = m < 6 && k < 3;
-  const int off = ld ? m * 3 + k : 0;  // padding lanes read element 0 of the same row (no extra line) and discard it
+  const int zs = zl.stride;
+  // padding lanes read an element their half-warp reads anyway (no extra line) and discard it
+  const int off = ld ? zpos(zl, m * 3 + k) : (lane < 16 ? 0 : zl.pad1);
   const unsigned beg = u_prod_ptr[warp], end = u_prod_ptr[warp + 1];
   const int row = u_row[warp];
   const bool diag = row == u_col[warp];
   if (only_diag && !diag) return;  // the off-diagonal blocks belong to k_schur_rowsync
   double c00 = 0.0, c01 = 0.0, c10 = 0.0, c11 = 0.0;
   unsigned p = beg;
+  __shared__ uint4 s_ent[SMB ? (CTA / 32) * 2 * (UNROLL / 2) : 1];   // [warp][buffer][UNROLL entries of 8 bytes]
+  uint4* const my_ent = s_ent + (SMB ? (threadIdx.x >> 5) * 2 * (UNROLL / 2) : 0);
+  unsigned batch = 0;
   if (!diag && PIPE && VEC) {
     uint2 nxv = make_uint2(0u, 0u);
     if (p + UNROLL <= end && lane < UNROLL) nxv = prod[p + lane];
     for (; p + UNROLL <= end; p += UNROLL) {
       uint2 pr[UNROLL];
+      if (SMB) {
+        uint4* slot = my_ent + (batch & 1u) * (UNROLL / 2);
+        batch++;
+        if (lane < UNROLL) reinterpret_cast<uint2*>(slot)[lane] = nxv;
+        __syncwarp();
 #pragma unroll
-      for (int j = 0; j < UNROLL; j++) { pr[j].x = __shfl_sync(0xffffffffu, nxv.x, j); pr[j].y = __shfl_sync(0xffffffffu, nxv.y, j); }
+        for (int j = 0; j < UNROLL; j += 2) {
+          const uint4 t = slot[j >> 1];
+          pr[j] = make_uint2(t.x, t.y); pr[j + 1] = make_uint2(t.z, t.w);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < UNROLL; j++) { pr[j].x = __shfl_sync(0xffffffffu, nxv.x, j); pr[j].y = __shfl_sync(0xffffffffu, nxv.y, j); }
+      }
       if (p + 2 * UNROLL <= end && lane < UNROLL) nxv = prod[p + UNROLL + lane];
       double a[UNROLL], b[UNROLL];
 #pragma unroll
@@ -446,20 +490,21 @@ __global__ void __launch_bounds__(CTA) k_schur_mma(const uint2* __restrict__ pro
         if (WIDE) {
           double2 ra = make_double2(0.0, 0.0), rb = make_double2(0.0, 0.0);
           if (lane < 9) {
-            ra = reinterpret_cast<const double2*>(Z + (size_t)pr[j].x * 18)[lane];
-            rb = reinterpret_cast<const double2*>(Z + (size_t)pr[j].y * 18)[lane];
+            const int q2 = lane + (lane >= 6 ? zl.gap / 2 : 0);   // gap is even: 16-byte pieces stay whole
+            ra = reinterpret_cast<const double2*>(Z + (size_t)pr[j].x * zs)[q2];
+            rb = reinterpret_cast<const double2*>(Z + (size_t)pr[j].y * zs)[q2];
           }
-          const int src = off >> 1;
+          const int cl = ld ? m * 3 + k : 0, src = cl >> 1;
           const double ax = __shfl_sync(0xffffffffu, ra.x, src), ay = __shfl_sync(0xffffffffu, ra.y, src);
           const double bx = __shfl_sync(0xffffffffu, rb.x, src), by = __shfl_sync(0xffffffffu, rb.y, src);
-          a[j] = (off & 1) ? ay : ax;
-          b[j] = (off & 1) ? by : bx;
+          a[j] = (cl & 1) ? ay : ax;
+          b[j] = (cl & 1) ? by : bx;
         } else if (PRED) {
           a[j] = 0.0; b[j] = 0.0;
-          if (ld) { a[j] = Z[(size_t)pr[j].x * 18 + off]; b[j] = Z[(size_t)pr[j].y * 18 + off]; }
+          if (ld) { a[j] = Z[(size_t)pr[j].x * zs + off]; b[j] = Z[(size_t)pr[j].y * zs + off]; }
         } else {
-          a[j] = Z[(size_t)pr[j].x * 18 + off];
-          b[j] = Z[(size_t)pr[j].y * 18 + off];
+          a[j] = Z[(size_t)pr[j].x * zs + off];
+          b[j] = Z[(size_t)pr[j].y * zs + off];
         }
       }
 #pragma unroll
@@ -470,7 +515,7 @@ __global__ void __launch_bounds__(CTA) k_schur_mma(const uint2* __restrict__ pro
     }
     for (; p < end; p++) {
       const uint2 pr = prod[p];
-      const double a = Z[(size_t)pr.x * 18 + off], b = Z[(size_t)pr.y * 18 + off];
+      const double a = Z[(size_t)pr.x * zs + off], b = Z[(size_t)pr.y * zs + off];
       if ((p - beg) & 1u) dmma_884(c10, c11, ld ? a : 0.0, ld ? b : 0.0);
       else dmma_884(c00, c01, ld ? a : 0.0, ld ? b : 0.0);
     }
@@ -493,8 +538,8 @@ __global__ void __launch_bounds__(CTA) k_schur_mma(const uint2* __restrict__ pro
       double a[UNROLL], b[UNROLL];
 #pragma unroll
       for (int j = 0; j < UNROLL; j++) {
-        a[j] = Z[(size_t)pr[j].x * 18 + off];
-        b[j] = Z[(size_t)pr[j].y * 18 + off];
+        a[j] = Z[(size_t)pr[j].x * zs + off];
+        b[j] = Z[(size_t)pr[j].y * zs + off];
       }
 #pragma unroll
       for (int j = 0; j < UNROLL; j += 2) {
@@ -504,7 +549,7 @@ __global__ void __launch_bounds__(CTA) k_schur_mma(const uint2* __restrict__ pro
     }
     for (; p < end; p++) {
       const uint2 pr = prod[p];
-      const double a = Z[(size_t)pr.x * 18 + off], b = Z[(size_t)pr.y * 18 + off];
+      const double a = Z[(size_t)pr.x * zs + off], b = Z[(size_t)pr.y * zs + off];
       if ((p - beg) & 1u) dmma_884(c10, c11, ld ? a : 0.0, ld ? b : 0.0);
       else dmma_884(c00, c01, ld ? a : 0.0, ld ? b : 0.0);
     }
@@ -516,8 +561,8 @@ __global__ void __launch_bounds__(CTA) k_schur_mma(const uint2* __restrict__ pro
       double a[UNROLL], b[UNROLL];
 #pragma unroll
       for (int j = 0; j < UNROLL; j++) {
-        a[j] = Z[(size_t)pr[j].x * 18 + off];
-        b[j] = Z[(size_t)pr[j].y * 18 + off];
+        a[j] = Z[(size_t)pr[j].x * zs + off];
+        b[j] = Z[(size_t)pr[j].y * zs + off];
       }
 #pragma unroll
       for (int j = 0; j < UNROLL; j += 2) {
@@ -527,7 +572,7 @@ __global__ void __launch_bounds__(CTA) k_schur_mma(const uint2* __restrict__ pro
     }
     for (; p < end; p++) {
       const uint2 pr = prod[p];
-      const double a = Z[(size_t)pr.x * 18 + off], b = Z[(size_t)pr.y * 18 + off];
+      const double a = Z[(size_t)pr.x * zs + off], b = Z[(size_t)pr.y * zs + off];
       if ((p - beg) & 1u) dmma_884(c10, c11, ld ? a : 0.0, ld ? b : 0.0);  // warp-uniform branch
       else dmma_884(c00, c01, ld ? a : 0.0, ld ? b : 0.0);
     }
@@ -539,13 +584,25 @@ __global__ void __launch_bounds__(CTA) k_schur_mma(const uint2* __restrict__ pro
         unsigned ex = 0u;
         if (lane < UNROLL) ex = prod[p + lane].x;
         unsigned e[UNROLL];
+        if (SMB && UNROLL % 4 == 0) {
+          uint4* slot = my_ent + (batch & 1u) * (UNROLL / 2);
+          batch++;
+          if (lane < UNROLL) reinterpret_cast<unsigned*>(slot)[lane] = ex;
+          __syncwarp();
 #pragma unroll
-        for (int j = 0; j < UNROLL; j++) e[j] = __shfl_sync(0xffffffffu, ex, j);
+          for (int j = 0; j < UNROLL; j += 4) {
+            const uint4 t = slot[j >> 2];
+            e[j] = t.x; e[j + 1] = t.y; e[j + 2] = t.z; e[j + 3] = t.w;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < UNROLL; j++) e[j] = __shfl_sync(0xffffffffu, ex, j);
+        }
         double a[UNROLL], g[UNROLL];
         int lm[UNROLL];
 #pragma unroll
         for (int j = 0; j < UNROLL; j++) {
-          a[j] = Z[(size_t)e[j] * 18 + off];
+          a[j] = Z[(size_t)e[j] * zs + off];
           lm[j] = gl ? o_lm[e[j]] : 0;
         }
 #pragma unroll
@@ -559,7 +616,7 @@ __global__ void __launch_bounds__(CTA) k_schur_mma(const uint2* __restrict__ pro
     }
     for (; p < end; p++) {
       const uint2 pr = prod[p];
-      const double a = Z[(size_t)pr.x * 18 + off];
+      const double a = Z[(size_t)pr.x * zs + off];
       double b = a;   // a diagonal list holds (e, e) pairs only: one row serves both operands
       if (!ld) b = 0.0;
       if (gl) b = gvec[3 * (size_t)o_lm[pr.x] + k];
@@ -761,9 +818,11 @@ __global__ void __launch_bounds__(TPB) k_backsub_points(const int* __restrict__ 
                                                         const double* __restrict__ Hll, const double* __restrict__ bl,
                                                         const double* __restrict__ x, const double* __restrict__ pt,
                                                         int Pl, double lambda, double* __restrict__ pt_trial,
-                                                        double* __restrict__ dx_out, double* __restrict__ scale_partials) {
+                                                        double* __restrict__ dx_out, double* __restrict__ scale_partials,
+                                                        ZLayout zl = ZLayout{18, 0, 0}) {
   __shared__ double red[TPB / 32];
   double acc = 0.0;
+  const int zs = zl.stride, zg2 = zl.gap / 2;
   for (int l = blockIdx.x * TPB + threadIdx.x; l < Pl; l += gridDim.x * TPB) {
     double d[6], u[6], b3[3], g[3], t[3] = {0, 0, 0}, xl[3];
 #pragma unroll
@@ -776,10 +835,10 @@ __global__ void __launch_bounds__(TPB) k_backsub_points(const int* __restrict__ 
     for (int o = beg; o < end; o++) {
       const int s = __ldg(pose_slot + o_kf[o]);
       if (s < 0) continue;
-      const double2* z2 = reinterpret_cast<const double2*>(Z + (size_t)o * 18);
+      const double2* z2 = reinterpret_cast<const double2*>(Z + (size_t)o * zs);
       double z[18];
 #pragma unroll
-      for (int i = 0; i < 9; i++) { const double2 v = z2[i]; z[2 * i] = v.x; z[2 * i + 1] = v.y; }
+      for (int i = 0; i < 9; i++) { const double2 v = z2[i < 6 ? i : i + zg2]; z[2 * i] = v.x; z[2 * i + 1] = v.y; }
 #pragma unroll
       for (int r = 0; r < 6; r++) {
         const double xr = __ldg(x + (size_t)s * 6 + r);

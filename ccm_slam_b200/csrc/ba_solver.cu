@@ -77,6 +77,7 @@ struct ccm_ba_handle {
   DevBuf<uint2> prod;
   // landmark-synchronous Schur panels (schur_panel.cuh)
   bool panel_on = false;
+  ZLayout zl{18, 0, 0};            // layout of the rows of Z (CCM_Z_LAYOUT = "stride,gap,pad1"; see ba_kernels.cuh)
   int npan = 0;
   DevBuf<int> o_slot, pose_lmin, pose_lmax, pose_cnt;
   DevBuf<unsigned char> pan_on, covered;
@@ -247,7 +248,7 @@ void step_scale(ccm_ba_handle* h, double lambda) {
   if (h->El == 0) return;
   KernelSpan sp(h, CCM_BA_K_SCALE);
   k_scale<<<div_up(h->El, TPB), TPB, 0, h->stream>>>(h->o_lm.p, h->W.p, h->Ep, h->Hll(), h->bl(), h->Pl, h->El, lambda,
-                                                     h->Z.p, h->gvec.p);
+                                                     h->Z.p, h->gvec.p, h->zl);
   CCM_LAUNCHED();
 }
 
@@ -261,7 +262,7 @@ int schur_mode() {
     if (!strcmp(v, "gather") || !strcmp(v, "0")) return 0;
     if (!strcmp(v, "mma")) return 1;
     const int m = atoi(v);
-    return (m >= 0 && m <= 14) ? m : 1;
+    return (m >= 0 && m <= 15) ? m : 1;
   }();
   const int o = g_schur_override.load(std::memory_order_relaxed);
   return o >= 0 ? o : env_mode;
@@ -270,14 +271,14 @@ int schur_mode() {
 template <int UNROLL, int CTA>
 void launch_schur_tiled(ccm_ba_handle* h, cudaStream_t s) {
   k_schur_mma<UNROLL, CTA, true, true><<<h->ntiles, CTA, 0, s>>>(h->prod.p, h->u_prod_ptr.p, h->u_row.p, h->u_col.p, h->nub, h->Z.p, h->o_lm.p,
-                                                                  h->gvec.p, h->U_val(), h->bneg(), h->tile_ptr.p, h->tile_u.p);
+                                                                  h->gvec.p, h->U_val(), h->bneg(), h->tile_ptr.p, h->tile_u.p, nullptr, 0, h->zl);
 }
 
 template <int UNROLL, int CTA, bool PIPE = false>
 void launch_schur_mma(ccm_ba_handle* h, cudaStream_t s) {
   k_schur_mma<UNROLL, CTA, PIPE><<<div_up((long long)h->nub * 32, CTA), CTA, 0, s>>>(h->prod.p, h->u_prod_ptr.p, h->u_row.p, h->u_col.p, h->nub,
                                                                               h->Z.p, h->o_lm.p, h->gvec.p, h->U_val(), h->bneg(), nullptr,
-                                                                              nullptr, h->panel_on ? h->covered.p : nullptr);
+                                                                              nullptr, h->panel_on ? h->covered.p : nullptr, 0, h->zl);
 }
 
 void launch_schur_panel(ccm_ba_handle* h, cudaStream_t s) {
@@ -294,33 +295,40 @@ void launch_schur(ccm_ba_handle* h, cudaStream_t s) {
     CCM_LAUNCHED();
   }
   const int mode = schur_mode();
+  const bool dense_rows = h->zl.stride == 18 && h->zl.gap == 0;
+  CCM_REQUIRE(dense_rows || (!h->panel_on && mode != 0 && !(mode == 10 && h->rs_ctas > 0)),
+              "a padded layout of Z (CCM_Z_LAYOUT) is read by the list kernel k_schur_mma only: not with CCM_SCHUR=0 / 10 or CCM_SCHUR_PANEL");
   if (mode == 10 && h->rs_ctas > 0) {   // off-diagonal blocks row-synchronously, diagonal blocks by the list kernel
     k_schur_rowsync<8><<<h->rs_ctas, 32 * RS_W, 0, s>>>(h->prod.p, h->u_prod_ptr.p, h->rs_first.p, h->rs_count.p, h->Z.p, h->U_val());
     k_schur_mma<8, 128, true><<<div_up((long long)h->nub * 32, 128), 128, 0, s>>>(h->prod.p, h->u_prod_ptr.p, h->u_row.p, h->u_col.p, h->nub, h->Z.p,
                                                                                h->o_lm.p, h->gvec.p, h->U_val(), h->bneg(), nullptr, nullptr,
-                                                                               h->panel_on ? h->covered.p : nullptr, 1);
+                                                                               h->panel_on ? h->covered.p : nullptr, 1, h->zl);
     return;
   }
   // Modes 11-14: the ncu capture of the list kernel (profiles/prof_r2_k_schur_mma.ncu-rep) shows the L1 data pipe at 72 % of its wavefront
   // rate -- the binding unit -- with 672 M load requests for 210 M products: two row loads and ONE BROADCAST ENTRY LOAD per product.
-  // 11 (default): the 8 entries of a batch in one coalesced load + shuffles: 8.43 -> 7.45 ms.  12: the same at unroll 16: 8.72 ms.
-  // 13: padding lanes predicated off instead of re-reading element 0: 9.05 ms.  14: rows as nine 16-byte loads + 64-bit shuffles to the
-  // fragment lanes: 17.3 ms (shuffles in bulk cost more than the wavefronts they save).  profiles/r2/vec_cfg5.log, vec2_cfg5.log
-  if (mode >= 11 && mode <= 14) {
+  // 11 (default): the 8 entries of a batch in one coalesced load + shuffles, diagonal blocks batched the same way: 8.43 -> 7.28 ms.
+  // 12: the same at unroll 16: 8.72 ms.  13: padding lanes predicated off instead of re-reading an element: 7.34 ms.  14: rows as nine
+  // 16-byte loads + 64-bit shuffles to the fragment lanes: 15.3 ms (shuffles in bulk cost more than the wavefronts they save).
+  // profiles/r2/vec_cfg5.log, vec2_cfg5.log, b23_schur.log
+  if (mode >= 11 && mode <= 15) {
     const unsigned char* cov = h->panel_on ? h->covered.p : nullptr;
-    if (mode == 14)
+    if (mode == 15)   // entries broadcast through shared memory instead of shuffles
+      k_schur_mma<8, 128, true, false, true, false, false, true><<<div_up((long long)h->nub * 32, 128), 128, 0, s>>>(
+          h->prod.p, h->u_prod_ptr.p, h->u_row.p, h->u_col.p, h->nub, h->Z.p, h->o_lm.p, h->gvec.p, h->U_val(), h->bneg(), nullptr, nullptr, cov, 0, h->zl);
+    else if (mode == 14)
       k_schur_mma<8, 128, true, false, true, false, true><<<div_up((long long)h->nub * 32, 128), 128, 0, s>>>(h->prod.p, h->u_prod_ptr.p, h->u_row.p, h->u_col.p,
                                                                                                     h->nub, h->Z.p, h->o_lm.p, h->gvec.p, h->U_val(), h->bneg(),
-                                                                                                    nullptr, nullptr, cov);
+                                                                                                    nullptr, nullptr, cov, 0, h->zl);
     else if (mode == 13)
       k_schur_mma<8, 128, true, false, true, true><<<div_up((long long)h->nub * 32, 128), 128, 0, s>>>(h->prod.p, h->u_prod_ptr.p, h->u_row.p, h->u_col.p, h->nub,
-                                                                                             h->Z.p, h->o_lm.p, h->gvec.p, h->U_val(), h->bneg(), nullptr, nullptr, cov);
+                                                                                             h->Z.p, h->o_lm.p, h->gvec.p, h->U_val(), h->bneg(), nullptr, nullptr, cov, 0, h->zl);
     else if (mode == 11)
       k_schur_mma<8, 128, true, false, true><<<div_up((long long)h->nub * 32, 128), 128, 0, s>>>(h->prod.p, h->u_prod_ptr.p, h->u_row.p, h->u_col.p, h->nub,
-                                                                                       h->Z.p, h->o_lm.p, h->gvec.p, h->U_val(), h->bneg(), nullptr, nullptr, cov);
+                                                                                       h->Z.p, h->o_lm.p, h->gvec.p, h->U_val(), h->bneg(), nullptr, nullptr, cov, 0, h->zl);
     else
       k_schur_mma<16, 128, true, false, true><<<div_up((long long)h->nub * 32, 128), 128, 0, s>>>(h->prod.p, h->u_prod_ptr.p, h->u_row.p, h->u_col.p, h->nub,
-                                                                                        h->Z.p, h->o_lm.p, h->gvec.p, h->U_val(), h->bneg(), nullptr, nullptr, cov);
+                                                                                        h->Z.p, h->o_lm.p, h->gvec.p, h->U_val(), h->bneg(), nullptr, nullptr, cov, 0, h->zl);
     return;
   }
   if (mode == 9 && h->ntiles > 0) {   // tiled schedules (the tile edge was fixed when the handle was created: CCM_SCHUR_TILE)
@@ -545,7 +553,7 @@ void step_update_and_residual(ccm_ba_handle* h, double lambda, int robust, doubl
   sum_partials_to(h, g1, h->scal.p + 2);
   const int g2 = grid_stride(h->Pl);
   k_backsub_points<<<g2, TPB, 0, s>>>(h->lm_ptr.p, h->o_kf.p, h->pose_slot.p, h->Z.p, h->Hll(), h->bl(), h->x.p, h->pt_cur,
-                                      h->Pl, lambda, h->pt_trial, dx_points, h->partials.p);
+                                      h->Pl, lambda, h->pt_trial, dx_points, h->partials.p, h->zl);
   CCM_LAUNCHED();
   sum_partials_to(h, g2, h->scal.p + 1);
   if (h->profile) { size_t ev1 = ev_record(h); h->spans.push_back({CCM_BA_K_BACKSUB, ev0, ev1}); ev0 = ev1; }
@@ -921,7 +929,14 @@ void build(ccm_ba_handle* h, const ccm_ba_problem* p) {
 
   lap("pose observation stream");
   // ---- linear-system storage
-  h->W.alloc(std::max(h->Ep * 18, (size_t)1)); h->Z.alloc(std::max((size_t)El * 18, (size_t)2));
+  if (const char* v = getenv("CCM_Z_LAYOUT")) {   // "stride,gap,pad1" in doubles (see ZLayout in ba_kernels.cuh)
+    int st = 18, gp = 0, pd = 0;
+    const int got = sscanf(v, "%d,%d,%d", &st, &gp, &pd);
+    CCM_REQUIRE(got >= 1 && st % 2 == 0 && gp % 2 == 0 && gp >= 0 && st >= 18 + gp && st <= 64 && pd >= 0 && pd < 18 + gp,
+                "CCM_Z_LAYOUT: stride,gap,pad1 with even stride >= 18 + gap, even gap >= 0, 0 <= pad1 < 18 + gap");
+    h->zl = ZLayout{st, gp, pd};
+  }
+  h->W.alloc(std::max(h->Ep * 18, (size_t)1)); h->Z.alloc(std::max((size_t)El * h->zl.stride, (size_t)2));
   h->HllBl.alloc(std::max((size_t)Pl * 9, (size_t)1)); h->gvec.alloc(std::max((size_t)Pl * 3, (size_t)1));
   h->Hbuf.alloc_zero((size_t)Kf * 42 + 2, s);
   h->Ubuf.alloc_zero((size_t)nub * 36 + (size_t)Kf * 6 + 1, s);
@@ -1356,7 +1371,7 @@ extern "C" int ccm_ba_debug_schur(ccm_ba_handle* h, int robust, double huber_del
 
 extern "C" int ccm_ba_debug_set_schur_mode(int mode) {
   return guarded([&] {
-    CCM_REQUIRE(mode >= -1 && mode <= 14, "ccm_ba_debug_set_schur_mode: -1 (CCM_SCHUR / default), 0 gather, 1 mma, 2..8 mma variants, 9 tiled, 10 row-synchronous, 11 / 12 vectorised entry loads");
+    CCM_REQUIRE(mode >= -1 && mode <= 15, "ccm_ba_debug_set_schur_mode: -1 (CCM_SCHUR / default), 0 gather, 1 mma, 2..8 mma variants, 9 tiled, 10 row-synchronous, 11..15 vectorised entry loads");
     g_schur_override.store(mode);
   });
 }
@@ -1391,14 +1406,14 @@ extern "C" int ccm_ba_time_kernel(ccm_ba_handle* h, int which, int reps, double 
                                                         h->pt_cur, h->El, 1, huber_delta, h->partials.p);
           break;
         case 3:
-          k_scale<<<div_up(h->El, TPB), TPB, 0, s>>>(h->o_lm.p, h->W.p, h->Ep, h->Hll(), h->bl(), h->Pl, h->El, lambda, h->Z.p, h->gvec.p);
+          k_scale<<<div_up(h->El, TPB), TPB, 0, s>>>(h->o_lm.p, h->W.p, h->Ep, h->Hll(), h->bl(), h->Pl, h->El, lambda, h->Z.p, h->gvec.p, h->zl);
           break;
         case 4:
           launch_schur(h, s);
           break;
         case 5:
           k_backsub_points<<<grid_stride(h->Pl), TPB, 0, s>>>(h->lm_ptr.p, h->o_kf.p, h->pose_slot.p, h->Z.p, h->Hll(), h->bl(),
-                                                              h->x.p, h->pt_cur, h->Pl, lambda, h->pt_trial, nullptr, h->partials.p);
+                                                              h->x.p, h->pt_cur, h->Pl, lambda, h->pt_trial, nullptr, h->partials.p, h->zl);
           break;
         case 6: {
           step_pcg(h, 1e-10, 2000);

@@ -17,7 +17,12 @@ ALL = [("untiled prefetch, unsorted lists", {"CCM_SCHUR_SORT": "0"}, 8), ("until
        ("tiled 2x2", {"CCM_SCHUR_TILE": "2"}, 9), ("tiled 3x3", {"CCM_SCHUR_TILE": "3"}, 9), ("tiled 4x4", {"CCM_SCHUR_TILE": "4"}, 9),
        ("tiled 4x4, unsorted lists", {"CCM_SCHUR_TILE": "4", "CCM_SCHUR_SORT": "0"}, 9), ("row-synchronous", {}, 10),
        ("vectorised entries u8", {}, 11), ("vectorised entries u16", {}, 12), ("vectorised entries u8 + predicated padding lanes", {}, 13),
-       ("vectorised entries u8 + wide row loads", {}, 14)]
+       ("vectorised entries u8 + wide row loads", {}, 14),
+       # layouts of the rows of Z (CCM_Z_LAYOUT = stride,gap,pad1; ZLayout in ba_kernels.cuh), all with the default kernel (mode 11)
+       ("layout dense 18,0,0", {"CCM_Z_LAYOUT": "18,0,0"}, 11), ("layout dense, idle lanes of half-warp 1 at element 12", {"CCM_Z_LAYOUT": "18,0,12"}, 11),
+       ("layout 32,4,16 (a line per half-warp)", {"CCM_Z_LAYOUT": "32,4,16"}, 11), ("layout 32,0,12 (aligned, contiguous)", {"CCM_Z_LAYOUT": "32,0,12"}, 11),
+       ("layout 24,4,16", {"CCM_Z_LAYOUT": "24,4,16"}, 11), ("layout 20,0,12", {"CCM_Z_LAYOUT": "20,0,12"}, 11),
+       ("layout 32,4,16 + predicated padding lanes", {"CCM_Z_LAYOUT": "32,4,16"}, 13)]
 want = sys.argv[2:]   # optional: substrings of the variant labels to run
 for label, env, mode in [v for v in ALL if not want or any(w in v[0] for w in want)]:
     for k, v in env.items():
@@ -26,12 +31,14 @@ for label, env, mode in [v for v in ALL if not want or any(w in v[0] for w in wa
         api._chk(api.lib().ccm_ba_debug_set_schur_mode(mode))     # before the handle: the tile schedule is built at create time for mode 9
         t0 = time.time(); h = api.BAHandle(p); t_create = time.time() - t0
         ms = [round(h.time_kernel(4, reps=5, lam=1e-3), 4) for _ in range(2)]
+        ms_scale = round(h.time_kernel(3, reps=5, lam=1e-3), 4)
+        ms_backsub = round(h.time_kernel(5, reps=5, lam=1e-3), 4)
         h.reset(); h.set_profile(True)
         r = h.optimize(iterations=20, want_state=True)
         st = h.kernel_stats()
         if ref is None:
             ref = r
-        print("RESULT " + json.dumps({"variant": label, "schur_ms_per_launch": ms, "create_s": round(t_create, 3), "iters": int(r["iters_done"]),
+        print("RESULT " + json.dumps({"variant": label, "schur_ms_per_launch": ms, "scale_ms": ms_scale, "backsub_ms": ms_backsub, "create_s": round(t_create, 3), "iters": int(r["iters_done"]),
                                       "pcg_iters": int(r["pcg_iters_total"]), "schur_ms_in_gba": round(st["schur"]["total_ms"], 3),
                                       "event_ms": round(r["t_optimize_event_ms"], 3),
                                       "max_abs_diff_vs_first": [float(np.abs(r["poses"] - ref["poses"]).max()), float(np.abs(r["points"] - ref["points"]).max())]}), flush=True)
