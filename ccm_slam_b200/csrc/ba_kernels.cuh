@@ -283,20 +283,11 @@ __global__ void __launch_bounds__(1024) k_sum_partials(const double* __restrict_
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// Layout of a row of Z (18 doubles = Z_o, 6 x 3 row-major) in memory.  The Schur kernel reads a row as one MMA operand fragment:
-// lanes 0..15 take elements 0..11, lanes 16..23 elements 12..17, and the L1 data pipe -- the unit that bounds that kernel -- works
-// per half-warp and per 128-byte line.  stride: doubles from one row to the next; gap: doubles skipped between element 11 and
-// element 12 (so that the second half-warp's six elements can sit in a line of their own); pad1: the element position the idle
-// lanes of the second half-warp read (the idle lanes of the first read position 0).  {18, 0, 0} is the dense layout.
-struct ZLayout { int stride, gap, pad1; };
-__host__ __device__ __forceinline__ int zpos(const ZLayout& z, int c) { return c + (c >= 12 ? z.gap : 0); }
-
 // K3/K4 first half: Z = W U^-1 (AoS, staged through shared memory for coalesced rows), g = U^-T bl.
-// reads 144 B/obs (W) + cached Hll ; writes 144 B/obs (Z) (whole 32-byte sectors of a padded row: 160 B)
+// reads 144 B/obs (W) + cached Hll ; writes 144 B/obs (Z)
 __global__ void __launch_bounds__(TPB) k_scale(const int* __restrict__ o_lm, const double* __restrict__ W, size_t Ep,
                                                const double* __restrict__ Hll, const double* __restrict__ bl, int Pl,
-                                               int E, double lambda, double* __restrict__ Z, double* __restrict__ gvec,
-                                               ZLayout zl = ZLayout{18, 0, 0}) {
+                                               int E, double lambda, double* __restrict__ Z, double* __restrict__ gvec) {
   __shared__ double tile[TPB * 19];
   const long long e0 = (long long)blockIdx.x * TPB;
   const long long e = e0 + threadIdx.x;
@@ -325,22 +316,9 @@ __global__ void __launch_bounds__(TPB) k_scale(const int* __restrict__ o_lm, con
     }
   }
   __syncthreads();
-  const int zs = zl.stride;
-  const long long nvalid = (E - e0 < TPB ? E - e0 : TPB) * zs;
-  double* out = Z + e0 * zs;
-  if (zs == 18) {
-    for (int i = threadIdx.x; i < nvalid; i += TPB) out[i] = tile[(i / 18) * 19 + (i % 18)];
-  } else {
-    // padded rows: positions [0, 12) and [12 + gap, 18 + gap) carry data; the other positions of a 32-byte sector that holds data
-    // are written as zeros (whole sectors leave the SM), sectors without data are not written at all
-    const int g = zl.gap, hi = (18 + g + 3) & ~3;
-    for (int i = threadIdx.x; i < nvalid; i += TPB) {
-      const int rw = i / zs, q = i - rw * zs;
-      if (q < 12) out[i] = tile[rw * 19 + q];
-      else if (q >= 12 + g && q < 18 + g) out[i] = tile[rw * 19 + q - g];
-      else if ((g == 0 || q >= ((12 + g) & ~3)) && q < hi) out[i] = 0.0;
-    }
-  }
+  const long long nvalid = (E - e0 < TPB ? E - e0 : TPB) * 18;
+  double* out = Z + e0 * 18;
+  for (int i = threadIdx.x; i < nvalid; i += TPB) out[i] = tile[(i / 18) * 19 + (i % 18)];
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -424,9 +402,10 @@ __device__ __forceinline__ void dmma_884(double& c0, double& c1, double a, doubl
 // PRED (with VEC): the 14 padding lanes of a fragment do not load at all (predicated off) instead of re-reading element 0 of the row.
 // WIDE (with VEC): a 144-byte row comes in as nine 16-byte loads (lanes 0..8) and reaches its fragment lanes by two 64-bit shuffles,
 // instead of eighteen 8-byte lanes: fewer L1 wavefronts per row, more shuffles.
-// SMB (with VEC): the entries of a batch go from the loading lanes through a per-warp shared-memory slot (double-buffered: one
-// __syncwarp per batch) and come back as broadcast 16-byte loads, two entries each: UNROLL / 2 + 1 shared-memory wavefronts per batch
-// instead of 2 UNROLL shuffles (a shuffle is a wavefront of the same L1 data pipe).
+// SMB (with VEC, CCM_SCHUR=15): the entries of a batch go from the loading lanes through a per-warp shared-memory slot (double-buffered:
+// one __syncwarp per batch) and come back as broadcast 16-byte loads, two entries each: UNROLL / 2 + 1 shared-memory wavefronts per
+// batch instead of 2 UNROLL shuffles (a shuffle is a wavefront of the same L1 data pipe).  Measured: 7.62 ms against 6.90 ms -- the
+// store / barrier / load chain in front of every batch costs more latency than the wavefronts are worth.
 template <int UNROLL, int CTA, bool PIPE = false, bool TILED = false, bool VEC = false, bool PRED = false, bool WIDE = false,
           bool SMB = false>
 __global__ void __launch_bounds__(CTA) k_schur_mma(const uint2* __restrict__ prod, const unsigned* __restrict__ u_prod_ptr,
@@ -435,8 +414,7 @@ __global__ void __launch_bounds__(CTA) k_schur_mma(const uint2* __restrict__ pro
                                                    const double* __restrict__ gvec, double* __restrict__ U_val,
                                                    double* __restrict__ bneg, const int* __restrict__ tile_ptr = nullptr,
                                                    const int* __restrict__ tile_u = nullptr,
-                                                   const unsigned char* __restrict__ covered = nullptr, int only_diag = 0,
-                                                   ZLayout zl = ZLayout{18, 0, 0}) {
+                                                   const unsigned char* __restrict__ covered = nullptr, int only_diag = 0) {
   static_assert(UNROLL % 2 == 0, "products alternate between two accumulator sets");
   int warp;
   if (TILED) {
@@ -452,9 +430,10 @@ __global__ void __launch_bounds__(CTA) k_schur_mma(const uint2* __restrict__ pro
   const int lane = threadIdx.x & 31;
   const int m = lane >> 2, k = lane & 3;
   const bool ld = m < 6 && k < 3;
-  const int zs = zl.stride;
-  // padding lanes read an element their half-warp reads anyway (no extra line) and discard it
-  const int off = ld ? zpos(zl, m * 3 + k) : (lane < 16 ? 0 : zl.pad1);
+  constexpr int zs = 18;   // doubles per row of Z.  Padded rows (a 128-byte line per half-warp, 160 / 192 / 256-byte strides) were measured
+                           // and are no faster: 7.16 .. 7.36 ms against 7.21 ms (profiles/r2/zlayout_cfg5.log)
+  // padding lanes read an element their own half-warp reads anyway (no extra line: 7.21 -> 7.13 ms) and discard it
+  const int off = ld ? m * 3 + k : (lane < 16 ? 0 : 12);
   const unsigned beg = u_prod_ptr[warp], end = u_prod_ptr[warp + 1];
   const int row = u_row[warp];
   const bool diag = row == u_col[warp];
@@ -490,9 +469,8 @@ __global__ void __launch_bounds__(CTA) k_schur_mma(const uint2* __restrict__ pro
         if (WIDE) {
           double2 ra = make_double2(0.0, 0.0), rb = make_double2(0.0, 0.0);
           if (lane < 9) {
-            const int q2 = lane + (lane >= 6 ? zl.gap / 2 : 0);   // gap is even: 16-byte pieces stay whole
-            ra = reinterpret_cast<const double2*>(Z + (size_t)pr[j].x * zs)[q2];
-            rb = reinterpret_cast<const double2*>(Z + (size_t)pr[j].y * zs)[q2];
+            ra = reinterpret_cast<const double2*>(Z + (size_t)pr[j].x * zs)[lane];
+            rb = reinterpret_cast<const double2*>(Z + (size_t)pr[j].y * zs)[lane];
           }
           const int cl = ld ? m * 3 + k : 0, src = cl >> 1;
           const double ax = __shfl_sync(0xffffffffu, ra.x, src), ay = __shfl_sync(0xffffffffu, ra.y, src);
@@ -700,6 +678,157 @@ __global__ void __launch_bounds__(32 * RS_W) k_schur_rowsync(const uint2* __rest
   }
 }
 
+// Grouped form (CCM_SCHUR=16 / 17; measured, NOT the default).  The list kernel is bound by the L1 data pipe: every product costs two
+// row loads of 144 bytes (two lines each: ~3 wavefronts), and a row Z_(l,a) is loaded once for every block (a, b) whose list holds l.
+// Here the off-diagonal upper blocks of a block row are cut into groups of QG consecutive blocks (a, b_1 .. b_QG), one warp per group,
+// and the lists are kept per group: an entry is (observation of a, observation of b_1 | none, .., observation of b_QG | none) for one
+// landmark, so the row of a is loaded ONCE per entry and multiplied into up to QG accumulator sets; an entry with one member costs
+// what a list product costs, so the form never loads more rows than the list kernel.  Diagonal blocks (their lists also feed the pose
+// pass, and they carry the g_l column) stay with k_schur_mma, launched with only_diag = 1.
+// Outcome on cfg5 (profiles/r2/quad_cfg5.log): 95.2 M entries for 190 M products (2.0 products per entry: 25 % fewer row loads), parity
+// green (tests/test_gpu_ba.py under CCM_SCHUR=16 and 17), and 13.6 ms per launch against 6.9 ms for the list kernel (cfg4: 0.20 against
+// 0.11 ms): 78-128 registers and sixteen conditional MMAs per batch cost more than the row loads saved.  Kept as a switch.
+constexpr int QG = 4;
+constexpr unsigned Q_NONE = 0xffffffffu;
+__device__ __forceinline__ int csr_pos(const unsigned* __restrict__ bitmap, const int* __restrict__ word_prefix,
+                                       const int* __restrict__ s_rowptr, int words, int a, int b);   // defined with the pattern kernels below
+
+// count (fill == 0) or fill (fill == 1) the grouped lists; one thread per local observation e (pose a, landmark l) walks the other
+// observations of l in list order and keeps ONE open entry: an observation of a later pose joins it if it falls into the same group
+// and its member slot is free, otherwise the entry is closed (a slot of the group's list taken by atomicAdd) and a new one opened.
+// Keyframe-ordered observation lists (the usual case) therefore give the densest entries; any other order only costs sharing.
+__global__ void __launch_bounds__(TPB) k_quad_entries(const int* __restrict__ o_kf, const int* __restrict__ o_lm,
+                                                      const int* __restrict__ lm_ptr, const int* __restrict__ pose_slot,
+                                                      const unsigned* __restrict__ bitmap, const int* __restrict__ word_prefix,
+                                                      const int* __restrict__ s_rowptr, const int* __restrict__ csr_u, int words,
+                                                      int E, int fill, const int* __restrict__ u_diag,
+                                                      const int* __restrict__ g_rowstart, unsigned* __restrict__ counters,
+                                                      const unsigned* __restrict__ g_ptr, unsigned* __restrict__ gent) {
+  const long long e = (long long)blockIdx.x * TPB + threadIdx.x;
+  if (e >= E) return;
+  const int a = pose_slot[o_kf[e]];
+  if (a < 0) return;
+  const int lm = o_lm[e];
+  const int beg = lm_ptr[lm], end = lm_ptr[lm + 1];
+  const int ud = u_diag[a], g0 = g_rowstart[a];
+  int open = -1;
+  unsigned m0 = Q_NONE, m1 = Q_NONE, m2 = Q_NONE, m3 = Q_NONE;
+  auto flush = [&]() {
+    if (open < 0) return;
+    const unsigned slot = atomicAdd(counters + open, 1u);
+    if (fill) {
+      unsigned* d = gent + ((size_t)g_ptr[open] + slot) * (QG + 1);
+      d[0] = (unsigned)e; d[1] = m0; d[2] = m1; d[3] = m2; d[4] = m3;
+    }
+  };
+  for (int o = beg; o < end; o++) {
+    const int b = pose_slot[o_kf[o]];
+    if (b <= a) continue;   // strictly upper blocks only (b < 0: fixed pose)
+    const int j = csr_u[csr_pos(bitmap, word_prefix, s_rowptr, words, a, b)] - ud - 1;
+    const int grp = g0 + (j >> 2), mi = j & 3;
+    const unsigned cur = mi == 0 ? m0 : mi == 1 ? m1 : mi == 2 ? m2 : m3;
+    if (grp != open || cur != Q_NONE) {
+      flush();
+      open = grp; m0 = m1 = m2 = m3 = Q_NONE;
+    }
+    if (mi == 0) m0 = (unsigned)o; else if (mi == 1) m1 = (unsigned)o; else if (mi == 2) m2 = (unsigned)o; else m3 = (unsigned)o;
+  }
+  flush();
+}
+
+// a row element if the member is present, 0 otherwise.  Volatile asm: the compiler would otherwise sink every conditional load into the
+// conditional MMA that consumes it (load, wait, multiply, sixteen times in a row) instead of keeping the batch's loads in flight together.
+__device__ __forceinline__ double ld_row_if(const double* p, unsigned present) {
+  double v;
+  asm volatile("{\n .reg .pred q;\n setp.ne.u32 q, %2, 0;\n mov.f64 %0, 0d0000000000000000;\n @q ld.global.nc.f64 %0, [%1];\n}"
+               : "=d"(v)
+               : "l"(p), "r"(present));
+  return v;
+}
+
+// one warp per group; EB entries per batch: their 5 EB words come in with one coalesced load and reach the lanes by shuffle (SMB:
+// through a double-buffered shared-memory slot and broadcast 16-byte loads), then the EB rows of a and the up to QG EB rows of
+// the b_i are in flight together; a member that is absent (warp-uniform) neither loads nor multiplies.
+template <int EB, int CTA, bool SMB>
+__global__ void __launch_bounds__(CTA) k_schur_quad(const unsigned* __restrict__ gent, const unsigned* __restrict__ g_ptr,
+                                                    const int* __restrict__ g_first, const int* __restrict__ g_count, int ng,
+                                                    const double* __restrict__ Z, double* __restrict__ U_val) {
+  static_assert(EB == 4, "a batch is 20 words: five 16-byte pieces");
+  constexpr int NW = EB * (QG + 1);
+  const int warp = (int)(((long long)blockIdx.x * CTA + threadIdx.x) >> 5);
+  if (warp >= ng) return;  // warp-uniform
+  const int lane = threadIdx.x & 31;
+  const int m = lane >> 2, k = lane & 3;
+  const bool ld = m < 6 && k < 3;
+  const int off = ld ? m * 3 + k : (lane < 16 ? 0 : 12);
+  const unsigned beg = g_ptr[warp], end = g_ptr[warp + 1];
+  __shared__ uint4 s_w[SMB ? (CTA / 32) * 2 * (NW / 4) : 1];
+  uint4* const my_w = s_w + (SMB ? (threadIdx.x >> 5) * 2 * (NW / 4) : 0);
+  double c[QG][2][2];
+#pragma unroll
+  for (int i = 0; i < QG; i++) { c[i][0][0] = c[i][0][1] = c[i][1][0] = c[i][1][1] = 0.0; }
+  unsigned p = beg, batch = 0;
+  unsigned nx = Q_NONE;
+  if (p + EB <= end && lane < NW) nx = gent[(size_t)p * (QG + 1) + lane];
+  for (; p + EB <= end; p += EB) {
+    unsigned w[NW];
+    if (SMB) {
+      uint4* slot = my_w + (batch & 1u) * (NW / 4);
+      batch++;
+      if (lane < NW) reinterpret_cast<unsigned*>(slot)[lane] = nx;
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < NW; j += 4) {
+        const uint4 t = slot[j >> 2];
+        w[j] = t.x; w[j + 1] = t.y; w[j + 2] = t.z; w[j + 3] = t.w;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < NW; j++) w[j] = __shfl_sync(0xffffffffu, nx, j);
+    }
+    if (p + 2 * EB <= end && lane < NW) nx = gent[(size_t)(p + EB) * (QG + 1) + lane];
+    double a[EB], b[EB][QG];
+#pragma unroll
+    for (int e = 0; e < EB; e++) {
+      a[e] = Z[(size_t)w[e * (QG + 1)] * 18 + off];
+#pragma unroll
+      for (int i = 0; i < QG; i++) {
+        const unsigned ob = w[e * (QG + 1) + 1 + i];
+        b[e][i] = ld_row_if(Z + (size_t)ob * 18 + off, ob != Q_NONE ? 1u : 0u);
+      }
+    }
+#pragma unroll
+    for (int e = 0; e < EB; e++) {
+#pragma unroll
+      for (int i = 0; i < QG; i++)
+        if (w[e * (QG + 1) + 1 + i] != Q_NONE) dmma_884(c[i][e & 1][0], c[i][e & 1][1], ld ? a[e] : 0.0, ld ? b[e][i] : 0.0);
+    }
+  }
+  for (; p < end; p++) {
+    unsigned t = Q_NONE;
+    if (lane < QG + 1) t = gent[(size_t)p * (QG + 1) + lane];
+    const unsigned oa = __shfl_sync(0xffffffffu, t, 0);
+    const double a = Z[(size_t)oa * 18 + off];
+#pragma unroll
+    for (int i = 0; i < QG; i++) {
+      const unsigned ob = __shfl_sync(0xffffffffu, t, 1 + i);
+      if (ob != Q_NONE) {
+        const double b = Z[(size_t)ob * 18 + off];
+        dmma_884(c[i][0][0], c[i][0][1], ld ? a : 0.0, ld ? b : 0.0);
+      }
+    }
+  }
+  const int u0 = g_first[warp], cnt = g_count[warp];
+  if (ld) {
+#pragma unroll
+    for (int i = 0; i < QG; i++)
+      if (i < cnt) {
+        U_val[(size_t)(u0 + i) * 36 + m * 6 + 2 * k] = -(c[i][0][0] + c[i][1][0]);
+        U_val[(size_t)(u0 + i) * 36 + m * 6 + 2 * k + 1] = -(c[i][0][1] + c[i][1][1]);
+      }
+  }
+}
+
 // S (full block-CSR) from the upper blocks: diagonal gets Hpp + lambda I, lower blocks are transposed copies.
 __global__ void __launch_bounds__(TPB) k_finalize_S(const int* __restrict__ s_row, const int* __restrict__ s_col,
                                                     const int* __restrict__ csr_u, long long nnzb,
@@ -818,11 +947,9 @@ __global__ void __launch_bounds__(TPB) k_backsub_points(const int* __restrict__ 
                                                         const double* __restrict__ Hll, const double* __restrict__ bl,
                                                         const double* __restrict__ x, const double* __restrict__ pt,
                                                         int Pl, double lambda, double* __restrict__ pt_trial,
-                                                        double* __restrict__ dx_out, double* __restrict__ scale_partials,
-                                                        ZLayout zl = ZLayout{18, 0, 0}) {
+                                                        double* __restrict__ dx_out, double* __restrict__ scale_partials) {
   __shared__ double red[TPB / 32];
   double acc = 0.0;
-  const int zs = zl.stride, zg2 = zl.gap / 2;
   for (int l = blockIdx.x * TPB + threadIdx.x; l < Pl; l += gridDim.x * TPB) {
     double d[6], u[6], b3[3], g[3], t[3] = {0, 0, 0}, xl[3];
 #pragma unroll
@@ -835,10 +962,10 @@ __global__ void __launch_bounds__(TPB) k_backsub_points(const int* __restrict__ 
     for (int o = beg; o < end; o++) {
       const int s = __ldg(pose_slot + o_kf[o]);
       if (s < 0) continue;
-      const double2* z2 = reinterpret_cast<const double2*>(Z + (size_t)o * zs);
+      const double2* z2 = reinterpret_cast<const double2*>(Z + (size_t)o * 18);
       double z[18];
 #pragma unroll
-      for (int i = 0; i < 9; i++) { const double2 v = z2[i < 6 ? i : i + zg2]; z[2 * i] = v.x; z[2 * i + 1] = v.y; }
+      for (int i = 0; i < 9; i++) { const double2 v = z2[i]; z[2 * i] = v.x; z[2 * i + 1] = v.y; }
 #pragma unroll
       for (int r = 0; r < 6; r++) {
         const double xr = __ldg(x + (size_t)s * 6 + r);

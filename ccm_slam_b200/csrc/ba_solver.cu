@@ -77,12 +77,17 @@ struct ccm_ba_handle {
   DevBuf<uint2> prod;
   // landmark-synchronous Schur panels (schur_panel.cuh)
   bool panel_on = false;
-  ZLayout zl{18, 0, 0};            // layout of the rows of Z (CCM_Z_LAYOUT = "stride,gap,pad1"; see ba_kernels.cuh)
   int npan = 0;
   DevBuf<int> o_slot, pose_lmin, pose_lmax, pose_cnt;
   DevBuf<unsigned char> pan_on, covered;
   DevBuf<int> rs_first, rs_count;  // row-synchronous Schur schedule (CCM_SCHUR=10): CTAs of <= RS_W off-diagonal blocks of one row
   int rs_ctas = 0;
+  // grouped Schur lists (CCM_SCHUR=16 / 17, k_schur_quad): groups of QG consecutive off-diagonal upper blocks of one row
+  DevBuf<unsigned> g_ptr, g_ent;   // [ng + 1] first entry of every group; entries of QG + 1 words
+  DevBuf<int> g_first, g_count;    // [ng] first upper block and number of blocks of every group
+  int ng = 0;
+  long long nquad = 0;             // grouped entries (local shard)
+  bool quad_built = false;         // the off-diagonal PAIR lists were not built: only k_schur_quad can form those blocks
   DevBuf<int> tile_ptr, tile_u;   // T x T tiles of upper blocks: the CTA schedule of the tiled Schur kernel
   int ntiles = 0, tile_T = 0;
   DevBuf<float4> kobs;            // per free pose: (u, v, signed w, landmark) of its observations, packed
@@ -248,7 +253,7 @@ void step_scale(ccm_ba_handle* h, double lambda) {
   if (h->El == 0) return;
   KernelSpan sp(h, CCM_BA_K_SCALE);
   k_scale<<<div_up(h->El, TPB), TPB, 0, h->stream>>>(h->o_lm.p, h->W.p, h->Ep, h->Hll(), h->bl(), h->Pl, h->El, lambda,
-                                                     h->Z.p, h->gvec.p, h->zl);
+                                                     h->Z.p, h->gvec.p);
   CCM_LAUNCHED();
 }
 
@@ -262,7 +267,7 @@ int schur_mode() {
     if (!strcmp(v, "gather") || !strcmp(v, "0")) return 0;
     if (!strcmp(v, "mma")) return 1;
     const int m = atoi(v);
-    return (m >= 0 && m <= 15) ? m : 1;
+    return (m >= 0 && m <= 17) ? m : 1;
   }();
   const int o = g_schur_override.load(std::memory_order_relaxed);
   return o >= 0 ? o : env_mode;
@@ -271,14 +276,14 @@ int schur_mode() {
 template <int UNROLL, int CTA>
 void launch_schur_tiled(ccm_ba_handle* h, cudaStream_t s) {
   k_schur_mma<UNROLL, CTA, true, true><<<h->ntiles, CTA, 0, s>>>(h->prod.p, h->u_prod_ptr.p, h->u_row.p, h->u_col.p, h->nub, h->Z.p, h->o_lm.p,
-                                                                  h->gvec.p, h->U_val(), h->bneg(), h->tile_ptr.p, h->tile_u.p, nullptr, 0, h->zl);
+                                                                  h->gvec.p, h->U_val(), h->bneg(), h->tile_ptr.p, h->tile_u.p, nullptr);
 }
 
 template <int UNROLL, int CTA, bool PIPE = false>
 void launch_schur_mma(ccm_ba_handle* h, cudaStream_t s) {
   k_schur_mma<UNROLL, CTA, PIPE><<<div_up((long long)h->nub * 32, CTA), CTA, 0, s>>>(h->prod.p, h->u_prod_ptr.p, h->u_row.p, h->u_col.p, h->nub,
                                                                               h->Z.p, h->o_lm.p, h->gvec.p, h->U_val(), h->bneg(), nullptr,
-                                                                              nullptr, h->panel_on ? h->covered.p : nullptr, 0, h->zl);
+                                                                              nullptr, h->panel_on ? h->covered.p : nullptr);
 }
 
 void launch_schur_panel(ccm_ba_handle* h, cudaStream_t s) {
@@ -295,14 +300,24 @@ void launch_schur(ccm_ba_handle* h, cudaStream_t s) {
     CCM_LAUNCHED();
   }
   const int mode = schur_mode();
-  const bool dense_rows = h->zl.stride == 18 && h->zl.gap == 0;
-  CCM_REQUIRE(dense_rows || (!h->panel_on && mode != 0 && !(mode == 10 && h->rs_ctas > 0)),
-              "a padded layout of Z (CCM_Z_LAYOUT) is read by the list kernel k_schur_mma only: not with CCM_SCHUR=0 / 10 or CCM_SCHUR_PANEL");
+  CCM_REQUIRE(h->quad_built == (mode == 16 || mode == 17),
+              "the grouped Schur lists (CCM_SCHUR=16/17) are built when the handle is created: set the mode before ccm_ba_create");
+  if (h->quad_built) {   // off-diagonal blocks by groups of one row sharing the row of a, diagonal blocks by the list kernel
+    if (h->ng > 0) {
+      if (mode == 17)
+        k_schur_quad<4, 128, true><<<div_up((long long)h->ng * 32, 128), 128, 0, s>>>(h->g_ent.p, h->g_ptr.p, h->g_first.p, h->g_count.p, h->ng, h->Z.p, h->U_val());
+      else
+        k_schur_quad<4, 128, false><<<div_up((long long)h->ng * 32, 128), 128, 0, s>>>(h->g_ent.p, h->g_ptr.p, h->g_first.p, h->g_count.p, h->ng, h->Z.p, h->U_val());
+    }
+    k_schur_mma<8, 128, true, false, true><<<div_up((long long)h->nub * 32, 128), 128, 0, s>>>(h->prod.p, h->u_prod_ptr.p, h->u_row.p, h->u_col.p, h->nub, h->Z.p,
+                                                                                          h->o_lm.p, h->gvec.p, h->U_val(), h->bneg(), nullptr, nullptr, nullptr, 1);
+    return;
+  }
   if (mode == 10 && h->rs_ctas > 0) {   // off-diagonal blocks row-synchronously, diagonal blocks by the list kernel
     k_schur_rowsync<8><<<h->rs_ctas, 32 * RS_W, 0, s>>>(h->prod.p, h->u_prod_ptr.p, h->rs_first.p, h->rs_count.p, h->Z.p, h->U_val());
     k_schur_mma<8, 128, true><<<div_up((long long)h->nub * 32, 128), 128, 0, s>>>(h->prod.p, h->u_prod_ptr.p, h->u_row.p, h->u_col.p, h->nub, h->Z.p,
                                                                                h->o_lm.p, h->gvec.p, h->U_val(), h->bneg(), nullptr, nullptr,
-                                                                               h->panel_on ? h->covered.p : nullptr, 1, h->zl);
+                                                                               h->panel_on ? h->covered.p : nullptr, 1);
     return;
   }
   // Modes 11-14: the ncu capture of the list kernel (profiles/prof_r2_k_schur_mma.ncu-rep) shows the L1 data pipe at 72 % of its wavefront
@@ -313,22 +328,22 @@ void launch_schur(ccm_ba_handle* h, cudaStream_t s) {
   // profiles/r2/vec_cfg5.log, vec2_cfg5.log, b23_schur.log
   if (mode >= 11 && mode <= 15) {
     const unsigned char* cov = h->panel_on ? h->covered.p : nullptr;
-    if (mode == 15)   // entries broadcast through shared memory instead of shuffles
+    if (mode == 15)   // entries broadcast through shared memory instead of shuffles: 7.62 ms against 6.90 ms (profiles/r2/quad_cfg5.log)
       k_schur_mma<8, 128, true, false, true, false, false, true><<<div_up((long long)h->nub * 32, 128), 128, 0, s>>>(
-          h->prod.p, h->u_prod_ptr.p, h->u_row.p, h->u_col.p, h->nub, h->Z.p, h->o_lm.p, h->gvec.p, h->U_val(), h->bneg(), nullptr, nullptr, cov, 0, h->zl);
+          h->prod.p, h->u_prod_ptr.p, h->u_row.p, h->u_col.p, h->nub, h->Z.p, h->o_lm.p, h->gvec.p, h->U_val(), h->bneg(), nullptr, nullptr, cov);
     else if (mode == 14)
       k_schur_mma<8, 128, true, false, true, false, true><<<div_up((long long)h->nub * 32, 128), 128, 0, s>>>(h->prod.p, h->u_prod_ptr.p, h->u_row.p, h->u_col.p,
                                                                                                     h->nub, h->Z.p, h->o_lm.p, h->gvec.p, h->U_val(), h->bneg(),
-                                                                                                    nullptr, nullptr, cov, 0, h->zl);
+                                                                                                    nullptr, nullptr, cov);
     else if (mode == 13)
       k_schur_mma<8, 128, true, false, true, true><<<div_up((long long)h->nub * 32, 128), 128, 0, s>>>(h->prod.p, h->u_prod_ptr.p, h->u_row.p, h->u_col.p, h->nub,
-                                                                                             h->Z.p, h->o_lm.p, h->gvec.p, h->U_val(), h->bneg(), nullptr, nullptr, cov, 0, h->zl);
+                                                                                             h->Z.p, h->o_lm.p, h->gvec.p, h->U_val(), h->bneg(), nullptr, nullptr, cov);
     else if (mode == 11)
       k_schur_mma<8, 128, true, false, true><<<div_up((long long)h->nub * 32, 128), 128, 0, s>>>(h->prod.p, h->u_prod_ptr.p, h->u_row.p, h->u_col.p, h->nub,
-                                                                                       h->Z.p, h->o_lm.p, h->gvec.p, h->U_val(), h->bneg(), nullptr, nullptr, cov, 0, h->zl);
+                                                                                       h->Z.p, h->o_lm.p, h->gvec.p, h->U_val(), h->bneg(), nullptr, nullptr, cov);
     else
       k_schur_mma<16, 128, true, false, true><<<div_up((long long)h->nub * 32, 128), 128, 0, s>>>(h->prod.p, h->u_prod_ptr.p, h->u_row.p, h->u_col.p, h->nub,
-                                                                                        h->Z.p, h->o_lm.p, h->gvec.p, h->U_val(), h->bneg(), nullptr, nullptr, cov, 0, h->zl);
+                                                                                        h->Z.p, h->o_lm.p, h->gvec.p, h->U_val(), h->bneg(), nullptr, nullptr, cov);
     return;
   }
   if (mode == 9 && h->ntiles > 0) {   // tiled schedules (the tile edge was fixed when the handle was created: CCM_SCHUR_TILE)
@@ -553,7 +568,7 @@ void step_update_and_residual(ccm_ba_handle* h, double lambda, int robust, doubl
   sum_partials_to(h, g1, h->scal.p + 2);
   const int g2 = grid_stride(h->Pl);
   k_backsub_points<<<g2, TPB, 0, s>>>(h->lm_ptr.p, h->o_kf.p, h->pose_slot.p, h->Z.p, h->Hll(), h->bl(), h->x.p, h->pt_cur,
-                                      h->Pl, lambda, h->pt_trial, dx_points, h->partials.p, h->zl);
+                                      h->Pl, lambda, h->pt_trial, dx_points, h->partials.p);
   CCM_LAUNCHED();
   sum_partials_to(h, g2, h->scal.p + 1);
   if (h->profile) { size_t ev1 = ev_record(h); h->spans.push_back({CCM_BA_K_BACKSUB, ev0, ev1}); ev0 = ev1; }
@@ -845,6 +860,57 @@ void build(ccm_ba_handle* h, const ccm_ba_problem* p) {
     CCM_CUDA(cudaFuncSetAttribute((const void*)k_schur_panel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SP_SMEM));
   }
   const unsigned char* cov = h->panel_on ? h->covered.p : nullptr;
+  // ---- grouped Schur lists (CCM_SCHUR=16 / 17): groups of QG consecutive off-diagonal upper blocks per row, entries built from the
+  // local observations; the pair lists below then hold the diagonal blocks only (every off-diagonal block marked as covered)
+  h->quad_built = (schur_mode() == 16 || schur_mode() == 17);
+  h->ng = 0;
+  if (h->quad_built) {
+    CCM_REQUIRE(!h->panel_on, "CCM_SCHUR=16/17 and CCM_SCHUR_PANEL are alternatives");
+    std::vector<int> grow((size_t)Kf + 1, 0), first, count;
+    for (int a2 = 0; a2 < Kf; a2++) {
+      const int u0 = h_udiag[a2] + 1, u1 = a2 + 1 < Kf ? h_udiag[a2 + 1] : nub;
+      for (int q = u0; q < u1; q += QG) { first.push_back(q); count.push_back(std::min(QG, u1 - q)); }
+      grow[a2 + 1] = (int)first.size();
+    }
+    h->ng = (int)first.size();
+    h->covered.alloc(std::max(nub, 1));
+    CCM_CUDA(cudaMemsetAsync(h->covered.p, 1, std::max(nub, 1), s));   // only read for off-diagonal blocks
+    cov = h->covered.p;
+    std::vector<unsigned> h_gp((size_t)h->ng + 1, 0);
+    if (h->ng > 0) { upload_vec(h->g_first, first, s); upload_vec(h->g_count, count, s); }
+    else { h->g_first.alloc(1); h->g_count.alloc(1); }
+    unsigned long long run = 0;
+    if (h->ng > 0 && El > 0) {
+      DevBuf<int> g_rowstart;
+      upload_vec(g_rowstart, grow, s);
+      DevBuf<unsigned> gcnt; gcnt.alloc_zero(h->ng, s);
+      k_quad_entries<<<div_up(El, TPB), TPB, 0, s>>>(h->o_kf.p, h->o_lm.p, h->lm_ptr.p, h->pose_slot.p, h->bitmap.p, h->word_prefix.p,
+                                                     h->s_rowptr.p, h->csr_u.p, words, El, 0, h->u_diag.p, g_rowstart.p, gcnt.p, nullptr, nullptr);
+      CCM_LAUNCHED();
+      std::vector<unsigned> c(h->ng);
+      gcnt.download(c.data(), h->ng, s);
+      CCM_CUDA(cudaStreamSynchronize(s));
+      for (int g = 0; g < h->ng; g++) { h_gp[g] = (unsigned)run; run += c[g]; }
+      CCM_REQUIRE(run < (1ull << 32) / (QG + 1), "too many grouped Schur entries for 32-bit offsets");
+      h_gp[h->ng] = (unsigned)run;
+      upload_vec(h->g_ptr, h_gp, s);
+      h->g_ent.alloc(std::max<size_t>((size_t)run * (QG + 1), 1));
+      if (run) {
+        CCM_CUDA(cudaMemsetAsync(gcnt.p, 0, sizeof(unsigned) * h->ng, s));
+        k_quad_entries<<<div_up(El, TPB), TPB, 0, s>>>(h->o_kf.p, h->o_lm.p, h->lm_ptr.p, h->pose_slot.p, h->bitmap.p, h->word_prefix.p,
+                                                       h->s_rowptr.p, h->csr_u.p, words, El, 1, h->u_diag.p, g_rowstart.p, gcnt.p, h->g_ptr.p, h->g_ent.p);
+        CCM_LAUNCHED();
+      }
+      CCM_CUDA(cudaStreamSynchronize(s));   // g_rowstart, gcnt and the host vectors die here
+    } else {
+      upload_vec(h->g_ptr, h_gp, s);
+      h->g_ent.alloc(1);
+      CCM_CUDA(cudaStreamSynchronize(s));
+    }
+    h->nquad = (long long)run;
+    if (sprof) fprintf(stderr, "[ccm_ba_create r%d] grouped Schur lists: %d groups, %lld entries\n", h->rank, h->ng, h->nquad);
+    lap("grouped product lists");
+  }
   // ---- Schur product lists (local shard)
   DevBuf<unsigned> counters; counters.alloc_zero(std::max(nub, 1), s);
   std::vector<unsigned> h_pp((size_t)nub + 1, 0);
@@ -929,14 +995,7 @@ void build(ccm_ba_handle* h, const ccm_ba_problem* p) {
 
   lap("pose observation stream");
   // ---- linear-system storage
-  if (const char* v = getenv("CCM_Z_LAYOUT")) {   // "stride,gap,pad1" in doubles (see ZLayout in ba_kernels.cuh)
-    int st = 18, gp = 0, pd = 0;
-    const int got = sscanf(v, "%d,%d,%d", &st, &gp, &pd);
-    CCM_REQUIRE(got >= 1 && st % 2 == 0 && gp % 2 == 0 && gp >= 0 && st >= 18 + gp && st <= 64 && pd >= 0 && pd < 18 + gp,
-                "CCM_Z_LAYOUT: stride,gap,pad1 with even stride >= 18 + gap, even gap >= 0, 0 <= pad1 < 18 + gap");
-    h->zl = ZLayout{st, gp, pd};
-  }
-  h->W.alloc(std::max(h->Ep * 18, (size_t)1)); h->Z.alloc(std::max((size_t)El * h->zl.stride, (size_t)2));
+  h->W.alloc(std::max(h->Ep * 18, (size_t)1)); h->Z.alloc(std::max((size_t)El * 18, (size_t)2));
   h->HllBl.alloc(std::max((size_t)Pl * 9, (size_t)1)); h->gvec.alloc(std::max((size_t)Pl * 3, (size_t)1));
   h->Hbuf.alloc_zero((size_t)Kf * 42 + 2, s);
   h->Ubuf.alloc_zero((size_t)nub * 36 + (size_t)Kf * 6 + 1, s);
@@ -985,7 +1044,7 @@ void build(ccm_ba_handle* h, const ccm_ba_problem* p) {
   if (Pl) CCM_CUDA(cudaMemcpyAsync(h->pt_trial, h->pt0.p, sizeof(double) * 3 * Pl, cudaMemcpyDeviceToDevice, s));
   h->pose_eval = h->pose_cur; h->pt_eval = h->pt_cur;
   CCM_CUDA(cudaStreamSynchronize(s));
-  h->device_bytes = (int64_t)(h->W.bytes() + h->Z.bytes() + h->prod.bytes() + h->s_val.bytes() + h->Ubuf.bytes() +
+  h->device_bytes = (int64_t)(h->W.bytes() + h->Z.bytes() + h->prod.bytes() + h->g_ent.bytes() + h->s_val.bytes() + h->Ubuf.bytes() +
                               h->bitmap.bytes() + h->word_prefix.bytes() + h->HllBl.bytes() + h->o_kf.bytes() * 2 +
                               h->o_uv.bytes() + h->o_w.bytes() * 2 + h->ptA.bytes() * 3);
   lap("storage + initial state");
@@ -1371,7 +1430,7 @@ extern "C" int ccm_ba_debug_schur(ccm_ba_handle* h, int robust, double huber_del
 
 extern "C" int ccm_ba_debug_set_schur_mode(int mode) {
   return guarded([&] {
-    CCM_REQUIRE(mode >= -1 && mode <= 15, "ccm_ba_debug_set_schur_mode: -1 (CCM_SCHUR / default), 0 gather, 1 mma, 2..8 mma variants, 9 tiled, 10 row-synchronous, 11..15 vectorised entry loads");
+    CCM_REQUIRE(mode >= -1 && mode <= 17, "ccm_ba_debug_set_schur_mode: -1 (CCM_SCHUR / default), 0 gather, 1 mma, 2..8 mma variants, 9 tiled, 10 row-synchronous, 11..15 vectorised entry loads, 16 / 17 grouped lists");
     g_schur_override.store(mode);
   });
 }
@@ -1406,14 +1465,14 @@ extern "C" int ccm_ba_time_kernel(ccm_ba_handle* h, int which, int reps, double 
                                                         h->pt_cur, h->El, 1, huber_delta, h->partials.p);
           break;
         case 3:
-          k_scale<<<div_up(h->El, TPB), TPB, 0, s>>>(h->o_lm.p, h->W.p, h->Ep, h->Hll(), h->bl(), h->Pl, h->El, lambda, h->Z.p, h->gvec.p, h->zl);
+          k_scale<<<div_up(h->El, TPB), TPB, 0, s>>>(h->o_lm.p, h->W.p, h->Ep, h->Hll(), h->bl(), h->Pl, h->El, lambda, h->Z.p, h->gvec.p);
           break;
         case 4:
           launch_schur(h, s);
           break;
         case 5:
           k_backsub_points<<<grid_stride(h->Pl), TPB, 0, s>>>(h->lm_ptr.p, h->o_kf.p, h->pose_slot.p, h->Z.p, h->Hll(), h->bl(),
-                                                              h->x.p, h->pt_cur, h->Pl, lambda, h->pt_trial, nullptr, h->partials.p, h->zl);
+                                                              h->x.p, h->pt_cur, h->Pl, lambda, h->pt_trial, nullptr, h->partials.p);
           break;
         case 6: {
           step_pcg(h, 1e-10, 2000);

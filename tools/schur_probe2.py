@@ -18,11 +18,10 @@ ALL = [("untiled prefetch, unsorted lists", {"CCM_SCHUR_SORT": "0"}, 8), ("until
        ("tiled 4x4, unsorted lists", {"CCM_SCHUR_TILE": "4", "CCM_SCHUR_SORT": "0"}, 9), ("row-synchronous", {}, 10),
        ("vectorised entries u8", {}, 11), ("vectorised entries u16", {}, 12), ("vectorised entries u8 + predicated padding lanes", {}, 13),
        ("vectorised entries u8 + wide row loads", {}, 14),
-       # layouts of the rows of Z (CCM_Z_LAYOUT = stride,gap,pad1; ZLayout in ba_kernels.cuh), all with the default kernel (mode 11)
-       ("layout dense 18,0,0", {"CCM_Z_LAYOUT": "18,0,0"}, 11), ("layout dense, idle lanes of half-warp 1 at element 12", {"CCM_Z_LAYOUT": "18,0,12"}, 11),
-       ("layout 32,4,16 (a line per half-warp)", {"CCM_Z_LAYOUT": "32,4,16"}, 11), ("layout 32,0,12 (aligned, contiguous)", {"CCM_Z_LAYOUT": "32,0,12"}, 11),
-       ("layout 24,4,16", {"CCM_Z_LAYOUT": "24,4,16"}, 11), ("layout 20,0,12", {"CCM_Z_LAYOUT": "20,0,12"}, 11),
-       ("layout 32,4,16 + predicated padding lanes", {"CCM_Z_LAYOUT": "32,4,16"}, 13)]
+       ("entries through shared memory (u8)", {}, 15), ("baseline: the default list kernel (mode 11)", {}, 11),
+       ("grouped lists (4 blocks of a row per warp), entries by shuffle", {}, 16),
+       ("grouped lists (4 blocks of a row per warp), entries through shared memory", {}, 17)]
+# (the padded layouts of the rows of Z measured in profiles/r2/zlayout_cfg5.log were a switch of commit f23ac9d, removed afterwards)
 want = sys.argv[2:]   # optional: substrings of the variant labels to run
 for label, env, mode in [v for v in ALL if not want or any(w in v[0] for w in want)]:
     for k, v in env.items():
