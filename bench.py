@@ -256,7 +256,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="cfg5", choices=sorted(synth.CONFIGS))
-    ap.add_argument("--e2e-steps", type=int, default=5)
+    ap.add_argument("--e2e-steps", type=int, default=11)   # median of 11: a busy box disturbs 3-5 of 9 wall-clock steps (profiles/r2/e2e_overlap.log)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true", help="skip the pre-flight parity block (oracle on rank 0, about 10 s)")
     ap.add_argument("--no-extras", action="store_true", help="skip the cfg4 and front-end sub-blocks of the N=1 line")

@@ -647,20 +647,44 @@ void build(ccm_ba_handle* h, const ccm_ba_problem* p) {
   std::vector<int> g_lm_ptr, g_kf, g_lm;
   DevBuf<int> g_dkf, g_dlm, g_dptr;  // multi-rank fast path: the global (kf, landmark) lists and landmark offsets on the device
   const bool multi = h->nranks > 1;
+  // One rank, grouped input: the measurements (pixel coordinates and weights, 12 of the 20 bytes per observation) travel on a
+  // second stream while the structure of S is built from the index lists on the first; the LM stream waits for them just
+  // before their first reader (the pose observation stream).  The guard drains that stream before the caller's arrays can go away.
+  // The stream and the event live as long as the process (creating a stream per handle costs a trip through the driver's global
+  // lock: up to 130 ms when something else holds it, e.g. an nvidia-smi query); the guard drains the stream before the caller's
+  // arrays can go away.  Builds on several threads share them: a later record only makes an earlier build wait for more.
+  struct MeasCopy {
+    cudaStream_t cs = nullptr;
+    cudaEvent_t ev = nullptr;
+    bool used = false;
+    ~MeasCopy() { if (used) cudaStreamSynchronize(cs); }
+  } meas;
   bool fast = E > 0;
   if (fast) {
     DevBuf<int>& dk = multi ? g_dkf : h->o_kf;
     DevBuf<int>& dl = multi ? g_dlm : h->o_lm;
     dk.upload(p->obs_kf, E, s); dl.upload(p->obs_mp, E, s);
-    if (!multi) { h->o_uv.upload(reinterpret_cast<const float2*>(p->obs_uv), E, s); h->o_w_raw.upload(p->obs_w, E, s); }
+    if (!multi) {
+      if (env_int("CCM_MEAS_OVERLAP", 1)) {
+        copy_stream(&meas.cs, &meas.ev);
+        meas.used = true;
+      } else {
+        meas.cs = s;   // same stream: no overlap
+      }
+      h->o_uv.upload(reinterpret_cast<const float2*>(p->obs_uv), E, meas.cs); h->o_w_raw.upload(p->obs_w, E, meas.cs);
+      if (meas.used) CCM_CUDA(cudaEventRecord(meas.ev, meas.cs));
+    }
     DevBuf<int> chk; chk.alloc_zero(2, s);
-    k_check_obs<<<grid_stride(E), TPB, 0, s>>>(dk.p, dl.p, multi ? nullptr : h->o_w_raw.p, E, K, P, chk.p);
+    k_check_obs<<<grid_stride(E), TPB, 0, s>>>(dk.p, dl.p, nullptr, E, K, P, chk.p);   // indices here; the weights of the one-rank path below
     CCM_LAUNCHED();
     int hc[2];
     chk.download(hc, 2, s);
     CCM_CUDA(cudaStreamSynchronize(s));
-    CCM_REQUIRE(hc[0] == 0, "ccm_ba_create: observation index out of range or negative information weight");
-    if (hc[1] != 0) { fast = false; g_dkf.release(); g_dlm.release(); }  // not grouped by landmark: take the sorting path
+    CCM_REQUIRE(hc[0] == 0, "ccm_ba_create: observation index out of range");
+    if (hc[1] != 0) {   // not grouped by landmark: take the sorting path (which uploads the measurements in sorted order itself)
+      fast = false; g_dkf.release(); g_dlm.release();
+      if (meas.used) CCM_CUDA(cudaStreamSynchronize(meas.cs));
+    }
   }
   if (fast && !multi) {
     h->sorted_input = true;
@@ -758,11 +782,6 @@ void build(ccm_ba_handle* h, const ccm_ba_problem* p) {
   if (Pl) CCM_CUDA(cudaMemcpyAsync(h->pt0.p, p->points + 3 * (size_t)h->L0, sizeof(double) * 3 * Pl, cudaMemcpyHostToDevice, s));
   h->ptA.alloc(std::max((size_t)Pl * 3, (size_t)1)); h->ptB.alloc(std::max((size_t)Pl * 3, (size_t)1));
   h->o_w.alloc(std::max(El, 1)); h->d_flags.alloc(std::max(El, 1));
-  if (El) {
-    h->d_flags.upload(h->h_flags.data(), El, s);
-    k_apply_flags<<<div_up(El, TPB), TPB, 0, s>>>(h->o_w_raw.p, h->d_flags.p, El, h->o_w.p);
-    CCM_LAUNCHED();
-  }
 
   // ---- covisibility bitmap over ALL observations (every rank needs the global pattern of S)
   h->words = (Kf + 31) / 32;
@@ -984,6 +1003,23 @@ void build(ccm_ba_handle* h, const ccm_ba_problem* p) {
     CCM_CUDA(cudaStreamSynchronize(s));
   }
   lap("product lists");
+  // ---- measurements: wait for their copy (one-rank path), validate the weights there, apply the edge flags
+  if (El) {
+    if (fast && !multi) {
+      if (meas.used) CCM_CUDA(cudaStreamWaitEvent(s, meas.ev, 0));
+      DevBuf<int> chk; chk.alloc_zero(2, s);
+      k_check_obs<<<grid_stride(El), TPB, 0, s>>>(h->o_kf.p, h->o_lm.p, h->o_w_raw.p, El, K, std::max(P, 1), chk.p);
+      CCM_LAUNCHED();
+      int hc[2];
+      chk.download(hc, 2, s);
+      CCM_CUDA(cudaStreamSynchronize(s));
+      CCM_REQUIRE(hc[0] == 0, "ccm_ba_create: negative information weight");
+    }
+    if (p->edge_flags) h->d_flags.upload(h->h_flags.data(), El, s);
+    else CCM_CUDA(cudaMemsetAsync(h->d_flags.p, 0, (size_t)El, s));   // no flags: nothing to send
+    k_apply_flags<<<div_up(El, TPB), TPB, 0, s>>>(h->o_w_raw.p, h->d_flags.p, El, h->o_w.p);
+    CCM_LAUNCHED();
+  }
   // packed per-pose observation stream for the pose pass
   {
     std::vector<unsigned> kp((size_t)Kf + 1, 0);

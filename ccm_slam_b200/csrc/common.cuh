@@ -49,6 +49,7 @@ extern std::atomic<uint64_t> g_launches;
 // create/solve/destroy cycles (LocalBA runs once per keyframe) reuse cached memory instead of paying cudaMalloc/cudaFree
 void* dev_alloc(size_t bytes);
 void dev_free(void* p);
+void copy_stream(cudaStream_t* cs, cudaEvent_t* ev);   // process-wide copy stream and event of the current device (runtime.cu)
 
 template <typename T>
 struct DevBuf {

@@ -56,6 +56,22 @@ static cudaStream_t alloc_stream(int dev) {
   return g_alloc_stream[dev];
 }
 
+// second stream (+ its event) of the current device for host-to-device copies that overlap kernels of a handle's own stream
+static cudaStream_t g_copy_stream[64] = {nullptr};
+static cudaEvent_t g_copy_event[64] = {nullptr};
+void copy_stream(cudaStream_t* cs, cudaEvent_t* ev) {
+  int dev = 0;
+  CCM_CUDA(cudaGetDevice(&dev));
+  dev &= 63;
+  std::lock_guard<std::mutex> lk(g_alloc_mu);
+  if (!g_copy_stream[dev]) {
+    CCM_CUDA(cudaStreamCreateWithFlags(&g_copy_stream[dev], cudaStreamNonBlocking));
+    CCM_CUDA(cudaEventCreateWithFlags(&g_copy_event[dev], cudaEventDisableTiming));
+  }
+  *cs = g_copy_stream[dev];
+  *ev = g_copy_event[dev];
+}
+
 void* dev_alloc(size_t bytes) {
   int dev = 0;
   CCM_CUDA(cudaGetDevice(&dev));

@@ -87,6 +87,27 @@ def test_unsorted_observations_give_the_same_answer(oracle):
     assert np.allclose(a["chi2"][perm], b["chi2"], rtol=1e-7, atol=1e-9)
 
 
+def test_create_rejects_bad_observations():
+    """ccm_ba_create validates the caller's arrays on the device (indices with the structure, the weights where their copy joins
+    the stream) and fails loudly; grouped and ungrouped input take different paths, both must refuse."""
+    p = synth.make_config("small")
+    rng = np.random.default_rng(5)
+    for shuffle in (False, True):
+        base = p.copy()
+        if shuffle:
+            perm = rng.permutation(p.E)
+            base.obs_kf, base.obs_mp, base.obs_uv, base.obs_w = p.obs_kf[perm], p.obs_mp[perm], p.obs_uv[perm], p.obs_w[perm]
+        q = base.copy(); q.obs_w = base.obs_w.copy(); q.obs_w[p.E // 2] = -1.0
+        with pytest.raises(api.CCMError, match="negative information weight"):
+            api.BAHandle(q)
+        q = base.copy(); q.obs_kf = base.obs_kf.copy(); q.obs_kf[7] = p.K
+        with pytest.raises(api.CCMError, match="out of range"):
+            api.BAHandle(q)
+    h = api.BAHandle(p)   # and the library is still usable afterwards
+    assert h.optimize(iterations=2)["iters_done"] >= 1
+    h.close()
+
+
 def test_local_ba_two_rounds_through_the_handle_api(oracle):
     """optimize(5) -> flag chi2>5.991 or depth<=0 as level 1 and drop the kernels -> optimize(10) (S/Optimizer.cpp:536-587)."""
     p = synth.make_config("cfg2")
