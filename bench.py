@@ -392,9 +392,12 @@ def main():
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     dom = max((k for k in kernels if k != "allreduce"), key=lambda k: kernels[k]["share"])
+    binding = None
     if os.path.exists(tpath):
         with open(tpath) as f:
-            traffic = json.load(f).get(args.workload, {}).get(dom)
+            tj = json.load(f)
+        traffic = tj.get(args.workload, {}).get(dom)
+        binding = tj.get("_binding_unit", {}).get(args.workload, {}).get(dom)   # from the same ncu capture: which unit bounds the kernel
     roof = {"kernel": dom, "bound": "hbm", "achieved": kernels[dom]["achieved_gbs"], "peak": hbm_peak, "unit": "GB/s",
             "frac": kernels[dom]["frac_of_hbm_peak"], "traffic": traffic, "peak_source": peak_src,
             "share_of_step": kernels[dom]["share"],
@@ -402,6 +405,8 @@ def main():
                                     "achieved": (ab["linearize"] + info["K_free"] * 336) / ((kernels["linearize"]["avg_ms"] + kernels["pose_pass"]["avg_ms"]) * 1e-3) / 1e9,
                                     "linearize_alone_gbs": kernels["linearize"]["achieved_gbs"]}}
     roof["named_target_kernel"]["frac"] = roof["named_target_kernel"]["achieved"] / hbm_peak
+    if binding:
+        roof["binding_unit_ncu"] = binding
     cpu = None if args.no_cpu_baseline else (cpu_from_parity or cpu_baseline(args))
     extras = {}
     if world == 1 and not args.no_extras and args.workload == "cfg5":
