@@ -649,10 +649,10 @@ void build(ccm_ba_handle* h, const ccm_ba_problem* p) {
   const bool multi = h->nranks > 1;
   // One rank, grouped input: the measurements (pixel coordinates and weights, 12 of the 20 bytes per observation) travel on a
   // second stream while the structure of S is built from the index lists on the first; the LM stream waits for them just
-  // before their first reader (the pose observation stream).  The guard drains that stream before the caller's arrays can go away.
-  // The stream and the event live as long as the process (creating a stream per handle costs a trip through the driver's global
-  // lock: up to 130 ms when something else holds it, e.g. an nvidia-smi query); the guard drains the stream before the caller's
-  // arrays can go away.  Builds on several threads share them: a later record only makes an earlier build wait for more.
+  // before their first reader (the pose observation stream).  The stream and its event live as long as the process (a stream
+  // per handle was measured: creating one goes through the driver's global lock and cost up to 130 ms when something else held
+  // it); the guard drains the stream before the caller's arrays can go away.  Builds on several threads share stream and
+  // event: a later record only makes an earlier build wait for more.  CCM_MEAS_OVERLAP=0 keeps everything on the handle's stream.
   struct MeasCopy {
     cudaStream_t cs = nullptr;
     cudaEvent_t ev = nullptr;
